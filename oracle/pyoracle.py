@@ -1,0 +1,425 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes binding of oracle/_build/liboracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Field elements travel as numpy uint64 arrays of shape (n, 4): little-endian
+64-bit limbs in Montgomery form (R = 2^256), exactly the layout of the reference's
+`MontgomeryLimbs::to_limbs()` (reference src/big_num/montgomery.rs:17-22).  Affine points are
+(n, 8) uint64: x limbs then y limbs in the T256 base field, identity = all zero.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FQ, FP, FPALLAS = 0, 1, 2
+P_T256_SCALAR = 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff
+P_T256_BASE = 0xffffffff0000000100000000000000017e72b42b30e7317793135661b1c4b117
+P_PALLAS_SCALAR = 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001
+MODS = {FQ: P_T256_SCALAR, FP: P_T256_BASE, FPALLAS: P_PALLAS_SCALAR}
+R = 1 << 256
+
+
+def build(native=False):
+    """Compile the oracle (gcc).  native=True builds a -march=native copy for CPU timing."""
+    out = "_build/native/liboracle.so" if native else "_build/liboracle.so"
+    args = ["make", "-C", _HERE, "OUT=" + out]
+    if native:
+        args.append("MARCH=native")
+    subprocess.run(args, check=True, capture_output=True)
+    return os.path.join(_HERE, out)
+
+
+def lib(native=False):
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "_build", "liboracle.so")
+    if native:
+        try:
+            path = build(native=True)
+        except Exception:
+            pass
+    if not os.path.exists(path):
+        path = build()
+    L = C.CDLL(path)
+    L.orc_init()
+    L.orc_ts_new.restype = C.c_void_p
+    L.orc_shape_new.restype = C.c_void_p
+    L.orc_get_max_threads.restype = C.c_int
+    _LIB = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def fe_array(n):
+    return np.zeros((n, 4), dtype=np.uint64)
+
+
+def int_to_limbs(v):
+    return [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+
+
+def limbs_to_int(l):
+    return sum(int(l[i]) << (64 * i) for i in range(4))
+
+
+def to_mont(vals, fid=FQ):
+    """python ints (canonical) -> (n,4) Montgomery limbs"""
+    p = MODS[fid]
+    out = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        out[i] = int_to_limbs((v % p) * R % p)
+    return out
+
+
+def from_mont(arr, fid=FQ):
+    p = MODS[fid]
+    rinv = pow(R, -1, p)
+    arr = np.asarray(arr, dtype=np.uint64).reshape(-1, 4)
+    return [limbs_to_int(a) * rinv % p for a in arr]
+
+
+def f_binop(name, a, b, fid=FQ):
+    a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+    o = np.zeros_like(a)
+    getattr(lib(), name)(C.c_int(fid), _p(a), _p(b), _p(o), C.c_size_t(a.shape[0]))
+    return o
+
+
+def f_mul(a, b, fid=FQ): return f_binop("orc_f_mul", a, b, fid)
+def f_add(a, b, fid=FQ): return f_binop("orc_f_add", a, b, fid)
+def f_sub(a, b, fid=FQ): return f_binop("orc_f_sub", a, b, fid)
+
+
+def f_inv(a, fid=FQ):
+    a = np.ascontiguousarray(a, dtype=np.uint64); o = np.zeros_like(a)
+    lib().orc_f_inv(C.c_int(fid), _p(a), _p(o), C.c_size_t(a.shape[0]))
+    return o
+
+
+def f_dot_delayed(a, b, fid=FQ):
+    a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+    o = fe_array(1)
+    lib().orc_f_dot_delayed(C.c_int(fid), _p(a), _p(b), C.c_size_t(a.shape[0]), _p(o))
+    return o
+
+
+def f_reduce9(limbs9, fid=FQ):
+    a = np.ascontiguousarray(limbs9, dtype=np.uint64); o = fe_array(1)
+    lib().orc_f_reduce9(C.c_int(fid), _p(a), _p(o))
+    return o
+
+
+def f_from_uniform(b, fid=FQ):
+    buf = np.frombuffer(bytes(b), dtype=np.uint8).copy(); n = len(buf) // 64
+    o = fe_array(n)
+    lib().orc_f_from_uniform(C.c_int(fid), _p(buf), _p(o), C.c_size_t(n))
+    return o
+
+
+def f_constants(fid):
+    mod, r1, r2 = fe_array(1), fe_array(1), fe_array(1)
+    inv = C.c_uint64(); ms = C.c_int()
+    lib().orc_f_constants(C.c_int(fid), _p(mod), _p(r1), _p(r2), C.byref(inv), C.byref(ms))
+    return limbs_to_int(mod[0]), limbs_to_int(r1[0]), limbs_to_int(r2[0]), inv.value, ms.value
+
+
+def keccak256(data):
+    buf = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, dtype=np.uint8)
+    out = np.zeros(32, dtype=np.uint8)
+    lib().orc_keccak256(_p(buf), C.c_size_t(len(data)), _p(out))
+    return bytes(out)
+
+
+class Transcript:
+    def __init__(self, label):
+        self.h = C.c_void_p(lib().orc_ts_new(label))
+
+    def __del__(self):
+        try:
+            lib().orc_ts_free(self.h)
+        except Exception:
+            pass
+
+    def absorb_bytes(self, label, data):
+        buf = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, dtype=np.uint8)
+        lib().orc_ts_absorb_bytes(self.h, label, _p(buf), C.c_size_t(len(data)))
+
+    def absorb_scalars(self, label, arr, fid=FQ):
+        arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+        lib().orc_ts_absorb_scalars(self.h, C.c_int(fid), label, _p(arr), C.c_size_t(arr.shape[0]))
+
+    def absorb_commitment(self, label, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.uint64).reshape(-1, 8)
+        lib().orc_ts_absorb_commitment(self.h, label, _p(pts), C.c_size_t(pts.shape[0]))
+
+    def dom_sep(self, b):
+        lib().orc_ts_dom_sep(self.h, b)
+
+    def squeeze(self, label, fid=FQ):
+        o = fe_array(1)
+        lib().orc_ts_squeeze(self.h, C.c_int(fid), label, _p(o))
+        return o
+
+    def state(self):
+        st = np.zeros(64, dtype=np.uint8); rnd = C.c_uint16()
+        lib().orc_ts_state(self.h, _p(st), C.byref(rnd))
+        return bytes(st), rnd.value
+
+
+def eq_evals(r):
+    r = np.ascontiguousarray(r, dtype=np.uint64).reshape(-1, 4)
+    out = fe_array(1 << r.shape[0])
+    lib().orc_eq_evals(_p(r), C.c_size_t(r.shape[0]), _p(out))
+    return out
+
+
+def bind_top(Z, r):
+    Z = np.ascontiguousarray(Z, dtype=np.uint64).copy(); r = np.ascontiguousarray(r, dtype=np.uint64)
+    lib().orc_bind_top(_p(Z), C.c_size_t(Z.shape[0]), _p(r))
+    return Z[: Z.shape[0] // 2]
+
+
+def unipoly_from_evals(evals):
+    evals = np.ascontiguousarray(evals, dtype=np.uint64); n = evals.shape[0]
+    out = fe_array(n)
+    lib().orc_unipoly_from_evals(_p(evals), C.c_int(n), _p(out))
+    return out
+
+
+def unipoly_eval(coeffs, r):
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64); r = np.ascontiguousarray(r, dtype=np.uint64)
+    o = fe_array(1)
+    lib().orc_unipoly_eval(_p(coeffs), C.c_int(coeffs.shape[0]), _p(r), _p(o))
+    return o
+
+
+def sumcheck_cubic_prove(claim, taus, A, B, Cc, ts):
+    """returns (polys (l,4,4), r (l,4), claims (3,4), raw (t0,tinf) sums (l,2,4)); A,B,C are copied"""
+    taus = np.ascontiguousarray(taus, dtype=np.uint64); l = taus.shape[0]
+    A = np.ascontiguousarray(A, dtype=np.uint64).copy(); B = np.ascontiguousarray(B, dtype=np.uint64).copy()
+    Cc = np.ascontiguousarray(Cc, dtype=np.uint64).copy(); claim = np.ascontiguousarray(claim, dtype=np.uint64)
+    polys = fe_array(4 * l); r = fe_array(l); claims = fe_array(3); traw = fe_array(2 * l)
+    lib().orc_sumcheck_cubic_prove(_p(claim), _p(taus), C.c_size_t(l), _p(A), _p(B), _p(Cc), ts.h,
+                                   _p(polys), _p(r), _p(claims), _p(traw))
+    return polys.reshape(l, 4, 4), r, claims, traw.reshape(l, 2, 4)
+
+
+def sumcheck_quad_prove(claim, rounds, A, B, ts):
+    A = np.ascontiguousarray(A, dtype=np.uint64).copy(); B = np.ascontiguousarray(B, dtype=np.uint64).copy()
+    claim = np.ascontiguousarray(claim, dtype=np.uint64)
+    polys = fe_array(3 * rounds); r = fe_array(rounds); claims = fe_array(2)
+    lib().orc_sumcheck_quad_prove(_p(claim), C.c_size_t(rounds), _p(A), _p(B), ts.h, _p(polys), _p(r), _p(claims))
+    return polys.reshape(rounds, 3, 4), r, claims
+
+
+def sumcheck_verify(polys, degree, claim, ts):
+    """polys: (rounds, degree+1, 4) full coefficients; the linear slot is ignored (re-derived)."""
+    polys = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, degree + 1, 4); rounds = polys.shape[0]
+    claim = np.ascontiguousarray(claim, dtype=np.uint64)
+    e = fe_array(1); r = fe_array(rounds)
+    lib().orc_sumcheck_verify(_p(polys), C.c_size_t(rounds), C.c_int(degree), _p(claim), ts.h, _p(e), _p(r))
+    return e, r
+
+
+class Shape:
+    """SplitR1CSShape handle: padded CSR matrices (data (nnz,4) u64, indices u32, indptr u32)."""
+
+    def __init__(self, num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges, A, B, Cm):
+        self.dims = (num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges)
+        self.num_cons = num_cons; self.num_vars = num_shared + num_precommitted + num_rest
+        self.num_public = num_public; self.num_challenges = num_challenges
+        self._keep = []
+        args = [C.c_size_t(x) for x in self.dims]
+        for (d, i, p) in (A, B, Cm):
+            d = np.ascontiguousarray(d, dtype=np.uint64).reshape(-1, 4)
+            if d.shape[0] == 0:
+                d = fe_array(1)
+            i = np.ascontiguousarray(i, dtype=np.uint32) if len(i) else np.zeros(1, dtype=np.uint32)
+            p = np.ascontiguousarray(p, dtype=np.uint32)
+            self._keep += [d, i, p]
+            args += [_p(d), _p(i), _p(p)]
+        self.h = C.c_void_p(lib().orc_shape_new(*args))
+
+    def __del__(self):
+        try:
+            lib().orc_shape_free(self.h)
+        except Exception:
+            pass
+
+    def multiply_vec(self, z):
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        az, bz, cz = fe_array(self.num_cons), fe_array(self.num_cons), fe_array(self.num_cons)
+        lib().orc_shape_multiply_vec(self.h, _p(z), _p(az), _p(bz), _p(cz))
+        return az, bz, cz
+
+    def abc(self, rx, r):
+        rx = np.ascontiguousarray(rx, dtype=np.uint64); r = np.ascontiguousarray(r, dtype=np.uint64)
+        out_len = self.num_vars + 1 + self.num_public + self.num_challenges
+        out = fe_array(out_len)
+        lib().orc_shape_abc(self.h, _p(rx), _p(r), _p(out), C.c_size_t(out_len))
+        return out
+
+    def eval_tables(self, tx, ty):
+        tx = np.ascontiguousarray(tx, dtype=np.uint64); ty = np.ascontiguousarray(ty, dtype=np.uint64)
+        out = fe_array(3)
+        lib().orc_shape_eval_tables(self.h, _p(tx), _p(ty), _p(out))
+        return out
+
+
+def csr_multiply_vec(rows, data, indices, indptr, z):
+    data = np.ascontiguousarray(data, dtype=np.uint64); indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    indptr = np.ascontiguousarray(indptr, dtype=np.uint32); z = np.ascontiguousarray(z, dtype=np.uint64)
+    out = fe_array(rows)
+    lib().orc_csr_multiply_vec(C.c_size_t(rows), _p(data), _p(indices), _p(indptr), _p(z), _p(out))
+    return out
+
+
+def msm(scalars, bases):
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64); bases = np.ascontiguousarray(bases, dtype=np.uint64)
+    out = np.zeros((1, 8), dtype=np.uint64)
+    lib().orc_msm(_p(scalars), _p(bases), C.c_size_t(scalars.shape[0]), _p(out))
+    return out
+
+
+def msm_small(scalars_u64, bases):
+    s = np.ascontiguousarray(scalars_u64, dtype=np.uint64); bases = np.ascontiguousarray(bases, dtype=np.uint64)
+    out = np.zeros((1, 8), dtype=np.uint64)
+    lib().orc_msm_small(_p(s), _p(bases), C.c_size_t(s.shape[0]), _p(out))
+    return out
+
+
+def scalar_mul(base, k):
+    base = np.ascontiguousarray(base, dtype=np.uint64); k = np.ascontiguousarray(k, dtype=np.uint64)
+    out = np.zeros((1, 8), dtype=np.uint64)
+    lib().orc_scalar_mul(_p(base), _p(k), _p(out))
+    return out
+
+
+def point_add(a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+    out = np.zeros((1, 8), dtype=np.uint64)
+    lib().orc_point_add(_p(a), _p(b), _p(out))
+    return out
+
+
+def on_curve(p):
+    p = np.ascontiguousarray(p, dtype=np.uint64)
+    return bool(lib().orc_on_curve(_p(p)))
+
+
+def hyrax_commit(ck, h, v, blinds, is_small=False):
+    ck = np.ascontiguousarray(ck, dtype=np.uint64); h = np.ascontiguousarray(h, dtype=np.uint64)
+    v = np.ascontiguousarray(v, dtype=np.uint64); blinds = np.ascontiguousarray(blinds, dtype=np.uint64)
+    num_cols = ck.shape[0]; n = v.shape[0]; rows = (n + num_cols - 1) // num_cols
+    out = np.zeros((rows, 8), dtype=np.uint64)
+    lib().orc_hyrax_commit(_p(ck), C.c_size_t(num_cols), _p(h), _p(v), C.c_size_t(n), _p(blinds), C.c_int(int(is_small)), _p(out))
+    return out
+
+
+def hyrax_bind(poly, L, r_len):
+    poly = np.ascontiguousarray(poly, dtype=np.uint64); L = np.ascontiguousarray(L, dtype=np.uint64)
+    out = fe_array(r_len)
+    lib().orc_hyrax_bind(_p(poly), _p(L), C.c_size_t(L.shape[0]), C.c_size_t(r_len), _p(out))
+    return out
+
+
+class _ProofView(C.Structure):
+    _fields_ = [("num_rounds_x", C.c_uint64), ("num_rounds_y", C.c_uint64), ("num_comm_rows", C.c_uint64), ("num_cols", C.c_uint64),
+                ("comm_W", C.c_void_p), ("outer_polys", C.c_void_p), ("claims_outer", C.c_void_p), ("inner_polys", C.c_void_p),
+                ("eval_W", C.c_void_p), ("blind_eval_W", C.c_void_p), ("delta", C.c_void_p), ("beta", C.c_void_p),
+                ("z_vec", C.c_void_p), ("z_delta", C.c_void_p), ("z_beta", C.c_void_p)]
+
+
+class _KeysView(C.Structure):
+    _fields_ = [("ck", C.c_void_p), ("num_cols", C.c_size_t), ("h", C.c_void_p), ("ck_s", C.c_void_p), ("h_s", C.c_void_p)]
+
+
+class _RandView(C.Structure):
+    _fields_ = [("blinds_W", C.c_void_p), ("blind_eval_W", C.c_void_p), ("d_vec", C.c_void_p), ("r_delta", C.c_void_p), ("r_beta", C.c_void_p)]
+
+
+class Proof:
+    """Flat proof buffers (same layout the product's C ABI fills)."""
+    FIELDS = ["comm_W", "outer_polys", "claims_outer", "inner_polys", "eval_W", "blind_eval_W", "delta", "beta", "z_vec", "z_delta", "z_beta"]
+
+    def __init__(self, l, nry, rows, num_cols):
+        self.l, self.nry, self.rows, self.num_cols = l, nry, rows, num_cols
+        self.comm_W = np.zeros((rows, 8), dtype=np.uint64)
+        self.outer_polys = fe_array(3 * l); self.claims_outer = fe_array(3); self.inner_polys = fe_array(2 * nry)
+        self.eval_W = fe_array(1); self.blind_eval_W = fe_array(1)
+        self.delta = np.zeros((1, 8), dtype=np.uint64); self.beta = np.zeros((1, 8), dtype=np.uint64)
+        self.z_vec = fe_array(num_cols); self.z_delta = fe_array(1); self.z_beta = fe_array(1)
+
+    def view(self):
+        v = _ProofView(self.l, self.nry, self.rows, self.num_cols)
+        for f in self.FIELDS:
+            setattr(v, f, getattr(self, f).ctypes.data)
+        return v
+
+    def equal(self, other):
+        return all(np.array_equal(getattr(self, f), getattr(other, f)) for f in self.FIELDS)
+
+
+class Keys:
+    def __init__(self, ck, h, ck_s, h_s):
+        self.ck = np.ascontiguousarray(ck, dtype=np.uint64); self.h = np.ascontiguousarray(h, dtype=np.uint64).reshape(1, 8)
+        self.ck_s = np.ascontiguousarray(ck_s, dtype=np.uint64).reshape(1, 8); self.h_s = np.ascontiguousarray(h_s, dtype=np.uint64).reshape(1, 8)
+
+    def view(self):
+        return _KeysView(self.ck.ctypes.data, self.ck.shape[0], self.h.ctypes.data, self.ck_s.ctypes.data, self.h_s.ctypes.data)
+
+
+class Rand:
+    def __init__(self, blinds_W, blind_eval_W, d_vec, r_delta, r_beta):
+        self.a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (blinds_W, blind_eval_W, d_vec, r_delta, r_beta)]
+
+    def view(self):
+        return _RandView(*[x.ctypes.data for x in self.a])
+
+
+def spartan_prove(shape, keys, vk_digest, public_values, W, comm_pre, rand, want_debug=False):
+    L = lib()
+    num_vars = shape.num_vars; N = shape.num_cons
+    l = N.bit_length() - 1; m = num_vars.bit_length() - 1; nry = m + 1
+    num_cols = keys.ck.shape[0]; rows = num_vars // num_cols
+    P = Proof(l, nry, rows, num_cols)
+    pv = P.view(); kv = keys.view(); rv = rand.view()
+    dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
+    pub = np.ascontiguousarray(public_values, dtype=np.uint64).reshape(-1, 4)
+    if pub.shape[0] == 0:
+        pub = fe_array(1)
+    W = np.ascontiguousarray(W, dtype=np.uint64); comm_pre = np.ascontiguousarray(comm_pre, dtype=np.uint64).reshape(-1, 8)
+    dbg = fe_array(2 * l + nry)
+    phases = (C.c_double * 6)()
+    rc = L.orc_spartan_prove(shape.h, C.byref(kv), _p(dig), _p(pub), _p(W), _p(comm_pre), C.c_size_t(comm_pre.shape[0]),
+                             C.byref(rv), C.byref(pv), _p(dbg), phases)
+    if rc != 0:
+        raise RuntimeError("orc_spartan_prove failed: %d" % rc)
+    P.phase_ms = list(phases)
+    if want_debug:
+        return P, dbg
+    return P
+
+
+def spartan_verify(shape, keys, vk_digest, public_values, proof):
+    kv = keys.view(); pv = proof.view()
+    dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
+    pub = np.ascontiguousarray(public_values, dtype=np.uint64).reshape(-1, 4)
+    if pub.shape[0] == 0:
+        pub = fe_array(1)
+    return lib().orc_spartan_verify(shape.h, C.byref(kv), _p(dig), _p(pub), C.byref(pv))
+
+
+def set_threads(n):
+    lib().orc_set_threads(C.c_int(n))
+
+
+def max_threads():
+    return lib().orc_get_max_threads()

@@ -1,0 +1,106 @@
+/* spartan2_b200 — C ABI of the B200-native Spartan2 prover hot path.
+ *
+ * Drop-in boundary for microsoft/Spartan2 (reference paths are relative to the reference
+ * repository).  The reference has no FFI; these are the entry points a patched fork binds at
+ * the seams listed in SURVEY.md §8(b) / INTEGRATION.md.  Every function is `extern "C"`, takes
+ * plain pointers and sizes, returns an int32 status (0 = OK, negative = error; the text is
+ * available from sp2_last_error) and never unwinds.
+ *
+ * Data layout (identical to the reference's in-memory types, so Rust slices cross without
+ * conversion):
+ *   scalar  F : 4 x uint64 little-endian limbs, Montgomery form R = 2^256, canonical [0,p)
+ *               = `MontgomeryLimbs::to_limbs()`           (src/big_num/montgomery.rs:17-22)
+ *   point   G : 8 x uint64 = affine x limbs then y limbs in the T256 base field (Montgomery),
+ *               identity encoded as all-zero             (from `to_coordinates()`,
+ *                                                         src/provider/traits.rs:107-108,259-268)
+ *   matrices  : CSR with uint32 column indices / row pointers (src/r1cs/sparse.rs:385-394;
+ *               the classified form at :29-45 already uses u32)
+ *
+ * Host pointers unless a parameter is documented as a device handle.  Callee never retains
+ * caller pointers past return.  Engine: T256HyraxEngine (src/provider/mod.rs:76-82).
+ */
+#ifndef SPARTAN2_B200_H
+#define SPARTAN2_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP2_OK 0
+#define SP2_ERR_CUDA (-1)               /* SpartanError::InternalError{reason}                    */
+#define SP2_ERR_INVALID_INPUT_LENGTH (-2) /* SpartanError::InvalidInputLength{reason}             */
+#define SP2_ERR_INVALID_WITNESS_LENGTH (-3) /* SpartanError::InvalidWitnessLength                 */
+#define SP2_ERR_INVALID_CK_LENGTH (-4)  /* SpartanError::InvalidCommitmentKeyLength               */
+#define SP2_ERR_DIVISION_BY_ZERO (-5)   /* SpartanError::DivisionByZero                           */
+#define SP2_ERR_INTERNAL (-6)           /* SpartanError::InternalError                            */
+#define SP2_ERR_UNSUPPORTED (-7)        /* path not offloaded: caller must use its CPU path       */
+
+typedef struct sp2_ctx sp2_ctx;         /* one per (process, GPU)                                 */
+typedef struct sp2_ck sp2_ck;           /* device-resident commitment key                         */
+typedef struct sp2_shape sp2_shape;     /* device-resident SplitR1CSShape                         */
+typedef struct sp2_prep sp2_prep;       /* device-resident SpartanPrepSNARK                       */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int32_t sp2_ctx_create(int32_t device, sp2_ctx **out);
+void sp2_ctx_destroy(sp2_ctx *ctx);
+const char *sp2_last_error(const sp2_ctx *ctx);
+uint64_t sp2_launch_count(const sp2_ctx *ctx);      /* kernels launched so far through ctx        */
+int32_t sp2_synchronize(sp2_ctx *ctx);
+
+/* ---- sum-check (src/sumcheck.rs) ------------------------------------------------------------ */
+/* Transcript hand-off: the Keccak256Transcript (src/provider/keccak.rs:26-31) right after a
+ * squeeze is fully described by (round, state[64]); the whole-loop provers take that pair,
+ * run every round's absorb(b"p")/squeeze(b"c") on the device and hand the pair back.           */
+typedef struct { uint16_t round; uint8_t state[64]; } sp2_transcript_state;
+
+/* Replaces SumcheckProof::prove_cubic_with_three_inputs (src/sumcheck.rs:502-571):
+ * claim, taus[l]; tables A,B,C of 2^l scalars (consumed: contents undefined after the call).
+ * Outputs: polys[l*4] full coefficients (low->high; the proof keeps [0],[2],[3]), r[l], claims[3].
+ * SP2_ERR_UNSUPPORTED when tau_i * prod eq = 0 (the reference's fallback, :1327-1396).          */
+int32_t sp2_sumcheck_cubic_prove(sp2_ctx *ctx, const uint64_t *claim, const uint64_t *taus, uint32_t l,
+                                 const uint64_t *A, const uint64_t *B, const uint64_t *C,
+                                 sp2_transcript_state *ts, uint64_t *polys, uint64_t *r, uint64_t *claims);
+
+/* Replaces SumcheckProof::prove_quad (src/sumcheck.rs:190-247): tables of 2^rounds scalars.
+ * Outputs: polys[rounds*3], r[rounds], claims[2].                                               */
+int32_t sp2_sumcheck_quad_prove(sp2_ctx *ctx, const uint64_t *claim, uint32_t rounds,
+                                const uint64_t *A, const uint64_t *B,
+                                sp2_transcript_state *ts, uint64_t *polys, uint64_t *r, uint64_t *claims);
+
+/* Device-resident variants (tables already in HBM; used by the fused prover and by bench.py's
+ * kernel-only timing).  dA/dB/dC are device pointers to 2^l scalars, bound in place.           */
+int32_t sp2_sumcheck_cubic_prove_dev(sp2_ctx *ctx, const uint64_t *claim, const uint64_t *taus, uint32_t l,
+                                     void *dA, void *dB, void *dC,
+                                     sp2_transcript_state *ts, uint64_t *polys, uint64_t *r, uint64_t *claims);
+int32_t sp2_sumcheck_quad_prove_dev(sp2_ctx *ctx, const uint64_t *claim, uint32_t rounds, void *dA, void *dB,
+                                    sp2_transcript_state *ts, uint64_t *polys, uint64_t *r, uint64_t *claims);
+
+/* ---- polynomials (src/polys) ---------------------------------------------------------------- */
+/* EqPolynomial::evals_from_points (src/polys/eq.rs:59-117): out[2^k], MSB-first.               */
+int32_t sp2_eq_table(sp2_ctx *ctx, const uint64_t *r, uint32_t k, uint64_t *out);
+/* MultilinearPolynomial::bind_poly_var_top (src/polys/multilinear.rs:95-164): Z[len] -> out[len/2] */
+int32_t sp2_bind_top(sp2_ctx *ctx, const uint64_t *Z, uint64_t len, const uint64_t *r, uint64_t *out);
+
+/* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
+int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
+int32_t sp2_dev_free(sp2_ctx *ctx, void *p);
+int32_t sp2_dev_upload(sp2_ctx *ctx, void *dst, const void *src, uint64_t bytes);
+int32_t sp2_dev_download(sp2_ctx *ctx, void *dst, const void *src, uint64_t bytes);
+int32_t sp2_dev_copy(sp2_ctx *ctx, void *dst, const void *src, uint64_t bytes);
+
+/* ---- test hooks: the device field layer, element-wise (tests/test_gpu_field.py) ------------- */
+/* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont; field: 0 = T256 scalar, 1 = T256 base */
+int32_t sp2_test_field_op(sp2_ctx *ctx, int32_t field, int32_t op, const uint64_t *a, const uint64_t *b,
+                          uint64_t *out, uint64_t n);
+/* sum_i a_i*b_i through the 544-bit delayed-reduction accumulator (big_num/delayed_reduction.rs) */
+int32_t sp2_test_dot_delayed(sp2_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t n, uint64_t *out);
+/* Keccak256Transcript on the device: absorb `data` under `label`, squeeze under `sq_label`.     */
+int32_t sp2_test_transcript(sp2_ctx *ctx, sp2_transcript_state *ts, const uint8_t *pending, uint32_t pending_len,
+                            const char *sq_label, uint64_t *challenge_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

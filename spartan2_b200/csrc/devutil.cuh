@@ -1,0 +1,68 @@
+// Device utilities: 256-bit global loads/stores, warp/block reductions of field elements.
+#pragma once
+#include <cuda_runtime.h>
+#include "field.cuh"
+
+namespace sp2 {
+
+// One field element per 256-bit transaction (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a):
+// a warp moves 1 KiB contiguous per request.
+__device__ __forceinline__ fe ldg_fe(const fe *p) {
+  fe r; u64 a, b, c, d;
+  asm volatile("ld.global.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  r.v[0] = (u32)a; r.v[1] = (u32)(a >> 32); r.v[2] = (u32)b; r.v[3] = (u32)(b >> 32);
+  r.v[4] = (u32)c; r.v[5] = (u32)(c >> 32); r.v[6] = (u32)d; r.v[7] = (u32)(d >> 32);
+  return r;
+}
+// read-only data reused across threads/CTAs (eq tables, z vector): keep it cacheable
+__device__ __forceinline__ fe ldg_fe_ro(const fe *p) {
+  fe r; u64 a, b, c, d;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  r.v[0] = (u32)a; r.v[1] = (u32)(a >> 32); r.v[2] = (u32)b; r.v[3] = (u32)(b >> 32);
+  r.v[4] = (u32)c; r.v[5] = (u32)(c >> 32); r.v[6] = (u32)d; r.v[7] = (u32)(d >> 32);
+  return r;
+}
+__device__ __forceinline__ void stg_fe(fe *p, const fe &x) {
+  u64 a = (u64)x.v[0] | ((u64)x.v[1] << 32), b = (u64)x.v[2] | ((u64)x.v[3] << 32);
+  u64 c = (u64)x.v[4] | ((u64)x.v[5] << 32), d = (u64)x.v[6] | ((u64)x.v[7] << 32);
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+__device__ __forceinline__ fe shfl_xor_fe(const fe &x, int m) {
+  fe r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, x.v[i], m);
+  return r;
+}
+// sum over the warp (modular adds); result valid in every lane
+__device__ __forceinline__ fe warp_sum_fq(fe x) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) x = Fq::add(x, shfl_xor_fe(x, m));
+  return x;
+}
+// sum of NV field elements per thread over the block; result in thread 0.  smem: NV * 32 fe.
+template <int NV>
+__device__ __forceinline__ void block_sum_fq(fe (&x)[NV], fe *smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    x[k] = warp_sum_fq(x[k]);
+    if (lane == 0) smem[k * 32 + warp] = x[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      fe v = lane < nw ? smem[k * 32 + lane] : Fq::zero();
+      x[k] = warp_sum_fq(v);
+    }
+  }
+}
+
+#define SP2_CUDA_OK(call)                                                     \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) return sp2::set_cuda_error(ctx, e_, #call, __LINE__); \
+  } while (0)
+
+}  // namespace sp2

@@ -1,0 +1,304 @@
+// 256-bit prime-field arithmetic for sm_100a: 8 x u32 limbs in registers, Montgomery form with
+// R = 2^256, canonical [0,p) results — bit-compatible with the reference's field elements
+// (4 x u64 little-endian Montgomery limbs, reference src/big_num/montgomery.rs:14-22,
+// src/big_num/macros.rs:59-73), so tables cross the C ABI without conversion.
+//
+//   Fq = T256 scalar field = NIST P-256 base prime p = 2^256 - 2^224 + 2^192 + 2^96 - 1.
+//        -p^-1 mod 2^32 = 1, so the Montgomery quotient digit is the limb itself and m*p is
+//        shifts/adds only: REDC costs no multiplications.  (SURVEY.md Appendix A.)
+//   Fp = T256 base field (curve coordinates for the MSM), generic modulus: CIOS.
+//
+// Restates the arithmetic of reference src/big_num/limbs.rs:178-349 (wide multiply-accumulate),
+// src/big_num/montgomery.rs:39-177 (REDC) and halo2curves' field ops on 32-bit integer pipes.
+// Single source for host (unit tests) and device (see prim.cuh).
+#pragma once
+#include "prim.cuh"
+#include "consts.cuh"
+
+namespace sp2 {
+
+struct alignas(32) fe { u32 v[8]; };     // one field element: 32 bytes, 256-bit loads/stores
+
+// ------------------------------------------------------------------------------------------
+// 256 x 256 -> 512 bit product.  Even/odd column accumulators so every a_j*b_i is one
+// IMAD.WIDE with carry (mad.lo.cc + madc.hi.cc pair).
+// ------------------------------------------------------------------------------------------
+template <int LEN>
+SP2_HD void mad_row4(u32 (&acc)[LEN], const int k, u32 x0, u32 x1, u32 x2, u32 x3, u32 b) {
+  acc[k + 0] = mad_lo_cc(x0, b, acc[k + 0]);
+  acc[k + 1] = madc_hi_cc(x0, b, acc[k + 1]);
+  acc[k + 2] = madc_lo_cc(x1, b, acc[k + 2]);
+  acc[k + 3] = madc_hi_cc(x1, b, acc[k + 3]);
+  acc[k + 4] = madc_lo_cc(x2, b, acc[k + 4]);
+  acc[k + 5] = madc_hi_cc(x2, b, acc[k + 5]);
+  acc[k + 6] = madc_lo_cc(x3, b, acc[k + 6]);
+  acc[k + 7] = madc_hi_cc(x3, b, acc[k + 7]);
+  if (k + 8 < LEN) acc[k + 8] = addc(acc[k + 8], 0);
+}
+
+SP2_HD void mul_wide(u32 (&r)[16], const fe &a, const fe &b) {
+  u32 E[16], O[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    // even i: a_even*b_i -> even columns (E at i), a_odd*b_i -> odd columns (O index i)
+    mad_row4<16>(E, i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+    mad_row4<16>(O, i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+    // odd i+1: a_even*b -> odd columns (O index i), a_odd*b -> even columns (E at i+2)
+    mad_row4<16>(O, i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i + 1]);
+    mad_row4<16>(E, i + 2, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i + 1]);
+  }
+  r[0] = E[0];
+  r[1] = add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) r[k] = addc_cc(E[k], O[k - 1]);
+  r[15] = addc(E[15], O[14]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic helpers parameterised by the modulus
+// ------------------------------------------------------------------------------------------
+template <class PR>
+SP2_HD void cond_sub_p(fe &x, u32 top) {     // x (+ top*2^256) in [0, 2p)  ->  [0, p)
+  u32 d[8];
+  d[0] = sub_cc(x.v[0], PR::P(0));
+#pragma unroll
+  for (int i = 1; i < 8; i++) d[i] = subc_cc(x.v[i], PR::P(i));
+  u32 b = subc(top, 0);                      // 0xffffffff iff x + top*2^256 < p
+  if (b != 0xffffffffu) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) x.v[i] = d[i];
+  }
+}
+
+template <class PR>
+struct Field {
+  SP2_HD static fe zero() { fe r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+  SP2_HD static fe one() { fe r; for (int i = 0; i < 8; i++) r.v[i] = PR::ONE(i); return r; }
+  SP2_HD static fe cst_r2() { fe r; for (int i = 0; i < 8; i++) r.v[i] = PR::R2(i); return r; }
+  SP2_HD static fe cst_r3() { fe r; for (int i = 0; i < 8; i++) r.v[i] = PR::R3(i); return r; }
+  SP2_HD static fe two_inv() { fe r; for (int i = 0; i < 8; i++) r.v[i] = PR::TWO_INV(i); return r; }
+  SP2_HD static fe six_inv() { fe r; for (int i = 0; i < 8; i++) r.v[i] = PR::SIX_INV(i); return r; }
+  SP2_HD static bool is_zero(const fe &a) { u32 o = 0; for (int i = 0; i < 8; i++) o |= a.v[i]; return o == 0; }
+  SP2_HD static bool eq(const fe &a, const fe &b) { u32 o = 0; for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i]; return o == 0; }
+
+  SP2_HD static fe add(const fe &a, const fe &b) {
+    fe r;
+    r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+    u32 top = addc(0, 0);
+    cond_sub_p<PR>(r, top);
+    return r;
+  }
+  SP2_HD static fe sub(const fe &a, const fe &b) {
+    fe r;
+    r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+    u32 m = subc(0, 0);                      // 0xffffffff iff borrow
+    r.v[0] = add_cc(r.v[0], PR::P(0) & m);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = addc_cc(r.v[i], PR::P(i) & m);
+    r.v[7] = addc(r.v[7], PR::P(7) & m);
+    return r;
+  }
+  SP2_HD static fe dbl(const fe &a) { return add(a, a); }
+  SP2_HD static fe neg(const fe &a) { return sub(zero(), a); }
+  // a/2 : (a + (a odd ? p : 0)) >> 1
+  SP2_HD static fe half(const fe &a) {
+    u32 m = 0u - (a.v[0] & 1u);
+    u32 t[9];
+    t[0] = add_cc(a.v[0], PR::P(0) & m);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = addc_cc(a.v[i], PR::P(i) & m);
+    t[8] = addc(0, 0);
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    return r;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Fq: P-256 prime, multiplication-free REDC
+// ------------------------------------------------------------------------------------------
+struct Fq : Field<FqParams> {
+  // Four 64-bit Montgomery rounds on t[0..NT-1] (NT >= 17; limbs above 15 absorb carries).
+  // After the call t[0..7] are (logically) zero and the value/2^256 sits in t[8..NT-1].
+  template <int NT>
+  SP2_HD static void redc_rounds(u32 (&t)[NT]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i = 2 * k;
+      const u32 m0 = t[i], m1 = t[i + 1];
+      // + m*2^96 + m*2^192 + m*2^256
+      t[i + 3] = add_cc(t[i + 3], m0);
+      t[i + 4] = addc_cc(t[i + 4], m1);
+      t[i + 5] = addc_cc(t[i + 5], 0);
+      t[i + 6] = addc_cc(t[i + 6], m0);
+      t[i + 7] = addc_cc(t[i + 7], m1);
+      t[i + 8] = addc_cc(t[i + 8], m0);
+      t[i + 9] = addc_cc(t[i + 9], m1);
+#pragma unroll
+      for (int j = i + 10; j < NT - 1; j++) t[j] = addc_cc(t[j], 0);
+      t[NT - 1] = addc(t[NT - 1], 0);
+      // - m*2^224   (the "- m" term cancels t[i], t[i+1])
+      t[i + 7] = sub_cc(t[i + 7], m0);
+      t[i + 8] = subc_cc(t[i + 8], m1);
+#pragma unroll
+      for (int j = i + 9; j < NT - 1; j++) t[j] = subc_cc(t[j], 0);
+      t[NT - 1] = subc(t[NT - 1], 0);
+    }
+  }
+  // t (16 limbs, < p*2^256)  ->  t / 2^256 mod p, canonical
+  SP2_HD static fe redc16(const u32 (&w)[16]) {
+    u32 t[17];
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[i] = w[i];
+    t[16] = 0;
+    redc_rounds<17>(t);
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[8 + i];
+    cond_sub_p<FqParams>(r, t[16]);
+    return r;
+  }
+  SP2_HD static fe mul(const fe &a, const fe &b) { u32 w[16]; mul_wide(w, a, b); return redc16(w); }
+  SP2_HD static fe sqr(const fe &a) { return mul(a, a); }
+
+  // x + hi*2^256 (hi < 2^32)  ==  x + hi*(2^224 - 2^192 - 2^96 + 1)  (mod p); returns the new top limb
+  SP2_HD static u32 fold_top(fe &x, u32 hi) {
+    u32 t[9];
+    t[0] = add_cc(x.v[0], hi);
+#pragma unroll
+    for (int i = 1; i < 7; i++) t[i] = addc_cc(x.v[i], 0);
+    t[7] = addc_cc(x.v[7], hi);
+    t[8] = addc(0, 0);
+    t[3] = sub_cc(t[3], hi);
+    t[4] = subc_cc(t[4], 0);
+    t[5] = subc_cc(t[5], 0);
+    t[6] = subc_cc(t[6], hi);
+    t[7] = subc_cc(t[7], 0);
+    t[8] = subc(t[8], 0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) x.v[i] = t[i];
+    return t[8];
+  }
+
+  // ---- delayed reduction: 544-bit accumulator (WideLimbs<9> analogue, limbs.rs:69-89) ----
+  struct acc { u32 v[17]; };
+  SP2_HD static acc acc_zero() { acc a; for (int i = 0; i < 17; i++) a.v[i] = 0; return a; }
+  // a += x*y  (unreduced_multiply_accumulate, delayed_reduction.rs:52-58); up to 2^32 products
+  SP2_HD static void mul_acc(acc &a, const fe &x, const fe &y) {
+    u32 w[16];
+    mul_wide(w, x, y);
+    a.v[0] = add_cc(a.v[0], w[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) a.v[i] = addc_cc(a.v[i], w[i]);
+    a.v[16] = addc(a.v[16], 0);
+  }
+  SP2_HD static void acc_add(acc &a, const acc &b) {
+    a.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) a.v[i] = addc_cc(a.v[i], b.v[i]);
+    a.v[16] = addc(a.v[16], b.v[16]);
+  }
+  // reduce (montgomery_reduce_9 analogue, montgomery.rs:39-109): acc / 2^256 mod p, canonical
+  SP2_HD static fe acc_reduce(const acc &a) {
+    u32 t[18];
+#pragma unroll
+    for (int i = 0; i < 17; i++) t[i] = a.v[i];
+    t[17] = 0;
+    redc_rounds<18>(t);                       // value/2^256 < 2^288 + p : limbs t[8..17]
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[8 + i];
+    // t[17] can only be 0 here (value < 2^289); fold the 9th limb (and the rare re-carries)
+    u32 top = fold_top(r, t[16]);
+    top = fold_top(r, top);
+    top = fold_top(r, top);
+    cond_sub_p<FqParams>(r, top);
+    cond_sub_p<FqParams>(r, 0);
+    return r;
+  }
+  // canonical integer <-> Montgomery
+  SP2_HD static fe to_mont(const fe &raw) { return mul(raw, cst_r2()); }
+  SP2_HD static fe from_mont(const fe &a) {
+    u32 w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w[i] = a.v[i]; w[8 + i] = 0; }
+    return redc16(w);
+  }
+  // halo2curves from_uniform_bytes: 512-bit little-endian integer mod p (lo, hi: raw 256-bit halves)
+  SP2_HD static fe from_uniform(const fe &lo, const fe &hi) { return add(mul(lo, cst_r2()), mul(hi, cst_r3())); }
+  SP2_HD static fe inv(const fe &a) {         // Fermat, a^(p-2); inv(0) = 0
+    fe r = one();
+    for (int i = 255; i >= 0; i--) {
+      r = sqr(r);
+      u32 e = FqParams::P(i >> 5);
+      if ((i >> 5) == 0) e -= 2;              // p - 2 (p's low limb is 0xffffffff: no borrow)
+      if ((e >> (i & 31)) & 1) r = mul(r, a);
+    }
+    return r;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Fp: generic modulus (T256 base field), CIOS Montgomery multiplication
+// ------------------------------------------------------------------------------------------
+struct Fp : Field<FpParams> {
+  SP2_HD static fe mul(const fe &a, const fe &b) {
+    u32 t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const u32 bi = b.v[i];
+      t[0] = mad_lo_cc(a.v[0], bi, t[0]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) t[j] = madc_lo_cc(a.v[j], bi, t[j]);
+      t[8] = addc_cc(t[8], 0);
+      t[9] = addc(t[9], 0);
+      t[1] = mad_hi_cc(a.v[0], bi, t[1]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) t[j + 1] = madc_hi_cc(a.v[j], bi, t[j + 1]);
+      t[9] = addc(t[9], 0);
+      const u32 m = mul_lo(t[0], FpParams::INV32);
+      t[0] = mad_lo_cc(m, FpParams::P(0), t[0]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) t[j] = madc_lo_cc(m, FpParams::P(j), t[j]);
+      t[8] = addc_cc(t[8], 0);
+      t[9] = addc(t[9], 0);
+      t[1] = mad_hi_cc(m, FpParams::P(0), t[1]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) t[j + 1] = madc_hi_cc(m, FpParams::P(j), t[j + 1]);
+      t[9] = addc(t[9], 0);
+#pragma unroll
+      for (int j = 0; j < 9; j++) t[j] = t[j + 1];
+      t[9] = 0;
+    }
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+    cond_sub_p<FpParams>(r, t[8]);
+    return r;
+  }
+  SP2_HD static fe sqr(const fe &a) { return mul(a, a); }
+  SP2_HD static fe to_mont(const fe &raw) { return mul(raw, cst_r2()); }
+  SP2_HD static fe from_mont(const fe &a) { fe o; for (int i = 0; i < 8; i++) o.v[i] = i == 0 ? 1u : 0u; return mul(a, o); }
+  SP2_HD static fe inv(const fe &a) {
+    fe r = one();
+    // p - 2: low limb 0xb1c4b117 - 2, no borrow
+    for (int i = 255; i >= 0; i--) {
+      r = sqr(r);
+      u32 e = FpParams::P(i >> 5);
+      if ((i >> 5) == 0) e -= 2;
+      if ((e >> (i & 31)) & 1) r = mul(r, a);
+    }
+    return r;
+  }
+};
+
+}  // namespace sp2

@@ -48,6 +48,12 @@ void sp2_ctx_destroy(sp2_ctx *ctx);
 const char *sp2_last_error(const sp2_ctx *ctx);
 uint64_t sp2_launch_count(const sp2_ctx *ctx);      /* kernels launched so far through ctx        */
 int32_t sp2_synchronize(sp2_ctx *ctx);
+int32_t sp2_num_sms(const sp2_ctx *ctx);
+/* Launch on a caller-owned CUDA stream (cudaStream_t) instead of the context's own.             */
+int32_t sp2_ctx_set_stream(sp2_ctx *ctx, void *cuda_stream);
+/* CUDA-event stopwatch on the context's stream (device time between the two calls).             */
+int32_t sp2_timer_start(sp2_ctx *ctx);
+int32_t sp2_timer_stop(sp2_ctx *ctx, float *ms);
 
 /* ---- sum-check (src/sumcheck.rs) ------------------------------------------------------------ */
 /* Transcript hand-off: the Keccak256Transcript (src/provider/keccak.rs:26-31) right after a
@@ -82,6 +88,9 @@ int32_t sp2_sumcheck_quad_prove_dev(sp2_ctx *ctx, const uint64_t *claim, uint32_
 int32_t sp2_eq_table(sp2_ctx *ctx, const uint64_t *r, uint32_t k, uint64_t *out);
 /* MultilinearPolynomial::bind_poly_var_top (src/polys/multilinear.rs:95-164): Z[len] -> out[len/2] */
 int32_t sp2_bind_top(sp2_ctx *ctx, const uint64_t *Z, uint64_t len, const uint64_t *r, uint64_t *out);
+/* device-resident variants (d_* are device pointers; asynchronous on the context's stream)      */
+int32_t sp2_eq_table_dev(sp2_ctx *ctx, const void *d_r, uint32_t k, void *d_out);
+int32_t sp2_bind_top_dev(sp2_ctx *ctx, const void *d_Z, uint64_t len, const void *d_r, void *d_out);
 
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
@@ -89,9 +98,13 @@ int32_t sp2_dev_free(sp2_ctx *ctx, void *p);
 int32_t sp2_dev_upload(sp2_ctx *ctx, void *dst, const void *src, uint64_t bytes);
 int32_t sp2_dev_download(sp2_ctx *ctx, void *dst, const void *src, uint64_t bytes);
 int32_t sp2_dev_copy(sp2_ctx *ctx, void *dst, const void *src, uint64_t bytes);
+int32_t sp2_dev_memset(sp2_ctx *ctx, void *dst, int32_t value, uint64_t bytes);
+/* page-locked host buffers (so uploads/downloads through this ABI are true async DMA)           */
+int32_t sp2_host_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
+int32_t sp2_host_free(sp2_ctx *ctx, void *p);
 
 /* ---- test hooks: the device field layer, element-wise (tests/test_gpu_field.py) ------------- */
-/* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont; field: 0 = T256 scalar, 1 = T256 base */
+/* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont, 6 half; field: 0 = T256 scalar, 1 = T256 base */
 int32_t sp2_test_field_op(sp2_ctx *ctx, int32_t field, int32_t op, const uint64_t *a, const uint64_t *b,
                           uint64_t *out, uint64_t n);
 /* sum_i a_i*b_i through the 544-bit delayed-reduction accumulator (big_num/delayed_reduction.rs) */

@@ -1,6 +1,6 @@
-// Library context: one per (process, GPU).  Owns the stream, a bump-free set of scratch
-// allocations and the last error string (errors are values, never C++ exceptions across the ABI;
-// mirrors the reference's SpartanError, src/errors.rs:12-110).
+// Library context: one per (process, GPU).  Owns the stream, cached scratch allocations and the
+// last error string (errors are values, never C++ exceptions across the ABI; mirrors the
+// reference's SpartanError, src/errors.rs:12-110).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -11,13 +11,19 @@
 
 struct sp2_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;        // all kernels of this context are launched here
+  bool own_stream = false;
   cudaStream_t side = nullptr;          // side stream for independent prologue work
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_side = nullptr;
   int num_sms = 148;
   std::string err;
   uint64_t launches = 0;                // kernels launched through this context (bench's gpu_launches)
-  std::vector<void *> owned;            // device allocations freed at destroy
+  // scratch slots: grown on demand, reused across calls (cudaMalloc/cudaFree are synchronising)
+  static const int NSLOT = 16;
+  void *slot[NSLOT] = {nullptr};
+  size_t slot_bytes[NSLOT] = {0};
+  void *pinned = nullptr;               // small pinned staging buffer for result read-back
+  size_t pinned_bytes = 0;
 };
 
 namespace sp2 {
@@ -30,12 +36,33 @@ inline int set_cuda_error(sp2_ctx *ctx, cudaError_t e, const char *what, int lin
   snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s [line %d]", (int)e, cudaGetErrorString(e), what, line);
   return set_error(ctx, SP2_ERR_CUDA, buf);
 }
-template <class T>
-inline int dev_alloc(sp2_ctx *ctx, T **p, size_t n) {
-  cudaError_t e = cudaMalloc((void **)p, n * sizeof(T) + 32);
-  if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaMalloc", __LINE__);
+#define SP2_TRY(expr) do { int rc_ = (expr); if (rc_ != SP2_OK) return rc_; } while (0)
+#define SP2_CUDA_OK(call)                                                     \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) return sp2::set_cuda_error(ctx, e_, #call, __LINE__); \
+  } while (0)
+#define SP2_LAUNCH_CHECK() do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return sp2::set_cuda_error(ctx, e_, "kernel launch", __LINE__); } while (0)
+
+// scratch slot `i` of at least `bytes` bytes (contents undefined)
+inline int scratch(sp2_ctx *ctx, int i, size_t bytes, void **out) {
+  if (ctx->slot_bytes[i] < bytes) {
+    if (ctx->slot[i]) { SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); SP2_CUDA_OK(cudaFree(ctx->slot[i])); ctx->slot[i] = nullptr; ctx->slot_bytes[i] = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    SP2_CUDA_OK(cudaMalloc(&ctx->slot[i], want));
+    ctx->slot_bytes[i] = want;
+  }
+  *out = ctx->slot[i];
   return SP2_OK;
 }
-#define SP2_TRY(expr) do { int rc_ = (expr); if (rc_ != SP2_OK) return rc_; } while (0)
-#define SP2_LAUNCH_CHECK() do { ctx->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return sp2::set_cuda_error(ctx, e_, "kernel launch", __LINE__); } while (0)
+inline int pinned(sp2_ctx *ctx, size_t bytes, void **out) {
+  if (ctx->pinned_bytes < bytes) {
+    if (ctx->pinned) { SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); SP2_CUDA_OK(cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    size_t want = bytes * 2 + 4096;
+    SP2_CUDA_OK(cudaMallocHost(&ctx->pinned, want));
+    ctx->pinned_bytes = want;
+  }
+  *out = ctx->pinned;
+  return SP2_OK;
+}
 }  // namespace sp2

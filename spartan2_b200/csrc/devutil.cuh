@@ -59,10 +59,4 @@ __device__ __forceinline__ void block_sum_fq(fe (&x)[NV], fe *smem) {
   }
 }
 
-#define SP2_CUDA_OK(call)                                                     \
-  do {                                                                        \
-    cudaError_t e_ = (call);                                                  \
-    if (e_ != cudaSuccess) return sp2::set_cuda_error(ctx, e_, #call, __LINE__); \
-  } while (0)
-
 }  // namespace sp2

@@ -20,7 +20,7 @@ struct DevTranscript {          // lives in global memory
 static_assert(sizeof(DevTranscript) == 2048, "DevTranscript layout");
 
 #if defined(__CUDACC__)
-__device__ __constant__ u64 KECCAK_RC_D[24] = {
+static __device__ __constant__ u64 KECCAK_RC_D[24] = {
     0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
     0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
     0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,

@@ -1,0 +1,174 @@
+"""Host-side mirror of the reference interface over the C ABI (see package docstring)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import OK, SpartanError, TranscriptState, lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _fe(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, 4)
+
+
+class Context:
+    """One per (process, GPU): sp2_ctx."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.sp2_ctx_create(C.c_int32(device), C.byref(h))
+        if rc != OK:
+            raise SpartanError(rc, "sp2_ctx_create failed: no usable sm_100 CUDA device %d (no CPU fallback)" % device)
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self.check(self.L.sp2_ctx_set_stream(self.h, C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sp2_ctx_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != OK:
+            raise SpartanError(rc, (self.L.sp2_last_error(self.h) or b"").decode())
+
+    def launch_count(self):
+        return int(self.L.sp2_launch_count(self.h))
+
+    def num_sms(self):
+        return int(self.L.sp2_num_sms(self.h))
+
+    def synchronize(self):
+        self.check(self.L.sp2_synchronize(self.h))
+
+    def timer_start(self):
+        self.check(self.L.sp2_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self.check(self.L.sp2_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    # -- raw memory ---------------------------------------------------------------------------
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        buf = DeviceBuffer(self, arr.nbytes)
+        buf.upload(arr)
+        return buf
+
+    def pinned_empty(self, shape, dtype=np.uint64):
+        """numpy array backed by page-locked host memory (sp2_host_alloc)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self.check(self.L.sp2_host_alloc(self.h, C.c_uint64(max(n, 32)), C.byref(p)))
+        raw = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pins = getattr(self, "_pins", []); self._pins.append(p)
+        return arr
+
+
+class DeviceBuffer:
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx; self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        ctx.check(ctx.L.sp2_dev_alloc(ctx.h, C.c_uint64(self.nbytes), C.byref(p)))
+        self.ptr = p
+
+    def upload(self, arr, offset=0):
+        arr = np.ascontiguousarray(arr)
+        assert offset + arr.nbytes <= self.nbytes
+        self.ctx.check(self.ctx.L.sp2_dev_upload(self.ctx.h, C.c_void_p(self.ptr.value + offset), _p(arr), C.c_uint64(arr.nbytes)))
+
+    def download(self, shape, dtype=np.uint64, offset=0):
+        out = np.zeros(shape, dtype=dtype)
+        assert offset + out.nbytes <= self.nbytes
+        self.ctx.check(self.ctx.L.sp2_dev_download(self.ctx.h, _p(out), C.c_void_p(self.ptr.value + offset), C.c_uint64(out.nbytes)))
+        return out
+
+    def copy_from(self, other, nbytes=None):
+        self.ctx.check(self.ctx.L.sp2_dev_copy(self.ctx.h, self.ptr, other.ptr, C.c_uint64(nbytes or other.nbytes)))
+
+    def free(self):
+        if self.ptr:
+            self.ctx.L.sp2_dev_free(self.ctx.h, self.ptr); self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class EqPolynomial:
+    """src/polys/eq.rs"""
+
+    @staticmethod
+    def evals_from_points(ctx, r):
+        r = _fe(r); k = r.shape[0]
+        out = np.zeros((1 << k, 4), dtype=np.uint64)
+        rr = r if k else np.zeros((1, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_eq_table(ctx.h, _p(rr), C.c_uint32(k), _p(out)))
+        return out
+
+
+class MultilinearPolynomial:
+    """src/polys/multilinear.rs"""
+
+    @staticmethod
+    def bind_poly_var_top(ctx, Z, r):
+        Z = _fe(Z); r = _fe(r)
+        out = np.zeros((Z.shape[0] // 2, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_bind_top(ctx.h, _p(Z), C.c_uint64(Z.shape[0]), _p(r), _p(out)))
+        return out
+
+
+class SumcheckProof:
+    """src/sumcheck.rs — whole-loop provers.  `ts` is a TranscriptState (round, state) hand-off; it is
+    advanced in place exactly as the reference's transcript would be by the l absorb/squeeze pairs."""
+
+    @staticmethod
+    def prove_cubic_with_three_inputs(ctx, claim, taus, A, B, Cz, ts):
+        """returns (polys (l,4,4) full coefficients low->high, r (l,4), claims (3,4)); A, B, C host arrays
+        or DeviceBuffers (bound in place on the device)."""
+        taus = _fe(taus); l = taus.shape[0]; claim = _fe(claim)
+        polys = np.zeros((l, 4, 4), dtype=np.uint64); r = np.zeros((l, 4), dtype=np.uint64); claims = np.zeros((3, 4), dtype=np.uint64)
+        if isinstance(A, DeviceBuffer):
+            rc = ctx.L.sp2_sumcheck_cubic_prove_dev(ctx.h, _p(claim), _p(taus), C.c_uint32(l), A.ptr, B.ptr, Cz.ptr,
+                                                    C.byref(ts), _p(polys), _p(r), _p(claims))
+        else:
+            A, B, Cz = _fe(A), _fe(B), _fe(Cz)
+            if not (A.shape[0] == B.shape[0] == Cz.shape[0] == (1 << l)):
+                raise SpartanError(-2, "tables must have 2^num_rounds entries")
+            rc = ctx.L.sp2_sumcheck_cubic_prove(ctx.h, _p(claim), _p(taus), C.c_uint32(l), _p(A), _p(B), _p(Cz),
+                                                C.byref(ts), _p(polys), _p(r), _p(claims))
+        ctx.check(rc)
+        return polys, r, claims
+
+    @staticmethod
+    def prove_quad(ctx, claim, num_rounds, A, B, ts):
+        """returns (polys (rounds,3,4), r (rounds,4), claims (2,4))"""
+        claim = _fe(claim); l = int(num_rounds)
+        polys = np.zeros((l, 3, 4), dtype=np.uint64); r = np.zeros((l, 4), dtype=np.uint64); claims = np.zeros((2, 4), dtype=np.uint64)
+        if isinstance(A, DeviceBuffer):
+            rc = ctx.L.sp2_sumcheck_quad_prove_dev(ctx.h, _p(claim), C.c_uint32(l), A.ptr, B.ptr, C.byref(ts), _p(polys), _p(r), _p(claims))
+        else:
+            A, B = _fe(A), _fe(B)
+            if not (A.shape[0] == B.shape[0] == (1 << l)):
+                raise SpartanError(-2, "tables must have 2^num_rounds entries")
+            rc = ctx.L.sp2_sumcheck_quad_prove(ctx.h, _p(claim), C.c_uint32(l), _p(A), _p(B), C.byref(ts), _p(polys), _p(r), _p(claims))
+        ctx.check(rc)
+        return polys, r, claims

@@ -92,6 +92,34 @@ int32_t sp2_bind_top(sp2_ctx *ctx, const uint64_t *Z, uint64_t len, const uint64
 int32_t sp2_eq_table_dev(sp2_ctx *ctx, const void *d_r, uint32_t k, void *d_out);
 int32_t sp2_bind_top_dev(sp2_ctx *ctx, const void *d_Z, uint64_t len, const void *d_r, void *d_out);
 
+/* ---- R1CS (src/r1cs/sparse.rs, src/r1cs/mod.rs) ---------------------------------------------- */
+/* Replaces SplitR1CSShape::precompute (src/r1cs/mod.rs:1059-1073): uploads the three padded CSR
+ * matrices (data: Montgomery scalars; indices/indptr: u32, src/r1cs/sparse.rs:385-394) and builds
+ * the device forms (dictionary-coded rows, transposes, filtered rows).  Column order of z:
+ * [W_shared | W_precommitted | W_rest | 1 | public | challenges]  (src/r1cs/mod.rs:830-853).     */
+int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpadded, uint64_t num_shared, uint64_t num_precommitted,
+                         uint64_t num_rest, uint64_t num_public, uint64_t num_challenges,
+                         const uint64_t *dataA, const uint32_t *indicesA, const uint32_t *indptrA,
+                         const uint64_t *dataB, const uint32_t *indicesB, const uint32_t *indptrB,
+                         const uint64_t *dataC, const uint32_t *indicesC, const uint32_t *indptrC, sp2_shape **out);
+void sp2_shape_free(sp2_shape *shape);
+/* pk.sizes() analogue: [num_cons, num_vars, num_cols, nnz, general nnz, long rows, long columns]  */
+int32_t sp2_shape_sizes(const sp2_shape *shape, uint64_t *out7);
+/* Replaces SplitR1CSShape::multiply_vec (src/r1cs/mod.rs:1075-1107): z[num_cols] -> az,bz,cz[num_cons].
+ * InvalidWitnessLength when z_len != num_cols.                                                   */
+int32_t sp2_spmv3(sp2_ctx *ctx, const sp2_shape *shape, const uint64_t *z, uint64_t z_len, uint64_t *az, uint64_t *bz, uint64_t *cz);
+int32_t sp2_spmv3_dev(sp2_ctx *ctx, const sp2_shape *shape, const void *d_z, void *d_az, void *d_bz, void *d_cz);
+/* Replaces multiply_vec_incremental_into (src/r1cs/mod.rs:1170-1211): cached + filtered columns.  */
+int32_t sp2_spmv3_incremental(sp2_ctx *ctx, const sp2_shape *shape, const uint64_t *z, uint64_t z_len, const uint64_t *cached_az,
+                              const uint64_t *cached_bz, const uint64_t *cached_cz, uint64_t *az, uint64_t *bz, uint64_t *cz);
+int32_t sp2_spmv3_incremental_dev(sp2_ctx *ctx, const sp2_shape *shape, const void *d_z, const void *d_cached_az, const void *d_cached_bz,
+                                  const void *d_cached_cz, void *d_az, void *d_bz, void *d_cz);
+/* Replaces bind_and_prepare_poly_ABC(_full) (src/r1cs/mod.rs:1235-1321): rx = eq(r_x) table of
+ * num_cons scalars, r the batching challenge; out[j] = sum_i (A + r B + r^2 C)[i,j] rx[i] for
+ * j < num_cols, zero up to out_len.                                                              */
+int32_t sp2_abc(sp2_ctx *ctx, const sp2_shape *shape, const uint64_t *rx, uint64_t rx_len, const uint64_t *r, uint64_t *out, uint64_t out_len);
+int32_t sp2_abc_dev(sp2_ctx *ctx, const sp2_shape *shape, const void *d_rx, const void *d_r, void *d_out, uint64_t out_len);
+
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_dev_free(sp2_ctx *ctx, void *p);
@@ -102,6 +130,9 @@ int32_t sp2_dev_memset(sp2_ctx *ctx, void *dst, int32_t value, uint64_t bytes);
 /* page-locked host buffers (so uploads/downloads through this ABI are true async DMA)           */
 int32_t sp2_host_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_host_free(sp2_ctx *ctx, void *p);
+
+/* debug: clock64() stamps of the last finalised sum-check round (7 values, SM cycles)           */
+int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out7);
 
 /* ---- test hooks: the device field layer, element-wise (tests/test_gpu_field.py) ------------- */
 /* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont, 6 half; field: 0 = T256 scalar, 1 = T256 base */

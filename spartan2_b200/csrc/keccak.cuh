@@ -90,6 +90,44 @@ __device__ __forceinline__ u64 keccak256_warp(const unsigned char *msg, int len,
   return s;
 }
 
+// ---- single-thread Keccak-f[1600]: the whole state in registers, rounds fully unrolled inside -------
+// Used by the sum-check round finaliser, where the two challenge halves are hashed by two threads of
+// two different warps: lower latency than the shuffle version (no SHFL dependency chains).
+__device__ __forceinline__ u64 rotl64c(u64 v, int n) { return n == 0 ? v : ((v << n) | (v >> (64 - n))); }
+__device__ __forceinline__ void keccak_f_regs(u64 (&a)[25]) {
+  constexpr int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+#pragma unroll 1
+  for (int rnd = 0; rnd < 24; rnd++) {
+    u64 c[5], d[5], b[25];
+#pragma unroll
+    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+#pragma unroll
+    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64c(c[(x + 1) % 5], 1);
+#pragma unroll
+    for (int y = 0; y < 5; y++)
+#pragma unroll
+      for (int x = 0; x < 5; x++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64c(a[x + 5 * y] ^ d[x], ROT[x + 5 * y]);
+#pragma unroll
+    for (int y = 0; y < 5; y++)
+#pragma unroll
+      for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+    a[0] ^= KECCAK_RC_D[rnd];
+  }
+}
+// Keccak-256 of an already padded message of `nblocks` 136-byte blocks held as u64 words; out: 4 words
+__device__ __forceinline__ void keccak256_padded(const u64 *words, int nblocks, u64 (&out)[4]) {
+  u64 a[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) a[i] = 0;
+  for (int blk = 0; blk < nblocks; blk++) {
+#pragma unroll
+    for (int i = 0; i < 17; i++) a[i] ^= words[blk * 17 + i];
+    keccak_f_regs(a);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) out[i] = a[i];
+}
+
 // squeeze (keccak.rs:70-94) executed by a 64-thread block: warp 0 -> lo, warp 1 -> hi.
 // `buf` is a shared-memory scratch of >= 2048 bytes.  Result: the challenge (Montgomery form)
 // is returned to every thread of warp 0... all threads via shared `out`.

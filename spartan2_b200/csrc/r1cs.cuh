@@ -1,0 +1,44 @@
+// Device-resident R1CS shape (reference src/r1cs/mod.rs:743-911 SplitR1CSShape, src/r1cs/sparse.rs).
+#pragma once
+#include <vector>
+#include "ctx.cuh"
+#include "devutil.cuh"
+
+namespace sp2 {
+
+// One sparse matrix in compressed form, either row-major (CSR, for M*z) or column-major (the transpose
+// in CSR form, for M^T * eq(rx)).  Entry = (index of the gathered vector element, coefficient id).
+// Coefficients are dictionary-coded: R1CS matrices hold a handful of distinct values (+-1, small
+// integers, powers of two) — the observation behind the reference's coefficient classes
+// (sparse.rs:29-45: unit_pos / unit_neg / small / general) — so an entry is 8 bytes instead of 36.
+// dict[0] = 1, dict[1] = -1 (adds/subs, no multiply); anything else is one Montgomery multiply.
+struct DevMatrix {
+  u32 nseg = 0;            // rows (CSR) or columns (transpose)
+  u32 nnz = 0;
+  u32 *ptr = nullptr;      // nseg + 1
+  uint2 *ent = nullptr;    // nnz: .x = gathered index, .y = coefficient id
+  fe *dict = nullptr;
+  u32 ndict = 0;
+  u32 *long_seg = nullptr; // segments with more than LONG_SEG entries (handled by a block each)
+  u32 nlong = 0;
+};
+constexpr u32 LONG_SEG = 48;
+
+}  // namespace sp2
+
+struct sp2_shape {
+  sp2_ctx *ctx = nullptr;
+  uint64_t num_cons = 0, num_cons_unpadded = 0, num_shared = 0, num_precommitted = 0, num_rest = 0, num_public = 0, num_challenges = 0;
+  uint64_t num_vars = 0, num_cols = 0;       // num_cols = num_vars + 1 + num_public + num_challenges
+  sp2::DevMatrix M[3];                       // A, B, C row-major
+  sp2::DevMatrix T[3];                       // transposes (column-major) for bind_and_prepare_poly_ABC
+  sp2::DevMatrix F[3];                       // row-major, columns >= num_shared + num_precommitted only (FilteredSpmv)
+  sp2::u32 *long_cols = nullptr; sp2::u32 nlong_cols = 0;   // columns whose A+B+C degree exceeds LONG_SEG
+  std::vector<void *> owned;
+  uint64_t nnz_total = 0, nnz_general = 0;
+};
+
+namespace sp2 {
+int spmv3_dev(sp2_ctx *ctx, const sp2_shape *S, const DevMatrix *mats, const fe *d_z, const fe *const *base, fe *const *out);
+int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe *d_out, uint64_t out_len);
+}  // namespace sp2

@@ -1,0 +1,36 @@
+// Device-resident sum-check state shared by sumcheck.cu and the fused prover (prover.cu).
+#pragma once
+#include "ctx.cuh"
+#include "keccak.cuh"
+
+namespace sp2 {
+
+constexpr int SC_MAX_ROUNDS = 40;
+constexpr int SC_MAX_BLOCKS = 2048;
+constexpr int SC_THREADS = 256;
+constexpr int SC_TAIL_THREADS = 512;
+constexpr unsigned long long SC_TAIL_LEN = 4096;   // tables this short are finished by one CTA in one launch
+
+struct ScState {
+  DevTranscript ts;           // transcript hand-off: (round, state) in, (round, state) out
+  fe claim;                   // quad: running claim (cubic sums t(0), t(1), t(inf) directly)
+  fe p;                       // eval_eq_left (sumcheck.rs:951)
+  fe L0, SL;                  // p*(1-tau_i), p*(2tau_i-1) for the round being evaluated
+  u32 ticket, l, flags, pad1;   // flags bit 0: warp-shuffle Keccak (default; measured 12.6k cycles/squeeze vs 22k for the one-thread register version)
+  fe taus[SC_MAX_ROUNDS];
+  // ---- everything above is uploaded by the host; everything below is produced on the device ----
+  fe r[SC_MAX_ROUNDS];
+  fe polys[SC_MAX_ROUNDS * 4];
+  fe claims[4];
+  unsigned long long clk[16];   // debug: clock64() stamps of the last finalised round (thread 0)
+  fe partial[3 * SC_MAX_BLOCKS];
+};
+
+int sc_state_upload(sp2_ctx *ctx, ScState **d_st, const uint64_t *claim, const uint64_t *taus, uint32_t l,
+                    const sp2_transcript_state *ts);
+int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uint64_t *polys, int ncoef, uint64_t *r,
+                      uint64_t *claims, int nclaims, uint32_t l);
+int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C);
+int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B);
+
+}  // namespace sp2

@@ -31,6 +31,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pins", []):
+                self.L.sp2_host_free(self.h, p)
+            self._pins = []
             self.L.sp2_ctx_destroy(self.h); self.h = None
 
     def __del__(self):
@@ -103,8 +106,9 @@ class DeviceBuffer:
         self.ctx.check(self.ctx.L.sp2_dev_copy(self.ctx.h, self.ptr, other.ptr, C.c_uint64(nbytes or other.nbytes)))
 
     def free(self):
-        if self.ptr:
-            self.ctx.L.sp2_dev_free(self.ctx.h, self.ptr); self.ptr = None
+        if self.ptr and getattr(self.ctx, "h", None):
+            self.ctx.L.sp2_dev_free(self.ctx.h, self.ptr)
+        self.ptr = None
 
     def __del__(self):
         try:
@@ -172,3 +176,67 @@ class SumcheckProof:
             rc = ctx.L.sp2_sumcheck_quad_prove(ctx.h, _p(claim), C.c_uint32(l), _p(A), _p(B), C.byref(ts), _p(polys), _p(r), _p(claims))
         ctx.check(rc)
         return polys, r, claims
+
+
+class SplitR1CSShape:
+    """src/r1cs/mod.rs:743-1398 — device-resident shape (sp2_shape).  A, B, C are padded CSR triples
+    (data (nnz,4) u64 Montgomery, indices u32, indptr u32 of num_cons+1 entries)."""
+
+    def __init__(self, ctx, num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges, A, B, Cm):
+        self.ctx = ctx
+        self.num_cons = num_cons; self.num_vars = num_shared + num_precommitted + num_rest
+        self.num_shared, self.num_precommitted, self.num_rest = num_shared, num_precommitted, num_rest
+        self.num_public = num_public; self.num_challenges = num_challenges
+        self.num_cols = self.num_vars + 1 + num_public + num_challenges
+        args = [C.c_uint64(x) for x in (num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges)]
+        keep = []
+        for (d, i, p) in (A, B, Cm):
+            d = np.ascontiguousarray(d, dtype=np.uint64).reshape(-1, 4)
+            if d.shape[0] == 0:
+                d = np.zeros((1, 4), dtype=np.uint64)
+            i = np.ascontiguousarray(i, dtype=np.uint32) if len(i) else np.zeros(1, dtype=np.uint32)
+            p = np.ascontiguousarray(p, dtype=np.uint32)
+            if p.shape[0] != num_cons + 1:
+                raise SpartanError(-2, "indptr must have num_cons + 1 entries")
+            keep += [d, i, p]
+            args += [_p(d), _p(i), _p(p)]
+        h = C.c_void_p()
+        ctx.check(ctx.L.sp2_shape_upload(ctx.h, *args, C.byref(h)))
+        self.h = h
+
+    def free(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.sp2_shape_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def sizes(self):
+        out = np.zeros(7, dtype=np.uint64)
+        self.ctx.L.sp2_shape_sizes(self.h, _p(out))
+        return dict(zip(["num_cons", "num_vars", "num_cols", "nnz", "nnz_general", "long_rows", "long_cols"], [int(x) for x in out]))
+
+    def multiply_vec(self, z):
+        z = _fe(z); n = self.num_cons
+        az, bz, cz = (np.zeros((n, 4), dtype=np.uint64) for _ in range(3))
+        self.ctx.check(self.ctx.L.sp2_spmv3(self.ctx.h, self.h, _p(z), C.c_uint64(z.shape[0]), _p(az), _p(bz), _p(cz)))
+        return az, bz, cz
+
+    def multiply_vec_incremental(self, z, cached_az, cached_bz, cached_cz):
+        z = _fe(z); n = self.num_cons
+        ca, cb, cc = _fe(cached_az), _fe(cached_bz), _fe(cached_cz)
+        az, bz, cz = (np.zeros((n, 4), dtype=np.uint64) for _ in range(3))
+        self.ctx.check(self.ctx.L.sp2_spmv3_incremental(self.ctx.h, self.h, _p(z), C.c_uint64(z.shape[0]), _p(ca), _p(cb), _p(cc),
+                                                        _p(az), _p(bz), _p(cz)))
+        return az, bz, cz
+
+    def bind_and_prepare_poly_ABC(self, evals_rx, r, full=False):
+        rx = _fe(evals_rx); r = _fe(r)
+        out_len = 2 * self.num_vars if full else self.num_cols
+        out = np.zeros((out_len, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.sp2_abc(self.ctx.h, self.h, _p(rx), C.c_uint64(rx.shape[0]), _p(r), _p(out), C.c_uint64(out_len)))
+        return out

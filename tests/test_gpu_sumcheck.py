@@ -54,17 +54,19 @@ def test_cubic_verifies(ctx, orc):
     assert pi(e_final)[0] == tb * (a * b - c) % Q
 
 
-def test_cubic_tau_zero_is_reported(ctx, orc):
-    """tau_i = 0 is the reference's fallback_three_inputs case (sumcheck.rs:1327-1396); the CUDA path
-    reports Unsupported instead of returning wrong coefficients."""
+def test_cubic_tau_zero_matches_reference_fallback(ctx, orc):
+    """tau_i = 0 makes l(1) * eval_eq_left = 0: the reference leaves derive_from_claim and takes
+    fallback_three_inputs (sumcheck.rs:1290-1292, 1327-1396).  The CUDA prover always sums t(1) directly, so the
+    case needs no special path — and must give the same polynomials."""
+    rng = np.random.default_rng(1); l = 6; n = 1 << l
     import spartan2_b200 as sp
-    rng = np.random.default_rng(1); l = 4; n = 1 << l
     A, B, Cz, taus = rand_fe(rng, n), rand_fe(rng, n), rand_fe(rng, n), rand_fe(rng, l)
-    taus[2] = 0
-    _, ts = ts_pair(orc)
-    with pytest.raises(sp.SpartanError) as ei:
-        sp.SumcheckProof.prove_cubic_with_three_inputs(ctx, np.zeros((1, 4), dtype=np.uint64), taus, A, B, Cz, ts)
-    assert ei.value.kind == "Unsupported"
+    taus[0] = 0; taus[3] = 0
+    claim = orc.f_dot_delayed(orc.eq_evals(taus), orc.f_sub(orc.f_mul(A, B), Cz))
+    t_or, ts = ts_pair(orc)
+    polys, r, claims = sp.SumcheckProof.prove_cubic_with_three_inputs(ctx, claim, taus, A, B, Cz, ts)
+    opolys, orr, oclaims, _ = orc.sumcheck_cubic_prove(claim, taus, A, B, Cz, t_or)
+    assert np.array_equal(polys, opolys) and np.array_equal(r, orr) and np.array_equal(claims, oclaims)
 
 
 @pytest.mark.parametrize("l", [1, 2, 3, 5, 8, 9, 12, 16, 18])

@@ -120,6 +120,26 @@ int32_t sp2_spmv3_incremental_dev(sp2_ctx *ctx, const sp2_shape *shape, const vo
 int32_t sp2_abc(sp2_ctx *ctx, const sp2_shape *shape, const uint64_t *rx, uint64_t rx_len, const uint64_t *r, uint64_t *out, uint64_t out_len);
 int32_t sp2_abc_dev(sp2_ctx *ctx, const sp2_shape *shape, const void *d_rx, const void *d_r, void *d_out, uint64_t out_len);
 
+/* ---- commitment provider (src/provider/msm.rs, src/provider/pcs/hyrax_pc.rs) ----------------- */
+/* Replaces PCSEngineTrait::precompute_ck (src/traits/pcs.rs:56-58): uploads the Hyrax key
+ * (n row bases, blinding base h; the 1-wide evaluation key ck_s, h_s — hyrax_pc.rs:152-190) and
+ * precomputes the 2^(8w) multiples of every base (cf. FixedBaseMul::precompute, msm.rs:651-689). */
+int32_t sp2_ck_upload(sp2_ctx *ctx, const uint64_t *bases_xy, uint32_t n, const uint64_t *h_xy, const uint64_t *ck_s_xy,
+                      const uint64_t *h_s_xy, sp2_ck **out);
+void sp2_ck_free(sp2_ck *ck);
+/* Replaces DlogGroupExt::vartime_multiscalar_mul (src/provider/traits.rs:118-134 -> msm.rs:187-222):
+ * out = sum_i scalars[i] * ck_i, affine (identity = all zero).  InvalidCommitmentKeyLength if n > key. */
+int32_t sp2_msm(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *scalars, uint32_t n, uint64_t *out_xy);
+/* Replaces HyraxPCS::commit / commit_zeros (hyrax_pc.rs:207-319): one Pedersen commitment per row of
+ * ck-width scalars, out_rows[i] = <v_row_i, ck> + blinds[i] * h.  `is_small` is the reference's hint
+ * (msm_small path); it does not change the result.                                               */
+int32_t sp2_hyrax_commit(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint64_t len, const uint64_t *blinds, uint64_t rows,
+                         int32_t is_small, uint64_t *out_rows);
+int32_t sp2_hyrax_commit_dev(sp2_ctx *ctx, const sp2_ck *ck, const void *d_v, uint64_t len, const void *d_blinds, uint64_t rows,
+                             void *d_out_rows);
+/* Replaces bind_with_delayed (hyrax_pc.rs:38-54): out[i] = sum_j L[j] * poly[j * r_len + i].      */
+int32_t sp2_hyrax_bind(sp2_ctx *ctx, const uint64_t *poly, const uint64_t *L, uint64_t rows, uint64_t r_len, uint64_t *out);
+
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_dev_free(sp2_ctx *ctx, void *p);

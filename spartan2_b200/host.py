@@ -240,3 +240,59 @@ class SplitR1CSShape:
         out = np.zeros((out_len, 4), dtype=np.uint64)
         self.ctx.check(self.ctx.L.sp2_abc(self.ctx.h, self.h, _p(rx), C.c_uint64(rx.shape[0]), _p(r), _p(out), C.c_uint64(out_len)))
         return out
+
+
+class CommitmentKey:
+    """HyraxPCS commitment key resident on the device (sp2_ck): ck (n row bases), h, and the 1-wide evaluation
+    key (ck_s, h_s) — src/provider/pcs/hyrax_pc.rs:152-190.  Points are (k, 8) u64 affine Montgomery."""
+
+    def __init__(self, ctx, ck, h, ck_s, h_s):
+        self.ctx = ctx
+        ck = np.ascontiguousarray(ck, dtype=np.uint64).reshape(-1, 8)
+        h, ck_s, h_s = (np.ascontiguousarray(x, dtype=np.uint64).reshape(1, 8) for x in (h, ck_s, h_s))
+        self.n = ck.shape[0]
+        hd = C.c_void_p()
+        ctx.check(ctx.L.sp2_ck_upload(ctx.h, _p(ck), C.c_uint32(self.n), _p(h), _p(ck_s), _p(h_s), C.byref(hd)))
+        self.h = hd
+
+    def free(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.sp2_ck_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DlogGroupExt:
+    """src/provider/traits.rs:118-162"""
+
+    @staticmethod
+    def vartime_multiscalar_mul(ctx, ck, scalars):
+        s = _fe(scalars)
+        out = np.zeros((1, 8), dtype=np.uint64)
+        ss = s if s.shape[0] else np.zeros((1, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_msm(ctx.h, ck.h, _p(ss), C.c_uint32(s.shape[0]), _p(out)))
+        return out
+
+
+class HyraxPCS:
+    """src/provider/pcs/hyrax_pc.rs"""
+
+    @staticmethod
+    def commit(ctx, ck, v, blinds, is_small=False):
+        v = _fe(v); blinds = _fe(blinds); rows = blinds.shape[0]
+        out = np.zeros((rows, 8), dtype=np.uint64)
+        vv = v if v.shape[0] else np.zeros((1, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_hyrax_commit(ctx.h, ck.h, _p(vv), C.c_uint64(v.shape[0]), _p(blinds), C.c_uint64(rows), C.c_int32(int(is_small)), _p(out)))
+        return out
+
+    @staticmethod
+    def bind_with_delayed(ctx, poly, L, r_len):
+        poly = _fe(poly); L = _fe(L)
+        out = np.zeros((r_len, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_hyrax_bind(ctx.h, _p(poly), _p(L), C.c_uint64(L.shape[0]), C.c_uint64(r_len), _p(out)))
+        return out

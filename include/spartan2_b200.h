@@ -151,8 +151,9 @@ int32_t sp2_dev_memset(sp2_ctx *ctx, void *dst, int32_t value, uint64_t bytes);
 int32_t sp2_host_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_host_free(sp2_ctx *ctx, void *p);
 
-/* debug: clock64() stamps of the last finalised sum-check round (7 values, SM cycles)           */
-int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out7);
+/* debug: 7 clock64() stamps (SM cycles) of the last finalised sum-check round, then 4 %globaltimer
+ * values (ns) of the last multi-CTA cubic round: [-, election, finalize end, first CTA entry]     */
+int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out11);
 
 /* ---- test hooks: the device field layer, element-wise (tests/test_gpu_field.py) ------------- */
 /* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont, 6 half; field: 0 = T256 scalar, 1 = T256 base */

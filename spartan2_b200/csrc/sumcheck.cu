@@ -59,6 +59,7 @@ __device__ __forceinline__ fe ld_state(const fe *p) {   // device-produced scala
 __device__ __noinline__ void fq_mul_ni(fe *out, const fe *a, const fe *b) { *out = Fq::mul(*a, *b); }
 __device__ __forceinline__ fe mul_ni(const fe &a, const fe &b) { fe o; fq_mul_ni(&o, &a, &b); return o; }
 
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // publish this CTA's partial sums and elect the last CTA of the grid
 template <int NV>
 __device__ __forceinline__ bool publish_and_elect(ScState *st, fe (&x)[NV], FinSmem &sm) {
@@ -74,6 +75,7 @@ __device__ __forceinline__ bool publish_and_elect(ScState *st, fe (&x)[NV], FinS
   __syncthreads();
   if (!sm.is_last) return false;
   __threadfence();
+  if (threadIdx.x == 0) st->gt[1] = gtimer();
   x[0] = Fq::zero(); x[1] = Fq::zero(); if (NV > 2) x[NV - 1] = Fq::zero();
   for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
 #pragma unroll
@@ -256,6 +258,7 @@ template <bool FUSED, int MODE>
 __global__ void __launch_bounds__(SC_THREADS, SC_CUBIC_MINB)
 k_cubic_round(ScState *st, fe *A, fe *B, fe *C, u64 P, int round1, int l, const fe *el, const fe *er, u32 out_len, u32 sh) {
   __shared__ FinSmem sm;
+  if (threadIdx.x == 0) atomicMin(&st->gt[0], gtimer());
   fe r;
   if (FUSED) r = ld_state(&st->r[round1 - 2]);
   fe x[3];
@@ -274,6 +277,7 @@ k_cubic_round(ScState *st, fe *A, fe *B, fe *C, u64 P, int round1, int l, const 
   block_sum_fq<3>(x, sm.red);
   if (!publish_and_elect<3>(st, x, sm)) return;
   cubic_finalize(st, round1, l, A, B, C, x, sm);
+  if (threadIdx.x == 0) { st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
 }
 
 // all remaining rounds [round_first, l] in one CTA (tables of <= SC_TAIL_LEN entries going in)
@@ -309,6 +313,7 @@ __global__ void __launch_bounds__(1024) k_cubic_init(ScState *st, int l, fe *eq_
     if (threadIdx.x == 0) {
       const fe tau = ldg_fe(&st->taus[0]);
       const fe l0 = Fq::sub(Fq::one(), tau);
+      st->gt[0] = ~0ull;
       stg_fe(&st->p, Fq::one());
       stg_fe(&st->L0, l0);
       stg_fe(&st->SL, Fq::sub(tau, l0));
@@ -502,11 +507,12 @@ extern "C" {
 
 /* debug: clock64() stamps (SM cycles) of the last finalised sum-check round: [tail round start, finalize start,
  * squeeze start, message built, hashed, challenge ready, finalize end] */
-int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out7) {
+int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out7 /* 11 values */) {
   cudaSetDevice(ctx->device);
   if (!ctx->slot[14]) return set_error(ctx, SP2_ERR_INTERNAL, "no sum-check has run");
   ScState *st = (ScState *)ctx->slot[14];
   SP2_CUDA_OK(cudaMemcpyAsync(out7, st->clk, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(out7 + 7, st->gt, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return SP2_OK;
 }

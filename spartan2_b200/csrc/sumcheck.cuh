@@ -23,6 +23,7 @@ struct ScState {
   fe polys[SC_MAX_ROUNDS * 4];
   fe claims[4];
   unsigned long long clk[16];   // debug: clock64() stamps of the last finalised round (thread 0)
+  unsigned long long gt[8];     // debug: %globaltimer (ns) of the last multi-CTA round: [first CTA entry, election, finalize end]
   fe partial[3 * SC_MAX_BLOCKS];
 };
 

@@ -140,6 +140,36 @@ int32_t sp2_hyrax_commit_dev(sp2_ctx *ctx, const sp2_ck *ck, const void *d_v, ui
 /* Replaces bind_with_delayed (hyrax_pc.rs:38-54): out[i] = sum_j L[j] * poly[j * r_len + i].      */
 int32_t sp2_hyrax_bind(sp2_ctx *ctx, const uint64_t *poly, const uint64_t *L, uint64_t rows, uint64_t r_len, uint64_t *out);
 
+/* ---- SpartanSNARK (src/spartan.rs) ------------------------------------------------------------ */
+/* Flat view of SpartanSNARK<E> (src/spartan.rs:126-139) over caller-owned buffers:
+ *   comm_W        num_comm_rows points (HyraxCommitment rows: shared | precommitted | rest)
+ *   outer_polys   num_rounds_x x 3 scalars  (CompressedUniPoly: c0, c2, c3 — univariate.rs:147-153)
+ *   claims_outer  3 scalars (Az, Bz, Cz at r_x)
+ *   inner_polys   num_rounds_y x 2 scalars  (c0, c2)
+ *   eval_W, blind_eval_W; IPA argument: delta, beta (points), z_vec (num_cols scalars), z_delta, z_beta
+ *   (HyraxEvaluationArgument / InnerProductArgumentLinear, hyrax_pc.rs:96-118, ipa.rs:104-121).           */
+typedef struct {
+  uint64_t num_rounds_x, num_rounds_y, num_comm_rows, num_cols;
+  uint64_t *comm_W, *outer_polys, *claims_outer, *inner_polys, *eval_W, *blind_eval_W, *delta, *beta, *z_vec, *z_delta, *z_beta;
+} sp2_spartan_proof;
+/* The prover's randomness (the reference draws it from thread_rng inside prove: hyrax_pc.rs:192-205,
+ * ipa.rs:140-145, bellpepper/r1cs.rs:467); the caller samples and passes it so runs are reproducible:
+ * blinds_W: one per commitment row; d_vec: num_cols scalars.                                      */
+typedef struct { const uint64_t *blinds_W, *blind_eval_W, *d_vec, *r_delta, *r_beta; } sp2_spartan_rand;
+
+/* Replaces SpartanSNARK::prep_prove (src/spartan.rs:176-216): uploads the shared+precommitted witness
+ * (num_shared + num_precommitted scalars), commits it row-wise (comm_out: rows x 8, may be NULL) and caches
+ * its Az/Bz/Cz on the device.  The returned handle is the device half of SpartanPrepSNARK (:107-124).       */
+int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck, const uint64_t *W_cached,
+                               const uint64_t *blinds_cached, int32_t is_small, uint64_t *comm_out, sp2_prep **out);
+void sp2_prep_free(sp2_prep *prep);
+/* Replaces SpartanSNARK::prove (src/spartan.rs:219-466).  W_rest: num_rest scalars (may be NULL when 0).
+ * phase_ms: optional 8 floats of device time (commit+transcript, matrix_vector_multiply, outer_sumcheck,
+ * prepare_poly_ABC, inner_sumcheck, pcs_prove, ipa response, total).  DivisionByZero as spartan.rs:417.  */
+int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck, sp2_prep *prep, const uint8_t *vk_digest,
+                          const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rand,
+                          sp2_spartan_proof *proof, float *phase_ms);
+
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_dev_free(sp2_ctx *ctx, void *p);

@@ -9,4 +9,4 @@ Field elements are numpy uint64 arrays of shape (n, 4): little-endian 64-bit lim
 (R = 2^256) — the reference's in-memory layout (src/big_num/montgomery.rs:17-22)."""
 from ._lib import SpartanError, TranscriptState, lib, LIB_PATH  # noqa: F401
 from .host import (CommitmentKey, Context, DeviceBuffer, DlogGroupExt, EqPolynomial, HyraxPCS, MultilinearPolynomial,
-                   SplitR1CSShape, SumcheckProof)  # noqa: F401
+                   SpartanPrepSNARK, SpartanProof, SpartanSNARK, SplitR1CSShape, SumcheckProof)  # noqa: F401

@@ -1,0 +1,399 @@
+// Fused SpartanSNARK prover: prep_prove + prove on the device.
+//
+// Restates reference src/spartan.rs:176-216 (prep_prove) and :219-466 (prove), with the witness
+// commitment of src/bellpepper/r1cs.rs:359-537 (commit of the precommitted section, rest section,
+// transcript absorbs) and HyraxPCS::prove + the linear inner-product argument
+// (src/provider/pcs/hyrax_pc.rs:387-478, src/provider/pcs/ipa.rs:125-170).
+//
+// Device/host split (B200 design): every field/group computation runs on the device; the host only
+// sequences launches and hashes BULK transcript data (commitment rows: tens of KB through a serial
+// Keccak is host-speed work).  The two sum-check loops run on the device end to end with the
+// transcript handed over as (round, state); the outer->inner transition (absorb claims_outer,
+// squeeze r, joint claim) also stays on the device.  Host syncs per prove: 3 (rest-commitment rows,
+// sum-check results + PCS points, IPA response) instead of one per sum-check round.
+#include <string.h>
+#include <algorithm>
+#include "ctx.cuh"
+#include "host_transcript.h"
+#include "keccak.cuh"
+#include "msm.cuh"
+#include "polys.cuh"
+#include "r1cs.cuh"
+#include "sumcheck.cuh"
+
+using namespace sp2;
+
+namespace sp2 {
+int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out);
+}
+
+struct sp2_prep {
+  sp2_ctx *ctx = nullptr;
+  const sp2_shape *S = nullptr;
+  const sp2_ck *ck = nullptr;
+  uint64_t cached_len = 0, cached_rows = 0, rows_total = 0;
+  fe *W = nullptr;                   // num_vars (cached part filled by prep_prove, rest by prove)
+  fe *cached[3] = {nullptr, nullptr, nullptr};   // Az/Bz/Cz over the shared+precommitted columns (spartan.rs:184-187)
+  fe *work[3] = {nullptr, nullptr, nullptr};     // sum-check tables
+  fe *z = nullptr, *abc = nullptr;   // num_cols each
+  fe *blinds = nullptr;              // rows_total
+  fe *small = nullptr;               // scalars scratch (see offsets below)
+  aff *points = nullptr;             // device points scratch: [rows_total comm rows | 4 PCS points]
+  fe *LZ = nullptr, *Ltab = nullptr, *Rtab = nullptr, *dvec = nullptr, *zvec = nullptr;
+  std::vector<uint64_t> comm_cached; // host copy of the cached commitment rows (affine)
+  std::vector<void *> owned;
+};
+
+namespace {
+
+enum SmallSlot { S_RJOINT = 0, S_EVALW = 1, S_EVALX = 2, S_RLZ = 3, S_IP = 4, S_BLIND_EVAL = 5, S_RDELTA = 6, S_RBETA = 7,
+                 S_ZDELTA = 8, S_ZBETA = 9, S_RIPA = 10, S_ERR = 11, S_COUNT = 16 };
+
+// taus from the host-squeezed 64-byte digests: from_uniform (LE 512-bit mod p), into the sum-check state
+__global__ void k_taus_from_digests(ScState *st, const unsigned char *dg, int l) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= l) return;
+  fe lo, hi;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const unsigned char *p = dg + 64 * i + 4 * k;
+    lo.v[k] = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+    hi.v[k] = (u32)p[32] | ((u32)p[33] << 8) | ((u32)p[34] << 16) | ((u32)p[35] << 24);
+  }
+  stg_fe(&st->taus[i], Fq::from_uniform(lo, hi));
+}
+
+__global__ void k_set_one(fe *p) { if (threadIdx.x == 0) stg_fe(p, Fq::one()); }
+
+// outer -> inner: absorb(b"claims_outer", [A(rx), B(rx), C(rx)]); r = squeeze(b"r");
+// joint = A + r B + r^2 C (spartan.rs:305-316).  Initialises the inner sum-check state.
+__global__ void __launch_bounds__(64) k_outer_to_inner(ScState *outer, ScState *inner, fe *small, int rounds_inner) {
+  __shared__ unsigned char buf[2304];
+  __shared__ fe ch;
+  DevTranscript *ts = &outer->ts;
+  if (threadIdx.x == 0) {
+    const char lab[] = "claims_outer";
+    ts->pending_len = 0;
+    ts_push_bytes(ts, (const unsigned char *)lab, 12);
+    for (int k = 0; k < 3; k++) ts_push_fe_be(ts, Fq::from_mont(outer->claims[k]));
+  }
+  __syncthreads();
+  ts_squeeze_block(ts, "r", 1, buf, &ch);
+  if (threadIdx.x == 0) {
+    const fe r = ch;
+    const fe joint = Fq::add(outer->claims[0], Fq::mul(r, Fq::add(outer->claims[1], Fq::mul(r, outer->claims[2]))));
+    stg_fe(&small[S_RJOINT], r);
+    inner->ts.round = ts->round; inner->ts.pending_len = 0;
+    for (int i = 0; i < 64; i++) inner->ts.state[i] = ts->state[i];
+    stg_fe(&inner->claim, joint);
+    inner->ticket = 0; inner->l = (u32)rounds_inner; inner->flags = outer->flags;
+  }
+}
+
+// eval_X = SparsePolynomial(X).evaluate(r_y[1..]) (polys/multilinear.rs:190-207);
+// eval_W = (eval_Z - r_y[0] eval_X) / (1 - r_y[0])   (spartan.rs:411-421)
+__global__ void __launch_bounds__(256) k_eval_w(const ScState *inner, const fe *X, u32 zlen, int m, fe *chis_scratch, fe *small) {
+  __shared__ fe red[32];
+  int nvz = 0; while (((u32)1 << nvz) < zlen) nvz++;
+  const int skip = m - 1 - nvz, k = nvz + 1;
+  const fe *ry1 = inner->r + 1;                       // r_y[1..]
+  eq_prefix_block(ry1 + skip, k, chis_scratch);
+  const fe *chis = chis_scratch + (((size_t)1 << k) - 1);
+  fe x[1] = {Fq::zero()};
+  for (u32 i = threadIdx.x; i < zlen; i += blockDim.x) x[0] = Fq::add(x[0], Fq::mul(ldg_fe(X + i), ldg_fe(chis + i)));
+  block_sum_fq<1>(x, red);
+  if (threadIdx.x == 0) {
+    fe common = Fq::one();
+    for (int i = 0; i < skip; i++) common = Fq::mul(common, Fq::sub(Fq::one(), ldg_fe(ry1 + i)));
+    const fe eval_X = Fq::mul(common, x[0]);
+    const fe ry0 = ldg_fe(&inner->r[0]);
+    const fe den = Fq::sub(Fq::one(), ry0);
+    if (Fq::is_zero(den)) ((u32 *)&small[S_ERR])[0] = 5;   // SpartanError::DivisionByZero
+    const fe eval_W = Fq::mul(Fq::sub(ldg_fe(&inner->claims[1]), Fq::mul(ry0, eval_X)), Fq::inv(den));
+    stg_fe(&small[S_EVALX], eval_X);
+    stg_fe(&small[S_EVALW], eval_W);
+  }
+}
+
+// out = <a, b> (delayed reduction), one CTA
+__global__ void __launch_bounds__(256) k_dot(const fe *a, const fe *b, u64 n, fe *out) {
+  __shared__ fe red[32];
+  Fq::acc acc = Fq::acc_zero();
+  for (u64 i = threadIdx.x; i < n; i += blockDim.x) Fq::mul_acc(acc, ldg_fe(a + i), ldg_fe(b + i));
+  fe x[1] = {Fq::acc_reduce(acc)};
+  block_sum_fq<1>(x, red);
+  if (threadIdx.x == 0) stg_fe(out, x[0]);
+}
+
+// IPA response (ipa.rs:155-167): r from the host-squeezed digest; z_vec = r*LZ + d; z_delta = r*r_LZ + r_delta;
+// z_beta = r*blind_eval + r_beta
+__global__ void __launch_bounds__(256) k_ipa_finish(const unsigned char *dg, const fe *LZ, const fe *d, u64 n, fe *zvec, fe *small) {
+  fe lo, hi;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const unsigned char *p = dg + 4 * k;
+    lo.v[k] = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+    hi.v[k] = (u32)p[32] | ((u32)p[33] << 8) | ((u32)p[34] << 16) | ((u32)p[35] << 24);
+  }
+  const fe r = Fq::from_uniform(lo, hi);
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stg_fe(zvec + i, Fq::add(Fq::mul(r, ldg_fe(LZ + i)), ldg_fe(d + i)));
+  if (i == 0) {
+    stg_fe(&small[S_RIPA], r);
+    stg_fe(&small[S_ZDELTA], Fq::add(Fq::mul(r, ldg_fe(&small[S_RLZ])), ldg_fe(&small[S_RDELTA])));
+    stg_fe(&small[S_ZBETA], Fq::add(Fq::mul(r, ldg_fe(&small[S_BLIND_EVAL])), ldg_fe(&small[S_RBETA])));
+  }
+}
+
+template <class T>
+int palloc(sp2_prep *P, T **p, size_t n) {
+  sp2_ctx *ctx = P->ctx;
+  SP2_CUDA_OK(cudaMalloc((void **)p, n * sizeof(T) + 64));
+  P->owned.push_back(*p);
+  return SP2_OK;
+}
+
+int log2_exact(uint64_t v) { int l = 0; while (((uint64_t)1 << l) < v) l++; return l; }
+
+}  // namespace
+
+extern "C" {
+
+void sp2_prep_free(sp2_prep *P) {
+  if (!P) return;
+  cudaSetDevice(P->ctx->device);
+  cudaStreamSynchronize(P->ctx->stream);
+  for (void *p : P->owned) cudaFree(p);
+  delete P;
+}
+
+/* SpartanSNARK::prep_prove (spartan.rs:176-216): commit the shared+precommitted witness sections
+ * (bellpepper/r1cs.rs:306-408 -> HyraxPCS::commit) and cache their Az/Bz/Cz (multiply_vec_precommitted). */
+int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, const uint64_t *W_cached, const uint64_t *blinds_cached,
+                               int32_t is_small, uint64_t *comm_out, sp2_prep **out) {
+  (void)is_small;
+  cudaSetDevice(ctx->device);
+  if (!out) return SP2_ERR_INTERNAL;
+  *out = nullptr;
+  const uint64_t width = ck->n, nv = S->num_vars;
+  if (nv == 0 || (nv & (nv - 1))) return set_error(ctx, SP2_ERR_INVALID_WITNESS_LENGTH, "prep_prove: num_vars must be a power of two");
+  if (nv % width || S->num_shared % width || S->num_precommitted % width || S->num_rest % width)
+    return set_error(ctx, SP2_ERR_INVALID_WITNESS_LENGTH, "prep_prove: witness sections must be multiples of the commitment width");
+  if (S->num_challenges) return set_error(ctx, SP2_ERR_UNSUPPORTED, "prep_prove: multi-round (challenge) circuits are not offloaded");
+  sp2_prep *P = new sp2_prep();
+  P->ctx = ctx; P->S = S; P->ck = ck;
+  P->cached_len = S->num_shared + S->num_precommitted; P->cached_rows = P->cached_len / width; P->rows_total = nv / width;
+  const uint64_t N = S->num_cons, nc = S->num_cols;
+  int rc = SP2_OK;
+  auto A = [&](int r) { if (rc == SP2_OK) rc = r; };
+  A(palloc(P, &P->W, nv));
+  for (int k = 0; k < 3; k++) { A(palloc(P, &P->cached[k], N)); A(palloc(P, &P->work[k], N)); }
+  A(palloc(P, &P->z, nc)); A(palloc(P, &P->abc, nc));
+  A(palloc(P, &P->blinds, P->rows_total)); A(palloc(P, &P->small, (size_t)S_COUNT));
+  A(palloc(P, &P->points, P->rows_total + 8));
+  A(palloc(P, &P->LZ, width)); A(palloc(P, &P->Ltab, std::max<uint64_t>(P->rows_total, 1))); A(palloc(P, &P->Rtab, width));
+  A(palloc(P, &P->dvec, width)); A(palloc(P, &P->zvec, width));
+  if (rc != SP2_OK) { sp2_prep_free(P); return rc; }
+  auto fail = [&](int r) { sp2_prep_free(P); return r; };
+  cudaError_t e = cudaMemsetAsync(P->W, 0, nv * sizeof(fe), ctx->stream);
+  if (e == cudaSuccess && P->cached_len) e = cudaMemcpyAsync(P->W, W_cached, P->cached_len * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && P->cached_rows) e = cudaMemcpyAsync(P->blinds, blinds_cached, P->cached_rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return fail(set_cuda_error(ctx, e, "prep upload", __LINE__));
+  // commitments of the cached rows
+  if (P->cached_rows) {
+    rc = sp2_hyrax_commit_dev(ctx, ck, P->W, P->cached_len, P->blinds, P->cached_rows, P->points);
+    if (rc != SP2_OK) return fail(rc);
+    P->comm_cached.resize(P->cached_rows * 8);
+    e = cudaMemcpyAsync(P->comm_cached.data(), P->points, P->cached_rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) return fail(set_cuda_error(ctx, e, "prep download", __LINE__));
+  }
+  // cached partial products: z = [W_cached | 0 ... 0]
+  e = cudaMemsetAsync(P->z, 0, nc * sizeof(fe), ctx->stream);
+  if (e == cudaSuccess && P->cached_len) e = cudaMemcpyAsync(P->z, P->W, P->cached_len * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) return fail(set_cuda_error(ctx, e, "prep z", __LINE__));
+  rc = spmv3_dev(ctx, S, S->M, P->z, nullptr, P->cached);
+  if (rc != SP2_OK) return fail(rc);
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return fail(set_cuda_error(ctx, e, "prep sync", __LINE__));
+  if (comm_out && P->cached_rows) memcpy(comm_out, P->comm_cached.data(), P->cached_rows * sizeof(aff));
+  *out = P;
+  return SP2_OK;
+}
+
+/* SpartanSNARK::prove (spartan.rs:219-466).  phase_ms (optional, 8 floats): device time of
+ * [witness commit + transcript, matrix_vector_multiply, outer_sumcheck, prepare_poly_ABC, inner_sumcheck,
+ *  pcs_prove (bind + MSMs), ipa response, total]. */
+int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp2_prep *P, const uint8_t *vk_digest,
+                          const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rnd, sp2_spartan_proof *proof,
+                          float *phase_ms) {
+  cudaSetDevice(ctx->device);
+  if (!P || P->S != S || P->ck != ck) return set_error(ctx, SP2_ERR_INTERNAL, "prove: prep state does not belong to this shape/key");
+  const uint64_t width = ck->n, nv = S->num_vars, N = S->num_cons, nc = S->num_cols;
+  const int l = log2_exact(N), m = log2_exact(nv), nry = m + 1;
+  const uint64_t num_extra = 1 + S->num_public;
+  const uint64_t rows = P->rows_total, rest_rows = rows - P->cached_rows;
+  int nvr = log2_exact(rows);
+  if (((uint64_t)1 << nvr) != rows || (width & (width - 1))) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "prove: rows and width must be powers of two");
+  int nvz = 0; while (((uint64_t)1 << nvz) < num_extra) nvz++;
+  if (m - 1 - nvz < 0) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "prove: too many public inputs for the witness length");
+  if (l > SC_MAX_ROUNDS || nry > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "prove: instance too large");
+
+  cudaEvent_t ev[9];
+  for (auto &x : ev) SP2_CUDA_OK(cudaEventCreate(&x));
+  auto mark = [&](int i) { cudaEventRecord(ev[i], ctx->stream); };
+  auto cleanup = [&]() { for (auto &x : ev) cudaEventDestroy(x); };
+  mark(0);
+
+  // ---- witness: rest section, blinds, randomness -------------------------------------------------
+  fe *small = P->small;
+  SP2_CUDA_OK(cudaMemsetAsync(small, 0, S_COUNT * sizeof(fe), ctx->stream));
+  if (S->num_rest) SP2_CUDA_OK(cudaMemcpyAsync(P->W + P->cached_len, W_rest, S->num_rest * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  if (rest_rows) SP2_CUDA_OK(cudaMemcpyAsync(P->blinds + P->cached_rows, rnd->blinds_W + 4 * P->cached_rows, rest_rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(&small[S_BLIND_EVAL], rnd->blind_eval_W, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(&small[S_RDELTA], rnd->r_delta, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(&small[S_RBETA], rnd->r_beta, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(P->dvec, rnd->d_vec, width * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  // z = W | 1 | X   (spartan.rs:248-253)
+  SP2_CUDA_OK(cudaMemcpyAsync(P->z, P->W, nv * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+  k_set_one<<<1, 32, 0, ctx->stream>>>(P->z + nv);
+  SP2_LAUNCH_CHECK();
+  if (S->num_public) SP2_CUDA_OK(cudaMemcpyAsync(P->z + nv + 1, public_values, S->num_public * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+
+  // ---- transcript up to the taus (host; spartan.rs:226-264, bellpepper/r1cs.rs:422-431,491) -----
+  sp2h::Transcript ts("SpartanSNARK");
+  ts.absorb_bytes("vk", vk_digest, 32);
+  ts.absorb_scalars("public_values", public_values, S->num_public);
+  const uint64_t sh_rows = S->num_shared / width, pre_rows = S->num_precommitted / width;
+  if (sh_rows) ts.absorb_commitment("comm_W_shared", P->comm_cached.data(), sh_rows);
+  if (pre_rows) ts.absorb_commitment("comm_W_precommitted", P->comm_cached.data() + 8 * sh_rows, pre_rows);
+  memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
+  // commit the rest section (r1cs.rs:467-470: blind + commit / commit_zeros)
+  if (rest_rows) {
+    SP2_TRY(sp2_hyrax_commit_dev(ctx, ck, P->W + P->cached_len, S->num_rest, P->blinds + P->cached_rows, rest_rows, P->points + P->cached_rows));
+    SP2_CUDA_OK(cudaMemcpyAsync(proof->comm_W + 8 * P->cached_rows, P->points + P->cached_rows, rest_rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+    SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                        // host sync 1
+  }
+  ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
+  proof->num_rounds_x = l; proof->num_rounds_y = nry; proof->num_comm_rows = rows; proof->num_cols = width;
+  std::vector<uint8_t> tau_dg((size_t)l * 64);
+  for (int i = 0; i < l; i++) ts.squeeze("t", tau_dg.data() + 64 * i);
+  mark(1);
+
+  // ---- Az, Bz, Cz (spartan.rs:271 -> multiply_vec_incremental_into) ------------------------------
+  { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
+    SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
+  mark(2);
+
+  // ---- outer sum-check (spartan.rs:293 -> sumcheck.rs:502) ---------------------------------------
+  ScState *st_outer, *st_inner;
+  { void *p; SP2_TRY(scratch(ctx, 14, sizeof(ScState), &p)); st_outer = (ScState *)p;
+    SP2_TRY(scratch(ctx, 9, sizeof(ScState), &p)); st_inner = (ScState *)p; }
+  sp2_transcript_state hts; hts.round = ts.round; memcpy(hts.state, ts.state, 64);
+  const uint64_t zero4[4] = {0, 0, 0, 0};
+  SP2_TRY(sc_state_upload(ctx, &st_outer, zero4, nullptr, (uint32_t)l, &hts));
+  void *d_dg; SP2_TRY(scratch(ctx, 8, (size_t)SC_MAX_ROUNDS * 64 + 64, &d_dg));
+  SP2_CUDA_OK(cudaMemcpyAsync(d_dg, tau_dg.data(), tau_dg.size(), cudaMemcpyHostToDevice, ctx->stream));
+  k_taus_from_digests<<<1, 64, 0, ctx->stream>>>(st_outer, (const unsigned char *)d_dg, l);
+  SP2_LAUNCH_CHECK();
+  SP2_TRY(sumcheck_cubic_enqueue(ctx, st_outer, (uint32_t)l, P->work[0], P->work[1], P->work[2]));
+  k_outer_to_inner<<<1, 64, 0, ctx->stream>>>(st_outer, st_inner, small, nry);
+  SP2_LAUNCH_CHECK();
+  mark(3);
+
+  // ---- eq(r_x) and poly_ABC (spartan.rs:320-321) ------------------------------------------------
+  fe *d_rx = P->work[0];                                                   // the sum-check consumed the tables
+  SP2_TRY(eq_table_dev(ctx, st_outer->r, (uint32_t)l, d_rx));
+  SP2_TRY(abc_dev(ctx, S, d_rx, &small[S_RJOINT], P->abc, nc));
+  mark(4);
+
+  // ---- inner sum-check: m+1 rounds over the virtual 2M tables (spartan.rs:330-404) ---------------
+  SP2_TRY(sumcheck_quad_enqueue(ctx, st_inner, (uint32_t)nry, P->abc, P->z, nc));
+  mark(5);
+
+  // ---- eval_W, PCS::prove (hyrax_pc.rs:387-478; ipa.rs:125-153) ----------------------------------
+  { void *chis; SP2_TRY(scratch(ctx, 12, ((size_t)4 << nvz) * sizeof(fe) + 64, &chis));
+    k_eval_w<<<1, 256, 0, ctx->stream>>>(st_inner, P->z + nv, (u32)num_extra, m, (fe *)chis, small);
+    SP2_LAUNCH_CHECK(); }
+  const fe *ry1 = st_inner->r + 1;
+  SP2_TRY(eq_table_dev(ctx, ry1 + nvr, (uint32_t)(m - nvr), P->Rtab));
+  std::vector<MsmJob> jobs;
+  MsmJob j;
+  if (nvr > 0) {
+    SP2_TRY(eq_table_dev(ctx, ry1, (uint32_t)nvr, P->Ltab));
+    SP2_TRY(hyrax_bind_dev(ctx, P->W, P->Ltab, rows, width, P->LZ));
+    k_dot<<<1, 256, 0, ctx->stream>>>(P->Ltab, P->blinds, rows, &small[S_RLZ]);
+    SP2_LAUNCH_CHECK();
+    memset(&j, 0, sizeof(j)); j.scalars = P->LZ; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = &small[S_RLZ];
+    jobs.push_back(j);                                                     // comm_LZ
+  } else {
+    SP2_CUDA_OK(cudaMemcpyAsync(P->LZ, P->W, width * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+    SP2_CUDA_OK(cudaMemcpyAsync(&small[S_RLZ], P->blinds, sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  k_dot<<<1, 256, 0, ctx->stream>>>(P->Rtab, P->dvec, width, &small[S_IP]);
+  SP2_LAUNCH_CHECK();
+  memset(&j, 0, sizeof(j)); j.scalars = P->dvec; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = &small[S_RDELTA];
+  jobs.push_back(j);                                                       // delta
+  memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = &small[S_EVALW];
+  j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = &small[S_BLIND_EVAL];
+  jobs.push_back(j);                                                       // comm_eval_W
+  memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = &small[S_IP];
+  j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = &small[S_RBETA];
+  jobs.push_back(j);                                                       // beta
+  aff *d_pts = P->points + rows;
+  SP2_TRY(msm_run(ctx, ck, jobs, d_pts));
+  mark(6);
+
+  // ---- results so far -> host -------------------------------------------------------------------
+  void *hp; SP2_TRY(pinned(ctx, 2 * sizeof(ScState) + 4096, &hp));
+  ScState *h_outer = (ScState *)hp, *h_inner = h_outer + 1;
+  uint64_t *h_small = (uint64_t *)(h_inner + 1), *h_pts = h_small + 4 * S_COUNT;
+  const size_t upto = offsetof(ScState, partial);
+  SP2_CUDA_OK(cudaMemcpyAsync(h_outer, st_outer, upto, cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(h_inner, st_inner, upto, cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(h_small, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(h_pts, d_pts, 4 * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                          // host sync 2
+  if (((uint32_t *)(h_small + 4 * S_ERR))[0] == 5) { cleanup(); return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "prove: 1 - r_y[0] = 0"); }
+  for (int i = 0; i < l; i++) {                                            // compressed: [c0, c2, c3] (univariate.rs:147-153)
+    memcpy(proof->outer_polys + 12 * i, &h_outer->polys[4 * i], 32);
+    memcpy(proof->outer_polys + 12 * i + 4, &h_outer->polys[4 * i + 2], 64);
+  }
+  memcpy(proof->claims_outer, h_outer->claims, 96);
+  for (int i = 0; i < nry; i++) {                                          // compressed: [c0, c2]
+    memcpy(proof->inner_polys + 8 * i, &h_inner->polys[4 * i], 32);
+    memcpy(proof->inner_polys + 8 * i + 4, &h_inner->polys[4 * i + 2], 32);
+  }
+  memcpy(proof->eval_W, h_small + 4 * S_EVALW, 32);
+  memcpy(proof->blind_eval_W, rnd->blind_eval_W, 32);
+  const uint64_t *comm_LZ, *p_delta, *p_ceval, *p_beta;
+  if (nvr > 0) { comm_LZ = h_pts; p_delta = h_pts + 8; p_ceval = h_pts + 16; p_beta = h_pts + 24; }
+  else { comm_LZ = proof->comm_W; p_delta = h_pts; p_ceval = h_pts + 8; p_beta = h_pts + 16; }
+  memcpy(proof->delta, p_delta, 64); memcpy(proof->beta, p_beta, 64);
+
+  // ---- transcript tail on the host: poly_com rows, IPA absorbs, r (hyrax_pc.rs:410; ipa.rs:134-153) ----
+  sp2h::Transcript t2((uint16_t)h_inner->ts.round, h_inner->ts.state);
+  t2.absorb_commitment("poly_com", proof->comm_W, rows);
+  t2.dom_sep("inner product argument (linear)");
+  t2.push("U", 1); t2.push_point(comm_LZ); t2.push_point(p_ceval);
+  t2.absorb_point("delta", p_delta);
+  t2.absorb_point("beta", p_beta);
+  uint8_t rdg[64];
+  t2.squeeze("r", rdg);
+  SP2_CUDA_OK(cudaMemcpyAsync(d_dg, rdg, 64, cudaMemcpyHostToDevice, ctx->stream));
+  k_ipa_finish<<<(unsigned)((width + 255) / 256), 256, 0, ctx->stream>>>((const unsigned char *)d_dg, P->LZ, P->dvec, width, P->zvec, small);
+  SP2_LAUNCH_CHECK();
+  mark(7);
+  SP2_CUDA_OK(cudaMemcpyAsync(proof->z_vec, P->zvec, width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(h_small, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                          // host sync 3
+  memcpy(proof->z_delta, h_small + 4 * S_ZDELTA, 32);
+  memcpy(proof->z_beta, h_small + 4 * S_ZBETA, 32);
+  if (phase_ms) {
+    for (int i = 0; i < 7; i++) cudaEventElapsedTime(&phase_ms[i], ev[i], ev[i + 1]);
+    cudaEventElapsedTime(&phase_ms[7], ev[0], ev[7]);
+  }
+  cleanup();
+  return SP2_OK;
+}
+
+}  // extern "C"

@@ -351,21 +351,26 @@ __device__ __forceinline__ void quad_finalize(ScState *st, int round1, int round
   SC_STAMP(6);
 }
 
+// `nvalid`: entries at index >= nvalid are not materialised and read as zero — the zero-suffix awareness of
+// the reference's MultilinearPolynomial{lo_eff, hi_eff} (multilinear.rs:36-43, 106-163; sumcheck.rs:136), used by
+// the Spartan inner sum-check whose virtual 2M-entry tables are non-zero only in the first M + num_extra slots
+// (spartan.rs:330-384 does that round by hand).
+__device__ __forceinline__ fe ldg_fe_valid(const fe *T, u64 idx, u64 nvalid) { return idx < nvalid ? ldg_fe(T + idx) : Fq::zero(); }
 template <bool FUSED>
-__device__ __forceinline__ void quad_body(fe *A, fe *B, u64 P, const fe &r, u64 first, u64 stride, fe (&x)[2]) {
+__device__ __forceinline__ void quad_body(fe *A, fe *B, u64 P, const fe &r, u64 first, u64 stride, u64 nvalid, fe (&x)[2]) {
   Fq::acc acc0 = Fq::acc_zero(), acci = Fq::acc_zero();
   for (u64 id = first; id < P; id += stride) {
     fe a0, a1, b0, b1;
     if (FUSED) {
-      const fe a00 = ldg_fe(A + id), a01 = ldg_fe(A + id + P), a10 = ldg_fe(A + id + 2 * P), a11 = ldg_fe(A + id + 3 * P);
-      const fe b00 = ldg_fe(B + id), b01 = ldg_fe(B + id + P), b10 = ldg_fe(B + id + 2 * P), b11 = ldg_fe(B + id + 3 * P);
+      const fe a00 = ldg_fe(A + id), a01 = ldg_fe(A + id + P), a10 = ldg_fe_valid(A, id + 2 * P, nvalid), a11 = ldg_fe_valid(A, id + 3 * P, nvalid);
+      const fe b00 = ldg_fe(B + id), b01 = ldg_fe(B + id + P), b10 = ldg_fe_valid(B, id + 2 * P, nvalid), b11 = ldg_fe_valid(B, id + 3 * P, nvalid);
       a0 = bind_pair(a00, a10, r); a1 = bind_pair(a01, a11, r);
       stg_fe(A + id, a0); stg_fe(A + id + P, a1);
       b0 = bind_pair(b00, b10, r); b1 = bind_pair(b01, b11, r);
       stg_fe(B + id, b0); stg_fe(B + id + P, b1);
     } else {
-      a0 = ldg_fe(A + id); a1 = ldg_fe(A + id + P);
-      b0 = ldg_fe(B + id); b1 = ldg_fe(B + id + P);
+      a0 = ldg_fe(A + id); a1 = ldg_fe_valid(A, id + P, nvalid);
+      b0 = ldg_fe(B + id); b1 = ldg_fe_valid(B, id + P, nvalid);
     }
     Fq::mul_acc(acc0, a0, b0);
     Fq::mul_acc(acci, Fq::sub(a1, a0), Fq::sub(b1, b0));
@@ -375,26 +380,28 @@ __device__ __forceinline__ void quad_body(fe *A, fe *B, u64 P, const fe &r, u64 
 
 template <bool FUSED>
 __global__ void __launch_bounds__(SC_THREADS, 2)
-k_quad_round(ScState *st, fe *A, fe *B, u64 P, int round1, int rounds) {
+k_quad_round(ScState *st, fe *A, fe *B, u64 P, int round1, int rounds, u64 nvalid) {
   __shared__ FinSmem sm;
   fe r;
   if (FUSED) r = ld_state(&st->r[round1 - 2]);
   fe x[2];
-  quad_body<FUSED>(A, B, P, r, (u64)blockIdx.x * SC_THREADS + threadIdx.x, (u64)gridDim.x * SC_THREADS, x);
+  quad_body<FUSED>(A, B, P, r, (u64)blockIdx.x * SC_THREADS + threadIdx.x, (u64)gridDim.x * SC_THREADS, nvalid, x);
   block_sum_fq<2>(x, sm.red);
   if (!publish_and_elect<2>(st, x, sm)) return;
   quad_finalize(st, round1, rounds, A, B, x, sm);
 }
 
 __global__ void __launch_bounds__(SC_TAIL_THREADS, 1)
-k_quad_tail(ScState *st, fe *A, fe *B, int round_first, int rounds) {
+k_quad_tail(ScState *st, fe *A, fe *B, int round_first, int rounds, u64 nvalid) {
   __shared__ FinSmem sm;
   for (int round1 = round_first; round1 <= rounds; round1++) {
     const u64 P = (u64)1 << (rounds - round1);
     fe x[2];
     SC_STAMP(0);
-    if (round1 > 1) quad_body<true>(A, B, P, ld_state(&st->r[round1 - 2]), threadIdx.x, blockDim.x, x);
-    else quad_body<false>(A, B, P, Fq::zero(), threadIdx.x, blockDim.x, x);
+    // only the first two launches can see unmaterialised entries; afterwards the bound table is dense
+    const u64 nv = round1 <= 2 ? nvalid : ~0ull;
+    if (round1 > 1) quad_body<true>(A, B, P, ld_state(&st->r[round1 - 2]), threadIdx.x, blockDim.x, nv, x);
+    else quad_body<false>(A, B, P, Fq::zero(), threadIdx.x, blockDim.x, nv, x);
     __syncthreads();
     block_sum_fq<2>(x, sm.red);
     quad_finalize(st, round1, rounds, A, B, x, sm);
@@ -483,19 +490,20 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
   return SP2_OK;
 }
 
-int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B) {
+int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid) {
   const unsigned target = (unsigned)ctx->num_sms * 2;
   for (uint32_t round1 = 1; round1 <= rounds; round1++) {
     const u64 P = (u64)1 << (rounds - round1);
     const u64 len_in = round1 > 1 ? 4 * P : 2 * P;
     if (len_in <= SC_TAIL_LEN) {
-      k_quad_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, A, B, (int)round1, (int)rounds);
+      k_quad_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, A, B, (int)round1, (int)rounds, nvalid);
       SP2_LAUNCH_CHECK();
       break;
     }
+    const u64 nv = round1 <= 2 ? nvalid : ~0ull;
     u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > target) nb = target;
-    if (round1 > 1) k_quad_round<true><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds);
-    else k_quad_round<false><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds);
+    if (round1 > 1) k_quad_round<true><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
+    else k_quad_round<false><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
     SP2_LAUNCH_CHECK();
   }
   return SP2_OK;
@@ -535,7 +543,7 @@ int32_t sp2_sumcheck_quad_prove_dev(sp2_ctx *ctx, const uint64_t *claim, uint32_
   if (rounds < 1 || rounds > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "sumcheck_quad: 1 <= num_rounds <= 40");
   ScState *st;
   SP2_TRY(sc_state_upload(ctx, &st, claim, nullptr, rounds, ts));
-  SP2_TRY(sumcheck_quad_enqueue(ctx, st, rounds, (fe *)dA, (fe *)dB));
+  SP2_TRY(sumcheck_quad_enqueue(ctx, st, rounds, (fe *)dA, (fe *)dB, ~0ull));
   return sc_state_download(ctx, st, ts, polys, 3, r, claims, 2, rounds);
 }
 

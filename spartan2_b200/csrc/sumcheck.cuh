@@ -32,6 +32,7 @@ int sc_state_upload(sp2_ctx *ctx, ScState **d_st, const uint64_t *claim, const u
 int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uint64_t *polys, int ncoef, uint64_t *r,
                       uint64_t *claims, int nclaims, uint32_t l);
 int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C);
-int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B);
+// nvalid: table entries at index >= nvalid are unmaterialised zeros (~0ull: dense tables)
+int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid);
 
 }  // namespace sp2

@@ -296,3 +296,86 @@ class HyraxPCS:
         out = np.zeros((r_len, 4), dtype=np.uint64)
         ctx.check(ctx.L.sp2_hyrax_bind(ctx.h, _p(poly), _p(L), C.c_uint64(L.shape[0]), C.c_uint64(r_len), _p(out)))
         return out
+
+
+class _ProofC(C.Structure):
+    _fields_ = [("num_rounds_x", C.c_uint64), ("num_rounds_y", C.c_uint64), ("num_comm_rows", C.c_uint64), ("num_cols", C.c_uint64)] + \
+               [(n, C.c_void_p) for n in ("comm_W", "outer_polys", "claims_outer", "inner_polys", "eval_W", "blind_eval_W", "delta", "beta",
+                                          "z_vec", "z_delta", "z_beta")]
+
+
+class _RandC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("blinds_W", "blind_eval_W", "d_vec", "r_delta", "r_beta")]
+
+
+class SpartanProof:
+    """Flat SpartanSNARK proof (include/spartan2_b200.h: sp2_spartan_proof)."""
+    FIELDS = ["comm_W", "outer_polys", "claims_outer", "inner_polys", "eval_W", "blind_eval_W", "delta", "beta", "z_vec", "z_delta", "z_beta"]
+
+    def __init__(self, l, nry, rows, num_cols):
+        z = lambda n, w=4: np.zeros((n, w), dtype=np.uint64)   # noqa: E731
+        self.l, self.nry, self.rows, self.num_cols = l, nry, rows, num_cols
+        self.comm_W = z(rows, 8); self.outer_polys = z(3 * l); self.claims_outer = z(3); self.inner_polys = z(2 * nry)
+        self.eval_W = z(1); self.blind_eval_W = z(1); self.delta = z(1, 8); self.beta = z(1, 8)
+        self.z_vec = z(num_cols); self.z_delta = z(1); self.z_beta = z(1)
+        self.phase_ms = None
+
+    def cview(self):
+        v = _ProofC(self.l, self.nry, self.rows, self.num_cols)
+        for f in self.FIELDS:
+            setattr(v, f, getattr(self, f).ctypes.data)
+        return v
+
+
+class SpartanPrepSNARK:
+    def __init__(self, ctx, h, comm):
+        self.ctx, self.h, self.comm = ctx, h, comm
+
+    def free(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.sp2_prep_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class SpartanSNARK:
+    """src/spartan.rs — prep_prove / prove on the device (setup = SplitR1CSShape + CommitmentKey uploads)."""
+
+    @staticmethod
+    def prep_prove(ctx, shape, ck, W_cached, blinds_cached, is_small=True):
+        W = _fe(W_cached); b = _fe(blinds_cached)
+        cached_len = shape.num_shared + shape.num_precommitted
+        if W.shape[0] != cached_len:
+            raise SpartanError(-3, "prep_prove expects shared + precommitted (%d) witness values" % cached_len)
+        rows = cached_len // ck.n
+        if b.shape[0] < rows:
+            raise SpartanError(-2, "one blind per commitment row")
+        comm = np.zeros((max(rows, 1), 8), dtype=np.uint64)
+        h = C.c_void_p()
+        Wp = W if W.shape[0] else np.zeros((1, 4), dtype=np.uint64)
+        bp = b if b.shape[0] else np.zeros((1, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_spartan_prep_prove(ctx.h, shape.h, ck.h, _p(Wp), _p(bp), C.c_int32(int(is_small)), _p(comm), C.byref(h)))
+        return SpartanPrepSNARK(ctx, h, comm[:rows])
+
+    @staticmethod
+    def prove(ctx, shape, ck, prep, vk_digest, public_values, W_rest, blinds_W, blind_eval_W, d_vec, r_delta, r_beta):
+        N, nv = shape.num_cons, shape.num_vars
+        l = N.bit_length() - 1; nry = nv.bit_length()
+        rows = nv // ck.n
+        P = SpartanProof(l, nry, rows, ck.n)
+        pv = P.cview()
+        arrs = [_fe(x) for x in (blinds_W, blind_eval_W, d_vec, r_delta, r_beta)]
+        rv = _RandC(*[a.ctypes.data for a in arrs])
+        dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
+        pub = _fe(public_values) if len(public_values) else np.zeros((1, 4), dtype=np.uint64)
+        Wr = _fe(W_rest) if W_rest is not None and len(W_rest) else np.zeros((1, 4), dtype=np.uint64)
+        ph = (C.c_float * 8)()
+        ctx.check(ctx.L.sp2_spartan_prove(ctx.h, shape.h, ck.h, prep.h, _p(dig), _p(pub), _p(Wr), C.byref(rv), C.byref(pv), ph))
+        P.phase_ms = dict(zip(["commit_transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck",
+                               "pcs_prove", "ipa_response", "total"], [float(x) for x in ph]))
+        return P

@@ -185,6 +185,10 @@ int32_t sp2_host_free(sp2_ctx *ctx, void *p);
  * values (ns) of the last multi-CTA cubic round: [-, election, finalize end, first CTA entry]     */
 int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out11);
 
+/* harness support: n pseudo-random T256 points (seeded multiples of the generator) for test/bench keys.
+ * (The reference derives its generators by hash-to-curve on the Rust side and ships them as bases.)        */
+int32_t sp2_test_points(sp2_ctx *ctx, uint64_t seed, uint32_t n, uint64_t *out_xy);
+
 /* ---- test hooks: the device field layer, element-wise (tests/test_gpu_field.py) ------------- */
 /* op: 0 mul, 1 add, 2 sub, 3 inv, 4 from_mont, 5 to_mont, 6 half; field: 0 = T256 scalar, 1 = T256 base */
 int32_t sp2_test_field_op(sp2_ctx *ctx, int32_t field, int32_t op, const uint64_t *a, const uint64_t *b,

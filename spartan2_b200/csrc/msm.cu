@@ -180,6 +180,33 @@ __global__ void __launch_bounds__(128) k_sum_rows(const fe *partial, u64 nparts,
   stg_fe(out + i, s);
 }
 
+
+// ---- harness support: n pseudo-random curve points s_i * G (no hash-to-curve on this side of the ABI; the
+// reference derives its generators in halo2curves, src/provider/traits.rs:205-249, and ships them as bases) ----
+__device__ __forceinline__ u64 splitmix64(u64 &x) { x += 0x9E3779B97F4A7C15ull; u64 z = x; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+__global__ void __launch_bounds__(64) k_test_points(u64 seed, u32 n, aff *out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // generator (3, 0x5a6dd32d...f02d) of T256 (verified there)
+  fe gx, gy;
+  const u32 GY[8] = {0x25b1f02du, 0x30b49549u, 0xa351bb3cu, 0xecd9d538u, 0xbe66600du, 0x4e97345cu, 0xf58708e6u, 0x5a6dd32du};
+#pragma unroll
+  for (int k = 0; k < 8; k++) { gx.v[k] = k == 0 ? 3u : 0u; gy.v[k] = GY[k]; }
+  aff g; g.x = Fp::to_mont(gx); g.y = Fp::to_mont(gy);
+  u64 st = seed ^ (0xD1B54A32D192ED03ull * (u64)(i + 1));
+  u32 k[8];
+#pragma unroll
+  for (int j = 0; j < 4; j++) { const u64 w = splitmix64(st); k[2 * j] = (u32)w; k[2 * j + 1] = (u32)(w >> 32); }
+  k[7] &= 0x7fffffffu; k[0] |= 1u;                   // 0 < k < group order
+  jac acc = jac_inf();
+  for (int b = 254; b >= 0; b--) {
+    acc = jac_dbl(acc);
+    if ((k[b >> 5] >> (b & 31)) & 1u) acc = jac_add_mixed(acc, g);
+  }
+  const aff a = jac_to_aff(acc);
+  stg_fe(&out[i].x, a.x); stg_fe(&out[i].y, a.y);
+}
+
 bool g_reduce_attr_set = false;
 
 }  // namespace
@@ -325,6 +352,17 @@ int32_t sp2_hyrax_bind(sp2_ctx *ctx, const uint64_t *poly, const uint64_t *L, ui
   SP2_CUDA_OK(cudaMemcpyAsync(d_L, L, rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
   SP2_TRY(hyrax_bind_dev(ctx, (const fe *)d_p, (const fe *)d_L, rows, r_len, (fe *)d_o));
   SP2_CUDA_OK(cudaMemcpyAsync(out, d_o, r_len * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return SP2_OK;
+}
+
+/* harness support: n pseudo-random T256 points (seeded multiples of the generator), affine, to the host */
+int32_t sp2_test_points(sp2_ctx *ctx, uint64_t seed, uint32_t n, uint64_t *out_xy) {
+  cudaSetDevice(ctx->device);
+  void *d; SP2_TRY(scratch(ctx, 0, (size_t)n * sizeof(aff) + 64, &d));
+  k_test_points<<<(n + 63) / 64, 64, 0, ctx->stream>>>(seed, n, (aff *)d);
+  SP2_LAUNCH_CHECK();
+  SP2_CUDA_OK(cudaMemcpyAsync(out_xy, d, (size_t)n * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return SP2_OK;
 }

@@ -63,6 +63,12 @@ class Context:
         self.check(self.L.sp2_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def test_points(self, n, seed=1):
+        """n pseudo-random T256 points (affine, Montgomery) for test/bench commitment keys."""
+        out = np.zeros((n, 8), dtype=np.uint64)
+        self.check(self.L.sp2_test_points(self.h, C.c_uint64(seed), C.c_uint32(n), _p(out)))
+        return out
+
     # -- raw memory ---------------------------------------------------------------------------
     def alloc(self, nbytes):
         return DeviceBuffer(self, nbytes)

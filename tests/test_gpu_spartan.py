@@ -60,3 +60,42 @@ def _run(ctx, orc, seed, lc, lv, width, num_public, rest_frac):
 ])
 def test_prove_bit_exact_and_verifies(ctx, orc, seed, lc, lv, width, npub, rest):
     _run(ctx, orc, seed, lc, lv, width, npub, rest)
+
+
+def test_sha256_circuit_prove(ctx, orc):
+    """The benchmark circuit itself (benches/sha256_spartan.rs:37-152) on a 64-byte message: 2 compressions,
+    N = M = 2^16, Hyrax width 2048, witness all bits (is_small = true, as the bench passes), key from the device
+    point generator (checked to be on the curve by the oracle)."""
+    import hashlib
+    import spartan2_b200 as sp
+    from spartan2_b200.frontend import Sha256Circuit
+    msg = bytes(range(64))
+    circ = Sha256Circuit(msg)
+    assert circ.digest == hashlib.sha256(msg).digest() and circ.is_satisfied()
+    width = 2048
+    pts = ctx.test_points(width + 3, seed=5)
+    assert all(orc.on_curve(pts[i:i + 1]) for i in (0, 1, 77, width + 2))
+    ck, h, ck_s, h_s = pts[:width], pts[width:width + 1], pts[width + 1:width + 2], pts[width + 2:width + 3]
+    A, B, Cm = circ.matrices()
+    W, X = circ.witness()
+    nv = circ.num_vars; rows = nv // width; cached_len = circ.num_precommitted; cached_rows = cached_len // width
+    rng = np.random.default_rng(64)
+    blinds = rand_fe(rng, rows); blind_eval = rand_fe(rng, 1); d_vec = rand_fe(rng, width); r_delta = rand_fe(rng, 1); r_beta = rand_fe(rng, 1)
+    vk = bytes(32)
+    S = sp.SplitR1CSShape(ctx, *circ.dims(), A, B, Cm)
+    K = sp.CommitmentKey(ctx, ck, h, ck_s, h_s)
+    prep = sp.SpartanSNARK.prep_prove(ctx, S, K, W[:cached_len], blinds[:cached_rows], is_small=True)
+    proof = sp.SpartanSNARK.prove(ctx, S, K, prep, vk, X, W[cached_len:], blinds, blind_eval, d_vec, r_delta, r_beta)
+    O = orc.Shape(*circ.dims(), A, B, Cm)
+    keys = orc.Keys(ck, h, ck_s, h_s)
+    comm_pre = orc.hyrax_commit(ck, h, W[:cached_len], blinds[:cached_rows], is_small=True)
+    assert np.array_equal(prep.comm, comm_pre)
+    oproof = orc.spartan_prove(O, keys, vk, X, W, comm_pre, orc.Rand(blinds, blind_eval, d_vec, r_delta, r_beta))
+    for f in sp.SpartanProof.FIELDS:
+        assert np.array_equal(getattr(proof, f).reshape(-1), getattr(oproof, f).reshape(-1)), f
+    vp = orc.Proof(proof.l, proof.nry, proof.rows, proof.num_cols)
+    for f in sp.SpartanProof.FIELDS:
+        getattr(vp, f)[...] = getattr(proof, f).reshape(getattr(vp, f).shape)
+    assert orc.spartan_verify(O, keys, vk, X, vp) == 0
+    sz = S.sizes()
+    assert sz["num_cons"] == 1 << 16 and sz["long_rows"] > 0 and sz["long_cols"] > 0

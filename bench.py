@@ -1,12 +1,15 @@
 #!/usr/bin/env python
-"""bench.py — the Spartan prover hot path on B200.
+"""bench.py — SpartanSNARK::prove of the SHA-256 circuit on B200 (BASELINE.json config 2).
 
   python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port, all host threads)
 
-One JSON line on stdout (rank 0).  A "step" is one pass of the prover hot path over one synthetic instance of
-the workload named in config.workload.  `value` = field-ops/s with inputs resident in HBM; `e2e` = the same
-through the C-ABI with HOST buffers (pinned), copies inside the timed region.
+One JSON line on stdout (rank 0).  A "step" is one `prove` (src/spartan.rs:219-466) of sha256_spartan on a 2 KiB
+all-zero message (benches/sha256_spartan.rs:167,200) after prep_prove, as the reference's bench times it (:224-244).
+`value` = field-ops/s with the witness and prep state resident in HBM (device timeline of the prove, CUDA events);
+`e2e` = the same prove through the C ABI from HOST buffers, wall clock, copies and host syncs included.
+field-op = one 256-bit modular multiplication-equivalent of the reference's algorithm, MSM work
+excluded from the count (its time is included in the step).
 """
 import argparse
 import json
@@ -23,13 +26,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "sha256_r1cs_prove_field_ops_per_sec"
 UNIT = "field-ops/s"
+WIDTH = 2048          # DEFAULT_COMMITMENT_WIDTH (src/lib.rs:63)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
 
 
@@ -84,29 +87,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------
-# workload: the two sum-checks of SpartanSNARK::prove at the 2 KiB SHA-256 shape (N = M = 2^20)
-# ------------------------------------------------------------------------------------------------
-class SumcheckWorkload:
-    """outer cubic sum-check over Az,Bz,Cz (2^l) + inner quadratic sum-check over (ABC, z) (2^m).
-    Algorithmic bytes / field-ops per SURVEY.md §8(d): cubic 368*T B and 7*T ops, quad 256*T B and 4*T ops."""
+class Workload:
+    """sha256_spartan: Sha256Circuit(vec![0u8; msg_len]) -> padded R1CS, witness, prover randomness (seeded)."""
 
-    def __init__(self, l, m, seed=0xDEADBEEF):
-        self.l, self.m = l, m
-        self.N, self.M = 1 << l, 1 << m
-        self.name = "spartan_sumchecks_N2^%d_M2^%d" % (l, m)
-        self.field_ops = 7 * self.N + 4 * self.M
-        self.bytes_cubic = 368 * self.N
-        self.bytes_quad = 256 * self.M
+    def __init__(self, msg_len, seed=0xDEADBEEF):
+        from spartan2_b200.frontend import Sha256Circuit
+        self.msg_len = msg_len
+        self.circ = c = Sha256Circuit(b"\x00" * msg_len, width=WIDTH)
+        self.name = "sha256_spartan_%dB_zero_message" % msg_len
+        self.A, self.B, self.C = c.matrices()
+        self.W, self.X = c.witness()
+        self.N, self.M = c.num_cons, c.num_vars
+        self.rows = self.M // WIDTH; self.cached_len = c.num_precommitted; self.cached_rows = self.cached_len // WIDTH
         rng = np.random.default_rng(seed)
-        self.taus = rand_fe(rng, l)
-        self.rng = rng
+        self.blinds = rand_fe(rng, self.rows); self.blind_eval = rand_fe(rng, 1); self.d_vec = rand_fe(rng, WIDTH)
+        self.r_delta = rand_fe(rng, 1); self.r_beta = rand_fe(rng, 1)
+        self.vk = bytes(32)
+        # general-coefficient entries (one modmul each in SpMV / ABC; everything else is adds)
+        is_gen = np.array([abs(v) != 1 for v in c.coef_values], dtype=bool)
+        gen = [int(is_gen[co].sum()) for (co, _, _) in c.raw]
+        self.nnz = sum(c.nnz); self.nnz_general = sum(gen)
+        N, M = self.N, self.M
+        # SURVEY.md §8(d): outer cubic 7N; eq table N; ABC 2N + general nnz; inner 4M + manual round 0 (3M);
+        # Hyrax bind M; incremental SpMV: general nnz of the filtered columns (bounded by nnz_general; counted as 0)
+        self.field_ops = 7 * N + N + 2 * N + self.nnz_general + 7 * M + M
+        self.bytes_outer = 368 * N
 
-    def host_tables(self, alloc):
-        A, B, C, X, Y = alloc((self.N, 4)), alloc((self.N, 4)), alloc((self.N, 4)), alloc((self.M, 4)), alloc((self.M, 4))
-        for t in (A, B, C, X, Y):
-            t[:] = rand_fe(self.rng, t.shape[0])
-        return A, B, C, X, Y
+    def describe(self):
+        c = self.circ
+        return {"workload": self.name, "num_cons": c.num_cons_unpadded, "N": self.N, "M": self.M, "nnz": self.nnz, "nnz_general": self.nnz_general,
+                "hyrax_rows": self.rows, "hyrax_width": WIDTH, "field_ops_per_step": self.field_ops,
+                "phases": ["commit_rest+transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck", "pcs_prove", "ipa_response"]}
 
 
 def run_cuda(args):
@@ -118,20 +129,16 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     ctx = sp.Context(local)
-    wl = SumcheckWorkload(args.log_n, args.log_n, seed=0xDEADBEEF + rank)
+    wl = Workload(args.msg_len, seed=0xDEADBEEF + rank)
     hbm_peak, peak_kind = peaks()
-    A, B, C, X, Y = wl.host_tables(ctx.pinned_empty)
-    zero = np.zeros((1, 4), dtype=np.uint64)
-    # pristine copies in HBM + working copies (the provers bind in place)
-    pr = [ctx.upload(t) for t in (A, B, C, X, Y)]
-    wk = [ctx.alloc(t.nbytes) for t in (A, B, C, X, Y)]
+    pts = ctx.test_points(WIDTH + 3, seed=7)
+    K = sp.CommitmentKey(ctx, pts[:WIDTH], pts[WIDTH:WIDTH + 1], pts[WIDTH + 1:WIDTH + 2], pts[WIDTH + 2:WIDTH + 3])
+    S = sp.SplitR1CSShape(ctx, *wl.circ.dims(), wl.A, wl.B, wl.C)
+    t0 = time.perf_counter()
+    prep = sp.SpartanSNARK.prep_prove(ctx, S, K, wl.W[:wl.cached_len], wl.blinds[:wl.cached_rows], is_small=True)
+    prep_ms = (time.perf_counter() - t0) * 1e3
+    W_rest = wl.W[wl.cached_len:]
     flush = ctx.alloc(512 << 20)                     # > 126 MB L2
-
-    def restore():
-        for d, s in zip(wk, pr):
-            d.copy_from(s)
-        ctx.check(ctx.L.sp2_dev_memset(ctx.h, flush.ptr, 0, 512 << 20))   # flush L2 between timed iterations
-        ctx.synchronize()
 
     def barrier():
         ctx.synchronize(); torch.cuda.synchronize()
@@ -139,68 +146,54 @@ def run_cuda(args):
             import torch.distributed as dist
             dist.barrier()
 
-    def step_device():
-        ts = sp.TranscriptState()
-        ctx.timer_start()
-        # device time of both sum-checks (kernels only; the tiny state download is after the timer)
-        sp.SumcheckProof.prove_cubic_with_three_inputs(ctx, zero, wl.taus, wk[0], wk[1], wk[2], ts)
-        t1 = ctx.timer_stop()
-        ctx.timer_start()
-        sp.SumcheckProof.prove_quad(ctx, zero, wl.m, wk[3], wk[4], ts)
-        t2 = ctx.timer_stop()
-        return t1, t2
-
-    def step_e2e():
-        ts = sp.TranscriptState()
+    def step():
+        ctx.check(ctx.L.sp2_dev_memset(ctx.h, flush.ptr, 0, 512 << 20))   # flush L2 between timed iterations
+        ctx.synchronize()
         t0 = time.perf_counter()
-        sp.SumcheckProof.prove_cubic_with_three_inputs(ctx, zero, wl.taus, A, B, C, ts)
-        sp.SumcheckProof.prove_quad(ctx, zero, wl.m, X, Y, ts)
-        return (time.perf_counter() - t0) * 1e3
+        proof = sp.SpartanSNARK.prove(ctx, S, K, prep, wl.vk, wl.X, W_rest, wl.blinds, wl.blind_eval, wl.d_vec, wl.r_delta, wl.r_beta)
+        wall = (time.perf_counter() - t0) * 1e3
+        return proof, wall
 
-    for _ in range(max(args.warmup, 3)):
-        restore(); step_device()
+    W_ = max(args.warmup, 3)
+    for _ in range(W_):
+        step()
     l0 = ctx.launch_count()
     sampler = ClockSampler(local); sampler.start()
     barrier()
-    t_c, t_q = [], []
+    dev, wall, phases = [], [], []
     for _ in range(args.steps):
-        restore()
-        a, b = step_device()
-        t_c.append(a); t_q.append(b)
-    barrier()
-    launches = ctx.launch_count() - l0
-    ms_dev = float(np.mean(t_c) + np.mean(t_q))
-    # e2e: host (pinned) tables -> H2D -> prove -> results back on the host, wall clock around the ABI calls
-    step_e2e()
-    barrier()
-    e2e_ms = float(np.mean([step_e2e() for _ in range(args.steps)]))
+        proof, w = step()
+        dev.append(proof.phase_ms["total"]); wall.append(w); phases.append(proof.phase_ms)
     barrier()
     clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    ms_dev, ms_wall = float(np.mean(dev)), float(np.mean(wall))
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms_dev, e2e_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_dev, ms_wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, e2e_ms = float(t[0]), float(t[1])
-    out = None
+        ms_dev, ms_wall = float(t[0]), float(t[1])
     if rank == 0:
-        ach = wl.bytes_cubic / (float(np.mean(t_c)) * 1e-3) / 1e9
+        ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
+        ach = wl.bytes_outer / (ph["outer_sumcheck"] * 1e-3) / 1e9
+        cfg = wl.describe()
+        cfg.update({"l2": "flushed between timed iterations (512 MiB memset)", "parallelism": "1 proof per GPU (replicas)" if world > 1 else "single GPU",
+                    "prep_prove_ms_untimed": prep_ms})
         out = {
             "metric": METRIC, "value": world * wl.field_ops / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32x8 (256-bit prime field, Montgomery)", "data": "synthetic",
-            "config": {"workload": wl.name, "phases": ["outer_sumcheck", "inner_sumcheck"], "l2": "flushed between timed iterations (512 MiB memset)",
-                       "field_ops_per_step": wl.field_ops, "replicas": world},
-            "e2e": {"value": world * wl.field_ops / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(A.nbytes * 3 + X.nbytes * 2), "d2h_bytes_per_step": int((wl.l * 4 + wl.l + 3 + wl.m * 3 + wl.m + 2) * 32)},
+            "warmup": W_, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 limbs (256-bit prime field, Montgomery)", "data": "synthetic", "config": cfg,
+            "e2e": {"value": world * wl.field_ops / (ms_wall * 1e-3), "unit": UNIT, "ms_per_step": ms_wall,
+                    "h2d_bytes_per_step": int(W_rest.nbytes + wl.X.nbytes + wl.d_vec.nbytes + wl.blinds.nbytes + 3 * 32 + 64 * 21),
+                    "d2h_bytes_per_step": int(sum(getattr(proof, f).nbytes for f in sp.SpartanProof.FIELDS))},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_cubic_round (outer sum-check, all rounds)", "achieved": ach, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "k_cubic_round/k_cubic_tail (outer sum-check, all %d rounds)" % proof.l, "achieved": ach, "peak": hbm_peak,
                          "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                         "ms": float(np.mean(t_c)), "algorithmic_bytes": wl.bytes_cubic},
-            "phase_ms": {"outer_sumcheck": float(np.mean(t_c)), "inner_sumcheck": float(np.mean(t_q))},
-            "clocks": clocks,
+                         "ms": ph["outer_sumcheck"], "algorithmic_bytes": wl.bytes_outer},
+            "phase_ms": ph, "prove_ms": ms_dev, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(sample_log_n=min(args.log_n, 16), threads=1)
+            out["cpu_baseline"] = cpu_prove(wl, pts, threads=1, steps=1, warmup=0)
         print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:
@@ -208,55 +201,55 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline(sample_log_n, threads, reps=1):
-    """The oracle port of the reference's CPU algorithm on a bounded sample of the same workload."""
+def cpu_prove(wl, pts, threads, steps, warmup):
+    """The oracle port of the reference's prover on the same workload (oracle/oracle.c, -march=native)."""
     from oracle import pyoracle as orc
     orc.lib(native=True)
     orc.set_threads(threads)
-    wl = SumcheckWorkload(sample_log_n, sample_log_n)
-    A, B, C, X, Y = wl.host_tables(lambda s: np.zeros(s, dtype=np.uint64))
-    zero = np.zeros((1, 4), dtype=np.uint64)
-    best = None
-    for _ in range(reps + 1):
-        t = orc.Transcript(b"bench")
+    O = orc.Shape(*wl.circ.dims(), wl.A, wl.B, wl.C)
+    keys = orc.Keys(pts[:WIDTH], pts[WIDTH:WIDTH + 1], pts[WIDTH + 1:WIDTH + 2], pts[WIDTH + 2:WIDTH + 3])
+    comm_pre = orc.hyrax_commit(pts[:WIDTH], pts[WIDTH:WIDTH + 1], wl.W[:wl.cached_len], wl.blinds[:wl.cached_rows], is_small=True)
+    rnd = orc.Rand(wl.blinds, wl.blind_eval, wl.d_vec, wl.r_delta, wl.r_beta)
+    times, ph = [], None
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.sumcheck_cubic_prove(zero, wl.taus, A, B, C, t)
-        orc.sumcheck_quad_prove(zero, wl.m, X, Y, t)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return {"value": wl.field_ops / best, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%s (oracle/oracle.c, -march=native, %d thread(s)), %.1f ms" % (wl.name, threads, best * 1e3)}
+        p = orc.spartan_prove(O, keys, wl.vk, wl.X, wl.W, comm_pre, rnd)
+        if i >= warmup:
+            times.append((time.perf_counter() - t0) * 1e3); ph = p.phase_ms
+    ms = float(np.mean(times))
+    return {"value": wl.field_ops / (ms * 1e-3), "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": ms,
+            "phase_ms": dict(zip(["commit_rest+transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck", "pcs_prove"], ph)),
+            "sample": "full workload %s, %d prove(s); oracle/oracle.c = C restatement of the reference's rayon prover (no Rust toolchain), OpenMP %d thread(s)" % (wl.name, steps, threads)}
+
+
+def oracle_points(orc, n, seed=7):
+    rng = np.random.default_rng(seed)
+    order = 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff
+    g = np.concatenate([orc.to_mont([3], orc.FP), orc.to_mont([0x5a6dd32df58708e64e97345cbe66600decd9d538a351bb3c30b4954925b1f02d], orc.FP)], axis=1)
+    deltas = [orc.scalar_mul(g, orc.to_mont([int.from_bytes(rng.bytes(32), "little") % order])) for _ in range(8)]
+    cur = orc.scalar_mul(g, orc.to_mont([int.from_bytes(rng.bytes(32), "little") % order]))
+    out = np.zeros((n, 8), dtype=np.uint64)
+    for i in range(n):
+        out[i] = cur[0]
+        cur = orc.point_add(cur, deltas[int(rng.integers(0, 8))])
+    return out
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import pyoracle as orc
     orc.lib(native=True)
     threads = orc.max_threads()
-    orc.set_threads(threads)
-    wl = SumcheckWorkload(args.log_n, args.log_n)
-    A, B, C, X, Y = wl.host_tables(lambda s: np.zeros(s, dtype=np.uint64))
-    zero = np.zeros((1, 4), dtype=np.uint64)
-
-    def step():
-        t = orc.Transcript(b"bench")
-        t0 = time.perf_counter()
-        orc.sumcheck_cubic_prove(zero, wl.taus, A, B, C, t)
-        orc.sumcheck_quad_prove(zero, wl.m, X, Y, t)
-        return (time.perf_counter() - t0) * 1e3
-    for _ in range(args.warmup):
-        step()
-    ms = float(np.mean([step() for _ in range(args.steps)]))
-    v = wl.field_ops / (ms * 1e-3)
+    wl = Workload(args.msg_len)
+    pts = oracle_points(orc, WIDTH + 3)
+    r = cpu_prove(wl, pts, threads, args.steps, args.warmup)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (256-bit prime field, Montgomery)",
-        "data": "synthetic", "config": {"workload": wl.name, "phases": ["outer_sumcheck", "inner_sumcheck"], "field_ops_per_step": wl.field_ops},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "full workload, oracle/oracle.c (C restatement of the reference's rayon prover; no Rust toolchain), OpenMP %d threads" % threads},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64x4 limbs (256-bit prime field, Montgomery)", "data": "synthetic", "config": wl.describe(), "phase_ms": r["phase_ms"],
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
@@ -266,7 +259,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--log-n", type=int, default=20, help="log2 of the padded constraint count (2 KiB SHA-256: 20)")
+    ap.add_argument("--msg-len", type=int, default=2048, help="SHA-256 message bytes (BASELINE config 2: 2048; config 1: 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

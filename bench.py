@@ -137,7 +137,10 @@ def run_cuda(args):
     t0 = time.perf_counter()
     prep = sp.SpartanSNARK.prep_prove(ctx, S, K, wl.W[:wl.cached_len], wl.blinds[:wl.cached_rows], is_small=True)
     prep_ms = (time.perf_counter() - t0) * 1e3
-    W_rest = wl.W[wl.cached_len:]
+    # the circuit allocates nothing in `synthesize` (benches/sha256_spartan.rs:140-148): the rest section is pure zero
+    # padding, which the ABI takes as NULL
+    assert not wl.W[wl.cached_len:].any()
+    W_rest = None
     flush = ctx.alloc(512 << 20)                     # > 126 MB L2
 
     def barrier():
@@ -184,7 +187,7 @@ def run_cuda(args):
             "warmup": W_, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 limbs (256-bit prime field, Montgomery)", "data": "synthetic", "config": cfg,
             "e2e": {"value": world * wl.field_ops / (ms_wall * 1e-3), "unit": UNIT, "ms_per_step": ms_wall,
-                    "h2d_bytes_per_step": int(W_rest.nbytes + wl.X.nbytes + wl.d_vec.nbytes + wl.blinds.nbytes + 3 * 32 + 64 * 21),
+                    "h2d_bytes_per_step": int(wl.X.nbytes + wl.d_vec.nbytes + wl.blinds.nbytes + 16 * 32 + 64 * 21),
                     "d2h_bytes_per_step": int(sum(getattr(proof, f).nbytes for f in sp.SpartanProof.FIELDS))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_cubic_round/k_cubic_tail (outer sum-check, all %d rounds)" % proof.l, "achieved": ach, "peak": hbm_peak,

@@ -135,8 +135,9 @@ int32_t sp2_msm(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *scalars, uint32_
  * (msm_small path); it does not change the result.                                               */
 int32_t sp2_hyrax_commit(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint64_t len, const uint64_t *blinds, uint64_t rows,
                          int32_t is_small, uint64_t *out_rows);
+/* device-resident variant: d_out_rows_jac receives rows JACOBIAN points (x, y, z: 12 limbs; z = 0 identity) */
 int32_t sp2_hyrax_commit_dev(sp2_ctx *ctx, const sp2_ck *ck, const void *d_v, uint64_t len, const void *d_blinds, uint64_t rows,
-                             void *d_out_rows);
+                             void *d_out_rows_jac);
 /* Replaces bind_with_delayed (hyrax_pc.rs:38-54): out[i] = sum_j L[j] * poly[j * r_len + i].      */
 int32_t sp2_hyrax_bind(sp2_ctx *ctx, const uint64_t *poly, const uint64_t *L, uint64_t rows, uint64_t r_len, uint64_t *out);
 
@@ -163,7 +164,8 @@ typedef struct { const uint64_t *blinds_W, *blind_eval_W, *d_vec, *r_delta, *r_b
 int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck, const uint64_t *W_cached,
                                const uint64_t *blinds_cached, int32_t is_small, uint64_t *comm_out, sp2_prep **out);
 void sp2_prep_free(sp2_prep *prep);
-/* Replaces SpartanSNARK::prove (src/spartan.rs:219-466).  W_rest: num_rest scalars (may be NULL when 0).
+/* Replaces SpartanSNARK::prove (src/spartan.rs:219-466).  W_rest: num_rest scalars, or NULL for an all-zero
+ * rest section (pure padding, as in the SHA-256 bench circuit whose `synthesize` allocates nothing).
  * phase_ms: optional 8 floats of device time (commit+transcript, matrix_vector_multiply, outer_sumcheck,
  * prepare_poly_ABC, inner_sumcheck, pcs_prove, ipa response, total).  DivisionByZero as spartan.rs:417.  */
 int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck, sp2_prep *prep, const uint8_t *vk_digest,

@@ -79,15 +79,89 @@ inline void limbs_to_be(const uint64_t c[4], uint8_t out[32]) {
   for (int i = 0; i < 32; i++) out[31 - i] = (uint8_t)(c[i >> 3] >> (8 * (i & 7)));
 }
 
+
+// ---- host base-field arithmetic (T256 Fp, Montgomery form): only to normalise the handful of Jacobian points
+// an MSM batch returns — a serial 256-bit inversion is ~15 us on a host core and ~130 us on a GPU thread ----
+inline void mont_mul(const uint64_t a[4], const uint64_t b[4], const uint64_t mod[4], uint64_t inv, uint64_t out[4]) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)a[j] * b[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+    const uint64_t m = t[0] * inv;
+    c = ((u128)m * mod[0] + t[0]) >> 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * mod[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  uint64_t d[4]; unsigned borrow = 0;
+  for (int i = 0; i < 4; i++) { u128 x = (u128)t[i] - mod[i] - borrow; d[i] = (uint64_t)x; borrow = (unsigned)((x >> 64) & 1); }
+  const bool ge = t[4] || !borrow;
+  for (int i = 0; i < 4; i++) out[i] = ge ? d[i] : t[i];
+}
+static const uint64_t FP_ONE[4] = {0x6ceca99e4e3b4ee9ULL, 0x818d4bd4cf18ce88ULL, 0xfffffffffffffffeULL, 0x00000000fffffffeULL};   // R mod p
+inline void fp_mul(const uint64_t a[4], const uint64_t b[4], uint64_t o[4]) { mont_mul(a, b, FP_MOD, FP_INV, o); }
+inline void fp_inv(const uint64_t a[4], uint64_t o[4]) {       // a^(p-2); inv(0) = 0
+  uint64_t e[4] = {FP_MOD[0] - 2, FP_MOD[1], FP_MOD[2], FP_MOD[3]};
+  uint64_t r[4]; memcpy(r, FP_ONE, 32);
+  for (int i = 255; i >= 0; i--) {
+    fp_mul(r, r, r);
+    if ((e[i >> 6] >> (i & 63)) & 1) fp_mul(r, a, r);
+  }
+  memcpy(o, r, 32);
+}
+// n Jacobian points (x,y,z: 12 limbs each) -> affine (x,y: 8 limbs each), identity (z = 0) -> all zero;
+// one inversion for the whole batch (Montgomery's trick)
+inline void batch_normalize(const uint64_t *jac, size_t n, uint64_t *aff) {
+  std::vector<uint64_t> pre(4 * (n + 1));
+  uint64_t acc[4]; memcpy(acc, FP_ONE, 32);
+  auto is_zero = [](const uint64_t *z) { return !(z[0] | z[1] | z[2] | z[3]); };
+  for (size_t i = 0; i < n; i++) {
+    memcpy(&pre[4 * i], acc, 32);
+    const uint64_t *z = jac + 12 * i + 8;
+    if (!is_zero(z)) fp_mul(acc, z, acc);
+  }
+  uint64_t inv[4]; fp_inv(acc, inv);
+  for (size_t i = n; i-- > 0;) {
+    const uint64_t *p = jac + 12 * i, *z = p + 8;
+    uint64_t *o = aff + 8 * i;
+    if (is_zero(z)) { memset(o, 0, 64); continue; }
+    uint64_t zi[4], zi2[4], zi3[4];
+    fp_mul(inv, &pre[4 * i], zi);
+    fp_mul(inv, z, inv);
+    fp_mul(zi, zi, zi2); fp_mul(zi2, zi, zi3);
+    fp_mul(p, zi2, o); fp_mul(p + 4, zi3, o + 4);
+  }
+}
+
 // ---- Keccak256Transcript --------------------------------------------------------------------------
 struct Transcript {
   uint16_t round = 0;
   uint8_t state[64];
   std::vector<uint8_t> buf;
 
-  static void updated_state(const uint8_t *in, size_t n, uint8_t out[64]) {    // keccak.rs:33-54
-    keccak256(in, n, 0x00, true, out);
-    keccak256(in, n, 0x01, true, out + 32);
+  // keccak.rs:33-54: K(in || 0x00) || K(in || 0x01).  The two messages share every full block of `in`: absorb
+  // those once, then fork the sponge for the two one-byte suffixes.
+  static void updated_state(const uint8_t *in, size_t n, uint8_t out[64]) {
+    uint64_t a[25]; memset(a, 0, sizeof(a));
+    const size_t full = n / 136;
+    for (size_t b = 0; b < full; b++) {
+      for (int i = 0; i < 17; i++) { uint64_t w; memcpy(&w, in + 136 * b + 8 * i, 8); a[i] ^= w; }
+      keccak_f(a);
+    }
+    const size_t rem = n - 136 * full;              // < 136 bytes left, then the suffix byte, then padding
+    for (int sfx = 0; sfx < 2; sfx++) {
+      uint64_t s[25]; memcpy(s, a, sizeof(s));
+      uint8_t blk[272]; memset(blk, 0, sizeof(blk));
+      memcpy(blk, in + 136 * full, rem);
+      blk[rem] = (uint8_t)sfx;
+      const size_t total = rem + 1, nb = total / 136 + 1;
+      blk[total] ^= 0x01; blk[136 * nb - 1] ^= 0x80;
+      for (size_t b = 0; b < nb; b++) {
+        for (int i = 0; i < 17; i++) { uint64_t w; memcpy(&w, blk + 136 * b + 8 * i, 8); s[i] ^= w; }
+        keccak_f(s);
+      }
+      memcpy(out + 32 * sfx, s, 32);
+    }
   }
   explicit Transcript(const char *label) {                                       // keccak.rs:57-68
     std::vector<uint8_t> in; const char *p = "NoTR"; in.insert(in.end(), p, p + 4); in.insert(in.end(), label, label + strlen(label));
@@ -111,6 +185,13 @@ struct Transcript {
     push(label, strlen(label));
     push("poly_commitment_begin", 21);
     for (size_t i = 0; i < rows; i++) push_point(rows_xy + 8 * i);
+    push("poly_commitment_end", 19);
+  }
+  // same framing from precomputed point bytes (64 per row)
+  void absorb_commitment_be(const char *label, const uint8_t *rows_be, size_t rows) {
+    push(label, strlen(label));
+    push("poly_commitment_begin", 21);
+    push(rows_be, 64 * rows);
     push("poly_commitment_end", 19);
   }
   // squeeze (keccak.rs:70-94): 64 uniform bytes; the caller reduces them mod p (on the device)

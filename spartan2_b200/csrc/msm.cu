@@ -7,19 +7,22 @@
 //   src/provider/pcs/hyrax_pc.rs:207-319  HyraxPCS::commit / commit_zeros (one Pedersen row per 2048)
 //   src/provider/pcs/hyrax_pc.rs:38-54    bind_with_delayed (LZ = L^T W)
 //
-// B200 design.  The commitment key is fixed at setup, so (like the reference's FixedBaseMul, but for
-// every base) the key upload precomputes table[w][i] = 2^(8w) * base_i in affine form: all 33 signed
-// byte-digit windows of all scalars then fall into ONE set of 128 buckets and the window-combining
-// Horner chain (256 serial doublings in the reference's loop, msm.rs:151-175) disappears.  Per MSM:
-//   accumulate: CTAs of 128 threads own 64 terms each; digits are counting-sorted by bucket in shared
-//               memory so that thread b walks only bucket b's entries (mixed adds, no atomics);
-//   reduce:     one CTA sums the per-CTA partial buckets, then sum_b b*B_b via 8 bit-plane tree sums
-//               and a 7-step Horner (instead of the 2*128 serial running-sum adds), then one inversion
-//               to affine.
+// B200 design: latency, not arithmetic, bounds these MSMs (2048 terms, 2 per proof on the critical path), so the
+// bucket method is dropped altogether.  The commitment key is fixed at setup and HBM is plentiful, so the key
+// upload precomputes, for EVERY base, the reference's FixedBaseMul table (msm.rs:651-689, which the reference
+// builds only for h and for <=64-wide keys): table[b][w][d] = d * 2^(8w) * base_b for the 33 signed byte-digit
+// windows and d = 1..128, affine (554 MB at 2051 bases).  An MSM is then a pure gather-and-sum of
+// <= 33 * n affine points: no buckets, no bucket reduction, no doublings.
+//   k_msm_gather: CTAs of 256 threads own 32 terms; digits are recoded once into shared memory, every thread
+//                 adds ~4 table entries (mixed Jacobian adds), then an 8-level shared-memory tree;
+//   k_msm_final:  one CTA per MSM sums the per-CTA partials (7-level tree) and emits ONE Jacobian point.
+// Normalisation to affine (one field inversion) is done by the caller on the host for the whole batch
+// (host_transcript.h: batch_normalize): ~15 us there vs ~130 us for a serial inversion on a GPU thread.
 // Many MSMs (Hyrax rows, the prover's blinded terms) are batched into one pair of launches.
 #include <string.h>
 #include "msm.cuh"
 #include "devutil.cuh"
+#include "host_transcript.h"
 
 using namespace sp2;
 
@@ -30,55 +33,60 @@ __device__ __forceinline__ void st_jac(jac *p, const jac &v) { stg_fe(&p->x, v.x
 __device__ __forceinline__ aff ld_aff_ro(const aff *p) { aff r; r.x = ldg_fe_ro(&p->x); r.y = ldg_fe_ro(&p->y); return r; }
 
 // ---- key precompute ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_ck_windows(const aff *bases, u32 nbase, jac *tmp) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nbase) return;
-  jac p = jac_from_aff(ld_aff_ro(bases + i));
-  for (int w = 0; w < MSM_NW; w++) {
-    st_jac(tmp + (size_t)w * nbase + i, p);
+// thread (b, w): the 128 multiples d * 2^(8w) * base_b, Jacobian, plus the running product of their Z's
+__global__ void __launch_bounds__(128) k_ck_multiples(const aff *bases, u32 nbase, jac *tmp, fe *pre) {
+  const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nbase * MSM_NW) return;
+  const u32 b = idx / MSM_NW, w = idx % MSM_NW;
+  jac p = jac_from_aff(ld_aff_ro(bases + b));
 #pragma unroll 1
-    for (int k = 0; k < MSM_C; k++) p = jac_dbl(p);
-  }
-}
-// batch normalisation (Montgomery's trick over the 33 windows of one base; cf. batch_normalize, msm.rs:669-676)
-__global__ void __launch_bounds__(128) k_ck_normalize(const jac *tmp, u32 nbase, aff *table) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nbase) return;
-  fe pre[MSM_NW];
+  for (u32 k = 0; k < 8 * w; k++) p = jac_dbl(p);
+  jac m = p;
   fe acc = Fp::one();
-  for (int w = 0; w < MSM_NW; w++) {
-    pre[w] = acc;
-    const fe z = ldg_fe(&tmp[(size_t)w * nbase + i].z);
-    if (!Fp::is_zero(z)) acc = Fp::mul(acc, z);
+  jac *out = tmp + (size_t)idx * MSM_ND;
+  fe *po = pre + (size_t)idx * (MSM_ND + 1);
+#pragma unroll 1
+  for (int d = 0; d < MSM_ND; d++) {
+    st_jac(out + d, m);
+    stg_fe(po + d, acc);
+    if (!Fp::is_zero(m.z)) acc = Fp::mul(acc, m.z);
+    m = jac_add(m, p);
   }
-  fe inv = Fp::inv(acc);
-  for (int w = MSM_NW - 1; w >= 0; w--) {
-    const jac p = ld_jac(tmp + (size_t)w * nbase + i);
+  stg_fe(po + MSM_ND, acc);     // (one spare slot per thread: total product)
+}
+// batch normalisation over the 128 multiples of one (b, w) (Montgomery's trick; cf. batch_normalize, msm.rs:669-676)
+__global__ void __launch_bounds__(128) k_ck_normalize(const jac *tmp, const fe *pre, u32 nbase, aff *table) {
+  const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nbase * MSM_NW) return;
+  const jac *in = tmp + (size_t)idx * MSM_ND;
+  const fe *pi = pre + (size_t)idx * (MSM_ND + 1);
+  aff *out = table + (size_t)idx * MSM_ND;
+  fe inv = Fp::inv(ldg_fe(pi + MSM_ND));
+#pragma unroll 1
+  for (int d = MSM_ND - 1; d >= 0; d--) {
+    const jac p = ld_jac(in + d);
     aff a;
     if (Fp::is_zero(p.z)) { a.x = Fp::zero(); a.y = Fp::zero(); }
-    else { a = jac_to_aff_with_inv(p, Fp::mul(inv, pre[w])); inv = Fp::mul(inv, p.z); }
-    stg_fe(&table[(size_t)w * nbase + i].x, a.x);
-    stg_fe(&table[(size_t)w * nbase + i].y, a.y);
+    else { a = jac_to_aff_with_inv(p, Fp::mul(inv, ldg_fe(pi + d))); inv = Fp::mul(inv, p.z); }
+    stg_fe(&out[d].x, a.x);
+    stg_fe(&out[d].y, a.y);
   }
 }
 
-// ---- accumulate --------------------------------------------------------------------------------
-struct AccSmem {
-  short dig[MSM_SLICE][MSM_NW + 1];
-  u32 bidx[MSM_SLICE];
-  u32 hist[MSM_NBUCKET + 2];
-  u32 cur[MSM_NBUCKET + 2];
-  unsigned short sorted[MSM_SLICE * MSM_NW];
+// ---- gather + sum ------------------------------------------------------------------------------
+struct GatherSmem {
+  short dig[MSM_TERMS][MSM_NW + 1];
+  u32 bidx[MSM_TERMS];
 };
 
-__global__ void __launch_bounds__(MSM_THREADS) k_msm_accumulate(const MsmJob *jobs, const aff *table, u32 nbase, jac *partial, u32 maxblk) {
-  __shared__ AccSmem sm;
+__global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, const aff *table, jac *partial, u32 maxblk) {
+  __shared__ GatherSmem sm;
+  __shared__ jac red[MSM_THREADS];
   const MsmJob job = jobs[blockIdx.y];
   if (blockIdx.x >= job.nblk) return;
   const u32 tid = threadIdx.x;
-  const u32 total = job.len + job.nextra, t0 = blockIdx.x * MSM_SLICE;
-  const u32 nterm = min((u32)MSM_SLICE, total - t0);
-  for (u32 i = tid; i < MSM_NBUCKET + 2; i += blockDim.x) sm.hist[i] = 0;
+  const u32 total = job.len + job.nextra, t0 = blockIdx.x * MSM_TERMS;
+  const u32 nterm = total > t0 ? min((u32)MSM_TERMS, total - t0) : 0;
   // signed byte digits of each scalar (to_repr() little-endian bytes, msm.rs:97-100; digit recoding :122-148)
   if (tid < nterm) {
     const u32 g = t0 + tid;
@@ -98,69 +106,40 @@ __global__ void __launch_bounds__(MSM_THREADS) k_msm_accumulate(const MsmJob *jo
     sm.dig[tid][32] = (short)carry;
   }
   __syncthreads();
-  if (tid < nterm) {
-    for (int w = 0; w < MSM_NW; w++) { const int d = sm.dig[tid][w]; if (d) atomicAdd(&sm.hist[d < 0 ? -d : d], 1u); }
-  }
-  __syncthreads();
-  if (tid == 0) { u32 run = 0; for (int b = 1; b <= MSM_NBUCKET + 1; b++) { const u32 c = sm.hist[b]; sm.hist[b] = run; sm.cur[b] = run; run += c; } }
-  __syncthreads();
-  if (tid < nterm) {
-    for (int w = 0; w < MSM_NW; w++) {
-      const int d = sm.dig[tid][w];
-      if (d) { const u32 pos = atomicAdd(&sm.cur[d < 0 ? -d : d], 1u); sm.sorted[pos] = (unsigned short)(tid | (w << 6) | (d < 0 ? 0x8000 : 0)); }
+  jac acc = jac_inf();
+  for (u32 p = tid; p < nterm * MSM_NW; p += MSM_THREADS) {
+    const u32 t = p / MSM_NW, w = p - t * MSM_NW;
+    const int d = sm.dig[t][w];
+    if (d) {
+      aff pt = ld_aff_ro(table + ((size_t)sm.bidx[t] * MSM_NW + w) * MSM_ND + (u32)((d < 0 ? -d : d) - 1));
+      if (d < 0) pt.y = Fp::neg(pt.y);
+      acc = jac_add_mixed(acc, pt);
     }
   }
+  red[tid] = acc;
   __syncthreads();
-  // thread `tid` owns bucket tid + 1
-  jac acc = jac_inf();
-  const u32 s = sm.hist[tid + 1], e = sm.hist[tid + 2];
-  for (u32 k = s; k < e; k++) {
-    const u32 code = sm.sorted[k];
-    const u32 t = code & 63u, w = (code >> 6) & 63u;
-    aff p = ld_aff_ro(table + (size_t)w * nbase + sm.bidx[t]);
-    if (code & 0x8000u) p.y = Fp::neg(p.y);
-    acc = jac_add_mixed(acc, p);
+#pragma unroll 1
+  for (u32 s = MSM_THREADS / 2; s >= 1; s >>= 1) {
+    if (tid < s) red[tid] = jac_add(red[tid], red[tid + s]);
+    __syncthreads();
   }
-  st_jac(partial + ((size_t)blockIdx.y * maxblk + blockIdx.x) * MSM_NBUCKET + tid, acc);
+  if (tid == 0) st_jac(partial + (size_t)blockIdx.y * maxblk + blockIdx.x, red[0]);
 }
 
-// ---- reduce ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MSM_RED_THREADS) k_msm_reduce(const MsmJob *jobs, const jac *partial, u32 maxblk, aff *out) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  jac *sm = (jac *)smem_raw;                       // MSM_RED_THREADS entries
-  __shared__ jac G[8];
+__global__ void __launch_bounds__(128) k_msm_final(const MsmJob *jobs, const jac *partial, u32 maxblk, jac *out) {
+  __shared__ jac red[128];
   const MsmJob job = jobs[blockIdx.x];
-  const u32 tid = threadIdx.x, b = tid & (MSM_NBUCKET - 1), part = tid >> 7;   // 4 parts
-  const jac *base = partial + (size_t)blockIdx.x * maxblk * MSM_NBUCKET;
+  const u32 tid = threadIdx.x;
   jac acc = jac_inf();
-  for (u32 blk = part; blk < job.nblk; blk += MSM_RED_THREADS / MSM_NBUCKET) acc = jac_add(acc, ld_jac(base + (size_t)blk * MSM_NBUCKET + b));
-  sm[tid] = acc;
+  for (u32 blk = tid; blk < job.nblk; blk += 128) acc = jac_add(acc, ld_jac(partial + (size_t)blockIdx.x * maxblk + blk));
+  red[tid] = acc;
   __syncthreads();
-  for (u32 s = 2; s >= 1; s >>= 1) {
-    if (part < s) sm[tid] = jac_add(sm[tid], sm[tid + s * MSM_NBUCKET]);
+#pragma unroll 1
+  for (u32 s = 64; s >= 1; s >>= 1) {
+    if (tid < s && tid + s < job.nblk) red[tid] = jac_add(red[tid], red[tid + s]);
     __syncthreads();
   }
-  const jac Bb = sm[b];                            // bucket b + 1
-  __syncthreads();
-  // sum_b (b+1) * B_b = sum_j 2^j * (sum over buckets whose index has bit j set)
-  for (int pass = 0; pass < 2; pass++) {
-    const int j = pass * 4 + (int)part;
-    sm[tid] = (((b + 1) >> j) & 1u) ? Bb : jac_inf();
-    __syncthreads();
-    for (u32 s = MSM_NBUCKET / 2; s >= 1; s >>= 1) {
-      if (b < s) sm[tid] = jac_add(sm[tid], sm[tid + s]);
-      __syncthreads();
-    }
-    if (b == 0) G[j] = sm[tid];
-    __syncthreads();
-  }
-  if (tid == 0) {
-    jac r = G[7];
-    for (int j = 6; j >= 0; j--) r = jac_add(jac_dbl(r), G[j]);
-    const aff a = jac_to_aff(r);
-    stg_fe(&out[blockIdx.x].x, a.x);
-    stg_fe(&out[blockIdx.x].y, a.y);
-  }
+  if (tid == 0) st_jac(out + blockIdx.x, red[0]);
 }
 
 // ---- Hyrax bind: LZ[i] = sum_j L[j] * W[j * r_len + i], delayed reduction (hyrax_pc.rs:38-54) ----
@@ -207,40 +186,31 @@ __global__ void __launch_bounds__(64) k_test_points(u64 seed, u32 n, aff *out) {
   stg_fe(&out[i].x, a.x); stg_fe(&out[i].y, a.y);
 }
 
-bool g_reduce_attr_set = false;
-
 }  // namespace
 
 namespace sp2 {
 
-int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, aff *d_out) {
+// d_out[njobs]: Jacobian results (the caller normalises on the host)
+int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, jac *d_out) {
   if (jobs_in.empty()) return SP2_OK;
-  const size_t CHUNK = 96;                         // bounds the partial-bucket scratch
-  if (!g_reduce_attr_set) {
-    SP2_CUDA_OK(cudaFuncSetAttribute(k_msm_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MSM_RED_THREADS * sizeof(jac))));
-    g_reduce_attr_set = true;
+  std::vector<MsmJob> jobs(jobs_in);
+  u32 maxblk = 1;
+  for (auto &j : jobs) {
+    if (j.base0 + j.len > ck->nbase) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "msm: more scalars than commitment-key bases");
+    j.nblk = (j.len + j.nextra + MSM_TERMS - 1) / MSM_TERMS;
+    if (j.nblk == 0) j.nblk = 1;
+    maxblk = std::max(maxblk, j.nblk);
   }
-  for (size_t c0 = 0; c0 < jobs_in.size(); c0 += CHUNK) {
-    const size_t nj = std::min(CHUNK, jobs_in.size() - c0);
-    std::vector<MsmJob> jobs(jobs_in.begin() + c0, jobs_in.begin() + c0 + nj);
-    u32 maxblk = 1;
-    for (auto &j : jobs) {
-      if (j.base0 + j.len > ck->nbase) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "msm: more scalars than commitment-key bases");
-      j.nblk = (j.len + j.nextra + MSM_SLICE - 1) / MSM_SLICE;
-      if (j.nblk == 0) j.nblk = 1;
-      maxblk = std::max(maxblk, j.nblk);
-    }
-    void *d_jobs, *d_partial;
-    SP2_TRY(scratch(ctx, 10, nj * sizeof(MsmJob), &d_jobs));
-    SP2_TRY(scratch(ctx, 11, nj * maxblk * MSM_NBUCKET * sizeof(jac), &d_partial));
-    // the job list is consumed asynchronously: stage it through a per-call copy (pageable -> the runtime
-    // copies it out before cudaMemcpyAsync returns)
-    SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), nj * sizeof(MsmJob), cudaMemcpyHostToDevice, ctx->stream));
-    k_msm_accumulate<<<dim3(maxblk, (unsigned)nj), MSM_THREADS, 0, ctx->stream>>>((const MsmJob *)d_jobs, ck->table, ck->nbase, (jac *)d_partial, maxblk);
-    SP2_LAUNCH_CHECK();
-    k_msm_reduce<<<(unsigned)nj, MSM_RED_THREADS, MSM_RED_THREADS * sizeof(jac), ctx->stream>>>((const MsmJob *)d_jobs, (const jac *)d_partial, maxblk, d_out + c0);
-    SP2_LAUNCH_CHECK();
-  }
+  const size_t nj = jobs.size();
+  void *d_jobs, *d_partial;
+  SP2_TRY(scratch(ctx, 10, nj * sizeof(MsmJob), &d_jobs));
+  SP2_TRY(scratch(ctx, 11, nj * maxblk * sizeof(jac), &d_partial));
+  // pageable source: the runtime stages it before cudaMemcpyAsync returns, so the local vector may die
+  SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), nj * sizeof(MsmJob), cudaMemcpyHostToDevice, ctx->stream));
+  k_msm_gather<<<dim3(maxblk, (unsigned)nj), MSM_THREADS, 0, ctx->stream>>>((const MsmJob *)d_jobs, ck->table, (jac *)d_partial, maxblk);
+  SP2_LAUNCH_CHECK();
+  k_msm_final<<<(unsigned)nj, 128, 0, ctx->stream>>>((const MsmJob *)d_jobs, (const jac *)d_partial, maxblk, d_out);
+  SP2_LAUNCH_CHECK();
   return SP2_OK;
 }
 
@@ -267,21 +237,24 @@ int32_t sp2_ck_upload(sp2_ctx *ctx, const uint64_t *bases_xy, uint32_t n, const 
   if (n == 0 || n > (1u << 24)) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "ck: bad number of bases");
   sp2_ck *ck = new sp2_ck();
   ck->ctx = ctx; ck->n = n; ck->nbase = n + 3;
-  aff *d_bases = nullptr; jac *tmp = nullptr;
+  aff *d_bases = nullptr; jac *tmp = nullptr; fe *pre = nullptr;
+  const size_t nent = (size_t)ck->nbase * MSM_NW * MSM_ND;       // table entries
   cudaError_t e = cudaMalloc((void **)&d_bases, (size_t)ck->nbase * sizeof(aff));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&tmp, (size_t)MSM_NW * ck->nbase * sizeof(jac));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&ck->table, (size_t)MSM_NW * ck->nbase * sizeof(aff));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&tmp, nent * sizeof(jac));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pre, (size_t)ck->nbase * MSM_NW * (MSM_ND + 1) * sizeof(fe));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ck->table, nent * sizeof(aff));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases, bases_xy, (size_t)n * sizeof(aff), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases + n, h_xy, sizeof(aff), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases + n + 1, ck_s_xy, sizeof(aff), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases + n + 2, h_s_xy, sizeof(aff), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
-    const unsigned blocks = (ck->nbase + 127) / 128;
-    k_ck_windows<<<blocks, 128, 0, ctx->stream>>>(d_bases, ck->nbase, tmp);
-    k_ck_normalize<<<blocks, 128, 0, ctx->stream>>>(tmp, ck->nbase, ck->table);
+    const unsigned blocks = (ck->nbase * MSM_NW + 127) / 128;
+    k_ck_multiples<<<blocks, 128, 0, ctx->stream>>>(d_bases, ck->nbase, tmp, pre);
+    k_ck_normalize<<<blocks, 128, 0, ctx->stream>>>(tmp, pre, ck->nbase, ck->table);
     ctx->launches += 2;
     e = cudaStreamSynchronize(ctx->stream);
   }
+  if (pre) cudaFree(pre);
   if (d_bases) cudaFree(d_bases);
   if (tmp) cudaFree(tmp);
   if (e != cudaSuccess) { if (ck->table) cudaFree(ck->table); delete ck; return set_cuda_error(ctx, e, "ck upload", __LINE__); }
@@ -302,20 +275,23 @@ int32_t sp2_msm(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *scalars, uint32_
   cudaSetDevice(ctx->device);
   if (n > ck->n) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "msm: more scalars than commitment-key bases");
   void *d_s, *d_o;
-  SP2_TRY(scratch(ctx, 0, (size_t)n * sizeof(fe) + 32, &d_s)); SP2_TRY(scratch(ctx, 1, sizeof(aff), &d_o));
+  SP2_TRY(scratch(ctx, 0, (size_t)n * sizeof(fe) + 32, &d_s)); SP2_TRY(scratch(ctx, 1, sizeof(jac), &d_o));
   if (n) SP2_CUDA_OK(cudaMemcpyAsync(d_s, scalars, (size_t)n * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
   MsmJob j; memset(&j, 0, sizeof(j));
   j.scalars = (const fe *)d_s; j.len = n; j.base0 = 0; j.nextra = 0;
-  SP2_TRY(msm_run(ctx, ck, std::vector<MsmJob>{j}, (aff *)d_o));
-  SP2_CUDA_OK(cudaMemcpyAsync(out_xy, d_o, sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_TRY(msm_run(ctx, ck, std::vector<MsmJob>{j}, (jac *)d_o));
+  uint64_t hj[12];
+  SP2_CUDA_OK(cudaMemcpyAsync(hj, d_o, sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  sp2h::batch_normalize(hj, 1, out_xy);
   return SP2_OK;
 }
 
 /* HyraxPCS::commit (hyrax_pc.rs:207-303; commit_zeros :305-319 is the all-zero v): rows of ck->n scalars,
- * out_rows[i] = sum_j v[i*n + j] * ck_j + blinds[i] * h.  d_v may be shorter than rows*n (last row ragged). */
+ * row i = sum_j v[i*n + j] * ck_j + blinds[i] * h.  d_v may be shorter than rows*n (last row ragged).
+ * d_out_rows_jac: rows Jacobian points (x, y, z: 12 limbs each; z = 0 is the identity) — normalise on the host. */
 int32_t sp2_hyrax_commit_dev(sp2_ctx *ctx, const sp2_ck *ck, const void *d_v, uint64_t len, const void *d_blinds, uint64_t rows,
-                             void *d_out_rows) {
+                             void *d_out_rows_jac) {
   cudaSetDevice(ctx->device);
   if (rows < (len + ck->n - 1) / ck->n) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "hyrax commit: too few rows for the vector");
   std::vector<MsmJob> jobs(rows);
@@ -325,7 +301,7 @@ int32_t sp2_hyrax_commit_dev(sp2_ctx *ctx, const sp2_ck *ck, const void *d_v, ui
     j.scalars = (const fe *)d_v + lo; j.len = hi > lo ? (u32)(hi - lo) : 0; j.base0 = 0;
     j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = (const fe *)d_blinds + i;
   }
-  return msm_run(ctx, ck, jobs, (aff *)d_out_rows);
+  return msm_run(ctx, ck, jobs, (jac *)d_out_rows_jac);
 }
 
 int32_t sp2_hyrax_commit(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint64_t len, const uint64_t *blinds, uint64_t rows,
@@ -334,12 +310,14 @@ int32_t sp2_hyrax_commit(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint
   cudaSetDevice(ctx->device);
   void *d_v, *d_b, *d_o;
   SP2_TRY(scratch(ctx, 0, len * sizeof(fe) + 32, &d_v)); SP2_TRY(scratch(ctx, 1, rows * sizeof(fe) + 32, &d_b));
-  SP2_TRY(scratch(ctx, 2, rows * sizeof(aff) + 32, &d_o));
+  SP2_TRY(scratch(ctx, 2, rows * sizeof(jac) + 32, &d_o));
   if (len) SP2_CUDA_OK(cudaMemcpyAsync(d_v, v, len * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(d_b, blinds, rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
   SP2_TRY(sp2_hyrax_commit_dev(ctx, ck, d_v, len, d_b, rows, d_o));
-  SP2_CUDA_OK(cudaMemcpyAsync(out_rows, d_o, rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint64_t> hj(rows * 12);
+  SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), d_o, rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  sp2h::batch_normalize(hj.data(), rows, out_rows);
   return SP2_OK;
 }
 

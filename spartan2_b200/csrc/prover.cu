@@ -38,16 +38,22 @@ struct sp2_prep {
   fe *z = nullptr, *abc = nullptr;   // num_cols each
   fe *blinds = nullptr;              // rows_total
   fe *small = nullptr;               // scalars scratch (see offsets below)
-  aff *points = nullptr;             // device points scratch: [rows_total comm rows | 4 PCS points]
+  jac *points = nullptr;             // device points scratch (Jacobian): [rows_total comm rows | 4 PCS points]
   fe *LZ = nullptr, *Ltab = nullptr, *Rtab = nullptr, *dvec = nullptr, *zvec = nullptr;
   std::vector<uint64_t> comm_cached; // host copy of the cached commitment rows (affine)
+  std::vector<uint8_t> comm_cached_be;  // their transcript bytes (x_BE || y_BE per row), computed once
+  fe *inbox = nullptr;               // per-prove host inputs, one H2D copy: [small slots | d_vec | blinds | X]
+  uint8_t *h_inbox = nullptr;        // pinned staging of the same layout (+ tau digests)
+  size_t inbox_bytes = 0;
+  cudaEvent_t ev[9] = {nullptr};
+  cudaEvent_t ev_r1 = nullptr, ev_inv = nullptr;
   std::vector<void *> owned;
 };
 
 namespace {
 
 enum SmallSlot { S_RJOINT = 0, S_EVALW = 1, S_EVALX = 2, S_RLZ = 3, S_IP = 4, S_BLIND_EVAL = 5, S_RDELTA = 6, S_RBETA = 7,
-                 S_ZDELTA = 8, S_ZBETA = 9, S_RIPA = 10, S_ERR = 11, S_COUNT = 16 };
+                 S_ZDELTA = 8, S_ZBETA = 9, S_RIPA = 10, S_ERR = 11, S_DENINV = 12, S_COUNT = 16 };
 
 // taus from the host-squeezed 64-byte digests: from_uniform (LE 512-bit mod p), into the sum-check state
 __global__ void k_taus_from_digests(ScState *st, const unsigned char *dg, int l) {
@@ -63,7 +69,20 @@ __global__ void k_taus_from_digests(ScState *st, const unsigned char *dg, int l)
   stg_fe(&st->taus[i], Fq::from_uniform(lo, hi));
 }
 
-__global__ void k_set_one(fe *p) { if (threadIdx.x == 0) stg_fe(p, Fq::one()); }
+// z[num_vars ..] = 1 | X   (spartan.rs:248-253)
+__global__ void k_z_tail(fe *ztail, const fe *X, u32 num_public) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) stg_fe(ztail, Fq::one());
+  if (i < num_public) stg_fe(ztail + 1 + i, ldg_fe(X + i));
+}
+// 1 / (1 - r_y[0]) as soon as the first inner challenge exists (side stream, overlaps the remaining inner rounds)
+__global__ void k_den_inv(const ScState *inner, fe *small) {
+  if (threadIdx.x == 0) {
+    const fe den = Fq::sub(Fq::one(), ldg_fe(&inner->r[0]));
+    if (Fq::is_zero(den)) ((u32 *)&small[S_ERR])[0] = 5;   // SpartanError::DivisionByZero
+    stg_fe(&small[S_DENINV], Fq::inv(den));
+  }
+}
 
 // outer -> inner: absorb(b"claims_outer", [A(rx), B(rx), C(rx)]); r = squeeze(b"r");
 // joint = A + r B + r^2 C (spartan.rs:305-316).  Initialises the inner sum-check state.
@@ -107,9 +126,7 @@ __global__ void __launch_bounds__(256) k_eval_w(const ScState *inner, const fe *
     for (int i = 0; i < skip; i++) common = Fq::mul(common, Fq::sub(Fq::one(), ldg_fe(ry1 + i)));
     const fe eval_X = Fq::mul(common, x[0]);
     const fe ry0 = ldg_fe(&inner->r[0]);
-    const fe den = Fq::sub(Fq::one(), ry0);
-    if (Fq::is_zero(den)) ((u32 *)&small[S_ERR])[0] = 5;   // SpartanError::DivisionByZero
-    const fe eval_W = Fq::mul(Fq::sub(ldg_fe(&inner->claims[1]), Fq::mul(ry0, eval_X)), Fq::inv(den));
+    const fe eval_W = Fq::mul(Fq::sub(ldg_fe(&inner->claims[1]), Fq::mul(ry0, eval_X)), ldg_fe(&small[S_DENINV]));
     stg_fe(&small[S_EVALX], eval_X);
     stg_fe(&small[S_EVALW], eval_W);
   }
@@ -164,6 +181,10 @@ void sp2_prep_free(sp2_prep *P) {
   cudaSetDevice(P->ctx->device);
   cudaStreamSynchronize(P->ctx->stream);
   for (void *p : P->owned) cudaFree(p);
+  if (P->h_inbox) cudaFreeHost(P->h_inbox);
+  for (auto &e : P->ev) if (e) cudaEventDestroy(e);
+  if (P->ev_r1) cudaEventDestroy(P->ev_r1);
+  if (P->ev_inv) cudaEventDestroy(P->ev_inv);
   delete P;
 }
 
@@ -189,10 +210,17 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
   A(palloc(P, &P->W, nv));
   for (int k = 0; k < 3; k++) { A(palloc(P, &P->cached[k], N)); A(palloc(P, &P->work[k], N)); }
   A(palloc(P, &P->z, nc)); A(palloc(P, &P->abc, nc));
-  A(palloc(P, &P->blinds, P->rows_total)); A(palloc(P, &P->small, (size_t)S_COUNT));
   A(palloc(P, &P->points, P->rows_total + 8));
   A(palloc(P, &P->LZ, width)); A(palloc(P, &P->Ltab, std::max<uint64_t>(P->rows_total, 1))); A(palloc(P, &P->Rtab, width));
-  A(palloc(P, &P->dvec, width)); A(palloc(P, &P->zvec, width));
+  A(palloc(P, &P->zvec, width));
+  P->inbox_bytes = ((size_t)S_COUNT + width + P->rows_total + S->num_public) * sizeof(fe);
+  { fe *ib = nullptr; A(palloc(P, &ib, (size_t)S_COUNT + width + P->rows_total + S->num_public)); P->inbox = ib; }
+  if (rc == SP2_OK && cudaMallocHost((void **)&P->h_inbox, P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64) != cudaSuccess) rc = set_error(ctx, SP2_ERR_CUDA, "cudaMallocHost");
+  if (rc == SP2_OK) {
+    P->small = P->inbox; P->dvec = P->inbox + S_COUNT; P->blinds = P->dvec + width;
+    for (auto &e : P->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&P->ev_r1, cudaEventDisableTiming); cudaEventCreateWithFlags(&P->ev_inv, cudaEventDisableTiming);
+  }
   if (rc != SP2_OK) { sp2_prep_free(P); return rc; }
   auto fail = [&](int r) { sp2_prep_free(P); return r; };
   cudaError_t e = cudaMemsetAsync(P->W, 0, nv * sizeof(fe), ctx->stream);
@@ -204,8 +232,14 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
     rc = sp2_hyrax_commit_dev(ctx, ck, P->W, P->cached_len, P->blinds, P->cached_rows, P->points);
     if (rc != SP2_OK) return fail(rc);
     P->comm_cached.resize(P->cached_rows * 8);
-    e = cudaMemcpyAsync(P->comm_cached.data(), P->points, P->cached_rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream);
+    std::vector<uint64_t> hj(P->cached_rows * 12);
+    e = cudaMemcpyAsync(hj.data(), P->points, P->cached_rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(set_cuda_error(ctx, e, "prep download", __LINE__));
+    sp2h::batch_normalize(hj.data(), P->cached_rows, P->comm_cached.data());
+    sp2h::Transcript tmp(0, (const uint8_t *)hj.data());           // (only used for its point encoder)
+    for (uint64_t i = 0; i < P->cached_rows; i++) tmp.push_point(P->comm_cached.data() + 8 * i);
+    P->comm_cached_be = tmp.buf;
   }
   // cached partial products: z = [W_cached | 0 ... 0]
   e = cudaMemsetAsync(P->z, 0, nc * sizeof(fe), ctx->stream);
@@ -238,45 +272,54 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   if (m - 1 - nvz < 0) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "prove: too many public inputs for the witness length");
   if (l > SC_MAX_ROUNDS || nry > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "prove: instance too large");
 
-  cudaEvent_t ev[9];
-  for (auto &x : ev) SP2_CUDA_OK(cudaEventCreate(&x));
+  cudaEvent_t *ev = P->ev;
   auto mark = [&](int i) { cudaEventRecord(ev[i], ctx->stream); };
-  auto cleanup = [&]() { for (auto &x : ev) cudaEventDestroy(x); };
+  auto cleanup = [&]() {};
   mark(0);
 
-  // ---- witness: rest section, blinds, randomness -------------------------------------------------
+  // ---- per-prove host inputs: one staged copy (randomness, blinds, public values) ------------------
   fe *small = P->small;
-  SP2_CUDA_OK(cudaMemsetAsync(small, 0, S_COUNT * sizeof(fe), ctx->stream));
-  if (S->num_rest) SP2_CUDA_OK(cudaMemcpyAsync(P->W + P->cached_len, W_rest, S->num_rest * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  if (rest_rows) SP2_CUDA_OK(cudaMemcpyAsync(P->blinds + P->cached_rows, rnd->blinds_W + 4 * P->cached_rows, rest_rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  SP2_CUDA_OK(cudaMemcpyAsync(&small[S_BLIND_EVAL], rnd->blind_eval_W, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  SP2_CUDA_OK(cudaMemcpyAsync(&small[S_RDELTA], rnd->r_delta, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  SP2_CUDA_OK(cudaMemcpyAsync(&small[S_RBETA], rnd->r_beta, sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
-  SP2_CUDA_OK(cudaMemcpyAsync(P->dvec, rnd->d_vec, width * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  { uint8_t *h = P->h_inbox;
+    memset(h, 0, S_COUNT * sizeof(fe));
+    memcpy(h + S_BLIND_EVAL * sizeof(fe), rnd->blind_eval_W, sizeof(fe));
+    memcpy(h + S_RDELTA * sizeof(fe), rnd->r_delta, sizeof(fe));
+    memcpy(h + S_RBETA * sizeof(fe), rnd->r_beta, sizeof(fe));
+    uint8_t *q = h + S_COUNT * sizeof(fe);
+    memcpy(q, rnd->d_vec, width * sizeof(fe)); q += width * sizeof(fe);
+    memcpy(q, rnd->blinds_W, rows * sizeof(fe)); q += rows * sizeof(fe);
+    if (S->num_public) memcpy(q, public_values, S->num_public * sizeof(fe));
+    SP2_CUDA_OK(cudaMemcpyAsync(P->inbox, h, P->inbox_bytes, cudaMemcpyHostToDevice, ctx->stream)); }
+  const fe *d_X = P->blinds + rows;
+  // rest section of the witness (NULL: all zero, e.g. pure padding as in the SHA-256 bench circuit)
+  if (S->num_rest) {
+    if (W_rest) SP2_CUDA_OK(cudaMemcpyAsync(P->W + P->cached_len, W_rest, S->num_rest * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    else SP2_CUDA_OK(cudaMemsetAsync(P->W + P->cached_len, 0, S->num_rest * sizeof(fe), ctx->stream));
+  }
   // z = W | 1 | X   (spartan.rs:248-253)
   SP2_CUDA_OK(cudaMemcpyAsync(P->z, P->W, nv * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
-  k_set_one<<<1, 32, 0, ctx->stream>>>(P->z + nv);
+  k_z_tail<<<(unsigned)(num_extra + 127) / 128, 128, 0, ctx->stream>>>(P->z + nv, d_X, (u32)S->num_public);
   SP2_LAUNCH_CHECK();
-  if (S->num_public) SP2_CUDA_OK(cudaMemcpyAsync(P->z + nv + 1, public_values, S->num_public * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
 
   // ---- transcript up to the taus (host; spartan.rs:226-264, bellpepper/r1cs.rs:422-431,491) -----
   sp2h::Transcript ts("SpartanSNARK");
   ts.absorb_bytes("vk", vk_digest, 32);
   ts.absorb_scalars("public_values", public_values, S->num_public);
   const uint64_t sh_rows = S->num_shared / width, pre_rows = S->num_precommitted / width;
-  if (sh_rows) ts.absorb_commitment("comm_W_shared", P->comm_cached.data(), sh_rows);
-  if (pre_rows) ts.absorb_commitment("comm_W_precommitted", P->comm_cached.data() + 8 * sh_rows, pre_rows);
+  if (sh_rows) ts.absorb_commitment_be("comm_W_shared", P->comm_cached_be.data(), sh_rows);
+  if (pre_rows) ts.absorb_commitment_be("comm_W_precommitted", P->comm_cached_be.data() + 64 * sh_rows, pre_rows);
   memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
   // commit the rest section (r1cs.rs:467-470: blind + commit / commit_zeros)
   if (rest_rows) {
     SP2_TRY(sp2_hyrax_commit_dev(ctx, ck, P->W + P->cached_len, S->num_rest, P->blinds + P->cached_rows, rest_rows, P->points + P->cached_rows));
-    SP2_CUDA_OK(cudaMemcpyAsync(proof->comm_W + 8 * P->cached_rows, P->points + P->cached_rows, rest_rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint64_t> hj(rest_rows * 12);
+    SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), P->points + P->cached_rows, rest_rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
     SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                        // host sync 1
+    sp2h::batch_normalize(hj.data(), rest_rows, proof->comm_W + 8 * P->cached_rows);
   }
   ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
   proof->num_rounds_x = l; proof->num_rounds_y = nry; proof->num_comm_rows = rows; proof->num_cols = width;
-  std::vector<uint8_t> tau_dg((size_t)l * 64);
-  for (int i = 0; i < l; i++) ts.squeeze("t", tau_dg.data() + 64 * i);
+  uint8_t *tau_dg = P->h_inbox + P->inbox_bytes;
+  for (int i = 0; i < l; i++) ts.squeeze("t", tau_dg + 64 * i);
   mark(1);
 
   // ---- Az, Bz, Cz (spartan.rs:271 -> multiply_vec_incremental_into) ------------------------------
@@ -292,7 +335,7 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   const uint64_t zero4[4] = {0, 0, 0, 0};
   SP2_TRY(sc_state_upload(ctx, &st_outer, zero4, nullptr, (uint32_t)l, &hts));
   void *d_dg; SP2_TRY(scratch(ctx, 8, (size_t)SC_MAX_ROUNDS * 64 + 64, &d_dg));
-  SP2_CUDA_OK(cudaMemcpyAsync(d_dg, tau_dg.data(), tau_dg.size(), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(d_dg, tau_dg, (size_t)l * 64, cudaMemcpyHostToDevice, ctx->stream));
   k_taus_from_digests<<<1, 64, 0, ctx->stream>>>(st_outer, (const unsigned char *)d_dg, l);
   SP2_LAUNCH_CHECK();
   SP2_TRY(sumcheck_cubic_enqueue(ctx, st_outer, (uint32_t)l, P->work[0], P->work[1], P->work[2]));
@@ -307,8 +350,13 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   mark(4);
 
   // ---- inner sum-check: m+1 rounds over the virtual 2M tables (spartan.rs:330-404) ---------------
-  SP2_TRY(sumcheck_quad_enqueue(ctx, st_inner, (uint32_t)nry, P->abc, P->z, nc));
+  SP2_TRY(sumcheck_quad_enqueue(ctx, st_inner, (uint32_t)nry, P->abc, P->z, nc, P->ev_r1));
+  SP2_CUDA_OK(cudaStreamWaitEvent(ctx->side, P->ev_r1, 0));
+  k_den_inv<<<1, 32, 0, ctx->side>>>(st_inner, small);
+  SP2_LAUNCH_CHECK();
+  SP2_CUDA_OK(cudaEventRecord(P->ev_inv, ctx->side));
   mark(5);
+  SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_inv, 0));
 
   // ---- eval_W, PCS::prove (hyrax_pc.rs:387-478; ipa.rs:125-153) ----------------------------------
   { void *chis; SP2_TRY(scratch(ctx, 12, ((size_t)4 << nvz) * sizeof(fe) + 64, &chis));
@@ -339,20 +387,22 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = &small[S_IP];
   j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = &small[S_RBETA];
   jobs.push_back(j);                                                       // beta
-  aff *d_pts = P->points + rows;
+  jac *d_pts = P->points + rows;
   SP2_TRY(msm_run(ctx, ck, jobs, d_pts));
   mark(6);
 
   // ---- results so far -> host -------------------------------------------------------------------
   void *hp; SP2_TRY(pinned(ctx, 2 * sizeof(ScState) + 4096, &hp));
   ScState *h_outer = (ScState *)hp, *h_inner = h_outer + 1;
-  uint64_t *h_small = (uint64_t *)(h_inner + 1), *h_pts = h_small + 4 * S_COUNT;
+  uint64_t *h_small = (uint64_t *)(h_inner + 1), *h_jac = h_small + 4 * S_COUNT;
+  uint64_t h_pts[32];
   const size_t upto = offsetof(ScState, partial);
   SP2_CUDA_OK(cudaMemcpyAsync(h_outer, st_outer, upto, cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(h_inner, st_inner, upto, cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(h_small, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
-  SP2_CUDA_OK(cudaMemcpyAsync(h_pts, d_pts, 4 * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(h_jac, d_pts, 4 * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                          // host sync 2
+  sp2h::batch_normalize(h_jac, jobs.size(), h_pts);
   if (((uint32_t *)(h_small + 4 * S_ERR))[0] == 5) { cleanup(); return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "prove: 1 - r_y[0] = 0"); }
   for (int i = 0; i < l; i++) {                                            // compressed: [c0, c2, c3] (univariate.rs:147-153)
     memcpy(proof->outer_polys + 12 * i, &h_outer->polys[4 * i], 32);
@@ -372,7 +422,10 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
 
   // ---- transcript tail on the host: poly_com rows, IPA absorbs, r (hyrax_pc.rs:410; ipa.rs:134-153) ----
   sp2h::Transcript t2((uint16_t)h_inner->ts.round, h_inner->ts.state);
-  t2.absorb_commitment("poly_com", proof->comm_W, rows);
+  t2.push("poly_com", 8); t2.push("poly_commitment_begin", 21);
+  t2.push(P->comm_cached_be.data(), P->comm_cached_be.size());
+  for (uint64_t i = P->cached_rows; i < rows; i++) t2.push_point(proof->comm_W + 8 * i);
+  t2.push("poly_commitment_end", 19);
   t2.dom_sep("inner product argument (linear)");
   t2.push("U", 1); t2.push_point(comm_LZ); t2.push_point(p_ceval);
   t2.absorb_point("delta", p_delta);

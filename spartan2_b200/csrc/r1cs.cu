@@ -135,19 +135,27 @@ __global__ void __launch_bounds__(256) k_abc(AbcArgs a, u32 ncols, const fe *rx,
   }
   stg_fe(out + col, res);
 }
-__global__ void __launch_bounds__(256) k_abc_long(AbcArgs a, const u32 *long_cols, const fe *rx, const fe *r, fe *out) {
-  __shared__ fe red[3 * 32];
-  const u32 col = long_cols[blockIdx.x];
+// long columns: one CTA per chunk of ABC_CHUNK entries of one matrix, then one warp per long column
+__global__ void __launch_bounds__(256) k_abc_long_chunks(AbcArgs a, const uint4_ *chunks, const fe *rx, fe *partial) {
+  __shared__ fe red[32];
+  const uint4_ c = chunks[blockIdx.x];
+  fe s[1] = {Fq::zero()};
+  for (u32 i = c.start + threadIdx.x; i < c.end; i += blockDim.x) accum_entry(s[0], a.ent[c.k][i], rx, a.dict[c.k]);
+  block_sum_fq<1>(s, red);
+  if (threadIdx.x == 0) stg_fe(partial + blockIdx.x, s[0]);
+}
+__global__ void __launch_bounds__(32) k_abc_long_finish(const u32 *long_cols, const u32 *chunk_first, const fe *partial, const fe *r, fe *out) {
+  const u32 lc = blockIdx.x;
   fe s[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    s[k] = Fq::zero();
-    for (u32 i = a.ptr[k][col] + threadIdx.x, e = a.ptr[k][col + 1]; i < e; i += blockDim.x) accum_entry(s[k], a.ent[k][i], rx, a.dict[k]);
+    fe v = Fq::zero();
+    for (u32 c = chunk_first[3 * lc + k] + threadIdx.x; c < chunk_first[3 * lc + k + 1]; c += 32) v = Fq::add(v, ldg_fe(partial + c));
+    s[k] = warp_sum_fq(v);
   }
-  block_sum_fq<3>(s, red);
   if (threadIdx.x == 0) {
     const fe rr = ldg_fe_ro(r);
-    stg_fe(out + col, Fq::add(s[0], Fq::mul(rr, Fq::add(s[1], Fq::mul(rr, s[2])))));
+    stg_fe(out + long_cols[lc], Fq::add(s[0], Fq::mul(rr, Fq::add(s[1], Fq::mul(rr, s[2])))));
   }
 }
 
@@ -179,7 +187,11 @@ int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe 
   k_abc<<<(ncols + 255) / 256, 256, 0, ctx->stream>>>(a, ncols, d_rx, d_r, d_out);
   SP2_LAUNCH_CHECK();
   if (S->nlong_cols) {
-    k_abc_long<<<S->nlong_cols, 256, 0, ctx->stream>>>(a, S->long_cols, d_rx, d_r, d_out);
+    if (S->nchunks) {
+      k_abc_long_chunks<<<S->nchunks, 256, 0, ctx->stream>>>(a, S->chunks, d_rx, S->chunk_partial);
+      SP2_LAUNCH_CHECK();
+    }
+    k_abc_long_finish<<<S->nlong_cols, 32, 0, ctx->stream>>>(S->long_cols, S->chunk_first, S->chunk_partial, d_r, d_out);
     SP2_LAUNCH_CHECK();
   }
   return SP2_OK;
@@ -209,6 +221,7 @@ int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpa
   const uint32_t *ptrs[3] = {indptrA, indptrB, indptrC};
   const u32 col_min = (u32)(num_shared + num_precommitted);
   std::vector<u32> coldeg(S->num_cols, 0);
+  std::vector<u32> tptr[3];
   int rc = SP2_OK;
   for (int k = 0; k < 3 && rc == SP2_OK; k++) {
     const size_t nnz = ptrs[k][num_cons];
@@ -240,6 +253,7 @@ int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpa
     { std::vector<u32> cur(ht.ptr.begin(), ht.ptr.end() - 1);
       for (size_t row = 0; row < num_cons; row++)
         for (u32 e = ptrs[k][row]; e < ptrs[k][row + 1]; e++) ht.ent[cur[inds[k][e]]++] = make_uint2((u32)row, cid[e]); }
+    tptr[k] = ht.ptr;
     mark_long(hm); mark_long(hf);
     rc = upload_matrix(S, hm, &S->M[k]);
     if (rc == SP2_OK) rc = upload_matrix(S, ht, &S->T[k]);
@@ -254,6 +268,24 @@ int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpa
     else {
       S->owned.push_back(S->long_cols);
       if (!lc.empty()) cudaMemcpy(S->long_cols, lc.data(), lc.size() * 4, cudaMemcpyHostToDevice);
+    }
+    std::vector<uint4_> ch; std::vector<u32> first;
+    for (size_t i = 0; i < lc.size(); i++)
+      for (int k = 0; k < 3; k++) {
+        first.push_back((u32)ch.size());
+        for (u32 s0 = tptr[k][lc[i]], e0 = tptr[k][lc[i] + 1]; s0 < e0; s0 += ABC_CHUNK) ch.push_back(uint4_{(u32)k, s0, std::min(e0, s0 + ABC_CHUNK), 0});
+      }
+    first.push_back((u32)ch.size());
+    S->nchunks = (u32)ch.size();
+    if (rc == SP2_OK) {
+      cudaError_t e2 = cudaMalloc((void **)&S->chunks, ch.size() * sizeof(uint4_) + 32);
+      if (e2 == cudaSuccess) { S->owned.push_back(S->chunks); e2 = cudaMalloc((void **)&S->chunk_first, first.size() * 4 + 32); }
+      if (e2 == cudaSuccess) { S->owned.push_back(S->chunk_first); e2 = cudaMalloc((void **)&S->chunk_partial, ch.size() * sizeof(fe) + 32); }
+      if (e2 == cudaSuccess) {
+        S->owned.push_back(S->chunk_partial);
+        if (!ch.empty()) cudaMemcpy(S->chunks, ch.data(), ch.size() * sizeof(uint4_), cudaMemcpyHostToDevice);
+        cudaMemcpy(S->chunk_first, first.data(), first.size() * 4, cudaMemcpyHostToDevice);
+      } else rc = set_cuda_error(ctx, e2, "cudaMalloc", __LINE__);
     }
   }
   if (rc != SP2_OK) { for (void *p : S->owned) cudaFree(p); delete S; return rc; }

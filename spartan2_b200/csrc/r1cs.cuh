@@ -23,6 +23,8 @@ struct DevMatrix {
   u32 nlong = 0;
 };
 constexpr u32 LONG_SEG = 48;
+constexpr u32 ABC_CHUNK = 2048;
+struct uint4_ { u32 k, start, end, pad; };
 
 }  // namespace sp2
 
@@ -34,6 +36,10 @@ struct sp2_shape {
   sp2::DevMatrix T[3];                       // transposes (column-major) for bind_and_prepare_poly_ABC
   sp2::DevMatrix F[3];                       // row-major, columns >= num_shared + num_precommitted only (FilteredSpmv)
   sp2::u32 *long_cols = nullptr; sp2::u32 nlong_cols = 0;   // columns whose A+B+C degree exceeds LONG_SEG
+  // long columns (the constant-one column of SHA-256 has ~10^6 entries) are cut into chunks of ABC_CHUNK entries,
+  // one CTA each: chunk = (matrix, first entry, last entry); chunk_first[3*lc + k] .. chunk_first[3*lc + k + 1]
+  // are the chunks of long column lc in matrix k
+  sp2::uint4_ *chunks = nullptr; sp2::u32 nchunks = 0; sp2::u32 *chunk_first = nullptr; sp2::fe *chunk_partial = nullptr;
   std::vector<void *> owned;
   uint64_t nnz_total = 0, nnz_general = 0;
 };

@@ -490,7 +490,8 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
   return SP2_OK;
 }
 
-int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid) {
+int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first) {
+  bool recorded = false;
   const unsigned target = (unsigned)ctx->num_sms * 2;
   for (uint32_t round1 = 1; round1 <= rounds; round1++) {
     const u64 P = (u64)1 << (rounds - round1);
@@ -498,12 +499,14 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
     if (len_in <= SC_TAIL_LEN) {
       k_quad_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, A, B, (int)round1, (int)rounds, nvalid);
       SP2_LAUNCH_CHECK();
+      if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
       break;
     }
     const u64 nv = round1 <= 2 ? nvalid : ~0ull;
     u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > target) nb = target;
     if (round1 > 1) k_quad_round<true><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
     else k_quad_round<false><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
+    if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
     SP2_LAUNCH_CHECK();
   }
   return SP2_OK;
@@ -543,7 +546,7 @@ int32_t sp2_sumcheck_quad_prove_dev(sp2_ctx *ctx, const uint64_t *claim, uint32_
   if (rounds < 1 || rounds > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "sumcheck_quad: 1 <= num_rounds <= 40");
   ScState *st;
   SP2_TRY(sc_state_upload(ctx, &st, claim, nullptr, rounds, ts));
-  SP2_TRY(sumcheck_quad_enqueue(ctx, st, rounds, (fe *)dA, (fe *)dB, ~0ull));
+  SP2_TRY(sumcheck_quad_enqueue(ctx, st, rounds, (fe *)dA, (fe *)dB, ~0ull, nullptr));
   return sc_state_download(ctx, st, ts, polys, 3, r, claims, 2, rounds);
 }
 

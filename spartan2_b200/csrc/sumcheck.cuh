@@ -33,6 +33,7 @@ int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uin
                       uint64_t *claims, int nclaims, uint32_t l);
 int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C);
 // nvalid: table entries at index >= nvalid are unmaterialised zeros (~0ull: dense tables)
-int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid);
+// after_first (optional): recorded once the launch that produces r[0] has been enqueued
+int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first);
 
 }  // namespace sp2

@@ -379,9 +379,9 @@ class SpartanSNARK:
         rv = _RandC(*[a.ctypes.data for a in arrs])
         dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
         pub = _fe(public_values) if len(public_values) else np.zeros((1, 4), dtype=np.uint64)
-        Wr = _fe(W_rest) if W_rest is not None and len(W_rest) else np.zeros((1, 4), dtype=np.uint64)
+        Wr = _fe(W_rest) if W_rest is not None and len(W_rest) else None      # None: all-zero rest section
         ph = (C.c_float * 8)()
-        ctx.check(ctx.L.sp2_spartan_prove(ctx.h, shape.h, ck.h, prep.h, _p(dig), _p(pub), _p(Wr), C.byref(rv), C.byref(pv), ph))
+        ctx.check(ctx.L.sp2_spartan_prove(ctx.h, shape.h, ck.h, prep.h, _p(dig), _p(pub), _p(Wr) if Wr is not None else None, C.byref(rv), C.byref(pv), ph))
         P.phase_ms = dict(zip(["commit_transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck",
                                "pcs_prove", "ipa_response", "total"], [float(x) for x in ph]))
         return P

@@ -249,40 +249,52 @@ struct Fq : Field<FqParams> {
 // Fp: generic modulus (T256 base field), CIOS Montgomery multiplication
 // ------------------------------------------------------------------------------------------
 struct Fp : Field<FpParams> {
+  // Montgomery multiplication = 256x256 wide product (IMAD.WIDE chains, shared with Fq) + word-by-word REDC that
+  // exploits the shape of the T256 base modulus: p = 2^256 - 2^224 + 2^192 + 2^128 + c (c < 2^128), i.e. limbs
+  // [p0,p1,p2,p3, 1, 0, 1, 2^32-1].  Per 32-bit round only m*p0..p3 are real multiplications (4 IMAD.WIDE, split
+  // into an even and an odd carry chain); the upper limbs are m<<128, m<<192 and (m<<256) - (m<<224): adds/subs.
+  // (The previous 32-bit CIOS used mad.hi, which SASS implements as the slow IMAD.HI.)
   SP2_HD static fe mul(const fe &a, const fe &b) {
-    u32 t[10];
+    u32 w[16];
+    mul_wide(w, a, b);
+    u32 t[18];
 #pragma unroll
-    for (int i = 0; i < 10; i++) t[i] = 0;
+    for (int i = 0; i < 16; i++) t[i] = w[i];
+    t[16] = 0; t[17] = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const u32 bi = b.v[i];
-      t[0] = mad_lo_cc(a.v[0], bi, t[0]);
+      const u32 m = mul_lo(t[i], FpParams::INV32);
+      // even chain: m*p0 -> limbs i,i+1; m*p2 -> limbs i+2,i+3; then + m at limb i+4, + m at limb i+6, + m at limb i+8
+      t[i + 0] = mad_lo_cc(m, FpParams::P(0), t[i + 0]);
+      t[i + 1] = madc_hi_cc(m, FpParams::P(0), t[i + 1]);
+      t[i + 2] = madc_lo_cc(m, FpParams::P(2), t[i + 2]);
+      t[i + 3] = madc_hi_cc(m, FpParams::P(2), t[i + 3]);
+      t[i + 4] = addc_cc(t[i + 4], m);
+      t[i + 5] = addc_cc(t[i + 5], 0);
+      t[i + 6] = addc_cc(t[i + 6], m);
+      t[i + 7] = addc_cc(t[i + 7], 0);
+      t[i + 8] = addc_cc(t[i + 8], m);
 #pragma unroll
-      for (int j = 1; j < 8; j++) t[j] = madc_lo_cc(a.v[j], bi, t[j]);
-      t[8] = addc_cc(t[8], 0);
-      t[9] = addc(t[9], 0);
-      t[1] = mad_hi_cc(a.v[0], bi, t[1]);
+      for (int j = i + 9; j < 17; j++) t[j] = addc_cc(t[j], 0);
+      t[17] = addc(t[17], 0);
+      // odd chain: m*p1 -> limbs i+1,i+2; m*p3 -> limbs i+3,i+4
+      t[i + 1] = mad_lo_cc(m, FpParams::P(1), t[i + 1]);
+      t[i + 2] = madc_hi_cc(m, FpParams::P(1), t[i + 2]);
+      t[i + 3] = madc_lo_cc(m, FpParams::P(3), t[i + 3]);
+      t[i + 4] = madc_hi_cc(m, FpParams::P(3), t[i + 4]);
 #pragma unroll
-      for (int j = 1; j < 8; j++) t[j + 1] = madc_hi_cc(a.v[j], bi, t[j + 1]);
-      t[9] = addc(t[9], 0);
-      const u32 m = mul_lo(t[0], FpParams::INV32);
-      t[0] = mad_lo_cc(m, FpParams::P(0), t[0]);
+      for (int j = i + 5; j < 17; j++) t[j] = addc_cc(t[j], 0);
+      t[17] = addc(t[17], 0);
+      // - m at limb i+7   (the 2^32-1 limb: m*(2^32-1)<<224 = (m<<256) - (m<<224); the + part went in above)
+      t[i + 7] = sub_cc(t[i + 7], m);
 #pragma unroll
-      for (int j = 1; j < 8; j++) t[j] = madc_lo_cc(m, FpParams::P(j), t[j]);
-      t[8] = addc_cc(t[8], 0);
-      t[9] = addc(t[9], 0);
-      t[1] = mad_hi_cc(m, FpParams::P(0), t[1]);
-#pragma unroll
-      for (int j = 1; j < 8; j++) t[j + 1] = madc_hi_cc(m, FpParams::P(j), t[j + 1]);
-      t[9] = addc(t[9], 0);
-#pragma unroll
-      for (int j = 0; j < 9; j++) t[j] = t[j + 1];
-      t[9] = 0;
+      for (int j = i + 8; j < 17; j++) t[j] = subc_cc(t[j], 0);
+      t[17] = subc(t[17], 0);
     }
     fe r;
 #pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-    cond_sub_p<FpParams>(r, t[8]);
+    for (int i = 0; i < 8; i++) r.v[i] = t[8 + i];
+    cond_sub_p<FpParams>(r, t[16]);
     return r;
   }
   SP2_HD static fe sqr(const fe &a) { return mul(a, a); }

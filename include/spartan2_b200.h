@@ -184,7 +184,8 @@ int32_t sp2_host_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_host_free(sp2_ctx *ctx, void *p);
 
 /* debug: 7 clock64() stamps (SM cycles) of the last finalised sum-check round, then 4 %globaltimer
- * values (ns) of the last multi-CTA cubic round: [-, election, finalize end, first CTA entry]     */
+ * values (ns) of the last multi-CTA cubic round: [-, election, finalize end, first CTA entry], then the
+ * clock64() start stamp of the previous tail round (12 values)                                    */
 int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out11);
 
 /* harness support: n pseudo-random T256 points (seeded multiples of the generator) for test/bench keys.

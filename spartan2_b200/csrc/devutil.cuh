@@ -40,22 +40,51 @@ __device__ __forceinline__ fe warp_sum_fq(fe x) {
   for (int m = 16; m >= 1; m >>= 1) x = Fq::add(x, shfl_xor_fe(x, m));
   return x;
 }
-// sum of NV field elements per thread over the block; result in thread 0.  smem: NV * 32 fe.
+// ---- limb-column reductions -------------------------------------------------------------------------------
+// Summing field elements across a warp with modular adds costs 5 dependent (shuffle x8, 8-limb carry chain,
+// conditional subtract) stages per value.  Instead every 32-bit limb column is summed as an independent u64
+// (32 lanes * 2^32 < 2^37: no overflow), 8*NV independent shuffle-add chains with full ILP, and carries are
+// propagated / reduced mod p once at the end.
+template <int NV>
+__device__ __forceinline__ void warp_sum_fq_cols(fe (&x)[NV]) {
+  u64 col[NV][8];
+#pragma unroll
+  for (int k = 0; k < NV; k++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) col[k][i] = x[k].v[i];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1)
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) col[k][i] += __shfl_xor_sync(0xffffffffu, col[k][i], m);
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    // carry-propagate the 8 columns into 8 limbs + a small top word (< 32), then fold the top word mod p
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += col[k][i]; x[k].v[i] = (u32)c; c >>= 32; }
+    u32 top = Fq::fold_top(x[k], (u32)c);
+    top = Fq::fold_top(x[k], top);
+    cond_sub_p<FqParams>(x[k], top);
+    cond_sub_p<FqParams>(x[k], 0);
+  }
+}
+// sum of NV field elements per thread over the block; result in every lane of warp 0.  smem: NV * 32 fe.
 template <int NV>
 __device__ __forceinline__ void block_sum_fq(fe (&x)[NV], fe *smem) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  warp_sum_fq_cols<NV>(x);
+  if (nw == 1) return;
+  if (lane == 0) {
 #pragma unroll
-  for (int k = 0; k < NV; k++) {
-    x[k] = warp_sum_fq(x[k]);
-    if (lane == 0) smem[k * 32 + warp] = x[k];
+    for (int k = 0; k < NV; k++) smem[k * 32 + warp] = x[k];
   }
   __syncthreads();
   if (warp == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-      fe v = lane < nw ? smem[k * 32 + lane] : Fq::zero();
-      x[k] = warp_sum_fq(v);
-    }
+    for (int k = 0; k < NV; k++) x[k] = lane < nw ? smem[k * 32 + lane] : Fq::zero();
+    warp_sum_fq_cols<NV>(x);
   }
 }
 

@@ -32,6 +32,7 @@ struct KeccakLane {             // per-lane constants of the permutation
   int c1, c2, c3, c4;           // same-column lanes for theta
   int xm1, xp1, xp2;            // row neighbours
   int src;                      // rho-pi source lane
+  int src1, src2;               // rho-pi source lanes of the row neighbours (x+1, y), (x+2, y): chi reads them directly
   int rot;                      // rho rotation of this lane's own value
 };
 __device__ __forceinline__ KeccakLane keccak_lane_init(int lane) {
@@ -42,6 +43,7 @@ __device__ __forceinline__ KeccakLane keccak_lane_init(int lane) {
   k.c1 = (i + 5) % 25; k.c2 = (i + 10) % 25; k.c3 = (i + 15) % 25; k.c4 = (i + 20) % 25;
   k.xm1 = (x + 4) % 5 + 5 * y; k.xp1 = (x + 1) % 5 + 5 * y; k.xp2 = (x + 2) % 5 + 5 * y;
   k.src = ((x + 3 * y) % 5) + 5 * x;
+  { const int x1 = (x + 1) % 5, x2 = (x + 2) % 5; k.src1 = ((x1 + 3 * y) % 5) + 5 * x1; k.src2 = ((x2 + 3 * y) % 5) + 5 * x2; }
   k.rot = ROT[i];
   return k;
 }
@@ -55,8 +57,10 @@ __device__ __forceinline__ u64 keccak_f_warp(u64 s, const KeccakLane &k, int lan
     u64 c = s ^ __shfl_sync(FULL, s, k.c1) ^ __shfl_sync(FULL, s, k.c2) ^ __shfl_sync(FULL, s, k.c3) ^ __shfl_sync(FULL, s, k.c4);
     u64 d = __shfl_sync(FULL, c, k.xm1) ^ rotl64(__shfl_sync(FULL, c, k.xp1), 1);
     s ^= d;
-    u64 b = __shfl_sync(FULL, rotl64(s, k.rot), k.src);
-    u64 b1 = __shfl_sync(FULL, b, k.xp1), b2 = __shfl_sync(FULL, b, k.xp2);
+    // rho in place, then pi and chi's two neighbour reads as ONE shuffle stage (three independent gathers from the
+    // rotated values) instead of pi followed by a dependent neighbour exchange
+    const u64 t = rotl64(s, k.rot);
+    const u64 b = __shfl_sync(FULL, t, k.src), b1 = __shfl_sync(FULL, t, k.src1), b2 = __shfl_sync(FULL, t, k.src2);
     s = b ^ (~b1 & b2);
     if (lane == 0) s ^= KECCAK_RC_D[rnd];
   }

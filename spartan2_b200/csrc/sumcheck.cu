@@ -29,6 +29,7 @@
 // computes, hence bit-identical.
 #include <stdlib.h>
 #include <string.h>
+#include <utility>
 #include "ctx.cuh"
 #include "keccak.cuh"
 #include "polys.cuh"
@@ -280,11 +281,77 @@ k_cubic_round(ScState *st, fe *A, fe *B, fe *C, u64 P, int round1, int l, const 
   if (threadIdx.x == 0) { st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
 }
 
-// all remaining rounds [round_first, l] in one CTA (tables of <= SC_TAIL_LEN entries going in)
+
+// ---- small rounds: three work items per pair ("roles") ---------------------------------------------------
+// When a round has fewer pairs than the GPU has threads, one thread per pair is a ~12-multiplication serial
+// chain on an otherwise idle machine.  Small rounds therefore split every pair into three independent items:
+//   role 0: binds the low entries  (a0, b0, c0), stores them, contributes E*(a0 b0 - c0) to t(0)
+//   role 1: binds the high entries (a1, b1, c1), stores them, contributes E*(a1 b1 - c1) to t(1)
+//   role 2: binds the DIFFERENCES (bind is linear: a1-a0 = bind(A[j+P]-A[j], A[j+3P]-A[j+2P])), contributes to t(inf)
+// Items of one pair read the same source entries, so binding cannot be in place here: small rounds ping-pong
+// between the table and a scratch copy (src -> dst).
+template <bool FUSED>
+__device__ __forceinline__ void cubic_roles(const fe *sA, const fe *sB, const fe *sC, fe *dA, fe *dB, fe *dC, u64 P, const fe &r,
+                                            const fe *el, const fe *er, u32 sh, int role, u64 first, u64 stride, fe (&x)[3]) {
+  // the role is uniform across a warp (role = warp index mod 3): no divergence, one accumulator per thread
+  Fq::acc acc = Fq::acc_zero();
+  const u64 mask = ((u64)1 << sh) - 1;
+  for (u64 id = first; id < P; id += stride) {
+    fe w = ldg_fe_ro(er + (el ? (id & mask) : id));
+    if (el) w = Fq::mul(ldg_fe_ro(el + (id >> sh)), w);
+    if (role < 2) {
+      const u64 o = role ? P : 0;
+      fe a, b, c;
+      if (FUSED) {
+        a = bind_pair(ldg_fe(sA + id + o), ldg_fe(sA + id + o + 2 * P), r); stg_fe(dA + id + o, a);
+        b = bind_pair(ldg_fe(sB + id + o), ldg_fe(sB + id + o + 2 * P), r); stg_fe(dB + id + o, b);
+        c = bind_pair(ldg_fe(sC + id + o), ldg_fe(sC + id + o + 2 * P), r); stg_fe(dC + id + o, c);
+      } else {
+        a = ldg_fe(sA + id + o); b = ldg_fe(sB + id + o); c = ldg_fe(sC + id + o);
+      }
+      Fq::mul_acc(acc, w, Fq::sub(Fq::mul(a, b), c));
+    } else {
+      fe da, db;
+      if (FUSED) {
+        da = bind_pair(Fq::sub(ldg_fe(sA + id + P), ldg_fe(sA + id)), Fq::sub(ldg_fe(sA + id + 3 * P), ldg_fe(sA + id + 2 * P)), r);
+        db = bind_pair(Fq::sub(ldg_fe(sB + id + P), ldg_fe(sB + id)), Fq::sub(ldg_fe(sB + id + 3 * P), ldg_fe(sB + id + 2 * P)), r);
+      } else {
+        da = Fq::sub(ldg_fe(sA + id + P), ldg_fe(sA + id));
+        db = Fq::sub(ldg_fe(sB + id + P), ldg_fe(sB + id));
+      }
+      Fq::mul_acc(acc, w, Fq::mul(da, db));
+    }
+  }
+  const fe v = Fq::acc_reduce(acc);
+  x[0] = role == 0 ? v : Fq::zero(); x[1] = role == 1 ? v : Fq::zero(); x[2] = role == 2 ? v : Fq::zero();
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(SC_ROLE_THREADS, 1)
+k_cubic_round_roles(ScState *st, const fe *sA, const fe *sB, const fe *sC, fe *dA, fe *dB, fe *dC, u64 P, int round1, int l,
+                    const fe *el, const fe *er, u32 sh) {
+  __shared__ FinSmem sm;
+  if (threadIdx.x == 0) atomicMin(&st->gt[0], gtimer());
+  fe r;
+  if (FUSED) r = ld_state(&st->r[round1 - 2]);
+  fe x[3];
+  { const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, trios = SC_ROLE_THREADS / 96;
+    cubic_roles<FUSED>(sA, sB, sC, dA, dB, dC, P, r, el, er, sh, w % 3, ((u64)blockIdx.x * trios + w / 3) * 32 + lane, (u64)gridDim.x * trios * 32, x); }
+  block_sum_fq<3>(x, sm.red);
+  if (!publish_and_elect<3>(st, x, sm)) return;
+  cubic_finalize(st, round1, l, FUSED ? dA : sA, FUSED ? dB : sB, FUSED ? dC : sC, x, sm);
+  if (threadIdx.x == 0) { st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
+}
+
+// all remaining rounds [round_first, l] in one CTA (tables of <= SC_TAIL_LEN entries going in); ping-pongs between
+// (A,B,C) and the scratch copies (A2,B2,C2)
 __global__ void __launch_bounds__(SC_TAIL_THREADS, 1)
-k_cubic_tail(ScState *st, fe *A, fe *B, fe *C, int round_first, int l, const fe *eq_left, const fe *eq_right) {
+k_cubic_tail(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int round_first, int l, const fe *eq_left, const fe *eq_right) {
   __shared__ FinSmem sm;
   const int first_half = l / 2, second_half = l - first_half;
+  fe *sA = A, *sB = B, *sC = C, *dA = A2, *dB = B2, *dC = C2;
+  const int role = (threadIdx.x >> 5) % 3;
+  const u64 slot = (u64)((threadIdx.x >> 5) / 3) * 32 + (threadIdx.x & 31), nslots = (SC_TAIL_THREADS / 96) * 32;
   for (int round1 = round_first; round1 <= l; round1++) {
     const u64 P = (u64)1 << (l - round1);
     const fe *el = nullptr, *er; u32 sh = 0;
@@ -295,12 +362,18 @@ k_cubic_tail(ScState *st, fe *A, fe *B, fe *C, int round_first, int l, const fe 
       er = eq_right + (((size_t)1 << (l - round1)) - 1);
     }
     fe x[3];
+    if (threadIdx.x == 0) st->clk[7] = st->clk[0];
     SC_STAMP(0);
-    if (round1 > 1) cubic_generic<true>(A, B, C, P, ld_state(&st->r[round1 - 2]), el, er, sh, threadIdx.x, blockDim.x, x);
-    else cubic_generic<false>(A, B, C, P, Fq::zero(), el, er, sh, threadIdx.x, blockDim.x, x);
+    if (round1 > 1) {
+      cubic_roles<true>(sA, sB, sC, dA, dB, dC, P, ld_state(&st->r[round1 - 2]), el, er, sh, role, slot, nslots, x);
+      fe *t;
+      t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t;      // the bound tables are now the source
+    } else {
+      cubic_roles<false>(sA, sB, sC, dA, dB, dC, P, Fq::zero(), el, er, sh, role, slot, nslots, x);
+    }
     __syncthreads();
     block_sum_fq<3>(x, sm.red);
-    cubic_finalize(st, round1, l, A, B, C, x, sm);
+    cubic_finalize(st, round1, l, sA, sB, sC, x, sm);
     __syncthreads();
   }
 }
@@ -391,20 +464,75 @@ k_quad_round(ScState *st, fe *A, fe *B, u64 P, int round1, int rounds, u64 nvali
   quad_finalize(st, round1, rounds, A, B, x, sm);
 }
 
-__global__ void __launch_bounds__(SC_TAIL_THREADS, 1)
-k_quad_tail(ScState *st, fe *A, fe *B, int round_first, int rounds, u64 nvalid) {
+// small rounds of the quadratic prover: role 0 binds/stores the low entries and sums a0*b0, role 1 binds/stores the
+// high entries, role 2 binds the differences and sums da*db (see cubic_roles)
+template <bool FUSED>
+__device__ __forceinline__ void quad_roles(const fe *sA, const fe *sB, fe *dA, fe *dB, u64 P, const fe &r, int role, u64 first, u64 stride,
+                                           u64 nvalid, fe (&x)[2]) {
+  Fq::acc acc = Fq::acc_zero();
+  for (u64 id = first; id < P; id += stride) {
+    if (role < 2) {
+      const u64 o = role ? P : 0;
+      if (FUSED) {
+        const fe a = bind_pair(ldg_fe(sA + id + o), ldg_fe_valid(sA, id + o + 2 * P, nvalid), r); stg_fe(dA + id + o, a);
+        const fe b = bind_pair(ldg_fe(sB + id + o), ldg_fe_valid(sB, id + o + 2 * P, nvalid), r); stg_fe(dB + id + o, b);
+        if (role == 0) Fq::mul_acc(acc, a, b);
+      } else if (role == 0) {
+        Fq::mul_acc(acc, ldg_fe(sA + id), ldg_fe(sB + id));
+      }
+    } else {
+      fe da, db;
+      if (FUSED) {
+        da = bind_pair(Fq::sub(ldg_fe(sA + id + P), ldg_fe(sA + id)), Fq::sub(ldg_fe_valid(sA, id + 3 * P, nvalid), ldg_fe_valid(sA, id + 2 * P, nvalid)), r);
+        db = bind_pair(Fq::sub(ldg_fe(sB + id + P), ldg_fe(sB + id)), Fq::sub(ldg_fe_valid(sB, id + 3 * P, nvalid), ldg_fe_valid(sB, id + 2 * P, nvalid)), r);
+      } else {
+        da = Fq::sub(ldg_fe_valid(sA, id + P, nvalid), ldg_fe(sA + id));
+        db = Fq::sub(ldg_fe_valid(sB, id + P, nvalid), ldg_fe(sB + id));
+      }
+      Fq::mul_acc(acc, da, db);
+    }
+  }
+  const fe v = Fq::acc_reduce(acc);
+  x[0] = role == 0 ? v : Fq::zero(); x[1] = role == 2 ? v : Fq::zero();
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(SC_ROLE_THREADS, 1)
+k_quad_round_roles(ScState *st, const fe *sA, const fe *sB, fe *dA, fe *dB, u64 P, int round1, int rounds, u64 nvalid) {
   __shared__ FinSmem sm;
+  fe r;
+  if (FUSED) r = ld_state(&st->r[round1 - 2]);
+  fe x[2];
+  { const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, trios = SC_ROLE_THREADS / 96;
+    quad_roles<FUSED>(sA, sB, dA, dB, P, r, w % 3, ((u64)blockIdx.x * trios + w / 3) * 32 + lane, (u64)gridDim.x * trios * 32, nvalid, x); }
+  block_sum_fq<2>(x, sm.red);
+  if (!publish_and_elect<2>(st, x, sm)) return;
+  quad_finalize(st, round1, rounds, FUSED ? dA : sA, FUSED ? dB : sB, x, sm);
+}
+
+__global__ void __launch_bounds__(SC_TAIL_THREADS, 1)
+k_quad_tail(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int rounds, u64 nvalid) {
+  __shared__ FinSmem sm;
+  fe *sA = A, *sB = B, *dA = A2, *dB = B2;
+  const int role = (threadIdx.x >> 5) % 3;
+  const u64 slot = (u64)((threadIdx.x >> 5) / 3) * 32 + (threadIdx.x & 31), nslots = (SC_TAIL_THREADS / 96) * 32;
   for (int round1 = round_first; round1 <= rounds; round1++) {
     const u64 P = (u64)1 << (rounds - round1);
     fe x[2];
+    if (threadIdx.x == 0) st->clk[7] = st->clk[0];
     SC_STAMP(0);
     // only the first two launches can see unmaterialised entries; afterwards the bound table is dense
     const u64 nv = round1 <= 2 ? nvalid : ~0ull;
-    if (round1 > 1) quad_body<true>(A, B, P, ld_state(&st->r[round1 - 2]), threadIdx.x, blockDim.x, nv, x);
-    else quad_body<false>(A, B, P, Fq::zero(), threadIdx.x, blockDim.x, nv, x);
+    if (round1 > 1) {
+      quad_roles<true>(sA, sB, dA, dB, P, ld_state(&st->r[round1 - 2]), role, slot, nslots, nv, x);
+      fe *t;
+      t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t;
+    } else {
+      quad_roles<false>(sA, sB, dA, dB, P, Fq::zero(), role, slot, nslots, nv, x);
+    }
     __syncthreads();
     block_sum_fq<2>(x, sm.red);
-    quad_finalize(st, round1, rounds, A, B, x, sm);
+    quad_finalize(st, round1, rounds, sA, sB, x, sm);
     __syncthreads();
   }
 }
@@ -455,12 +583,16 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
   k_cubic_init<<<2, 1024, 0, ctx->stream>>>(st, (int)l, eq_left, eq_right);
   SP2_LAUNCH_CHECK();
   const unsigned target = (unsigned)ctx->num_sms * 2;
+  // scratch copies for the small (role-split, ping-pong) rounds: tables of <= SC_ROLE_LEN entries going in
+  void *pp; SP2_TRY(scratch(ctx, 7, 3 * (SC_ROLE_LEN / 2) * sizeof(fe), &pp));
+  fe *s2[3] = {(fe *)pp, (fe *)pp + SC_ROLE_LEN / 2, (fe *)pp + SC_ROLE_LEN};
+  fe *src[3] = {A, B, C}, *dst[3] = {s2[0], s2[1], s2[2]};
   for (uint32_t round1 = 1; round1 <= l; round1++) {
     const bool fused = round1 > 1;
     const u64 P = (u64)1 << (l - round1);                       // pairs evaluated this round
     const u64 len_in = fused ? 4 * P : 2 * P;                   // table length going into this launch
     if (len_in <= SC_TAIL_LEN) {
-      k_cubic_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, A, B, C, (int)round1, (int)l, eq_left, eq_right);
+      k_cubic_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
       SP2_LAUNCH_CHECK();
       break;
     }
@@ -472,6 +604,18 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
       er = eq_right + (((size_t)1 << second_half) - 1); sh = (u32)second_half;
     } else {
       er = eq_right + (((size_t)1 << (l - round1)) - 1);
+    }
+    if (len_in <= SC_ROLE_LEN) {                                  // small multi-CTA round: three items per pair, src -> dst
+      const u64 per_cta = (SC_ROLE_THREADS / 96) * 32;             // pairs per CTA and pass
+      u64 nb = (P + per_cta - 1) / per_cta; if (nb > (u64)ctx->num_sms) nb = ctx->num_sms;
+      if (fused) {
+        k_cubic_round_roles<true><<<(unsigned)nb, SC_ROLE_THREADS, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], P, (int)round1, (int)l, el, er, sh);
+        for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);
+      } else {
+        k_cubic_round_roles<false><<<(unsigned)nb, SC_ROLE_THREADS, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], P, (int)round1, (int)l, el, er, sh);
+      }
+      SP2_LAUNCH_CHECK();
+      continue;
     }
     const u64 in_len = (u64)1 << sh;
     if (in_first && in_len >= SC_THREADS && in_len / SC_THREADS <= target) {
@@ -493,21 +637,34 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
 int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first) {
   bool recorded = false;
   const unsigned target = (unsigned)ctx->num_sms * 2;
+  void *pp; SP2_TRY(scratch(ctx, 6, 2 * (SC_ROLE_LEN / 2) * sizeof(fe), &pp));
+  fe *src[2] = {A, B}, *dst[2] = {(fe *)pp, (fe *)pp + SC_ROLE_LEN / 2};
   for (uint32_t round1 = 1; round1 <= rounds; round1++) {
     const u64 P = (u64)1 << (rounds - round1);
     const u64 len_in = round1 > 1 ? 4 * P : 2 * P;
     if (len_in <= SC_TAIL_LEN) {
-      k_quad_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, A, B, (int)round1, (int)rounds, nvalid);
+      k_quad_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);
       SP2_LAUNCH_CHECK();
       if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
       break;
     }
     const u64 nv = round1 <= 2 ? nvalid : ~0ull;
-    u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > target) nb = target;
-    if (round1 > 1) k_quad_round<true><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
-    else k_quad_round<false><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
-    if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
+    if (len_in <= SC_ROLE_LEN) {
+      const u64 per_cta = (SC_ROLE_THREADS / 96) * 32;
+      u64 nb = (P + per_cta - 1) / per_cta; if (nb > (u64)ctx->num_sms) nb = ctx->num_sms;
+      if (round1 > 1) {
+        k_quad_round_roles<true><<<(unsigned)nb, SC_ROLE_THREADS, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], P, (int)round1, (int)rounds, nv);
+        std::swap(src[0], dst[0]); std::swap(src[1], dst[1]);
+      } else {
+        k_quad_round_roles<false><<<(unsigned)nb, SC_ROLE_THREADS, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], P, (int)round1, (int)rounds, nv);
+      }
+    } else {
+      u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > target) nb = target;
+      if (round1 > 1) k_quad_round<true><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
+      else k_quad_round<false><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
+    }
     SP2_LAUNCH_CHECK();
+    if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
   }
   return SP2_OK;
 }
@@ -524,6 +681,7 @@ int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out7 /* 11 values */) {
   ScState *st = (ScState *)ctx->slot[14];
   SP2_CUDA_OK(cudaMemcpyAsync(out7, st->clk, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(out7 + 7, st->gt, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(out7 + 11, &st->clk[7], sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return SP2_OK;
 }

@@ -8,8 +8,10 @@ namespace sp2 {
 constexpr int SC_MAX_ROUNDS = 40;
 constexpr int SC_MAX_BLOCKS = 2048;
 constexpr int SC_THREADS = 256;
-constexpr int SC_TAIL_THREADS = 512;
+constexpr int SC_TAIL_THREADS = 384;   // 12 warps = 4 role trios
+constexpr int SC_ROLE_THREADS = 384;
 constexpr unsigned long long SC_TAIL_LEN = 4096;   // tables this short are finished by one CTA in one launch
+constexpr unsigned long long SC_ROLE_LEN = 1ull << 16;   // tables this short use the role-split (3 items per pair) rounds
 
 struct ScState {
   DevTranscript ts;           // transcript hand-off: (round, state) in, (round, state) out

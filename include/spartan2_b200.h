@@ -83,6 +83,25 @@ int32_t sp2_sumcheck_cubic_prove_dev(sp2_ctx *ctx, const uint64_t *claim, const 
 int32_t sp2_sumcheck_quad_prove_dev(sp2_ctx *ctx, const uint64_t *claim, uint32_t rounds, void *dA, void *dB,
                                     sp2_transcript_state *ts, uint64_t *polys, uint64_t *r, uint64_t *claims);
 
+/* ---- multi-GPU sharding of the sum-checks -------------------------------------------------
+ * One process per GPU.  The 2^l hypercube is split cyclically on the low index bits (rank g owns entries
+ * i = g mod nranks), so every bind pair is local; per round the <= 3 partial sums are exchanged by the round
+ * kernel itself through CUDA-IPC-mapped peer mailboxes over NVLink (no NCCL call, no extra launch); below
+ * 2^16 entries the shards are all-gathered and every rank finishes redundantly.  Setup: each rank creates a
+ * comm, the 64-byte handles are all-gathered by the host (torch.distributed, MPI, ...), then connect.       */
+typedef struct sp2_comm sp2_comm;
+int32_t sp2_comm_create(sp2_ctx *ctx, int32_t rank, int32_t nranks, sp2_comm **out);
+int32_t sp2_comm_handle(sp2_comm *comm, uint8_t *out64);
+int32_t sp2_comm_connect(sp2_comm *comm, const uint8_t *all_handles /* nranks x 64 bytes, rank order */);
+void sp2_comm_destroy(sp2_comm *comm);
+/* dA, dB, dC: this rank's shards (2^l / nranks entries each, device pointers), bound in place; every rank passes
+ * the same claim / taus / transcript and receives identical outputs (same meaning as the single-GPU provers). */
+int32_t sp2_sumcheck_cubic_prove_sharded_dev(sp2_ctx *ctx, sp2_comm *comm, const uint64_t *claim, const uint64_t *taus, uint32_t l,
+                                             void *dA, void *dB, void *dC, sp2_transcript_state *ts, uint64_t *polys, uint64_t *r,
+                                             uint64_t *claims);
+int32_t sp2_sumcheck_quad_prove_sharded_dev(sp2_ctx *ctx, sp2_comm *comm, const uint64_t *claim, uint32_t rounds, void *dA, void *dB,
+                                            sp2_transcript_state *ts, uint64_t *polys, uint64_t *r, uint64_t *claims);
+
 /* ---- polynomials (src/polys) ---------------------------------------------------------------- */
 /* EqPolynomial::evals_from_points (src/polys/eq.rs:59-117): out[2^k], MSB-first.               */
 int32_t sp2_eq_table(sp2_ctx *ctx, const uint64_t *r, uint32_t k, uint64_t *out);

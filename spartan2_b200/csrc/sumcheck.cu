@@ -87,6 +87,66 @@ __device__ __forceinline__ bool publish_and_elect(ScState *st, fe (&x)[NV], FinS
   return true;
 }
 
+// Cross-GPU sum of the round's partial sums, executed by the last CTA of every rank's round kernel: write the local
+// sums into every peer's mailbox (peer stores over NVLink), publish with a system-scope fence + flag, wait for
+// all peers' flags, add.  x valid in warp 0 on entry and on exit.
+template <int NV>
+__device__ __forceinline__ void exchange_sums(const DevComm &dc, int slot, fe (&x)[NV], FinSmem &sm) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) sm.g[k] = x[k];
+  }
+  __syncthreads();
+  if (tid < dc.n) {
+    MailBox *mb = dc.peer[tid];
+#pragma unroll
+    for (int k = 0; k < NV; k++) stg_fe(&mb->sums[slot][dc.rank][k], sm.g[k]);
+    __threadfence_system();
+    *(volatile u32 *)&mb->flag[slot][dc.rank] = dc.epoch;
+    // wait for rank `tid`'s contribution to arrive in the local mailbox
+    const MailBox *me = dc.peer[dc.rank];
+    while (*(volatile const u32 *)&me->flag[slot][tid] != dc.epoch) {}
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const MailBox *me = dc.peer[dc.rank];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      fe acc = Fq::zero();
+      for (int q = 0; q < dc.n; q++) {
+        fe v; u64 a, b, c, d;
+        asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(&me->sums[slot][q][k]));
+        v.v[0] = (u32)a; v.v[1] = (u32)(a >> 32); v.v[2] = (u32)b; v.v[3] = (u32)(b >> 32);
+        v.v[4] = (u32)c; v.v[5] = (u32)(c >> 32); v.v[6] = (u32)d; v.v[7] = (u32)(d >> 32);
+        acc = Fq::add(acc, v);
+      }
+      x[k] = acc;
+    }
+  }
+}
+
+// All-gather of the shards into every rank's gather area (global index order i = (j << k) | rank), by peer stores.
+__global__ void __launch_bounds__(256) k_shard_gather(DevComm dc, const fe *A, const fe *B, const fe *C, u64 len_local, int ntab) {
+  const fe *T[3] = {A, B, C};
+  for (int t = 0; t < ntab; t++)
+    for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < len_local; j += (u64)gridDim.x * blockDim.x) {
+      const fe v = ldg_fe(T[t] + j);
+      for (int q = 0; q < dc.n; q++) stg_fe(&dc.peer[q]->gather[t][(j << dc.k) | (u64)dc.rank], v);
+    }
+}
+// publish / wait for the gather (one CTA, after k_shard_gather on the same stream)
+__global__ void k_shard_barrier(DevComm dc, int slot) {
+  const int tid = threadIdx.x;
+  if (tid < dc.n) {
+    __threadfence_system();
+    *(volatile u32 *)&dc.peer[tid]->flag[slot][dc.rank] = dc.epoch;
+    while (*(volatile const u32 *)&dc.peer[dc.rank]->flag[slot][tid] != dc.epoch) {}
+    __threadfence_system();
+  }
+}
+
 // Transcript step shared by both provers.  On entry lanes [0, ncoef) of warp 0 hold the canonical
 // (non-Montgomery) transcript coefficients in `canon` (UniPoly::to_transcript_bytes: all but the
 // linear term, each to_repr() little-endian, univariate.rs:182-190).  Returns the challenge to all.
@@ -237,12 +297,14 @@ __device__ __forceinline__ void cubic_pair(fe *A, fe *B, fe *C, u64 id, u64 P, c
 // (second half, sumcheck.rs:1107-1142)
 template <bool FUSED>
 __device__ __forceinline__ void cubic_generic(fe *A, fe *B, fe *C, u64 P, const fe &r, const fe *el, const fe *er, u32 sh,
-                                              u64 first, u64 stride, fe (&x)[3]) {
+                                              u64 first, u64 stride, fe (&x)[3], int shard_k = 0, int shard_rank = 0) {
+  // sh: GLOBAL width of x_in; weights are indexed by the global pair id
   Fq::acc acc0 = Fq::acc_zero(), acc1 = Fq::acc_zero(), acci = Fq::acc_zero();
   const u64 mask = ((u64)1 << sh) - 1;
   for (u64 id = first; id < P; id += stride) {
-    fe w = ldg_fe_ro(er + (el ? (id & mask) : id));
-    if (el) w = Fq::mul(ldg_fe_ro(el + (id >> sh)), w);
+    const u64 gid = (id << shard_k) | (u64)shard_rank;
+    fe w = ldg_fe_ro(er + (el ? (gid & mask) : gid));
+    if (el) w = Fq::mul(ldg_fe_ro(el + (gid >> sh)), w);
     cubic_pair<FUSED>(A, B, C, id, P, r, w, acc0, acc1, acci);
   }
   x[0] = Fq::acc_reduce(acc0); x[1] = Fq::acc_reduce(acc1); x[2] = Fq::acc_reduce(acci);
@@ -257,7 +319,9 @@ __device__ __forceinline__ void cubic_generic(fe *A, fe *B, fe *C, u64 P, const 
 #endif
 template <bool FUSED, int MODE>
 __global__ void __launch_bounds__(SC_THREADS, SC_CUBIC_MINB)
-k_cubic_round(ScState *st, fe *A, fe *B, fe *C, u64 P, int round1, int l, const fe *el, const fe *er, u32 out_len, u32 sh) {
+k_cubic_round(ScState *st, fe *A, fe *B, fe *C, u64 P, int round1, int l, const fe *el, const fe *er, u32 out_len, u32 sh,
+              DevComm dc) {
+  // P, A, B, C are LOCAL (this rank's shard); weights are indexed by the GLOBAL pair id (id << k) | rank
   __shared__ FinSmem sm;
   if (threadIdx.x == 0) atomicMin(&st->gt[0], gtimer());
   fe r;
@@ -265,18 +329,20 @@ k_cubic_round(ScState *st, fe *A, fe *B, fe *C, u64 P, int round1, int l, const 
   fe x[3];
   if (MODE == 0) {
     Fq::acc acc0 = Fq::acc_zero(), acc1 = Fq::acc_zero(), acci = Fq::acc_zero();
+    // sh is the LOCAL width of x_in (global width minus k)
     const u64 xi = (u64)blockIdx.x * SC_THREADS + threadIdx.x;
     for (u32 xo = blockIdx.y; xo < out_len; xo += gridDim.y)
       cubic_pair<FUSED>(A, B, C, ((u64)xo << sh) | xi, P, r, ldg_fe_ro(el + xo), acc0, acc1, acci);
-    const fe wr = ldg_fe_ro(er + xi);
+    const fe wr = ldg_fe_ro(er + ((xi << dc.k) | (u64)dc.rank));
     x[0] = Fq::mul(wr, Fq::acc_reduce(acc0));
     x[1] = Fq::mul(wr, Fq::acc_reduce(acc1));
     x[2] = Fq::mul(wr, Fq::acc_reduce(acci));
   } else {
-    cubic_generic<FUSED>(A, B, C, P, r, el, er, sh, (u64)blockIdx.x * SC_THREADS + threadIdx.x, (u64)gridDim.x * SC_THREADS, x);
+    cubic_generic<FUSED>(A, B, C, P, r, el, er, sh, (u64)blockIdx.x * SC_THREADS + threadIdx.x, (u64)gridDim.x * SC_THREADS, x, dc.k, dc.rank);
   }
   block_sum_fq<3>(x, sm.red);
   if (!publish_and_elect<3>(st, x, sm)) return;
+  if (dc.n > 1) exchange_sums<3>(dc, round1, x, sm);
   cubic_finalize(st, round1, l, A, B, C, x, sm);
   if (threadIdx.x == 0) { st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
 }
@@ -453,7 +519,7 @@ __device__ __forceinline__ void quad_body(fe *A, fe *B, u64 P, const fe &r, u64 
 
 template <bool FUSED>
 __global__ void __launch_bounds__(SC_THREADS, 2)
-k_quad_round(ScState *st, fe *A, fe *B, u64 P, int round1, int rounds, u64 nvalid) {
+k_quad_round(ScState *st, fe *A, fe *B, u64 P, int round1, int rounds, u64 nvalid, DevComm dc) {
   __shared__ FinSmem sm;
   fe r;
   if (FUSED) r = ld_state(&st->r[round1 - 2]);
@@ -461,6 +527,7 @@ k_quad_round(ScState *st, fe *A, fe *B, u64 P, int round1, int rounds, u64 nvali
   quad_body<FUSED>(A, B, P, r, (u64)blockIdx.x * SC_THREADS + threadIdx.x, (u64)gridDim.x * SC_THREADS, nvalid, x);
   block_sum_fq<2>(x, sm.red);
   if (!publish_and_elect<2>(st, x, sm)) return;
+  if (dc.n > 1) exchange_sums<2>(dc, round1, x, sm);
   quad_finalize(st, round1, rounds, A, B, x, sm);
 }
 
@@ -573,8 +640,22 @@ int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uin
   return SP2_OK;
 }
 
+static DevComm comm_none() { DevComm d; memset(&d, 0, sizeof(d)); d.n = 1; return d; }
+
+// all-gather the shards (len_local entries per table) into every rank's gather area and return the local copy
+static int shard_gather(sp2_ctx *ctx, const DevComm &dc, fe *const *src, int ntab, u64 len_local, fe **out) {
+  if ((len_local << dc.k) > SC_ROLE_LEN) return set_error(ctx, SP2_ERR_INTERNAL, "shard gather: table too large");
+  unsigned nb = (unsigned)((len_local + 255) / 256); if (nb > (unsigned)ctx->num_sms * 4) nb = ctx->num_sms * 4; if (nb == 0) nb = 1;
+  k_shard_gather<<<nb, 256, 0, ctx->stream>>>(dc, src[0], src[1], ntab > 2 ? src[2] : src[1], len_local, ntab);
+  SP2_LAUNCH_CHECK();
+  k_shard_barrier<<<1, 32, 0, ctx->stream>>>(dc, SC_MAX_ROUNDS + 1);
+  SP2_LAUNCH_CHECK();
+  for (int t = 0; t < ntab; t++) out[t] = dc.peer[dc.rank]->gather[t];
+  return SP2_OK;
+}
+
 // enqueue the whole cubic sum-check on ctx->stream (state already on the device, taus in st->taus)
-int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C) {
+int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C, const DevComm *dcp) {
   const int first_half = (int)l / 2, second_half = (int)l - first_half;
   void *eqs;
   const size_t nleft = (size_t)1 << (first_half > 0 ? first_half : 1), nright = (size_t)2 << second_half;
@@ -587,11 +668,25 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
   void *pp; SP2_TRY(scratch(ctx, 7, 3 * (SC_ROLE_LEN / 2) * sizeof(fe), &pp));
   fe *s2[3] = {(fe *)pp, (fe *)pp + SC_ROLE_LEN / 2, (fe *)pp + SC_ROLE_LEN};
   fe *src[3] = {A, B, C}, *dst[3] = {s2[0], s2[1], s2[2]};
+  DevComm dc = dcp ? *dcp : comm_none();
+  bool sharded = dc.n > 1;
+  if (sharded) {
+    if ((int)l < dc.k) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "sharded sum-check: fewer entries than ranks");
+    k_shard_barrier<<<1, 32, 0, ctx->stream>>>(dc, 0);          // every rank has finished the previous sharded call
+    SP2_LAUNCH_CHECK();
+  }
   for (uint32_t round1 = 1; round1 <= l; round1++) {
     const bool fused = round1 > 1;
-    const u64 P = (u64)1 << (l - round1);                       // pairs evaluated this round
-    const u64 len_in = fused ? 4 * P : 2 * P;                   // table length going into this launch
-    if (len_in <= SC_TAIL_LEN) {
+    const u64 Pg = (u64)1 << (l - round1);                      // pairs evaluated this round (global)
+    const u64 len_in = fused ? 4 * Pg : 2 * Pg;                 // global table length going into this launch
+    if (sharded && len_in <= SC_ROLE_LEN) {                      // hand-off: gather the shards, finish redundantly on every rank
+      fe *g[3];
+      SP2_TRY(shard_gather(ctx, dc, src, 3, len_in >> dc.k, g));
+      for (int k = 0; k < 3; k++) src[k] = g[k];
+      sharded = false; dc = comm_none();
+    }
+    const u64 P = sharded ? Pg >> dc.k : Pg;                    // local pairs
+    if (!sharded && len_in <= SC_TAIL_LEN) {
       k_cubic_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
       SP2_LAUNCH_CHECK();
       break;
@@ -605,7 +700,7 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     } else {
       er = eq_right + (((size_t)1 << (l - round1)) - 1);
     }
-    if (len_in <= SC_ROLE_LEN) {                                  // small multi-CTA round: three items per pair, src -> dst
+    if (!sharded && len_in <= SC_ROLE_LEN) {                      // small multi-CTA round: three items per pair, src -> dst
       const u64 per_cta = (SC_ROLE_THREADS / 96) * 32;             // pairs per CTA and pass
       u64 nb = (P + per_cta - 1) / per_cta; if (nb > (u64)ctx->num_sms) nb = ctx->num_sms;
       if (fused) {
@@ -617,39 +712,57 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
       SP2_LAUNCH_CHECK();
       continue;
     }
-    const u64 in_len = (u64)1 << sh;
-    if (in_first && in_len >= SC_THREADS && in_len / SC_THREADS <= target) {
-      dim3 grid((unsigned)(in_len / SC_THREADS), 1);
+    // large round: in place on (A, B, C) — local shards when sharded
+    const u64 in_len_local = ((u64)1 << sh) >> dc.k;             // local width of x_in (two-level mode)
+    if (in_first && in_len_local >= SC_THREADS && in_len_local / SC_THREADS <= target) {
+      dim3 grid((unsigned)(in_len_local / SC_THREADS), 1);
       unsigned gy = target / grid.x; if (gy < 1) gy = 1; if (gy > out_len) gy = out_len;
       grid.y = gy;
-      if (fused) k_cubic_round<true, 0><<<grid, SC_THREADS, 0, ctx->stream>>>(st, A, B, C, P, (int)round1, (int)l, el, er, out_len, sh);
-      else k_cubic_round<false, 0><<<grid, SC_THREADS, 0, ctx->stream>>>(st, A, B, C, P, (int)round1, (int)l, el, er, out_len, sh);
+      const u32 sh_local = sh - (u32)dc.k;
+      if (fused) k_cubic_round<true, 0><<<grid, SC_THREADS, 0, ctx->stream>>>(st, A, B, C, P, (int)round1, (int)l, el, er, out_len, sh_local, dc);
+      else k_cubic_round<false, 0><<<grid, SC_THREADS, 0, ctx->stream>>>(st, A, B, C, P, (int)round1, (int)l, el, er, out_len, sh_local, dc);
     } else {
-      u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > target) nb = target;
-      if (fused) k_cubic_round<true, 1><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, C, P, (int)round1, (int)l, el, er, out_len, sh);
-      else k_cubic_round<false, 1><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, C, P, (int)round1, (int)l, el, er, out_len, sh);
+      u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > target) nb = target; if (nb == 0) nb = 1;
+      if (fused) k_cubic_round<true, 1><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, C, P, (int)round1, (int)l, el, er, out_len, sh, dc);
+      else k_cubic_round<false, 1><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, C, P, (int)round1, (int)l, el, er, out_len, sh, dc);
     }
     SP2_LAUNCH_CHECK();
   }
   return SP2_OK;
 }
 
-int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first) {
+int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first,
+                          const DevComm *dcp) {
   bool recorded = false;
   const unsigned target = (unsigned)ctx->num_sms * 2;
   void *pp; SP2_TRY(scratch(ctx, 6, 2 * (SC_ROLE_LEN / 2) * sizeof(fe), &pp));
   fe *src[2] = {A, B}, *dst[2] = {(fe *)pp, (fe *)pp + SC_ROLE_LEN / 2};
+  DevComm dc = dcp ? *dcp : comm_none();
+  bool sharded = dc.n > 1;
+  if (sharded) {
+    if (nvalid != ~0ull) return set_error(ctx, SP2_ERR_UNSUPPORTED, "sharded quad sum-check needs dense tables");
+    if ((int)rounds < dc.k) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "sharded sum-check: fewer entries than ranks");
+    k_shard_barrier<<<1, 32, 0, ctx->stream>>>(dc, 0);
+    SP2_LAUNCH_CHECK();
+  }
   for (uint32_t round1 = 1; round1 <= rounds; round1++) {
-    const u64 P = (u64)1 << (rounds - round1);
-    const u64 len_in = round1 > 1 ? 4 * P : 2 * P;
-    if (len_in <= SC_TAIL_LEN) {
+    const u64 Pg = (u64)1 << (rounds - round1);
+    const u64 len_in = round1 > 1 ? 4 * Pg : 2 * Pg;
+    if (sharded && len_in <= SC_ROLE_LEN) {
+      fe *g[3];
+      SP2_TRY(shard_gather(ctx, dc, src, 2, len_in >> dc.k, g));
+      src[0] = g[0]; src[1] = g[1];
+      sharded = false; dc = comm_none();
+    }
+    const u64 P = sharded ? Pg >> dc.k : Pg;
+    if (!sharded && len_in <= SC_TAIL_LEN) {
       k_quad_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);
       SP2_LAUNCH_CHECK();
       if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
       break;
     }
     const u64 nv = round1 <= 2 ? nvalid : ~0ull;
-    if (len_in <= SC_ROLE_LEN) {
+    if (!sharded && len_in <= SC_ROLE_LEN) {
       const u64 per_cta = (SC_ROLE_THREADS / 96) * 32;
       u64 nb = (P + per_cta - 1) / per_cta; if (nb > (u64)ctx->num_sms) nb = ctx->num_sms;
       if (round1 > 1) {
@@ -659,9 +772,9 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
         k_quad_round_roles<false><<<(unsigned)nb, SC_ROLE_THREADS, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], P, (int)round1, (int)rounds, nv);
       }
     } else {
-      u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > target) nb = target;
-      if (round1 > 1) k_quad_round<true><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
-      else k_quad_round<false><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv);
+      u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > target) nb = target; if (nb == 0) nb = 1;
+      if (round1 > 1) k_quad_round<true><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv, dc);
+      else k_quad_round<false><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(st, A, B, P, (int)round1, (int)rounds, nv, dc);
     }
     SP2_LAUNCH_CHECK();
     if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }

@@ -29,13 +29,34 @@ struct ScState {
   fe partial[3 * SC_MAX_BLOCKS];
 };
 
+// ---- multi-GPU sharding (one process per GPU; peers' mailboxes are CUDA-IPC mapped over NVLink) ----------------
+// The 2^l hypercube is split CYCLICALLY on the low index bits: rank g of G = 2^k owns global indices i = g (mod G),
+// stored densely at i >> k.  Both entries of every bind pair (i, i + len/2) share their low bits, so every round is
+// local; only the <= 3 partial sums cross GPUs, written by the round kernel's last CTA straight into every peer's
+// mailbox (st.global over NVLink + system fence + flag) — the exchange is fused into the compute kernel, no NCCL
+// call and no extra launch per round.  Once the table has <= SC_ROLE_LEN entries the shards are all-gathered
+// (again by peer stores) and every rank finishes the latency-bound small rounds redundantly.
+constexpr int SC_MAX_RANKS = 8;
+struct MailBox {
+  fe sums[SC_MAX_ROUNDS + 2][SC_MAX_RANKS][4];
+  u32 flag[SC_MAX_ROUNDS + 2][SC_MAX_RANKS];
+  fe gather[3][SC_ROLE_LEN];
+};
+struct DevComm {
+  int rank, n, k;             // n = 2^k ranks
+  u32 epoch;                  // distinguishes successive sum-checks (flags are compared to it, never reset)
+  MailBox *peer[SC_MAX_RANKS];   // peer[rank] is the local mailbox
+};
+
 int sc_state_upload(sp2_ctx *ctx, ScState **d_st, const uint64_t *claim, const uint64_t *taus, uint32_t l,
                     const sp2_transcript_state *ts);
 int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uint64_t *polys, int ncoef, uint64_t *r,
                       uint64_t *claims, int nclaims, uint32_t l);
-int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C);
+// dc: nullptr for a single GPU; otherwise A, B, C are this rank's cyclic shards (2^(l-k) entries) of the global tables
+int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C, const DevComm *dc = nullptr);
 // nvalid: table entries at index >= nvalid are unmaterialised zeros (~0ull: dense tables)
 // after_first (optional): recorded once the launch that produces r[0] has been enqueued
-int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first);
+int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first,
+                          const DevComm *dc = nullptr);
 
 }  // namespace sp2

@@ -385,3 +385,54 @@ class SpartanSNARK:
         P.phase_ms = dict(zip(["commit_transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck",
                                "pcs_prove", "ipa_response", "total"], [float(x) for x in ph]))
         return P
+
+
+def shard_cyclic(table, nranks, rank):
+    """This rank's shard of a table split cyclically on the low index bits (entries i = rank mod nranks)."""
+    return np.ascontiguousarray(np.asarray(table)[rank::nranks])
+
+
+class Comm:
+    """Peer mailboxes for the sharded sum-checks (sp2_comm).  `allgather_bytes(b: bytes) -> list[bytes]` is the host's
+    collective (e.g. built on torch.distributed.all_gather_object); it is only used once, to exchange IPC handles."""
+
+    def __init__(self, ctx, rank, nranks, allgather_bytes=None):
+        self.ctx, self.rank, self.nranks = ctx, rank, nranks
+        h = C.c_void_p()
+        ctx.check(ctx.L.sp2_comm_create(ctx.h, C.c_int32(rank), C.c_int32(nranks), C.byref(h)))
+        self.h = h
+        if nranks > 1:
+            buf = (C.c_uint8 * 64)()
+            ctx.check(ctx.L.sp2_comm_handle(self.h, buf))
+            handles = allgather_bytes(bytes(buf))
+            assert len(handles) == nranks and all(len(x) == 64 for x in handles)
+            allb = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+            ctx.check(ctx.L.sp2_comm_connect(self.h, _p(allb)))
+
+    def free(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.sp2_comm_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def prove_cubic_with_three_inputs(self, claim, taus, A, B, Cz, ts):
+        """A, B, Cz: DeviceBuffers holding this rank's cyclic shards."""
+        ctx = self.ctx
+        taus = _fe(taus); l = taus.shape[0]; claim = _fe(claim)
+        polys = np.zeros((l, 4, 4), dtype=np.uint64); r = np.zeros((l, 4), dtype=np.uint64); claims = np.zeros((3, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_sumcheck_cubic_prove_sharded_dev(ctx.h, self.h, _p(claim), _p(taus), C.c_uint32(l), A.ptr, B.ptr, Cz.ptr,
+                                                             C.byref(ts), _p(polys), _p(r), _p(claims)))
+        return polys, r, claims
+
+    def prove_quad(self, claim, num_rounds, A, B, ts):
+        ctx = self.ctx
+        claim = _fe(claim); l = int(num_rounds)
+        polys = np.zeros((l, 3, 4), dtype=np.uint64); r = np.zeros((l, 4), dtype=np.uint64); claims = np.zeros((2, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_sumcheck_quad_prove_sharded_dev(ctx.h, self.h, _p(claim), C.c_uint32(l), A.ptr, B.ptr, C.byref(ts), _p(polys),
+                                                            _p(r), _p(claims)))
+        return polys, r, claims

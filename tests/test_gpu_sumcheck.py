@@ -130,3 +130,24 @@ def test_full_size_linearity_property(ctx, orc):
         tb = tb * (t * x + (1 - t) * (1 - x)) % Q
     a, b, c = pi(claims)
     assert pi(e_final)[0] == tb * (a * b - c) % Q
+
+
+def test_sharded_api_single_rank(ctx, orc):
+    """The multi-GPU entry points with a 1-rank communicator (the N > 1 path is exercised by tools/multi_gpu_check.py
+    under torchrun and by tests/test_sharding_gloo.py on CPU): same results as the plain provers."""
+    import spartan2_b200 as sp
+    comm = sp.Comm(ctx, 0, 1)
+    rng = np.random.default_rng(5); l = 13; n = 1 << l
+    A, B, Cz, taus = rand_fe(rng, n), rand_fe(rng, n), rand_fe(rng, n), rand_fe(rng, l)
+    claim = orc.f_dot_delayed(orc.eq_evals(taus), orc.f_sub(orc.f_mul(A, B), Cz))
+    t_or, ts = ts_pair(orc)
+    polys, r, claims = comm.prove_cubic_with_three_inputs(claim, taus, ctx.upload(A), ctx.upload(B), ctx.upload(Cz), ts)
+    opolys, orr, oclaims, _ = orc.sumcheck_cubic_prove(claim, taus, A, B, Cz, t_or)
+    assert np.array_equal(polys, opolys) and np.array_equal(r, orr) and np.array_equal(claims, oclaims)
+    qclaim = orc.f_dot_delayed(A, B)
+    qpolys, qr, qclaims = comm.prove_quad(qclaim, l, ctx.upload(A), ctx.upload(B), ts)
+    opolys, orr, oclaims = orc.sumcheck_quad_prove(qclaim, l, A, B, t_or)
+    assert np.array_equal(qpolys, opolys) and np.array_equal(qr, orr) and np.array_equal(qclaims, oclaims)
+    with pytest.raises(sp.SpartanError):
+        sp.Comm(ctx, 0, 3)                      # ranks must be a power of two <= 8
+    comm.free()

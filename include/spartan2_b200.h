@@ -191,6 +191,34 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck
                           const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rand,
                           sp2_spartan_proof *proof, float *phase_ms);
 
+/* ---- NeutronNova building blocks (src/neutronnova_zk.rs, src/polys/power.rs, src/r1cs/mod.rs) ------------
+ * The ZK drivers draw one challenge per round from the in-circuit verifier (process_round, out of scope), so the
+ * seams are per-round {evaluate, fold/bind} pairs on device-resident tables rather than whole loops.            */
+/* PowPolynomial::split_evals (src/polys/power.rs:65-86): [1,t,..,t^(left-1)] || [1,t^left,..] (host out)       */
+int32_t sp2_pow_split_evals(sp2_ctx *ctx, const uint64_t *t, uint32_t left, uint32_t right, uint64_t *out);
+/* One NIFS round (src/neutronnova_zk.rs:98-178 prove_helper per pair, :78-87 suffix weights, summed over pairs):
+ * m live layers of N = left*right entries, layer q at slot q*stride of dA/dB/dC; out2 = (e0, quad_coeff).       */
+int32_t sp2_nifs_round_dev(sp2_ctx *ctx, uint32_t t, const uint64_t *rhos, uint32_t ell_b, uint32_t left, uint32_t right, const void *dE,
+                           const void *dA, const void *dB, const void *dC, uint64_t N, uint64_t m, uint64_t stride, uint64_t *out2);
+/* fold_abc_pair for every pair (src/neutronnova_zk.rs:738-776): slot 2p*stride <- lo + r_b (hi - lo), in place   */
+int32_t sp2_nifs_fold_dev(sp2_ctx *ctx, void *dA, void *dB, void *dC, uint64_t N, uint64_t m, uint64_t stride, const uint64_t *r_b);
+/* weights_from_r (src/r1cs/mod.rs:153-166), LSB-first                                                            */
+int32_t sp2_weights_from_r(sp2_ctx *ctx, const uint64_t *r_bs, uint32_t ell, uint32_t n, uint64_t *out);
+/* R1CSWitness::fold_multiple, W part (src/r1cs/mod.rs:570-660): d_out[j] = sum_i w[i] * dWs[i*dim + j]            */
+int32_t sp2_fold_vectors_dev(sp2_ctx *ctx, const void *dWs, uint64_t n, uint64_t dim, const uint64_t *w, void *d_out);
+/* compute_eval_points_cubic_with_additive_term(_with_outer_pow) (src/sumcheck.rs:262-342, 366-498): out3 =
+ * evaluations at 0, 2, 3, unscaled by base_tau; tables of table_len entries                                      */
+int32_t sp2_sc_pow_cubic_eval_dev(sp2_ctx *ctx, const void *d_pow_left, uint32_t left, const void *d_pow_right, const void *dA, const void *dB,
+                                  const void *dC, uint64_t table_len, uint64_t *out3);
+/* compute_eval_points_quad (src/sumcheck.rs:128-174): out2 = (eval_point_0, bound_coeff)                         */
+int32_t sp2_sc_quad_eval_dev(sp2_ctx *ctx, const void *dA, const void *dB, uint64_t table_len, uint64_t *out2);
+/* bind_poly_var_top on up to 8 device tables with one challenge, in place (the rayon::join bind fan-out of
+ * src/sumcheck.rs:880-903)                                                                                        */
+int32_t sp2_bind_tables_dev(sp2_ctx *ctx, void *const *d_tables, uint32_t ntables, uint64_t table_len, const uint64_t *r);
+/* HyraxPCS::fold_commitments (src/provider/pcs/hyrax_pc.rs:737-793 -> msm_shared_weights, msm.rs:228-356):
+ * out[row] = sum_i w[i] * comms[i*rows + row], affine in/out                                                      */
+int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n, uint32_t rows, const uint64_t *w, uint64_t *out_xy);
+
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_dev_free(sp2_ctx *ctx, void *p);

@@ -1019,3 +1019,138 @@ EXPORT int orc_spartan_verify(const shape *S, const keys_view *K, const uint8_t 
   free(tau); free(op); free(rx); free(ip); free(ry); free(X); free(Tx); free(Ty); ts_free(&ts);
   return rc;
 }
+
+/* ------------------------------------------------------------------------------------
+ * NeutronNova building blocks (neutronnova_zk.rs, polys/power.rs, r1cs/mod.rs, sumcheck.rs)
+ * Function-level restatements: the ZK driver around them (verifier circuit, process_round) is
+ * out of scope; challenges are inputs.
+ * ---------------------------------------------------------------------------------- */
+/* PowPolynomial::split_evals (polys/power.rs:65-86): [1,t,..,t^(left-1)] || [1,t^left,t^(2 left),..] */
+EXPORT void orc_pow_split_evals(const fe *t, size_t left, size_t right, fe *out) {
+  f_one(&FQ, &out[0]);
+  for (size_t i = 1; i < left; i++) f_mul(&FQ, &out[i], &out[i - 1], t);
+  fe step; f_mul(&FQ, &step, &out[left - 1], t);
+  f_one(&FQ, &out[left]);
+  for (size_t i = 1; i < right; i++) f_mul(&FQ, &out[left + i], &out[left + i - 1], &step);
+}
+/* suffix_weight_full (neutronnova_zk.rs:78-87) */
+static void suffix_weight_full(size_t t, size_t ell_b, size_t pair_idx, const fe *rhos, fe *w) {
+  fe one; f_one(&FQ, &one); *w = one; size_t k = pair_idx;
+  for (size_t s = t + 1; s < ell_b; s++) {
+    fe f; if (k & 1) f = rhos[s]; else f_sub(&FQ, &f, &one, &rhos[s]);
+    f_mul(&FQ, w, w, &f); k >>= 1;
+  }
+}
+/* NeutronNovaNIFS::prove_helper (neutronnova_zk.rs:98-178), one pair of layers */
+static void nifs_prove_helper(size_t round, size_t left, size_t right, const fe *e, const fe *Az1, const fe *Bz1, const fe *Cz1,
+                              const fe *Az2, const fe *Bz2, fe *e0, fe *quad) {
+  const fe *f = e + left, *el = e;
+  acc9 a0, aq; memset(&a0, 0, sizeof(a0)); memset(&aq, 0, sizeof(aq));
+  for (size_t i = 0; i < right; i++) {
+    acc9 i0, iq; memset(&i0, 0, sizeof(i0)); memset(&iq, 0, sizeof(iq));
+    for (size_t j = 0; j < left; j++) {
+      size_t k = i * left + j; fe v, da, db;
+      if (round != 0) { f_mul(&FQ, &v, &Az1[k], &Bz1[k]); f_sub(&FQ, &v, &v, &Cz1[k]); f_mul_acc(&i0, &el[j], &v); }
+      f_sub(&FQ, &da, &Az2[k], &Az1[k]); f_sub(&FQ, &db, &Bz2[k], &Bz1[k]); f_mul(&FQ, &v, &da, &db);
+      f_mul_acc(&iq, &el[j], &v);
+    }
+    fe r0, rq; f_reduce9(&FQ, &r0, &i0); f_reduce9(&FQ, &rq, &iq);
+    f_mul_acc(&a0, &f[i], &r0); f_mul_acc(&aq, &f[i], &rq);
+  }
+  f_reduce9(&FQ, e0, &a0); f_reduce9(&FQ, quad, &aq);
+}
+/* one NIFS round evaluation over m live layers (standard field path, neutronnova_zk.rs:809-833 / fallback branches):
+ * layers are stored layer-major (layer q at offset q*N); returns (e0, quad_coeff) = sum_p w_p * prove_helper(pair p) */
+EXPORT void orc_nifs_round(size_t t, size_t ell_b, const fe *rhos, size_t left, size_t right, const fe *E, const fe *A, const fe *B,
+                           const fe *Cm, size_t N, size_t m, fe *out2) {
+  fe e0, q; f_zero(&e0); f_zero(&q);
+  for (size_t p = 0; p < m / 2; p++) {
+    fe pe, pq, w, tmp;
+    nifs_prove_helper(t, left, right, E, A + 2 * p * N, B + 2 * p * N, Cm + 2 * p * N, A + (2 * p + 1) * N, B + (2 * p + 1) * N, &pe, &pq);
+    suffix_weight_full(t, ell_b, p, rhos, &w);
+    f_mul(&FQ, &tmp, &pe, &w); f_add(&FQ, &e0, &e0, &tmp);
+    f_mul(&FQ, &tmp, &pq, &w); f_add(&FQ, &q, &q, &tmp);
+  }
+  out2[0] = e0; out2[1] = q;
+}
+/* fold_abc_pair over all pairs (neutronnova_zk.rs:738-776): layer p <- lo + r_b (hi - lo); compacts to m/2 layers */
+EXPORT void orc_nifs_fold(fe *L, size_t N, size_t m, const fe *r_b) {
+  for (size_t p = 0; p < m / 2; p++)
+    for (size_t k = 0; k < N; k++) {
+      fe d; f_sub(&FQ, &d, &L[(2 * p + 1) * N + k], &L[2 * p * N + k]); f_mul(&FQ, &d, &d, r_b);
+      f_add(&FQ, &L[p * N + k], &L[2 * p * N + k], &d);
+    }
+}
+/* weights_from_r (r1cs/mod.rs:153-166): eq(i, r) with LSB-first bits */
+EXPORT void orc_weights_from_r(const fe *r_bs, size_t ell, size_t n, fe *w) {
+  fe one; f_one(&FQ, &one);
+  for (size_t i = 0; i < n; i++) {
+    fe wi = one; size_t k = i;
+    for (size_t t = 0; t < ell; t++) { fe f; if (k & 1) f = r_bs[t]; else f_sub(&FQ, &f, &one, &r_bs[t]); f_mul(&FQ, &wi, &wi, &f); k >>= 1; }
+    w[i] = wi;
+  }
+}
+/* R1CSWitness::fold_multiple, W part (r1cs/mod.rs:570-660): out[j] = sum_i w_i * Ws[i][j] */
+EXPORT void orc_fold_vectors(const fe *Ws, size_t n, size_t dim, const fe *w, fe *out) {
+  for (size_t j = 0; j < dim; j++) {
+    acc9 a; memset(&a, 0, sizeof(a));
+    for (size_t i = 0; i < n; i++) f_mul_acc(&a, &w[i], &Ws[i * dim + j]);
+    f_reduce9(&FQ, &out[j], &a);
+  }
+}
+/* compute_eval_points_cubic_with_additive_term_with_outer_pow (sumcheck.rs:366-498) incl. the len < left case
+ * (:262-342 with the weight table as first polynomial).  table_len = current length of A/B/C. */
+EXPORT void orc_pow_cubic_eval(const fe *pl, size_t left, const fe *pr, const fe *A, const fe *B, const fe *Cm, size_t table_len, fe *out3) {
+  size_t len = table_len / 2;
+  acc9 a0, a2, a3; memset(&a0, 0, sizeof(a0)); memset(&a2, 0, sizeof(a2)); memset(&a3, 0, sizeof(a3));
+  if (len < left) {
+    for (size_t i = 0; i < len; i++) {
+      fe v, wb, ab, bb, cb, t;
+      f_mul(&FQ, &v, &A[i], &B[i]); f_sub(&FQ, &v, &v, &Cm[i]); f_mul_acc(&a0, &pl[i], &v);
+      f_dbl(&FQ, &wb, &pl[i + len]); f_sub(&FQ, &wb, &wb, &pl[i]);
+      f_dbl(&FQ, &ab, &A[i + len]); f_sub(&FQ, &ab, &ab, &A[i]);
+      f_dbl(&FQ, &bb, &B[i + len]); f_sub(&FQ, &bb, &bb, &B[i]);
+      f_dbl(&FQ, &cb, &Cm[i + len]); f_sub(&FQ, &cb, &cb, &Cm[i]);
+      f_mul(&FQ, &v, &ab, &bb); f_sub(&FQ, &v, &v, &cb); f_mul_acc(&a2, &wb, &v);
+      f_add(&FQ, &wb, &wb, &pl[i + len]); f_sub(&FQ, &wb, &wb, &pl[i]);
+      f_add(&FQ, &ab, &ab, &A[i + len]); f_sub(&FQ, &ab, &ab, &A[i]);
+      f_add(&FQ, &bb, &bb, &B[i + len]); f_sub(&FQ, &bb, &bb, &B[i]);
+      f_add(&FQ, &cb, &cb, &Cm[i + len]); f_sub(&FQ, &cb, &cb, &Cm[i]);
+      f_mul(&FQ, &v, &ab, &bb); f_sub(&FQ, &v, &v, &cb); f_mul_acc(&a3, &wb, &v); (void)t;
+    }
+  } else {
+    size_t right = len / left;
+    for (size_t i = 0; i < left; i++) {
+      acc9 i0, i2, i3; memset(&i0, 0, sizeof(i0)); memset(&i2, 0, sizeof(i2)); memset(&i3, 0, sizeof(i3));
+      for (size_t j = 0; j < right; j++) {
+        size_t low = i + j * left, high = low + len;
+        const fe *tl = &pr[j], *th = &pr[j + right];
+        fe v, tb, ab, bb, cb;
+        f_mul(&FQ, &v, &A[low], &B[low]); f_sub(&FQ, &v, &v, &Cm[low]); f_mul_acc(&i0, tl, &v);
+        f_dbl(&FQ, &tb, th); f_sub(&FQ, &tb, &tb, tl);
+        f_dbl(&FQ, &ab, &A[high]); f_sub(&FQ, &ab, &ab, &A[low]);
+        f_dbl(&FQ, &bb, &B[high]); f_sub(&FQ, &bb, &bb, &B[low]);
+        f_dbl(&FQ, &cb, &Cm[high]); f_sub(&FQ, &cb, &cb, &Cm[low]);
+        f_mul(&FQ, &v, &ab, &bb); f_sub(&FQ, &v, &v, &cb); f_mul_acc(&i2, &tb, &v);
+        f_add(&FQ, &tb, &tb, th); f_sub(&FQ, &tb, &tb, tl);
+        f_add(&FQ, &ab, &ab, &A[high]); f_sub(&FQ, &ab, &ab, &A[low]);
+        f_add(&FQ, &bb, &bb, &B[high]); f_sub(&FQ, &bb, &bb, &B[low]);
+        f_add(&FQ, &cb, &cb, &Cm[high]); f_sub(&FQ, &cb, &cb, &Cm[low]);
+        f_mul(&FQ, &v, &ab, &bb); f_sub(&FQ, &v, &v, &cb); f_mul_acc(&i3, &tb, &v);
+      }
+      fe r0, r2, r3; f_reduce9(&FQ, &r0, &i0); f_reduce9(&FQ, &r2, &i2); f_reduce9(&FQ, &r3, &i3);
+      f_mul_acc(&a0, &pl[i], &r0); f_mul_acc(&a2, &pl[i], &r2); f_mul_acc(&a3, &pl[i], &r3);
+    }
+  }
+  f_reduce9(&FQ, &out3[0], &a0); f_reduce9(&FQ, &out3[1], &a2); f_reduce9(&FQ, &out3[2], &a3);
+}
+/* compute_eval_points_quad (sumcheck.rs:128-174) */
+EXPORT void orc_quad_eval(const fe *A, const fe *B, size_t table_len, fe *out2) { quad_points(A, B, table_len, &out2[0], &out2[1]); }
+/* HyraxPCS::fold_commitments (hyrax_pc.rs:737-793) as group elements: out[row] = sum_i w_i * comms[i][row] */
+EXPORT void orc_fold_commitments(const apt *comms, size_t n, size_t rows, const fe *w, apt *out) {
+  for (size_t r = 0; r < rows; r++) {
+    pt acc; pt_set_inf(&CV, &acc);
+    for (size_t i = 0; i < n; i++) { pt t; pt_mul_fe(&t, &comms[i * rows + r], &w[i]); pt_add(&CV, &acc, &acc, &t); }
+    pt_to_affine(&CV, &out[r], &acc);
+  }
+}

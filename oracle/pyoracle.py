@@ -423,3 +423,57 @@ def set_threads(n):
 
 def max_threads():
     return lib().orc_get_max_threads()
+
+
+# ---- NeutronNova building blocks -------------------------------------------------------------------
+def pow_split_evals(t, left, right):
+    t = np.ascontiguousarray(t, dtype=np.uint64); out = fe_array(left + right)
+    lib().orc_pow_split_evals(_p(t), C.c_size_t(left), C.c_size_t(right), _p(out))
+    return out
+
+
+def nifs_round(t, rhos, left, right, E, A, B, Cm, N, m):
+    rhos = np.ascontiguousarray(rhos, dtype=np.uint64).reshape(-1, 4)
+    E, A, B, Cm = (np.ascontiguousarray(x, dtype=np.uint64) for x in (E, A, B, Cm))
+    out = fe_array(2)
+    lib().orc_nifs_round(C.c_size_t(t), C.c_size_t(rhos.shape[0]), _p(rhos), C.c_size_t(left), C.c_size_t(right), _p(E), _p(A), _p(B), _p(Cm),
+                         C.c_size_t(N), C.c_size_t(m), _p(out))
+    return out
+
+
+def nifs_fold(L, N, m, r_b):
+    L = np.ascontiguousarray(L, dtype=np.uint64).copy(); r_b = np.ascontiguousarray(r_b, dtype=np.uint64)
+    lib().orc_nifs_fold(_p(L), C.c_size_t(N), C.c_size_t(m), _p(r_b))
+    return L[: (m // 2) * N]
+
+
+def weights_from_r(r_bs, n):
+    r_bs = np.ascontiguousarray(r_bs, dtype=np.uint64).reshape(-1, 4); out = fe_array(n)
+    lib().orc_weights_from_r(_p(r_bs), C.c_size_t(r_bs.shape[0]), C.c_size_t(n), _p(out))
+    return out
+
+
+def fold_vectors(Ws, n, dim, w):
+    Ws = np.ascontiguousarray(Ws, dtype=np.uint64); w = np.ascontiguousarray(w, dtype=np.uint64); out = fe_array(dim)
+    lib().orc_fold_vectors(_p(Ws), C.c_size_t(n), C.c_size_t(dim), _p(w), _p(out))
+    return out
+
+
+def pow_cubic_eval(pl, pr, A, B, Cm):
+    pl, pr, A, B, Cm = (np.ascontiguousarray(x, dtype=np.uint64) for x in (pl, pr, A, B, Cm))
+    out = fe_array(3)
+    lib().orc_pow_cubic_eval(_p(pl), C.c_size_t(pl.shape[0]), _p(pr), _p(A), _p(B), _p(Cm), C.c_size_t(A.shape[0]), _p(out))
+    return out
+
+
+def quad_eval(A, B):
+    A, B = (np.ascontiguousarray(x, dtype=np.uint64) for x in (A, B)); out = fe_array(2)
+    lib().orc_quad_eval(_p(A), _p(B), C.c_size_t(A.shape[0]), _p(out))
+    return out
+
+
+def fold_commitments(comms, n, rows, w):
+    comms = np.ascontiguousarray(comms, dtype=np.uint64); w = np.ascontiguousarray(w, dtype=np.uint64)
+    out = np.zeros((rows, 8), dtype=np.uint64)
+    lib().orc_fold_commitments(_p(comms), C.c_size_t(n), C.c_size_t(rows), _p(w), _p(out))
+    return out

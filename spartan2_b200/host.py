@@ -436,3 +436,87 @@ class Comm:
         ctx.check(ctx.L.sp2_sumcheck_quad_prove_sharded_dev(ctx.h, self.h, _p(claim), C.c_uint32(l), A.ptr, B.ptr, C.byref(ts), _p(polys),
                                                             _p(r), _p(claims)))
         return polys, r, claims
+
+
+class PowPolynomial:
+    """src/polys/power.rs"""
+
+    @staticmethod
+    def split_evals(ctx, t, left, right):
+        t = _fe(t); out = np.zeros((left + right, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_pow_split_evals(ctx.h, _p(t), C.c_uint32(left), C.c_uint32(right), _p(out)))
+        return out
+
+
+class NeutronNovaNIFS:
+    """src/neutronnova_zk.rs:511-1273 — the per-round kernels of the multi-folding scheme on device-resident layers.
+    A, B, C: DeviceBuffers of n*N scalars, layer-major.  The challenges r_b come from the caller (the reference draws
+    them through its in-circuit verifier)."""
+
+    def __init__(self, ctx, E, left, right, A, B, Cz, n):
+        self.ctx, self.left, self.right, self.N, self.n = ctx, left, right, left * right, n
+        self.dE = ctx.upload(_fe(E)); self.A, self.B, self.C = A, B, Cz
+        self.m = n; self.stride = 1; self.t = 0
+
+    def round_eval(self, rhos):
+        rhos = _fe(rhos); out = np.zeros((2, 4), dtype=np.uint64); ctx = self.ctx
+        ctx.check(ctx.L.sp2_nifs_round_dev(ctx.h, C.c_uint32(self.t), _p(rhos), C.c_uint32(rhos.shape[0]), C.c_uint32(self.left), C.c_uint32(self.right),
+                                           self.dE.ptr, self.A.ptr, self.B.ptr, self.C.ptr, C.c_uint64(self.N), C.c_uint64(self.m), C.c_uint64(self.stride), _p(out)))
+        return out
+
+    def fold(self, r_b):
+        r_b = _fe(r_b); ctx = self.ctx
+        ctx.check(ctx.L.sp2_nifs_fold_dev(ctx.h, self.A.ptr, self.B.ptr, self.C.ptr, C.c_uint64(self.N), C.c_uint64(self.m), C.c_uint64(self.stride), _p(r_b)))
+        self.m //= 2; self.stride *= 2; self.t += 1
+
+    def layer0(self):
+        """the folded (Az, Bz, Cz) layers once m == 1"""
+        return tuple(b.download((self.N, 4)) for b in (self.A, self.B, self.C))
+
+
+def weights_from_r(ctx, r_bs, n):
+    r_bs = _fe(r_bs); out = np.zeros((n, 4), dtype=np.uint64)
+    ctx.check(ctx.L.sp2_weights_from_r(ctx.h, _p(r_bs), C.c_uint32(r_bs.shape[0]), C.c_uint32(n), _p(out)))
+    return out
+
+
+class R1CSWitness:
+    """src/r1cs/mod.rs:540-660"""
+
+    @staticmethod
+    def fold_multiple(ctx, r_bs, Ws):
+        """Ws: (n, dim, 4) witness vectors; returns the folded W (dim, 4)."""
+        Ws = np.ascontiguousarray(Ws, dtype=np.uint64); n, dim = Ws.shape[0], Ws.shape[1]
+        w = weights_from_r(ctx, r_bs, n)
+        dW = ctx.upload(Ws); out = ctx.alloc(dim * 32)
+        ctx.check(ctx.L.sp2_fold_vectors_dev(ctx.h, dW.ptr, C.c_uint64(n), C.c_uint64(dim), _p(w), out.ptr))
+        return out.download((dim, 4))
+
+
+class SumcheckRounds:
+    """Per-round evaluation points + binds of the ZK sum-check drivers (src/sumcheck.rs:702-917)."""
+
+    @staticmethod
+    def eval_points_cubic_with_outer_pow(ctx, d_pow_left, left, d_pow_right, dA, dB, dC, table_len):
+        out = np.zeros((3, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_sc_pow_cubic_eval_dev(ctx.h, d_pow_left.ptr, C.c_uint32(left), d_pow_right.ptr, dA.ptr, dB.ptr, dC.ptr, C.c_uint64(table_len), _p(out)))
+        return out
+
+    @staticmethod
+    def eval_points_quad(ctx, dA, dB, table_len):
+        out = np.zeros((2, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_sc_quad_eval_dev(ctx.h, dA.ptr, dB.ptr, C.c_uint64(table_len), _p(out)))
+        return out
+
+    @staticmethod
+    def bind_poly_var_top(ctx, tables, table_len, r):
+        r = _fe(r); arr = (C.c_void_p * len(tables))(*[t.ptr.value for t in tables])
+        ctx.check(ctx.L.sp2_bind_tables_dev(ctx.h, arr, C.c_uint32(len(tables)), C.c_uint64(table_len), _p(r)))
+
+
+def fold_commitments(ctx, comms, n, rows, w):
+    """HyraxPCS::fold_commitments: comms (n*rows, 8) affine, w (n, 4) -> (rows, 8)."""
+    comms = np.ascontiguousarray(comms, dtype=np.uint64).reshape(-1, 8); w = _fe(w)
+    out = np.zeros((rows, 8), dtype=np.uint64)
+    ctx.check(ctx.L.sp2_fold_commitments(ctx.h, _p(comms), C.c_uint32(n), C.c_uint32(rows), _p(w), _p(out)))
+    return out

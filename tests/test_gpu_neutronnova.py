@@ -1,0 +1,99 @@
+"""NeutronNova building blocks on the device vs the oracle (which tests/test_oracle_neutronnova.py pins to the
+definitions): split power table, a complete multi-round NIFS (evaluate -> challenge -> fold layers), witness folding,
+the pow-weighted cubic / quadratic per-round evaluation points with binding across all rounds, commitment folding."""
+import numpy as np
+import pytest
+
+from tests.gpu_util import ctx, rand_fe  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("left,right", [(1, 1), (2, 1), (8, 4), (256, 128)])
+def test_pow_split_evals(ctx, orc, left, right):
+    import spartan2_b200 as sp
+    t = rand_fe(np.random.default_rng(left), 1)
+    assert np.array_equal(sp.PowPolynomial.split_evals(ctx, t, left, right), orc.pow_split_evals(t, left, right))
+
+
+@pytest.mark.parametrize("n,left,right", [(2, 8, 4), (8, 32, 32), (32, 256, 128)])
+def test_nifs_rounds_and_folds(ctx, orc, n, left, right):
+    import spartan2_b200 as sp
+    rng = np.random.default_rng(n)
+    N = left * right; ell_b = n.bit_length() - 1
+    A, B, Cm = rand_fe(rng, n * N), rand_fe(rng, n * N), rand_fe(rng, n * N)
+    tau = rand_fe(rng, 1); rhos = rand_fe(rng, ell_b); r_bs = rand_fe(rng, ell_b)
+    E = orc.pow_split_evals(tau, left, right)
+    nifs = sp.NeutronNovaNIFS(ctx, E, left, right, ctx.upload(A), ctx.upload(B), ctx.upload(Cm), n)
+    oA, oB, oC, m = A, B, Cm, n
+    for t in range(ell_b):
+        got = nifs.round_eval(rhos)
+        want = orc.nifs_round(t, rhos, left, right, E, oA, oB, oC, N, m)
+        assert np.array_equal(got, want), t
+        nifs.fold(r_bs[t:t + 1])
+        oA, oB, oC = (orc.nifs_fold(x, N, m, r_bs[t:t + 1]) for x in (oA, oB, oC))
+        m //= 2
+    fa, fb, fc = nifs.layer0()
+    assert np.array_equal(fa, oA) and np.array_equal(fb, oB) and np.array_equal(fc, oC)
+    # the folded layer equals the eq-weighted sum of the original layers (fold_multiple's weights, LSB-first)
+    w = sp.weights_from_r(ctx, r_bs, n)
+    assert np.array_equal(w, orc.weights_from_r(r_bs, n))
+    assert np.array_equal(orc.fold_vectors(A, n, N, w), fa)
+
+
+def test_fold_multiple(ctx, orc):
+    import spartan2_b200 as sp
+    rng = np.random.default_rng(4)
+    n, dim = 8, 5000
+    Ws = rand_fe(rng, n * dim).reshape(n, dim, 4)
+    Ws[1] = orc.to_mont([int(x) for x in rng.integers(0, 2, size=dim)])       # a boolean ("small") witness among them
+    r_bs = rand_fe(rng, 3)
+    got = sp.R1CSWitness.fold_multiple(ctx, r_bs, Ws)
+    assert np.array_equal(got, orc.fold_vectors(Ws.reshape(-1, 4), n, dim, orc.weights_from_r(r_bs, n)))
+
+
+def test_pow_cubic_rounds_with_binding(ctx, orc):
+    """All 10 rounds of the NeutronNova outer sum-check shape (one branch): evaluation points, then bind A, B, C."""
+    import spartan2_b200 as sp
+    rng = np.random.default_rng(8)
+    left, right = 32, 32; n = left * right
+    tau = rand_fe(rng, 1)
+    E = orc.pow_split_evals(tau, left, right)
+    A, B, Cm = rand_fe(rng, n), rand_fe(rng, n), rand_fe(rng, n)
+    dA, dB, dC = ctx.upload(A), ctx.upload(B), ctx.upload(Cm)
+    dpl, dpr = ctx.upload(E[:left]), ctx.upload(E[left:])
+    oA, oB, oC = A, B, Cm
+    tl = n
+    while tl >= 2:
+        got = sp.SumcheckRounds.eval_points_cubic_with_outer_pow(ctx, dpl, left, dpr, dA, dB, dC, tl)
+        assert np.array_equal(got, orc.pow_cubic_eval(E[:left], E[left:], oA[:tl], oB[:tl], oC[:tl])), tl
+        r = rand_fe(rng, 1)
+        sp.SumcheckRounds.bind_poly_var_top(ctx, [dA, dB, dC], tl, r)
+        oA, oB, oC = (orc.bind_top(x[:tl], r) for x in (oA, oB, oC))
+        tl //= 2
+        assert np.array_equal(dA.download((tl, 4)), oA)
+
+
+def test_quad_rounds_with_binding(ctx, orc):
+    import spartan2_b200 as sp
+    rng = np.random.default_rng(9)
+    n = 1 << 12
+    A, B = rand_fe(rng, n), rand_fe(rng, n)
+    dA, dB = ctx.upload(A), ctx.upload(B)
+    oA, oB, tl = A, B, n
+    while tl >= 2:
+        assert np.array_equal(sp.SumcheckRounds.eval_points_quad(ctx, dA, dB, tl), orc.quad_eval(oA[:tl], oB[:tl]))
+        r = rand_fe(rng, 1)
+        sp.SumcheckRounds.bind_poly_var_top(ctx, [dA, dB], tl, r)
+        oA, oB = orc.bind_top(oA[:tl], r), orc.bind_top(oB[:tl], r)
+        tl //= 2
+
+
+def test_fold_commitments(ctx, orc):
+    import spartan2_b200 as sp
+    rng = np.random.default_rng(10)
+    n, rows = 8, 5
+    pts = ctx.test_points(n * rows, seed=3)
+    w = rand_fe(rng, n)
+    w[0] = orc.to_mont([1])[0]; w[1] = 0                  # unit and zero weights
+    assert np.array_equal(sp.fold_commitments(ctx, pts, n, rows, w), orc.fold_commitments(pts, n, rows, w))

@@ -344,7 +344,7 @@ k_cubic_round(ScState *st, fe *A, fe *B, fe *C, u64 P, int round1, int l, const 
   if (!publish_and_elect<3>(st, x, sm)) return;
   if (dc.n > 1) exchange_sums<3>(dc, round1, x, sm);
   cubic_finalize(st, round1, l, A, B, C, x, sm);
-  if (threadIdx.x == 0) { st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
+  if (threadIdx.x == 0) { st->gt[4] = st->gt[2]; st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
 }
 
 
@@ -406,7 +406,7 @@ k_cubic_round_roles(ScState *st, const fe *sA, const fe *sB, const fe *sC, fe *d
   block_sum_fq<3>(x, sm.red);
   if (!publish_and_elect<3>(st, x, sm)) return;
   cubic_finalize(st, round1, l, FUSED ? dA : sA, FUSED ? dB : sB, FUSED ? dC : sC, x, sm);
-  if (threadIdx.x == 0) { st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
+  if (threadIdx.x == 0) { st->gt[4] = st->gt[2]; st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
 }
 
 // all remaining rounds [round_first, l] in one CTA (tables of <= SC_TAIL_LEN entries going in); ping-pongs between
@@ -795,6 +795,7 @@ int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out7 /* 11 values */) {
   SP2_CUDA_OK(cudaMemcpyAsync(out7, st->clk, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(out7 + 7, st->gt, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(out7 + 11, &st->clk[7], sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(out7 + 12, &st->gt[4], sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return SP2_OK;
 }

@@ -234,6 +234,9 @@ int32_t sp2_host_free(sp2_ctx *ctx, void *p);
  * values (ns) of the last multi-CTA cubic round: [-, election, finalize end, first CTA entry], then the
  * clock64() start stamp of the previous tail round (12 values)                                    */
 int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out11);
+/* debug: rounds x 4 %globaltimer stamps (ns) of the last persistent cubic kernel (CTA 0): start, own compute done,
+ * all CTAs arrived, finalised                                                                      */
+int32_t sp2_debug_sc_round_profile(sp2_ctx *ctx, uint64_t *out, uint32_t rounds);
 
 /* harness support: n pseudo-random T256 points (seeded multiples of the generator) for test/bench keys.
  * (The reference derives its generators by hash-to-curve on the Rust side and ships them as bases.)        */

@@ -6,10 +6,11 @@
 namespace sp2 {
 
 // One field element per 256-bit transaction (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a):
-// a warp moves 1 KiB contiguous per request.
+// a warp moves 1 KiB contiguous per request.  Table loads are .cg (L2 only): streaming data has no L1 reuse, and the
+// persistent multi-round kernels re-read entries other CTAs wrote in the previous round.
 __device__ __forceinline__ fe ldg_fe(const fe *p) {
   fe r; u64 a, b, c, d;
-  asm volatile("ld.global.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
   r.v[0] = (u32)a; r.v[1] = (u32)(a >> 32); r.v[2] = (u32)b; r.v[3] = (u32)(b >> 32);
   r.v[4] = (u32)c; r.v[5] = (u32)(c >> 32); r.v[6] = (u32)d; r.v[7] = (u32)(d >> 32);
   return r;

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(64) k_outer_to_inner(ScState *outer, ScState *
     inner->ts.round = ts->round; inner->ts.pending_len = 0;
     for (int i = 0; i < 64; i++) inner->ts.state[i] = ts->state[i];
     stg_fe(&inner->claim, joint);
-    inner->ticket = 0; inner->l = (u32)rounds_inner; inner->flags = outer->flags;
+    inner->ticket = 0; inner->l = (u32)rounds_inner; inner->flags = outer->flags; inner->arrived = 0; inner->released = 0;
   }
 }
 

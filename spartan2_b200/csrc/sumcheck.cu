@@ -604,6 +604,166 @@ k_quad_tail(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int roun
   }
 }
 
+// ---- persistent multi-round kernels ------------------------------------------------------------------------
+// All multi-CTA rounds of a sum-check in ONE cooperative launch (one CTA per SM): per round every CTA computes its
+// partial sums, arrives at a grid barrier (monotonic counter), CTA 0 sums the partials, runs the finaliser (so the
+// finaliser's code and the transcript state stay warm on one SM) and releases the grid by publishing the round
+// number; the others spin on it.  Saves, per round, the launch gap (measured 5 us), the last-CTA election and a cold
+// finaliser (+5 us) of the one-launch-per-round scheme.
+__device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) { u32 v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
+// returns true on CTA 0 with the grid-wide sums in x (warp 0); other CTAs return false after the release
+template <int NV>
+__device__ __forceinline__ bool persist_gather(ScState *st, u32 seq, fe (&x)[NV], FinSmem &sm) {
+  const u32 G = gridDim.x, tid = threadIdx.x;
+  if (blockIdx.x != 0) {
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; k++) stg_fe(&st->partial[3 * blockIdx.x + k], x[k]);
+    }
+    __syncthreads();                                  // every thread's table stores of this round precede the fence
+    if (tid == 0) { __threadfence(); atomicAdd(&st->arrived, 1u); }
+    return false;
+  }
+  if (tid == 0) { while (ld_volatile_u32(&st->arrived) < (G - 1) * seq) {} __threadfence(); }
+  __syncthreads();
+  fe y[NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) y[k] = Fq::zero();
+  for (u32 b = 1 + tid; b < G; b += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) y[k] = Fq::add(y[k], ld_state(&st->partial[3 * b + k]));
+  }
+  block_sum_fq<NV>(y, sm.red);
+  if (tid < 32) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) x[k] = Fq::add(x[k], y[k]);
+  }
+  return true;
+}
+__device__ __forceinline__ void persist_release(ScState *st, u32 seq) {       // CTA 0, after the finaliser
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); *(volatile u32 *)&st->released = seq; }
+}
+__device__ __forceinline__ void persist_wait(ScState *st, u32 seq) {          // other CTAs
+  if (threadIdx.x == 0) { while (ld_volatile_u32(&st->released) < seq) {} __threadfence(); }
+  __syncthreads();
+}
+
+struct PersistCubic {
+  ScState *st; fe *A, *B, *C, *A2, *B2, *C2; int l, round_first, round_end; const fe *eq_left, *eq_right;
+};
+
+#ifndef SC_PERSIST_MINB
+#define SC_PERSIST_MINB 1
+#endif
+__global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_cubic_persist(PersistCubic a) {
+  __shared__ FinSmem sm;
+  ScState *st = a.st;
+  const int l = a.l, first_half = l / 2, second_half = l - first_half;
+  const u32 G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+  fe *sA = a.A, *sB = a.B, *sC = a.C, *dA = a.A2, *dB = a.B2, *dC = a.C2;
+  u32 seq = 0;
+  for (int round1 = a.round_first; round1 < a.round_end; round1++) {
+    const bool fused = round1 > 1;
+    const u64 P = (u64)1 << (l - round1);
+    const u64 len_in = fused ? 4 * P : 2 * P;
+    const bool in_first = round1 < first_half;
+    const fe *el = nullptr, *er; u32 out_len = 1, sh = 0;
+    if (in_first) {
+      const int kl = first_half - round1;
+      el = a.eq_left + (((size_t)1 << kl) - 1); out_len = 1u << kl;
+      er = a.eq_right + (((size_t)1 << second_half) - 1); sh = (u32)second_half;
+    } else {
+      er = a.eq_right + (((size_t)1 << (l - round1)) - 1);
+    }
+    if (bid == 0 && tid == 0) st->prof[round1 - 1][0] = gtimer();
+    fe r = Fq::zero();
+    if (fused) r = ld_state(&st->r[round1 - 2]);
+    fe x[3];
+    const bool roles = len_in <= SC_ROLE_LEN;
+    if (roles) {
+      // 256 threads = 2 role trios (warps 0..5); warps 6, 7 idle
+      const int w = tid >> 5, lane = tid & 31;
+      if (w < 6) {
+        const u64 first = ((u64)bid * 2 + w / 3) * 32 + lane, stride = (u64)G * 64;
+        if (fused) cubic_roles<true>(sA, sB, sC, dA, dB, dC, P, r, el, er, sh, w % 3, first, stride, x);
+        else cubic_roles<false>(sA, sB, sC, dA, dB, dC, P, r, el, er, sh, w % 3, first, stride, x);
+      } else { x[0] = Fq::zero(); x[1] = Fq::zero(); x[2] = Fq::zero(); }
+    } else {
+      const u64 in_len = (u64)1 << sh;
+      if (in_first && in_len >= SC_THREADS && in_len / SC_THREADS <= G) {
+        const u32 gx = (u32)(in_len / SC_THREADS); u32 gy = G / gx; if (gy > out_len) gy = out_len;
+        const u32 bx = bid % gx, by = bid / gx;
+        Fq::acc acc0 = Fq::acc_zero(), acc1 = Fq::acc_zero(), acci = Fq::acc_zero();
+        const u64 xi = (u64)bx * SC_THREADS + tid;
+        if (by < gy) {
+          if (fused) { for (u32 xo = by; xo < out_len; xo += gy) cubic_pair<true>(sA, sB, sC, ((u64)xo << sh) | xi, P, r, ldg_fe_ro(el + xo), acc0, acc1, acci); }
+          else { for (u32 xo = by; xo < out_len; xo += gy) cubic_pair<false>(sA, sB, sC, ((u64)xo << sh) | xi, P, r, ldg_fe_ro(el + xo), acc0, acc1, acci); }
+        }
+        const fe wr = ldg_fe_ro(er + xi);
+        x[0] = Fq::mul(wr, Fq::acc_reduce(acc0)); x[1] = Fq::mul(wr, Fq::acc_reduce(acc1)); x[2] = Fq::mul(wr, Fq::acc_reduce(acci));
+      } else {
+        if (fused) cubic_generic<true>(sA, sB, sC, P, r, el, er, sh, (u64)bid * SC_THREADS + tid, (u64)G * SC_THREADS, x);
+        else cubic_generic<false>(sA, sB, sC, P, r, el, er, sh, (u64)bid * SC_THREADS + tid, (u64)G * SC_THREADS, x);
+      }
+    }
+    block_sum_fq<3>(x, sm.red);
+    seq++;
+    const bool swapped = roles && fused;
+    if (swapped) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t; }
+    if (bid == 0 && tid == 0) st->prof[round1 - 1][1] = gtimer();
+    if (persist_gather<3>(st, seq, x, sm)) {
+      if (tid == 0) st->prof[round1 - 1][2] = gtimer();
+      cubic_finalize(st, round1, l, sA, sB, sC, x, sm);
+      if (tid == 0) st->prof[round1 - 1][3] = gtimer();
+      persist_release(st, seq);
+    } else {
+      persist_wait(st, seq);
+    }
+  }
+}
+
+struct PersistQuad { ScState *st; fe *A, *B, *A2, *B2; int rounds, round_first, round_end; u64 nvalid; };
+
+__global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_quad_persist(PersistQuad a) {
+  __shared__ FinSmem sm;
+  ScState *st = a.st;
+  const u32 G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+  fe *sA = a.A, *sB = a.B, *dA = a.A2, *dB = a.B2;
+  u32 seq = 0;
+  for (int round1 = a.round_first; round1 < a.round_end; round1++) {
+    const bool fused = round1 > 1;
+    const u64 P = (u64)1 << (a.rounds - round1);
+    const u64 len_in = fused ? 4 * P : 2 * P;
+    const u64 nv = round1 <= 2 ? a.nvalid : ~0ull;
+    fe r = Fq::zero();
+    if (fused) r = ld_state(&st->r[round1 - 2]);
+    fe x[2];
+    const bool roles = len_in <= SC_ROLE_LEN;
+    if (roles) {
+      const int w = tid >> 5, lane = tid & 31;
+      if (w < 6) {
+        const u64 first = ((u64)bid * 2 + w / 3) * 32 + lane, stride = (u64)G * 64;
+        if (fused) quad_roles<true>(sA, sB, dA, dB, P, r, w % 3, first, stride, nv, x);
+        else quad_roles<false>(sA, sB, dA, dB, P, r, w % 3, first, stride, nv, x);
+      } else { x[0] = Fq::zero(); x[1] = Fq::zero(); }
+    } else {
+      if (fused) quad_body<true>(sA, sB, P, r, (u64)bid * SC_THREADS + tid, (u64)G * SC_THREADS, nv, x);
+      else quad_body<false>(sA, sB, P, r, (u64)bid * SC_THREADS + tid, (u64)G * SC_THREADS, nv, x);
+    }
+    block_sum_fq<2>(x, sm.red);
+    seq++;
+    if (roles && fused) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; }
+    if (persist_gather<2>(st, seq, x, sm)) {
+      quad_finalize(st, round1, a.rounds, sA, sB, x, sm);
+      persist_release(st, seq);
+    } else {
+      persist_wait(st, seq);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -640,6 +800,7 @@ int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uin
   return SP2_OK;
 }
 
+static bool use_persistent() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_NO_PERSIST"); v = (e && e[0] == '1') ? 0 : 1; } return v == 1; }
 static DevComm comm_none() { DevComm d; memset(&d, 0, sizeof(d)); d.n = 1; return d; }
 
 // all-gather the shards (len_local entries per table) into every rank's gather area and return the local copy
@@ -675,7 +836,22 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     k_shard_barrier<<<1, 32, 0, ctx->stream>>>(dc, 0);          // every rank has finished the previous sharded call
     SP2_LAUNCH_CHECK();
   }
-  for (uint32_t round1 = 1; round1 <= l; round1++) {
+  uint32_t round_start = 1;
+  if (!sharded && use_persistent()) {
+    // all multi-CTA rounds in one cooperative launch (one CTA per SM), then the single-CTA tail
+    uint32_t round_end = 1;
+    while (round_end <= l && ((round_end > 1 ? 4ull : 2ull) << (l - round_end)) > SC_TAIL_LEN) round_end++;
+    if (round_end > 1) {
+      PersistCubic pa{st, A, B, C, dst[0], dst[1], dst[2], (int)l, 1, (int)round_end, eq_left, eq_right};
+      void *args[] = {&pa};
+      SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_cubic_persist, dim3(ctx->num_sms * SC_PERSIST_MINB), dim3(SC_THREADS), args, 0, ctx->stream));
+      ctx->launches++;
+      for (uint32_t rr = 2; rr < round_end; rr++)              // fused role rounds ping-pong src <-> dst
+        if ((4ull << (l - rr)) <= SC_ROLE_LEN) for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);
+      round_start = round_end;
+    }
+  }
+  for (uint32_t round1 = round_start; round1 <= l; round1++) {
     const bool fused = round1 > 1;
     const u64 Pg = (u64)1 << (l - round1);                      // pairs evaluated this round (global)
     const u64 len_in = fused ? 4 * Pg : 2 * Pg;                 // global table length going into this launch
@@ -745,7 +921,22 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
     k_shard_barrier<<<1, 32, 0, ctx->stream>>>(dc, 0);
     SP2_LAUNCH_CHECK();
   }
-  for (uint32_t round1 = 1; round1 <= rounds; round1++) {
+  uint32_t round_start = 1;
+  if (!sharded && use_persistent()) {
+    uint32_t round_end = 1;
+    while (round_end <= rounds && ((round_end > 1 ? 4ull : 2ull) << (rounds - round_end)) > SC_TAIL_LEN) round_end++;
+    if (round_end > 1) {
+      PersistQuad pa{st, A, B, dst[0], dst[1], (int)rounds, 1, (int)round_end, nvalid};
+      void *args[] = {&pa};
+      SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_quad_persist, dim3(ctx->num_sms * SC_PERSIST_MINB), dim3(SC_THREADS), args, 0, ctx->stream));
+      ctx->launches++;
+      if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
+      for (uint32_t rr = 2; rr < round_end; rr++)
+        if ((4ull << (rounds - rr)) <= SC_ROLE_LEN) { std::swap(src[0], dst[0]); std::swap(src[1], dst[1]); }
+      round_start = round_end;
+    }
+  }
+  for (uint32_t round1 = round_start; round1 <= rounds; round1++) {
     const u64 Pg = (u64)1 << (rounds - round1);
     const u64 len_in = round1 > 1 ? 4 * Pg : 2 * Pg;
     if (sharded && len_in <= SC_ROLE_LEN) {
@@ -788,6 +979,17 @@ extern "C" {
 
 /* debug: clock64() stamps (SM cycles) of the last finalised sum-check round: [tail round start, finalize start,
  * squeeze start, message built, hashed, challenge ready, finalize end] */
+/* debug: per-round %globaltimer stamps (ns) of the last persistent cubic kernel: rounds x [start, own compute done, all CTAs
+ * arrived, finalised] */
+int32_t sp2_debug_sc_round_profile(sp2_ctx *ctx, uint64_t *out, uint32_t rounds) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->slot[14] || rounds > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INTERNAL, "no sum-check has run");
+  ScState *st = (ScState *)ctx->slot[14];
+  SP2_CUDA_OK(cudaMemcpyAsync(out, st->prof, (size_t)rounds * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return SP2_OK;
+}
+
 int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out7 /* 11 values */) {
   cudaSetDevice(ctx->device);
   if (!ctx->slot[14]) return set_error(ctx, SP2_ERR_INTERNAL, "no sum-check has run");

@@ -18,7 +18,8 @@ struct ScState {
   fe claim;                   // quad: running claim (cubic sums t(0), t(1), t(inf) directly)
   fe p;                       // eval_eq_left (sumcheck.rs:951)
   fe L0, SL;                  // p*(1-tau_i), p*(2tau_i-1) for the round being evaluated
-  u32 ticket, l, flags, pad1;   // flags bit 0: warp-shuffle Keccak (default; measured 12.6k cycles/squeeze vs 22k for the one-thread register version)
+  u32 ticket, l, flags, arrived;     // arrived / released: monotonic counters of the persistent kernels' grid barrier
+  u32 released, pad1[3];   // flags bit 0: warp-shuffle Keccak (default; measured 12.6k cycles/squeeze vs 22k for the one-thread register version)
   fe taus[SC_MAX_ROUNDS];
   // ---- everything above is uploaded by the host; everything below is produced on the device ----
   fe r[SC_MAX_ROUNDS];
@@ -26,6 +27,7 @@ struct ScState {
   fe claims[4];
   unsigned long long clk[16];   // debug: clock64() stamps of the last finalised round (thread 0)
   unsigned long long gt[8];     // debug: %globaltimer (ns) of the last multi-CTA round: [first CTA entry, election, finalize end]
+  unsigned long long prof[SC_MAX_ROUNDS][4];   // debug: per persistent round on CTA 0: %globaltimer at start, own compute done, all arrived, finalised
   fe partial[3 * SC_MAX_BLOCKS];
 };
 

@@ -15,24 +15,45 @@ namespace sp2h {
 typedef unsigned __int128 u128;
 
 // ---- Keccak-256 (0x01 padding, not SHA-3) -------------------------------------------------------
-inline uint64_t rotl(uint64_t v, int n) { return n ? (v << n) | (v >> (64 - n)) : v; }
-inline void keccak_f(uint64_t a[25]) {
+#define SP2H_ROL(v, n) (((v) << (n)) | ((v) >> (64 - (n))))
+// Keccak-f[1600], fully unrolled rounds with the 25 lanes in locals (this hashes the tens of KB of commitment rows a
+// prove absorbs: ~0.3 us per permutation instead of ~3 us for a table-driven loop)
+inline void keccak_f(uint64_t st[25]) {
   static const uint64_t RC[24] = {
       0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
       0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
       0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
       0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-  static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  uint64_t a00 = st[0], a01 = st[1], a02 = st[2], a03 = st[3], a04 = st[4], a05 = st[5], a06 = st[6], a07 = st[7], a08 = st[8], a09 = st[9],
+           a10 = st[10], a11 = st[11], a12 = st[12], a13 = st[13], a14 = st[14], a15 = st[15], a16 = st[16], a17 = st[17], a18 = st[18],
+           a19 = st[19], a20 = st[20], a21 = st[21], a22 = st[22], a23 = st[23], a24 = st[24];
   for (int rnd = 0; rnd < 24; rnd++) {
-    uint64_t c[5], d[5], b[25];
-    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
-    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl(c[(x + 1) % 5], 1);
-    for (int y = 0; y < 5; y++)
-      for (int x = 0; x < 5; x++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl(a[x + 5 * y] ^ d[x], ROT[x + 5 * y]);
-    for (int y = 0; y < 5; y++)
-      for (int x = 0; x < 5; x++) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
-    a[0] ^= RC[rnd];
+    // theta
+    const uint64_t c0 = a00 ^ a05 ^ a10 ^ a15 ^ a20, c1 = a01 ^ a06 ^ a11 ^ a16 ^ a21, c2 = a02 ^ a07 ^ a12 ^ a17 ^ a22,
+                   c3 = a03 ^ a08 ^ a13 ^ a18 ^ a23, c4 = a04 ^ a09 ^ a14 ^ a19 ^ a24;
+    const uint64_t d0 = c4 ^ SP2H_ROL(c1, 1), d1 = c0 ^ SP2H_ROL(c2, 1), d2 = c1 ^ SP2H_ROL(c3, 1), d3 = c2 ^ SP2H_ROL(c4, 1), d4 = c3 ^ SP2H_ROL(c0, 1);
+    a00 ^= d0; a05 ^= d0; a10 ^= d0; a15 ^= d0; a20 ^= d0;
+    a01 ^= d1; a06 ^= d1; a11 ^= d1; a16 ^= d1; a21 ^= d1;
+    a02 ^= d2; a07 ^= d2; a12 ^= d2; a17 ^= d2; a22 ^= d2;
+    a03 ^= d3; a08 ^= d3; a13 ^= d3; a18 ^= d3; a23 ^= d3;
+    a04 ^= d4; a09 ^= d4; a14 ^= d4; a19 ^= d4; a24 ^= d4;
+    // rho + pi: b[y + 5*((2x+3y)%5)] = rot(a[x + 5y])
+    const uint64_t b00 = a00, b10 = SP2H_ROL(a01, 1), b20 = SP2H_ROL(a02, 62), b05 = SP2H_ROL(a03, 28), b15 = SP2H_ROL(a04, 27),
+                   b16 = SP2H_ROL(a05, 36), b01 = SP2H_ROL(a06, 44), b11 = SP2H_ROL(a07, 6), b21 = SP2H_ROL(a08, 55), b06 = SP2H_ROL(a09, 20),
+                   b07 = SP2H_ROL(a10, 3), b17 = SP2H_ROL(a11, 10), b02 = SP2H_ROL(a12, 43), b12 = SP2H_ROL(a13, 25), b22 = SP2H_ROL(a14, 39),
+                   b23 = SP2H_ROL(a15, 41), b08 = SP2H_ROL(a16, 45), b18 = SP2H_ROL(a17, 15), b03 = SP2H_ROL(a18, 21), b13 = SP2H_ROL(a19, 8),
+                   b14 = SP2H_ROL(a20, 18), b24 = SP2H_ROL(a21, 2), b09 = SP2H_ROL(a22, 61), b19 = SP2H_ROL(a23, 56), b04 = SP2H_ROL(a24, 14);
+    // chi
+    a00 = b00 ^ (~b01 & b02); a01 = b01 ^ (~b02 & b03); a02 = b02 ^ (~b03 & b04); a03 = b03 ^ (~b04 & b00); a04 = b04 ^ (~b00 & b01);
+    a05 = b05 ^ (~b06 & b07); a06 = b06 ^ (~b07 & b08); a07 = b07 ^ (~b08 & b09); a08 = b08 ^ (~b09 & b05); a09 = b09 ^ (~b05 & b06);
+    a10 = b10 ^ (~b11 & b12); a11 = b11 ^ (~b12 & b13); a12 = b12 ^ (~b13 & b14); a13 = b13 ^ (~b14 & b10); a14 = b14 ^ (~b10 & b11);
+    a15 = b15 ^ (~b16 & b17); a16 = b16 ^ (~b17 & b18); a17 = b17 ^ (~b18 & b19); a18 = b18 ^ (~b19 & b15); a19 = b19 ^ (~b15 & b16);
+    a20 = b20 ^ (~b21 & b22); a21 = b21 ^ (~b22 & b23); a22 = b22 ^ (~b23 & b24); a23 = b23 ^ (~b24 & b20); a24 = b24 ^ (~b20 & b21);
+    a00 ^= RC[rnd];
   }
+  st[0] = a00; st[1] = a01; st[2] = a02; st[3] = a03; st[4] = a04; st[5] = a05; st[6] = a06; st[7] = a07; st[8] = a08; st[9] = a09;
+  st[10] = a10; st[11] = a11; st[12] = a12; st[13] = a13; st[14] = a14; st[15] = a15; st[16] = a16; st[17] = a17; st[18] = a18; st[19] = a19;
+  st[20] = a20; st[21] = a21; st[22] = a22; st[23] = a23; st[24] = a24;
 }
 inline void keccak256(const uint8_t *in, size_t n, uint8_t suffix_byte, bool with_suffix, uint8_t out[32]) {
   uint64_t a[25]; memset(a, 0, sizeof(a));

@@ -309,22 +309,28 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   if (pre_rows) ts.absorb_commitment_be("comm_W_precommitted", P->comm_cached_be.data() + 64 * sh_rows, pre_rows);
   memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
   // commit the rest section (r1cs.rs:467-470: blind + commit / commit_zeros)
+  bool spmv_done = false;
   if (rest_rows) {
     SP2_TRY(sp2_hyrax_commit_dev(ctx, ck, P->W + P->cached_len, S->num_rest, P->blinds + P->cached_rows, rest_rows, P->points + P->cached_rows));
     std::vector<uint64_t> hj(rest_rows * 12);
     SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), P->points + P->cached_rows, rest_rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
-    SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                        // host sync 1
+    SP2_CUDA_OK(cudaEventRecord(P->ev_r1, ctx->stream));
+    // Az, Bz, Cz (spartan.rs:271 -> multiply_vec_incremental_into) do not depend on the taus: enqueue them now so they
+    // run while the host normalises / hashes the commitment rows
+    { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
+      SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
+    spmv_done = true;
+    SP2_CUDA_OK(cudaEventSynchronize(P->ev_r1));                            // host sync 1 (rows only)
     sp2h::batch_normalize(hj.data(), rest_rows, proof->comm_W + 8 * P->cached_rows);
   }
+  if (!spmv_done) { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
+    SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
   ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
   proof->num_rounds_x = l; proof->num_rounds_y = nry; proof->num_comm_rows = rows; proof->num_cols = width;
   uint8_t *tau_dg = P->h_inbox + P->inbox_bytes;
   for (int i = 0; i < l; i++) ts.squeeze("t", tau_dg + 64 * i);
   mark(1);
 
-  // ---- Az, Bz, Cz (spartan.rs:271 -> multiply_vec_incremental_into) ------------------------------
-  { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
-    SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
   mark(2);
 
   // ---- outer sum-check (spartan.rs:293 -> sumcheck.rs:502) ---------------------------------------

@@ -99,3 +99,39 @@ def test_sha256_circuit_prove(ctx, orc):
     assert orc.spartan_verify(O, keys, vk, X, vp) == 0
     sz = S.sizes()
     assert sz["num_cons"] == 1 << 16 and sz["long_rows"] > 0 and sz["long_cols"] > 0
+
+
+@pytest.mark.parametrize("msg_len", [2048])
+def test_full_size_config_proof_is_accepted_by_the_oracle_verifier(ctx, orc, msg_len):
+    """BASELINE config 2 at full size (2 KiB message, N = M = 2^20): the device-made proof must be accepted by the
+    oracle's restatement of SpartanSNARK::verify (src/spartan.rs:469-578), and rejected after tampering — the
+    size-independent property; bit-level comparison with the oracle prover is done at 2^16 above."""
+    import hashlib
+    import spartan2_b200 as sp
+    from spartan2_b200.frontend import Sha256Circuit
+    msg = b"\x00" * msg_len
+    circ = Sha256Circuit(msg)
+    assert circ.digest == hashlib.sha256(msg).digest()
+    width = 2048
+    pts = ctx.test_points(width + 3, seed=5)
+    ck, h, ck_s, h_s = pts[:width], pts[width:width + 1], pts[width + 1:width + 2], pts[width + 2:width + 3]
+    A, B, Cm = circ.matrices(); W, X = circ.witness()
+    nv = circ.num_vars; rows = nv // width; cl = circ.num_precommitted; cr = cl // width
+    rng = np.random.default_rng(msg_len)
+    blinds = rand_fe(rng, rows); be = rand_fe(rng, 1); dv = rand_fe(rng, width); rd = rand_fe(rng, 1); rb = rand_fe(rng, 1)
+    vk = bytes(range(32))
+    S = sp.SplitR1CSShape(ctx, *circ.dims(), A, B, Cm)
+    K = sp.CommitmentKey(ctx, ck, h, ck_s, h_s)
+    prep = sp.SpartanSNARK.prep_prove(ctx, S, K, W[:cl], blinds[:cr], is_small=True)
+    proof = sp.SpartanSNARK.prove(ctx, S, K, prep, vk, X, None, blinds, be, dv, rd, rb)
+    assert proof.l == 20 and proof.nry == 21 and proof.rows == 512
+    O = orc.Shape(*circ.dims(), A, B, Cm)
+    keys = orc.Keys(ck, h, ck_s, h_s)
+    orc.set_threads(orc.max_threads())
+    vp = orc.Proof(proof.l, proof.nry, proof.rows, proof.num_cols)
+    for f in sp.SpartanProof.FIELDS:
+        getattr(vp, f)[...] = getattr(proof, f).reshape(getattr(vp, f).shape)
+    assert orc.spartan_verify(O, keys, vk, X, vp) == 0
+    vp.z_vec[7, 1] ^= np.uint64(4)
+    assert orc.spartan_verify(O, keys, vk, X, vp) != 0
+    orc.set_threads(1)

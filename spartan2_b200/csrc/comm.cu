@@ -7,13 +7,6 @@
 
 using namespace sp2;
 
-struct sp2_comm {
-  sp2_ctx *ctx = nullptr;
-  DevComm dc;
-  bool connected = false;
-  bool opened[SC_MAX_RANKS] = {false};
-};
-
 extern "C" {
 
 int32_t sp2_comm_create(sp2_ctx *ctx, int32_t rank, int32_t nranks, sp2_comm **out) {

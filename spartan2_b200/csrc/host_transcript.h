@@ -154,53 +154,63 @@ inline void batch_normalize(const uint64_t *jac, size_t n, uint64_t *aff) {
   }
 }
 
+// ---- streaming Keccak-256 sponge: data is permuted as it is pushed, so bulk absorbs (commitment rows) are hashed
+// while the GPU is busy; squeeze only finishes the last block(s) ------------------------------------------------
+struct Sponge {
+  uint64_t a[25]; uint8_t blk[136]; size_t fill = 0;
+  Sponge() { memset(a, 0, sizeof(a)); }
+  void absorb(const void *p, size_t n) {
+    const uint8_t *q = (const uint8_t *)p;
+    while (n) {
+      const size_t take = n < 136 - fill ? n : 136 - fill;
+      memcpy(blk + fill, q, take); fill += take; q += take; n -= take;
+      if (fill == 136) { for (int i = 0; i < 17; i++) { uint64_t w; memcpy(&w, blk + 8 * i, 8); a[i] ^= w; } keccak_f(a); fill = 0; }
+    }
+  }
+  // digest of (everything absorbed || suffix byte), without disturbing this sponge
+  void finish_with_suffix(uint8_t sfx, uint8_t out[32]) const {
+    Sponge s = *this;
+    s.absorb(&sfx, 1);
+    memset(s.blk + s.fill, 0, 136 - s.fill);
+    s.blk[s.fill] ^= 0x01; s.blk[135] ^= 0x80;
+    for (int i = 0; i < 17; i++) { uint64_t w; memcpy(&w, s.blk + 8 * i, 8); s.a[i] ^= w; }
+    keccak_f(s.a);
+    memcpy(out, s.a, 32);
+  }
+};
+inline void point_be(const uint64_t *xy, uint8_t out[64]) {   // traits.rs:288-305: x_BE || y_BE
+  uint64_t c[4];
+  from_mont(xy, FP_MOD, FP_INV, c); limbs_to_be(c, out);
+  from_mont(xy + 4, FP_MOD, FP_INV, c); limbs_to_be(c, out + 32);
+}
+
 // ---- Keccak256Transcript --------------------------------------------------------------------------
 struct Transcript {
   uint16_t round = 0;
   uint8_t state[64];
-  std::vector<uint8_t> buf;
+  Sponge sp;                       // absorbs since the last squeeze (keccak.rs keeps them in a buffer and hashes at squeeze)
 
-  // keccak.rs:33-54: K(in || 0x00) || K(in || 0x01).  The two messages share every full block of `in`: absorb
-  // those once, then fork the sponge for the two one-byte suffixes.
+  // keccak.rs:33-54: K(in || 0x00) || K(in || 0x01)
   static void updated_state(const uint8_t *in, size_t n, uint8_t out[64]) {
-    uint64_t a[25]; memset(a, 0, sizeof(a));
-    const size_t full = n / 136;
-    for (size_t b = 0; b < full; b++) {
-      for (int i = 0; i < 17; i++) { uint64_t w; memcpy(&w, in + 136 * b + 8 * i, 8); a[i] ^= w; }
-      keccak_f(a);
-    }
-    const size_t rem = n - 136 * full;              // < 136 bytes left, then the suffix byte, then padding
-    for (int sfx = 0; sfx < 2; sfx++) {
-      uint64_t s[25]; memcpy(s, a, sizeof(s));
-      uint8_t blk[272]; memset(blk, 0, sizeof(blk));
-      memcpy(blk, in + 136 * full, rem);
-      blk[rem] = (uint8_t)sfx;
-      const size_t total = rem + 1, nb = total / 136 + 1;
-      blk[total] ^= 0x01; blk[136 * nb - 1] ^= 0x80;
-      for (size_t b = 0; b < nb; b++) {
-        for (int i = 0; i < 17; i++) { uint64_t w; memcpy(&w, blk + 136 * b + 8 * i, 8); s[i] ^= w; }
-        keccak_f(s);
-      }
-      memcpy(out + 32 * sfx, s, 32);
-    }
+    Sponge s; s.absorb(in, n);
+    s.finish_with_suffix(0x00, out); s.finish_with_suffix(0x01, out + 32);
   }
   explicit Transcript(const char *label) {                                       // keccak.rs:57-68
     std::vector<uint8_t> in; const char *p = "NoTR"; in.insert(in.end(), p, p + 4); in.insert(in.end(), label, label + strlen(label));
     updated_state(in.data(), in.size(), state);
   }
+  // a transcript whose (round, state) are not known yet (they are spliced in at squeeze time, after the absorbed data)
+  Transcript() { memset(state, 0, 64); }
   Transcript(uint16_t rnd, const uint8_t st[64]) : round(rnd) { memcpy(state, st, 64); }
-  void push(const void *p, size_t n) { const uint8_t *q = (const uint8_t *)p; buf.insert(buf.end(), q, q + n); }
+  void set_state(uint16_t rnd, const uint8_t st[64]) { round = rnd; memcpy(state, st, 64); }
+  void push(const void *p, size_t n) { sp.absorb(p, n); }
   void absorb_bytes(const char *label, const void *p, size_t n) { push(label, strlen(label)); push(p, n); }   // keccak.rs:96-99
   void dom_sep(const char *b) { push("NoDS", 4); push(b, strlen(b)); }                                       // keccak.rs:101-104
   void absorb_scalars(const char *label, const uint64_t *mont, size_t n) {       // traits.rs:282-286: 32 bytes big-endian each
     push(label, strlen(label));
     for (size_t i = 0; i < n; i++) { uint64_t c[4]; uint8_t b[32]; from_mont(mont + 4 * i, FQ_MOD, FQ_INV, c); limbs_to_be(c, b); push(b, 32); }
   }
-  void push_point(const uint64_t *xy) {                                          // traits.rs:288-305: x_BE || y_BE
-    uint64_t c[4]; uint8_t b[32];
-    from_mont(xy, FP_MOD, FP_INV, c); limbs_to_be(c, b); push(b, 32);
-    from_mont(xy + 4, FP_MOD, FP_INV, c); limbs_to_be(c, b); push(b, 32);
-  }
+  void push_point(const uint64_t *xy) { uint8_t b[64]; point_be(xy, b); push(b, 64); }
   void absorb_point(const char *label, const uint64_t *xy) { push(label, strlen(label)); push_point(xy); }
   void absorb_commitment(const char *label, const uint64_t *rows_xy, size_t rows) {   // hyrax_pc.rs:714-729
     push(label, strlen(label));
@@ -219,10 +229,10 @@ struct Transcript {
   void squeeze(const char *label, uint8_t out[64]) {
     const uint8_t le[2] = {(uint8_t)(round & 0xff), (uint8_t)(round >> 8)};
     push("NoDS", 4); push(le, 2); push(state, 64); push(label, strlen(label));
-    updated_state(buf.data(), buf.size(), out);
+    sp.finish_with_suffix(0x00, out); sp.finish_with_suffix(0x01, out + 32);
     round++;
     memcpy(state, out, 64);
-    buf.clear();
+    sp = Sponge();
   }
 };
 

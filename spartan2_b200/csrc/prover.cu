@@ -237,9 +237,8 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return fail(set_cuda_error(ctx, e, "prep download", __LINE__));
     sp2h::batch_normalize(hj.data(), P->cached_rows, P->comm_cached.data());
-    sp2h::Transcript tmp(0, (const uint8_t *)hj.data());           // (only used for its point encoder)
-    for (uint64_t i = 0; i < P->cached_rows; i++) tmp.push_point(P->comm_cached.data() + 8 * i);
-    P->comm_cached_be = tmp.buf;
+    P->comm_cached_be.resize(64 * P->cached_rows);
+    for (uint64_t i = 0; i < P->cached_rows; i++) sp2h::point_be(P->comm_cached.data() + 8 * i, P->comm_cached_be.data() + 64 * i);
   }
   // cached partial products: z = [W_cached | 0 ... 0]
   e = cudaMemsetAsync(P->z, 0, nc * sizeof(fe), ctx->stream);
@@ -326,6 +325,15 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   if (!spmv_done) { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
     SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
   ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
+  // the PCS transcript (hyrax_pc.rs:410) re-absorbs all commitment rows; its (round, state) come from the device after the
+  // sum-checks, but they enter the hash AFTER the absorbed data, so the rows are hashed now, under the sum-checks
+  sp2h::Transcript t2;
+  auto absorb_poly_com = [&]() {
+    t2.push("poly_com", 8); t2.push("poly_commitment_begin", 21);
+    t2.push(P->comm_cached_be.data(), P->comm_cached_be.size());
+    for (uint64_t i = P->cached_rows; i < rows; i++) t2.push_point(proof->comm_W + 8 * i);
+    t2.push("poly_commitment_end", 19);
+  };
   proof->num_rounds_x = l; proof->num_rounds_y = nry; proof->num_comm_rows = rows; proof->num_cols = width;
   uint8_t *tau_dg = P->h_inbox + P->inbox_bytes;
   for (int i = 0; i < l; i++) ts.squeeze("t", tau_dg + 64 * i);
@@ -397,6 +405,7 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   SP2_TRY(msm_run(ctx, ck, jobs, d_pts));
   mark(6);
 
+  absorb_poly_com();                                                        // host hashing overlapped with the device work above
   // ---- results so far -> host -------------------------------------------------------------------
   void *hp; SP2_TRY(pinned(ctx, 2 * sizeof(ScState) + 4096, &hp));
   ScState *h_outer = (ScState *)hp, *h_inner = h_outer + 1;
@@ -427,11 +436,7 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   memcpy(proof->delta, p_delta, 64); memcpy(proof->beta, p_beta, 64);
 
   // ---- transcript tail on the host: poly_com rows, IPA absorbs, r (hyrax_pc.rs:410; ipa.rs:134-153) ----
-  sp2h::Transcript t2((uint16_t)h_inner->ts.round, h_inner->ts.state);
-  t2.push("poly_com", 8); t2.push("poly_commitment_begin", 21);
-  t2.push(P->comm_cached_be.data(), P->comm_cached_be.size());
-  for (uint64_t i = P->cached_rows; i < rows; i++) t2.push_point(proof->comm_W + 8 * i);
-  t2.push("poly_commitment_end", 19);
+  t2.set_state((uint16_t)h_inner->ts.round, h_inner->ts.state);
   t2.dom_sep("inner product argument (linear)");
   t2.push("U", 1); t2.push_point(comm_LZ); t2.push_point(p_ceval);
   t2.absorb_point("delta", p_delta);

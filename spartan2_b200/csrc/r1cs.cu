@@ -168,7 +168,7 @@ int spmv3_dev(sp2_ctx *ctx, const sp2_shape *S, const DevMatrix *mats, const fe 
     a.base[k] = base ? base[k] : nullptr; a.out[k] = out[k];
     maxlong = std::max(maxlong, mats[k].nlong);
   }
-  const u32 nrows = (u32)S->num_cons;
+  const u32 nrows = (u32)S->rows_local;
   k_spmv3<<<dim3((nrows + 255) / 256, 3), 256, 0, ctx->stream>>>(a, nrows, d_z);
   SP2_LAUNCH_CHECK();
   if (maxlong) {
@@ -181,7 +181,7 @@ int spmv3_dev(sp2_ctx *ctx, const sp2_shape *S, const DevMatrix *mats, const fe 
 int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe *d_out, uint64_t out_len) {
   AbcArgs a;
   for (int k = 0; k < 3; k++) { a.ptr[k] = S->T[k].ptr; a.ent[k] = S->T[k].ent; a.dict[k] = S->T[k].dict; }
-  const u32 ncols = (u32)S->num_cols;
+  const u32 ncols = (u32)S->cols_local;                    // == num_cols on a single GPU
   if (out_len < ncols) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "abc: output shorter than num_vars + num_extra");
   if (out_len > ncols) SP2_CUDA_OK(cudaMemsetAsync(d_out + ncols, 0, (out_len - ncols) * sizeof(fe), ctx->stream));
   k_abc<<<(ncols + 255) / 256, 256, 0, ctx->stream>>>(a, ncols, d_rx, d_r, d_out);
@@ -201,26 +201,29 @@ int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe 
 
 extern "C" {
 
-int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpadded, uint64_t num_shared, uint64_t num_precommitted,
-                         uint64_t num_rest, uint64_t num_public, uint64_t num_challenges,
-                         const uint64_t *dataA, const uint32_t *indicesA, const uint32_t *indptrA,
-                         const uint64_t *dataB, const uint32_t *indicesB, const uint32_t *indptrB,
-                         const uint64_t *dataC, const uint32_t *indicesC, const uint32_t *indptrC, sp2_shape **out) {
+static int32_t shape_upload_impl(sp2_ctx *ctx, int rank, int nranks, uint64_t num_cons, uint64_t num_cons_unpadded, uint64_t num_shared,
+                                 uint64_t num_precommitted, uint64_t num_rest, uint64_t num_public, uint64_t num_challenges,
+                                 const uint64_t *const *datas, const uint32_t *const *inds, const uint32_t *const *ptrs, sp2_shape **out) {
   cudaSetDevice(ctx->device);
   if (!out) return SP2_ERR_INTERNAL;
   *out = nullptr;
   if (num_cons == 0 || (num_cons & (num_cons - 1)) || num_cons > (1ull << 31)) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "shape: num_cons must be a power of two");
+  int sk = 0; while ((1 << sk) < nranks) sk++;
+  if (nranks < 1 || (1 << sk) != nranks || rank < 0 || rank >= nranks || (uint64_t)nranks > num_cons)
+    return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "shape: the number of ranks must be a power of two <= num_cons");
   sp2_shape *S = new sp2_shape();
   S->ctx = ctx;
   S->num_cons = num_cons; S->num_cons_unpadded = num_cons_unpadded; S->num_shared = num_shared; S->num_precommitted = num_precommitted;
   S->num_rest = num_rest; S->num_public = num_public; S->num_challenges = num_challenges;
   S->num_vars = num_shared + num_precommitted + num_rest;
   S->num_cols = S->num_vars + 1 + num_public + num_challenges;
-  const uint64_t *datas[3] = {dataA, dataB, dataC};
-  const uint32_t *inds[3] = {indicesA, indicesB, indicesC};
-  const uint32_t *ptrs[3] = {indptrA, indptrB, indptrC};
+  S->rank = rank; S->nranks = nranks; S->shard_k = sk;
+  const u32 G = (u32)nranks, gmask = G - 1;
+  const size_t rows_local = num_cons >> sk;
+  const size_t cols_local = S->num_cols > (uint64_t)rank ? (S->num_cols - rank + G - 1) / G : 0;
+  S->rows_local = rows_local; S->cols_local = cols_local;
   const u32 col_min = (u32)(num_shared + num_precommitted);
-  std::vector<u32> coldeg(S->num_cols, 0);
+  std::vector<u32> coldeg(cols_local, 0);
   std::vector<u32> tptr[3];
   int rc = SP2_OK;
   for (int k = 0; k < 3 && rc == SP2_OK; k++) {
@@ -233,26 +236,27 @@ int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpa
     ht.dict = hm.dict; hf.dict = hm.dict;
     S->nnz_total += nnz;
     for (size_t e = 0; e < nnz; e++) if (cid[e] > 1) S->nnz_general++;
-    // row-major + filtered row-major
-    hm.ptr.assign(ptrs[k], ptrs[k] + num_cons + 1);
-    hm.ent.resize(nnz);
-    hf.ptr.resize(num_cons + 1);
-    for (size_t row = 0; row < num_cons; row++) {
-      hf.ptr[row] = (u32)hf.ent.size();
+    // row-major + filtered row-major, this rank's rows only (all rows on a single GPU)
+    hm.ptr.resize(rows_local + 1); hf.ptr.resize(rows_local + 1);
+    for (size_t lr = 0; lr < rows_local; lr++) {
+      const size_t row = (lr << sk) | (size_t)rank;
+      hm.ptr[lr] = (u32)hm.ent.size(); hf.ptr[lr] = (u32)hf.ent.size();
       for (u32 e = ptrs[k][row]; e < ptrs[k][row + 1]; e++) {
-        hm.ent[e] = make_uint2(inds[k][e], cid[e]);
-        if (inds[k][e] >= col_min) hf.ent.push_back(hm.ent[e]);
+        const uint2 en = make_uint2(inds[k][e], cid[e]);
+        hm.ent.push_back(en);
+        if (inds[k][e] >= col_min) hf.ent.push_back(en);
       }
     }
-    hf.ptr[num_cons] = (u32)hf.ent.size();
-    // transpose by counting sort
-    ht.ptr.assign(S->num_cols + 1, 0);
-    for (size_t e = 0; e < nnz; e++) ht.ptr[inds[k][e] + 1]++;
-    for (size_t c = 0; c < S->num_cols; c++) { coldeg[c] += ht.ptr[c + 1]; ht.ptr[c + 1] += ht.ptr[c]; }
-    ht.ent.resize(nnz);
+    hm.ptr[rows_local] = (u32)hm.ent.size(); hf.ptr[rows_local] = (u32)hf.ent.size();
+    // transpose by counting sort, this rank's columns only; entries gather eq(r_x) at the GLOBAL row
+    ht.ptr.assign(cols_local + 1, 0);
+    for (size_t e = 0; e < nnz; e++) if ((inds[k][e] & gmask) == (u32)rank) ht.ptr[(inds[k][e] >> sk) + 1]++;
+    for (size_t c = 0; c < cols_local; c++) { coldeg[c] += ht.ptr[c + 1]; ht.ptr[c + 1] += ht.ptr[c]; }
+    ht.ent.resize(ht.ptr[cols_local]);
     { std::vector<u32> cur(ht.ptr.begin(), ht.ptr.end() - 1);
       for (size_t row = 0; row < num_cons; row++)
-        for (u32 e = ptrs[k][row]; e < ptrs[k][row + 1]; e++) ht.ent[cur[inds[k][e]]++] = make_uint2((u32)row, cid[e]); }
+        for (u32 e = ptrs[k][row]; e < ptrs[k][row + 1]; e++)
+          if ((inds[k][e] & gmask) == (u32)rank) ht.ent[cur[inds[k][e] >> sk]++] = make_uint2((u32)row, cid[e]); }
     tptr[k] = ht.ptr;
     mark_long(hm); mark_long(hf);
     rc = upload_matrix(S, hm, &S->M[k]);
@@ -261,7 +265,7 @@ int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpa
   }
   if (rc == SP2_OK) {
     std::vector<u32> lc;
-    for (size_t c = 0; c < S->num_cols; c++) if (coldeg[c] > LONG_SEG) lc.push_back((u32)c);
+    for (size_t c = 0; c < cols_local; c++) if (coldeg[c] > LONG_SEG) lc.push_back((u32)c);
     S->nlong_cols = (u32)lc.size();
     cudaError_t e = cudaMalloc((void **)&S->long_cols, lc.size() * 4 + 32);
     if (e != cudaSuccess) rc = set_cuda_error(ctx, e, "cudaMalloc", __LINE__);
@@ -291,6 +295,32 @@ int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpa
   if (rc != SP2_OK) { for (void *p : S->owned) cudaFree(p); delete S; return rc; }
   *out = S;
   return SP2_OK;
+}
+
+int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpadded, uint64_t num_shared, uint64_t num_precommitted,
+                         uint64_t num_rest, uint64_t num_public, uint64_t num_challenges,
+                         const uint64_t *dataA, const uint32_t *indicesA, const uint32_t *indptrA,
+                         const uint64_t *dataB, const uint32_t *indicesB, const uint32_t *indptrB,
+                         const uint64_t *dataC, const uint32_t *indicesC, const uint32_t *indptrC, sp2_shape **out) {
+  const uint64_t *datas[3] = {dataA, dataB, dataC};
+  const uint32_t *inds[3] = {indicesA, indicesB, indicesC};
+  const uint32_t *ptrs[3] = {indptrA, indptrB, indptrC};
+  return shape_upload_impl(ctx, 0, 1, num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges,
+                           datas, inds, ptrs, out);
+}
+
+/* One rank's shard of the shape for the multi-GPU prover: same (whole) CSR inputs on every rank; rank g keeps the rows
+ * i = g (mod nranks) of A, B, C and the columns j = g (mod nranks) of their transposes. */
+int32_t sp2_shape_upload_sharded(sp2_ctx *ctx, int32_t rank, int32_t nranks, uint64_t num_cons, uint64_t num_cons_unpadded, uint64_t num_shared,
+                                 uint64_t num_precommitted, uint64_t num_rest, uint64_t num_public, uint64_t num_challenges,
+                                 const uint64_t *dataA, const uint32_t *indicesA, const uint32_t *indptrA,
+                                 const uint64_t *dataB, const uint32_t *indicesB, const uint32_t *indptrB,
+                                 const uint64_t *dataC, const uint32_t *indicesC, const uint32_t *indptrC, sp2_shape **out) {
+  const uint64_t *datas[3] = {dataA, dataB, dataC};
+  const uint32_t *inds[3] = {indicesA, indicesB, indicesC};
+  const uint32_t *ptrs[3] = {indptrA, indptrB, indptrC};
+  return shape_upload_impl(ctx, rank, nranks, num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges,
+                           datas, inds, ptrs, out);
 }
 
 void sp2_shape_free(sp2_shape *S) {
@@ -326,7 +356,7 @@ int32_t sp2_spmv3_incremental_dev(sp2_ctx *ctx, const sp2_shape *S, const void *
 int32_t sp2_spmv3(sp2_ctx *ctx, const sp2_shape *S, const uint64_t *z, uint64_t z_len, uint64_t *az, uint64_t *bz, uint64_t *cz) {
   cudaSetDevice(ctx->device);
   if (z_len != S->num_cols) return set_error(ctx, SP2_ERR_INVALID_WITNESS_LENGTH, "multiply_vec: z has the wrong length");
-  const size_t nb = S->num_cons * sizeof(fe);
+  const size_t nb = S->rows_local * sizeof(fe);
   void *dz, *da, *db, *dc;
   SP2_TRY(scratch(ctx, 0, z_len * sizeof(fe), &dz)); SP2_TRY(scratch(ctx, 1, nb, &da)); SP2_TRY(scratch(ctx, 2, nb, &db)); SP2_TRY(scratch(ctx, 3, nb, &dc));
   SP2_CUDA_OK(cudaMemcpyAsync(dz, z, z_len * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
@@ -342,7 +372,7 @@ int32_t sp2_spmv3_incremental(sp2_ctx *ctx, const sp2_shape *S, const uint64_t *
                               const uint64_t *cached_bz, const uint64_t *cached_cz, uint64_t *az, uint64_t *bz, uint64_t *cz) {
   cudaSetDevice(ctx->device);
   if (z_len != S->num_cols) return set_error(ctx, SP2_ERR_INVALID_WITNESS_LENGTH, "multiply_vec_incremental: z has the wrong length");
-  const size_t nb = S->num_cons * sizeof(fe);
+  const size_t nb = S->rows_local * sizeof(fe);
   void *dz, *d[3];
   SP2_TRY(scratch(ctx, 0, z_len * sizeof(fe), &dz));
   for (int k = 0; k < 3; k++) SP2_TRY(scratch(ctx, 1 + k, nb, &d[k]));

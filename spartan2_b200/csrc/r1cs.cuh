@@ -32,6 +32,12 @@ struct sp2_shape {
   sp2_ctx *ctx = nullptr;
   uint64_t num_cons = 0, num_cons_unpadded = 0, num_shared = 0, num_precommitted = 0, num_rest = 0, num_public = 0, num_challenges = 0;
   uint64_t num_vars = 0, num_cols = 0;       // num_cols = num_vars + 1 + num_public + num_challenges
+  // Multi-GPU shard of the shape: rank g of G = 2^shard_k keeps the rows i = g (mod G) of M and F
+  // (local row i >> shard_k: Az/Bz/Cz land directly in the cyclic sum-check layout) and the columns j = g (mod G) of
+  // the transposes T (local column j >> shard_k: poly_ABC lands in the inner sum-check's cyclic layout).  Gathered
+  // vectors (z for M/F, eq(r_x) for T) are replicated and indexed globally.  rank 0 of 1 = the whole shape.
+  int rank = 0, nranks = 1, shard_k = 0;
+  uint64_t rows_local = 0, cols_local = 0;   // num_cons >> shard_k; number of columns j < num_cols with j = rank (mod G)
   sp2::DevMatrix M[3];                       // A, B, C row-major
   sp2::DevMatrix T[3];                       // transposes (column-major) for bind_and_prepare_poly_ABC
   sp2::DevMatrix F[3];                       // row-major, columns >= num_shared + num_precommitted only (FilteredSpmv)

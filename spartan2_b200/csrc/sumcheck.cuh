@@ -50,6 +50,15 @@ struct DevComm {
   MailBox *peer[SC_MAX_RANKS];   // peer[rank] is the local mailbox
 };
 
+}  // namespace sp2
+struct sp2_comm {                // host handle of one rank's endpoint (comm.cu)
+  sp2_ctx *ctx = nullptr;
+  sp2::DevComm dc;
+  bool connected = false;
+  bool opened[sp2::SC_MAX_RANKS] = {false};
+};
+namespace sp2 {
+
 int sc_state_upload(sp2_ctx *ctx, ScState **d_st, const uint64_t *claim, const uint64_t *taus, uint32_t l,
                     const sp2_transcript_state *ts);
 int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uint64_t *polys, int ncoef, uint64_t *r,

@@ -121,6 +121,16 @@ int32_t sp2_shape_upload(sp2_ctx *ctx, uint64_t num_cons, uint64_t num_cons_unpa
                          const uint64_t *dataA, const uint32_t *indicesA, const uint32_t *indptrA,
                          const uint64_t *dataB, const uint32_t *indicesB, const uint32_t *indptrB,
                          const uint64_t *dataC, const uint32_t *indicesC, const uint32_t *indptrC, sp2_shape **out);
+/* One rank's shard of the shape for the multi-GPU prover: every rank passes the same whole CSR matrices;
+ * rank g of nranks = 2^k keeps rows i = g (mod nranks) of A, B, C (so Az/Bz/Cz land directly in the cyclic sum-check
+ * layout, local row i >> k) and columns j = g (mod nranks) of the transposes (poly_ABC lands in the inner sum-check's
+ * cyclic layout).  With such a handle sp2_spmv3* produce num_cons / nranks rows and sp2_abc* this rank's columns.   */
+int32_t sp2_shape_upload_sharded(sp2_ctx *ctx, int32_t rank, int32_t nranks, uint64_t num_cons, uint64_t num_cons_unpadded,
+                                 uint64_t num_shared, uint64_t num_precommitted, uint64_t num_rest, uint64_t num_public,
+                                 uint64_t num_challenges,
+                                 const uint64_t *dataA, const uint32_t *indicesA, const uint32_t *indptrA,
+                                 const uint64_t *dataB, const uint32_t *indicesB, const uint32_t *indptrB,
+                                 const uint64_t *dataC, const uint32_t *indicesC, const uint32_t *indptrC, sp2_shape **out);
 void sp2_shape_free(sp2_shape *shape);
 /* pk.sizes() analogue: [num_cons, num_vars, num_cols, nnz, general nnz, long rows, long columns]  */
 int32_t sp2_shape_sizes(const sp2_shape *shape, uint64_t *out7);
@@ -190,6 +200,14 @@ void sp2_prep_free(sp2_prep *prep);
 int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck, sp2_prep *prep, const uint8_t *vk_digest,
                           const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rand,
                           sp2_spartan_proof *proof, float *phase_ms);
+
+/* SpartanSNARK::prove with the 2^l hypercube split across the GPUs of `comm` (one process per GPU).  Every
+ * rank calls with the same inputs, its shard of the shape (sp2_shape_upload_sharded) and the prep state made from it,
+ * and receives the identical proof.  Sharded: Az/Bz/Cz rows, both sum-checks (per round the <= 3 partial sums cross
+ * NVLink inside the round kernel), poly_ABC columns.  Replicated: witness, commitments, eq(r_x), Hyrax bind, PCS MSMs. */
+int32_t sp2_spartan_prove_sharded(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape *shape, const sp2_ck *ck, sp2_prep *prep,
+                                  const uint8_t *vk_digest, const uint64_t *public_values, const uint64_t *W_rest,
+                                  const sp2_spartan_rand *rand, sp2_spartan_proof *proof, float *phase_ms);
 
 /* ---- NeutronNova building blocks (src/neutronnova_zk.rs, src/polys/power.rs, src/r1cs/mod.rs) ------------
  * The ZK drivers draw one challenge per round from the in-circuit verifier (process_round, out of scope), so the

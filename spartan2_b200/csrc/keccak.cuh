@@ -67,6 +67,26 @@ __device__ __forceinline__ u64 keccak_f_warp(u64 s, const KeccakLane &k, int lan
   return s;
 }
 
+// Variant with theta as ONE shuffle stage: d(x) = XOR_y s[x-1,y] ^ rotl1(XOR_y s[x+1,y]) gathered straight from s (ten
+// independent gathers) instead of column parities followed by a dependent neighbour exchange: two dependent shuffle
+// stages per round instead of three, at the price of 8 more SHFLs.
+__device__ __forceinline__ u64 keccak_f_warp2(u64 s, const KeccakLane &k, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const int xm = k.xm1 % 5, xp = k.xp1 % 5;
+#pragma unroll 1
+  for (int rnd = 0; rnd < 24; rnd++) {
+    u64 a = __shfl_sync(FULL, s, xm), b = __shfl_sync(FULL, s, xp);
+#pragma unroll
+    for (int y = 1; y < 5; y++) { a ^= __shfl_sync(FULL, s, xm + 5 * y); b ^= __shfl_sync(FULL, s, xp + 5 * y); }
+    s ^= a ^ rotl64(b, 1);
+    const u64 t = rotl64(s, k.rot);
+    const u64 b0 = __shfl_sync(FULL, t, k.src), b1 = __shfl_sync(FULL, t, k.src1), b2 = __shfl_sync(FULL, t, k.src2);
+    s = b0 ^ (~b1 & b2);
+    if (lane == 0) s ^= KECCAK_RC_D[rnd];
+  }
+  return s;
+}
+
 // Keccak-256 of msg[0..len) || suffix by one warp; msg in shared (or global) memory.
 // Returns the digest word (u64) in lanes 0..3.
 __device__ __forceinline__ u64 keccak256_warp(const unsigned char *msg, int len, unsigned char suffix, int lane) {

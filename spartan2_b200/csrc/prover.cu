@@ -35,7 +35,8 @@ struct sp2_prep {
   fe *W = nullptr;                   // num_vars (cached part filled by prep_prove, rest by prove)
   fe *cached[3] = {nullptr, nullptr, nullptr};   // Az/Bz/Cz over the shared+precommitted columns (spartan.rs:184-187)
   fe *work[3] = {nullptr, nullptr, nullptr};     // sum-check tables
-  fe *z = nullptr, *abc = nullptr;   // num_cols each
+  fe *z = nullptr, *abc = nullptr;   // num_cols each (abc: 2M/G, dense, when the shape is a multi-GPU shard)
+  fe *zs = nullptr, *rx = nullptr;   // multi-GPU only: this rank's cyclic shard of the virtual 2M-entry z table; full eq(r_x)
   fe *blinds = nullptr;              // rows_total
   fe *small = nullptr;               // scalars scratch (see offsets below)
   jac *points = nullptr;             // device points scratch (Jacobian): [rows_total comm rows | 4 PCS points]
@@ -74,6 +75,13 @@ __global__ void k_z_tail(fe *ztail, const fe *X, u32 num_public) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) stg_fe(ztail, Fq::one());
   if (i < num_public) stg_fe(ztail + 1 + i, ldg_fe(X + i));
+}
+// multi-GPU: this rank's cyclic shard of the inner sum-check's virtual z table (2M entries: z | zeros)
+__global__ void __launch_bounds__(256) k_z_shard(const fe *z, u64 nc, fe *zs, u64 len_local, int k, int rank) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len_local) return;
+  const u64 g = (i << k) | (u64)rank;
+  stg_fe(zs + i, g < nc ? ldg_fe(z + g) : Fq::zero());
 }
 // 1 / (1 - r_y[0]) as soon as the first inner challenge exists (side stream, overlaps the remaining inner rounds)
 __global__ void k_den_inv(const ScState *inner, fe *small) {
@@ -204,12 +212,15 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
   sp2_prep *P = new sp2_prep();
   P->ctx = ctx; P->S = S; P->ck = ck;
   P->cached_len = S->num_shared + S->num_precommitted; P->cached_rows = P->cached_len / width; P->rows_total = nv / width;
-  const uint64_t N = S->num_cons, nc = S->num_cols;
+  const uint64_t N = S->num_cons, nc = S->num_cols, Nl = S->rows_local;
+  const bool shard = S->nranks > 1;
+  if (shard && ((2 * nv) >> S->shard_k) == 0) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "prep_prove: fewer variables than ranks");
   int rc = SP2_OK;
   auto A = [&](int r) { if (rc == SP2_OK) rc = r; };
   A(palloc(P, &P->W, nv));
-  for (int k = 0; k < 3; k++) { A(palloc(P, &P->cached[k], N)); A(palloc(P, &P->work[k], N)); }
-  A(palloc(P, &P->z, nc)); A(palloc(P, &P->abc, nc));
+  for (int k = 0; k < 3; k++) { A(palloc(P, &P->cached[k], Nl)); A(palloc(P, &P->work[k], Nl)); }
+  A(palloc(P, &P->z, nc)); A(palloc(P, &P->abc, shard ? (2 * nv) >> S->shard_k : nc));
+  if (shard) { A(palloc(P, &P->zs, (2 * nv) >> S->shard_k)); A(palloc(P, &P->rx, N)); }
   A(palloc(P, &P->points, P->rows_total + 8));
   A(palloc(P, &P->LZ, width)); A(palloc(P, &P->Ltab, std::max<uint64_t>(P->rows_total, 1))); A(palloc(P, &P->Rtab, width));
   A(palloc(P, &P->zvec, width));
@@ -256,11 +267,15 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
 /* SpartanSNARK::prove (spartan.rs:219-466).  phase_ms (optional, 8 floats): device time of
  * [witness commit + transcript, matrix_vector_multiply, outer_sumcheck, prepare_poly_ABC, inner_sumcheck,
  *  pcs_prove (bind + MSMs), ipa response, total]. */
-int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp2_prep *P, const uint8_t *vk_digest,
-                          const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rnd, sp2_spartan_proof *proof,
-                          float *phase_ms) {
+static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape *S, const sp2_ck *ck, sp2_prep *P, const uint8_t *vk_digest,
+                                  const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rnd, sp2_spartan_proof *proof,
+                                  float *phase_ms) {
   cudaSetDevice(ctx->device);
   if (!P || P->S != S || P->ck != ck) return set_error(ctx, SP2_ERR_INTERNAL, "prove: prep state does not belong to this shape/key");
+  const bool shard = S->nranks > 1;
+  if (shard && (!comm || !comm->connected || comm->dc.n != S->nranks || comm->dc.rank != S->rank))
+    return set_error(ctx, SP2_ERR_INTERNAL, "prove: a sharded shape needs the connected comm of the same rank / size");
+  if (!shard && comm && comm->dc.n > 1) return set_error(ctx, SP2_ERR_INTERNAL, "prove: comm given but the shape is not sharded");
   const uint64_t width = ck->n, nv = S->num_vars, N = S->num_cons, nc = S->num_cols;
   const int l = log2_exact(N), m = log2_exact(nv), nry = m + 1;
   const uint64_t num_extra = 1 + S->num_public;
@@ -300,13 +315,17 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   SP2_LAUNCH_CHECK();
 
   // ---- transcript up to the taus (host; spartan.rs:226-264, bellpepper/r1cs.rs:422-431,491) -----
+  // The host hashes the cached commitment rows AFTER the device work of this phase has been enqueued (below), so the
+  // ~30 KB of serial Keccak runs under the rest-section commitment and the SpMV instead of in front of them.
   sp2h::Transcript ts("SpartanSNARK");
-  ts.absorb_bytes("vk", vk_digest, 32);
-  ts.absorb_scalars("public_values", public_values, S->num_public);
-  const uint64_t sh_rows = S->num_shared / width, pre_rows = S->num_precommitted / width;
-  if (sh_rows) ts.absorb_commitment_be("comm_W_shared", P->comm_cached_be.data(), sh_rows);
-  if (pre_rows) ts.absorb_commitment_be("comm_W_precommitted", P->comm_cached_be.data() + 64 * sh_rows, pre_rows);
-  memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
+  auto absorb_head = [&]() {
+    ts.absorb_bytes("vk", vk_digest, 32);
+    ts.absorb_scalars("public_values", public_values, S->num_public);
+    const uint64_t sh_rows = S->num_shared / width, pre_rows = S->num_precommitted / width;
+    if (sh_rows) ts.absorb_commitment_be("comm_W_shared", P->comm_cached_be.data(), sh_rows);
+    if (pre_rows) ts.absorb_commitment_be("comm_W_precommitted", P->comm_cached_be.data() + 64 * sh_rows, pre_rows);
+    memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
+  };
   // commit the rest section (r1cs.rs:467-470: blind + commit / commit_zeros)
   bool spmv_done = false;
   if (rest_rows) {
@@ -319,11 +338,13 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
     { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
       SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
     spmv_done = true;
+    absorb_head();
     SP2_CUDA_OK(cudaEventSynchronize(P->ev_r1));                            // host sync 1 (rows only)
     sp2h::batch_normalize(hj.data(), rest_rows, proof->comm_W + 8 * P->cached_rows);
   }
   if (!spmv_done) { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
-    SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
+    SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work));
+    absorb_head(); }
   ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
   // the PCS transcript (hyrax_pc.rs:410) re-absorbs all commitment rows; its (round, state) come from the device after the
   // sum-checks, but they enter the hash AFTER the absorbed data, so the rows are hashed now, under the sum-checks
@@ -352,19 +373,27 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   SP2_CUDA_OK(cudaMemcpyAsync(d_dg, tau_dg, (size_t)l * 64, cudaMemcpyHostToDevice, ctx->stream));
   k_taus_from_digests<<<1, 64, 0, ctx->stream>>>(st_outer, (const unsigned char *)d_dg, l);
   SP2_LAUNCH_CHECK();
-  SP2_TRY(sumcheck_cubic_enqueue(ctx, st_outer, (uint32_t)l, P->work[0], P->work[1], P->work[2]));
+  if (shard) comm->dc.epoch++;
+  SP2_TRY(sumcheck_cubic_enqueue(ctx, st_outer, (uint32_t)l, P->work[0], P->work[1], P->work[2], shard ? &comm->dc : nullptr));
   k_outer_to_inner<<<1, 64, 0, ctx->stream>>>(st_outer, st_inner, small, nry);
   SP2_LAUNCH_CHECK();
   mark(3);
 
   // ---- eq(r_x) and poly_ABC (spartan.rs:320-321) ------------------------------------------------
-  fe *d_rx = P->work[0];                                                   // the sum-check consumed the tables
+  // multi-GPU: eq(r_x) is replicated (write-only, N entries); each rank builds its columns of poly_ABC
+  fe *d_rx = shard ? P->rx : P->work[0];                                   // the sum-check consumed the tables
+  const uint64_t inner_local = (2 * nv) >> S->shard_k;                     // this rank's share of the virtual 2M-entry tables
   SP2_TRY(eq_table_dev(ctx, st_outer->r, (uint32_t)l, d_rx));
-  SP2_TRY(abc_dev(ctx, S, d_rx, &small[S_RJOINT], P->abc, nc));
+  SP2_TRY(abc_dev(ctx, S, d_rx, &small[S_RJOINT], P->abc, shard ? inner_local : nc));
+  if (shard) {
+    k_z_shard<<<(unsigned)((inner_local + 255) / 256), 256, 0, ctx->stream>>>(P->z, nc, P->zs, inner_local, S->shard_k, S->rank);
+    SP2_LAUNCH_CHECK();
+  }
   mark(4);
 
   // ---- inner sum-check: m+1 rounds over the virtual 2M tables (spartan.rs:330-404) ---------------
-  SP2_TRY(sumcheck_quad_enqueue(ctx, st_inner, (uint32_t)nry, P->abc, P->z, nc, P->ev_r1));
+  if (shard) { comm->dc.epoch++; SP2_TRY(sumcheck_quad_enqueue(ctx, st_inner, (uint32_t)nry, P->abc, P->zs, ~0ull, P->ev_r1, &comm->dc)); }
+  else SP2_TRY(sumcheck_quad_enqueue(ctx, st_inner, (uint32_t)nry, P->abc, P->z, nc, P->ev_r1));
   SP2_CUDA_OK(cudaStreamWaitEvent(ctx->side, P->ev_r1, 0));
   k_den_inv<<<1, 32, 0, ctx->side>>>(st_inner, small);
   SP2_LAUNCH_CHECK();
@@ -458,6 +487,24 @@ int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp
   }
   cleanup();
   return SP2_OK;
+}
+
+int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *ck, sp2_prep *P, const uint8_t *vk_digest,
+                          const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rnd, sp2_spartan_proof *proof,
+                          float *phase_ms) {
+  return spartan_prove_impl(ctx, nullptr, S, ck, P, vk_digest, public_values, W_rest, rnd, proof, phase_ms);
+}
+
+/* SpartanSNARK::prove with the hypercube split across the GPUs of `comm`: every rank (one process per GPU) calls
+ * this with the same inputs, its own shard of the shape (sp2_shape_upload_sharded) and the prep state made from it.  Sharded:
+ * Az/Bz/Cz (rows i = rank mod G), both sum-checks (cyclic tables, <= 3 partial sums per round exchanged inside the round
+ * kernels over NVLink), poly_ABC (columns j = rank mod G).  Replicated (latency-bound, cheaper to recompute than to exchange):
+ * witness, commitments, eq(r_x), the Hyrax bind and the PCS MSMs.  Every rank returns the identical proof. */
+int32_t sp2_spartan_prove_sharded(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape *S, const sp2_ck *ck, sp2_prep *P, const uint8_t *vk_digest,
+                                  const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rnd, sp2_spartan_proof *proof,
+                                  float *phase_ms) {
+  if (!comm) return set_error(ctx, SP2_ERR_INTERNAL, "prove_sharded: comm is NULL");
+  return spartan_prove_impl(ctx, comm, S, ck, P, vk_digest, public_values, W_rest, rnd, proof, phase_ms);
 }
 
 }  // extern "C"

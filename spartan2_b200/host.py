@@ -188,8 +188,12 @@ class SplitR1CSShape:
     """src/r1cs/mod.rs:743-1398 — device-resident shape (sp2_shape).  A, B, C are padded CSR triples
     (data (nnz,4) u64 Montgomery, indices u32, indptr u32 of num_cons+1 entries)."""
 
-    def __init__(self, ctx, num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges, A, B, Cm):
+    def __init__(self, ctx, num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges, A, B, Cm,
+                 rank=0, nranks=1):
+        """rank / nranks: this GPU's shard for the multi-GPU prover (rows and transposed columns i = rank mod nranks);
+        the same whole matrices are passed on every rank."""
         self.ctx = ctx
+        self.rank, self.nranks = rank, nranks
         self.num_cons = num_cons; self.num_vars = num_shared + num_precommitted + num_rest
         self.num_shared, self.num_precommitted, self.num_rest = num_shared, num_precommitted, num_rest
         self.num_public = num_public; self.num_challenges = num_challenges
@@ -207,7 +211,10 @@ class SplitR1CSShape:
             keep += [d, i, p]
             args += [_p(d), _p(i), _p(p)]
         h = C.c_void_p()
-        ctx.check(ctx.L.sp2_shape_upload(ctx.h, *args, C.byref(h)))
+        if nranks == 1:
+            ctx.check(ctx.L.sp2_shape_upload(ctx.h, *args, C.byref(h)))
+        else:
+            ctx.check(ctx.L.sp2_shape_upload_sharded(ctx.h, C.c_int32(rank), C.c_int32(nranks), *args, C.byref(h)))
         self.h = h
 
     def free(self):
@@ -227,13 +234,13 @@ class SplitR1CSShape:
         return dict(zip(["num_cons", "num_vars", "num_cols", "nnz", "nnz_general", "long_rows", "long_cols"], [int(x) for x in out]))
 
     def multiply_vec(self, z):
-        z = _fe(z); n = self.num_cons
+        z = _fe(z); n = self.num_cons // self.nranks     # a shard returns its rows i = rank (mod nranks)
         az, bz, cz = (np.zeros((n, 4), dtype=np.uint64) for _ in range(3))
         self.ctx.check(self.ctx.L.sp2_spmv3(self.ctx.h, self.h, _p(z), C.c_uint64(z.shape[0]), _p(az), _p(bz), _p(cz)))
         return az, bz, cz
 
     def multiply_vec_incremental(self, z, cached_az, cached_bz, cached_cz):
-        z = _fe(z); n = self.num_cons
+        z = _fe(z); n = self.num_cons // self.nranks
         ca, cb, cc = _fe(cached_az), _fe(cached_bz), _fe(cached_cz)
         az, bz, cz = (np.zeros((n, 4), dtype=np.uint64) for _ in range(3))
         self.ctx.check(self.ctx.L.sp2_spmv3_incremental(self.ctx.h, self.h, _p(z), C.c_uint64(z.shape[0]), _p(ca), _p(cb), _p(cc),
@@ -243,6 +250,8 @@ class SplitR1CSShape:
     def bind_and_prepare_poly_ABC(self, evals_rx, r, full=False):
         rx = _fe(evals_rx); r = _fe(r)
         out_len = 2 * self.num_vars if full else self.num_cols
+        if self.nranks > 1:                               # a shard returns its columns j = rank (mod nranks)
+            out_len = (out_len - self.rank + self.nranks - 1) // self.nranks
         out = np.zeros((out_len, 4), dtype=np.uint64)
         self.ctx.check(self.ctx.L.sp2_abc(self.ctx.h, self.h, _p(rx), C.c_uint64(rx.shape[0]), _p(r), _p(out), C.c_uint64(out_len)))
         return out
@@ -369,7 +378,8 @@ class SpartanSNARK:
         return SpartanPrepSNARK(ctx, h, comm[:rows])
 
     @staticmethod
-    def prove(ctx, shape, ck, prep, vk_digest, public_values, W_rest, blinds_W, blind_eval_W, d_vec, r_delta, r_beta):
+    def prove(ctx, shape, ck, prep, vk_digest, public_values, W_rest, blinds_W, blind_eval_W, d_vec, r_delta, r_beta, comm=None):
+        """comm: a connected Comm when `shape` is a multi-GPU shard (every rank calls with the same inputs and gets the same proof)."""
         N, nv = shape.num_cons, shape.num_vars
         l = N.bit_length() - 1; nry = nv.bit_length()
         rows = nv // ck.n
@@ -381,7 +391,11 @@ class SpartanSNARK:
         pub = _fe(public_values) if len(public_values) else np.zeros((1, 4), dtype=np.uint64)
         Wr = _fe(W_rest) if W_rest is not None and len(W_rest) else None      # None: all-zero rest section
         ph = (C.c_float * 8)()
-        ctx.check(ctx.L.sp2_spartan_prove(ctx.h, shape.h, ck.h, prep.h, _p(dig), _p(pub), _p(Wr) if Wr is not None else None, C.byref(rv), C.byref(pv), ph))
+        tail = (shape.h, ck.h, prep.h, _p(dig), _p(pub), _p(Wr) if Wr is not None else None, C.byref(rv), C.byref(pv), ph)
+        if comm is None:
+            ctx.check(ctx.L.sp2_spartan_prove(ctx.h, *tail))
+        else:
+            ctx.check(ctx.L.sp2_spartan_prove_sharded(ctx.h, comm.h, *tail))
         P.phase_ms = dict(zip(["commit_transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck",
                                "pcs_prove", "ipa_response", "total"], [float(x) for x in ph]))
         return P

@@ -72,3 +72,30 @@ def test_wrong_witness_length(ctx, orc):
     with pytest.raises(sp.SpartanError) as ei:
         S.multiply_vec(z_of(inst)[:-1])
     assert ei.value.kind == "InvalidWitnessLength"
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+@pytest.mark.parametrize("lc,lv,seed", [(8, 7, 2), (13, 13, 4)])
+def test_sharded_shape_rows_and_columns(ctx, orc, nranks, lc, lv, seed):
+    # multi-GPU shards of the shape, every shard run on this one GPU: rank g owns rows / transposed columns
+    # i = g (mod nranks); interleaving the shard outputs must reproduce the whole-shape result of the oracle
+    import spartan2_b200 as sp
+    inst = random_r1cs(seed, lc, lv, num_public=3, rest_frac=0.25)
+    O = orc.Shape(*dims(inst), inst["A"], inst["B"], inst["C"])
+    z = z_of(inst)
+    oa, ob, oc = O.multiply_vec(z)
+    rng = np.random.default_rng(seed)
+    rx = orc.eq_evals(rand_fe(rng, lc)); r = rand_fe(rng, 1)
+    oabc = O.abc(rx, r)
+    cached_len = inst["num_shared"] + inst["num_precommitted"]
+    z_cached = z.copy(); z_cached[cached_len:] = 0
+    for g in range(nranks):
+        S = sp.SplitR1CSShape(ctx, *dims(inst), inst["A"], inst["B"], inst["C"], rank=g, nranks=nranks)
+        az, bz, cz = S.multiply_vec(z)
+        assert np.array_equal(az, oa[g::nranks]) and np.array_equal(bz, ob[g::nranks]) and np.array_equal(cz, oc[g::nranks])
+        ca, cb, cc = S.multiply_vec(z_cached)
+        ia, ib, ic = S.multiply_vec_incremental(z, ca, cb, cc)
+        assert np.array_equal(ia, az) and np.array_equal(ib, bz) and np.array_equal(ic, cz)
+        got = S.bind_and_prepare_poly_ABC(rx, r)
+        assert np.array_equal(got, oabc[g::nranks])
+        S.free()

@@ -254,7 +254,18 @@ struct Fp : Field<FpParams> {
   // [p0,p1,p2,p3, 1, 0, 1, 2^32-1].  Per 32-bit round only m*p0..p3 are real multiplications (4 IMAD.WIDE, split
   // into an even and an odd carry chain); the upper limbs are m<<128, m<<192 and (m<<256) - (m<<224): adds/subs.
   // (The previous 32-bit CIOS used mad.hi, which SASS implements as the slow IMAD.HI.)
-  SP2_HD static fe mul(const fe &a, const fe &b) {
+  // On the device the curve code calls the multiplication OUT OF LINE (operands and result in registers, no stack):
+  // a Jacobian addition is 16 multiplications of ~360 instructions each, and with everything inlined the MSM kernels
+  // were 280-300 KB of straight-line code executed once per tree level by a handful of warps — bound by instruction
+  // fetch from L2, not by arithmetic (ncu: 115 us for a 7-level tree of 128 points).  One shared 5.8 KB body stays
+  // resident in the instruction cache.
+#if defined(__CUDA_ARCH__)
+  static __device__ __noinline__ fe mul_ni(fe a, fe b) { return mul_inl(a, b); }
+  static __device__ __forceinline__ fe mul(const fe &a, const fe &b) { return mul_ni(a, b); }
+#else
+  SP2_HD static fe mul(const fe &a, const fe &b) { return mul_inl(a, b); }
+#endif
+  SP2_HD static fe mul_inl(const fe &a, const fe &b) {
     u32 w[16];
     mul_wide(w, a, b);
     u32 t[18];

@@ -57,31 +57,14 @@ __device__ __forceinline__ u64 keccak_f_warp(u64 s, const KeccakLane &k, int lan
     u64 c = s ^ __shfl_sync(FULL, s, k.c1) ^ __shfl_sync(FULL, s, k.c2) ^ __shfl_sync(FULL, s, k.c3) ^ __shfl_sync(FULL, s, k.c4);
     u64 d = __shfl_sync(FULL, c, k.xm1) ^ rotl64(__shfl_sync(FULL, c, k.xp1), 1);
     s ^= d;
+    // (A variant with theta gathered in ONE stage — ten independent gathers straight from s instead of column parities
+    // followed by a dependent neighbour exchange, two dependent shuffle stages per round instead of three — was measured
+    // on B200: no faster, 2.045 vs 2.014 ms per prove; SHFL issue, not the dependency depth, sets the pace.)
     // rho in place, then pi and chi's two neighbour reads as ONE shuffle stage (three independent gathers from the
     // rotated values) instead of pi followed by a dependent neighbour exchange
     const u64 t = rotl64(s, k.rot);
     const u64 b = __shfl_sync(FULL, t, k.src), b1 = __shfl_sync(FULL, t, k.src1), b2 = __shfl_sync(FULL, t, k.src2);
     s = b ^ (~b1 & b2);
-    if (lane == 0) s ^= KECCAK_RC_D[rnd];
-  }
-  return s;
-}
-
-// Variant with theta as ONE shuffle stage: d(x) = XOR_y s[x-1,y] ^ rotl1(XOR_y s[x+1,y]) gathered straight from s (ten
-// independent gathers) instead of column parities followed by a dependent neighbour exchange: two dependent shuffle
-// stages per round instead of three, at the price of 8 more SHFLs.
-__device__ __forceinline__ u64 keccak_f_warp2(u64 s, const KeccakLane &k, int lane) {
-  const unsigned FULL = 0xffffffffu;
-  const int xm = k.xm1 % 5, xp = k.xp1 % 5;
-#pragma unroll 1
-  for (int rnd = 0; rnd < 24; rnd++) {
-    u64 a = __shfl_sync(FULL, s, xm), b = __shfl_sync(FULL, s, xp);
-#pragma unroll
-    for (int y = 1; y < 5; y++) { a ^= __shfl_sync(FULL, s, xm + 5 * y); b ^= __shfl_sync(FULL, s, xp + 5 * y); }
-    s ^= a ^ rotl64(b, 1);
-    const u64 t = rotl64(s, k.rot);
-    const u64 b0 = __shfl_sync(FULL, t, k.src), b1 = __shfl_sync(FULL, t, k.src1), b2 = __shfl_sync(FULL, t, k.src2);
-    s = b0 ^ (~b1 & b2);
     if (lane == 0) s ^= KECCAK_RC_D[rnd];
   }
   return s;

@@ -329,7 +329,8 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   // commit the rest section (r1cs.rs:467-470: blind + commit / commit_zeros)
   bool spmv_done = false;
   if (rest_rows) {
-    SP2_TRY(sp2_hyrax_commit_dev(ctx, ck, P->W + P->cached_len, S->num_rest, P->blinds + P->cached_rows, rest_rows, P->points + P->cached_rows));
+    // an all-zero rest section is HyraxPCS::commit_zeros (hyrax_pc.rs:305-319): rows = blind_i * h, no row terms to walk
+    SP2_TRY(sp2_hyrax_commit_dev(ctx, ck, P->W + P->cached_len, W_rest ? S->num_rest : 0, P->blinds + P->cached_rows, rest_rows, P->points + P->cached_rows));
     std::vector<uint64_t> hj(rest_rows * 12);
     SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), P->points + P->cached_rows, rest_rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
     SP2_CUDA_OK(cudaEventRecord(P->ev_r1, ctx->stream));

@@ -191,10 +191,9 @@ __device__ __forceinline__ fe sc_squeeze(ScState *st, FinSmem &sm, const fe &can
       const int lane = tid & 31, w = tid >> 5;
       const KeccakLane kl = keccak_lane_init(lane);
       u64 s = 0;
-      const bool v2 = (st->flags & 2u) != 0;
       for (int blk = 0; blk < nblocks; blk++) {
         if (lane < 17) s ^= sm.m[w][blk * 17 + lane];
-        s = v2 ? keccak_f_warp2(s, kl, lane) : keccak_f_warp(s, kl, lane);
+        s = keccak_f_warp(s, kl, lane);
       }
       if (lane < 4) sm.dg[w * 4 + lane] = s;
     }
@@ -779,10 +778,7 @@ int sc_state_upload(sp2_ctx *ctx, ScState **d_st, const uint64_t *claim, const u
   hs->ts.round = ts->round; hs->ts.pending_len = 0; memcpy(hs->ts.state, ts->state, 64);
   memcpy(&hs->claim, claim, sizeof(fe));
   hs->l = l;
-  { static int kflag = -1;
-    if (kflag < 0) { const char *e = getenv("SP2_KECCAK_THREAD"); kflag = (e && e[0] == '1') ? 0 : 1;
-                     const char *e2 = getenv("SP2_KECCAK_V2"); if (e2 && e2[0] == '1') kflag |= 2; }
-    hs->flags = (u32)kflag; }
+  { static int kflag = -1; if (kflag < 0) { const char *e = getenv("SP2_KECCAK_THREAD"); kflag = (e && e[0] == '1') ? 0 : 1; } hs->flags = (u32)kflag; }
   if (taus) memcpy(hs->taus, taus, (size_t)l * sizeof(fe));
   SP2_CUDA_OK(cudaMemcpyAsync(d, hs, head, cudaMemcpyHostToDevice, ctx->stream));
   *d_st = (ScState *)d;

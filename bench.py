@@ -129,11 +129,25 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     ctx = sp.Context(local)
-    wl = Workload(args.msg_len, seed=0xDEADBEEF + rank)
+    sharded = bool(args.sharded) and world > 1
+    # replicas (default): every GPU proves its own instance (independent proofs: weak scaling, no data-path exchange);
+    # --sharded: ONE proof, its 2^l hypercube split across the GPUs (strong scaling)
+    wl = Workload(args.msg_len, seed=0xDEADBEEF + (0 if sharded else rank))
     hbm_peak, peak_kind = peaks()
     pts = ctx.test_points(WIDTH + 3, seed=7)
     K = sp.CommitmentKey(ctx, pts[:WIDTH], pts[WIDTH:WIDTH + 1], pts[WIDTH + 1:WIDTH + 2], pts[WIDTH + 2:WIDTH + 3])
-    S = sp.SplitR1CSShape(ctx, *wl.circ.dims(), wl.A, wl.B, wl.C)
+    comm = None
+    if sharded:
+        import torch.distributed as dist
+
+        def allgather_bytes(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        comm = sp.Comm(ctx, rank, world, allgather_bytes)
+        S = sp.SplitR1CSShape(ctx, *wl.circ.dims(), wl.A, wl.B, wl.C, rank=rank, nranks=world)
+    else:
+        S = sp.SplitR1CSShape(ctx, *wl.circ.dims(), wl.A, wl.B, wl.C)
     t0 = time.perf_counter()
     prep = sp.SpartanSNARK.prep_prove(ctx, S, K, wl.W[:wl.cached_len], wl.blinds[:wl.cached_rows], is_small=True)
     prep_ms = (time.perf_counter() - t0) * 1e3
@@ -152,8 +166,11 @@ def run_cuda(args):
     def step():
         ctx.check(ctx.L.sp2_dev_memset(ctx.h, flush.ptr, 0, 512 << 20))   # flush L2 between timed iterations
         ctx.synchronize()
+        if sharded:
+            import torch.distributed as dist
+            dist.barrier()
         t0 = time.perf_counter()
-        proof = sp.SpartanSNARK.prove(ctx, S, K, prep, wl.vk, wl.X, W_rest, wl.blinds, wl.blind_eval, wl.d_vec, wl.r_delta, wl.r_beta)
+        proof = sp.SpartanSNARK.prove(ctx, S, K, prep, wl.vk, wl.X, W_rest, wl.blinds, wl.blind_eval, wl.d_vec, wl.r_delta, wl.r_beta, comm=comm)
         wall = (time.perf_counter() - t0) * 1e3
         return proof, wall
 
@@ -180,13 +197,15 @@ def run_cuda(args):
         ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
         ach = wl.bytes_outer / (ph["outer_sumcheck"] * 1e-3) / 1e9
         cfg = wl.describe()
-        cfg.update({"l2": "flushed between timed iterations (512 MiB memset)", "parallelism": "1 proof per GPU (replicas)" if world > 1 else "single GPU",
-                    "prep_prove_ms_untimed": prep_ms})
+        par = "single GPU" if world == 1 else ("one proof, hypercube sharded across %d GPUs (rows/columns i mod %d; per-round sums exchanged in-kernel over NVLink)" % (world, world)
+                                               if sharded else "1 proof per GPU (replicas)")
+        cfg.update({"l2": "flushed between timed iterations (512 MiB memset)", "parallelism": par, "prep_prove_ms_untimed": prep_ms})
+        jobs = 1 if sharded else world
         out = {
-            "metric": METRIC, "value": world * wl.field_ops / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": W_, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": jobs * wl.field_ops / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": W_, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "u32x8 limbs (256-bit prime field, Montgomery)", "data": "synthetic", "config": cfg,
-            "e2e": {"value": world * wl.field_ops / (ms_wall * 1e-3), "unit": UNIT, "ms_per_step": ms_wall,
+            "e2e": {"value": jobs * wl.field_ops / (ms_wall * 1e-3), "unit": UNIT, "ms_per_step": ms_wall,
                     "h2d_bytes_per_step": int(wl.X.nbytes + wl.d_vec.nbytes + wl.blinds.nbytes + 16 * 32 + 64 * 21),
                     "d2h_bytes_per_step": int(sum(getattr(proof, f).nbytes for f in sp.SpartanProof.FIELDS))},
             "gpu_launches": int(launches),
@@ -198,6 +217,8 @@ def run_cuda(args):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_prove(wl, pts, threads=1, steps=1, warmup=0)
         print(json.dumps(out), flush=True)
+    if comm is not None:
+        comm.free()
     ctx.close()
     if world > 1:
         import torch.distributed as dist
@@ -264,6 +285,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--msg-len", type=int, default=2048, help="SHA-256 message bytes (BASELINE config 2: 2048; config 1: 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="N > 1: one proof with its hypercube sharded across the GPUs (strong scaling) instead of one proof per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

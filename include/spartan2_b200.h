@@ -237,6 +237,19 @@ int32_t sp2_bind_tables_dev(sp2_ctx *ctx, void *const *d_tables, uint32_t ntable
  * out[row] = sum_i w[i] * comms[i*rows + row], affine in/out                                                      */
 int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n, uint32_t rows, const uint64_t *w, uint64_t *out_xy);
 
+/* ---- host Keccak256Transcript (src/provider/keccak.rs:18-105 behind TranscriptEngineTrait, src/traits/transcript.rs) ----
+ * Host-side Fiat-Shamir for drivers that interleave per-round device calls with transcript steps (a Rust caller keeps
+ * using its own Keccak256Transcript; this is the same object for C/C++/Python hosts).  Scalars are Montgomery limbs. */
+typedef struct sp2_transcript sp2_transcript;
+int32_t sp2_transcript_new(const char *label, sp2_transcript **out);
+void sp2_transcript_free(sp2_transcript *t);
+int32_t sp2_transcript_absorb_bytes(sp2_transcript *t, const char *label, const uint8_t *data, uint64_t n);
+int32_t sp2_transcript_absorb_scalars(sp2_transcript *t, const char *label, const uint64_t *scalars, uint64_t n);
+int32_t sp2_transcript_absorb_commitment(sp2_transcript *t, const char *label, const uint64_t *rows_xy, uint64_t rows);
+int32_t sp2_transcript_dom_sep(sp2_transcript *t, const char *label);
+int32_t sp2_transcript_squeeze(sp2_transcript *t, const char *label, uint64_t *out_scalar);
+int32_t sp2_transcript_get_state(const sp2_transcript *t, sp2_transcript_state *out);
+
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_dev_free(sp2_ctx *ctx, void *p);

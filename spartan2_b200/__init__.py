@@ -8,6 +8,6 @@ follow microsoft/Spartan2 (`SumcheckProof::prove_cubic_with_three_inputs`, `prov
 Field elements are numpy uint64 arrays of shape (n, 4): little-endian 64-bit limbs in Montgomery form
 (R = 2^256) — the reference's in-memory layout (src/big_num/montgomery.rs:17-22)."""
 from ._lib import SpartanError, TranscriptState, lib, LIB_PATH  # noqa: F401
-from .host import (Comm, CommitmentKey, Context, NeutronNovaNIFS, PowPolynomial, R1CSWitness, SumcheckRounds,
+from .host import (Comm, CommitmentKey, Context, Keccak256Transcript, NeutronNovaNIFS, PowPolynomial, R1CSWitness, SumcheckRounds,
                    fold_commitments, weights_from_r, DeviceBuffer, DlogGroupExt, EqPolynomial, HyraxPCS, MultilinearPolynomial,
                    SpartanPrepSNARK, SpartanProof, SpartanSNARK, SplitR1CSShape, SumcheckProof, shard_cyclic)  # noqa: F401

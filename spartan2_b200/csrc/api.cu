@@ -1,6 +1,7 @@
 // Context, device-memory helpers and element-wise test hooks of the C ABI (include/spartan2_b200.h).
 #include <string.h>
 #include "ctx.cuh"
+#include "host_transcript.h"
 #include "devutil.cuh"
 #include "keccak.cuh"
 
@@ -209,6 +210,43 @@ int32_t sp2_test_transcript(sp2_ctx *ctx, sp2_transcript_state *ts, const uint8_
   SP2_CUDA_OK(cudaMemcpyAsync(challenge_out, dout, 32, cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   ts->round = (uint16_t)h.round; memcpy(ts->state, h.state, 64);
+  return SP2_OK;
+}
+
+/* ---- host Keccak256Transcript (src/provider/keccak.rs:18-105; TranscriptEngineTrait, src/traits/transcript.rs) ----
+ * For host-side drivers that run the Fiat-Shamir steps between per-round device calls (the NeutronNova seams). */
+struct sp2_transcript { sp2h::Transcript t; explicit sp2_transcript(const char *label) : t(label) {} };
+
+int32_t sp2_transcript_new(const char *label, sp2_transcript **out) {
+  if (!out || !label) return SP2_ERR_INTERNAL;
+  *out = new sp2_transcript(label);
+  return SP2_OK;
+}
+void sp2_transcript_free(sp2_transcript *t) { delete t; }
+int32_t sp2_transcript_absorb_bytes(sp2_transcript *t, const char *label, const uint8_t *data, uint64_t n) {
+  t->t.absorb_bytes(label, data, (size_t)n);
+  return SP2_OK;
+}
+/* scalars in Montgomery form; absorbed as 32 big-endian canonical bytes each (src/provider/traits.rs:282-286) */
+int32_t sp2_transcript_absorb_scalars(sp2_transcript *t, const char *label, const uint64_t *scalars, uint64_t n) {
+  t->t.absorb_scalars(label, scalars, (size_t)n);
+  return SP2_OK;
+}
+/* commitment rows (affine points), framed as HyraxCommitment::to_transcript_bytes (hyrax_pc.rs:714-729) */
+int32_t sp2_transcript_absorb_commitment(sp2_transcript *t, const char *label, const uint64_t *rows_xy, uint64_t rows) {
+  t->t.absorb_commitment(label, rows_xy, (size_t)rows);
+  return SP2_OK;
+}
+int32_t sp2_transcript_dom_sep(sp2_transcript *t, const char *label) { t->t.dom_sep(label); return SP2_OK; }
+/* squeeze (keccak.rs:70-94) -> challenge as a Montgomery scalar */
+int32_t sp2_transcript_squeeze(sp2_transcript *t, const char *label, uint64_t *out_scalar) {
+  uint8_t dg[64];
+  t->t.squeeze(label, dg);
+  sp2h::fq_from_uniform(dg, out_scalar);
+  return SP2_OK;
+}
+int32_t sp2_transcript_get_state(const sp2_transcript *t, sp2_transcript_state *out) {
+  out->round = t->t.round; memcpy(out->state, t->t.state, 64);
   return SP2_OK;
 }
 

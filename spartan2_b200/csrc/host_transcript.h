@@ -236,4 +236,33 @@ struct Transcript {
   }
 };
 
+// ---- challenge = from_uniform(64 squeezed bytes): 512-bit little-endian integer mod q, Montgomery form
+// (provider/traits.rs:275-280; halo2curves from_uniform_bytes) ---------------------------------------------------
+inline void fq_pow2_mont(int k, uint64_t out[4]) {              // 2^k mod q (canonical) by doubling
+  uint64_t r[4] = {1, 0, 0, 0};
+  for (int i = 0; i < k; i++) {
+    uint64_t d[4]; unsigned carry = 0;
+    for (int j = 0; j < 4; j++) { const uint64_t v = r[j]; d[j] = (v << 1) | carry; carry = (unsigned)(v >> 63); }
+    uint64_t e[4]; unsigned borrow = 0;
+    for (int j = 0; j < 4; j++) { u128 x = (u128)d[j] - FQ_MOD[j] - borrow; e[j] = (uint64_t)x; borrow = (unsigned)((x >> 64) & 1); }
+    const bool ge = carry || !borrow;
+    for (int j = 0; j < 4; j++) r[j] = ge ? e[j] : d[j];
+  }
+  memcpy(out, r, 32);
+}
+inline void fq_from_uniform(const uint8_t dg[64], uint64_t out_mont[4]) {
+  static uint64_t R2[4], R3[4]; static bool init = false;
+  if (!init) { fq_pow2_mont(512, R2); fq_pow2_mont(768, R3); init = true; }
+  uint64_t lo[4], hi[4], a[4], b[4];
+  memcpy(lo, dg, 32); memcpy(hi, dg + 32, 32);
+  mont_mul(lo, R2, FQ_MOD, FQ_INV, a);                           // lo * R
+  mont_mul(hi, R3, FQ_MOD, FQ_INV, b);                           // hi * 2^256 * R
+  unsigned carry = 0; uint64_t s4[4];
+  for (int j = 0; j < 4; j++) { u128 x = (u128)a[j] + b[j] + carry; s4[j] = (uint64_t)x; carry = (unsigned)(x >> 64); }
+  uint64_t e[4]; unsigned borrow = 0;
+  for (int j = 0; j < 4; j++) { u128 x = (u128)s4[j] - FQ_MOD[j] - borrow; e[j] = (uint64_t)x; borrow = (unsigned)((x >> 64) & 1); }
+  const bool ge = carry || !borrow;
+  for (int j = 0; j < 4; j++) out_mont[j] = ge ? e[j] : s4[j];
+}
+
 }  // namespace sp2h

@@ -452,6 +452,53 @@ class Comm:
         return polys, r, claims
 
 
+class Keccak256Transcript:
+    """src/provider/keccak.rs:18-105 — the host transcript of the library (pure host code: usable without a GPU).
+    Scalars are (n, 4) u64 Montgomery limbs; squeeze returns the challenge as a (1, 4) Montgomery scalar."""
+
+    def __init__(self, label):
+        from ._lib import lib
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.sp2_transcript_new(bytes(label), C.byref(h))
+        if rc != 0:
+            raise SpartanError(rc, "transcript")
+        self.h = h
+
+    def absorb_bytes(self, label, data):
+        d = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, dtype=np.uint8)
+        self.L.sp2_transcript_absorb_bytes(self.h, bytes(label), _p(d), C.c_uint64(len(data)))
+
+    def absorb_scalars(self, label, scalars):
+        a = _fe(scalars)
+        self.L.sp2_transcript_absorb_scalars(self.h, bytes(label), _p(a if a.shape[0] else np.zeros((1, 4), dtype=np.uint64)), C.c_uint64(a.shape[0]))
+
+    def absorb_commitment(self, label, rows_xy):
+        a = np.ascontiguousarray(rows_xy, dtype=np.uint64).reshape(-1, 8)
+        self.L.sp2_transcript_absorb_commitment(self.h, bytes(label), _p(a), C.c_uint64(a.shape[0]))
+
+    def dom_sep(self, label):
+        self.L.sp2_transcript_dom_sep(self.h, bytes(label))
+
+    def squeeze(self, label):
+        out = np.zeros((1, 4), dtype=np.uint64)
+        self.L.sp2_transcript_squeeze(self.h, bytes(label), _p(out))
+        return out
+
+    def state(self):
+        from ._lib import TranscriptState
+        t = TranscriptState()
+        self.L.sp2_transcript_get_state(self.h, C.byref(t))
+        return t
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.sp2_transcript_free(self.h); self.h = None
+        except Exception:
+            pass
+
+
 class PowPolynomial:
     """src/polys/power.rs"""
 

@@ -1,0 +1,257 @@
+"""NeutronNova prover hot path (BASELINE configs 3 / 5) driven through the per-round device seams.
+
+Follows `NeutronNovaZkSNARK::prove` (src/neutronnova_zk.rs:1609-2093) along its three hot loops:
+  A  NeutronNovaNIFS::prove (:511-1273): per round (e0, quad) over the instance pairs -> `finish_round!` (:703-735) ->
+     challenge r_b -> pairwise fold of the Az/Bz/Cz layers; then R1CSWitness::fold_multiple (src/r1cs/mod.rs:570-660)
+  B  prove_cubic_with_additive_term_batched_zk (src/sumcheck.rs:786-917): 2 branches (step, core), pow(tau) weights
+  C  bind_and_prepare_poly_ABC_full x 2 (:1868-1875), prove_quad_batched_zk (src/sumcheck.rs:702-782)
+with the per-step SpMV of prep_prove (:1538-1549) in front.
+
+What is NOT the reference here: the reference draws every challenge from `process_round` (src/bellpepper/r1cs.rs:735-816),
+which synthesises one round of its in-circuit verifier, Pedersen-commits that round's witness and squeezes the
+transcript — the ZK wrapper, out of scope.  This driver keeps the data path and the host scalar algebra
+of each round exactly as the reference has them and takes the challenge from a plain Keccak transcript
+(absorb(b"p", round polynomial coefficients) / squeeze(b"c"), as src/sumcheck.rs:536-548 does in the non-ZK provers).
+So it exercises and times HOT LOOPS A-C at the reference's sizes, and its every intermediate value is checked
+against the oracle (tests/test_gpu_neutronnova.py), but its output is not a NeutronNovaZkSNARK proof.
+
+The driver is backend-agnostic: `ops` supplies the bulk operations.  `DeviceOps` (below) is the CUDA path; the tests
+run the same driver over the oracle's CPU functions."""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _fq as fq
+from .host import (NeutronNovaNIFS, PowPolynomial, SumcheckRounds, _fe, _p, weights_from_r)
+
+
+def compute_tensor_decomp(n):
+    """neutronnova_zk.rs:58-67: (ell, left, right) with left = 2^ceil(ell/2), right = 2^floor(ell/2)."""
+    ell = max(n - 1, 0).bit_length()
+    return ell, 1 << ((ell + 1) // 2), 1 << (ell // 2)
+
+
+class DeviceOps:
+    """Bulk operations on device-resident tables through the C ABI (one SplitR1CSShape: the step and the core circuit
+    of the SHA-256 chain share their shape, benches/sha256_neutronnova.rs:103-178)."""
+
+    def __init__(self, ctx, shape):
+        self.ctx, self.S = ctx, shape
+        self.N, self.M, self.ncols = shape.num_cons, shape.num_vars, shape.num_cols
+
+    def _off(self, buf, elems):
+        return C.c_void_p(buf.ptr.value + 32 * elems)
+
+    # ---- prep_prove: Az_i, Bz_i, Cz_i for every step, layer-major (neutronnova_zk.rs:1538-1549) ----
+    def spmv_layers(self, zs):
+        ctx, n, N = self.ctx, len(zs), self.N
+        A, B, Cz = (ctx.alloc(n * N * 32) for _ in range(3))
+        dz = ctx.alloc(self.ncols * 32)
+        for i, z in enumerate(zs):
+            dz.upload(_fe(z))
+            ctx.check(ctx.L.sp2_spmv3_dev(ctx.h, self.S.h, dz.ptr, self._off(A, i * N), self._off(B, i * N), self._off(Cz, i * N)))
+        return A, B, Cz
+
+    def pow_split(self, tau, left, right):
+        return PowPolynomial.split_evals(self.ctx, tau, left, right)
+
+    def nifs(self, E, left, right, A, B, Cz, n):
+        return NeutronNovaNIFS(self.ctx, E, left, right, A, B, Cz, n)      # folds in place; layer 0 = the folded tables
+
+    def nifs_result(self, nifs):
+        return nifs.A, nifs.B, nifs.C
+
+    def fold_witness(self, r_bs, Ws):
+        """R1CSWitness::fold_multiple (W part) into the head of a zero 2M-entry z table (then u = 1 at index M)."""
+        ctx = self.ctx
+        Ws = np.ascontiguousarray(Ws, dtype=np.uint64); n, dim = Ws.shape[0], Ws.shape[1]
+        w = weights_from_r(ctx, r_bs, n)
+        dW = ctx.upload(Ws)
+        z = ctx.alloc(2 * self.M * 32)
+        ctx.check(ctx.L.sp2_dev_memset(ctx.h, z.ptr, 0, C.c_uint64(2 * self.M * 32)))
+        ctx.check(ctx.L.sp2_fold_vectors_dev(ctx.h, dW.ptr, C.c_uint64(n), C.c_uint64(dim), _p(w), z.ptr))
+        z.upload(fq.from_int(1), offset=32 * self.M)
+        return z
+
+    def z_table(self, W):
+        ctx = self.ctx
+        z = ctx.alloc(2 * self.M * 32)
+        ctx.check(ctx.L.sp2_dev_memset(ctx.h, z.ptr, 0, C.c_uint64(2 * self.M * 32)))
+        z.upload(_fe(W)); z.upload(fq.from_int(1), offset=32 * self.M)
+        return z
+
+    def tables(self, arr):
+        return self.ctx.upload(_fe(arr))
+
+    def pow_cubic_eval(self, pl, left, pr, A, B, Cz, tl):
+        return SumcheckRounds.eval_points_cubic_with_outer_pow(self.ctx, pl, left, pr, A, B, Cz, tl)
+
+    def quad_eval(self, A, B, tl):
+        return SumcheckRounds.eval_points_quad(self.ctx, A, B, tl)
+
+    def bind(self, tables, tl, r):
+        SumcheckRounds.bind_poly_var_top(self.ctx, tables, tl, r)
+
+    def head(self, table, k=1):
+        return table.download((k, 4))
+
+    def eq_table(self, r_x):
+        ctx = self.ctx
+        r_x = _fe(r_x); d_r = ctx.upload(r_x); out = ctx.alloc((1 << r_x.shape[0]) * 32)
+        ctx.check(ctx.L.sp2_eq_table_dev(ctx.h, d_r.ptr, C.c_uint32(r_x.shape[0]), out.ptr))
+        return out
+
+    def abc_full(self, rx, r):
+        ctx = self.ctx
+        d_r = ctx.upload(_fe(r)); out = ctx.alloc(2 * self.M * 32)
+        ctx.check(ctx.L.sp2_abc_dev(ctx.h, self.S.h, rx.ptr, d_r.ptr, out.ptr, C.c_uint64(2 * self.M)))
+        return out
+
+    def sync(self):
+        self.ctx.synchronize()
+
+
+def run(ops, ts, n_cons, step_zs, step_Ws, core_z, core_W, trace=None, timing=None):
+    """One pass of HOT LOOPS A-C.  step_zs / core_z: z = [W | 1 | X] vectors; step_Ws / core_W: the witnesses.
+    `ts`: a transcript with absorb_scalars / squeeze.  `trace`: optional list receiving (name, array) for every
+    intermediate value a verifier (or the parity test) would see.  Returns a dict of the final claims."""
+    rec = (lambda name, v: trace.append((name, np.array(v, dtype=np.uint64, copy=True)))) if trace is not None else (lambda name, v: None)
+    tm = timing if timing is not None else {}
+    t0 = time.perf_counter()
+
+    def lap(name):
+        nonlocal t0
+        ops.sync(); t1 = time.perf_counter(); tm[name] = tm.get(name, 0.0) + (t1 - t0) * 1e3; t0 = t1
+
+    n = len(step_zs)
+    assert n & (n - 1) == 0 and n >= 2, "the number of step instances must be a power of two"
+    ell_b = n.bit_length() - 1
+    ell, left, right = compute_tensor_decomp(n_cons)
+    N = 1 << ell
+    Q = fq.Q
+
+    # ---- prep_prove: per-step matrix-vector products --------------------------------------------------------------
+    A, B, Cz = ops.spmv_layers(step_zs)
+    Ac, Bc, Cc = ops.spmv_layers([core_z])
+    lap("matrix_vector_multiply")
+
+    # ---- HOT LOOP A: NIFS ----------------------------------------------------------------------------------------
+    ts.absorb_scalars(b"T", fq.from_int(0))
+    tau = ts.squeeze(b"tau")
+    E = ops.pow_split(tau, left, right)
+    rhos = np.concatenate([ts.squeeze(b"rho") for _ in range(ell_b)], axis=0)
+    rec("E", E)
+    nifs = ops.nifs(E, left, right, A, B, Cz, n)
+    T_cur, acc_eq, r_bs = 0, 1, []
+    for t in range(ell_b):
+        e0q = nifs.round_eval(rhos)
+        rec("nifs_round_%d" % t, e0q)
+        e0, quad = fq.to_ints(e0q)
+        rho = fq.to_int(rhos[t])
+        # finish_round! (neutronnova_zk.rs:703-735)
+        one_minus_rho = (1 - rho) % Q; two_rho_minus_one = (rho - one_minus_rho) % Q
+        c = e0 * acc_eq % Q; a = quad * acc_eq % Q
+        if rho == 0:
+            raise ZeroDivisionError("rho = 0 (SpartanError::DivisionByZero)")
+        a_b_c = (T_cur - c * one_minus_rho) * pow(rho, -1, Q) % Q
+        b = (a_b_c - a - c) % Q
+        coeffs = [c * one_minus_rho % Q, (c * two_rho_minus_one + b * one_minus_rho) % Q,
+                  (b * two_rho_minus_one + a * one_minus_rho) % Q, a * two_rho_minus_one % Q]
+        poly = fq.from_ints(coeffs)
+        rec("nifs_poly_%d" % t, poly)
+        ts.absorb_scalars(b"p", poly)
+        r_b_l = ts.squeeze(b"c"); r_b = fq.to_int(r_b_l)
+        r_bs.append(r_b_l)
+        acc_eq = acc_eq * (((1 - r_b) * (1 - rho) + r_b * rho) % Q) % Q
+        T_cur = fq.unipoly_eval(coeffs, r_b)
+        nifs.fold(r_b_l)
+    r_bs = np.concatenate(r_bs, axis=0)
+    T_out = T_cur * pow(acc_eq, -1, Q) % Q                      # :1206-1208
+    As, Bs, Cs = ops.nifs_result(nifs)
+    rec("folded_head", np.concatenate([ops.head(x, 4) for x in (As, Bs, Cs)], axis=0))
+    lap("nifs")
+    z_step = ops.fold_witness(r_bs, step_Ws)                    # R1CSWitness::fold_multiple + (u = 1)
+    z_core = ops.z_table(core_W)
+    rec("W_fold_head", ops.head(z_step, 8))
+    lap("fold_witness")
+
+    # ---- HOT LOOP B: batched outer sum-check (sumcheck.rs:786-917) ---------------------------------------------------
+    pl, pr = ops.tables(E[:left]), ops.tables(E[left:])
+    E_int = None
+    base_tau, len_pow = 1, left * right
+    claim_s, claim_c = T_out, 0
+    r_x = []
+    tl = N
+    for i in range(ell):
+        ev_s = fq.to_ints(ops.pow_cubic_eval(pl, left, pr, As, Bs, Cs, tl))
+        ev_c = fq.to_ints(ops.pow_cubic_eval(pl, left, pr, Ac, Bc, Cc, tl))
+        rec("outer_evals_%d" % i, fq.from_ints(ev_s + ev_c))
+        ev_s = [v * base_tau % Q for v in ev_s]; ev_c = [v * base_tau % Q for v in ev_c]
+        poly_s = fq.unipoly_from_evals([ev_s[0], (claim_s - ev_s[0]) % Q, ev_s[1], ev_s[2]])
+        poly_c = fq.unipoly_from_evals([ev_c[0], (claim_c - ev_c[0]) % Q, ev_c[1], ev_c[2]])
+        cs = fq.from_ints(poly_s + poly_c)
+        rec("outer_polys_%d" % i, cs)
+        ts.absorb_scalars(b"p", cs)
+        r_l = ts.squeeze(b"c"); r_i = fq.to_int(r_l); r_x.append(r_l)
+        claim_s, claim_c = fq.unipoly_eval(poly_s, r_i), fq.unipoly_eval(poly_c, r_i)
+        ops.bind([As, Ac, Bs, Bc, Cs, Cc], tl, r_l)
+        tl //= 2
+        len_pow >>= 1
+        if E_int is None:
+            E_int = fq.to_ints(E)
+        pw = E_int[len_pow % left] * E_int[left + len_pow // left] % Q
+        base_tau = base_tau * (((pw - 1) * r_i + 1) % Q) % Q
+    r_x = np.concatenate(r_x, axis=0)
+    claims = np.concatenate([ops.head(x) for x in (As, Bs, Cs, Ac, Bc, Cc)], axis=0)
+    rec("claims_outer", claims)
+    rec("tau_at_rx", fq.from_int(base_tau))
+    lap("outer_sumcheck_batched")
+
+    # ---- batching challenge, eq(r_x), poly_ABC for both branches (neutronnova_zk.rs:1853-1875) ----------------------------
+    ts.absorb_scalars(b"claims_outer", claims)
+    r_l = ts.squeeze(b"r"); r = fq.to_int(r_l)
+    cl = fq.to_ints(claims)
+    claim_js = (cl[0] + r * cl[1] + r * r % Q * cl[2]) % Q
+    claim_jc = (cl[3] + r * cl[4] + r * r % Q * cl[5]) % Q
+    rx = ops.eq_table(r_x)
+    abc_s = ops.abc_full(rx, r_l)
+    abc_c = ops.abc_full(rx, r_l)          # S_core == S_step for the SHA-256 chain; two calls as in the reference
+    rec("abc_head", ops.head(abc_s, 8))
+    lap("compute_eval_table_sparse")
+
+    # ---- HOT LOOP C: batched inner sum-check (sumcheck.rs:702-782) ------------------------------------------------------
+    tl = 2 * ops.M
+    r_y = []
+    for j in range(ops.M.bit_length()):
+        e_s = fq.to_ints(ops.quad_eval(abc_s, z_step, tl)); e_c = fq.to_ints(ops.quad_eval(abc_c, z_core, tl))
+        rec("inner_evals_%d" % j, fq.from_ints(e_s + e_c))
+        polys = []
+        for (e0, tinf), claim in ((e_s, claim_js), (e_c, claim_jc)):
+            e2 = (2 * claim - 3 * e0 + 2 * tinf) % Q            # BDDT (sumcheck.rs:731-733)
+            polys.append(fq.unipoly_from_evals([e0, (claim - e0) % Q, e2]))
+        cs = fq.from_ints(polys[0] + polys[1])
+        rec("inner_polys_%d" % j, cs)
+        ts.absorb_scalars(b"p", cs)
+        r_l2 = ts.squeeze(b"c"); r_j = fq.to_int(r_l2); r_y.append(r_l2)
+        ops.bind([abc_s, z_step, abc_c, z_core], tl, r_l2)
+        tl //= 2
+        claim_js, claim_jc = fq.unipoly_eval(polys[0], r_j), fq.unipoly_eval(polys[1], r_j)
+    finals = np.concatenate([ops.head(x) for x in (abc_s, abc_c, z_step, z_core)], axis=0)
+    rec("inner_final", finals)
+    lap("inner_sumcheck_batched")
+    # eval_W = (eval_Z - r_y[0] * eval_X) / (1 - r_y[0]); X = [1] (no public IO in the step circuit): eval_X = prod (1 - r_y[1..])
+    ry = [fq.to_int(x) for x in r_y]
+    eval_X = 1
+    for v in ry[1:]:
+        eval_X = eval_X * (1 - v) % Q
+    inv = pow((1 - ry[0]) % Q, -1, Q)
+    fi = fq.to_ints(finals)
+    out = {"eval_W_step": (fi[2] - ry[0] * eval_X) * inv % Q, "eval_W_core": (fi[3] - ry[0] * eval_X) * inv % Q,
+           "claim_inner_step": claim_js, "claim_inner_core": claim_jc, "T_out": T_out, "r_b": r_bs, "r_x": r_x, "r_y": np.concatenate(r_y, axis=0)}
+    rec("eval_W", fq.from_ints([out["eval_W_step"], out["eval_W_core"]]))
+    # the verifier's final checks of the two sum-checks (what the reference's in-circuit verifier enforces):
+    #   outer: claim(r_x) = tau(r_x) * (Az(r_x) * Bz(r_x) - Cz(r_x)) per branch;  inner: claim(r_y) = ABC(r_y) * z(r_y)
+    out["outer_ok"] = (claim_s == base_tau * ((cl[0] * cl[1] - cl[2]) % Q) % Q) and (claim_c == base_tau * ((cl[3] * cl[4] - cl[5]) % Q) % Q)
+    out["inner_ok"] = (claim_js == fi[0] * fi[2] % Q) and (claim_jc == fi[1] * fi[3] % Q)
+    return out

@@ -97,3 +97,28 @@ def test_fold_commitments(ctx, orc):
     w = rand_fe(rng, n)
     w[0] = orc.to_mont([1])[0]; w[1] = 0                  # unit and zero weights
     assert np.array_equal(sp.fold_commitments(ctx, pts, n, rows, w), orc.fold_commitments(pts, n, rows, w))
+
+
+@pytest.mark.parametrize("n", [4, 32])
+def test_hot_path_device_vs_oracle(ctx, orc, n):
+    """HOT LOOPS A-C of NeutronNovaZkSNARK::prove (spartan2_b200.neutronnova.run) on the SHA-256 chain — n = 32 is
+    BASELINE config 3 (32 step circuits of one compression each + the core circuit, N = M = 2^15 per instance): the
+    same driver over the CUDA backend and over the oracle backend, with identical transcripts; every recorded
+    intermediate value (NIFS rounds and polynomials, folded layers and witness, 15 x 2 outer and 16 x 2 inner round
+    evaluations, claims, poly_ABC, final evaluations) must be bit-identical, and the verifier's final equations hold."""
+    import spartan2_b200 as sp
+    from spartan2_b200 import neutronnova as nn
+    from tests.neutronnova_ops import OracleOps, sha_chain_instances
+    c0, zs, Ws, zc, Wc = sha_chain_instances(n)
+    A, B, Cm = c0.matrices()
+    S = sp.SplitR1CSShape(ctx, *c0.dims(), A, B, Cm)
+    tr_d, tr_o = [], []
+    out_d = nn.run(nn.DeviceOps(ctx, S), sp.Keccak256Transcript(b"neutronnova_prove"), c0.num_cons, zs, Ws, zc, Wc, trace=tr_d)
+    out_o = nn.run(OracleOps(orc.Shape(*c0.dims(), A, B, Cm), c0.dims()), orc.Transcript(b"neutronnova_prove"), c0.num_cons, zs, Ws, zc, Wc, trace=tr_o)
+    assert [t[0] for t in tr_d] == [t[0] for t in tr_o]
+    for (name, a), (_, b) in zip(tr_d, tr_o):
+        assert np.array_equal(a, b), name
+    assert out_d["outer_ok"] and out_d["inner_ok"] and out_o["outer_ok"] and out_o["inner_ok"]
+    for k in ("eval_W_step", "eval_W_core", "T_out"):
+        assert out_d[k] == out_o[k]
+    S.free()

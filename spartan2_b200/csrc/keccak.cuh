@@ -59,7 +59,10 @@ __device__ __forceinline__ u64 keccak_f_warp(u64 s, const KeccakLane &k, int lan
     s ^= d;
     // (A variant with theta gathered in ONE stage — ten independent gathers straight from s instead of column parities
     // followed by a dependent neighbour exchange, two dependent shuffle stages per round instead of three — was measured
-    // on B200: no faster, 2.045 vs 2.014 ms per prove; SHFL issue, not the dependency depth, sets the pace.)
+    // on B200: no faster, 2.045 vs 2.014 ms per prove.  A variant with the cross-lane traffic through SHARED MEMORY
+    // (store s | sync | 10 LDS.64 -> theta, rho | store | sync | 3 LDS.64 -> pi, chi; 55 instructions per round) was
+    // measured SLOWER: 14.7k vs 12.2k cycles per squeeze of two permutations.  One warp cannot hide its own ALU/LDS
+    // latencies: the round is a ~250-cycle dependent chain either way.)
     // rho in place, then pi and chi's two neighbour reads as ONE shuffle stage (three independent gathers from the
     // rotated values) instead of pi followed by a dependent neighbour exchange
     const u64 t = rotl64(s, k.rot);

@@ -223,8 +223,12 @@ __device__ __forceinline__ fe sc_squeeze(ScState *st, FinSmem &sm, const fe &can
 // cubic: s(X) = l(X) * p * t(X),  l(X) = (1-tau) + (2tau-1) X,  t(X) = t0 + tb X + tinf X^2
 // x = (t(0), t(1), t(inf)) valid in every lane of warp 0.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cubic_finalize(ScState *st, int round1, int l, const fe *A, const fe *B, const fe *C,
-                                               const fe (&x)[3], FinSmem &sm) {
+// The finaliser is split so that only what the NEXT ROUND'S PAIR WORK needs (the challenge) sits on the critical
+// path: cubic_finalize_pre ends with r known to every thread of the CTA; cubic_bound (the eq-prefix update, three
+// serial multiplications that only the next round's FINALISER reads) and cubic_claims run afterwards on a thread that
+// has no pair work, overlapped with the next round (persistent kernels: after the grid release; tail kernels: the
+// scalar warp at the start of the next round).
+__device__ __forceinline__ fe cubic_finalize_pre(ScState *st, int round1, const fe (&x)[3], FinSmem &sm) {
   const int tid = threadIdx.x, i = round1 - 1;
   fe canon = Fq::zero();
   SC_STAMP(1);
@@ -248,23 +252,36 @@ __device__ __forceinline__ void cubic_finalize(ScState *st, int round1, int l, c
   }
   const fe r = sc_squeeze(st, sm, canon, 3);
   if (tid == 0) stg_fe(&st->r[i], r);
-  if (tid == 32) {            // bound(): p <- p * (1 - tau - r + 2 r tau) = p * l(r)   (sumcheck.rs:1399-1405)
-    const fe tau = ld_state(&st->taus[i]);
-    const fe l0 = Fq::sub(Fq::one(), tau), sl = Fq::sub(tau, l0);
-    const fe pn = mul_ni(ld_state(&st->p), Fq::add(l0, mul_ni(sl, r)));
-    stg_fe(&st->p, pn);
-    if (round1 < l) {
-      const fe tn = ld_state(&st->taus[i + 1]);
-      const fe l0n = Fq::sub(Fq::one(), tn), sln = Fq::sub(tn, l0n);
-      stg_fe(&st->L0, mul_ni(pn, l0n));
-      stg_fe(&st->SL, mul_ni(pn, sln));
-    }
+  return r;
+}
+// bound(): p <- p * (1 - tau - r + 2 r tau) = p * l(r)   (sumcheck.rs:1399-1405), and the next round's L0 / SL.  One thread.
+__device__ __forceinline__ void cubic_bound(ScState *st, int round1, int l, const fe &r) {
+  const int i = round1 - 1;
+  const fe tau = ld_state(&st->taus[i]);
+  const fe l0 = Fq::sub(Fq::one(), tau), sl = Fq::sub(tau, l0);
+  const fe pn = mul_ni(ld_state(&st->p), Fq::add(l0, mul_ni(sl, r)));
+  stg_fe(&st->p, pn);
+  if (round1 < l) {
+    const fe tn = ld_state(&st->taus[i + 1]);
+    const fe l0n = Fq::sub(Fq::one(), tn), sln = Fq::sub(tn, l0n);
+    stg_fe(&st->L0, mul_ni(pn, l0n));
+    stg_fe(&st->SL, mul_ni(pn, sln));
   }
-  if (round1 == l && (tid == 64 || tid == 96 || tid == 128)) {   // final claims: bind the length-2 tables
+}
+// final claims: bind the length-2 tables (threads 64, 96, 128 of the CTA)
+__device__ __forceinline__ void cubic_claims(ScState *st, const fe *A, const fe *B, const fe *C, const fe &r) {
+  const int tid = threadIdx.x;
+  if (tid == 64 || tid == 96 || tid == 128) {
     const fe *T = tid == 64 ? A : tid == 96 ? B : C;
     const fe lo = ld_state(T), hi = ld_state(T + 1);
     stg_fe(&st->claims[(tid - 64) / 32], Fq::add(lo, mul_ni(Fq::sub(hi, lo), r)));
   }
+}
+__device__ __forceinline__ void cubic_finalize(ScState *st, int round1, int l, const fe *A, const fe *B, const fe *C,
+                                               const fe (&x)[3], FinSmem &sm) {
+  const fe r = cubic_finalize_pre(st, round1, x, sm);
+  if (threadIdx.x == 32) cubic_bound(st, round1, l, r);
+  if (round1 == l) cubic_claims(st, A, B, C, r);
   SC_STAMP(6);
 }
 
@@ -411,13 +428,18 @@ k_cubic_round_roles(ScState *st, const fe *sA, const fe *sB, const fe *sC, fe *d
 
 // all remaining rounds [round_first, l] in one CTA (tables of <= SC_TAIL_LEN entries going in); ping-pongs between
 // (A,B,C) and the scratch copies (A2,B2,C2)
-__global__ void __launch_bounds__(SC_TAIL_THREADS, 1)
+// The CTA has SC_TAIL_THREADS role threads plus one SCALAR WARP (warp SC_TAIL_THREADS/32) that has no pair work: at
+// the start of round i+1 its lane 0 runs round i's cubic_bound while the role warps already evaluate round i+1.
+__global__ void __launch_bounds__(SC_TAIL_THREADS + 32, 1)
 k_cubic_tail(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int round_first, int l, const fe *eq_left, const fe *eq_right) {
   __shared__ FinSmem sm;
   const int first_half = l / 2, second_half = l - first_half;
   fe *sA = A, *sB = B, *sC = C, *dA = A2, *dB = B2, *dC = C2;
-  const int role = (threadIdx.x >> 5) % 3;
-  const u64 slot = (u64)((threadIdx.x >> 5) / 3) * 32 + (threadIdx.x & 31), nslots = (SC_TAIL_THREADS / 96) * 32;
+  const int warp = threadIdx.x >> 5, role = warp % 3;
+  const bool scalar_warp = warp >= SC_TAIL_THREADS / 32;
+  const u64 slot = (u64)(warp / 3) * 32 + (threadIdx.x & 31), nslots = (SC_TAIL_THREADS / 96) * 32;
+  fe r = Fq::zero();
+  if (round_first > 1) r = ld_state(&st->r[round_first - 2]);
   for (int round1 = round_first; round1 <= l; round1++) {
     const u64 P = (u64)1 << (l - round1);
     const fe *el = nullptr, *er; u32 sh = 0;
@@ -427,20 +449,22 @@ k_cubic_tail(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int round
     } else {
       er = eq_right + (((size_t)1 << (l - round1)) - 1);
     }
-    fe x[3];
+    fe x[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
     if (threadIdx.x == 0) st->clk[7] = st->clk[0];
     SC_STAMP(0);
-    if (round1 > 1) {
-      cubic_roles<true>(sA, sB, sC, dA, dB, dC, P, ld_state(&st->r[round1 - 2]), el, er, sh, role, slot, nslots, x);
-      fe *t;
-      t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t;      // the bound tables are now the source
+    if (scalar_warp) {
+      if (round1 > round_first && threadIdx.x == SC_TAIL_THREADS) cubic_bound(st, round1 - 1, l, r);
+    } else if (round1 > 1) {
+      cubic_roles<true>(sA, sB, sC, dA, dB, dC, P, r, el, er, sh, role, slot, nslots, x);
     } else {
       cubic_roles<false>(sA, sB, sC, dA, dB, dC, P, Fq::zero(), el, er, sh, role, slot, nslots, x);
     }
+    if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t; }   // the bound tables are now the source
     __syncthreads();
     block_sum_fq<3>(x, sm.red);
-    cubic_finalize(st, round1, l, sA, sB, sC, x, sm);
-    __syncthreads();
+    r = cubic_finalize_pre(st, round1, x, sm);
+    if (round1 == l) cubic_claims(st, sA, sB, sC, r);
+    SC_STAMP(6);
   }
 }
 
@@ -465,28 +489,42 @@ __global__ void __launch_bounds__(1024) k_cubic_init(ScState *st, int l, fe *eq_
 // ---------------------------------------------------------------------------------------------
 // quadratic: eval0 = sum a_lo b_lo, tinf = sum (a_hi-a_lo)(b_hi-b_lo)   (sumcheck.rs:128-174)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void quad_finalize(ScState *st, int round1, int rounds, const fe *A, const fe *B,
-                                              const fe (&x)[2], FinSmem &sm) {
+// split like the cubic finaliser: quad_finalize_pre leaves r with every thread (and the round's (e0, b, tinf) in
+// sm.g[0..2] for quad_claim); the running-claim update (two serial multiplications, read by the next FINALISER only)
+// and the final claims run off the critical path
+__device__ __forceinline__ fe quad_finalize_pre(ScState *st, int round1, const fe (&x)[2], FinSmem &sm) {
   const int tid = threadIdx.x, i = round1 - 1;
   fe canon = Fq::zero();
-  fe e0 = x[0], ti = x[1], b = Fq::zero();
   SC_STAMP(1);
   if (tid < 32) {
     // from_evals([e0, claim-e0, 2claim-3e0+2tinf]) = [e0, claim - 2 e0 - tinf, tinf]  (sumcheck.rs:205-216)
-    b = Fq::sub(Fq::sub(ld_state(&st->claim), Fq::dbl(e0)), ti);
+    const fe e0 = x[0], ti = x[1];
+    const fe b = Fq::sub(Fq::sub(ld_state(&st->claim), Fq::dbl(e0)), ti);
     if (tid < 3) stg_fe(&st->polys[4 * i + tid], tid == 0 ? e0 : tid == 1 ? b : ti);
     if (tid < 2) canon = Fq::from_mont(tid == 0 ? e0 : ti);
+    if (tid == 0) { sm.g[0] = e0; sm.g[1] = b; sm.g[2] = ti; }
   }
-  const fe r = sc_squeeze(st, sm, canon, 2);
-  if (tid == 0) {
-    stg_fe(&st->r[i], r);
-    stg_fe(&st->claim, Fq::add(e0, mul_ni(r, Fq::add(b, mul_ni(r, ti)))));
-  }
-  if (round1 == rounds && (tid == 64 || tid == 96)) {
+  const fe r = sc_squeeze(st, sm, canon, 2);      // (its barriers publish sm.g[0..2] to the CTA)
+  if (tid == 0) stg_fe(&st->r[i], r);
+  return r;
+}
+// claim <- poly(r); one thread; (e0, b, tinf) by value (copied out of sm.g before the next round overwrites it)
+__device__ __forceinline__ void quad_claim(ScState *st, const fe &e0, const fe &b, const fe &ti, const fe &r) {
+  stg_fe(&st->claim, Fq::add(e0, mul_ni(r, Fq::add(b, mul_ni(r, ti)))));
+}
+__device__ __forceinline__ void quad_claims(ScState *st, const fe *A, const fe *B, const fe &r) {
+  const int tid = threadIdx.x;
+  if (tid == 64 || tid == 96) {
     const fe *T = tid == 64 ? A : B;
     const fe lo = ld_state(T), hi = ld_state(T + 1);
     stg_fe(&st->claims[(tid - 64) / 32], Fq::add(lo, mul_ni(Fq::sub(hi, lo), r)));
   }
+}
+__device__ __forceinline__ void quad_finalize(ScState *st, int round1, int rounds, const fe *A, const fe *B,
+                                              const fe (&x)[2], FinSmem &sm) {
+  const fe r = quad_finalize_pre(st, round1, x, sm);
+  if (threadIdx.x == 0) quad_claim(st, sm.g[0], sm.g[1], sm.g[2], r);
+  if (round1 == rounds) quad_claims(st, A, B, r);
   SC_STAMP(6);
 }
 
@@ -577,30 +615,35 @@ k_quad_round_roles(ScState *st, const fe *sA, const fe *sB, fe *dA, fe *dB, u64 
   quad_finalize(st, round1, rounds, FUSED ? dA : sA, FUSED ? dB : sB, x, sm);
 }
 
-__global__ void __launch_bounds__(SC_TAIL_THREADS, 1)
+__global__ void __launch_bounds__(SC_TAIL_THREADS + 32, 1)
 k_quad_tail(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int rounds, u64 nvalid) {
   __shared__ FinSmem sm;
   fe *sA = A, *sB = B, *dA = A2, *dB = B2;
-  const int role = (threadIdx.x >> 5) % 3;
-  const u64 slot = (u64)((threadIdx.x >> 5) / 3) * 32 + (threadIdx.x & 31), nslots = (SC_TAIL_THREADS / 96) * 32;
+  const int warp = threadIdx.x >> 5, role = warp % 3;
+  const bool scalar_warp = warp >= SC_TAIL_THREADS / 32;     // see k_cubic_tail
+  const u64 slot = (u64)(warp / 3) * 32 + (threadIdx.x & 31), nslots = (SC_TAIL_THREADS / 96) * 32;
+  fe r = Fq::zero();
+  if (round_first > 1) r = ld_state(&st->r[round_first - 2]);
   for (int round1 = round_first; round1 <= rounds; round1++) {
     const u64 P = (u64)1 << (rounds - round1);
-    fe x[2];
+    fe x[2] = {Fq::zero(), Fq::zero()};
     if (threadIdx.x == 0) st->clk[7] = st->clk[0];
     SC_STAMP(0);
     // only the first two launches can see unmaterialised entries; afterwards the bound table is dense
     const u64 nv = round1 <= 2 ? nvalid : ~0ull;
-    if (round1 > 1) {
-      quad_roles<true>(sA, sB, dA, dB, P, ld_state(&st->r[round1 - 2]), role, slot, nslots, nv, x);
-      fe *t;
-      t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t;
+    if (scalar_warp) {
+      if (round1 > round_first && threadIdx.x == SC_TAIL_THREADS) quad_claim(st, sm.g[0], sm.g[1], sm.g[2], r);
+    } else if (round1 > 1) {
+      quad_roles<true>(sA, sB, dA, dB, P, r, role, slot, nslots, nv, x);
     } else {
       quad_roles<false>(sA, sB, dA, dB, P, Fq::zero(), role, slot, nslots, nv, x);
     }
+    if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; }
     __syncthreads();
     block_sum_fq<2>(x, sm.red);
-    quad_finalize(st, round1, rounds, sA, sB, x, sm);
-    __syncthreads();
+    r = quad_finalize_pre(st, round1, x, sm);
+    if (round1 == rounds) quad_claims(st, sA, sB, r);
+    SC_STAMP(6);
   }
 }
 
@@ -715,9 +758,12 @@ __global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_cubic_persist(P
     if (bid == 0 && tid == 0) st->prof[round1 - 1][1] = gtimer();
     if (persist_gather<3>(st, seq, x, sm)) {
       if (tid == 0) st->prof[round1 - 1][2] = gtimer();
-      cubic_finalize(st, round1, l, sA, sB, sC, x, sm);
+      const fe rn = cubic_finalize_pre(st, round1, x, sm);
       if (tid == 0) st->prof[round1 - 1][3] = gtimer();
       persist_release(st, seq);
+      // off the critical path: the grid is already streaming the next round (warps 6, 7 have no pair work in role rounds)
+      if (tid == SC_THREADS - 32) cubic_bound(st, round1, l, rn);
+      if (round1 == l) cubic_claims(st, sA, sB, sC, rn);
     } else {
       persist_wait(st, seq);
     }
@@ -756,8 +802,10 @@ __global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_quad_persist(Pe
     seq++;
     if (roles && fused) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; }
     if (persist_gather<2>(st, seq, x, sm)) {
-      quad_finalize(st, round1, a.rounds, sA, sB, x, sm);
+      const fe rn = quad_finalize_pre(st, round1, x, sm);
       persist_release(st, seq);
+      if (tid == SC_THREADS - 32) quad_claim(st, sm.g[0], sm.g[1], sm.g[2], rn);
+      if (round1 == a.rounds) quad_claims(st, sA, sB, rn);
     } else {
       persist_wait(st, seq);
     }
@@ -863,7 +911,7 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     }
     const u64 P = sharded ? Pg >> dc.k : Pg;                    // local pairs
     if (!sharded && len_in <= SC_TAIL_LEN) {
-      k_cubic_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
+      k_cubic_tail<<<1, SC_TAIL_THREADS + 32, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
       SP2_LAUNCH_CHECK();
       break;
     }
@@ -947,7 +995,7 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
     }
     const u64 P = sharded ? Pg >> dc.k : Pg;
     if (!sharded && len_in <= SC_TAIL_LEN) {
-      k_quad_tail<<<1, SC_TAIL_THREADS, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);
+      k_quad_tail<<<1, SC_TAIL_THREADS + 32, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);
       SP2_LAUNCH_CHECK();
       if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
       break;

@@ -237,10 +237,50 @@ int32_t sp2_bind_tables_dev(sp2_ctx *ctx, void *const *d_tables, uint32_t ntable
  * out[row] = sum_i w[i] * comms[i*rows + row], affine in/out                                                      */
 int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n, uint32_t rows, const uint64_t *w, uint64_t *out_xy);
 
+/* ---- fused NeutronNova hot path (BASELINE configs 3 / 5) ----------------------------------------------------------
+ * NeutronNovaZkSNARK::{prep_prove, prove} (src/neutronnova_zk.rs:1477-1603, 1609-2093), data path: the per-step
+ * Az/Bz/Cz of prep_prove, then HOT LOOP A (NeutronNovaNIFS::prove :511-1273 + R1CSWitness::fold_multiple,
+ * src/r1cs/mod.rs:570-660), HOT LOOP B (prove_cubic_with_additive_term_batched, two branches, src/sumcheck.rs:786-917),
+ * bind_and_prepare_poly_ABC_full x 2 (:1868-1875) and HOT LOOP C (prove_quad_batched, src/sumcheck.rs:702-782), with all
+ * tables device-resident and the per-round scalar algebra + Keccak transcript on the host inside the library (one
+ * host-mapped flag round trip per round).  Challenges are transcript-derived (absorb b"p" / squeeze b"c"); the
+ * reference's ZK wrapper draws them from its in-circuit verifier (process_round), which is out of scope — a fork
+ * that keeps the ZK wrapper uses the per-round seams above instead.  Every scalar below is 4 x u64 Montgomery limbs;
+ * the caller allocates all arrays (sizes in scalars). */
+typedef struct sp2_nn_prep sp2_nn_prep;
+typedef struct sp2_transcript sp2_transcript;
+typedef struct {
+  uint32_t n_steps, ell_b, ell, rounds_y;   /* out: instances, log2(instances), log2(num_cons), log2(2 * num_vars) */
+  uint64_t *nifs_evals;    /* ell_b x 2: (e0, quad_coeff) per round (prove_helper sums, :98-178)                  */
+  uint64_t *nifs_polys;    /* ell_b x 4: finish_round! coefficients (:703-735)                                    */
+  uint64_t *r_b;           /* ell_b                                                                                */
+  uint64_t *T_out;         /* 1: T_cur / acc_eq (:1206-1208)                                                      */
+  uint64_t *outer_evals;   /* ell x 6: evaluations at (0, 2, 3) of the step and the core branch, unscaled         */
+  uint64_t *outer_polys;   /* ell x 8: the two cubic round polynomials                                            */
+  uint64_t *r_x;           /* ell                                                                                  */
+  uint64_t *claims_outer;  /* 6: Az, Bz, Cz (step), Az, Bz, Cz (core) at r_x                                      */
+  uint64_t *tau_at_rx;     /* 1                                                                                    */
+  uint64_t *r;             /* 1: batching challenge                                                               */
+  uint64_t *inner_evals;   /* rounds_y x 4: (eval_0, bound_coeff) per branch                                      */
+  uint64_t *inner_polys;   /* rounds_y x 6: the two quadratic round polynomials                                   */
+  uint64_t *r_y;           /* rounds_y                                                                             */
+  uint64_t *inner_final;   /* 4: poly_ABC (step, core), z (step, core) at r_y                                     */
+  uint64_t *eval_W;        /* 2                                                                                    */
+  uint64_t *heads;         /* optional (may be NULL), 28: first 4 entries of the folded Az, Bz, Cz; first 8 of the
+                              folded witness; first 8 of poly_ABC (step) — parity probes                          */
+  int32_t outer_ok, inner_ok;  /* the verifier's final equations of the two sum-checks hold                        */
+} sp2_nn_proof;
+/* step_zs: n_steps x num_cols scalars (z_i = [W_i | 1 | X_i]); core_z: num_cols.  n_steps: power of two in [2, 256]. */
+int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *shape, uint32_t n_steps, const uint64_t *step_zs, const uint64_t *core_z,
+                                   sp2_nn_prep **out);
+/* phase_ms (optional, 6 floats): nifs, fold_witness, outer_sumcheck_batched, compute_eval_table_sparse,
+ * inner_sumcheck_batched, total (host wall clock; every phase ends in a host wait)                                  */
+int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *prep, sp2_transcript *ts, sp2_nn_proof *proof, float *phase_ms);
+void sp2_neutronnova_prep_free(sp2_nn_prep *prep);
+
 /* ---- host Keccak256Transcript (src/provider/keccak.rs:18-105 behind TranscriptEngineTrait, src/traits/transcript.rs) ----
  * Host-side Fiat-Shamir for drivers that interleave per-round device calls with transcript steps (a Rust caller keeps
  * using its own Keccak256Transcript; this is the same object for C/C++/Python hosts).  Scalars are Montgomery limbs. */
-typedef struct sp2_transcript sp2_transcript;
 int32_t sp2_transcript_new(const char *label, sp2_transcript **out);
 void sp2_transcript_free(sp2_transcript *t);
 int32_t sp2_transcript_absorb_bytes(sp2_transcript *t, const char *label, const uint8_t *data, uint64_t n);

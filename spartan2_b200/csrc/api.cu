@@ -215,7 +215,6 @@ int32_t sp2_test_transcript(sp2_ctx *ctx, sp2_transcript_state *ts, const uint8_
 
 /* ---- host Keccak256Transcript (src/provider/keccak.rs:18-105; TranscriptEngineTrait, src/traits/transcript.rs) ----
  * For host-side drivers that run the Fiat-Shamir steps between per-round device calls (the NeutronNova seams). */
-struct sp2_transcript { sp2h::Transcript t; explicit sp2_transcript(const char *label) : t(label) {} };
 
 int32_t sp2_transcript_new(const char *label, sp2_transcript **out) {
   if (!out || !label) return SP2_ERR_INTERNAL;

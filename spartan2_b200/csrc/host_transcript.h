@@ -266,3 +266,6 @@ inline void fq_from_uniform(const uint8_t dg[64], uint64_t out_mont[4]) {
 }
 
 }  // namespace sp2h
+
+// the C-ABI handle of the host transcript (include/spartan2_b200.h: sp2_transcript_*)
+struct sp2_transcript { sp2h::Transcript t; explicit sp2_transcript(const char *label) : t(label) {} };

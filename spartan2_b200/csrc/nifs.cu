@@ -385,3 +385,580 @@ int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n,
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Fused NeutronNova hot path: HOT LOOPS A-C of NeutronNovaZkSNARK::prove (src/neutronnova_zk.rs:1609-2093) with the
+// per-step products of prep_prove (:1538-1549) in front, driven from C++ inside the library.
+//
+// State is device-resident across the whole prove (layers, witnesses, tables); the host only does what the reference
+// also does on its main thread between the parallel loops: the per-round scalar algebra (finish_round!, UniPoly
+// interpolation, claim updates) and the Keccak transcript.  Per round the device publishes the <= 6 round sums into
+// HOST-MAPPED pinned memory (st.global over PCIe + system fence + sequence flag) and the host spins on the flag: no
+// cudaMemcpy, no stream synchronisation; the challenge travels back as a kernel ARGUMENT of the next launch (bind /
+// fold), so a round costs one flag round trip instead of upload + download + two syncs.
+//
+// Challenges come from a plain Keccak transcript (absorb b"p" / squeeze b"c", as the non-ZK provers do,
+// src/sumcheck.rs:536-548): the reference's ZK driver draws them through its in-circuit verifier (process_round,
+// src/bellpepper/r1cs.rs:735-816), which is out of scope.  The data path, the host algebra per round and
+// every intermediate value are the reference's; spartan2_b200/neutronnova.py is the same driver over the per-round C-ABI
+// seams (and, in the tests, over the oracle), and tests/test_gpu_neutronnova.py compares the two value by value.
+// =====================================================================================================================
+#include <atomic>
+#include <chrono>
+#include "r1cs.cuh"
+
+namespace sp2 {
+int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out);
+}
+
+struct sp2_nn_prep {
+  sp2_ctx *ctx = nullptr;
+  const sp2_shape *S = nullptr;
+  uint32_t n = 0, ell_b = 0, ell = 0, left = 0, right = 0;
+  uint64_t N = 0, M = 0, ncols = 0;
+  fe *zs = nullptr, *zc = nullptr;           // n x ncols, ncols
+  fe *Ws = nullptr;                          // n x M (contiguous copies of the witness sections)
+  fe *L[3] = {nullptr, nullptr, nullptr};    // cached step layers Az_i, Bz_i, Cz_i: n x N, layer-major
+  fe *Lc[3] = {nullptr, nullptr, nullptr};   // cached core layers
+  fe *work[3] = {nullptr, nullptr, nullptr}, *workc[3] = {nullptr, nullptr, nullptr};   // folded / bound in place by prove
+  fe *z_step = nullptr, *z_core = nullptr, *abc_s = nullptr, *abc_c = nullptr;          // 2M each
+  fe *E = nullptr, *rx = nullptr, *small = nullptr, *partials = nullptr;
+  u32 *ticket = nullptr;
+  // host-mapped mailbox: [0] sequence flag, results at +64 bytes
+  unsigned char *h_mail = nullptr; unsigned char *d_mail = nullptr;
+  unsigned char *h_stage = nullptr;          // pinned staging for small uploads / head read-backs
+  u32 seq = 0;
+  std::vector<void *> owned;
+};
+
+namespace {
+
+constexpr size_t NN_MAIL_BYTES = 4096, NN_STAGE_BYTES = 1 << 16, NN_SMALL_FE = 1024, NN_MAX_PARTS = 4096;
+
+__global__ void __launch_bounds__(NF_THREADS) k_nifs_fold_v(fe *A, fe *B, fe *C, u64 N, u64 pairs, u64 stride, fe rr) {
+  fe *T[3] = {A, B, C};
+  for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < pairs * N; q += (u64)gridDim.x * blockDim.x) {
+    const u64 p = q / N, k = q - p * N;
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      fe *lo = T[s] + (2 * p) * stride * N + k;
+      stg_fe(lo, bind_pair(ldg_fe(lo), ldg_fe(T[s] + (2 * p + 1) * stride * N + k), rr));
+    }
+  }
+}
+// group g (one CTA) sums its nparts partial NV-tuples and writes them to the host-mapped mailbox; the last group to
+// finish publishes the sequence number (system-scope fence first: the host reads the sums after it sees the flag)
+template <int NV>
+__global__ void __launch_bounds__(NF_THREADS) k_publish(const fe *partials, u32 nparts, fe *mail_out, u32 *mail_flag, u32 seq, u32 *ticket) {
+  __shared__ fe red[NV * 32];
+  const fe *src = partials + (size_t)blockIdx.x * nparts * NV;
+  fe x[NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) x[k] = Fq::zero();
+  for (u32 b = threadIdx.x; b < nparts; b += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < NV; k++) x[k] = Fq::add(x[k], ldg_fe(src + (size_t)b * NV + k));
+  block_sum_fq<NV>(x, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) stg_fe(mail_out + blockIdx.x * NV + k, x[k]);
+    __threadfence_system();
+    const u32 t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) { *ticket = 0; __threadfence_system(); *(volatile u32 *)mail_flag = seq; }
+  }
+}
+__global__ void k_set_one(fe *p) { if (threadIdx.x == 0) stg_fe(p, Fq::one()); }
+__global__ void __launch_bounds__(256) k_copy_rows(const fe *src, u64 src_stride, fe *dst, u64 dst_stride, u64 len, u64 rows) {
+  for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < rows * len; q += (u64)gridDim.x * blockDim.x) {
+    const u64 rw = q / len, i = q - rw * len;
+    stg_fe(dst + rw * dst_stride + i, ldg_fe(src + rw * src_stride + i));
+  }
+}
+
+// ---- one launch per round of the batched sum-checks: [bind to the previous challenge] + evaluate both branches +
+// last-CTA reduction + publication in the host-mapped mailbox ------------------------------------------------------
+struct NnTables { fe *t[2][3]; };                     // [branch][A, B, C] (outer) or [branch][poly_ABC, z, -] (inner)
+template <bool FUSED>
+__device__ __forceinline__ void nn_ld_pair(fe *T, u64 low, u64 len, const fe &r, fe &lo, fe &hi) {
+  if (FUSED) {                                         // the table still has 4*len entries: bind (low, low+2len), (low+len, low+3len) in place
+    lo = bind_pair(ldg_fe(T + low), ldg_fe(T + low + 2 * len), r);
+    hi = bind_pair(ldg_fe(T + low + len), ldg_fe(T + low + 3 * len), r);
+    stg_fe(T + low, lo); stg_fe(T + low + len, hi);
+  } else {
+    lo = ldg_fe(T + low); hi = ldg_fe(T + low + len);
+  }
+}
+// the last CTA of the grid (atomic ticket) sums the per-CTA partial NV-tuples of both branches and publishes 2*NV sums
+template <int NV>
+__device__ __forceinline__ void nn_publish_last(fe (&x)[NV], fe *partials, fe *red, int *is_last, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+  const u32 nb = gridDim.x, ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) stg_fe(partials + (size_t)cta * NV + k, x[k]);
+    __threadfence();
+    *is_last = atomicAdd(ticket, 1u) == ncta - 1;
+  }
+  __syncthreads();
+  if (!*is_last) return;
+  __threadfence();
+  for (u32 br = 0; br < gridDim.y; br++) {
+    fe y[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) y[k] = Fq::zero();
+    for (u32 b = threadIdx.x; b < nb; b += blockDim.x)
+#pragma unroll
+      for (int k = 0; k < NV; k++) y[k] = Fq::add(y[k], ldg_fe(partials + ((size_t)br * nb + b) * NV + k));
+    __syncthreads();
+    block_sum_fq<NV>(y, red);
+    if (threadIdx.x == 0)
+#pragma unroll
+      for (int k = 0; k < NV; k++) stg_fe(mail_out + br * NV + k, y[k]);
+  }
+  if (threadIdx.x == 0) { *ticket = 0; __threadfence_system(); *(volatile u32 *)mail_flag = seq; }
+}
+// outer: evaluation points (0, 2, 3) of sum_x pow(x) (A B - C) per branch (compute_eval_points_cubic_with_additive_term
+// [_with_outer_pow], src/sumcheck.rs:262-342, 366-498); len = half the (bound) table length
+template <bool FUSED>
+__global__ void __launch_bounds__(NF_THREADS) k_nn_outer_round(NnTables tb, const fe *pl, u32 left, const fe *pr, u64 len, fe r, fe *partials,
+                                                               u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+  __shared__ fe red[3 * 32];
+  __shared__ int is_last;
+  fe *A = tb.t[blockIdx.y][0], *B = tb.t[blockIdx.y][1], *C = tb.t[blockIdx.y][2];
+  fe x[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
+  if (len >= left) {
+    const u64 right = len / left;
+    const u64 per = (right + gridDim.x - 1) / gridDim.x, j0 = blockIdx.x * per, j1 = min(right, j0 + per);
+    for (u32 i = threadIdx.x; i < left; i += blockDim.x) {
+      Fq::acc a0 = Fq::acc_zero(), a2 = Fq::acc_zero(), a3 = Fq::acc_zero();
+      for (u64 j = j0; j < j1; j++) {
+        const u64 low = i + j * left;
+        const fe tl = ldg_fe_ro(pr + j), th = ldg_fe_ro(pr + j + right);
+        fe al, ah, bl, bh, cl, ch;
+        nn_ld_pair<FUSED>(A, low, len, r, al, ah); nn_ld_pair<FUSED>(B, low, len, r, bl, bh); nn_ld_pair<FUSED>(C, low, len, r, cl, ch);
+        Fq::mul_acc(a0, tl, Fq::sub(Fq::mul(al, bl), cl));
+        const fe dt = Fq::sub(th, tl), da = Fq::sub(ah, al), db = Fq::sub(bh, bl), dc = Fq::sub(ch, cl);
+        fe tb2 = Fq::add(th, dt), ab = Fq::add(ah, da), bb = Fq::add(bh, db), cb = Fq::add(ch, dc);      // 2*high - low
+        Fq::mul_acc(a2, tb2, Fq::sub(Fq::mul(ab, bb), cb));
+        tb2 = Fq::add(tb2, dt); ab = Fq::add(ab, da); bb = Fq::add(bb, db); cb = Fq::add(cb, dc);          // 3*high - 2*low
+        Fq::mul_acc(a3, tb2, Fq::sub(Fq::mul(ab, bb), cb));
+      }
+      const fe w = ldg_fe_ro(pl + i);
+      x[0] = Fq::add(x[0], Fq::mul(w, Fq::acc_reduce(a0)));
+      x[1] = Fq::add(x[1], Fq::mul(w, Fq::acc_reduce(a2)));
+      x[2] = Fq::add(x[2], Fq::mul(w, Fq::acc_reduce(a3)));
+    }
+  } else {                                            // len < left: the left table itself is the weight polynomial
+    Fq::acc a0 = Fq::acc_zero(), a2 = Fq::acc_zero(), a3 = Fq::acc_zero();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (u64)gridDim.x * blockDim.x) {
+      const fe tl = ldg_fe_ro(pl + i), th = ldg_fe_ro(pl + i + len);
+      fe al, ah, bl, bh, cl, ch;
+      nn_ld_pair<FUSED>(A, i, len, r, al, ah); nn_ld_pair<FUSED>(B, i, len, r, bl, bh); nn_ld_pair<FUSED>(C, i, len, r, cl, ch);
+      Fq::mul_acc(a0, tl, Fq::sub(Fq::mul(al, bl), cl));
+      const fe dt = Fq::sub(th, tl), da = Fq::sub(ah, al), db = Fq::sub(bh, bl), dc = Fq::sub(ch, cl);
+      fe tb2 = Fq::add(th, dt), ab = Fq::add(ah, da), bb = Fq::add(bh, db), cb = Fq::add(ch, dc);
+      Fq::mul_acc(a2, tb2, Fq::sub(Fq::mul(ab, bb), cb));
+      tb2 = Fq::add(tb2, dt); ab = Fq::add(ab, da); bb = Fq::add(bb, db); cb = Fq::add(cb, dc);
+      Fq::mul_acc(a3, tb2, Fq::sub(Fq::mul(ab, bb), cb));
+    }
+    x[0] = Fq::acc_reduce(a0); x[1] = Fq::acc_reduce(a2); x[2] = Fq::acc_reduce(a3);
+  }
+  block_sum_fq<3>(x, red);
+  __syncthreads();
+  nn_publish_last<3>(x, partials, red, &is_last, ticket, mail_out, mail_flag, seq);
+}
+// inner: (sum a_lo b_lo, sum (a_hi - a_lo)(b_hi - b_lo)) per branch (compute_eval_points_quad, src/sumcheck.rs:128-174)
+template <bool FUSED>
+__global__ void __launch_bounds__(NF_THREADS) k_nn_inner_round(NnTables tb, u64 len, fe r, fe *partials, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+  __shared__ fe red[2 * 32];
+  __shared__ int is_last;
+  fe *A = tb.t[blockIdx.y][0], *B = tb.t[blockIdx.y][1];
+  Fq::acc a0 = Fq::acc_zero(), ai = Fq::acc_zero();
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (u64)gridDim.x * blockDim.x) {
+    fe al, ah, bl, bh;
+    nn_ld_pair<FUSED>(A, i, len, r, al, ah); nn_ld_pair<FUSED>(B, i, len, r, bl, bh);
+    Fq::mul_acc(a0, al, bl);
+    Fq::mul_acc(ai, Fq::sub(ah, al), Fq::sub(bh, bl));
+  }
+  fe x[2] = {Fq::acc_reduce(a0), Fq::acc_reduce(ai)};
+  block_sum_fq<2>(x, red);
+  __syncthreads();
+  nn_publish_last<2>(x, partials, red, &is_last, ticket, mail_out, mail_flag, seq);
+}
+// last bind of a sum-check: the tables have two entries left; out[s] = T_s[0] + r (T_s[1] - T_s[0]) -> mailbox
+__global__ void k_bind_heads(TablePtrs tp, u32 ntab, fe r, fe *mail_out, u32 *mail_flag, u32 seq) {
+  const u32 i = threadIdx.x;
+  if (i < ntab) stg_fe(mail_out + i, bind_pair(ldg_fe(tp.t[i]), ldg_fe(tp.t[i] + 1), r));
+  __syncthreads();
+  if (i == 0) { __threadfence_system(); *(volatile u32 *)mail_flag = seq; }
+}
+
+// Host-side scalar field for the per-round algebra: the same Montgomery representation as `fe` (8 x u32 == 4 x u64
+// little-endian), multiplied with 64-bit limbs / __int128 (host_transcript.h: mont_mul) — the 32-bit carry-chain
+// emulation that field.cuh falls back to on the host costs ~1 us per multiplication, this ~40 ns.
+struct HF {
+  static void ld(const fe &a, uint64_t o[4]) { memcpy(o, a.v, 32); }
+  static fe st(const uint64_t a[4]) { fe r; memcpy(r.v, a, 32); return r; }
+  static fe zero() { return Fq::zero(); }
+  static fe one() { return Fq::one(); }
+  static bool is_zero(const fe &a) { return Fq::is_zero(a); }
+  static bool eq(const fe &a, const fe &b) { return Fq::eq(a, b); }
+  static fe add(const fe &x, const fe &y) {
+    uint64_t a[4], b[4], s[4], d[4]; ld(x, a); ld(y, b);
+    unsigned carry = 0, borrow = 0;
+    for (int j = 0; j < 4; j++) { const sp2h::u128 t = (sp2h::u128)a[j] + b[j] + carry; s[j] = (uint64_t)t; carry = (unsigned)(t >> 64); }
+    for (int j = 0; j < 4; j++) { const sp2h::u128 t = (sp2h::u128)s[j] - sp2h::FQ_MOD[j] - borrow; d[j] = (uint64_t)t; borrow = (unsigned)((t >> 64) & 1); }
+    return st((carry || !borrow) ? d : s);
+  }
+  static fe sub(const fe &x, const fe &y) {
+    uint64_t a[4], b[4], d[4]; ld(x, a); ld(y, b);
+    unsigned borrow = 0;
+    for (int j = 0; j < 4; j++) { const sp2h::u128 t = (sp2h::u128)a[j] - b[j] - borrow; d[j] = (uint64_t)t; borrow = (unsigned)((t >> 64) & 1); }
+    if (borrow) { unsigned carry = 0; for (int j = 0; j < 4; j++) { const sp2h::u128 t = (sp2h::u128)d[j] + sp2h::FQ_MOD[j] + carry; d[j] = (uint64_t)t; carry = (unsigned)(t >> 64); } }
+    return st(d);
+  }
+  static fe dbl(const fe &x) { return add(x, x); }
+  static fe mul(const fe &x, const fe &y) { uint64_t a[4], b[4], o[4]; ld(x, a); ld(y, b); sp2h::mont_mul(a, b, sp2h::FQ_MOD, sp2h::FQ_INV, o); return st(o); }
+  static fe sqr(const fe &x) { return mul(x, x); }
+  static fe inv(const fe &x) {              // Fermat, x^(q-2); inv(0) = 0
+    const uint64_t e[4] = {sp2h::FQ_MOD[0] - 2, sp2h::FQ_MOD[1], sp2h::FQ_MOD[2], sp2h::FQ_MOD[3]};
+    fe r = one();
+    for (int i = 255; i >= 0; i--) { r = sqr(r); if ((e[i >> 6] >> (i & 63)) & 1) r = mul(r, x); }
+    return r;
+  }
+  static fe two_inv() { return Fq::two_inv(); }
+  static fe six_inv() { return Fq::six_inv(); }
+};
+struct NnHost {
+  static fe load(const uint64_t *p) { fe r; memcpy(r.v, p, 32); return r; }
+  static void store(uint64_t *p, const fe &x) { memcpy(p, x.v, 32); }
+  static fe eval(const fe *c, int n, const fe &r) { fe acc = c[n - 1]; for (int i = n - 2; i >= 0; i--) acc = HF::add(HF::mul(acc, r), c[i]); return acc; }
+  // UniPoly::from_evals (src/polys/univariate.rs:84-120): evaluations at 0, 1, 2[, 3] -> coefficients low to high
+  static void from_evals3(const fe &e0, const fe &e1, const fe &e2, fe *c) {
+    c[2] = HF::mul(HF::add(HF::sub(e2, HF::dbl(e1)), e0), HF::two_inv());
+    c[1] = HF::sub(HF::sub(e1, e0), c[2]);
+    c[0] = e0;
+  }
+  static void from_evals4(const fe &e0, const fe &e1, const fe &e2, const fe &e3, fe *c) {
+    const fe t1 = HF::add(HF::dbl(e1), e1), t2 = HF::add(HF::dbl(e2), e2);
+    c[3] = HF::mul(HF::sub(HF::add(HF::sub(e3, t2), t1), e0), HF::six_inv());
+    c[2] = HF::sub(HF::mul(HF::add(HF::sub(e2, HF::dbl(e1)), e0), HF::two_inv()), HF::add(HF::dbl(c[3]), c[3]));
+    c[1] = HF::sub(HF::sub(HF::sub(e1, e0), c[2]), c[3]);
+    c[0] = e0;
+  }
+};
+
+// wait for the device to publish sequence number `seq` in the mailbox (bounded: a wedged stream surfaces as an error)
+int nn_wait(sp2_nn_prep *P, u32 seq) {
+  sp2_ctx *ctx = P->ctx;
+  volatile u32 *flag = (volatile u32 *)P->h_mail;
+  const auto t0 = std::chrono::steady_clock::now();
+  uint64_t spins = 0;
+  while (*flag != seq) {
+    if ((++spins & 0xfffff) == 0) {
+      const cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) return set_cuda_error(ctx, e, "neutronnova round", __LINE__);
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0)
+        return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: device did not publish a round result within 20 s");
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return SP2_OK;
+}
+inline const fe *nn_mail(const sp2_nn_prep *P) { return (const fe *)(P->h_mail + 64); }
+inline fe *nn_mail_dev(const sp2_nn_prep *P) { return (fe *)(P->d_mail + 64); }
+
+int nn_alloc(sp2_nn_prep *P, size_t nfe, fe **out) {
+  sp2_ctx *ctx = P->ctx; void *p;
+  SP2_CUDA_OK(cudaMalloc(&p, std::max<size_t>(nfe, 1) * sizeof(fe)));
+  P->owned.push_back(p); *out = (fe *)p;
+  return SP2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void sp2_neutronnova_prep_free(sp2_nn_prep *P) {
+  if (!P) return;
+  cudaSetDevice(P->ctx->device);
+  cudaStreamSynchronize(P->ctx->stream);
+  for (void *p : P->owned) cudaFree(p);
+  if (P->h_mail) cudaFreeHost(P->h_mail);
+  if (P->h_stage) cudaFreeHost(P->h_stage);
+  delete P;
+}
+
+/* NeutronNovaZkSNARK::prep_prove, data path (src/neutronnova_zk.rs:1477-1603): the n step instances z_i = [W_i | 1 | X_i]
+ * (num_cols scalars each, host) and the core instance are uploaded once; Az_i, Bz_i, Cz_i for every step and for the
+ * core circuit are computed on the device and cached, layer-major.  n must be a power of two >= 2. */
+int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *S, uint32_t n_steps, const uint64_t *step_zs, const uint64_t *core_z,
+                                   sp2_nn_prep **out) {
+  cudaSetDevice(ctx->device);
+  if (!out) return SP2_ERR_INTERNAL;
+  *out = nullptr;
+  if (n_steps < 2 || (n_steps & (n_steps - 1))) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "neutronnova: the number of step instances must be a power of two >= 2");
+  if (S->nranks != 1) return set_error(ctx, SP2_ERR_UNSUPPORTED, "neutronnova: whole shape expected");
+  sp2_nn_prep *P = new sp2_nn_prep();
+  P->ctx = ctx; P->S = S; P->n = n_steps; P->N = S->num_cons; P->M = S->num_vars; P->ncols = S->num_cols;
+  while ((1u << P->ell_b) < n_steps) P->ell_b++;
+  while ((1ull << P->ell) < P->N) P->ell++;
+  P->left = 1u << ((P->ell + 1) / 2); P->right = 1u << (P->ell / 2);          // compute_tensor_decomp (:58-67)
+  int rc = SP2_OK;
+  auto fail = [&](int code) { sp2_neutronnova_prep_free(P); return code; };
+  const size_t n = n_steps, N = P->N, M = P->M, nc = P->ncols;
+  if ((rc = nn_alloc(P, n * nc, &P->zs)) || (rc = nn_alloc(P, nc, &P->zc)) || (rc = nn_alloc(P, n * M, &P->Ws))) return fail(rc);
+  for (int k = 0; k < 3; k++)
+    if ((rc = nn_alloc(P, n * N, &P->L[k])) || (rc = nn_alloc(P, N, &P->Lc[k])) || (rc = nn_alloc(P, n * N, &P->work[k])) || (rc = nn_alloc(P, N, &P->workc[k])))
+      return fail(rc);
+  if ((rc = nn_alloc(P, 2 * M, &P->z_step)) || (rc = nn_alloc(P, 2 * M, &P->z_core)) || (rc = nn_alloc(P, 2 * M, &P->abc_s)) || (rc = nn_alloc(P, 2 * M, &P->abc_c)) ||
+      (rc = nn_alloc(P, (size_t)P->left + P->right, &P->E)) || (rc = nn_alloc(P, N, &P->rx)) || (rc = nn_alloc(P, NN_SMALL_FE, &P->small)) ||
+      (rc = nn_alloc(P, NN_MAX_PARTS * 6, &P->partials)))
+    return fail(rc);
+  { void *p; if (cudaMalloc(&p, 64) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->ticket = (u32 *)p;
+    cudaMemsetAsync(p, 0, 64, ctx->stream); }
+  if (cudaHostAlloc((void **)&P->h_mail, NN_MAIL_BYTES, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void **)&P->d_mail, P->h_mail, 0) != cudaSuccess ||
+      cudaMallocHost((void **)&P->h_stage, NN_STAGE_BYTES) != cudaSuccess)
+    return fail(set_error(ctx, SP2_ERR_CUDA, "neutronnova: pinned allocation failed"));
+  memset(P->h_mail, 0, NN_MAIL_BYTES);
+  // upload the instances (one copy each), split off the witness sections, per-step products
+  if (cudaMemcpyAsync(P->zs, step_zs, n * nc * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+      cudaMemcpyAsync(P->zc, core_z, nc * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    return fail(set_error(ctx, SP2_ERR_CUDA, "neutronnova: upload failed"));
+  k_copy_rows<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(P->zs, nc, P->Ws, M, M, n);
+  ctx->launches++;
+  for (size_t i = 0; i < n; i++) {
+    fe *o[3] = {P->L[0] + i * N, P->L[1] + i * N, P->L[2] + i * N};
+    if ((rc = spmv3_dev(ctx, S, S->M, P->zs + i * nc, nullptr, o))) return fail(rc);
+  }
+  { fe *o[3] = {P->Lc[0], P->Lc[1], P->Lc[2]}; if ((rc = spmv3_dev(ctx, S, S->M, P->zc, nullptr, o))) return fail(rc); }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "neutronnova: prep_prove failed on the device"));
+  *out = P;
+  return SP2_OK;
+}
+
+/* HOT LOOPS A-C (see the section header).  `ts` is advanced exactly as the Python driver advances its transcript.
+ * phase_ms (optional, 6 floats): nifs, fold_witness, outer_sumcheck_batched, compute_eval_table_sparse,
+ * inner_sumcheck_batched, total — host wall clock (every phase ends in a host wait). */
+int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_nn_proof *pf, float *phase_ms) {
+  cudaSetDevice(ctx->device);
+  if (!P || !tsh || !pf) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: null argument");
+  sp2h::Transcript &ts = tsh->t;
+  const sp2_shape *S = P->S;
+  const u32 n = P->n, ell_b = P->ell_b, ell = P->ell, left = P->left, right = P->right;
+  const u64 N = P->N, M = P->M;
+  u32 my = 0; while ((1ull << my) < 2 * M) my++;                       // inner rounds: log2(2M)
+  if (N > (1ull << 31) || n > 256 || ell_b > 8 || my > 40 || ell > 40) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "neutronnova_prove: size out of range");
+  pf->n_steps = n; pf->ell_b = ell_b; pf->ell = ell; pf->rounds_y = my; pf->outer_ok = 0; pf->inner_ok = 0;
+  typedef NnHost H;
+  const fe one = HF::one(), zero = HF::zero();
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) { return (float)(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()); };
+  const auto t_begin = now(); auto t_phase = t_begin;
+  float ph[6] = {0, 0, 0, 0, 0, 0};
+  auto squeeze = [&](const char *label) { uint8_t dg[64]; uint64_t o[4]; ts.squeeze(label, dg); sp2h::fq_from_uniform(dg, o); return H::load(o); };
+  auto absorb = [&](const char *label, const fe *v, size_t k) { ts.absorb_scalars(label, (const uint64_t *)v, k); };
+  size_t stage_off = 0;
+  auto stage = [&](const void *src, size_t bytes, fe *dst) -> int {   // small async upload through pinned staging
+    if (stage_off + bytes > NN_STAGE_BYTES) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: staging overflow");
+    memcpy(P->h_stage + stage_off, src, bytes);
+    SP2_CUDA_OK(cudaMemcpyAsync(dst, P->h_stage + stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    stage_off += (bytes + 63) & ~(size_t)63;
+    return SP2_OK;
+  };
+  u32 *mail_flag = (u32 *)P->d_mail;
+
+  // working copies of the cached layers (the NIFS folds and the sum-check binds are in place)
+  for (int k = 0; k < 3; k++) {
+    SP2_CUDA_OK(cudaMemcpyAsync(P->work[k], P->L[k], (size_t)n * N * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+    SP2_CUDA_OK(cudaMemcpyAsync(P->workc[k], P->Lc[k], (size_t)N * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  fe *As = P->work[0], *Bs = P->work[1], *Cs = P->work[2], *Ac = P->workc[0], *Bc = P->workc[1], *Cc = P->workc[2];
+
+  // ---- HOT LOOP A: NIFS (neutronnova_zk.rs:511-1273) ----------------------------------------------------------
+  absorb("T", &zero, 1);
+  const fe tau = squeeze("tau");
+  SP2_TRY(stage(&tau, sizeof(fe), P->small));
+  k_pow_split<<<(left + right + 127) / 128, 128, 0, ctx->stream>>>(P->small, left, right, P->E);
+  SP2_LAUNCH_CHECK();
+  std::vector<fe> rhos(ell_b), rho_inv(ell_b);
+  for (u32 t = 0; t < ell_b; t++) rhos[t] = squeeze("rho");
+  SP2_TRY(stage(rhos.data(), ell_b * sizeof(fe), P->small + 8));
+  const fe *d_rhos = P->small + 8;
+  { // batch inversion of the rhos (finish_round! divides by rho, :703-735): one inversion, on the host while the device copies
+    std::vector<fe> pre(ell_b + 1); pre[0] = one;
+    for (u32 t = 0; t < ell_b; t++) { if (HF::is_zero(rhos[t])) return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "neutronnova: rho = 0"); pre[t + 1] = HF::mul(pre[t], rhos[t]); }
+    fe inv = HF::inv(pre[ell_b]);
+    for (u32 t = ell_b; t-- > 0;) { rho_inv[t] = HF::mul(inv, pre[t]); inv = HF::mul(inv, rhos[t]); }
+  }
+  fe T_cur = zero, acc_eq = one;
+  std::vector<fe> r_bs(ell_b);
+  u64 m = n, stride = 1;
+  for (u32 t = 0; t < ell_b; t++) {
+    const u32 pairs = (u32)(m / 2);
+    u32 chunks = std::max<u32>(1, std::min<u32>(right, (u32)(ctx->num_sms * 4) / std::max<u32>(1, pairs)));
+    if ((size_t)chunks * pairs > NN_MAX_PARTS) chunks = std::max<u32>(1, (u32)(NN_MAX_PARTS / pairs));
+    const u32 threads = std::min<u32>(NF_THREADS, (left + 31) / 32 * 32);
+    k_nifs_round<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(t, d_rhos, ell_b, left, right, P->E, As, Bs, Cs, N, stride, P->partials);
+    SP2_LAUNCH_CHECK();
+    const u32 seq = ++P->seq;
+    k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, nn_mail_dev(P), mail_flag, seq, P->ticket);
+    SP2_LAUNCH_CHECK();
+    SP2_TRY(nn_wait(P, seq));
+    const fe e0 = nn_mail(P)[0], quad = nn_mail(P)[1];
+    H::store(pf->nifs_evals + 8 * t, e0); H::store(pf->nifs_evals + 8 * t + 4, quad);
+    // finish_round! (neutronnova_zk.rs:703-735)
+    const fe rho = rhos[t], omr = HF::sub(one, rho), trm = HF::sub(rho, omr);
+    const fe c = HF::mul(e0, acc_eq), a = HF::mul(quad, acc_eq);
+    const fe a_b_c = HF::mul(HF::sub(T_cur, HF::mul(c, omr)), rho_inv[t]);
+    const fe b = HF::sub(HF::sub(a_b_c, a), c);
+    fe co[4] = {HF::mul(c, omr), HF::add(HF::mul(c, trm), HF::mul(b, omr)), HF::add(HF::mul(b, trm), HF::mul(a, omr)), HF::mul(a, trm)};
+    for (int k = 0; k < 4; k++) H::store(pf->nifs_polys + 16 * t + 4 * k, co[k]);
+    absorb("p", co, 4);
+    const fe r_b = squeeze("c");
+    r_bs[t] = r_b; H::store(pf->r_b + 4 * t, r_b);
+    acc_eq = HF::mul(acc_eq, HF::add(HF::mul(HF::sub(one, r_b), omr), HF::mul(r_b, rho)));
+    T_cur = H::eval(co, 4, r_b);
+    const u64 work = (m / 2) * N;
+    const unsigned nb = (unsigned)std::min<u64>((work + NF_THREADS - 1) / NF_THREADS, (u64)ctx->num_sms * 8);
+    k_nifs_fold_v<<<nb, NF_THREADS, 0, ctx->stream>>>(As, Bs, Cs, N, m / 2, stride, r_b);
+    SP2_LAUNCH_CHECK();
+    m /= 2; stride *= 2;
+  }
+  if (HF::is_zero(acc_eq)) return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "neutronnova: acc_eq = 0");
+  const fe T_out = HF::mul(T_cur, HF::inv(acc_eq));                      // :1206-1208
+  H::store(pf->T_out, T_out);
+  unsigned char *heads_stage = P->h_stage + NN_STAGE_BYTES - 28 * sizeof(fe);   // parity read-backs, copied out at the end
+  if (pf->heads) for (int k = 0; k < 3; k++)
+    SP2_CUDA_OK(cudaMemcpyAsync(heads_stage + k * 4 * sizeof(fe), P->work[k], 4 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ph[0] = ms_since(t_phase); t_phase = now();
+
+  // ---- R1CSWitness::fold_multiple (src/r1cs/mod.rs:570-660) + the z tables of the inner sum-check -----------------
+  SP2_TRY(stage(r_bs.data(), ell_b * sizeof(fe), P->small + 64));
+  k_weights_from_r<<<(n + 127) / 128, 128, 0, ctx->stream>>>(P->small + 64, ell_b, n, P->small + 128);
+  SP2_LAUNCH_CHECK();
+  SP2_CUDA_OK(cudaMemsetAsync(P->z_step + M, 0, (size_t)M * sizeof(fe), ctx->stream));
+  SP2_CUDA_OK(cudaMemsetAsync(P->z_core + M, 0, (size_t)M * sizeof(fe), ctx->stream));
+  { const unsigned nb = (unsigned)std::min<u64>((M + NF_THREADS - 1) / NF_THREADS, (u64)ctx->num_sms * 8);
+    k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->Ws, n, M, P->small + 128, P->z_step);
+    SP2_LAUNCH_CHECK(); }
+  SP2_CUDA_OK(cudaMemcpyAsync(P->z_core, P->zc, (size_t)M * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+  k_set_one<<<1, 32, 0, ctx->stream>>>(P->z_step + M); SP2_LAUNCH_CHECK();
+  k_set_one<<<1, 32, 0, ctx->stream>>>(P->z_core + M); SP2_LAUNCH_CHECK();
+  if (pf->heads) SP2_CUDA_OK(cudaMemcpyAsync(heads_stage + 12 * sizeof(fe), P->z_step, 8 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ph[1] = ms_since(t_phase); t_phase = now();      // (asynchronous: the device time of this phase lands in the next one)
+
+  // ---- HOT LOOP B: batched outer sum-check, 2 branches (src/sumcheck.rs:786-917) ----------------------------------
+  std::vector<fe> tau_pow(ell + 1);                 // tau^(2^k)
+  tau_pow[0] = tau; for (u32 k = 1; k <= ell; k++) tau_pow[k] = HF::sqr(tau_pow[k - 1]);
+  fe base_tau = one, claim_s = T_out, claim_c = zero;
+  std::vector<fe> r_x(ell);
+  fe *step_t[3] = {As, Bs, Cs}, *core_t[3] = {Ac, Bc, Cc};
+  u64 tl = N;
+  NnTables otb; for (int k = 0; k < 3; k++) { otb.t[0][k] = step_t[k]; otb.t[1][k] = core_t[k]; }
+  fe r_prev = zero;
+  for (u32 i = 0; i < ell; i++) {
+    const u64 len = tl / 2;
+    u32 nb;                                            // CTAs per branch
+    if (len >= left) nb = (u32)std::max<u64>(1, std::min<u64>(len / left, (u64)ctx->num_sms));
+    else nb = (u32)((len + NF_THREADS - 1) / NF_THREADS);
+    const u32 threads = len >= left ? std::min<u32>(NF_THREADS, (left + 31) / 32 * 32) : NF_THREADS;
+    const u32 seq = ++P->seq;
+    if (i == 0) k_nn_outer_round<false><<<dim3(nb, 2), threads, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+    else k_nn_outer_round<true><<<dim3(nb, 2), threads, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+    SP2_LAUNCH_CHECK();
+    SP2_TRY(nn_wait(P, seq));
+    fe ev[6];
+    for (int k = 0; k < 6; k++) { ev[k] = nn_mail(P)[k]; H::store(pf->outer_evals + 24 * i + 4 * k, ev[k]); ev[k] = HF::mul(ev[k], base_tau); }
+    fe co[8];
+    H::from_evals4(ev[0], HF::sub(claim_s, ev[0]), ev[1], ev[2], co);
+    H::from_evals4(ev[3], HF::sub(claim_c, ev[3]), ev[4], ev[5], co + 4);
+    for (int k = 0; k < 8; k++) H::store(pf->outer_polys + 32 * i + 4 * k, co[k]);
+    absorb("p", co, 8);
+    const fe r_i = squeeze("c");
+    r_x[i] = r_i; H::store(pf->r_x + 4 * i, r_i);
+    claim_s = H::eval(co, 4, r_i); claim_c = H::eval(co + 4, 4, r_i);
+    r_prev = r_i;                                      // bound by the next round's launch (or by k_bind_heads after the last)
+    tl /= 2;
+    const fe pw = tau_pow[ell - 1 - i];             // tau^(N >> (i+1)) = E[len_pow % left] * E[left + len_pow / left]
+    base_tau = HF::mul(base_tau, HF::add(HF::mul(HF::sub(pw, one), r_i), one));
+  }
+  fe cl[6];
+  { TablePtrs tp; tp.t[0] = As; tp.t[1] = Bs; tp.t[2] = Cs; tp.t[3] = Ac; tp.t[4] = Bc; tp.t[5] = Cc; tp.t[6] = nullptr; tp.t[7] = nullptr;
+    const u32 seq = ++P->seq;
+    k_bind_heads<<<1, 32, 0, ctx->stream>>>(tp, 6, r_prev, nn_mail_dev(P), mail_flag, seq);
+    SP2_LAUNCH_CHECK();
+    SP2_TRY(nn_wait(P, seq));
+    for (int k = 0; k < 6; k++) { cl[k] = nn_mail(P)[k]; H::store(pf->claims_outer + 4 * k, cl[k]); } }
+  H::store(pf->tau_at_rx, base_tau);
+  pf->outer_ok = HF::eq(claim_s, HF::mul(base_tau, HF::sub(HF::mul(cl[0], cl[1]), cl[2]))) &&
+                 HF::eq(claim_c, HF::mul(base_tau, HF::sub(HF::mul(cl[3], cl[4]), cl[5])));
+  ph[2] = ms_since(t_phase); t_phase = now();
+
+  // ---- batching challenge, eq(r_x), poly_ABC for both branches (neutronnova_zk.rs:1853-1875) ------------------------
+  absorb("claims_outer", cl, 6);
+  const fe r = squeeze("r");
+  H::store(pf->r, r);
+  const fe r2 = HF::sqr(r);
+  fe claim_js = HF::add(HF::add(cl[0], HF::mul(r, cl[1])), HF::mul(r2, cl[2]));
+  fe claim_jc = HF::add(HF::add(cl[3], HF::mul(r, cl[4])), HF::mul(r2, cl[5]));
+  SP2_TRY(stage(r_x.data(), ell * sizeof(fe), P->small + 512));
+  SP2_TRY(stage(&r, sizeof(fe), P->small + 600));
+  SP2_TRY(eq_table_dev(ctx, P->small + 512, ell, P->rx));
+  SP2_TRY(abc_dev(ctx, S, P->rx, P->small + 600, P->abc_s, 2 * M));
+  SP2_TRY(abc_dev(ctx, S, P->rx, P->small + 600, P->abc_c, 2 * M));   // S_core == S_step for the SHA-256 chain; two calls as in the reference
+  if (pf->heads) SP2_CUDA_OK(cudaMemcpyAsync(heads_stage + 20 * sizeof(fe), P->abc_s, 8 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  ph[3] = ms_since(t_phase); t_phase = now();
+
+  // ---- HOT LOOP C: batched inner sum-check (src/sumcheck.rs:702-782) -------------------------------------------------
+  std::vector<fe> r_y(my);
+  tl = 2 * M;
+  NnTables itb; itb.t[0][0] = P->abc_s; itb.t[0][1] = P->z_step; itb.t[0][2] = nullptr; itb.t[1][0] = P->abc_c; itb.t[1][1] = P->z_core; itb.t[1][2] = nullptr;
+  r_prev = zero;
+  for (u32 j = 0; j < my; j++) {
+    const u64 len = tl / 2;
+    const u32 nb = (u32)std::max<u64>(1, std::min<u64>((len + NF_THREADS - 1) / NF_THREADS, (u64)ctx->num_sms));
+    const u32 seq = ++P->seq;
+    if (j == 0) k_nn_inner_round<false><<<dim3(nb, 2), NF_THREADS, 0, ctx->stream>>>(itb, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+    else k_nn_inner_round<true><<<dim3(nb, 2), NF_THREADS, 0, ctx->stream>>>(itb, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+    SP2_LAUNCH_CHECK();
+    SP2_TRY(nn_wait(P, seq));
+    fe co[6];
+    for (int b = 0; b < 2; b++) {
+      const fe e0 = nn_mail(P)[2 * b], tinf = nn_mail(P)[2 * b + 1], claim = b ? claim_jc : claim_js;
+      H::store(pf->inner_evals + 16 * j + 8 * b, e0); H::store(pf->inner_evals + 16 * j + 8 * b + 4, tinf);
+      const fe e2 = HF::add(HF::sub(HF::dbl(claim), HF::add(HF::dbl(e0), e0)), HF::dbl(tinf));        // BDDT (sumcheck.rs:731-733)
+      H::from_evals3(e0, HF::sub(claim, e0), e2, co + 3 * b);
+    }
+    for (int k = 0; k < 6; k++) H::store(pf->inner_polys + 24 * j + 4 * k, co[k]);
+    absorb("p", co, 6);
+    const fe r_j = squeeze("c");
+    r_y[j] = r_j; H::store(pf->r_y + 4 * j, r_j);
+    r_prev = r_j;
+    tl /= 2;
+    claim_js = H::eval(co, 3, r_j); claim_jc = H::eval(co + 3, 3, r_j);
+  }
+  fe fi[4];
+  { TablePtrs tp; tp.t[0] = P->abc_s; tp.t[1] = P->abc_c; tp.t[2] = P->z_step; tp.t[3] = P->z_core; for (int k = 4; k < 8; k++) tp.t[k] = nullptr;
+    const u32 seq = ++P->seq;
+    k_bind_heads<<<1, 32, 0, ctx->stream>>>(tp, 4, r_prev, nn_mail_dev(P), mail_flag, seq);
+    SP2_LAUNCH_CHECK();
+    SP2_TRY(nn_wait(P, seq));
+    for (int k = 0; k < 4; k++) { fi[k] = nn_mail(P)[k]; H::store(pf->inner_final + 4 * k, fi[k]); } }
+  // eval_W = (eval_Z - r_y[0] * eval_X) / (1 - r_y[0]); X = [1]: eval_X = prod (1 - r_y[1..])
+  fe eval_X = one;
+  for (u32 j = 1; j < my; j++) eval_X = HF::mul(eval_X, HF::sub(one, r_y[j]));
+  const fe den = HF::sub(one, r_y[0]);
+  if (HF::is_zero(den)) return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "neutronnova: r_y[0] = 1");
+  const fe inv = HF::inv(den);
+  H::store(pf->eval_W, HF::mul(HF::sub(fi[2], HF::mul(r_y[0], eval_X)), inv));
+  H::store(pf->eval_W + 4, HF::mul(HF::sub(fi[3], HF::mul(r_y[0], eval_X)), inv));
+  pf->inner_ok = HF::eq(claim_js, HF::mul(fi[0], fi[2])) && HF::eq(claim_jc, HF::mul(fi[1], fi[3]));
+  ph[4] = ms_since(t_phase);
+  if (pf->heads) { SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); memcpy(pf->heads, heads_stage, 28 * sizeof(fe)); }
+  ph[5] = ms_since(t_begin);
+  if (phase_ms) memcpy(phase_ms, ph, sizeof(ph));
+  return SP2_OK;
+}
+
+}  // extern "C"

@@ -255,3 +255,73 @@ def run(ops, ts, n_cons, step_zs, step_Ws, core_z, core_W, trace=None, timing=No
     out["outer_ok"] = (claim_s == base_tau * ((cl[0] * cl[1] - cl[2]) % Q) % Q) and (claim_c == base_tau * ((cl[3] * cl[4] - cl[5]) % Q) % Q)
     out["inner_ok"] = (claim_js == fi[0] * fi[2] % Q) and (claim_jc == fi[1] * fi[3] % Q)
     return out
+
+
+class _NnProofC(C.Structure):
+    _fields_ = [("n_steps", C.c_uint32), ("ell_b", C.c_uint32), ("ell", C.c_uint32), ("rounds_y", C.c_uint32)] + \
+               [(k, C.c_void_p) for k in ("nifs_evals", "nifs_polys", "r_b", "T_out", "outer_evals", "outer_polys", "r_x", "claims_outer", "tau_at_rx",
+                                          "r", "inner_evals", "inner_polys", "r_y", "inner_final", "eval_W", "heads")] + \
+               [("outer_ok", C.c_int32), ("inner_ok", C.c_int32)]
+
+
+class NeutronNovaProver:
+    """The fused path of the library (include/spartan2_b200.h: sp2_neutronnova_prep_prove / sp2_neutronnova_prove): the same
+    HOT LOOPS A-C as `run` above, with the round loop, the per-round scalar algebra and the Keccak transcript in C++
+    inside the library and all tables device-resident — one host-mapped flag round trip per round instead of several
+    C-ABI calls.  `prove` returns a dict keyed like `run`'s trace (so the parity test compares the two directly)."""
+
+    PHASES = ("nifs", "fold_witness", "outer_sumcheck_batched", "compute_eval_table_sparse", "inner_sumcheck_batched", "total")
+
+    def __init__(self, ctx, shape, step_zs, core_z):
+        self.ctx, self.S = ctx, shape
+        zs = np.ascontiguousarray(np.stack([_fe(z) for z in step_zs]), dtype=np.uint64)
+        zc = _fe(core_z)
+        if zs.shape[1] != shape.num_cols or zc.shape[0] != shape.num_cols:
+            from ._lib import SpartanError
+            raise SpartanError(-3, "z vectors must have num_cols entries")
+        self.n = zs.shape[0]
+        h = C.c_void_p()
+        ctx.check(ctx.L.sp2_neutronnova_prep_prove(ctx.h, shape.h, C.c_uint32(self.n), _p(zs), _p(zc), C.byref(h)))
+        self.h = h
+
+    def prove(self, ts):
+        """ts: spartan2_b200.Keccak256Transcript (advanced in place).  Returns (values, phase_ms)."""
+        ctx, S = self.ctx, self.S
+        ell_b = self.n.bit_length() - 1; ell = S.num_cons.bit_length() - 1; my = (2 * S.num_vars).bit_length() - 1
+        shapes = {"nifs_evals": (ell_b, 2), "nifs_polys": (ell_b, 4), "r_b": (ell_b,), "T_out": (1,), "outer_evals": (ell, 6), "outer_polys": (ell, 8),
+                  "r_x": (ell,), "claims_outer": (6,), "tau_at_rx": (1,), "r": (1,), "inner_evals": (my, 4), "inner_polys": (my, 6), "r_y": (my,),
+                  "inner_final": (4,), "eval_W": (2,), "heads": (28,)}
+        out = {k: np.zeros(v + (4,), dtype=np.uint64) for k, v in shapes.items()}
+        pc = _NnProofC()
+        for k, a in out.items():
+            setattr(pc, k, a.ctypes.data)
+        ph = (C.c_float * 6)()
+        ctx.check(ctx.L.sp2_neutronnova_prove(ctx.h, self.h, ts.h, C.byref(pc), ph))
+        out["outer_ok"], out["inner_ok"] = bool(pc.outer_ok), bool(pc.inner_ok)
+        return out, dict(zip(self.PHASES, [float(x) for x in ph]))
+
+    @staticmethod
+    def as_trace(v):
+        """The fused prover's outputs under the names `run` records them (minus E, which only `run` exposes)."""
+        t = {}
+        for i in range(v["nifs_evals"].shape[0]):
+            t["nifs_round_%d" % i] = v["nifs_evals"][i]; t["nifs_poly_%d" % i] = v["nifs_polys"][i]
+        t["folded_head"] = v["heads"][:12]; t["W_fold_head"] = v["heads"][12:20]; t["abc_head"] = v["heads"][20:28]
+        for i in range(v["outer_evals"].shape[0]):
+            t["outer_evals_%d" % i] = v["outer_evals"][i]; t["outer_polys_%d" % i] = v["outer_polys"][i]
+        t["claims_outer"] = v["claims_outer"]; t["tau_at_rx"] = v["tau_at_rx"]
+        for j in range(v["inner_evals"].shape[0]):
+            t["inner_evals_%d" % j] = v["inner_evals"][j]; t["inner_polys_%d" % j] = v["inner_polys"][j]
+        t["inner_final"] = v["inner_final"]; t["eval_W"] = v["eval_W"]
+        return t
+
+    def free(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.sp2_neutronnova_prep_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -122,3 +122,41 @@ def test_hot_path_device_vs_oracle(ctx, orc, n):
     for k in ("eval_W_step", "eval_W_core", "T_out"):
         assert out_d[k] == out_o[k]
     S.free()
+
+
+@pytest.mark.parametrize("n", [2, 32])
+def test_fused_prover_vs_oracle(ctx, orc, n):
+    """The fused path of the library (sp2_neutronnova_prep_prove + sp2_neutronnova_prove: round loop, scalar algebra and
+    transcript in C++, tables device-resident) against the per-round driver over the ORACLE backend with an identical
+    transcript: every value a verifier would see — NIFS sums and polynomials, both branches' 15 outer and 16 inner
+    round evaluations and polynomials, claims, tau(r_x), the folded layers / witness / poly_ABC probes, the final
+    evaluations — bit-identical; the challenges r_b, r_x, r_y and the transcript end state agree."""
+    import spartan2_b200 as sp
+    from spartan2_b200 import neutronnova as nn
+    from tests.neutronnova_ops import OracleOps, sha_chain_instances
+    c0, zs, Ws, zc, Wc = sha_chain_instances(n)
+    A, B, Cm = c0.matrices()
+    S = sp.SplitR1CSShape(ctx, *c0.dims(), A, B, Cm)
+    prover = nn.NeutronNovaProver(ctx, S, zs, zc)
+    for rep in range(2):                                   # prove twice from the same prep state: the cached layers are not consumed
+        ts_d = sp.Keccak256Transcript(b"neutronnova_prove")
+        v, ph = prover.prove(ts_d)
+    tr_o = []
+    ts_o = orc.Transcript(b"neutronnova_prove")
+    out_o = nn.run(OracleOps(orc.Shape(*c0.dims(), A, B, Cm), c0.dims()), ts_o, c0.num_cons, zs, Ws, zc, Wc, trace=tr_o)
+    got = nn.NeutronNovaProver.as_trace(v)
+    names = [t[0] for t in tr_o if t[0] != "E"]
+    assert sorted(names) == sorted(got.keys())
+    for name, b in tr_o:
+        if name != "E":
+            assert np.array_equal(got[name].reshape(-1), b.reshape(-1)), name
+    assert v["outer_ok"] and v["inner_ok"] and out_o["outer_ok"] and out_o["inner_ok"]
+    for k in ("r_b", "r_x", "r_y"):
+        assert np.array_equal(v[k].reshape(-1), np.asarray(out_o[k], dtype=np.uint64).reshape(-1)), k
+    from spartan2_b200 import _fq as fq
+    assert fq.to_int(v["T_out"]) == out_o["T_out"]
+    assert fq.to_ints(v["eval_W"]) == [out_o["eval_W_step"], out_o["eval_W_core"]]
+    st, rnd = ts_o.state()
+    assert ts_d.state().get() == (st, rnd)
+    assert ph["total"] > 0
+    prover.free(); S.free()

@@ -1154,3 +1154,128 @@ EXPORT void orc_fold_commitments(const apt *comms, size_t n, size_t rows, const 
     pt_to_affine(&CV, &out[r], &acc);
   }
 }
+
+/* ------------------------------------------------------------------------------------
+ * Small-value path (big_num/small_value.rs; its users in neutronnova_zk.rs)
+ * ---------------------------------------------------------------------------------- */
+#define SMALL_VALUE_MAX ((((uint64_t)1) << 62) - 1)          /* small_value.rs:32 */
+/* to_small_vec_or_zero (small_value.rs:42-85): canonical value in [0, 2^62-1] -> v, in [p-(2^62-1), p-1] -> -(p-v),
+ * anything else -> 0 with its index recorded.  Returns the number of large positions (ascending). */
+EXPORT size_t orc_to_small_vec_or_zero(const fe *poly, size_t n, int64_t *out, uint64_t *large_positions) {
+  size_t nl = 0;
+  for (size_t idx = 0; idx < n; idx++) {
+    fe c; f_to_raw(&FQ, c.l, &poly[idx]);                      /* to_repr(): canonical little-endian limbs */
+    if (c.l[1] == 0 && c.l[2] == 0 && c.l[3] == 0 && c.l[0] <= SMALL_VALUE_MAX) { out[idx] = (int64_t)c.l[0]; continue; }
+    uint64_t d[4];
+    f_sub4(d, FQ.mod, c.l);
+    if (d[1] == 0 && d[2] == 0 && d[3] == 0 && d[0] > 0 && d[0] <= SMALL_VALUE_MAX) { out[idx] = -(int64_t)d[0]; continue; }
+    out[idx] = 0; large_positions[nl++] = idx;
+  }
+  return nl;
+}
+/* SmallAccumulator (small_value.rs:96-196): separate positive / negative 448-bit sums of field_mont * |i128| */
+typedef struct { uint64_t pos[7], neg[7]; } small_acc;
+static void small_acc_accumulate(small_acc *a, const fe *f, __int128 val) {
+  if (val == 0) return;
+  const u128 av = val > 0 ? (u128)val : (u128)(-val);
+  uint64_t *t = val > 0 ? a->pos : a->neg;
+  const uint64_t lo = (uint64_t)av, hi = (uint64_t)(av >> 64);
+  u128 carry = 0;
+  for (int j = 0; j < 4; j++) { u128 p = (u128)f->l[j] * lo + t[j] + carry; t[j] = (uint64_t)p; carry = p >> 64; }
+  for (int j = 4; j < 7 && carry; j++) { u128 s = (u128)t[j] + carry; t[j] = (uint64_t)s; carry = s >> 64; }
+  if (hi) {
+    carry = 0;
+    for (int j = 0; j < 4; j++) { u128 p = (u128)f->l[j] * hi + t[j + 1] + carry; t[j + 1] = (uint64_t)p; carry = p >> 64; }
+    for (int j = 5; j < 7 && carry; j++) { u128 s = (u128)t[j] + carry; t[j] = (uint64_t)s; carry = s >> 64; }
+  }
+}
+/* reduce_7_to_field (small_value.rs:204-222): acc mod p, read as Montgomery limbs.  The general case is the
+ * reference's binary long division (limbs.rs:411-470), restated as shift-and-subtract from the top bit. */
+static void reduce_7_to_field(fe *out, const uint64_t acc[7]) {
+  if (acc[4] == 0 && acc[5] == 0 && acc[6] == 0) {
+    uint64_t b[4] = {acc[0], acc[1], acc[2], acc[3]};
+    for (int i = 0; i < FQ.max_sub; i++) if (f_gte4(b, FQ.mod)) f_sub4(b, b, FQ.mod);
+    memcpy(out->l, b, 32);
+    return;
+  }
+  uint64_t r[5] = {0, 0, 0, 0, 0};                             /* remainder < 2p fits 5 limbs */
+  for (int bit = 447; bit >= 0; bit--) {
+    for (int i = 4; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 63);
+    r[0] = (r[0] << 1) | ((acc[bit >> 6] >> (bit & 63)) & 1);
+    if (r[4] || f_gte4(r, FQ.mod)) { uint64_t bw = f_sub4(r, r, FQ.mod); r[4] -= bw; }
+  }
+  memcpy(out->l, r, 32);
+}
+static void small_acc_reduce(fe *out, const small_acc *a) {
+  fe p, n; reduce_7_to_field(&p, a->pos); reduce_7_to_field(&n, a->neg);
+  f_sub(&FQ, out, &p, &n);
+}
+/* test hook: sum_j f[j] * vals[j] through SmallAccumulator (vals as (lo, hi) two's-complement i128 halves) */
+EXPORT void orc_small_acc_dot(const fe *f, const uint64_t *vals_lo, const int64_t *vals_hi, size_t n, fe *out) {
+  small_acc a; memset(&a, 0, sizeof(a));
+  for (size_t j = 0; j < n; j++) small_acc_accumulate(&a, &f[j], (__int128)(((u128)(uint64_t)vals_hi[j] << 64) | vals_lo[j]));
+  small_acc_reduce(out, &a);
+}
+/* NeutronNovaNIFS::prove_helper_small (neutronnova_zk.rs:255-325): round 0, quad coefficient of one pair */
+static void nifs_prove_helper_small(size_t left, size_t right, const fe *e, const fe *Az1, const fe *Bz1, const fe *Az2, const fe *Bz2,
+                                    const int64_t *a1, const int64_t *b1, const int64_t *a2, const int64_t *b2,
+                                    const uint64_t *large_positions, size_t n_large, fe *quad) {
+  const fe *f = e + left, *el = e;
+  const size_t total = left * right;
+  acc9 aq; memset(&aq, 0, sizeof(aq));
+  for (size_t i = 0; i < right; i++) {
+    small_acc in; memset(&in, 0, sizeof(in));
+    for (size_t j = 0; j < left; j++) {
+      const size_t k = i * left + j;
+      const __int128 da = (__int128)a2[k] - (__int128)a1[k], db = (__int128)b2[k] - (__int128)b1[k];
+      small_acc_accumulate(&in, &el[j], da * db);
+    }
+    fe red; small_acc_reduce(&red, &in);
+    f_mul_acc(&aq, &f[i], &red);
+  }
+  f_reduce9(&FQ, quad, &aq);
+  for (size_t q = 0; q < n_large; q++) {                       /* field correction at the zeroed positions */
+    const size_t k = large_positions[q];
+    if (k >= total) continue;
+    const size_t i = k / left, j = k % left;
+    fe da, db, t;
+    f_sub(&FQ, &da, &Az2[k], &Az1[k]); f_sub(&FQ, &db, &Bz2[k], &Bz1[k]);
+    f_mul(&FQ, &t, &f[i], &el[j]); f_mul(&FQ, &t, &t, &da); f_mul(&FQ, &t, &t, &db);
+    f_add(&FQ, quad, quad, &t);
+  }
+}
+/* NIFS round 0 on the i64 layers (neutronnova_zk.rs:781-810): e0 = 0, quad = sum_p w_p * prove_helper_small(pair p) */
+EXPORT void orc_nifs_round0_small(size_t ell_b, const fe *rhos, size_t left, size_t right, const fe *E, const fe *A, const fe *B,
+                                  const int64_t *A64, const int64_t *B64, const uint64_t *large_positions, size_t n_large, size_t N, size_t m,
+                                  fe *out2) {
+  fe q; f_zero(&q); f_zero(&out2[0]);
+  for (size_t p = 0; p < m / 2; p++) {
+    fe pq, w, tmp;
+    nifs_prove_helper_small(left, right, E, A + 2 * p * N, B + 2 * p * N, A + (2 * p + 1) * N, B + (2 * p + 1) * N,
+                            A64 + 2 * p * N, B64 + 2 * p * N, A64 + (2 * p + 1) * N, B64 + (2 * p + 1) * N, large_positions, n_large, &pq);
+    suffix_weight_full(0, ell_b, p, rhos, &w);
+    f_mul(&FQ, &tmp, &pq, &w); f_add(&FQ, &q, &q, &tmp);
+  }
+  out2[1] = q;
+}
+/* c_vals (neutronnova_zk.rs:649-693): c_vals[b] = sum_k E[k] * Cz_b[k] from the i64 layer, corrected at large positions */
+EXPORT void orc_nifs_cvals_small(size_t left, size_t right, const fe *E, const fe *Cl, const int64_t *C64, const uint64_t *large_positions,
+                                 size_t n_large, size_t N, size_t n, fe *vals) {
+  const fe *f = E + left, *el = E;
+  for (size_t b = 0; b < n; b++) {
+    acc9 acc; memset(&acc, 0, sizeof(acc));
+    for (size_t i = 0; i < right; i++) {
+      small_acc in; memset(&in, 0, sizeof(in));
+      for (size_t j = 0; j < left; j++) small_acc_accumulate(&in, &el[j], (__int128)C64[b * N + i * left + j]);
+      fe red; small_acc_reduce(&red, &in);
+      f_mul_acc(&acc, &f[i], &red);
+    }
+    f_reduce9(&FQ, &vals[b], &acc);
+  }
+  for (size_t q = 0; q < n_large; q++) {
+    const size_t k = large_positions[q];
+    if (k >= left * right) continue;
+    fe ef; f_mul(&FQ, &ef, &el[k % left], &f[k / left]);
+    for (size_t b = 0; b < n; b++) { fe t; f_mul(&FQ, &t, &ef, &Cl[b * N + k]); f_add(&FQ, &vals[b], &vals[b], &t); }
+  }
+}

@@ -477,3 +477,43 @@ def fold_commitments(comms, n, rows, w):
     out = np.zeros((rows, 8), dtype=np.uint64)
     lib().orc_fold_commitments(_p(comms), C.c_size_t(n), C.c_size_t(rows), _p(w), _p(out))
     return out
+
+
+# ---- small-value path (big_num/small_value.rs and its users in neutronnova_zk.rs) ---------------------------------
+def to_small_vec_or_zero(poly):
+    """-> (i64 values, ascending positions of the values that did not fit and were stored as 0)"""
+    poly = np.ascontiguousarray(poly, dtype=np.uint64).reshape(-1, 4); n = poly.shape[0]
+    out = np.zeros(n, dtype=np.int64); large = np.zeros(max(n, 1), dtype=np.uint64)
+    L = lib(); L.orc_to_small_vec_or_zero.restype = C.c_size_t
+    k = L.orc_to_small_vec_or_zero(_p(poly), C.c_size_t(n), _p(out), _p(large))
+    return out, large[:k].copy()
+
+
+def small_acc_dot(f, vals):
+    """sum_j f[j] * vals[j] through SmallAccumulator; vals: python ints in the i128 range"""
+    f = np.ascontiguousarray(f, dtype=np.uint64).reshape(-1, 4); n = f.shape[0]
+    lo = np.array([v & 0xFFFFFFFFFFFFFFFF for v in vals], dtype=np.uint64)
+    hi = np.array([(v >> 64) for v in vals], dtype=np.int64)
+    out = fe_array(1)
+    lib().orc_small_acc_dot(_p(f), _p(lo), _p(hi), C.c_size_t(n), _p(out))
+    return out
+
+
+def nifs_round0_small(rhos, left, right, E, A, B, A64, B64, large, N, m):
+    rhos = np.ascontiguousarray(rhos, dtype=np.uint64).reshape(-1, 4)
+    E, A, B = (np.ascontiguousarray(x, dtype=np.uint64) for x in (E, A, B))
+    A64, B64 = (np.ascontiguousarray(x, dtype=np.int64) for x in (A64, B64))
+    large = np.ascontiguousarray(large, dtype=np.uint64); lp = large if large.shape[0] else np.zeros(1, dtype=np.uint64)
+    out = fe_array(2)
+    lib().orc_nifs_round0_small(C.c_size_t(rhos.shape[0]), _p(rhos), C.c_size_t(left), C.c_size_t(right), _p(E), _p(A), _p(B), _p(A64), _p(B64),
+                                _p(lp), C.c_size_t(large.shape[0]), C.c_size_t(N), C.c_size_t(m), _p(out))
+    return out
+
+
+def nifs_cvals_small(left, right, E, Cl, C64, large, N, n):
+    E, Cl = (np.ascontiguousarray(x, dtype=np.uint64) for x in (E, Cl)); C64 = np.ascontiguousarray(C64, dtype=np.int64)
+    large = np.ascontiguousarray(large, dtype=np.uint64); lp = large if large.shape[0] else np.zeros(1, dtype=np.uint64)
+    out = fe_array(n)
+    lib().orc_nifs_cvals_small(C.c_size_t(left), C.c_size_t(right), _p(E), _p(Cl), _p(C64), _p(lp), C.c_size_t(large.shape[0]), C.c_size_t(N),
+                               C.c_size_t(n), _p(out))
+    return out

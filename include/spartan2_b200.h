@@ -237,6 +237,23 @@ int32_t sp2_bind_tables_dev(sp2_ctx *ctx, void *const *d_tables, uint32_t ntable
  * out[row] = sum_i w[i] * comms[i*rows + row], affine in/out                                                      */
 int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n, uint32_t rows, const uint64_t *w, uint64_t *out_xy);
 
+/* ---- small-value path (src/big_num/small_value.rs and its users in src/neutronnova_zk.rs) ---------------------------
+ * to_small_vec_or_zero (small_value.rs:42-85) for up to 4 device tables of n_layers x N scalars (the Az, Bz, Cz layers of
+ * prep_prove, neutronnova_zk.rs:1551-1584): values with |v| <= 2^62 - 1 become int64, all others 0; the UNION of the
+ * large positions over all layers of all tables is zeroed in every int64 table and returned ascending in d_positions
+ * (N uint64, device); *n_large = their number.                                                                       */
+int32_t sp2_to_small_layers_dev(sp2_ctx *ctx, const void *const *d_tables, void *const *d_i64, uint32_t ntables, uint64_t n_layers, uint64_t N,
+                                void *d_positions, uint64_t *n_large);
+/* NIFS round 0 on the i64 layers: prove_helper_small (neutronnova_zk.rs:255-325: i64 differences, i128 product,
+ * SmallAccumulator small_value.rs:96-196, reduce_7_to_field :204-222, field correction at the large positions) per
+ * pair, suffix weights, summed over pairs (:781-810).  out2 = (0, quad_coeff).                                       */
+int32_t sp2_nifs_round0_small_dev(sp2_ctx *ctx, const uint64_t *rhos, uint32_t ell_b, uint32_t left, uint32_t right, const void *dE, const void *dA64,
+                                  const void *dB64, const void *dA, const void *dB, const void *d_positions, uint64_t n_large, uint64_t N, uint64_t m,
+                                  uint64_t *out2);
+/* c_vals[b] = sum_k E[k] * Cz_b[k] from the i64 C layers (neutronnova_zk.rs:649-693), n scalars to the host           */
+int32_t sp2_nifs_cvals_small_dev(sp2_ctx *ctx, uint32_t left, uint32_t right, const void *dE, const void *dC, const void *dC64, const void *d_positions,
+                                 uint64_t n_large, uint64_t N, uint64_t n, uint64_t *out_vals);
+
 /* ---- fused NeutronNova hot path (BASELINE configs 3 / 5) ----------------------------------------------------------
  * NeutronNovaZkSNARK::{prep_prove, prove} (src/neutronnova_zk.rs:1477-1603, 1609-2093), data path: the per-step
  * Az/Bz/Cz of prep_prove, then HOT LOOP A (NeutronNovaNIFS::prove :511-1273 + R1CSWitness::fold_multiple,

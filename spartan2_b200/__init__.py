@@ -10,4 +10,4 @@ Field elements are numpy uint64 arrays of shape (n, 4): little-endian 64-bit lim
 from ._lib import SpartanError, TranscriptState, lib, LIB_PATH  # noqa: F401
 from .host import (Comm, CommitmentKey, Context, Keccak256Transcript, NeutronNovaNIFS, PowPolynomial, R1CSWitness, SumcheckRounds,
                    fold_commitments, weights_from_r, DeviceBuffer, DlogGroupExt, EqPolynomial, HyraxPCS, MultilinearPolynomial,
-                   SpartanPrepSNARK, SpartanProof, SpartanSNARK, SplitR1CSShape, SumcheckProof, shard_cyclic)  # noqa: F401
+                   SmallValue, SpartanPrepSNARK, SpartanProof, SpartanSNARK, SplitR1CSShape, SumcheckProof, shard_cyclic)  # noqa: F401

@@ -409,6 +409,11 @@ int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n,
 
 namespace sp2 {
 int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out);
+// small_value.cu
+int nifs_round0_small_enqueue(sp2_ctx *ctx, const fe *d_rhos, u32 ell_b, u32 left, u32 right, const fe *dE, const void *dA64, const void *dB64,
+                              const fe *dA, const fe *dB, const void *d_positions, u64 n_large, u64 N, u64 m, fe *d_partials, fe *d_out);
+int small_layers_enqueue(sp2_ctx *ctx, const fe *const *d_tabs, void *const *d_i64, u32 ntab, u64 n_layers, u64 N, void *d_flags, void *d_positions,
+                         u64 *d_count);
 }
 
 struct sp2_nn_prep {
@@ -423,6 +428,10 @@ struct sp2_nn_prep {
   fe *work[3] = {nullptr, nullptr, nullptr}, *workc[3] = {nullptr, nullptr, nullptr};   // folded / bound in place by prove
   fe *z_step = nullptr, *z_core = nullptr, *abc_s = nullptr, *abc_c = nullptr;          // 2M each
   fe *E = nullptr, *rx = nullptr, *small = nullptr, *partials = nullptr;
+  // small-value layers (prep_prove, neutronnova_zk.rs:1551-1584): i64 copies of the cached step layers with the union of
+  // the large positions zeroed, the ascending list of those positions
+  void *L64[3] = {nullptr, nullptr, nullptr}, *large_pos = nullptr, *large_flags = nullptr;
+  uint64_t n_large = 0; bool has_i64 = false;
   u32 *ticket = nullptr;
   // host-mapped mailbox: [0] sequence flag, results at +64 bytes
   unsigned char *h_mail = nullptr; unsigned char *d_mail = nullptr;
@@ -732,6 +741,19 @@ int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *S, uint32_t n_
     if ((rc = spmv3_dev(ctx, S, S->M, P->zs + i * nc, nullptr, o))) return fail(rc);
   }
   { fe *o[3] = {P->Lc[0], P->Lc[1], P->Lc[2]}; if ((rc = spmv3_dev(ctx, S, S->M, P->zc, nullptr, o))) return fail(rc); }
+  { // i64 layers for the small-value NIFS round 0 (SP2_NN_NO_SMALL=1: field path only)
+    const char *e = getenv("SP2_NN_NO_SMALL");
+    if (!(e && e[0] == '1')) {
+      for (int k = 0; k < 3; k++) { void *p; if (cudaMalloc(&p, n * N * 8) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->L64[k] = p; }
+      { void *p; if (cudaMalloc(&p, N * 8 + 64) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->large_pos = p; }
+      { void *p; if (cudaMalloc(&p, N + 64) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->large_flags = p; }
+      const fe *tabs[3] = {P->L[0], P->L[1], P->L[2]};
+      u64 *d_count = (u64 *)((unsigned char *)P->large_pos + N * 8);
+      if ((rc = small_layers_enqueue(ctx, tabs, P->L64, 3, n, N, P->large_flags, P->large_pos, d_count))) return fail(rc);
+      if (cudaMemcpyAsync(&P->n_large, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "neutronnova: prep_prove"));
+      P->has_i64 = true;
+    }
+  }
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "neutronnova: prep_prove failed on the device"));
   *out = P;
   return SP2_OK;
@@ -799,10 +821,18 @@ int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh,
     u32 chunks = std::max<u32>(1, std::min<u32>(right, (u32)(ctx->num_sms * 4) / std::max<u32>(1, pairs)));
     if ((size_t)chunks * pairs > NN_MAX_PARTS) chunks = std::max<u32>(1, (u32)(NN_MAX_PARTS / pairs));
     const u32 threads = std::min<u32>(NF_THREADS, (left + 31) / 32 * 32);
-    k_nifs_round<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(t, d_rhos, ell_b, left, right, P->E, As, Bs, Cs, N, stride, P->partials);
-    SP2_LAUNCH_CHECK();
     const u32 seq = ++P->seq;
-    k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, nn_mail_dev(P), mail_flag, seq, P->ticket);
+    if (t == 0 && P->has_i64) {
+      // round 0 on the i64 layers (prove_helper_small, :255-325): e0 = 0, quad from i64 differences / i128 products
+      SP2_CUDA_OK(cudaMemsetAsync(P->partials, 0, sizeof(fe), ctx->stream));
+      SP2_TRY(nifs_round0_small_enqueue(ctx, d_rhos, ell_b, left, right, P->E, P->L64[0], P->L64[1], As, Bs, P->large_pos, P->n_large, N, m,
+                                        P->partials + 64, P->partials + 1));
+      k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, 1, nn_mail_dev(P), mail_flag, seq, P->ticket);
+    } else {
+      k_nifs_round<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(t, d_rhos, ell_b, left, right, P->E, As, Bs, Cs, N, stride, P->partials);
+      SP2_LAUNCH_CHECK();
+      k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, nn_mail_dev(P), mail_flag, seq, P->ticket);
+    }
     SP2_LAUNCH_CHECK();
     SP2_TRY(nn_wait(P, seq));
     const fe e0 = nn_mail(P)[0], quad = nn_mail(P)[1];

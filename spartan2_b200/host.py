@@ -535,6 +535,36 @@ class NeutronNovaNIFS:
         return tuple(b.download((self.N, 4)) for b in (self.A, self.B, self.C))
 
 
+class SmallValue:
+    """src/big_num/small_value.rs on device-resident layers (i64 tables, SmallAccumulator sums) and the NIFS kernels that
+    consume them (src/neutronnova_zk.rs:255-325, 649-693, 1551-1584)."""
+
+    @staticmethod
+    def to_small_layers(ctx, tables, n_layers, N):
+        """tables: DeviceBuffers of n_layers*N scalars -> (i64 DeviceBuffers, positions DeviceBuffer (u64, ascending), n_large)"""
+        outs = [ctx.alloc(n_layers * N * 8) for _ in tables]
+        pos = ctx.alloc(max(N, 1) * 8)
+        tin = (C.c_void_p * len(tables))(*[t.ptr.value for t in tables]); tout = (C.c_void_p * len(tables))(*[t.ptr.value for t in outs])
+        nl = C.c_uint64()
+        ctx.check(ctx.L.sp2_to_small_layers_dev(ctx.h, tin, tout, C.c_uint32(len(tables)), C.c_uint64(n_layers), C.c_uint64(N), pos.ptr, C.byref(nl)))
+        return outs, pos, int(nl.value)
+
+    @staticmethod
+    def nifs_round0(ctx, rhos, left, right, dE, dA64, dB64, dA, dB, dpos, n_large, N, m):
+        rhos = _fe(rhos); out = np.zeros((2, 4), dtype=np.uint64)
+        rr = rhos if rhos.shape[0] else np.zeros((1, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_nifs_round0_small_dev(ctx.h, _p(rr), C.c_uint32(rhos.shape[0]), C.c_uint32(left), C.c_uint32(right), dE.ptr, dA64.ptr, dB64.ptr,
+                                                  dA.ptr, dB.ptr, dpos.ptr, C.c_uint64(n_large), C.c_uint64(N), C.c_uint64(m), _p(out)))
+        return out
+
+    @staticmethod
+    def cvals(ctx, left, right, dE, dC, dC64, dpos, n_large, N, n):
+        out = np.zeros((n, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_nifs_cvals_small_dev(ctx.h, C.c_uint32(left), C.c_uint32(right), dE.ptr, dC.ptr, dC64.ptr, dpos.ptr, C.c_uint64(n_large),
+                                                 C.c_uint64(N), C.c_uint64(n), _p(out)))
+        return out
+
+
 def weights_from_r(ctx, r_bs, n):
     r_bs = _fe(r_bs); out = np.zeros((n, 4), dtype=np.uint64)
     ctx.check(ctx.L.sp2_weights_from_r(ctx.h, _p(r_bs), C.c_uint32(r_bs.shape[0]), C.c_uint32(n), _p(out)))

@@ -33,6 +33,9 @@ print("CUDA  (B200, per-round seams, %d launches): total %.2f ms; %s" % (best[2]
 # the fused path of the library: round loop + scalar algebra + transcript in C++, tables device-resident
 t0 = time.perf_counter()
 prover = nn.NeutronNovaProver(ctx, S, zs, zc)
+prover.free()                                   # first call pays the lazy module load of its kernels; time the second
+t0 = time.perf_counter()
+prover = nn.NeutronNovaProver(ctx, S, zs, zc)
 prep_ms = (time.perf_counter() - t0) * 1e3
 bestf = None
 for it in range(6):
@@ -44,7 +47,7 @@ for it in range(6):
         bestf = (wall, ph, ctx.launch_count() - l0)
 from spartan2_b200 import _fq as fq  # noqa: E402
 assert fq.to_int(v["T_out"]) == out["T_out"] and fq.to_ints(v["eval_W"]) == [out["eval_W_step"], out["eval_W_core"]]
-print("CUDA  (B200, fused sp2_neutronnova_prove, %d launches): prove %.3f ms (prep_prove incl. upload + %d SpMVs: %.2f ms); %s"
+print("CUDA  (B200, fused sp2_neutronnova_prove, %d launches): prove %.3f ms (prep_prove incl. upload, %d SpMVs, i64 layers: %.2f ms); %s"
       % (bestf[2], bestf[0], n + 1, prep_ms, {k: round(x, 3) for k, x in bestf[1].items()}), flush=True)
 if "--no-cpu" not in sys.argv:
     from oracle import pyoracle as orc

@@ -112,6 +112,15 @@ class Workload:
         # Hyrax bind M; incremental SpMV: general nnz of the filtered columns (bounded by nnz_general; counted as 0)
         self.field_ops = 7 * N + N + 2 * N + self.nnz_general + 7 * M + M
         self.bytes_outer = 368 * N
+        # the persistent kernel k_cubic_persist runs rounds 1..R-1 of the outer sum-check (tables > 4096 entries going in,
+        # sumcheck.cu: sumcheck_cubic_enqueue): round 1 reads 2.5 tables, round i >= 2 reads 3 * T/2^(i-2) entries and
+        # writes half as many (bind fused into the evaluation)  — SURVEY.md §8(d) accounting, 32 B per entry
+        l = N.bit_length() - 1
+        r_end = 1
+        while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > 4096:
+            r_end += 1
+        self.persist_rounds = r_end - 1
+        self.bytes_persist = (80 * N if r_end > 1 else 0) + sum(144 * (N >> (i - 2)) for i in range(2, r_end))
 
     def describe(self):
         c = self.circ
@@ -180,10 +189,14 @@ def run_cuda(args):
     l0 = ctx.launch_count()
     sampler = ClockSampler(local); sampler.start()
     barrier()
-    dev, wall, phases = [], [], []
+    import ctypes as C
+    dev, wall, phases, persist = [], [], [], []
     for _ in range(args.steps):
         proof, w = step()
         dev.append(proof.phase_ms["total"]); wall.append(w); phases.append(proof.phase_ms)
+        ms = C.c_float()
+        if not sharded and ctx.L.sp2_last_cubic_persist_ms(ctx.h, C.byref(ms)) == 0:
+            persist.append(float(ms.value))
     barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count() - l0
@@ -195,7 +208,18 @@ def run_cuda(args):
         ms_dev, ms_wall = float(t[0]), float(t[1])
     if rank == 0:
         ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
-        ach = wl.bytes_outer / (ph["outer_sumcheck"] * 1e-3) / 1e9
+        ach_phase = wl.bytes_outer / (ph["outer_sumcheck"] * 1e-3) / 1e9
+        traffic = ncu_traffic("k_cubic_persist")
+        if persist:
+            k_ms = float(np.mean(persist))
+            roof = {"bound": "hbm", "kernel": "k_cubic_persist (rounds 1-%d of the outer sum-check, bind fused into the next evaluation, one cooperative launch)" % wl.persist_rounds,
+                    "achieved": wl.bytes_persist / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": traffic, "peak_kind": peak_kind,
+                    "ms": k_ms, "algorithmic_bytes": wl.bytes_persist, "share_of_step": k_ms / ms_dev,
+                    "note": "latency-bound at N = 2^20: %d rounds, each ending in a grid barrier + serial Keccak finaliser (~17 us) vs ~%.0f us of compulsory streaming; see tables_bench for the same kernel on 2^24-entry tables" % (wl.persist_rounds, wl.bytes_persist / hbm_peak / 1e3)}
+        else:
+            roof = {"bound": "hbm", "kernel": "outer sum-check (all %d rounds)" % proof.l, "achieved": ach_phase, "peak": hbm_peak, "unit": "GB/s",
+                    "traffic": None, "peak_kind": peak_kind, "ms": ph["outer_sumcheck"], "algorithmic_bytes": wl.bytes_outer}
+        roof["frac"] = roof["achieved"] / hbm_peak
         cfg = wl.describe()
         par = "single GPU" if world == 1 else ("one proof, hypercube sharded across %d GPUs (rows/columns i mod %d; per-round sums exchanged in-kernel over NVLink)" % (world, world)
                                                if sharded else "1 proof per GPU (replicas)")
@@ -209,11 +233,14 @@ def run_cuda(args):
                     "h2d_bytes_per_step": int(wl.X.nbytes + wl.d_vec.nbytes + wl.blinds.nbytes + 16 * 32 + 64 * 21),
                     "d2h_bytes_per_step": int(sum(getattr(proof, f).nbytes for f in sp.SpartanProof.FIELDS))},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_cubic_round/k_cubic_tail (outer sum-check, all %d rounds)" % proof.l, "achieved": ach, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                         "ms": ph["outer_sumcheck"], "algorithmic_bytes": wl.bytes_outer},
+            "roofline": roof,
+            "roofline_phase": {"phase": "outer_sumcheck (k_cubic_init + k_cubic_persist + k_cubic_tail, all %d rounds)" % proof.l, "achieved": ach_phase, "unit": "GB/s",
+                               "frac": ach_phase / hbm_peak, "ms": ph["outer_sumcheck"], "algorithmic_bytes": wl.bytes_outer},
             "phase_ms": ph, "prove_ms": ms_dev, "clocks": clocks,
         }
+        if world == 1 and not args.no_extras:
+            out["tables_bench"] = tables_bench(ctx, sp, hbm_peak)
+            out["neutronnova"] = neutronnova_bench(ctx, sp)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_prove(wl, pts, threads=1, steps=1, warmup=0)
         print(json.dumps(out), flush=True)
@@ -223,6 +250,91 @@ def run_cuda(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the capture named in it); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(p))[kernel]["dram_bytes"])
+    except Exception:
+        return None
+
+
+def tables_bench(ctx, sp, hbm_peak, num_vars=24):
+    """The reference's pure-table sum-check benchmark (src/sumcheck.rs:1450-1553) at num_vars = 24 on device-resident
+    tables: the SAME kernels as the prove, at a size where streaming rather than per-round latency dominates."""
+    import ctypes as C
+    rng = np.random.default_rng(0xDEADBEEF)
+    n = 1 << num_vars; chunk = 1 << 20
+    host = [rand_fe(rng, chunk) for _ in range(3)]
+    tabs = [ctx.alloc(n * 32) for _ in range(3)]
+    small = [ctx.upload(h) for h in host]
+
+    def fill():
+        for t, sbuf in zip(tabs, small):
+            for i in range(n // chunk):
+                ctx.check(ctx.L.sp2_dev_copy(ctx.h, C.c_void_p(t.ptr.value + i * chunk * 32), sbuf.ptr, C.c_uint64(chunk * 32)))
+    taus = rand_fe(rng, num_vars); zero = np.zeros((1, 4), dtype=np.uint64)
+    tot, per = [], []
+    for it in range(4):
+        fill()
+        ctx.synchronize()
+        ts = sp.TranscriptState()
+        ctx.timer_start()
+        sp.SumcheckProof.prove_cubic_with_three_inputs(ctx, zero, taus, tabs[0], tabs[1], tabs[2], ts)
+        ms = ctx.timer_stop()
+        k = C.c_float(); ctx.check(ctx.L.sp2_last_cubic_persist_ms(ctx.h, C.byref(k)))
+        if it:
+            tot.append(ms); per.append(float(k.value))
+    for t in tabs + small:
+        t.free()
+    l = num_vars; r_end = 1
+    while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > 4096:
+        r_end += 1
+    b_persist = 80 * n + sum(144 * (n >> (i - 2)) for i in range(2, r_end))
+    k_ms, t_ms = float(np.mean(per)), float(np.mean(tot))
+    return {"workload": "prove_cubic_with_three_inputs, 3 uniform random tables of 2^%d entries, device-resident (1.5 GiB > L2)" % num_vars,
+            "kernel": "k_cubic_persist (rounds 1-%d)" % (r_end - 1), "ms": k_ms, "algorithmic_bytes": b_persist,
+            "achieved": b_persist / (k_ms * 1e-3) / 1e9, "unit": "GB/s", "frac": b_persist / (k_ms * 1e-3) / 1e9 / hbm_peak,
+            "sumcheck_total_ms": t_ms, "field_ops_per_sec": 7 * n / (t_ms * 1e-3)}
+
+
+def neutronnova_bench(ctx, sp, n=32):
+    """BASELINE config 3: sha256_neutronnova, 32 step circuits (2048 B total) — HOT LOOPS A-C through the fused path of the
+    library (sp2_neutronnova_prep_prove / sp2_neutronnova_prove), wall clock of the C-ABI call."""
+    from spartan2_b200 import neutronnova as nn
+    from spartan2_b200.frontend import Sha256Circuit
+    from spartan2_b200 import _fq as fq
+    one = fq.from_int(1)
+    circs = [Sha256Circuit(bytes([i % 256]) * 64, kind="compression") for i in range(n)] + [Sha256Circuit(bytes(64), kind="compression")]
+    zs = []
+    for c in circs:
+        W, X = c.witness(); zs.append(np.concatenate([W, one, X], axis=0))
+    c0 = circs[0]
+    A, B, Cm = c0.matrices()
+    S = sp.SplitR1CSShape(ctx, *c0.dims(), A, B, Cm)
+    t0 = time.perf_counter()
+    prover = nn.NeutronNovaProver(ctx, S, zs[:n], zs[n])
+    prep_ms = (time.perf_counter() - t0) * 1e3
+    walls, phs = [], []
+    l0 = None
+    for it in range(8):
+        if it == 3:
+            l0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        v, ph = prover.prove(sp.Keccak256Transcript(b"neutronnova_prove"))
+        if it >= 3:
+            walls.append((time.perf_counter() - t0) * 1e3); phs.append(ph)
+        assert v["outer_ok"] and v["inner_ok"]
+    launches = (ctx.launch_count() - l0) // 5
+    prover.free(); S.free()
+    N = c0.num_cons; M = c0.num_vars
+    # field-ops (SURVEY §8d): NIFS ~3 n N (+ folds 3 n N), witness fold n M, pow-cubic 2 branches 12 N, ABC 2 x (2N + general nnz), inner 2 x 4 (2M)
+    return {"workload": "sha256_neutronnova_%d_steps (N = M = 2^%d per instance)" % (n, N.bit_length() - 1), "prove_ms": float(np.mean(walls)),
+            "phase_ms": {k: float(np.mean([p[k] for p in phs])) for k in phs[0]}, "prep_prove_ms_untimed": prep_ms, "gpu_launches": int(launches),
+            "challenges": "transcript-derived (non-ZK); the reference's in-circuit verifier (process_round) is out of scope"}
 
 
 def cpu_prove(wl, pts, threads, steps, warmup):
@@ -285,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--msg-len", type=int, default=2048, help="SHA-256 message bytes (BASELINE config 2: 2048; config 1: 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 2^24 pure-table sum-check leg and the config-3 NeutronNova leg (N = 1 only)")
     ap.add_argument("--sharded", action="store_true", help="N > 1: one proof with its hypercube sharded across the GPUs (strong scaling) instead of one proof per GPU")
     args = ap.parse_args()
     if args.impl == "reference":

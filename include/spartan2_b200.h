@@ -307,6 +307,10 @@ int32_t sp2_transcript_dom_sep(sp2_transcript *t, const char *label);
 int32_t sp2_transcript_squeeze(sp2_transcript *t, const char *label, uint64_t *out_scalar);
 int32_t sp2_transcript_get_state(const sp2_transcript *t, sp2_transcript_state *out);
 
+/* measurement hook: duration in ms (CUDA events on the library's stream) of the most recent persistent cubic
+ * sum-check kernel (all multi-CTA rounds of prove_cubic_with_three_inputs in one launch)                              */
+int32_t sp2_last_cubic_persist_ms(sp2_ctx *ctx, float *ms);
+
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);
 int32_t sp2_dev_free(sp2_ctx *ctx, void *p);

@@ -26,7 +26,7 @@ int32_t sp2_ctx_create(int32_t device, sp2_ctx **out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SP2_ERR_CUDA; }
   ctx->own_stream = true;
   cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
-  cudaEventCreate(&ctx->ev_a); cudaEventCreate(&ctx->ev_b);
+  cudaEventCreate(&ctx->ev_a); cudaEventCreate(&ctx->ev_b); cudaEventCreate(&ctx->ev_k0); cudaEventCreate(&ctx->ev_k1);
   cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming);
   *out = ctx;
   return SP2_OK;
@@ -42,6 +42,8 @@ void sp2_ctx_destroy(sp2_ctx *ctx) {
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
   delete ctx;
 }
@@ -75,6 +77,15 @@ int32_t sp2_timer_stop(sp2_ctx *ctx, float *ms) {
   return SP2_OK;
 }
 
+/* duration (CUDA events on the library's stream) of the most recent persistent cubic sum-check kernel k_cubic_persist —
+ * the largest single kernel of a prove; the caller must have synchronised the stream */
+int32_t sp2_last_cubic_persist_ms(sp2_ctx *ctx, float *ms) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->ev_k_valid) return set_error(ctx, SP2_ERR_INTERNAL, "no persistent cubic kernel has run");
+  SP2_CUDA_OK(cudaEventSynchronize(ctx->ev_k1));
+  SP2_CUDA_OK(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+  return SP2_OK;
+}
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out) {
   cudaSetDevice(ctx->device);
   SP2_CUDA_OK(cudaMalloc(out, bytes ? bytes : 32));

@@ -15,6 +15,8 @@ struct sp2_ctx {
   bool own_stream = false;
   cudaStream_t side = nullptr;          // side stream for independent prologue work
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the last persistent cubic sum-check kernel (bench.py: roofline of the dominant kernel)
+  bool ev_k_valid = false;
   int num_sms = 148;
   std::string err;
   uint64_t launches = 0;                // kernels launched through this context (bench's gpu_launches)

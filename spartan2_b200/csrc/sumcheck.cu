@@ -892,7 +892,10 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     if (round_end > 1) {
       PersistCubic pa{st, A, B, C, dst[0], dst[1], dst[2], (int)l, 1, (int)round_end, eq_left, eq_right};
       void *args[] = {&pa};
+      SP2_CUDA_OK(cudaEventRecord(ctx->ev_k0, ctx->stream));
       SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_cubic_persist, dim3(ctx->num_sms * SC_PERSIST_MINB), dim3(SC_THREADS), args, 0, ctx->stream));
+      SP2_CUDA_OK(cudaEventRecord(ctx->ev_k1, ctx->stream));
+      ctx->ev_k_valid = true;
       ctx->launches++;
       for (uint32_t rr = 2; rr < round_end; rr++)              // fused role rounds ping-pong src <-> dst
         if ((4ull << (l - rr)) <= SC_ROLE_LEN) for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);

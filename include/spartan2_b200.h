@@ -294,6 +294,18 @@ int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *shape, uint32_
  * inner_sumcheck_batched, total (host wall clock; every phase ends in a host wait)                                  */
 int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *prep, sp2_transcript *ts, sp2_nn_proof *proof, float *phase_ms);
 void sp2_neutronnova_prep_free(sp2_nn_prep *prep);
+/* Multi-GPU NeutronNova (one process per GPU): the step instances are the independent units — rank g of
+ * nranks (a power of two) holds n_local instances [g * n_local, (g+1) * n_local); the NIFS rounds fold adjacent pairs
+ * locally for log2(n_local) rounds (per round the two sums cross ranks inside the publish kernel through `comm`'s peer
+ * mailboxes — sp2_comm_create/_handle/_connect; comm = NULL: one 64-byte host all-gather per round), then the surviving
+ * layer triples are all-gathered and the remaining log2(nranks) rounds, the sum-checks and poly_ABC run replicated;
+ * the witness fold is a local partial + all-gather + sum.  `allgather` is the host's collective (recv = contributions in
+ * rank order; on_device = 1: both pointers are device memory, complete on return).  Every rank gets the identical proof. */
+typedef int32_t (*sp2_allgather_fn)(void *user, const void *send, uint64_t bytes, void *recv, int32_t on_device);
+int32_t sp2_neutronnova_prep_prove_sharded(sp2_ctx *ctx, const sp2_shape *shape, int32_t rank, int32_t nranks, uint32_t n_local,
+                                           const uint64_t *local_step_zs, const uint64_t *core_z, sp2_nn_prep **out);
+int32_t sp2_neutronnova_prove_sharded(sp2_ctx *ctx, sp2_nn_prep *prep, sp2_transcript *ts, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
+                                      sp2_nn_proof *proof, float *phase_ms);
 
 /* ---- host Keccak256Transcript (src/provider/keccak.rs:18-105 behind TranscriptEngineTrait, src/traits/transcript.rs) ----
  * Host-side Fiat-Shamir for drivers that interleave per-round device calls with transcript steps (a Rust caller keeps

@@ -1061,13 +1061,21 @@ static void nifs_prove_helper(size_t round, size_t left, size_t right, const fe 
 }
 /* one NIFS round evaluation over m live layers (standard field path, neutronnova_zk.rs:809-833 / fallback branches):
  * layers are stored layer-major (layer q at offset q*N); returns (e0, quad_coeff) = sum_p w_p * prove_helper(pair p) */
+/* pair_offset: index of the first pair among ALL live pairs when A, B, Cm hold only a contiguous block of the layers (the
+ * multi-GPU instance sharding of SURVEY.md §8e; 0 for the whole set) */
+EXPORT void orc_nifs_round_block(size_t t, size_t ell_b, const fe *rhos, size_t left, size_t right, const fe *E, const fe *A, const fe *B,
+                                 const fe *Cm, size_t N, size_t m, size_t pair_offset, fe *out2);
 EXPORT void orc_nifs_round(size_t t, size_t ell_b, const fe *rhos, size_t left, size_t right, const fe *E, const fe *A, const fe *B,
                            const fe *Cm, size_t N, size_t m, fe *out2) {
+  orc_nifs_round_block(t, ell_b, rhos, left, right, E, A, B, Cm, N, m, 0, out2);
+}
+EXPORT void orc_nifs_round_block(size_t t, size_t ell_b, const fe *rhos, size_t left, size_t right, const fe *E, const fe *A, const fe *B,
+                                 const fe *Cm, size_t N, size_t m, size_t pair_offset, fe *out2) {
   fe e0, q; f_zero(&e0); f_zero(&q);
   for (size_t p = 0; p < m / 2; p++) {
     fe pe, pq, w, tmp;
     nifs_prove_helper(t, left, right, E, A + 2 * p * N, B + 2 * p * N, Cm + 2 * p * N, A + (2 * p + 1) * N, B + (2 * p + 1) * N, &pe, &pq);
-    suffix_weight_full(t, ell_b, p, rhos, &w);
+    suffix_weight_full(t, ell_b, p + pair_offset, rhos, &w);
     f_mul(&FQ, &tmp, &pe, &w); f_add(&FQ, &e0, &e0, &tmp);
     f_mul(&FQ, &tmp, &pq, &w); f_add(&FQ, &q, &q, &tmp);
   }

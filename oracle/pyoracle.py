@@ -432,12 +432,13 @@ def pow_split_evals(t, left, right):
     return out
 
 
-def nifs_round(t, rhos, left, right, E, A, B, Cm, N, m):
+def nifs_round(t, rhos, left, right, E, A, B, Cm, N, m, pair_offset=0):
+    """pair_offset: first GLOBAL pair index when A, B, Cm are one rank's contiguous block of the live layers"""
     rhos = np.ascontiguousarray(rhos, dtype=np.uint64).reshape(-1, 4)
     E, A, B, Cm = (np.ascontiguousarray(x, dtype=np.uint64) for x in (E, A, B, Cm))
     out = fe_array(2)
-    lib().orc_nifs_round(C.c_size_t(t), C.c_size_t(rhos.shape[0]), _p(rhos), C.c_size_t(left), C.c_size_t(right), _p(E), _p(A), _p(B), _p(Cm),
-                         C.c_size_t(N), C.c_size_t(m), _p(out))
+    lib().orc_nifs_round_block(C.c_size_t(t), C.c_size_t(rhos.shape[0]), _p(rhos), C.c_size_t(left), C.c_size_t(right), _p(E), _p(A), _p(B), _p(Cm),
+                               C.c_size_t(N), C.c_size_t(m), C.c_size_t(pair_offset), _p(out))
     return out
 
 

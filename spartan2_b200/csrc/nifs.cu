@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(NF_THREADS) k_reduce_partials(const fe *partia
 // One NIFS round: grid (i-chunks, pairs); thread owns j (the contiguous index), walks its i-chunk:
 //   acc += f[i] * v(i, j), then * e_left[j]   (prove_helper's nested sums with inner/outer swapped: one flush per thread)
 __global__ void __launch_bounds__(NF_THREADS) k_nifs_round(u32 t, const fe *rhos, u32 ell_b, u32 left, u32 right, const fe *E, const fe *A,
-                                                           const fe *B, const fe *C, u64 N, u64 stride, fe *partials) {
+                                                           const fe *B, const fe *C, u64 N, u64 stride, fe *partials, u32 pair_offset = 0) {
   __shared__ fe red[2 * 32];
   __shared__ fe wsh;
   const u32 p = blockIdx.y;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(NF_THREADS) k_nifs_round(u32 t, const fe *rhos
   const fe *B1 = B + (u64)(2 * p) * stride * N, *B2 = B + (u64)(2 * p + 1) * stride * N;
   const fe *C1 = C + (u64)(2 * p) * stride * N;
   if (threadIdx.x == 0) {                       // suffix_weight_full(t, ell_b, p, rhos)
-    fe w = Fq::one(); u32 k = p;
+    fe w = Fq::one(); u32 k = p + pair_offset;        // pair_offset: a multi-GPU shard's first GLOBAL pair index
     for (u32 s = t + 1; s < ell_b; s++) { const fe r = ldg_fe(rhos + s); w = Fq::mul(w, (k & 1u) ? r : Fq::sub(Fq::one(), r)); k >>= 1; }
     wsh = w;
   }
@@ -406,12 +406,14 @@ int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n,
 #include <atomic>
 #include <chrono>
 #include "r1cs.cuh"
+#include "sumcheck.cuh"
 
 namespace sp2 {
 int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out);
 // small_value.cu
 int nifs_round0_small_enqueue(sp2_ctx *ctx, const fe *d_rhos, u32 ell_b, u32 left, u32 right, const fe *dE, const void *dA64, const void *dB64,
-                              const fe *dA, const fe *dB, const void *d_positions, u64 n_large, u64 N, u64 m, fe *d_partials, fe *d_out);
+                              const fe *dA, const fe *dB, const void *d_positions, u64 n_large, u64 N, u64 m, fe *d_partials, fe *d_out,
+                              u32 pair_offset = 0);
 int small_layers_enqueue(sp2_ctx *ctx, const fe *const *d_tabs, void *const *d_i64, u32 ntab, u64 n_layers, u64 N, void *d_flags, void *d_positions,
                          u64 *d_count);
 }
@@ -419,7 +421,11 @@ int small_layers_enqueue(sp2_ctx *ctx, const fe *const *d_tabs, void *const *d_i
 struct sp2_nn_prep {
   sp2_ctx *ctx = nullptr;
   const sp2_shape *S = nullptr;
-  uint32_t n = 0, ell_b = 0, ell = 0, left = 0, right = 0;
+  uint32_t n = 0, ell_b = 0, ell = 0, left = 0, right = 0;   // n: instances held by THIS rank; ell_b = log2 of the global count
+  // multi-GPU: rank g of G owns the step instances [g*n, (g+1)*n) of n_total = G*n; the core instance is replicated
+  int rank = 0, nranks = 1; uint32_t n_total = 0;
+  fe *gath = nullptr;                        // nranks x 3 x N: the surviving (A, B, C) layers of all ranks
+  fe *wpart = nullptr;                       // nranks x M: per-rank partial witness folds
   uint64_t N = 0, M = 0, ncols = 0;
   fe *zs = nullptr, *zc = nullptr;           // n x ncols, ncols
   fe *Ws = nullptr;                          // n x M (contiguous copies of the witness sections)
@@ -474,6 +480,51 @@ __global__ void __launch_bounds__(NF_THREADS) k_publish(const fe *partials, u32 
     __threadfence_system();
     const u32 t = atomicAdd(ticket, 1u);
     if (t == gridDim.x - 1) { *ticket = 0; __threadfence_system(); *(volatile u32 *)mail_flag = seq; }
+  }
+}
+// Multi-GPU variant of k_publish<2>: this rank's two round sums go straight into every peer's mailbox (CUDA-IPC mapped
+// device memory, plain stores over NVLink + system fence + epoch flag — the exchange of sumcheck.cu: exchange_sums), the
+// kernel waits for the peers' contributions, adds, and publishes the GLOBAL sums to the host: no host collective per
+// NIFS round.  The wait is bounded (2 s of %globaltimer): a missing peer surfaces as a host-side timeout, not a hang.
+__global__ void __launch_bounds__(NF_THREADS) k_publish_xchg(const fe *partials, u32 nparts, DevComm dc, int slot, fe *mail_out, u32 *mail_flag, u32 seq) {
+  __shared__ fe red[2 * 32];
+  __shared__ fe g[2];
+  __shared__ int bad;
+  fe x[2] = {Fq::zero(), Fq::zero()};
+  for (u32 b = threadIdx.x; b < nparts; b += blockDim.x) { x[0] = Fq::add(x[0], ldg_fe(partials + (size_t)b * 2)); x[1] = Fq::add(x[1], ldg_fe(partials + (size_t)b * 2 + 1)); }
+  block_sum_fq<2>(x, red);
+  if (threadIdx.x == 0) { g[0] = x[0]; g[1] = x[1]; bad = 0; }
+  __syncthreads();
+  if (threadIdx.x < (u32)dc.n) {
+    MailBox *mb = dc.peer[threadIdx.x];
+    stg_fe(&mb->sums[slot][dc.rank][0], g[0]); stg_fe(&mb->sums[slot][dc.rank][1], g[1]);
+    __threadfence_system();
+    *(volatile u32 *)&mb->flag[slot][dc.rank] = dc.epoch;
+    const MailBox *me = dc.peer[dc.rank];
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (*(volatile const u32 *)&me->flag[slot][threadIdx.x] != dc.epoch) {
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) { bad = 1; break; }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && !bad) {
+    const MailBox *me = dc.peer[dc.rank];
+    for (int k = 0; k < 2; k++) {
+      fe acc = Fq::zero();
+      for (int q = 0; q < dc.n; q++) {
+        fe v; u64 a, b, c, d;
+        asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(&me->sums[slot][q][k]));
+        v.v[0] = (u32)a; v.v[1] = (u32)(a >> 32); v.v[2] = (u32)b; v.v[3] = (u32)(b >> 32);
+        v.v[4] = (u32)c; v.v[5] = (u32)(c >> 32); v.v[6] = (u32)d; v.v[7] = (u32)(d >> 32);
+        acc = Fq::add(acc, v);
+      }
+      stg_fe(mail_out + k, acc);
+    }
+    __threadfence_system();
+    *(volatile u32 *)mail_flag = seq;
   }
 }
 __global__ void k_set_one(fe *p) { if (threadIdx.x == 0) stg_fe(p, Fq::one()); }
@@ -700,16 +751,20 @@ void sp2_neutronnova_prep_free(sp2_nn_prep *P) {
 /* NeutronNovaZkSNARK::prep_prove, data path (src/neutronnova_zk.rs:1477-1603): the n step instances z_i = [W_i | 1 | X_i]
  * (num_cols scalars each, host) and the core instance are uploaded once; Az_i, Bz_i, Cz_i for every step and for the
  * core circuit are computed on the device and cached, layer-major.  n must be a power of two >= 2. */
-int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *S, uint32_t n_steps, const uint64_t *step_zs, const uint64_t *core_z,
-                                   sp2_nn_prep **out) {
+static int32_t nn_prep_impl(sp2_ctx *ctx, const sp2_shape *S, int rank, int nranks, uint32_t n_steps, const uint64_t *step_zs, const uint64_t *core_z,
+                            sp2_nn_prep **out) {
   cudaSetDevice(ctx->device);
   if (!out) return SP2_ERR_INTERNAL;
   *out = nullptr;
-  if (n_steps < 2 || (n_steps & (n_steps - 1))) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "neutronnova: the number of step instances must be a power of two >= 2");
+  if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "neutronnova: ranks must be a power of two");
+  const uint64_t n_total = (uint64_t)n_steps * nranks;
+  if (n_steps < 1 || (n_steps & (n_steps - 1)) || n_total < 2) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "neutronnova: the number of step instances must be a power of two >= 2");
+  if (n_total > 256) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "neutronnova: at most 256 step instances");
   if (S->nranks != 1) return set_error(ctx, SP2_ERR_UNSUPPORTED, "neutronnova: whole shape expected");
   sp2_nn_prep *P = new sp2_nn_prep();
   P->ctx = ctx; P->S = S; P->n = n_steps; P->N = S->num_cons; P->M = S->num_vars; P->ncols = S->num_cols;
-  while ((1u << P->ell_b) < n_steps) P->ell_b++;
+  P->rank = rank; P->nranks = nranks; P->n_total = (uint32_t)n_total;
+  while ((1u << P->ell_b) < n_total) P->ell_b++;
   while ((1ull << P->ell) < P->N) P->ell++;
   P->left = 1u << ((P->ell + 1) / 2); P->right = 1u << (P->ell / 2);          // compute_tensor_decomp (:58-67)
   int rc = SP2_OK;
@@ -723,6 +778,7 @@ int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *S, uint32_t n_
       (rc = nn_alloc(P, (size_t)P->left + P->right, &P->E)) || (rc = nn_alloc(P, N, &P->rx)) || (rc = nn_alloc(P, NN_SMALL_FE, &P->small)) ||
       (rc = nn_alloc(P, NN_MAX_PARTS * 6, &P->partials)))
     return fail(rc);
+  if (nranks > 1 && ((rc = nn_alloc(P, (size_t)nranks * 3 * N, &P->gath)) || (rc = nn_alloc(P, (size_t)nranks * M, &P->wpart)))) return fail(rc);
   { void *p; if (cudaMalloc(&p, 64) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->ticket = (u32 *)p;
     cudaMemsetAsync(p, 0, 64, ctx->stream); }
   if (cudaHostAlloc((void **)&P->h_mail, NN_MAIL_BYTES, cudaHostAllocMapped) != cudaSuccess ||
@@ -743,7 +799,7 @@ int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *S, uint32_t n_
   { fe *o[3] = {P->Lc[0], P->Lc[1], P->Lc[2]}; if ((rc = spmv3_dev(ctx, S, S->M, P->zc, nullptr, o))) return fail(rc); }
   { // i64 layers for the small-value NIFS round 0 (SP2_NN_NO_SMALL=1: field path only)
     const char *e = getenv("SP2_NN_NO_SMALL");
-    if (!(e && e[0] == '1')) {
+    if (!(e && e[0] == '1') && n >= 2) {
       for (int k = 0; k < 3; k++) { void *p; if (cudaMalloc(&p, n * N * 8) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->L64[k] = p; }
       { void *p; if (cudaMalloc(&p, N * 8 + 64) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->large_pos = p; }
       { void *p; if (cudaMalloc(&p, N + 64) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->large_flags = p; }
@@ -758,20 +814,37 @@ int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *S, uint32_t n_
   *out = P;
   return SP2_OK;
 }
+int32_t sp2_neutronnova_prep_prove(sp2_ctx *ctx, const sp2_shape *S, uint32_t n_steps, const uint64_t *step_zs, const uint64_t *core_z,
+                                   sp2_nn_prep **out) {
+  return nn_prep_impl(ctx, S, 0, 1, n_steps, step_zs, core_z, out);
+}
+/* Multi-GPU (one process per GPU): rank g of G = nranks holds the n_local step instances [g * n_local, (g+1) * n_local)
+ * of n_local * G in total (instances are the independent units); the core instance is replicated. */
+int32_t sp2_neutronnova_prep_prove_sharded(sp2_ctx *ctx, const sp2_shape *S, int32_t rank, int32_t nranks, uint32_t n_local,
+                                           const uint64_t *local_step_zs, const uint64_t *core_z, sp2_nn_prep **out) {
+  return nn_prep_impl(ctx, S, rank, nranks, n_local, local_step_zs, core_z, out);
+}
 
 /* HOT LOOPS A-C (see the section header).  `ts` is advanced exactly as the Python driver advances its transcript.
  * phase_ms (optional, 6 floats): nifs, fold_witness, outer_sumcheck_batched, compute_eval_table_sparse,
  * inner_sumcheck_batched, total — host wall clock (every phase ends in a host wait). */
-int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_nn_proof *pf, float *phase_ms) {
+static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
+                             sp2_nn_proof *pf, float *phase_ms) {
   cudaSetDevice(ctx->device);
   if (!P || !tsh || !pf) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: null argument");
+  if (P->nranks > 1 && !allgather) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: a sharded prep state needs the all-gather callback");
+  if (comm && (!comm->connected || comm->dc.n != P->nranks || comm->dc.rank != P->rank)) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: comm does not match the prep state");
+  const bool xchg = comm && P->nranks > 1;          // per-round sums exchanged inside the publish kernel over NVLink
+  if (xchg) comm->dc.epoch++;
   sp2h::Transcript &ts = tsh->t;
   const sp2_shape *S = P->S;
   const u32 n = P->n, ell_b = P->ell_b, ell = P->ell, left = P->left, right = P->right;
+  const u32 G = (u32)P->nranks, rank = (u32)P->rank, n_total = P->n_total;
+  u32 ell_local = 0; while ((1u << ell_local) < n) ell_local++;          // NIFS rounds that are local to a rank
   const u64 N = P->N, M = P->M;
   u32 my = 0; while ((1ull << my) < 2 * M) my++;                       // inner rounds: log2(2M)
-  if (N > (1ull << 31) || n > 256 || ell_b > 8 || my > 40 || ell > 40) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "neutronnova_prove: size out of range");
-  pf->n_steps = n; pf->ell_b = ell_b; pf->ell = ell; pf->rounds_y = my; pf->outer_ok = 0; pf->inner_ok = 0;
+  if (N > (1ull << 31) || n_total > 256 || ell_b > 8 || my > 40 || ell > 40) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "neutronnova_prove: size out of range");
+  pf->n_steps = n_total; pf->ell_b = ell_b; pf->ell = ell; pf->rounds_y = my; pf->outer_ok = 0; pf->inner_ok = 0;
   typedef NnHost H;
   const fe one = HF::one(), zero = HF::zero();
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -816,26 +889,51 @@ int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh,
   fe T_cur = zero, acc_eq = one;
   std::vector<fe> r_bs(ell_b);
   u64 m = n, stride = 1;
+  bool gathered = G == 1;
   for (u32 t = 0; t < ell_b; t++) {
+    if (!gathered && t >= ell_local) {
+      // every rank is down to ONE layer triple: all-gather them (rank order = instance order) and finish the last
+      // log2(G) rounds replicated.  recv layout [rank][A|B|C][N]: table k of layer q sits at gath + (3q + k) N, i.e.
+      // layer-major with stride 3 from base gath + k N — exactly what the round / fold kernels take.
+      fe *mine = P->gath + (size_t)rank * 3 * N;
+      for (int k = 0; k < 3; k++) SP2_CUDA_OK(cudaMemcpyAsync(mine + (size_t)k * N, P->work[k], (size_t)N * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+      SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      if (allgather(user, mine, (uint64_t)3 * N * sizeof(fe), P->gath, 1) != 0) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: all-gather of the surviving layers failed");
+      As = P->gath; Bs = P->gath + N; Cs = P->gath + 2 * N;
+      m = G; stride = 3; gathered = true;
+    }
+    const bool local = t < ell_local && G > 1;
     const u32 pairs = (u32)(m / 2);
+    const u32 pair_offset = local ? rank * pairs : 0;
     u32 chunks = std::max<u32>(1, std::min<u32>(right, (u32)(ctx->num_sms * 4) / std::max<u32>(1, pairs)));
     if ((size_t)chunks * pairs > NN_MAX_PARTS) chunks = std::max<u32>(1, (u32)(NN_MAX_PARTS / pairs));
     const u32 threads = std::min<u32>(NF_THREADS, (left + 31) / 32 * 32);
     const u32 seq = ++P->seq;
-    if (t == 0 && P->has_i64) {
+    if (t == 0 && P->has_i64 && ell_local > 0) {
       // round 0 on the i64 layers (prove_helper_small, :255-325): e0 = 0, quad from i64 differences / i128 products
       SP2_CUDA_OK(cudaMemsetAsync(P->partials, 0, sizeof(fe), ctx->stream));
       SP2_TRY(nifs_round0_small_enqueue(ctx, d_rhos, ell_b, left, right, P->E, P->L64[0], P->L64[1], As, Bs, P->large_pos, P->n_large, N, m,
-                                        P->partials + 64, P->partials + 1));
-      k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, 1, nn_mail_dev(P), mail_flag, seq, P->ticket);
+                                        P->partials + 64, P->partials + 1, pair_offset));
+      if (local && xchg) k_publish_xchg<<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, 1, comm->dc, (int)t + 1, nn_mail_dev(P), mail_flag, seq);
+      else k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, 1, nn_mail_dev(P), mail_flag, seq, P->ticket);
     } else {
-      k_nifs_round<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(t, d_rhos, ell_b, left, right, P->E, As, Bs, Cs, N, stride, P->partials);
+      k_nifs_round<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(t, d_rhos, ell_b, left, right, P->E, As, Bs, Cs, N, stride, P->partials, pair_offset);
       SP2_LAUNCH_CHECK();
-      k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, nn_mail_dev(P), mail_flag, seq, P->ticket);
+      if (local && xchg) k_publish_xchg<<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, comm->dc, (int)t + 1, nn_mail_dev(P), mail_flag, seq);
+      else k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, nn_mail_dev(P), mail_flag, seq, P->ticket);
     }
     SP2_LAUNCH_CHECK();
     SP2_TRY(nn_wait(P, seq));
-    const fe e0 = nn_mail(P)[0], quad = nn_mail(P)[1];
+    fe e0 = nn_mail(P)[0], quad = nn_mail(P)[1];
+    if (local && !xchg) {
+      // the round's two sums over ALL ranks' pairs: one 64-byte all-gather + modular adds on the host — every rank then
+      // derives the identical polynomial and challenge
+      fe mine2[2] = {e0, quad};
+      std::vector<fe> all(2 * G);
+      if (allgather(user, mine2, sizeof(mine2), all.data(), 0) != 0) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: all-gather of the round sums failed");
+      e0 = zero; quad = zero;
+      for (u32 g = 0; g < G; g++) { e0 = HF::add(e0, all[2 * g]); quad = HF::add(quad, all[2 * g + 1]); }
+    }
     H::store(pf->nifs_evals + 8 * t, e0); H::store(pf->nifs_evals + 8 * t + 4, quad);
     // finish_round! (neutronnova_zk.rs:703-735)
     const fe rho = rhos[t], omr = HF::sub(one, rho), trm = HF::sub(rho, omr);
@@ -859,19 +957,33 @@ int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh,
   const fe T_out = HF::mul(T_cur, HF::inv(acc_eq));                      // :1206-1208
   H::store(pf->T_out, T_out);
   unsigned char *heads_stage = P->h_stage + NN_STAGE_BYTES - 28 * sizeof(fe);   // parity read-backs, copied out at the end
-  if (pf->heads) for (int k = 0; k < 3; k++)
-    SP2_CUDA_OK(cudaMemcpyAsync(heads_stage + k * 4 * sizeof(fe), P->work[k], 4 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  if (pf->heads) { const fe *fold3[3] = {As, Bs, Cs};
+    for (int k = 0; k < 3; k++) SP2_CUDA_OK(cudaMemcpyAsync(heads_stage + k * 4 * sizeof(fe), fold3[k], 4 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream)); }
   ph[0] = ms_since(t_phase); t_phase = now();
 
   // ---- R1CSWitness::fold_multiple (src/r1cs/mod.rs:570-660) + the z tables of the inner sum-check -----------------
   SP2_TRY(stage(r_bs.data(), ell_b * sizeof(fe), P->small + 64));
-  k_weights_from_r<<<(n + 127) / 128, 128, 0, ctx->stream>>>(P->small + 64, ell_b, n, P->small + 128);
+  k_weights_from_r<<<(n_total + 127) / 128, 128, 0, ctx->stream>>>(P->small + 64, ell_b, n_total, P->small + 128);
   SP2_LAUNCH_CHECK();
   SP2_CUDA_OK(cudaMemsetAsync(P->z_step + M, 0, (size_t)M * sizeof(fe), ctx->stream));
   SP2_CUDA_OK(cudaMemsetAsync(P->z_core + M, 0, (size_t)M * sizeof(fe), ctx->stream));
   { const unsigned nb = (unsigned)std::min<u64>((M + NF_THREADS - 1) / NF_THREADS, (u64)ctx->num_sms * 8);
-    k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->Ws, n, M, P->small + 128, P->z_step);
-    SP2_LAUNCH_CHECK(); }
+    if (G == 1) {
+      k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->Ws, n, M, P->small + 128, P->z_step);
+      SP2_LAUNCH_CHECK();
+    } else {
+      // this rank's part of the weighted sum (its instances' global weights), all-gather of the G partial vectors, sum
+      fe *mine = P->wpart + (size_t)rank * M;
+      k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->Ws, n, M, P->small + 128 + (size_t)rank * n, mine);
+      SP2_LAUNCH_CHECK();
+      SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      if (allgather(user, mine, (uint64_t)M * sizeof(fe), P->wpart, 1) != 0) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: all-gather of the witness partials failed");
+      std::vector<fe> ones(G, one);
+      SP2_TRY(stage(ones.data(), G * sizeof(fe), P->small + 700));
+      k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->wpart, G, M, P->small + 700, P->z_step);
+      SP2_LAUNCH_CHECK();
+    }
+  }
   SP2_CUDA_OK(cudaMemcpyAsync(P->z_core, P->zc, (size_t)M * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
   k_set_one<<<1, 32, 0, ctx->stream>>>(P->z_step + M); SP2_LAUNCH_CHECK();
   k_set_one<<<1, 32, 0, ctx->stream>>>(P->z_core + M); SP2_LAUNCH_CHECK();
@@ -989,6 +1101,20 @@ int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh,
   ph[5] = ms_since(t_begin);
   if (phase_ms) memcpy(phase_ms, ph, sizeof(ph));
   return SP2_OK;
+}
+int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_nn_proof *pf, float *phase_ms) {
+  return nn_prove_impl(ctx, P, tsh, nullptr, nullptr, nullptr, pf, phase_ms);
+}
+/* Sharded prove: every rank calls with its own prep state and an identical transcript and receives the identical
+ * proof.  `allgather(user, send, bytes, recv, on_device)` is the host's collective (NCCL through torch.distributed in
+ * this repo's harness): recv = the ranks' `bytes`-long contributions in rank order; on_device = 1 when both pointers are
+ * device memory (the library has synchronised its stream before the call and expects the data to be complete on
+ * return).  Per prove: one device gather of the surviving layer triples (3 N scalars per rank) and one of the witness
+ * partials (M scalars per rank); the two sums of every local NIFS round cross ranks INSIDE the publish kernel through
+ * `comm`'s peer mailboxes (NVLink stores), or, when comm is NULL, through a 64-byte host gather per round. */
+int32_t sp2_neutronnova_prove_sharded(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
+                                      sp2_nn_proof *pf, float *phase_ms) {
+  return nn_prove_impl(ctx, P, tsh, comm, allgather, user, pf, phase_ms);
 }
 
 }  // extern "C"

@@ -108,20 +108,20 @@ __global__ void __launch_bounds__(1024) k_compact_flags(const unsigned char *fla
   for (u64 k = s; k < e; k++) if (flags[k]) positions[o++] = k;
 }
 
-__device__ __forceinline__ fe suffix_weight0(u32 ell_b, u32 p, const fe *rhos) {      // suffix_weight_full(0, ell_b, p, rhos)
+__device__ __forceinline__ fe suffix_weight0(u32 ell_b, u32 p, const fe *rhos) {      // suffix_weight_full(0, ell_b, p, rhos); p: GLOBAL pair index
   fe w = Fq::one(); u32 k = p;
   for (u32 s = 1; s < ell_b; s++) { const fe r = ldg_fe(rhos + s); w = Fq::mul(w, (k & 1u) ? r : Fq::sub(Fq::one(), r)); k >>= 1; }
   return w;
 }
 // round 0 of the NIFS on i64 layers: grid (i-chunks, pairs); partial[pair * chunks + chunk] = w_pair * sum
 __global__ void __launch_bounds__(SV_THREADS) k_nifs_round0_small(u32 ell_b, const fe *rhos, u32 left, u32 right, const fe *E, const i64 *A64,
-                                                                  const i64 *B64, u64 N, fe *partials) {
+                                                                  const i64 *B64, u64 N, fe *partials, u32 pair_offset) {
   __shared__ fe red[32];
   __shared__ fe wsh;
   const u32 p = blockIdx.y;
   const fe *el = E, *f = E + left;
   const i64 *a1 = A64 + (u64)(2 * p) * N, *a2 = a1 + N, *b1 = B64 + (u64)(2 * p) * N, *b2 = b1 + N;
-  if (threadIdx.x == 0) wsh = suffix_weight0(ell_b, p, rhos);
+  if (threadIdx.x == 0) wsh = suffix_weight0(ell_b, p + pair_offset, rhos);
   fe x[1] = {Fq::zero()};
   const u32 per = (right + gridDim.x - 1) / gridDim.x, i0 = blockIdx.x * per, i1 = min(right, i0 + per);
   for (u32 j = threadIdx.x; j < left; j += blockDim.x) {
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_nifs_round0_small(u32 ell_b, con
 }
 // field correction at the zeroed positions: one CTA per pair
 __global__ void __launch_bounds__(SV_THREADS) k_nifs_round0_fix(u32 ell_b, const fe *rhos, u32 left, u32 right, const fe *E, const fe *A, const fe *B,
-                                                                const u64 *positions, u64 n_large, u64 N, fe *partials) {
+                                                                const u64 *positions, u64 n_large, u64 N, fe *partials, u32 pair_offset) {
   __shared__ fe red[32];
   const u32 p = blockIdx.x;
   const fe *el = E, *f = E + left;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_nifs_round0_fix(u32 ell_b, const
   }
   block_sum_fq<1>(x, red);
   __syncthreads();
-  if (threadIdx.x == 0) stg_fe(partials + p, Fq::mul(x[0], suffix_weight0(ell_b, p, rhos)));
+  if (threadIdx.x == 0) stg_fe(partials + p, Fq::mul(x[0], suffix_weight0(ell_b, p + pair_offset, rhos)));
 }
 // c_vals[b] = sum_k E[k] * Cz_b[k]: one CTA per instance
 __global__ void __launch_bounds__(SV_THREADS) k_nifs_cvals_small(u32 left, u32 right, const fe *E, const fe *Cl, const i64 *C64, const u64 *positions,
@@ -189,15 +189,15 @@ __global__ void __launch_bounds__(SV_THREADS) k_sum_partials1(const fe *partials
 namespace sp2 {
 // quad coefficient of NIFS round 0 from the i64 layers -> *d_out (device); positions may be null when n_large == 0
 int nifs_round0_small_enqueue(sp2_ctx *ctx, const fe *d_rhos, u32 ell_b, u32 left, u32 right, const fe *dE, const void *dA64, const void *dB64,
-                              const fe *dA, const fe *dB, const void *d_positions, u64 n_large, u64 N, u64 m, fe *d_partials, fe *d_out) {
+                              const fe *dA, const fe *dB, const void *d_positions, u64 n_large, u64 N, u64 m, fe *d_partials, fe *d_out, u32 pair_offset) {
   const u32 pairs = (u32)(m / 2);
   u32 chunks = std::max<u32>(1, std::min<u32>(right, (u32)(ctx->num_sms * 4) / std::max<u32>(1, pairs)));
   const u32 threads = std::min<u32>(SV_THREADS, (left + 31) / 32 * 32);
-  k_nifs_round0_small<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(ell_b, d_rhos, left, right, dE, (const i64 *)dA64, (const i64 *)dB64, N, d_partials);
+  k_nifs_round0_small<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(ell_b, d_rhos, left, right, dE, (const i64 *)dA64, (const i64 *)dB64, N, d_partials, pair_offset);
   SP2_LAUNCH_CHECK();
   u32 nparts = chunks * pairs;
   if (n_large) {
-    k_nifs_round0_fix<<<pairs, SV_THREADS, 0, ctx->stream>>>(ell_b, d_rhos, left, right, dE, dA, dB, (const u64 *)d_positions, n_large, N, d_partials + nparts);
+    k_nifs_round0_fix<<<pairs, SV_THREADS, 0, ctx->stream>>>(ell_b, d_rhos, left, right, dE, dA, dB, (const u64 *)d_positions, n_large, N, d_partials + nparts, pair_offset);
     SP2_LAUNCH_CHECK();
     nparts += pairs;
   }
@@ -255,7 +255,7 @@ int32_t sp2_nifs_round0_small_dev(sp2_ctx *ctx, const uint64_t *rhos, uint32_t e
   SP2_TRY(scratch(ctx, 1, ((size_t)ctx->num_sms * 4 + m + 8) * sizeof(fe), &part));
   fe *d_out = (fe *)part + (size_t)ctx->num_sms * 4 + m;
   SP2_TRY(nifs_round0_small_enqueue(ctx, (const fe *)dr, ell_b, left, right, (const fe *)dE, dA64, dB64, (const fe *)dA, (const fe *)dB, d_positions, n_large,
-                                    N, m, (fe *)part, d_out));
+                                    N, m, (fe *)part, d_out, 0));
   memset(out2, 0, sizeof(fe));
   SP2_CUDA_OK(cudaMemcpyAsync(out2 + 4, d_out, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));

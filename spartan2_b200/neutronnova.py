@@ -272,16 +272,36 @@ class NeutronNovaProver:
 
     PHASES = ("nifs", "fold_witness", "outer_sumcheck_batched", "compute_eval_table_sparse", "inner_sumcheck_batched", "total")
 
-    def __init__(self, ctx, shape, step_zs, core_z):
-        self.ctx, self.S = ctx, shape
+    ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32)
+
+    def __init__(self, ctx, shape, step_zs, core_z, rank=0, nranks=1, allgather=None, comm=None):
+        """step_zs: this rank's instances (all of them on a single GPU).  Multi-GPU: rank g of nranks passes the instances
+        [g * n_local, (g+1) * n_local) and `allgather(send_ptr, nbytes, recv_ptr, on_device) -> None`, the host's collective
+        (see torch_allgather below)."""
+        self.ctx, self.S, self.comm = ctx, shape, comm     # comm: spartan2_b200.Comm (peer mailboxes) for the in-kernel exchange of the round sums
         zs = np.ascontiguousarray(np.stack([_fe(z) for z in step_zs]), dtype=np.uint64)
         zc = _fe(core_z)
         if zs.shape[1] != shape.num_cols or zc.shape[0] != shape.num_cols:
             from ._lib import SpartanError
             raise SpartanError(-3, "z vectors must have num_cols entries")
-        self.n = zs.shape[0]
+        self.n_local = zs.shape[0]; self.n = self.n_local * nranks; self.rank, self.nranks = rank, nranks
         h = C.c_void_p()
-        ctx.check(ctx.L.sp2_neutronnova_prep_prove(ctx.h, shape.h, C.c_uint32(self.n), _p(zs), _p(zc), C.byref(h)))
+        if nranks == 1:
+            ctx.check(ctx.L.sp2_neutronnova_prep_prove(ctx.h, shape.h, C.c_uint32(self.n), _p(zs), _p(zc), C.byref(h)))
+            self._cb = None
+        else:
+            ctx.check(ctx.L.sp2_neutronnova_prep_prove_sharded(ctx.h, shape.h, C.c_int32(rank), C.c_int32(nranks), C.c_uint32(self.n_local), _p(zs), _p(zc),
+                                                               C.byref(h)))
+
+            def cb(user, send, nbytes, recv, on_device):
+                try:
+                    allgather(send, int(nbytes), recv, bool(on_device))
+                    return 0
+                except Exception as e:                     # never unwind across the ABI
+                    import sys
+                    sys.stderr.write("allgather callback failed: %r\n" % (e,))
+                    return -1
+            self._cb = self.ALLGATHER_FN(cb)
         self.h = h
 
     def prove(self, ts):
@@ -296,7 +316,10 @@ class NeutronNovaProver:
         for k, a in out.items():
             setattr(pc, k, a.ctypes.data)
         ph = (C.c_float * 6)()
-        ctx.check(ctx.L.sp2_neutronnova_prove(ctx.h, self.h, ts.h, C.byref(pc), ph))
+        if self._cb is None:
+            ctx.check(ctx.L.sp2_neutronnova_prove(ctx.h, self.h, ts.h, C.byref(pc), ph))
+        else:
+            ctx.check(ctx.L.sp2_neutronnova_prove_sharded(ctx.h, self.h, ts.h, self.comm.h if self.comm is not None else None, self._cb, None, C.byref(pc), ph))
         out["outer_ok"], out["inner_ok"] = bool(pc.outer_ok), bool(pc.inner_ok)
         return out, dict(zip(self.PHASES, [float(x) for x in ph]))
 
@@ -325,3 +348,29 @@ class NeutronNovaProver:
             self.free()
         except Exception:
             pass
+
+
+def torch_allgather(world, device):
+    """An `allgather` for NeutronNovaProver built on torch.distributed (NCCL): device buffers are wrapped in place through
+    __cuda_array_interface__ (no staging copy); the 64-byte per-round host messages go through a small device tensor."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+
+    class _Raw:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+    def allgather(send, nbytes, recv, on_device):
+        if on_device:
+            src = torch.as_tensor(_Raw(send, nbytes), device=device)
+            dst = torch.as_tensor(_Raw(recv, nbytes * world), device=device)
+            dist.all_gather_into_tensor(dst, src.clone())          # send aliases recv's own slot: gather from a copy
+            torch.cuda.synchronize(device)
+        else:
+            src = torch.frombuffer(bytearray(ctypes.string_at(send, nbytes)), dtype=torch.uint8).to(device)
+            dst = torch.empty(nbytes * world, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(dst, src)
+            host = dst.cpu().numpy()                               # keep the array alive across the memmove
+            ctypes.memmove(recv, host.ctypes.data, nbytes * world)
+    return allgather

@@ -75,3 +75,67 @@ def test_cyclic_sharding_scheme_world2():
     port = 29600 + (os.getpid() % 300)
     mp.spawn(_worker, args=(port, ret), nprocs=WORLD, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def _worker_nn(rank, port, ret):
+    """NeutronNova instance sharding: rank g holds the contiguous block of instances [g n/G, (g+1) n/G).
+    Two gloo ranks run the NIFS on their blocks — per round the local (e0, quad) with suffix weights taken at the GLOBAL
+    pair index, all-gathered and added mod p; local folds; then the surviving layers and the witness partials are
+    all-gathered — and must reproduce the single-process oracle values."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        from oracle import pyoracle as orc
+        n, left, right = 8, 8, 4
+        N = left * right; ell_b = 3; nl = n // WORLD; M = 16
+        rng = np.random.default_rng(7)                                # same global data on both ranks
+        A, B, Cm = _rand_fe(rng, n * N), _rand_fe(rng, n * N), _rand_fe(rng, n * N)
+        Ws = _rand_fe(rng, n * M)
+        E = orc.pow_split_evals(_rand_fe(rng, 1), left, right); rhos = _rand_fe(rng, ell_b); r_bs = _rand_fe(rng, ell_b)
+        blk = slice(rank * nl * N, (rank + 1) * nl * N)
+        lA, lB, lC = A[blk].copy(), B[blk].copy(), Cm[blk].copy()
+        fA, fB, fC, m, ml = A, B, Cm, n, nl
+        for t in range(ell_b):
+            want = orc.nifs_round(t, rhos, left, right, E, fA, fB, fC, N, m)
+            if ml >= 2:                                               # local round
+                mine = orc.nifs_round(t, rhos, left, right, E, lA, lB, lC, N, ml, pair_offset=rank * (ml // 2))
+                parts = [None] * WORLD
+                dist.all_gather_object(parts, mine.tolist())
+                got = np.zeros((2, 4), dtype=np.uint64)
+                for p in parts:
+                    got = orc.f_add(got, np.array(p, dtype=np.uint64))
+                lA, lB, lC = (orc.nifs_fold(x, N, ml, r_bs[t:t + 1]) for x in (lA, lB, lC))
+                ml //= 2
+                if ml == 1:                                           # hand-off: gather the surviving layers in rank order
+                    gath = [None] * WORLD
+                    dist.all_gather_object(gath, [lA.tolist(), lB.tolist(), lC.tolist()])
+                    lA, lB, lC = (np.concatenate([np.array(g[k], dtype=np.uint64) for g in gath], axis=0) for k in range(3))
+                    ml = 0; mrep = WORLD
+            else:                                                     # replicated rounds on the gathered layers
+                got = orc.nifs_round(t, rhos, left, right, E, lA, lB, lC, N, mrep)
+                lA, lB, lC = (orc.nifs_fold(x, N, mrep, r_bs[t:t + 1]) for x in (lA, lB, lC))
+                mrep //= 2
+            assert np.array_equal(got, want), t
+            fA, fB, fC = (orc.nifs_fold(x, N, m, r_bs[t:t + 1]) for x in (fA, fB, fC))
+            m //= 2
+        assert np.array_equal(lA, fA) and np.array_equal(lB, fB) and np.array_equal(lC, fC)
+        # witness fold: local partial with the GLOBAL weights of this rank's instances, gathered, added
+        w = orc.weights_from_r(r_bs, n)
+        part = orc.fold_vectors(Ws[rank * nl * M:(rank + 1) * nl * M], nl, M, np.ascontiguousarray(w[rank * nl:(rank + 1) * nl]))
+        parts = [None] * WORLD
+        dist.all_gather_object(parts, part.tolist())
+        tot = np.zeros((M, 4), dtype=np.uint64)
+        for p in parts:
+            tot = orc.f_add(tot, np.array(p, dtype=np.uint64))
+        assert np.array_equal(tot, orc.fold_vectors(Ws, n, M, w))
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_neutronnova_instance_sharding_world2():
+    mgr = mp.Manager(); ret = mgr.dict()
+    port = 29950 + (os.getpid() % 300)
+    mp.spawn(_worker_nn, args=(port, ret), nprocs=WORLD, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}

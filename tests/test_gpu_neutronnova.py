@@ -160,3 +160,21 @@ def test_fused_prover_vs_oracle(ctx, orc, n):
     assert ts_d.state().get() == (st, rnd)
     assert ph["total"] > 0
     prover.free(); S.free()
+
+
+def test_fused_prover_argument_errors(ctx, orc):
+    """SpartanError mirroring (src/errors.rs:12-110) at the fused entry points: a step count that is not a power of two
+    (the reference pads to one, neutronnova_zk.rs:529-552 — the caller's job here) and z vectors of the wrong length."""
+    import spartan2_b200 as sp
+    from spartan2_b200 import neutronnova as nn
+    from tests.neutronnova_ops import sha_chain_instances
+    c0, zs, Ws, zc, Wc = sha_chain_instances(2)
+    A, B, Cm = c0.matrices()
+    S = sp.SplitR1CSShape(ctx, *c0.dims(), A, B, Cm)
+    with pytest.raises(sp.SpartanError) as ei:
+        nn.NeutronNovaProver(ctx, S, [zs[0], zs[1], zs[0]], zc)
+    assert ei.value.kind == "InvalidInputLength"
+    with pytest.raises(sp.SpartanError) as ei:
+        nn.NeutronNovaProver(ctx, S, [zs[0][:-1], zs[1][:-1]], zc)
+    assert ei.value.kind == "InvalidWitnessLength"
+    S.free()

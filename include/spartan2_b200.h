@@ -304,6 +304,11 @@ void sp2_neutronnova_prep_free(sp2_nn_prep *prep);
 typedef int32_t (*sp2_allgather_fn)(void *user, const void *send, uint64_t bytes, void *recv, int32_t on_device);
 int32_t sp2_neutronnova_prep_prove_sharded(sp2_ctx *ctx, const sp2_shape *shape, int32_t rank, int32_t nranks, uint32_t n_local,
                                            const uint64_t *local_step_zs, const uint64_t *core_z, sp2_nn_prep **out);
+/* optional: map every rank's exchange buffer through CUDA IPC (handle = 64 bytes, all-gathered by the host in rank
+ * order) so that the two bulk exchanges of a sharded prove become peer stores over NVLink (needs `comm` for the flag
+ * barriers); without it they go through the `allgather` callback                                                     */
+int32_t sp2_neutronnova_prep_ipc_handle(sp2_nn_prep *prep, uint8_t *out64);
+int32_t sp2_neutronnova_prep_connect(sp2_nn_prep *prep, const uint8_t *all_handles);
 int32_t sp2_neutronnova_prove_sharded(sp2_ctx *ctx, sp2_nn_prep *prep, sp2_transcript *ts, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
                                       sp2_nn_proof *proof, float *phase_ms);
 

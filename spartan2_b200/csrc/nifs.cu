@@ -426,6 +426,9 @@ struct sp2_nn_prep {
   int rank = 0, nranks = 1; uint32_t n_total = 0;
   fe *gath = nullptr;                        // nranks x 3 x N: the surviving (A, B, C) layers of all ranks
   fe *wpart = nullptr;                       // nranks x M: per-rank partial witness folds
+  // gath and wpart live in ONE allocation (xbuf) that peers map through CUDA IPC, so the two bulk exchanges of a sharded
+  // prove are plain stores into every peer's copy over NVLink (k_nn_scatter) instead of a host-driven collective
+  fe *xbuf = nullptr; fe *peer_x[8] = {nullptr}; bool peer_opened[8] = {false}; bool peers_connected = false;
   uint64_t N = 0, M = 0, ncols = 0;
   fe *zs = nullptr, *zc = nullptr;           // n x ncols, ncols
   fe *Ws = nullptr;                          // n x M (contiguous copies of the witness sections)
@@ -525,6 +528,30 @@ __global__ void __launch_bounds__(NF_THREADS) k_publish_xchg(const fe *partials,
     }
     __threadfence_system();
     *(volatile u32 *)mail_flag = seq;
+  }
+}
+// bulk exchange of a sharded prove: every rank stores its block straight into all ranks' exchange buffers (peer memory
+// over NVLink; its own copy included) at the same offset, then a flag barrier over the comm mailboxes makes the data of
+// all ranks visible everywhere (system-scope fences on both sides; bounded wait)
+struct NnPeers { fe *x[8]; int n; };
+__global__ void __launch_bounds__(256) k_nn_scatter(const fe *src, u64 count, NnPeers pe, u64 dst_offset) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (u64)gridDim.x * blockDim.x) {
+    const fe v = ldg_fe(src + i);
+    for (int q = 0; q < pe.n; q++) stg_fe(pe.x[q] + dst_offset + i, v);
+  }
+}
+__global__ void k_nn_barrier(DevComm dc, int slot) {
+  const int tid = threadIdx.x;
+  if (tid < dc.n) {
+    __threadfence_system();
+    *(volatile u32 *)&dc.peer[tid]->flag[slot][dc.rank] = dc.epoch;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (*(volatile const u32 *)&dc.peer[dc.rank]->flag[slot][tid] != dc.epoch) {
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) break;             // a missing peer must not wedge the GPU; the parity of the outputs will show it
+    }
+    __threadfence_system();
   }
 }
 __global__ void k_set_one(fe *p) { if (threadIdx.x == 0) stg_fe(p, Fq::one()); }
@@ -742,6 +769,7 @@ void sp2_neutronnova_prep_free(sp2_nn_prep *P) {
   if (!P) return;
   cudaSetDevice(P->ctx->device);
   cudaStreamSynchronize(P->ctx->stream);
+  for (int q = 0; q < 8; q++) if (P->peer_opened[q]) cudaIpcCloseMemHandle(P->peer_x[q]);
   for (void *p : P->owned) cudaFree(p);
   if (P->h_mail) cudaFreeHost(P->h_mail);
   if (P->h_stage) cudaFreeHost(P->h_stage);
@@ -778,7 +806,10 @@ static int32_t nn_prep_impl(sp2_ctx *ctx, const sp2_shape *S, int rank, int nran
       (rc = nn_alloc(P, (size_t)P->left + P->right, &P->E)) || (rc = nn_alloc(P, N, &P->rx)) || (rc = nn_alloc(P, NN_SMALL_FE, &P->small)) ||
       (rc = nn_alloc(P, NN_MAX_PARTS * 6, &P->partials)))
     return fail(rc);
-  if (nranks > 1 && ((rc = nn_alloc(P, (size_t)nranks * 3 * N, &P->gath)) || (rc = nn_alloc(P, (size_t)nranks * M, &P->wpart)))) return fail(rc);
+  if (nranks > 1) {
+    if ((rc = nn_alloc(P, (size_t)nranks * (3 * N + M), &P->xbuf))) return fail(rc);
+    P->gath = P->xbuf; P->wpart = P->xbuf + (size_t)nranks * 3 * N; P->peer_x[rank] = P->xbuf;
+  }
   { void *p; if (cudaMalloc(&p, 64) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->ticket = (u32 *)p;
     cudaMemsetAsync(p, 0, 64, ctx->stream); }
   if (cudaHostAlloc((void **)&P->h_mail, NN_MAIL_BYTES, cudaHostAllocMapped) != cudaSuccess ||
@@ -832,9 +863,10 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
                              sp2_nn_proof *pf, float *phase_ms) {
   cudaSetDevice(ctx->device);
   if (!P || !tsh || !pf) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: null argument");
-  if (P->nranks > 1 && !allgather) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: a sharded prep state needs the all-gather callback");
   if (comm && (!comm->connected || comm->dc.n != P->nranks || comm->dc.rank != P->rank)) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: comm does not match the prep state");
   const bool xchg = comm && P->nranks > 1;          // per-round sums exchanged inside the publish kernel over NVLink
+  const bool peer_x = xchg && P->peers_connected;   // bulk exchanges as peer stores too (else through the allgather callback)
+  if (P->nranks > 1 && !peer_x && !allgather) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: a sharded prep state needs connected peers or the all-gather callback");
   if (xchg) comm->dc.epoch++;
   sp2h::Transcript &ts = tsh->t;
   const sp2_shape *S = P->S;
@@ -896,9 +928,21 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
       // log2(G) rounds replicated.  recv layout [rank][A|B|C][N]: table k of layer q sits at gath + (3q + k) N, i.e.
       // layer-major with stride 3 from base gath + k N — exactly what the round / fold kernels take.
       fe *mine = P->gath + (size_t)rank * 3 * N;
-      for (int k = 0; k < 3; k++) SP2_CUDA_OK(cudaMemcpyAsync(mine + (size_t)k * N, P->work[k], (size_t)N * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
-      SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-      if (allgather(user, mine, (uint64_t)3 * N * sizeof(fe), P->gath, 1) != 0) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: all-gather of the surviving layers failed");
+      if (peer_x) {
+        NnPeers pe; pe.n = (int)G; for (u32 q = 0; q < 8; q++) pe.x[q] = q < G ? P->peer_x[q] : nullptr;
+        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 30);      // every rank has entered this prove: its exchange buffer is free
+        SP2_LAUNCH_CHECK();
+        for (int k = 0; k < 3; k++) {
+          k_nn_scatter<<<ctx->num_sms, 256, 0, ctx->stream>>>(P->work[k], N, pe, (u64)rank * 3 * N + (u64)k * N);
+          SP2_LAUNCH_CHECK();
+        }
+        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 31);
+        SP2_LAUNCH_CHECK();
+      } else {
+        for (int k = 0; k < 3; k++) SP2_CUDA_OK(cudaMemcpyAsync(mine + (size_t)k * N, P->work[k], (size_t)N * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+        SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        if (allgather(user, mine, (uint64_t)3 * N * sizeof(fe), P->gath, 1) != 0) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: all-gather of the surviving layers failed");
+      }
       As = P->gath; Bs = P->gath + N; Cs = P->gath + 2 * N;
       m = G; stride = 3; gathered = true;
     }
@@ -974,10 +1018,23 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
     } else {
       // this rank's part of the weighted sum (its instances' global weights), all-gather of the G partial vectors, sum
       fe *mine = P->wpart + (size_t)rank * M;
-      k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->Ws, n, M, P->small + 128 + (size_t)rank * n, mine);
-      SP2_LAUNCH_CHECK();
-      SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-      if (allgather(user, mine, (uint64_t)M * sizeof(fe), P->wpart, 1) != 0) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: all-gather of the witness partials failed");
+      if (peer_x) {
+        // the partial goes to a private scratch first (the exchange buffer may still be read by a slower peer's previous
+        // phase only before barrier 30 of this prove, which every rank has passed by now), then to every rank's wpart
+        fe *tmp = P->z_core;                                       // not yet initialised for this prove: free scratch of >= M entries
+        k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->Ws, n, M, P->small + 128 + (size_t)rank * n, tmp);
+        SP2_LAUNCH_CHECK();
+        NnPeers pe; pe.n = (int)G; for (u32 q = 0; q < 8; q++) pe.x[q] = q < G ? P->peer_x[q] : nullptr;
+        k_nn_scatter<<<ctx->num_sms, 256, 0, ctx->stream>>>(tmp, M, pe, (u64)G * 3 * N + (u64)rank * M);
+        SP2_LAUNCH_CHECK();
+        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 32);
+        SP2_LAUNCH_CHECK();
+      } else {
+        k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->Ws, n, M, P->small + 128 + (size_t)rank * n, mine);
+        SP2_LAUNCH_CHECK();
+        SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        if (allgather(user, mine, (uint64_t)M * sizeof(fe), P->wpart, 1) != 0) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: all-gather of the witness partials failed");
+      }
       std::vector<fe> ones(G, one);
       SP2_TRY(stage(ones.data(), G * sizeof(fe), P->small + 700));
       k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->wpart, G, M, P->small + 700, P->z_step);
@@ -1100,6 +1157,31 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
   if (pf->heads) { SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); memcpy(pf->heads, heads_stage, 28 * sizeof(fe)); }
   ph[5] = ms_since(t_begin);
   if (phase_ms) memcpy(phase_ms, ph, sizeof(ph));
+  return SP2_OK;
+}
+/* CUDA-IPC handle (64 bytes) of this rank's exchange buffer, to be all-gathered by the host and passed to
+ * sp2_neutronnova_prep_connect on every rank: afterwards the two bulk exchanges of a sharded prove are peer stores. */
+int32_t sp2_neutronnova_prep_ipc_handle(sp2_nn_prep *P, uint8_t *out64) {
+  sp2_ctx *ctx = P->ctx;
+  cudaSetDevice(ctx->device);
+  if (!P->xbuf) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: not a sharded prep state");
+  cudaIpcMemHandle_t h;
+  SP2_CUDA_OK(cudaIpcGetMemHandle(&h, P->xbuf));
+  memcpy(out64, &h, 64);
+  return SP2_OK;
+}
+int32_t sp2_neutronnova_prep_connect(sp2_nn_prep *P, const uint8_t *all_handles) {
+  sp2_ctx *ctx = P->ctx;
+  cudaSetDevice(ctx->device);
+  if (!P->xbuf) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: not a sharded prep state");
+  for (int q = 0; q < P->nranks; q++) {
+    if (q == P->rank || P->peer_opened[q]) continue;
+    cudaIpcMemHandle_t h; memcpy(&h, all_handles + 64 * q, 64);
+    void *p = nullptr;
+    SP2_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    P->peer_x[q] = (fe *)p; P->peer_opened[q] = true;
+  }
+  P->peers_connected = true;
   return SP2_OK;
 }
 int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_nn_proof *pf, float *phase_ms) {

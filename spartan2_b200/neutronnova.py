@@ -274,10 +274,12 @@ class NeutronNovaProver:
 
     ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32)
 
-    def __init__(self, ctx, shape, step_zs, core_z, rank=0, nranks=1, allgather=None, comm=None):
+    def __init__(self, ctx, shape, step_zs, core_z, rank=0, nranks=1, allgather=None, comm=None, allgather_bytes=None):
         """step_zs: this rank's instances (all of them on a single GPU).  Multi-GPU: rank g of nranks passes the instances
         [g * n_local, (g+1) * n_local) and `allgather(send_ptr, nbytes, recv_ptr, on_device) -> None`, the host's collective
-        (see torch_allgather below)."""
+        (see torch_allgather below).  With `comm` (spartan2_b200.Comm) the per-round sums cross ranks inside the kernels;
+        with `allgather_bytes` as well (bytes -> list of every rank's bytes, used once for the 64-byte IPC handles) the
+        two bulk exchanges become peer stores too and `allgather` is never called."""
         self.ctx, self.S, self.comm = ctx, shape, comm     # comm: spartan2_b200.Comm (peer mailboxes) for the in-kernel exchange of the round sums
         zs = np.ascontiguousarray(np.stack([_fe(z) for z in step_zs]), dtype=np.uint64)
         zc = _fe(core_z)
@@ -301,7 +303,13 @@ class NeutronNovaProver:
                     import sys
                     sys.stderr.write("allgather callback failed: %r\n" % (e,))
                     return -1
-            self._cb = self.ALLGATHER_FN(cb)
+            self._cb = self.ALLGATHER_FN(cb) if allgather is not None else C.cast(None, self.ALLGATHER_FN)
+            if comm is not None and allgather_bytes is not None:
+                buf = (C.c_uint8 * 64)()
+                ctx.check(ctx.L.sp2_neutronnova_prep_ipc_handle(h, buf))
+                handles = allgather_bytes(bytes(buf))
+                allb = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+                ctx.check(ctx.L.sp2_neutronnova_prep_connect(h, _p(allb)))
         self.h = h
 
     def prove(self, ts):

@@ -52,7 +52,8 @@ def main():
         S = sp.SplitR1CSShape(ctx, *c0.dims(), A, B, Cm)
         zc = z_of(core)
         t0 = time.perf_counter()
-        prover = nn.NeutronNovaProver(ctx, S, [z_of(circs[i]) for i in mine], zc, rank=rank, nranks=world, allgather=nn.torch_allgather(world, dev), comm=comm)
+        prover = nn.NeutronNovaProver(ctx, S, [z_of(circs[i]) for i in mine], zc, rank=rank, nranks=world, allgather=nn.torch_allgather(world, dev), comm=comm,
+                                      allgather_bytes=allgather_bytes if os.environ.get("SP2_NN_NCCL_GATHER") != "1" else None)
         ctx.synchronize(); prep_ms = (time.perf_counter() - t0) * 1e3
         best = None
         for it in range(6):

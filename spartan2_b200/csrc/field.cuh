@@ -56,6 +56,37 @@ SP2_HD void mul_wide(u32 (&r)[16], const fe &a, const fe &b) {
   r[15] = addc(E[15], O[14]);
 }
 
+// Two independent 256 x 256 products in LOCKSTEP: the carry chains of the two products alternate in program order.
+// ptxas interleaves independent chains only within a short window (it does so for the even / odd chains of one product,
+// not across two ~360-instruction multiplications placed one after the other — checked in SASS), so the instruction-
+// level parallelism of a pair of independent products has to be laid out in the source.
+SP2_HD void mul_wide2(u32 (&r0)[16], u32 (&r1)[16], const fe &a0, const fe &b0, const fe &a1, const fe &b1) {
+  u32 E0[16], O0[16], E1[16], O1[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) { E0[i] = 0; O0[i] = 0; E1[i] = 0; O1[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    mad_row4<16>(E0, i, a0.v[0], a0.v[2], a0.v[4], a0.v[6], b0.v[i]);
+    mad_row4<16>(E1, i, a1.v[0], a1.v[2], a1.v[4], a1.v[6], b1.v[i]);
+    mad_row4<16>(O0, i, a0.v[1], a0.v[3], a0.v[5], a0.v[7], b0.v[i]);
+    mad_row4<16>(O1, i, a1.v[1], a1.v[3], a1.v[5], a1.v[7], b1.v[i]);
+    mad_row4<16>(O0, i, a0.v[0], a0.v[2], a0.v[4], a0.v[6], b0.v[i + 1]);
+    mad_row4<16>(O1, i, a1.v[0], a1.v[2], a1.v[4], a1.v[6], b1.v[i + 1]);
+    mad_row4<16>(E0, i + 2, a0.v[1], a0.v[3], a0.v[5], a0.v[7], b0.v[i + 1]);
+    mad_row4<16>(E1, i + 2, a1.v[1], a1.v[3], a1.v[5], a1.v[7], b1.v[i + 1]);
+  }
+  r0[0] = E0[0];
+  r0[1] = add_cc(E0[1], O0[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) r0[k] = addc_cc(E0[k], O0[k - 1]);
+  r0[15] = addc(E0[15], O0[14]);
+  r1[0] = E1[0];
+  r1[1] = add_cc(E1[1], O1[0]);
+#pragma unroll
+  for (int k = 2; k < 15; k++) r1[k] = addc_cc(E1[k], O1[k - 1]);
+  r1[15] = addc(E1[15], O1[14]);
+}
+
 // ------------------------------------------------------------------------------------------
 // Generic helpers parameterised by the modulus
 // ------------------------------------------------------------------------------------------
@@ -259,12 +290,65 @@ struct Fp : Field<FpParams> {
   // were 280-300 KB of straight-line code executed once per tree level by a handful of warps — bound by instruction
   // fetch from L2, not by arithmetic (ncu: 115 us for a 7-level tree of 128 points).  One shared 5.8 KB body stays
   // resident in the instruction cache.
+  // mul2: TWO INDEPENDENT products per out-of-line call, computed in lockstep (mul_inl2).  A point addition is a
+  // dependency chain of 11-16 multiplications executed by few warps (the MSM kernels run at IPC ~0.3), and one
+  // multiplication alone is a ~1100-cycle chain of dependent carry instructions; the independent products of a formula
+  // level (e.g. Z1^2 and Z2^2) share one call whose interleaved chains fill the idle issue slots.  Body: ~12 KB, still
+  // instruction-cache resident, unlike the fully inlined additions.
+  struct fe2 { fe a, b; };
 #if defined(__CUDA_ARCH__)
   static __device__ __noinline__ fe mul_ni(fe a, fe b) { return mul_inl(a, b); }
   static __device__ __forceinline__ fe mul(const fe &a, const fe &b) { return mul_ni(a, b); }
+  static __device__ __noinline__ fe2 mul2_ni(fe a0, fe b0, fe a1, fe b1) { fe2 r; mul_inl2(a0, b0, a1, b1, r.a, r.b); return r; }
+  static __device__ __forceinline__ void mul2(const fe &a0, const fe &b0, const fe &a1, const fe &b1, fe &o0, fe &o1) {
+    const fe2 r = mul2_ni(a0, b0, a1, b1); o0 = r.a; o1 = r.b;
+  }
 #else
   SP2_HD static fe mul(const fe &a, const fe &b) { return mul_inl(a, b); }
+  SP2_HD static void mul2(const fe &a0, const fe &b0, const fe &a1, const fe &b1, fe &o0, fe &o1) { mul_inl2(a0, b0, a1, b1, o0, o1); }
 #endif
+  // one word-by-word REDC round (see mul_inl) on t[i..17]
+  SP2_HD static void redc_round(u32 (&t)[18], const int i) {
+    const u32 m = mul_lo(t[i], FpParams::INV32);
+    t[i + 0] = mad_lo_cc(m, FpParams::P(0), t[i + 0]);
+    t[i + 1] = madc_hi_cc(m, FpParams::P(0), t[i + 1]);
+    t[i + 2] = madc_lo_cc(m, FpParams::P(2), t[i + 2]);
+    t[i + 3] = madc_hi_cc(m, FpParams::P(2), t[i + 3]);
+    t[i + 4] = addc_cc(t[i + 4], m);
+    t[i + 5] = addc_cc(t[i + 5], 0);
+    t[i + 6] = addc_cc(t[i + 6], m);
+    t[i + 7] = addc_cc(t[i + 7], 0);
+    t[i + 8] = addc_cc(t[i + 8], m);
+#pragma unroll
+    for (int j = i + 9; j < 17; j++) t[j] = addc_cc(t[j], 0);
+    t[17] = addc(t[17], 0);
+    t[i + 1] = mad_lo_cc(m, FpParams::P(1), t[i + 1]);
+    t[i + 2] = madc_hi_cc(m, FpParams::P(1), t[i + 2]);
+    t[i + 3] = madc_lo_cc(m, FpParams::P(3), t[i + 3]);
+    t[i + 4] = madc_hi_cc(m, FpParams::P(3), t[i + 4]);
+#pragma unroll
+    for (int j = i + 5; j < 17; j++) t[j] = addc_cc(t[j], 0);
+    t[17] = addc(t[17], 0);
+    t[i + 7] = sub_cc(t[i + 7], m);
+#pragma unroll
+    for (int j = i + 8; j < 17; j++) t[j] = subc_cc(t[j], 0);
+    t[17] = subc(t[17], 0);
+  }
+  // two independent Montgomery products in lockstep (mul_wide2 + alternating REDC rounds)
+  SP2_HD static void mul_inl2(const fe &a0, const fe &b0, const fe &a1, const fe &b1, fe &o0, fe &o1) {
+    u32 w0[16], w1[16];
+    mul_wide2(w0, w1, a0, b0, a1, b1);
+    u32 t0[18], t1[18];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { t0[i] = w0[i]; t1[i] = w1[i]; }
+    t0[16] = 0; t0[17] = 0; t1[16] = 0; t1[17] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { redc_round(t0, i); redc_round(t1, i); }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { o0.v[i] = t0[8 + i]; o1.v[i] = t1[8 + i]; }
+    cond_sub_p<FpParams>(o0, t0[16]);
+    cond_sub_p<FpParams>(o1, t1[16]);
+  }
   SP2_HD static fe mul_inl(const fe &a, const fe &b) {
     u32 w[16];
     mul_wide(w, a, b);

@@ -178,3 +178,68 @@ def test_fused_prover_argument_errors(ctx, orc):
         nn.NeutronNovaProver(ctx, S, [zs[0][:-1], zs[1][:-1]], zc)
     assert ei.value.kind == "InvalidWitnessLength"
     S.free()
+
+
+@pytest.mark.parametrize("n,world", [(4, 2), (8, 4), (2, 2)])
+def test_sharded_prover_two_ranks_on_one_gpu(ctx, orc, n, world):
+    """The instance-sharded prove (sp2_neutronnova_prep_prove_sharded / _prove_sharded) with `world` ranks
+    emulated on ONE GPU: one context + prep state per rank, one host thread per rank, and an in-process all-gather
+    (threading.Barrier + device copies) as the `allgather` callback — the callback variant of every exchange (round sums
+    on the host, surviving layers and witness partials on the device).  Every rank must return exactly what the
+    single-GPU fused prove of all n instances returns (which test_fused_prover_vs_oracle pins to the oracle)."""
+    import ctypes as C
+    import threading
+    import spartan2_b200 as sp
+    from spartan2_b200 import neutronnova as nn
+    from tests.neutronnova_ops import sha_chain_instances
+    c0, zs, Ws, zc, Wc = sha_chain_instances(n)
+    A, B, Cm = c0.matrices()
+    S = sp.SplitR1CSShape(ctx, *c0.dims(), A, B, Cm)
+    single = nn.NeutronNovaProver(ctx, S, zs, zc)
+    want, _ = single.prove(sp.Keccak256Transcript(b"neutronnova_prove"))
+    single.free()
+    nl = n // world
+    ctxs = [sp.Context(0) for _ in range(world)]
+    shapes = [sp.SplitR1CSShape(c, *c0.dims(), A, B, Cm) for c in ctxs]
+    bar = threading.Barrier(world)
+    slots = [None] * world
+
+    def make_allgather(rank):
+        def allgather(send, nbytes, recv, on_device):
+            slots[rank] = (send, nbytes)
+            bar.wait()
+            for q in range(world):
+                src, nb = slots[q]
+                assert nb == nbytes
+                if on_device:       # same GPU: a device-to-device copy stands in for the peer transfer
+                    if recv + q * nbytes != src:
+                        ctxs[rank].check(ctxs[rank].L.sp2_dev_copy(ctxs[rank].h, C.c_void_p(recv + q * nbytes), C.c_void_p(src), C.c_uint64(nbytes)))
+                else:
+                    C.memmove(recv + q * nbytes, src, nbytes)
+            if on_device:
+                ctxs[rank].synchronize()
+            bar.wait()              # nobody reuses its send buffer before every rank has copied it
+        return allgather
+    provers = [nn.NeutronNovaProver(ctxs[r], shapes[r], zs[r * nl:(r + 1) * nl], zc, rank=r, nranks=world, allgather=make_allgather(r)) for r in range(world)]
+    outs, errs = [None] * world, []
+
+    def run(r):
+        try:
+            outs[r], _ = provers[r].prove(sp.Keccak256Transcript(b"neutronnova_prove"))
+        except Exception as e:      # a failing rank must not leave the others waiting in the barrier
+            errs.append(e); bar.abort()
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ths]
+    [t.join(timeout=120) for t in ths]
+    assert not errs, errs
+    for r in range(world):
+        for k, v in want.items():
+            if isinstance(v, np.ndarray):
+                assert np.array_equal(outs[r][k], v), (r, k)
+        assert outs[r]["outer_ok"] and outs[r]["inner_ok"]
+    for p in provers:
+        p.free()
+    for s_ in shapes + [S]:
+        s_.free()
+    for c in ctxs:
+        c.close()

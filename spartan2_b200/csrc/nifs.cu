@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(256) k_nn_scatter(const fe *src, u64 count, Nn
     for (int q = 0; q < pe.n; q++) stg_fe(pe.x[q] + dst_offset + i, v);
   }
 }
-__global__ void k_nn_barrier(DevComm dc, int slot) {
+__global__ void k_nn_barrier(DevComm dc, int slot, u32 *err) {
   const int tid = threadIdx.x;
   if (tid < dc.n) {
     __threadfence_system();
@@ -549,7 +549,7 @@ __global__ void k_nn_barrier(DevComm dc, int slot) {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     while (*(volatile const u32 *)&dc.peer[dc.rank]->flag[slot][tid] != dc.epoch) {
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 2000000000ull) break;             // a missing peer must not wedge the GPU; the parity of the outputs will show it
+      if (t1 - t0 > 2000000000ull) { atomicExch(err, 1u); break; }   // a missing peer must not wedge the GPU: the prove returns an error
     }
     __threadfence_system();
   }
@@ -930,13 +930,13 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
       fe *mine = P->gath + (size_t)rank * 3 * N;
       if (peer_x) {
         NnPeers pe; pe.n = (int)G; for (u32 q = 0; q < 8; q++) pe.x[q] = q < G ? P->peer_x[q] : nullptr;
-        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 30);      // every rank has entered this prove: its exchange buffer is free
+        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 30, P->ticket + 1);      // every rank has entered this prove: its exchange buffer is free
         SP2_LAUNCH_CHECK();
         for (int k = 0; k < 3; k++) {
           k_nn_scatter<<<ctx->num_sms, 256, 0, ctx->stream>>>(P->work[k], N, pe, (u64)rank * 3 * N + (u64)k * N);
           SP2_LAUNCH_CHECK();
         }
-        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 31);
+        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 31, P->ticket + 1);
         SP2_LAUNCH_CHECK();
       } else {
         for (int k = 0; k < 3; k++) SP2_CUDA_OK(cudaMemcpyAsync(mine + (size_t)k * N, P->work[k], (size_t)N * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1027,7 +1027,7 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
         NnPeers pe; pe.n = (int)G; for (u32 q = 0; q < 8; q++) pe.x[q] = q < G ? P->peer_x[q] : nullptr;
         k_nn_scatter<<<ctx->num_sms, 256, 0, ctx->stream>>>(tmp, M, pe, (u64)G * 3 * N + (u64)rank * M);
         SP2_LAUNCH_CHECK();
-        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 32);
+        k_nn_barrier<<<1, 32, 0, ctx->stream>>>(comm->dc, 32, P->ticket + 1);
         SP2_LAUNCH_CHECK();
       } else {
         k_fold_vectors<<<nb, NF_THREADS, 0, ctx->stream>>>(P->Ws, n, M, P->small + 128 + (size_t)rank * n, mine);
@@ -1155,6 +1155,12 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
   pf->inner_ok = HF::eq(claim_js, HF::mul(fi[0], fi[2])) && HF::eq(claim_jc, HF::mul(fi[1], fi[3]));
   ph[4] = ms_since(t_phase);
   if (pf->heads) { SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); memcpy(pf->heads, heads_stage, 28 * sizeof(fe)); }
+  if (peer_x) {                                     // did every peer-store barrier complete?
+    u32 *h_err = (u32 *)(P->h_stage + NN_STAGE_BYTES - 28 * sizeof(fe) - 64);
+    SP2_CUDA_OK(cudaMemcpyAsync(h_err, P->ticket + 1, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (*h_err) { cudaMemsetAsync(P->ticket + 1, 0, sizeof(u32), ctx->stream); return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova: a peer did not reach an exchange barrier within 2 s"); }
+  }
   ph[5] = ms_since(t_begin);
   if (phase_ms) memcpy(phase_ms, ph, sizeof(ph));
   return SP2_OK;

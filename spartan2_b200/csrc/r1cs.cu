@@ -115,9 +115,10 @@ __global__ void __launch_bounds__(128) k_spmv3_long(Spmv3Args a, const fe *z) {
 struct AbcArgs { const u32 *ptr[3]; const uint2 *ent[3]; const fe *dict[3]; };
 
 // poly_ABC[col] = sum_A a*rx[row] + r * sum_B b*rx[row] + r^2 * sum_C c*rx[row]   (mod.rs:1324-1398)
-__global__ void __launch_bounds__(256) k_abc(AbcArgs a, u32 ncols, const fe *rx, const fe *r, fe *out) {
-  const u32 col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= ncols) return;
+__global__ void __launch_bounds__(256) k_abc(AbcArgs a, u32 ncols, const u32 *order, const fe *rx, const fe *r, fe *out) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncols) return;
+  const u32 col = order[t];                     // degree-sorted assignment (sp2_shape::col_order)
   u32 tot = 0;
 #pragma unroll
   for (int k = 0; k < 3; k++) tot += a.ptr[k][col + 1] - a.ptr[k][col];
@@ -184,7 +185,7 @@ int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe 
   const u32 ncols = (u32)S->cols_local;                    // == num_cols on a single GPU
   if (out_len < ncols) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "abc: output shorter than num_vars + num_extra");
   if (out_len > ncols) SP2_CUDA_OK(cudaMemsetAsync(d_out + ncols, 0, (out_len - ncols) * sizeof(fe), ctx->stream));
-  k_abc<<<(ncols + 255) / 256, 256, 0, ctx->stream>>>(a, ncols, d_rx, d_r, d_out);
+  k_abc<<<(ncols + 255) / 256, 256, 0, ctx->stream>>>(a, ncols, S->col_order, d_rx, d_r, d_out);
   SP2_LAUNCH_CHECK();
   if (S->nlong_cols) {
     if (S->nchunks) {
@@ -264,6 +265,15 @@ static int32_t shape_upload_impl(sp2_ctx *ctx, int rank, int nranks, uint64_t nu
     if (rc == SP2_OK) rc = upload_matrix(S, hf, &S->F[k]);
   }
   if (rc == SP2_OK) {
+    { // degree-sorted column order for k_abc (stable; SP2_ABC_UNSORTED=1 keeps the natural order for A/B measurements)
+      std::vector<u32> ord(cols_local);
+      for (size_t c = 0; c < cols_local; c++) ord[c] = (u32)c;
+      const char *env = getenv("SP2_ABC_UNSORTED");
+      if (!(env && env[0] == '1')) std::stable_sort(ord.begin(), ord.end(), [&](u32 x, u32 y) { return coldeg[x] > coldeg[y]; });
+      cudaError_t e0 = cudaMalloc((void **)&S->col_order, cols_local * 4 + 32);
+      if (e0 != cudaSuccess) rc = set_cuda_error(ctx, e0, "cudaMalloc", __LINE__);
+      else { S->owned.push_back(S->col_order); cudaMemcpy(S->col_order, ord.data(), cols_local * 4, cudaMemcpyHostToDevice); }
+    }
     std::vector<u32> lc;
     for (size_t c = 0; c < cols_local; c++) if (coldeg[c] > LONG_SEG) lc.push_back((u32)c);
     S->nlong_cols = (u32)lc.size();

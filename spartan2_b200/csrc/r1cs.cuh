@@ -42,6 +42,9 @@ struct sp2_shape {
   sp2::DevMatrix T[3];                       // transposes (column-major) for bind_and_prepare_poly_ABC
   sp2::DevMatrix F[3];                       // row-major, columns >= num_shared + num_precommitted only (FilteredSpmv)
   sp2::u32 *long_cols = nullptr; sp2::u32 nlong_cols = 0;   // columns whose A+B+C degree exceeds LONG_SEG
+  // columns in order of decreasing A+B+C degree: thread t of k_abc takes column col_order[t], so the lanes of a warp
+  // walk segments of (nearly) equal length — a thread-per-column gather is bound by the LONGEST column of each warp
+  sp2::u32 *col_order = nullptr;
   // long columns (the constant-one column of SHA-256 has ~10^6 entries) are cut into chunks of ABC_CHUNK entries,
   // one CTA each: chunk = (matrix, first entry, last entry); chunk_first[3*lc + k] .. chunk_first[3*lc + k + 1]
   // are the chunks of long column lc in matrix k

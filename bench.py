@@ -90,7 +90,7 @@ class ClockSampler:
 class Workload:
     """sha256_spartan: Sha256Circuit(vec![0u8; msg_len]) -> padded R1CS, witness, prover randomness (seeded)."""
 
-    def __init__(self, msg_len, seed=0xDEADBEEF):
+    def __init__(self, msg_len, seed=0xDEADBEEF, tail_len=1024):
         from spartan2_b200.frontend import Sha256Circuit
         self.msg_len = msg_len
         self.circ = c = Sha256Circuit(b"\x00" * msg_len, width=WIDTH)
@@ -112,12 +112,12 @@ class Workload:
         # Hyrax bind M; incremental SpMV: general nnz of the filtered columns (bounded by nnz_general; counted as 0)
         self.field_ops = 7 * N + N + 2 * N + self.nnz_general + 7 * M + M
         self.bytes_outer = 368 * N
-        # the persistent kernel k_cubic_persist runs rounds 1..R-1 of the outer sum-check (tables > 4096 entries going in,
+        # the persistent kernel k_cubic_persist runs rounds 1..R-1 of the outer sum-check (tables > tail_len entries going in,
         # sumcheck.cu: sumcheck_cubic_enqueue): round 1 reads 2.5 tables, round i >= 2 reads 3 * T/2^(i-2) entries and
         # writes half as many (bind fused into the evaluation)  — SURVEY.md §8(d) accounting, 32 B per entry
         l = N.bit_length() - 1
         r_end = 1
-        while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > 4096:
+        while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > tail_len:
             r_end += 1
         self.persist_rounds = r_end - 1
         self.bytes_persist = (80 * N if r_end > 1 else 0) + sum(144 * (N >> (i - 2)) for i in range(2, r_end))
@@ -141,7 +141,7 @@ def run_cuda(args):
     sharded = bool(args.sharded) and world > 1
     # replicas (default): every GPU proves its own instance (independent proofs: weak scaling, no data-path exchange);
     # --sharded: ONE proof, its 2^l hypercube split across the GPUs (strong scaling)
-    wl = Workload(args.msg_len, seed=0xDEADBEEF + (0 if sharded else rank))
+    wl = Workload(args.msg_len, seed=0xDEADBEEF + (0 if sharded else rank), tail_len=int(ctx.L.sp2_sc_tail_len()))
     hbm_peak, peak_kind = peaks()
     pts = ctx.test_points(WIDTH + 3, seed=7)
     K = sp.CommitmentKey(ctx, pts[:WIDTH], pts[WIDTH:WIDTH + 1], pts[WIDTH + 1:WIDTH + 2], pts[WIDTH + 2:WIDTH + 3])
@@ -291,7 +291,8 @@ def tables_bench(ctx, sp, hbm_peak, num_vars=24):
     for t in tabs + small:
         t.free()
     l = num_vars; r_end = 1
-    while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > 4096:
+    tail_len = int(ctx.L.sp2_sc_tail_len())
+    while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > tail_len:
         r_end += 1
     b_persist = 80 * n + sum(144 * (n >> (i - 2)) for i in range(2, r_end))
     k_ms, t_ms = float(np.mean(per)), float(np.mean(tot))

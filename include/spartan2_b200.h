@@ -327,6 +327,8 @@ int32_t sp2_transcript_get_state(const sp2_transcript *t, sp2_transcript_state *
 /* measurement hook: duration in ms (CUDA events on the library's stream) of the most recent persistent cubic
  * sum-check kernel (all multi-CTA rounds of prove_cubic_with_three_inputs in one launch)                              */
 int32_t sp2_last_cubic_persist_ms(sp2_ctx *ctx, float *ms);
+/* table length at or below which the single-CTA tail kernels take over from the persistent multi-CTA kernels          */
+uint64_t sp2_sc_tail_len(void);
 
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);

@@ -48,6 +48,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.sp2_last_error.restype = C.c_char_p
     L.sp2_launch_count.restype = C.c_uint64
+    L.sp2_sc_tail_len.restype = C.c_uint64
     L.sp2_neutronnova_prep_free.restype = None
     L.sp2_neutronnova_prep_free.argtypes = [C.c_void_p]
     _lib = L

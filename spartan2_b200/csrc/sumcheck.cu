@@ -1032,6 +1032,10 @@ extern "C" {
  * squeeze start, message built, hashed, challenge ready, finalize end] */
 /* debug: per-round %globaltimer stamps (ns) of the last persistent cubic kernel: rounds x [start, own compute done, all CTAs
  * arrived, finalised] */
+/* tables of at most this many entries are finished by the single-CTA tail kernels; larger ones go through the persistent
+ * multi-CTA kernels (bench.py derives from it which rounds k_cubic_persist covers) */
+uint64_t sp2_sc_tail_len(void) { return SC_TAIL_LEN; }
+
 int32_t sp2_debug_sc_round_profile(sp2_ctx *ctx, uint64_t *out, uint32_t rounds) {
   cudaSetDevice(ctx->device);
   if (!ctx->slot[14] || rounds > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INTERNAL, "no sum-check has run");

@@ -10,8 +10,16 @@ constexpr int SC_MAX_BLOCKS = 2048;
 constexpr int SC_THREADS = 256;
 constexpr int SC_TAIL_THREADS = 384;   // 12 warps = 4 role trios
 constexpr int SC_ROLE_THREADS = 384;
-constexpr unsigned long long SC_TAIL_LEN = 4096;   // tables this short are finished by one CTA in one launch
-constexpr unsigned long long SC_ROLE_LEN = 1ull << 16;   // tables this short use the role-split (3 items per pair) rounds
+// thresholds swept on B200 at N = 2^20 (prove ms): (4096, 2^16) 1.93 | (8192, 2^16) 2.01 | (2048, 2^16) 1.88 | (1024, 2^16) 1.89 |
+// (4096, 2^15) 1.91 | (4096, 2^17) 1.93 | (2048, 2^15) 1.88 | (2048, 2^14) 1.90 | (1024, 2^15) 1.87
+#ifndef SP2_SC_TAIL_LEN
+#define SP2_SC_TAIL_LEN 1024
+#endif
+#ifndef SP2_SC_ROLE_LOG
+#define SP2_SC_ROLE_LOG 15
+#endif
+constexpr unsigned long long SC_TAIL_LEN = SP2_SC_TAIL_LEN;   // tables this short are finished by one CTA in one launch
+constexpr unsigned long long SC_ROLE_LEN = 1ull << SP2_SC_ROLE_LOG;   // tables this short use the role-split (3 items per pair) rounds
 
 struct ScState {
   DevTranscript ts;           // transcript hand-off: (round, state) in, (round, state) out

@@ -226,7 +226,8 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
   A(palloc(P, &P->zvec, width));
   P->inbox_bytes = ((size_t)S_COUNT + width + P->rows_total + S->num_public) * sizeof(fe);
   { fe *ib = nullptr; A(palloc(P, &ib, (size_t)S_COUNT + width + P->rows_total + S->num_public)); P->inbox = ib; }
-  if (rc == SP2_OK && cudaMallocHost((void **)&P->h_inbox, P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64) != cudaSuccess) rc = set_error(ctx, SP2_ERR_CUDA, "cudaMallocHost");
+  // pinned staging: [inbox | tau digests | rest-commitment rows (Jacobian) read back in prove]
+  if (rc == SP2_OK && cudaMallocHost((void **)&P->h_inbox, P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64 + P->rows_total * sizeof(jac)) != cudaSuccess) rc = set_error(ctx, SP2_ERR_CUDA, "cudaMallocHost");
   if (rc == SP2_OK) {
     P->small = P->inbox; P->dvec = P->inbox + S_COUNT; P->blinds = P->dvec + width;
     for (auto &e : P->ev) cudaEventCreate(&e);
@@ -331,8 +332,8 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   if (rest_rows) {
     // an all-zero rest section is HyraxPCS::commit_zeros (hyrax_pc.rs:305-319): rows = blind_i * h, no row terms to walk
     SP2_TRY(sp2_hyrax_commit_dev(ctx, ck, P->W + P->cached_len, W_rest ? S->num_rest : 0, P->blinds + P->cached_rows, rest_rows, P->points + P->cached_rows));
-    std::vector<uint64_t> hj(rest_rows * 12);
-    SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), P->points + P->cached_rows, rest_rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t *hj = (uint64_t *)(P->h_inbox + P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64);      // pinned: a true async DMA
+    SP2_CUDA_OK(cudaMemcpyAsync(hj, P->points + P->cached_rows, rest_rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
     SP2_CUDA_OK(cudaEventRecord(P->ev_r1, ctx->stream));
     // Az, Bz, Cz (spartan.rs:271 -> multiply_vec_incremental_into) do not depend on the taus: enqueue them now so they
     // run while the host normalises / hashes the commitment rows
@@ -341,7 +342,7 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     spmv_done = true;
     absorb_head();
     SP2_CUDA_OK(cudaEventSynchronize(P->ev_r1));                            // host sync 1 (rows only)
-    sp2h::batch_normalize(hj.data(), rest_rows, proof->comm_W + 8 * P->cached_rows);
+    sp2h::batch_normalize(hj, rest_rows, proof->comm_W + 8 * P->cached_rows);
   }
   if (!spmv_done) { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
     SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work));

@@ -94,6 +94,14 @@ int32_t sp2_comm_create(sp2_ctx *ctx, int32_t rank, int32_t nranks, sp2_comm **o
 int32_t sp2_comm_handle(sp2_comm *comm, uint8_t *out64);
 int32_t sp2_comm_connect(sp2_comm *comm, const uint8_t *all_handles /* nranks x 64 bytes, rank order */);
 void sp2_comm_destroy(sp2_comm *comm);
+/* Ranks living in ONE process (several contexts on one GPU or on peer-enabled GPUs) connect without CUDA IPC:
+ * mailboxes[q] = rank q's sp2_comm_mailbox() device pointer.                                                         */
+int32_t sp2_comm_mailbox(sp2_comm *comm, void **out);
+int32_t sp2_comm_connect_ptrs(sp2_comm *comm, void *const *mailboxes /* nranks device pointers, rank order */);
+/* Every device-side wait on a peer is bounded (2 s): when a rank fails or dies mid-call the others return
+ * SP2_ERR_INTERNAL instead of wedging their GPU.  Afterwards every rank calls sp2_comm_reset (host barrier before and
+ * after) to bring the mailbox flags / epochs back in step.                                                           */
+int32_t sp2_comm_reset(sp2_comm *comm);
 /* dA, dB, dC: this rank's shards (2^l / nranks entries each, device pointers), bound in place; every rank passes
  * the same claim / taus / transcript and receives identical outputs (same meaning as the single-GPU provers). */
 int32_t sp2_sumcheck_cubic_prove_sharded_dev(sp2_ctx *ctx, sp2_comm *comm, const uint64_t *claim, const uint64_t *taus, uint32_t l,
@@ -184,7 +192,9 @@ typedef struct {
 } sp2_spartan_proof;
 /* The prover's randomness (the reference draws it from thread_rng inside prove: hyrax_pc.rs:192-205,
  * ipa.rs:140-145, bellpepper/r1cs.rs:467); the caller samples and passes it so runs are reproducible:
- * blinds_W: one per commitment row; d_vec: num_cols scalars.                                      */
+ * blinds_W: one per commitment row (rows of the shared / precommitted sections are IGNORED: those rows were committed
+ * by sp2_spartan_prep_prove with `blinds_cached` and keep that blind — comm_W is reused, bellpepper/r1cs.rs:422-431; only
+ * the rest rows are committed, with blinds_W[cached_rows..], inside prove, :467-470); d_vec: num_cols scalars.          */
 typedef struct { const uint64_t *blinds_W, *blind_eval_W, *d_vec, *r_delta, *r_beta; } sp2_spartan_rand;
 
 /* Replaces SpartanSNARK::prep_prove (src/spartan.rs:176-216): uploads the shared+precommitted witness
@@ -309,6 +319,9 @@ int32_t sp2_neutronnova_prep_prove_sharded(sp2_ctx *ctx, const sp2_shape *shape,
  * barriers); without it they go through the `allgather` callback                                                     */
 int32_t sp2_neutronnova_prep_ipc_handle(sp2_nn_prep *prep, uint8_t *out64);
 int32_t sp2_neutronnova_prep_connect(sp2_nn_prep *prep, const uint8_t *all_handles);
+/* in-process variant (ranks in one process, no CUDA IPC): xbufs[q] = rank q's sp2_neutronnova_prep_xbuf() pointer */
+int32_t sp2_neutronnova_prep_xbuf(sp2_nn_prep *prep, void **out);
+int32_t sp2_neutronnova_prep_connect_ptrs(sp2_nn_prep *prep, void *const *xbufs);
 int32_t sp2_neutronnova_prove_sharded(sp2_ctx *ctx, sp2_nn_prep *prep, sp2_transcript *ts, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
                                       sp2_nn_proof *proof, float *phase_ms);
 

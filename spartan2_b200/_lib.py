@@ -46,10 +46,61 @@ def lib():
         raise RuntimeError("spartan2_b200: %s is missing — run `python -m spartan2_b200.build` (nvcc, sm_100a); "
                            "there is no CPU fallback" % LIB_PATH)
     L = C.CDLL(LIB_PATH)
-    L.sp2_last_error.restype = C.c_char_p
-    L.sp2_launch_count.restype = C.c_uint64
-    L.sp2_sc_tail_len.restype = C.c_uint64
-    L.sp2_neutronnova_prep_free.restype = None
-    L.sp2_neutronnova_prep_free.argtypes = [C.c_void_p]
+    for name, (restype, argtypes) in header_prototypes().items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = restype, argtypes
     _lib = L
     return L
+
+
+HEADER_PATH = os.path.join(HERE, "..", "include", "spartan2_b200.h")
+_SCALARS = {"int32_t": C.c_int32, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64, "int64_t": C.c_int64, "uint16_t": C.c_uint16,
+            "uint8_t": C.c_uint8, "int": C.c_int, "float": C.c_float, "double": C.c_double, "size_t": C.c_size_t,
+            "sp2_allgather_fn": C.c_void_p}
+
+
+def header_prototypes(path=HEADER_PATH):
+    """{name: (restype, argtypes)} for every function include/spartan2_b200.h declares, so that ctypes converts every
+    argument to the width the C side reads (an undeclared uint64_t parameter would travel as a 32-bit int).  Pointers of
+    every kind are c_void_p (accepts None, ints, arrays, byref() and callback objects); `const char *` is c_char_p."""
+    import re
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", " ", src)
+    src = re.sub(r"^\s*#.*$", " ", src, flags=re.M)
+    src = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", " ", src, flags=re.S)      # struct bodies hold no prototypes
+    src = re.sub(r"typedef[^;{]*;", " ", src)
+    out = {}
+
+    def ctype(decl, is_ret=False):
+        decl = decl.strip()
+        if "(" in decl:                                   # function-pointer parameter
+            return C.c_void_p
+        if "*" in decl:
+            base = decl.replace("const", " ").split("*")[0].split()
+            if base and base[0] == "char":
+                return C.c_char_p
+            return C.c_void_p
+        toks = [t for t in decl.replace("const", " ").split() if t]
+        if toks[0] == "void":
+            return None
+        return _SCALARS[toks[0]]
+
+    for m in re.finditer(r"([\w\s\*]+?)\b(sp2_\w+)\s*\(([^;{}]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        # split on commas outside parentheses
+        parts, depth, cur = [], 0, ""
+        for ch in args:
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            if ch == "," and depth == 0:
+                parts.append(cur); cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur)
+        argtypes = [] if (len(parts) == 1 and parts[0].strip() == "void") else [ctype(a) for a in parts]
+        out[name] = (ctype(ret + " ", True), argtypes)
+    return out

@@ -7,6 +7,18 @@
 
 using namespace sp2;
 
+namespace sp2 {
+// after the calling function has synchronised the stream: did a bounded peer wait of this rank expire?
+int comm_check(sp2_ctx *ctx, sp2_comm *c) {
+  if (!c || c->dc.n <= 1) return SP2_OK;
+  u32 e = 0;
+  SP2_CUDA_OK(cudaMemcpyAsync(&e, &c->dc.peer[c->dc.rank]->err, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (e) return set_error(ctx, SP2_ERR_INTERNAL, "sharded sum-check: a peer did not publish its round sums within 2 s (call sp2_comm_reset on every rank)");
+  return SP2_OK;
+}
+}  // namespace sp2
+
 extern "C" {
 
 int32_t sp2_comm_create(sp2_ctx *ctx, int32_t rank, int32_t nranks, sp2_comm **out) {
@@ -56,6 +68,31 @@ int32_t sp2_comm_connect(sp2_comm *c, const uint8_t *all_handles) {
   return SP2_OK;
 }
 
+/* In-process variant of connect for ranks that live in ONE process (several contexts on one GPU, or on peer-enabled
+ * GPUs): mailboxes[q] = rank q's sp2_comm_mailbox() pointer, no CUDA IPC involved.  Used by the single-GPU multi-rank
+ * tests of the NVLink mailbox protocol (tests/test_gpu_multirank.py). */
+int32_t sp2_comm_mailbox(sp2_comm *c, void **out) { *out = c->dc.peer[c->dc.rank]; return SP2_OK; }
+int32_t sp2_comm_connect_ptrs(sp2_comm *c, void *const *mailboxes) {
+  for (int q = 0; q < c->dc.n; q++) if (q != c->dc.rank) c->dc.peer[q] = (MailBox *)mailboxes[q];
+  c->connected = true;
+  return SP2_OK;
+}
+
+/* Collective re-initialisation after a failed sharded call (a rank returned an error between the epoch bump and its
+ * kernels, or a bounded device wait expired): every rank calls it, with a host barrier before and after, and the
+ * mailbox flags / epoch start from zero again. */
+int32_t sp2_comm_reset(sp2_comm *c) {
+  sp2_ctx *ctx = c->ctx;
+  cudaSetDevice(ctx->device);
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  MailBox *mb = c->dc.peer[c->dc.rank];
+  SP2_CUDA_OK(cudaMemsetAsync(mb->flag, 0, sizeof(mb->flag), ctx->stream));
+  SP2_CUDA_OK(cudaMemsetAsync(&mb->err, 0, sizeof(u32), ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  c->dc.epoch = 0;
+  return SP2_OK;
+}
+
 void sp2_comm_destroy(sp2_comm *c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
@@ -74,11 +111,13 @@ int32_t sp2_sumcheck_cubic_prove_sharded_dev(sp2_ctx *ctx, sp2_comm *c, const ui
   cudaSetDevice(ctx->device);
   if (!c->connected) return set_error(ctx, SP2_ERR_INTERNAL, "comm: not connected");
   if (l < 1 || l > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "sumcheck_cubic: 1 <= num_rounds <= 40");
-  c->dc.epoch++;
   ScState *st;
   SP2_TRY(sc_state_upload(ctx, &st, claim, taus, l, ts));
+  c->dc.epoch++;                                    // only once the fallible host steps in front of the kernels are done
   SP2_TRY(sumcheck_cubic_enqueue(ctx, st, l, (fe *)dA, (fe *)dB, (fe *)dC, &c->dc));
-  return sc_state_download(ctx, st, ts, polys, 4, r, claims, 3, l);
+  const int rc = sc_state_download(ctx, st, ts, polys, 4, r, claims, 3, l);
+  SP2_TRY(comm_check(ctx, c));
+  return rc;
 }
 
 int32_t sp2_sumcheck_quad_prove_sharded_dev(sp2_ctx *ctx, sp2_comm *c, const uint64_t *claim, uint32_t rounds, void *dA, void *dB,
@@ -86,11 +125,13 @@ int32_t sp2_sumcheck_quad_prove_sharded_dev(sp2_ctx *ctx, sp2_comm *c, const uin
   cudaSetDevice(ctx->device);
   if (!c->connected) return set_error(ctx, SP2_ERR_INTERNAL, "comm: not connected");
   if (rounds < 1 || rounds > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "sumcheck_quad: 1 <= num_rounds <= 40");
-  c->dc.epoch++;
   ScState *st;
   SP2_TRY(sc_state_upload(ctx, &st, claim, nullptr, rounds, ts));
+  c->dc.epoch++;
   SP2_TRY(sumcheck_quad_enqueue(ctx, st, rounds, (fe *)dA, (fe *)dB, ~0ull, nullptr, &c->dc));
-  return sc_state_download(ctx, st, ts, polys, 3, r, claims, 2, rounds);
+  const int rc = sc_state_download(ctx, st, ts, polys, 3, r, claims, 2, rounds);
+  SP2_TRY(comm_check(ctx, c));
+  return rc;
 }
 
 }  // extern "C"

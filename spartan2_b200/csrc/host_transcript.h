@@ -251,8 +251,11 @@ inline void fq_pow2_mont(int k, uint64_t out[4]) {              // 2^k mod q (ca
   memcpy(out, r, 32);
 }
 inline void fq_from_uniform(const uint8_t dg[64], uint64_t out_mont[4]) {
-  static uint64_t R2[4], R3[4]; static bool init = false;
-  if (!init) { fq_pow2_mont(512, R2); fq_pow2_mont(768, R3); init = true; }
+  // function-local static with a dynamic initialiser: C++11 guarantees a thread-safe one-time initialisation (contexts on
+  // several host threads squeeze concurrently)
+  struct Consts { uint64_t R2[4], R3[4]; Consts() { fq_pow2_mont(512, R2); fq_pow2_mont(768, R3); } };
+  static const Consts K;
+  const uint64_t *R2 = K.R2, *R3 = K.R3;
   uint64_t lo[4], hi[4], a[4], b[4];
   memcpy(lo, dg, 32); memcpy(hi, dg + 32, 32);
   mont_mul(lo, R2, FQ_MOD, FQ_INV, a);                           // lo * R

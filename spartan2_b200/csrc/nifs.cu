@@ -1190,6 +1190,18 @@ int32_t sp2_neutronnova_prep_connect(sp2_nn_prep *P, const uint8_t *all_handles)
   P->peers_connected = true;
   return SP2_OK;
 }
+/* in-process variant (ranks in one process: no CUDA IPC): xbufs[q] = rank q's sp2_neutronnova_prep_xbuf() pointer */
+int32_t sp2_neutronnova_prep_xbuf(sp2_nn_prep *P, void **out) {
+  if (!P->xbuf) return set_error(P->ctx, SP2_ERR_INTERNAL, "neutronnova: not a sharded prep state");
+  *out = P->xbuf;
+  return SP2_OK;
+}
+int32_t sp2_neutronnova_prep_connect_ptrs(sp2_nn_prep *P, void *const *xbufs) {
+  if (!P->xbuf) return set_error(P->ctx, SP2_ERR_INTERNAL, "neutronnova: not a sharded prep state");
+  for (int q = 0; q < P->nranks; q++) if (q != P->rank) P->peer_x[q] = (fe *)xbufs[q];
+  P->peers_connected = true;
+  return SP2_OK;
+}
 int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_nn_proof *pf, float *phase_ms) {
   return nn_prove_impl(ctx, P, tsh, nullptr, nullptr, nullptr, pf, phase_ms);
 }

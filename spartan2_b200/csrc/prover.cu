@@ -43,6 +43,7 @@ struct sp2_prep {
   fe *LZ = nullptr, *Ltab = nullptr, *Rtab = nullptr, *dvec = nullptr, *zvec = nullptr;
   std::vector<uint64_t> comm_cached; // host copy of the cached commitment rows (affine)
   std::vector<uint8_t> comm_cached_be;  // their transcript bytes (x_BE || y_BE per row), computed once
+  std::vector<uint64_t> blinds_cached_host;   // the blinds prep_prove committed the cached rows with (prove reuses them)
   fe *inbox = nullptr;               // per-prove host inputs, one H2D copy: [small slots | d_vec | blinds | X]
   uint8_t *h_inbox = nullptr;        // pinned staging of the same layout (+ tau digests)
   size_t inbox_bytes = 0;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(64) k_outer_to_inner(ScState *outer, ScState *
     inner->ts.round = ts->round; inner->ts.pending_len = 0;
     for (int i = 0; i < 64; i++) inner->ts.state[i] = ts->state[i];
     stg_fe(&inner->claim, joint);
-    inner->ticket = 0; inner->l = (u32)rounds_inner; inner->flags = outer->flags; inner->arrived = 0; inner->released = 0;
+    inner->ticket = 0; inner->l = (u32)rounds_inner; inner->flags = outer->flags; inner->arrived = 0; inner->released = 0; inner->err = 0;
   }
 }
 
@@ -209,12 +210,12 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
   if (nv % width || S->num_shared % width || S->num_precommitted % width || S->num_rest % width)
     return set_error(ctx, SP2_ERR_INVALID_WITNESS_LENGTH, "prep_prove: witness sections must be multiples of the commitment width");
   if (S->num_challenges) return set_error(ctx, SP2_ERR_UNSUPPORTED, "prep_prove: multi-round (challenge) circuits are not offloaded");
+  const bool shard = S->nranks > 1;
+  if (shard && ((2 * nv) >> S->shard_k) == 0) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "prep_prove: fewer variables than ranks");
   sp2_prep *P = new sp2_prep();
   P->ctx = ctx; P->S = S; P->ck = ck;
   P->cached_len = S->num_shared + S->num_precommitted; P->cached_rows = P->cached_len / width; P->rows_total = nv / width;
   const uint64_t N = S->num_cons, nc = S->num_cols, Nl = S->rows_local;
-  const bool shard = S->nranks > 1;
-  if (shard && ((2 * nv) >> S->shard_k) == 0) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "prep_prove: fewer variables than ranks");
   int rc = SP2_OK;
   auto A = [&](int r) { if (rc == SP2_OK) rc = r; };
   A(palloc(P, &P->W, nv));
@@ -237,6 +238,7 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
   auto fail = [&](int r) { sp2_prep_free(P); return r; };
   cudaError_t e = cudaMemsetAsync(P->W, 0, nv * sizeof(fe), ctx->stream);
   if (e == cudaSuccess && P->cached_len) e = cudaMemcpyAsync(P->W, W_cached, P->cached_len * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
+  if (P->cached_rows) P->blinds_cached_host.assign(blinds_cached, blinds_cached + 4 * P->cached_rows);
   if (e == cudaSuccess && P->cached_rows) e = cudaMemcpyAsync(P->blinds, blinds_cached, P->cached_rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) return fail(set_cuda_error(ctx, e, "prep upload", __LINE__));
   // commitments of the cached rows
@@ -301,7 +303,10 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     memcpy(h + S_RBETA * sizeof(fe), rnd->r_beta, sizeof(fe));
     uint8_t *q = h + S_COUNT * sizeof(fe);
     memcpy(q, rnd->d_vec, width * sizeof(fe)); q += width * sizeof(fe);
-    memcpy(q, rnd->blinds_W, rows * sizeof(fe)); q += rows * sizeof(fe);
+    // blinds: the shared / precommitted rows keep the blinds prep_prove committed them with (comm_W is reused from there, and
+    // r_LZ = <L, blinds> must match it); only the rest rows take fresh blinds from `rand` (bellpepper/r1cs.rs:467-470)
+    memcpy(q, P->blinds_cached_host.data(), P->cached_rows * sizeof(fe));
+    memcpy(q + P->cached_rows * sizeof(fe), rnd->blinds_W + 4 * P->cached_rows, (rows - P->cached_rows) * sizeof(fe)); q += rows * sizeof(fe);
     if (S->num_public) memcpy(q, public_values, S->num_public * sizeof(fe));
     SP2_CUDA_OK(cudaMemcpyAsync(P->inbox, h, P->inbox_bytes, cudaMemcpyHostToDevice, ctx->stream)); }
   const fe *d_X = P->blinds + rows;
@@ -448,6 +453,8 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   SP2_CUDA_OK(cudaMemcpyAsync(h_small, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(h_jac, d_pts, 4 * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                          // host sync 2
+  if (h_outer->err || h_inner->err) { cleanup(); return set_error(ctx, SP2_ERR_INTERNAL, "prove: a device-side wait (grid barrier) did not complete within 2 s"); }
+  if (shard) SP2_TRY(comm_check(ctx, comm));
   sp2h::batch_normalize(h_jac, jobs.size(), h_pts);
   if (((uint32_t *)(h_small + 4 * S_ERR))[0] == 5) { cleanup(); return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "prove: 1 - r_y[0] = 0"); }
   for (int i = 0; i < l; i++) {                                            // compressed: [c0, c2, c3] (univariate.rs:147-153)

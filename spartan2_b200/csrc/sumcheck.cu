@@ -61,6 +61,22 @@ __device__ __noinline__ void fq_mul_ni(fe *out, const fe *a, const fe *b) { *out
 __device__ __forceinline__ fe mul_ni(const fe &a, const fe &b) { fe o; fq_mul_ni(&o, &a, &b); return o; }
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// Bounded spin: waits until pred() holds; gives up after SC_WAIT_NS of %globaltimer (sampled every 256 polls so the
+// timer read stays off the fast path) and raises *err instead of hanging — a peer that failed or died, or a grid that
+// lost a CTA, must come back to the host as SP2_ERR_INTERNAL, not as a wedged GPU.
+template <class Pred>
+__device__ __forceinline__ bool spin_until(Pred pred, u32 *err) {
+  unsigned long long t0 = 0; u32 polls = 0;
+  while (!pred()) {
+    if ((++polls & 255u) == 0) {
+      const unsigned long long t = gtimer();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > SC_WAIT_NS) { atomicExch(err, 1u); return false; }
+      if (*(volatile u32 *)err) return false;             // another wait of this call already expired: do not queue up behind it
+    }
+  }
+  return true;
+}
 // publish this CTA's partial sums and elect the last CTA of the grid
 template <int NV>
 __device__ __forceinline__ bool publish_and_elect(ScState *st, fe (&x)[NV], FinSmem &sm) {
@@ -104,9 +120,10 @@ __device__ __forceinline__ void exchange_sums(const DevComm &dc, int slot, fe (&
     for (int k = 0; k < NV; k++) stg_fe(&mb->sums[slot][dc.rank][k], sm.g[k]);
     __threadfence_system();
     *(volatile u32 *)&mb->flag[slot][dc.rank] = dc.epoch;
-    // wait for rank `tid`'s contribution to arrive in the local mailbox
-    const MailBox *me = dc.peer[dc.rank];
-    while (*(volatile const u32 *)&me->flag[slot][tid] != dc.epoch) {}
+    // wait for rank `tid`'s contribution to arrive in the local mailbox (bounded: see spin_until)
+    MailBox *me = dc.peer[dc.rank];
+    const volatile u32 *fl = &me->flag[slot][tid]; const u32 want = dc.epoch;
+    spin_until([=] { return *fl == want; }, &me->err);
     __threadfence_system();
   }
   __syncthreads();
@@ -142,7 +159,9 @@ __global__ void k_shard_barrier(DevComm dc, int slot) {
   if (tid < dc.n) {
     __threadfence_system();
     *(volatile u32 *)&dc.peer[tid]->flag[slot][dc.rank] = dc.epoch;
-    while (*(volatile const u32 *)&dc.peer[dc.rank]->flag[slot][tid] != dc.epoch) {}
+    MailBox *me = dc.peer[dc.rank];
+    const volatile u32 *fl = &me->flag[slot][tid]; const u32 want = dc.epoch;
+    spin_until([=] { return *fl == want; }, &me->err);
     __threadfence_system();
   }
 }
@@ -668,7 +687,7 @@ __device__ __forceinline__ bool persist_gather(ScState *st, u32 seq, fe (&x)[NV]
     if (tid == 0) { __threadfence(); atomicAdd(&st->arrived, 1u); }
     return false;
   }
-  if (tid == 0) { while (ld_volatile_u32(&st->arrived) < (G - 1) * seq) {} __threadfence(); }
+  if (tid == 0) { const u32 want = (G - 1) * seq; spin_until([=] { return ld_volatile_u32(&st->arrived) >= want; }, &st->err); __threadfence(); }
   __syncthreads();
   fe y[NV];
 #pragma unroll
@@ -689,7 +708,7 @@ __device__ __forceinline__ void persist_release(ScState *st, u32 seq) {       //
   if (threadIdx.x == 0) { __threadfence(); *(volatile u32 *)&st->released = seq; }
 }
 __device__ __forceinline__ void persist_wait(ScState *st, u32 seq) {          // other CTAs
-  if (threadIdx.x == 0) { while (ld_volatile_u32(&st->released) < seq) {} __threadfence(); }
+  if (threadIdx.x == 0) { spin_until([=] { return ld_volatile_u32(&st->released) >= seq; }, &st->err); __threadfence(); }
   __syncthreads();
 }
 
@@ -841,6 +860,7 @@ int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uin
   const size_t upto = offsetof(ScState, partial);
   SP2_CUDA_OK(cudaMemcpyAsync(hs, d_st, upto, cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (hs->err) return set_error(ctx, SP2_ERR_INTERNAL, "sum-check: a device-side wait (grid barrier) did not complete within 2 s");
   ts->round = (uint16_t)hs->ts.round; memcpy(ts->state, hs->ts.state, 64);
   for (uint32_t i = 0; i < l; i++) memcpy(polys + (size_t)i * ncoef * 4, &hs->polys[4 * i], (size_t)ncoef * sizeof(fe));
   memcpy(r, hs->r, (size_t)l * sizeof(fe));

@@ -27,7 +27,8 @@ struct ScState {
   fe p;                       // eval_eq_left (sumcheck.rs:951)
   fe L0, SL;                  // p*(1-tau_i), p*(2tau_i-1) for the round being evaluated
   u32 ticket, l, flags, arrived;     // arrived / released: monotonic counters of the persistent kernels' grid barrier
-  u32 released, pad1[3];   // flags bit 0: warp-shuffle Keccak (default; measured 12.6k cycles/squeeze vs 22k for the one-thread register version)
+  u32 released, err, pad1[2];   // err: a bounded device wait (grid barrier / peer mailbox) timed out -> SP2_ERR_INTERNAL on the host
+  // flags bit 0: warp-shuffle Keccak (default; measured 12.6k cycles/squeeze vs 22k for the one-thread register version)
   fe taus[SC_MAX_ROUNDS];
   // ---- everything above is uploaded by the host; everything below is produced on the device ----
   fe r[SC_MAX_ROUNDS];
@@ -51,7 +52,10 @@ struct MailBox {
   fe sums[SC_MAX_ROUNDS + 2][SC_MAX_RANKS][4];
   u32 flag[SC_MAX_ROUNDS + 2][SC_MAX_RANKS];
   fe gather[3][SC_ROLE_LEN];
+  u32 err, pad[7];            // set by a round / barrier kernel of the LOCAL rank whose bounded wait for a peer expired
 };
+// every device-side wait is bounded (a dead or failed peer must surface as an error code, not wedge the GPU)
+constexpr unsigned long long SC_WAIT_NS = 2000000000ull;
 struct DevComm {
   int rank, n, k;             // n = 2^k ranks
   u32 epoch;                  // distinguishes successive sum-checks (flags are compared to it, never reset)
@@ -77,5 +81,7 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
 // after_first (optional): recorded once the launch that produces r[0] has been enqueued
 int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first,
                           const DevComm *dc = nullptr);
+// after a stream synchronisation: SP2_ERR_INTERNAL if a bounded peer wait of this rank expired (comm.cu)
+int comm_check(sp2_ctx *ctx, sp2_comm *c);
 
 }  // namespace sp2

@@ -17,18 +17,27 @@ def _shapes(ctx, orc, inst):
 
 
 def test_reference_spmv_known_answer(ctx):
-    # sparse.rs:637-653: [[2,0,1],[0,3,0],[0,0,4]] (as A) times z = [... ] -> the product [25, 9, 4] with z = [12? ...]
-    # the reference's vector is (2,0,1; 0,3,0; 0,0,4) * (12, 3, 1) = (25, 9, 4)
+    # the reference's own vector (src/r1cs/sparse.rs:637-653, test_matrix_vector_multiplication), read from the committed
+    # fixture tests/golden/reference_kats.json: [[0,2,7],[0,0,3],[4,0,0]] * [1,2,3] = [25,9,4]
+    import json
+    import os
     import spartan2_b200 as sp
-    data = np.array([mont(2), mont(1), mont(3), mont(4)], dtype=np.uint64)
-    idx = np.array([0, 2, 1, 2], dtype=np.uint32)
-    ptr = np.array([0, 2, 3, 4, 4], dtype=np.uint32)       # padded to 4 rows
+    k = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))["spmv"]
+    assert k["matrix"] == [[0, 2, 7], [0, 0, 3], [4, 0, 0]] and k["z"] == [1, 2, 3] and k["out"] == [25, 9, 4]
+    data, idx, ptr = [], [], [0]
+    for row in k["matrix"]:
+        for j, v in enumerate(row):
+            if v:
+                data.append(mont(v)); idx.append(j)
+        ptr.append(len(idx))
+    ptr.append(len(idx))                                     # padded to 4 rows
+    data = np.array(data, dtype=np.uint64); idx = np.array(idx, dtype=np.uint32); ptr = np.array(ptr, dtype=np.uint32)
     empty = (np.zeros((0, 4), dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros(5, dtype=np.uint32))
-    # columns: 2 witness vars + the constant one => z = (12, 3 | 1)
+    # columns: 2 witness vars + the constant one => z = (1, 2 | 3)
     S = sp.SplitR1CSShape(ctx, 4, 3, 0, 2, 0, 0, 0, (data, idx, ptr), empty, empty)
-    z = np.array([mont(12), mont(3), mont(1)], dtype=np.uint64)
+    z = np.array([mont(v) for v in k["z"]], dtype=np.uint64)
     az, bz, cz = S.multiply_vec(z)
-    assert az.tolist() == [mont(25), mont(9), mont(4), mont(0)]
+    assert az.tolist() == [mont(v) for v in k["out"]] + [mont(0)]
     assert not bz.any() and not cz.any()
 
 

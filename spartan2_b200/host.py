@@ -415,13 +415,32 @@ class Comm:
         h = C.c_void_p()
         ctx.check(ctx.L.sp2_comm_create(ctx.h, C.c_int32(rank), C.c_int32(nranks), C.byref(h)))
         self.h = h
-        if nranks > 1:
+        if nranks > 1 and allgather_bytes is not None:
             buf = (C.c_uint8 * 64)()
             ctx.check(ctx.L.sp2_comm_handle(self.h, buf))
             handles = allgather_bytes(bytes(buf))
             assert len(handles) == nranks and all(len(x) == 64 for x in handles)
             allb = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
             ctx.check(ctx.L.sp2_comm_connect(self.h, _p(allb)))
+
+    @staticmethod
+    def in_process(ctxs):
+        """One comm per context, all in THIS process (several contexts on one GPU, or on peer-enabled GPUs): the mailboxes are
+        exchanged as raw device pointers (sp2_comm_connect_ptrs), no CUDA IPC.  Rank q = ctxs[q]."""
+        n = len(ctxs)
+        comms = [Comm(c, q, n) for q, c in enumerate(ctxs)]
+        ptrs = (C.c_void_p * n)()
+        for q, cm in enumerate(comms):
+            p = C.c_void_p()
+            cm.ctx.check(cm.ctx.L.sp2_comm_mailbox(cm.h, C.byref(p)))
+            ptrs[q] = p.value
+        for cm in comms:
+            cm.ctx.check(cm.ctx.L.sp2_comm_connect_ptrs(cm.h, ptrs))
+        return comms
+
+    def reset(self):
+        """Collective (every rank, host barrier before and after): flags / epochs back to zero after a failed sharded call."""
+        self.ctx.check(self.ctx.L.sp2_comm_reset(self.h))
 
     def free(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):

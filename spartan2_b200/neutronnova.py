@@ -312,6 +312,19 @@ class NeutronNovaProver:
                 ctx.check(ctx.L.sp2_neutronnova_prep_connect(h, _p(allb)))
         self.h = h
 
+    @staticmethod
+    def connect_in_process(provers):
+        """Ranks living in one process (tests: several contexts on one GPU): the exchange buffers are handed over as raw
+        device pointers (sp2_neutronnova_prep_connect_ptrs) so the bulk exchanges are peer stores, as over CUDA IPC."""
+        n = len(provers)
+        ptrs = (C.c_void_p * n)()
+        for q, pr in enumerate(provers):
+            p = C.c_void_p()
+            pr.ctx.check(pr.ctx.L.sp2_neutronnova_prep_xbuf(pr.h, C.byref(p)))
+            ptrs[q] = p.value
+        for pr in provers:
+            pr.ctx.check(pr.ctx.L.sp2_neutronnova_prep_connect_ptrs(pr.h, ptrs))
+
     def prove(self, ts):
         """ts: spartan2_b200.Keccak256Transcript (advanced in place).  Returns (values, phase_ms)."""
         ctx, S = self.ctx, self.S

@@ -102,10 +102,10 @@ def test_sha256_circuit_prove(ctx, orc):
 
 
 @pytest.mark.parametrize("msg_len", [2048])
-def test_full_size_config_proof_is_accepted_by_the_oracle_verifier(ctx, orc, msg_len):
-    """BASELINE config 2 at full size (2 KiB message, N = M = 2^20): the device-made proof must be accepted by the
-    oracle's restatement of SpartanSNARK::verify (src/spartan.rs:469-578), and rejected after tampering — the
-    size-independent property; bit-level comparison with the oracle prover is done at 2^16 above."""
+def test_full_size_config_proof_is_bit_exact_and_accepted_by_the_oracle_verifier(ctx, orc, msg_len):
+    """BASELINE config 2 at full size (2 KiB message, N = M = 2^20): EVERY field of the device-made proof equals the
+    oracle prover's (same keys, witness and prover randomness; restatement of src/spartan.rs:219-466), the oracle's
+    restatement of SpartanSNARK::verify (src/spartan.rs:469-578) accepts it, and rejects it after tampering."""
     import hashlib
     import spartan2_b200 as sp
     from spartan2_b200.frontend import Sha256Circuit
@@ -128,6 +128,11 @@ def test_full_size_config_proof_is_accepted_by_the_oracle_verifier(ctx, orc, msg
     O = orc.Shape(*circ.dims(), A, B, Cm)
     keys = orc.Keys(ck, h, ck_s, h_s)
     orc.set_threads(orc.max_threads())
+    comm_pre = orc.hyrax_commit(ck, h, W[:cl], blinds[:cr], is_small=True)
+    assert np.array_equal(prep.comm, comm_pre)
+    oproof = orc.spartan_prove(O, keys, vk, X, W, comm_pre, orc.Rand(blinds, be, dv, rd, rb))
+    for f in sp.SpartanProof.FIELDS:
+        assert np.array_equal(getattr(proof, f).reshape(-1), getattr(oproof, f).reshape(-1)), "full-size parity: " + f
     vp = orc.Proof(proof.l, proof.nry, proof.rows, proof.num_cols)
     for f in sp.SpartanProof.FIELDS:
         getattr(vp, f)[...] = getattr(proof, f).reshape(getattr(vp, f).shape)

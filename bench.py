@@ -4,8 +4,14 @@
   python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port, all host threads)
 
-One JSON line on stdout (rank 0).  A "step" is one `prove` (src/spartan.rs:219-466) of sha256_spartan on a 2 KiB
-all-zero message (benches/sha256_spartan.rs:167,200) after prep_prove, as the reference's bench times it (:224-244).
+One JSON line on stdout (rank 0).  A "step" is one `prove` (src/spartan.rs:219-466) of sha256_spartan after prep_prove,
+as the reference's bench times it (benches/sha256_spartan.rs:224-244):
+  --gpus 1   BASELINE config 2: the 2 KiB all-zero message (benches/sha256_spartan.rs:167,200), N = M = 2^20, one GPU;
+  --gpus N>1 BASELINE config 4: ONE proof of the 8 KiB message (N = M = 2^22) with its hypercube sharded across the N
+             GPUs (north_star's partition; "scaling": "strong"), plus BASELINE config 5 (sha256_neutronnova, 256 step
+             circuits, instance-sharded) as the `neutronnova_config5` object.  `--replicas` keeps the old one-proof-per-
+             GPU mode (weak scaling, no data-path exchange).
+The reference arm (`--impl reference`) runs the same config as the CUDA arm at the same --gpus.
 `value` = field-ops/s with the witness and prep state resident in HBM (device timeline of the prove, CUDA events);
 `e2e` = the same prove through the C ABI from HOST buffers, wall clock, copies and host syncs included.
 field-op = one 256-bit modular multiplication-equivalent of the reference's algorithm, MSM work
@@ -129,7 +135,15 @@ class Workload:
                 "phases": ["commit_rest+transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck", "pcs_prove", "ipa_response"]}
 
 
+def default_msg_len(args, world):
+    """--gpus 1: BASELINE config 2 (2 KiB message); --gpus N > 1: config 4 (8 KiB message, N = M = 2^22), sharded."""
+    if args.msg_len:
+        return args.msg_len
+    return 2048 if (world == 1 or args.replicas) else 8192
+
+
 def run_cuda(args):
+    import ctypes as C
     import torch
     import spartan2_b200 as sp
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -138,21 +152,21 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     ctx = sp.Context(local)
-    sharded = bool(args.sharded) and world > 1
-    # replicas (default): every GPU proves its own instance (independent proofs: weak scaling, no data-path exchange);
-    # --sharded: ONE proof, its 2^l hypercube split across the GPUs (strong scaling)
-    wl = Workload(args.msg_len, seed=0xDEADBEEF + (0 if sharded else rank), tail_len=int(ctx.L.sp2_sc_tail_len()))
+    # N > 1: ONE proof, its 2^l hypercube split across the GPUs (strong scaling);
+    # --replicas: every GPU proves its own instance (independent proofs: weak scaling, no data-path exchange)
+    sharded = world > 1 and not args.replicas
+    wl = Workload(default_msg_len(args, world), seed=0xDEADBEEF + (0 if sharded else rank), tail_len=int(ctx.L.sp2_sc_tail_len()))
     hbm_peak, peak_kind = peaks()
     pts = ctx.test_points(WIDTH + 3, seed=7)
     K = sp.CommitmentKey(ctx, pts[:WIDTH], pts[WIDTH:WIDTH + 1], pts[WIDTH + 1:WIDTH + 2], pts[WIDTH + 2:WIDTH + 3])
     comm = None
-    if sharded:
-        import torch.distributed as dist
 
-        def allgather_bytes(b):
-            out = [None] * world
-            dist.all_gather_object(out, b)
-            return out
+    def allgather_bytes(b):
+        import torch.distributed as dist
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+    if sharded:
         comm = sp.Comm(ctx, rank, world, allgather_bytes)
         S = sp.SplitR1CSShape(ctx, *wl.circ.dims(), wl.A, wl.B, wl.C, rank=rank, nranks=world)
     else:
@@ -172,27 +186,26 @@ def run_cuda(args):
             import torch.distributed as dist
             dist.barrier()
 
-    def step():
+    def step(shape, prp, cm):
         ctx.check(ctx.L.sp2_dev_memset(ctx.h, flush.ptr, 0, 512 << 20))   # flush L2 between timed iterations
         ctx.synchronize()
-        if sharded:
+        if cm is not None:
             import torch.distributed as dist
             dist.barrier()
         t0 = time.perf_counter()
-        proof = sp.SpartanSNARK.prove(ctx, S, K, prep, wl.vk, wl.X, W_rest, wl.blinds, wl.blind_eval, wl.d_vec, wl.r_delta, wl.r_beta, comm=comm)
+        proof = sp.SpartanSNARK.prove(ctx, shape, K, prp, wl.vk, wl.X, W_rest, wl.blinds, wl.blind_eval, wl.d_vec, wl.r_delta, wl.r_beta, comm=cm)
         wall = (time.perf_counter() - t0) * 1e3
         return proof, wall
 
     W_ = max(args.warmup, 3)
     for _ in range(W_):
-        step()
+        step(S, prep, comm)
     l0 = ctx.launch_count()
     sampler = ClockSampler(local); sampler.start()
     barrier()
-    import ctypes as C
     dev, wall, phases, persist = [], [], [], []
     for _ in range(args.steps):
-        proof, w = step()
+        proof, w = step(S, prep, comm)
         dev.append(proof.phase_ms["total"]); wall.append(w); phases.append(proof.phase_ms)
         ms = C.c_float()
         if not sharded and ctx.L.sp2_last_cubic_persist_ms(ctx.h, C.byref(ms)) == 0:
@@ -201,13 +214,36 @@ def run_cuda(args):
     clocks = sampler.stop()
     launches = ctx.launch_count() - l0
     ms_dev, ms_wall = float(np.mean(dev)), float(np.mean(wall))
+    ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
+    parity = {}
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms_dev, ms_wall], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([ms_dev, ms_wall] + [ph[k] for k in sorted(ph)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                       # max over ranks, per phase too
         ms_dev, ms_wall = float(t[0]), float(t[1])
+        ph = {k: float(t[2 + i]) for i, k in enumerate(sorted(ph))}
+    single = None
+    if sharded:
+        # every rank must hold the same proof; rank 0 also proves the same instance on ONE GPU (same protocol) for the
+        # strong-scaling reference point and compares the two proofs bit for bit
+        import hashlib
+        blob = hashlib.sha256(b"".join(getattr(proof, f).tobytes() for f in sp.SpartanProof.FIELDS)).hexdigest()
+        parity["all_ranks_identical"] = len(set(allgather_bytes(blob))) == 1
+        prep.free(); S.free()
+        if rank == 0:
+            S1 = sp.SplitR1CSShape(ctx, *wl.circ.dims(), wl.A, wl.B, wl.C)
+            prep1 = sp.SpartanSNARK.prep_prove(ctx, S1, K, wl.W[:wl.cached_len], wl.blinds[:wl.cached_rows], is_small=True)
+            d1, w1, p1s = [], [], []
+            for i in range(3 + max(3, args.steps // 2)):
+                p1, w = step(S1, prep1, None)
+                if i >= 3:
+                    d1.append(p1.phase_ms["total"]); w1.append(w); p1s.append(p1.phase_ms)
+            parity["sharded_equals_single_gpu_proof"] = all(np.array_equal(getattr(proof, f), getattr(p1, f)) for f in sp.SpartanProof.FIELDS)
+            single = {"ms_per_step": float(np.mean(d1)), "e2e_ms_per_step": float(np.mean(w1)),
+                      "phase_ms": {k: float(np.mean([p[k] for p in p1s])) for k in p1s[0]},
+                      "note": "the same instance, keys, randomness and timing protocol on rank 0's GPU alone (strong-scaling reference point)"}
+            prep1.free(); S1.free()
     if rank == 0:
-        ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
         ach_phase = wl.bytes_outer / (ph["outer_sumcheck"] * 1e-3) / 1e9
         traffic = ncu_traffic("k_cubic_persist")
         if persist:
@@ -215,34 +251,53 @@ def run_cuda(args):
             roof = {"bound": "hbm", "kernel": "k_cubic_persist (rounds 1-%d of the outer sum-check, bind fused into the next evaluation, one cooperative launch)" % wl.persist_rounds,
                     "achieved": wl.bytes_persist / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": traffic, "peak_kind": peak_kind,
                     "ms": k_ms, "algorithmic_bytes": wl.bytes_persist, "share_of_step": k_ms / ms_dev,
-                    "note": "latency-bound at N = 2^20: %d rounds, each ending in a grid barrier + serial Keccak finaliser (~17 us) vs ~%.0f us of compulsory streaming; see tables_bench for the same kernel on 2^24-entry tables" % (wl.persist_rounds, wl.bytes_persist / hbm_peak / 1e3)}
+                    "note": "latency-bound at N = 2^20: %d rounds, each ending in a grid barrier + serial Keccak finaliser vs ~%.0f us of compulsory streaming; see tables_bench for the same kernel on 2^24-entry tables" % (wl.persist_rounds, wl.bytes_persist / hbm_peak / 1e3)}
         else:
-            roof = {"bound": "hbm", "kernel": "outer sum-check (all %d rounds)" % proof.l, "achieved": ach_phase, "peak": hbm_peak, "unit": "GB/s",
-                    "traffic": None, "peak_kind": peak_kind, "ms": ph["outer_sumcheck"], "algorithmic_bytes": wl.bytes_outer}
-        roof["frac"] = roof["achieved"] / hbm_peak
-        cfg = wl.describe()
+            # sharded: the outer sum-check is one launch per round on every rank (k_cubic_round, the in-kernel exchange needs the
+            # last-CTA form); the phase is reported against the aggregate HBM bandwidth of the GPUs it runs on
+            roof = {"bound": "hbm", "kernel": "outer sum-check phase (all %d rounds, k_cubic_round per round on each of %d GPUs + gather + tail)" % (proof.l, world),
+                    "achieved": ach_phase, "peak": hbm_peak * world, "unit": "GB/s", "traffic": None, "peak_kind": peak_kind + " x %d GPUs" % world,
+                    "ms": ph["outer_sumcheck"], "algorithmic_bytes": wl.bytes_outer}
+        roof["frac"] = roof["achieved"] / roof["peak"]
         par = "single GPU" if world == 1 else ("one proof, hypercube sharded across %d GPUs (rows/columns i mod %d; per-round sums exchanged in-kernel over NVLink)" % (world, world)
                                                if sharded else "1 proof per GPU (replicas)")
-        cfg.update({"l2": "flushed between timed iterations (512 MiB memset)", "parallelism": par, "prep_prove_ms_untimed": prep_ms})
-        jobs = 1 if sharded else world
+        jobs = 1 if sharded or world == 1 else world
         out = {
             "metric": METRIC, "value": jobs * wl.field_ops / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": W_, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-            "dtype": "u32x8 limbs (256-bit prime field, Montgomery)", "data": "synthetic", "config": cfg,
+            "dtype": "u32x8 limbs (256-bit prime field, Montgomery)", "data": "synthetic", "config": wl.describe(),
+            "protocol": {"l2": "flushed between timed iterations (512 MiB memset)", "parallelism": par, "prep_prove_ms_untimed": prep_ms,
+                         "timing": "CUDA events on the library's stream around one prove, mean of the timed steps, max over ranks"},
             "e2e": {"value": jobs * wl.field_ops / (ms_wall * 1e-3), "unit": UNIT, "ms_per_step": ms_wall,
                     "h2d_bytes_per_step": int(wl.X.nbytes + wl.d_vec.nbytes + wl.blinds.nbytes + 16 * 32 + 64 * 21),
                     "d2h_bytes_per_step": int(sum(getattr(proof, f).nbytes for f in sp.SpartanProof.FIELDS))},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "roofline_phase": {"phase": "outer_sumcheck (k_cubic_init + k_cubic_persist + k_cubic_tail, all %d rounds)" % proof.l, "achieved": ach_phase, "unit": "GB/s",
-                               "frac": ach_phase / hbm_peak, "ms": ph["outer_sumcheck"], "algorithmic_bytes": wl.bytes_outer},
+            "roofline_phase": {"phase": "outer_sumcheck (all %d rounds)" % proof.l, "achieved": ach_phase, "unit": "GB/s",
+                               "frac": ach_phase / (hbm_peak * (world if sharded else 1)), "ms": ph["outer_sumcheck"], "algorithmic_bytes": wl.bytes_outer},
             "phase_ms": ph, "prove_ms": ms_dev, "clocks": clocks,
         }
-        if world == 1 and not args.no_extras:
-            out["tables_bench"] = tables_bench(ctx, sp, hbm_peak)
-            out["neutronnova"] = neutronnova_bench(ctx, sp)
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_prove(wl, pts, threads=1, steps=1, warmup=0)
+        if single is not None:
+            out["single_gpu"] = single
+    else:
+        out = None
+    if world == 1 and not args.no_extras:
+        out["tables_bench"] = tables_bench(ctx, sp, hbm_peak)
+        out["neutronnova"] = neutronnova_bench(ctx, sp)
+    if world == 1 and not args.no_cpu_baseline:
+        # the oracle port, one thread, on the full workload; its proof is compared with the device's bit for bit
+        cb, oproof = cpu_prove(wl, pts, threads=1, steps=1, warmup=0, want_proof=True)
+        parity["fields_compared"] = len(sp.SpartanProof.FIELDS)
+        parity["bit_exact_vs_oracle_prover"] = all(np.array_equal(getattr(proof, f).reshape(-1), getattr(oproof, f).reshape(-1)) for f in sp.SpartanProof.FIELDS)
+        out["cpu_baseline"] = cb
+        if not args.no_extras:
+            out["cpu_baseline_config1"] = cpu_prove(Workload(1024), pts, threads=1, steps=1, warmup=0)
+    if sharded and not args.no_extras:
+        nn5 = neutronnova_sharded_bench(ctx, sp, comm, rank, world, local, allgather_bytes, n=256)
+        if rank == 0:
+            out["neutronnova_config5"] = nn5
+    if rank == 0:
+        out["parity"] = parity
         print(json.dumps(out), flush=True)
     if comm is not None:
         comm.free()
@@ -250,6 +305,64 @@ def run_cuda(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def neutronnova_sharded_bench(ctx, sp, comm, rank, world, local, allgather_bytes, n=256):
+    """BASELINE config 5: sha256_neutronnova with n = 256 step circuits, the instances sharded across the GPUs
+    (sp2_neutronnova_prep_prove_sharded / _prove_sharded: local NIFS rounds, per-round sums and bulk exchanges over NVLink
+    peer memory); wall clock of the C-ABI call, max over ranks; rank 0 also runs all n instances on one GPU."""
+    import torch
+    import torch.distributed as dist
+    from spartan2_b200 import neutronnova as nn
+    from spartan2_b200 import _fq as fq
+    from spartan2_b200.frontend import Sha256Circuit
+    one = fq.from_int(1); dev = torch.device("cuda", local)
+    nl = n // world
+
+    def z_of(c):
+        W, X = c.witness()
+        return np.concatenate([W, one, X], axis=0)
+    core = Sha256Circuit(bytes(64), kind="compression")
+    A, B, Cm = core.matrices()
+    S = sp.SplitR1CSShape(ctx, *core.dims(), A, B, Cm)
+    mine = [z_of(Sha256Circuit(bytes([i % 256]) * 64, kind="compression")) for i in range(rank * nl, (rank + 1) * nl)]
+    t0 = time.perf_counter()
+    prover = nn.NeutronNovaProver(ctx, S, mine, z_of(core), rank=rank, nranks=world, allgather=nn.torch_allgather(world, dev), comm=comm,
+                                  allgather_bytes=allgather_bytes)
+    ctx.synchronize(); prep_ms = (time.perf_counter() - t0) * 1e3
+    walls, phs = [], []
+    for it in range(8):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v, ph = prover.prove(sp.Keccak256Transcript(b"neutronnova_prove"))
+        if it >= 3:
+            walls.append((time.perf_counter() - t0) * 1e3); phs.append(ph)
+    t = torch.tensor([float(np.mean(walls))] + [float(np.mean([p[k] for p in phs])) for k in sorted(phs[0])], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    import hashlib
+    keys = sorted(k for k in v if isinstance(v[k], np.ndarray))
+    blob = hashlib.sha256(b"".join(np.ascontiguousarray(v[k]).tobytes() for k in keys)).hexdigest()
+    same = len(set(allgather_bytes(blob))) == 1
+    out = None
+    prover.free()
+    if rank == 0:
+        allz = [z_of(Sha256Circuit(bytes([i % 256]) * 64, kind="compression")) for i in range(n)]
+        single = nn.NeutronNovaProver(ctx, S, allz, z_of(core))
+        w1, p1 = [], []
+        for it in range(6):
+            t0 = time.perf_counter()
+            v1, ph1 = single.prove(sp.Keccak256Transcript(b"neutronnova_prove"))
+            if it >= 3:
+                w1.append((time.perf_counter() - t0) * 1e3); p1.append(ph1)
+        eq = all(np.array_equal(v[k], v1[k]) for k in keys) and bool(v["outer_ok"] and v["inner_ok"])
+        single.free()
+        out = {"workload": "sha256_neutronnova_%d_steps (N = M = 2^15 per instance), %d instances per GPU" % (n, nl), "prove_ms": float(t[0]),
+               "phase_ms": {k: float(t[1 + i]) for i, k in enumerate(sorted(phs[0]))}, "prep_prove_ms_untimed": prep_ms,
+               "single_gpu": {"prove_ms": float(np.mean(w1)), "phase_ms": {k: float(np.mean([p[k] for p in p1])) for k in p1[0]}},
+               "parity": {"all_ranks_identical": same, "sharded_equals_single_gpu": eq},
+               "timing": "host wall clock of the C-ABI call (every phase ends in a host wait), mean of 5 after 3 warm-ups, max over ranks"}
+    S.free()
+    return out
 
 
 def ncu_traffic(kernel):
@@ -338,7 +451,7 @@ def neutronnova_bench(ctx, sp, n=32):
             "challenges": "transcript-derived (non-ZK); the reference's in-circuit verifier (process_round) is out of scope"}
 
 
-def cpu_prove(wl, pts, threads, steps, warmup):
+def cpu_prove(wl, pts, threads, steps, warmup, want_proof=False):
     """The oracle port of the reference's prover on the same workload (oracle/oracle.c, -march=native)."""
     from oracle import pyoracle as orc
     orc.lib(native=True)
@@ -354,7 +467,23 @@ def cpu_prove(wl, pts, threads, steps, warmup):
         if i >= warmup:
             times.append((time.perf_counter() - t0) * 1e3); ph = p.phase_ms
     ms = float(np.mean(times))
-    return {"value": wl.field_ops / (ms * 1e-3), "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": ms,
+    res = _cpu_result(wl, ms, threads, steps, ph)
+    return (res, p) if want_proof else res
+
+
+def host_cpu():
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip(); break
+    except OSError:
+        pass
+    return {"model": model, "nproc": os.cpu_count()}
+
+
+def _cpu_result(wl, ms, threads, steps, ph):
+    return {"value": wl.field_ops / (ms * 1e-3), "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": ms, "host": host_cpu(),
             "phase_ms": dict(zip(["commit_rest+transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck", "pcs_prove"], ph)),
             "sample": "full workload %s, %d prove(s); oracle/oracle.c = C restatement of the reference's rayon prover (no Rust toolchain), OpenMP %d thread(s)" % (wl.name, steps, threads)}
 
@@ -378,14 +507,15 @@ def run_reference(args):
     from oracle import pyoracle as orc
     orc.lib(native=True)
     threads = orc.max_threads()
-    wl = Workload(args.msg_len)
+    wl = Workload(default_msg_len(args, args.gpus))          # the CUDA arm's config at this --gpus
     pts = oracle_points(orc, WIDTH + 3)
     r = cpu_prove(wl, pts, threads, args.steps, args.warmup)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "reference_kind": "oracle_port (oracle/oracle.c: C/OpenMP restatement of the reference's rayon prover; the Rust crate cannot be built in this image)",
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong" if (args.gpus > 1 and not args.replicas) else "weak", "vs_baseline": None,
         "dtype": "u64x4 limbs (256-bit prime field, Montgomery)", "data": "synthetic", "config": wl.describe(), "phase_ms": r["phase_ms"],
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"], "host": r["host"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -396,10 +526,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--msg-len", type=int, default=2048, help="SHA-256 message bytes (BASELINE config 2: 2048; config 1: 1024)")
+    ap.add_argument("--msg-len", type=int, default=0, help="SHA-256 message bytes (default: 2048 = BASELINE config 2 at --gpus 1, 8192 = config 4 at --gpus N > 1; config 1: 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the 2^24 pure-table sum-check leg and the config-3 NeutronNova leg (N = 1 only)")
-    ap.add_argument("--sharded", action="store_true", help="N > 1: one proof with its hypercube sharded across the GPUs (strong scaling) instead of one proof per GPU")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: one independent proof per GPU (weak scaling) instead of ONE proof sharded across the GPUs (the default)")
+    ap.add_argument("--sharded", action="store_true", help="(default for N > 1; kept for compatibility)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1287,3 +1287,384 @@ EXPORT void orc_nifs_cvals_small(size_t left, size_t right, const fe *E, const f
     for (size_t b = 0; b < n; b++) { fe t; f_mul(&FQ, &t, &ef, &Cl[b * N + k]); f_add(&FQ, &vals[b], &vals[b], &t); }
   }
 }
+
+/* ------------------------------------------------------------------------------------
+ * Hyrax commitment family on group elements: commit_without_blind / commit_incremental (hyrax_pc.rs:533-607),
+ * rerandomize_commitment (:321-344), fold_blinds (:795-819), fold_commitments_partial (:821-874)
+ * ---------------------------------------------------------------------------------- */
+/* commit_without_blind (hyrax_pc.rs:533-567): raw row points, identity (0,0) for an all-zero row */
+EXPORT void orc_hyrax_commit_without_blind(const apt *ck, size_t num_cols, const fe *v, size_t n, int is_small, apt *out) {
+  size_t rows = (n + num_cols - 1) / num_cols;
+#pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1)
+  for (size_t i = 0; i < rows; i++) {
+    size_t lo = i * num_cols, hi = lo + num_cols < n ? lo + num_cols : n, len = hi - lo;
+    const fe *s = v + lo; pt acc; int all_zero = 1;
+    for (size_t j = 0; j < len; j++) if (!f_is_zero(&s[j])) { all_zero = 0; break; }
+    if (all_zero) { f_zero(&out[i].x); f_zero(&out[i].y); continue; }
+    if (is_small) {
+      uint64_t *sm = (uint64_t *)malloc(len * 8);
+      for (size_t j = 0; j < len; j++) { uint64_t raw[4]; f_to_raw(&FQ, raw, &s[j]); sm[j] = raw[0]; }
+      msm_small_serial(sm, ck, len, &acc); free(sm);
+    } else msm(s, ck, len, 0, &acc);
+    pt_to_affine(&CV, &out[i], &acc);
+  }
+}
+/* commit_incremental (hyrax_pc.rs:569-607): raw[i] + <delta_row_i, ck> + blind_i * h */
+EXPORT void orc_hyrax_commit_incremental(const apt *ck, size_t num_cols, const apt *h, const apt *raw, size_t n_raw, const fe *delta, size_t n,
+                                         const fe *blinds, apt *out) {
+  size_t rows = (n + num_cols - 1) / num_cols;
+#pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1)
+  for (size_t i = 0; i < rows; i++) {
+    size_t lo = i * num_cols, hi = lo + num_cols < n ? lo + num_cols : n, len = hi - lo;
+    const fe *s = delta + lo; pt acc, hb; int all_zero = 1;
+    for (size_t j = 0; j < len; j++) if (!f_is_zero(&s[j])) { all_zero = 0; break; }
+    if (i < n_raw) pt_from_affine(&CV, &acc, &raw[i]); else pt_set_inf(&CV, &acc);
+    if (!all_zero) { pt d; msm(s, ck, len, 0, &d); pt_add(&CV, &acc, &acc, &d); }
+    pt_mul_fe(&hb, h, &blinds[i]); pt_add(&CV, &acc, &acc, &hb);
+    pt_to_affine(&CV, &out[i], &acc);
+  }
+}
+/* rerandomize_commitment (hyrax_pc.rs:321-344): comm[i] + (r_new[i] - r_old[i]) * h */
+EXPORT void orc_hyrax_rerandomize(const apt *h, const apt *comm, const fe *r_old, const fe *r_new, size_t rows, apt *out) {
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+  for (size_t i = 0; i < rows; i++) {
+    fe d; f_sub(&FQ, &d, &r_new[i], &r_old[i]);
+    pt a, hb; pt_from_affine(&CV, &a, &comm[i]); pt_mul_fe(&hb, h, &d); pt_add(&CV, &a, &a, &hb);
+    pt_to_affine(&CV, &out[i], &a);
+  }
+}
+/* fold_blinds (hyrax_pc.rs:795-819): out[row] = sum_k w_k * blinds[k][row] */
+EXPORT void orc_fold_blinds(const fe *blinds, size_t n, size_t rows, const fe *w, fe *out) {
+  for (size_t r = 0; r < rows; r++) {
+    fe acc; f_zero(&acc);
+    for (size_t k = 0; k < n; k++) { fe t; f_mul(&FQ, &t, &blinds[k * rows + r], &w[k]); f_add(&FQ, &acc, &acc, &t); }
+    out[r] = acc;
+  }
+}
+/* fold_commitments_partial (hyrax_pc.rs:821-874): MSM-fold the data rows, rest rows = folded_blind[row] * h */
+EXPORT void orc_fold_commitments_partial(const apt *comms, size_t n, size_t rows, const fe *w, size_t num_data_rows, const fe *folded_blind,
+                                         const apt *h, apt *out) {
+  if (num_data_rows >= rows) { orc_fold_commitments(comms, n, rows, w, out); return; }
+#pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1)
+  for (size_t r = 0; r < rows; r++) {
+    pt acc; pt_set_inf(&CV, &acc);
+    if (r < num_data_rows) for (size_t i = 0; i < n; i++) { pt t; pt_mul_fe(&t, &comms[i * rows + r], &w[i]); pt_add(&CV, &acc, &acc, &t); }
+    else pt_mul_fe(&acc, h, &folded_blind[r]);
+    pt_to_affine(&CV, &out[r], &acc);
+  }
+}
+
+/* ------------------------------------------------------------------------------------
+ * NeutronNova, NON-ZK variant: NeutronNovaZkSNARK::{prove, verify} (neutronnova_zk.rs:1609-2093, 2096-2330) with the ZK
+ * wrapper removed.  The data path, the per-round scalar algebra, the instance / witness / commitment folds and the
+ * closing PCS::prove are the reference's; what differs is WHERE the challenges come from: the reference commits every
+ * round message inside its in-circuit verifier (process_round, bellpepper/r1cs.rs:735-816: out of scope) and
+ * squeezes after that commitment; here the round polynomials are absorbed directly (b"p", all coefficients as scalars)
+ * and the challenge squeezed (b"c"), as the non-ZK SpartanSNARK does (sumcheck.rs:536-548), eval_W_{step,core} are
+ * revealed with their blinds (as SpartanSNARK reveals eval_W, spartan.rs:126-139) and their commitments absorbed before
+ * c_eval.  The verifier below checks exactly what NeutronNovaVerifierCircuit (zk.rs:600-940) + verify (:2096-2330) check.
+ * Requires num_shared == 0 and num_challenges == 0 (the SHA-256 chain of benches/sha256_neutronnova.rs).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  uint64_t n_steps, ell_b, ell, rounds_y, rows, num_cols;
+  apt *comm_W_steps;       /* n_steps * rows : U_i.comm_W (precommitted rows rerandomised, rest rows = blind * h) */
+  apt *comm_W_core;        /* rows */
+  fe *nifs_polys;          /* ell_b * 4 */
+  fe *outer_polys;         /* ell * 8 : step | core cubic per round */
+  fe *claims_outer;        /* 6 */
+  fe *inner_polys;         /* rounds_y * 6 : step | core quadratic per round */
+  fe *eval_W, *blind_eval_W;   /* 2 each: step, core */
+  apt *delta, *beta; fe *z_vec; fe *z_delta, *z_beta;
+} nn_proof_view;
+typedef struct {
+  const fe *blinds_steps;  /* n_steps * rows: the blinds of U_i.comm_W (fresh per prove: rerandomisation + rest rows) */
+  const fe *blinds_core;   /* rows */
+  const fe *blind_eval_W;  /* 2 */
+  const fe *d_vec, *r_delta, *r_beta;
+} nn_rand_view;
+
+static void nn_absorb_instance(transcript *ts, const char *label, const apt *comm, size_t rows, const fe *X, size_t nx) {
+  /* R1CSInstance::to_transcript_bytes (r1cs/mod.rs:728-736): comm_W bytes then X */
+  ts_push(ts, label, strlen(label));
+  ts_push(ts, "poly_commitment_begin", 21);
+  for (size_t i = 0; i < rows; i++) { uint8_t b[64]; apt_to_bytes(&comm[i], b); ts_push(ts, b, 64); }
+  ts_push(ts, "poly_commitment_end", 19);
+  for (size_t i = 0; i < nx; i++) { uint8_t b[32]; fe_to_be_bytes(&FQ, &X[i], b); ts_push(ts, b, 32); }
+}
+static void nn_pow_eval(const fe *tau, const fe *rx, size_t ell, fe *out) {
+  /* PowPolynomial::evaluate (polys/power.rs): prod_i (1 + (tau^(2^(ell-1-i)) - 1) r_i), first challenge = top variable */
+  fe *tp = (fe *)malloc((ell + 1) * sizeof(fe)); tp[0] = *tau;
+  for (size_t k = 1; k <= ell; k++) f_sqr(&FQ, &tp[k], &tp[k - 1]);
+  fe one, acc, t; f_one(&FQ, &one); acc = one;
+  for (size_t i = 0; i < ell; i++) { f_sub(&FQ, &t, &tp[ell - 1 - i], &one); f_mul(&FQ, &t, &t, &rx[i]); f_add(&FQ, &t, &t, &one); f_mul(&FQ, &acc, &acc, &t); }
+  *out = acc; free(tp);
+}
+
+/* zs: n * num_cols (z_i = [W_i | 1 | X_i]); zc: num_cols.  comm_pre_*: the PrecommittedState commitments of prep_prove
+ * (pre_rows per instance) with their blinds.  debug (optional, 8 fe): T_out, tau_at_rx, r, c_eval, eq_rho_at_rb.
+ * phase_ms (optional, 8 doubles): rerandomize+commit_zeros, transcript absorb, NIFS, fold (witness, blinds, instances),
+ * outer, poly_ABC, inner, pcs. */
+EXPORT int orc_neutronnova_prove(const shape *S, const keys_view *K, const uint8_t vk_digest[32], size_t n, const fe *zs, const fe *zc,
+                                 const apt *comm_pre_steps, const fe *blinds_pre_steps, const apt *comm_pre_core, const fe *blinds_pre_core,
+                                 const nn_rand_view *R, nn_proof_view *P, fe *debug, double *phase_ms) {
+  double t_last = 0; (void)t_last;
+#ifdef _OPENMP
+  t_last = omp_get_wtime();
+#endif
+  if (S->num_shared || S->num_challenges) return -7;
+  const size_t N = S->num_cons, M = S->num_vars, ncols = S->num_vars + 1 + S->num_public, width = K->num_cols;
+  const size_t rows = M / width, pre_rows = S->num_precommitted / width, np = S->num_public;
+  size_t ell_b = 0; while (((size_t)1 << ell_b) < n) ell_b++;
+  size_t ell = 0; while (((size_t)1 << ell) < N) ell++;
+  size_t my = 0; while (((size_t)1 << my) < 2 * M) my++;
+  const size_t left = (size_t)1 << ((ell + 1) / 2), right = (size_t)1 << (ell / 2);
+  if (((size_t)1 << ell_b) != n || n < 2) return -2;
+  P->n_steps = n; P->ell_b = ell_b; P->ell = ell; P->rounds_y = my; P->rows = rows; P->num_cols = width;
+  fe one, zero; f_one(&FQ, &one); f_zero(&zero);
+  /* rerandomize_in_place (bellpepper/r1cs.rs:568-602 -> hyrax_pc.rs:321-344) + commit_zeros of the rest rows (r1cs.rs:467-470) */
+  for (size_t i = 0; i <= n; i++) {
+    const apt *cp = i < n ? comm_pre_steps + i * pre_rows : comm_pre_core;
+    const fe *bo = i < n ? blinds_pre_steps + i * pre_rows : blinds_pre_core;
+    const fe *bn = i < n ? R->blinds_steps + i * rows : R->blinds_core;
+    apt *out = i < n ? P->comm_W_steps + i * rows : P->comm_W_core;
+    orc_hyrax_rerandomize(K->h, cp, bo, bn, pre_rows, out);
+    for (size_t r = pre_rows; r < rows; r++) { pt hb; pt_mul_fe(&hb, K->h, &bn[r]); pt_to_affine(&CV, &out[r], &hb); }
+  }
+  TICK(0);
+  transcript ts; ts_new(&ts, "neutronnova_prove");
+  ts_absorb_bytes(&ts, "vk", vk_digest, 32);
+  nn_absorb_instance(&ts, "core_instance", P->comm_W_core, rows, zc + M + 1, np);
+  for (size_t i = 0; i < n; i++) nn_absorb_instance(&ts, "U", P->comm_W_steps + i * rows, rows, zs + i * ncols + M + 1, np);
+  ts_absorb_scalars(&ts, &FQ, "T", &zero, 1);
+  fe tau; ts_squeeze(&ts, &FQ, "tau", &tau);
+  fe *E = (fe *)malloc((left + right) * sizeof(fe)); orc_pow_split_evals(&tau, left, right, E);
+  fe *rhos = (fe *)malloc((ell_b + 1) * sizeof(fe));
+  for (size_t t = 0; t < ell_b; t++) ts_squeeze(&ts, &FQ, "rho", &rhos[t]);
+  TICK(1);
+  /* layers (prep_prove's cached matvec, neutronnova_zk.rs:1538-1549) */
+  fe *A = (fe *)malloc(n * N * sizeof(fe)), *B = (fe *)malloc(n * N * sizeof(fe)), *Cm = (fe *)malloc(n * N * sizeof(fe));
+  for (size_t i = 0; i < n; i++) orc_shape_multiply_vec(S, zs + i * ncols, A + i * N, B + i * N, Cm + i * N);
+  fe *Ac = (fe *)malloc(N * sizeof(fe)), *Bc = (fe *)malloc(N * sizeof(fe)), *Cc = (fe *)malloc(N * sizeof(fe));
+  orc_shape_multiply_vec(S, zc, Ac, Bc, Cc);
+#ifdef _OPENMP
+  t_last = omp_get_wtime();                                  /* the matvec is prep_prove work: untimed */
+#endif
+  /* HOT LOOP A: NIFS rounds (neutronnova_zk.rs:778-1168), finish_round! (:703-735) */
+  fe T_cur = zero, acc_eq = one, *r_b = (fe *)malloc((ell_b + 1) * sizeof(fe));
+  size_t m = n;
+  for (size_t t = 0; t < ell_b; t++) {
+    fe e0q[2]; orc_nifs_round(t, ell_b, rhos, left, right, E, A, B, Cm, N, m, e0q);
+    fe rho = rhos[t], omr, trm, c, a, abc, b, rinv, tmp, tmp2, co[4];
+    f_sub(&FQ, &omr, &one, &rho); f_sub(&FQ, &trm, &rho, &omr);
+    f_mul(&FQ, &c, &e0q[0], &acc_eq); f_mul(&FQ, &a, &e0q[1], &acc_eq);
+    if (!f_inv(&FQ, &rinv, &rho)) return -5;
+    f_mul(&FQ, &tmp, &c, &omr); f_sub(&FQ, &tmp, &T_cur, &tmp); f_mul(&FQ, &abc, &tmp, &rinv);
+    f_sub(&FQ, &b, &abc, &a); f_sub(&FQ, &b, &b, &c);
+    f_mul(&FQ, &co[0], &c, &omr);
+    f_mul(&FQ, &tmp, &c, &trm); f_mul(&FQ, &tmp2, &b, &omr); f_add(&FQ, &co[1], &tmp, &tmp2);
+    f_mul(&FQ, &tmp, &b, &trm); f_mul(&FQ, &tmp2, &a, &omr); f_add(&FQ, &co[2], &tmp, &tmp2);
+    f_mul(&FQ, &co[3], &a, &trm);
+    memcpy(&P->nifs_polys[4 * t], co, sizeof(co));
+    ts_absorb_scalars(&ts, &FQ, "p", co, 4);
+    ts_squeeze(&ts, &FQ, "c", &r_b[t]);
+    f_sub(&FQ, &tmp, &one, &r_b[t]); f_mul(&FQ, &tmp, &tmp, &omr); f_mul(&FQ, &tmp2, &r_b[t], &rho); f_add(&FQ, &tmp, &tmp, &tmp2);
+    f_mul(&FQ, &acc_eq, &acc_eq, &tmp);
+    unipoly_eval(co, 4, &r_b[t], &T_cur);
+    orc_nifs_fold(A, N, m, &r_b[t]); orc_nifs_fold(B, N, m, &r_b[t]); orc_nifs_fold(Cm, N, m, &r_b[t]);
+    m /= 2;
+  }
+  fe T_out, ainv; if (!f_inv(&FQ, &ainv, &acc_eq)) return -5;
+  f_mul(&FQ, &T_out, &T_cur, &ainv);
+  TICK(2);
+  /* fold_multiple (r1cs/mod.rs:570-660), fold_blinds, X fold, fold_commitments_partial (neutronnova_zk.rs:1212-1262) */
+  fe *w = (fe *)malloc(n * sizeof(fe)); orc_weights_from_r(r_b, ell_b, n, w);
+  fe *Wf = (fe *)calloc(2 * M, sizeof(fe)), *Wc = (fe *)calloc(2 * M, sizeof(fe));     /* z tables of the inner sum-check */
+  for (size_t j = 0; j < M; j++) { acc9 a; memset(&a, 0, sizeof(a)); for (size_t i = 0; i < n; i++) f_mul_acc(&a, &w[i], &zs[i * ncols + j]); f_reduce9(&FQ, &Wf[j], &a); }
+  fe *blind_fold = (fe *)malloc(rows * sizeof(fe)); orc_fold_blinds(R->blinds_steps, n, rows, w, blind_fold);
+  fe *X_acc = (fe *)calloc(np + 1, sizeof(fe));
+  for (size_t i = 0; i < n; i++) for (size_t j = 0; j < np; j++) { fe t; f_mul(&FQ, &t, &w[i], &zs[i * ncols + M + 1 + j]); f_add(&FQ, &X_acc[j], &X_acc[j], &t); }
+  apt *comm_fold = (apt *)malloc(rows * sizeof(apt));
+  orc_fold_commitments_partial(P->comm_W_steps, n, rows, w, pre_rows, blind_fold, K->h, comm_fold);
+  Wf[M] = one; memcpy(&Wf[M + 1], X_acc, np * sizeof(fe));
+  memcpy(Wc, zc, M * sizeof(fe)); Wc[M] = one; memcpy(&Wc[M + 1], zc + M + 1, np * sizeof(fe));
+  fe *W_fold = (fe *)malloc(M * sizeof(fe)); memcpy(W_fold, Wf, M * sizeof(fe));
+  TICK(3);
+  /* HOT LOOP B: prove_cubic_with_additive_term_batched (sumcheck.rs:786-917) */
+  fe *tau_pow = (fe *)malloc((ell + 1) * sizeof(fe)); tau_pow[0] = tau;
+  for (size_t k = 1; k <= ell; k++) f_sqr(&FQ, &tau_pow[k], &tau_pow[k - 1]);
+  fe base_tau = one, claim_s = T_out, claim_c = zero, *r_x = (fe *)malloc(ell * sizeof(fe));
+  size_t tl = N;
+  for (size_t i = 0; i < ell; i++) {
+    fe ev[6], evl[8], co[8], tmp;
+    orc_pow_cubic_eval(E, left, E + left, A, B, Cm, tl, ev); orc_pow_cubic_eval(E, left, E + left, Ac, Bc, Cc, tl, ev + 3);
+    for (int k = 0; k < 6; k++) f_mul(&FQ, &ev[k], &ev[k], &base_tau);
+    evl[0] = ev[0]; f_sub(&FQ, &evl[1], &claim_s, &ev[0]); evl[2] = ev[1]; evl[3] = ev[2];
+    evl[4] = ev[3]; f_sub(&FQ, &evl[5], &claim_c, &ev[3]); evl[6] = ev[4]; evl[7] = ev[5];
+    unipoly_from_evals_deg3(evl, co); unipoly_from_evals_deg3(evl + 4, co + 4);
+    memcpy(&P->outer_polys[8 * i], co, sizeof(co));
+    ts_absorb_scalars(&ts, &FQ, "p", co, 8);
+    ts_squeeze(&ts, &FQ, "c", &r_x[i]);
+    unipoly_eval(co, 4, &r_x[i], &claim_s); unipoly_eval(co + 4, 4, &r_x[i], &claim_c);
+    bind_top(A, tl, &r_x[i]); bind_top(B, tl, &r_x[i]); bind_top(Cm, tl, &r_x[i]);
+    bind_top(Ac, tl, &r_x[i]); bind_top(Bc, tl, &r_x[i]); bind_top(Cc, tl, &r_x[i]);
+    tl /= 2;
+    f_sub(&FQ, &tmp, &tau_pow[ell - 1 - i], &one); f_mul(&FQ, &tmp, &tmp, &r_x[i]); f_add(&FQ, &tmp, &tmp, &one);
+    f_mul(&FQ, &base_tau, &base_tau, &tmp);
+  }
+  fe cl[6] = { A[0], B[0], Cm[0], Ac[0], Bc[0], Cc[0] };
+  memcpy(P->claims_outer, cl, sizeof(cl));
+  TICK(4);
+  ts_absorb_scalars(&ts, &FQ, "claims_outer", cl, 6);
+  fe r, r2, claim_js, claim_jc, t1; ts_squeeze(&ts, &FQ, "r", &r); f_sqr(&FQ, &r2, &r);
+  f_mul(&FQ, &t1, &r, &cl[1]); f_add(&FQ, &claim_js, &cl[0], &t1); f_mul(&FQ, &t1, &r2, &cl[2]); f_add(&FQ, &claim_js, &claim_js, &t1);
+  f_mul(&FQ, &t1, &r, &cl[4]); f_add(&FQ, &claim_jc, &cl[3], &t1); f_mul(&FQ, &t1, &r2, &cl[5]); f_add(&FQ, &claim_jc, &claim_jc, &t1);
+  fe *rx = (fe *)malloc(N * sizeof(fe)); eq_evals(r_x, ell, rx);
+  fe *abc_s = (fe *)malloc(2 * M * sizeof(fe)), *abc_c = (fe *)malloc(2 * M * sizeof(fe));
+  orc_shape_abc(S, rx, &r, abc_s, 2 * M); orc_shape_abc(S, rx, &r, abc_c, 2 * M);
+  TICK(5);
+  /* HOT LOOP C: prove_quad_batched (sumcheck.rs:702-782) */
+  fe *r_y = (fe *)malloc(my * sizeof(fe));
+  tl = 2 * M;
+  for (size_t j = 0; j < my; j++) {
+    fe e[4], co[6];
+    quad_points(abc_s, Wf, tl, &e[0], &e[1]); quad_points(abc_c, Wc, tl, &e[2], &e[3]);
+    quad_round_poly(&e[0], &e[1], &claim_js, co); quad_round_poly(&e[2], &e[3], &claim_jc, co + 3);
+    memcpy(&P->inner_polys[6 * j], co, sizeof(co));
+    ts_absorb_scalars(&ts, &FQ, "p", co, 6);
+    ts_squeeze(&ts, &FQ, "c", &r_y[j]);
+    bind_top(abc_s, tl, &r_y[j]); bind_top(Wf, tl, &r_y[j]); bind_top(abc_c, tl, &r_y[j]); bind_top(Wc, tl, &r_y[j]);
+    tl /= 2;
+    unipoly_eval(co, 3, &r_y[j], &claim_js); unipoly_eval(co + 3, 3, &r_y[j], &claim_jc);
+  }
+  /* eval_W (neutronnova_zk.rs:1930-1951) */
+  fe *Xs = (fe *)malloc((np + 1) * sizeof(fe)), *Xc = (fe *)malloc((np + 1) * sizeof(fe));
+  Xs[0] = one; memcpy(&Xs[1], X_acc, np * sizeof(fe)); Xc[0] = one; memcpy(&Xc[1], zc + M + 1, np * sizeof(fe));
+  fe eXs, eXc, den, dinv; sparse_poly_eval(my - 1, Xs, np + 1, r_y + 1, &eXs); sparse_poly_eval(my - 1, Xc, np + 1, r_y + 1, &eXc);
+  f_sub(&FQ, &den, &one, &r_y[0]); if (!f_inv(&FQ, &dinv, &den)) return -5;
+  f_mul(&FQ, &t1, &r_y[0], &eXs); f_sub(&FQ, &P->eval_W[0], &Wf[0], &t1); f_mul(&FQ, &P->eval_W[0], &P->eval_W[0], &dinv);
+  f_mul(&FQ, &t1, &r_y[0], &eXc); f_sub(&FQ, &P->eval_W[1], &Wc[0], &t1); f_mul(&FQ, &P->eval_W[1], &P->eval_W[1], &dinv);
+  P->blind_eval_W[0] = R->blind_eval_W[0]; P->blind_eval_W[1] = R->blind_eval_W[1];
+  TICK(6);
+  /* commitments to the two evaluations (the reference's per-round commits of eval_W_step / eval_W_core), c_eval, folds
+   * (neutronnova_zk.rs:2019-2051), PCS::prove (:2053-2064) */
+  apt ce[2];
+  for (int b = 0; b < 2; b++) { pt a, hb; pt_mul_fe(&a, K->ck_s, &P->eval_W[b]); pt_mul_fe(&hb, K->h_s, &R->blind_eval_W[b]); pt_add(&CV, &a, &a, &hb); pt_to_affine(&CV, &ce[b], &a); }
+  ts_absorb_point(&ts, "comm_eval_W_step", &ce[0]); ts_absorb_point(&ts, "comm_eval_W_core", &ce[1]);
+  fe c_eval; ts_squeeze(&ts, &FQ, "c_eval", &c_eval);
+  fe wts[2] = { one, c_eval };
+  apt *pair = (apt *)malloc(2 * rows * sizeof(apt)), *comm = (apt *)malloc(rows * sizeof(apt));
+  memcpy(pair, comm_fold, rows * sizeof(apt)); memcpy(pair + rows, P->comm_W_core, rows * sizeof(apt));
+  orc_fold_commitments(pair, 2, rows, wts, comm);
+  fe *blind = (fe *)malloc(rows * sizeof(fe));
+  for (size_t i = 0; i < rows; i++) { f_mul(&FQ, &t1, &c_eval, &R->blinds_core[i]); f_add(&FQ, &blind[i], &blind_fold[i], &t1); }
+  fe *Wfin = (fe *)malloc(M * sizeof(fe));
+  for (size_t j = 0; j < M; j++) { f_mul(&FQ, &t1, &c_eval, &zc[j]); f_add(&FQ, &Wfin[j], &W_fold[j], &t1); }
+  apt comm_eval; orc_fold_commitments(ce, 2, 1, wts, &comm_eval);
+  fe blind_eval; f_mul(&FQ, &t1, &c_eval, &R->blind_eval_W[1]); f_add(&FQ, &blind_eval, &R->blind_eval_W[0], &t1);
+  rand_view RV = { blind, &blind_eval, R->d_vec, R->r_delta, R->r_beta };
+  proof_view PV; memset(&PV, 0, sizeof(PV)); PV.delta = P->delta; PV.beta = P->beta; PV.z_vec = P->z_vec; PV.z_delta = P->z_delta; PV.z_beta = P->z_beta;
+  hyrax_prove(K, &ts, comm, rows, Wfin, M, blind, r_y + 1, my - 1, &comm_eval, &RV, &PV, NULL);
+  TICK(7);
+  if (debug) { debug[0] = T_out; debug[1] = base_tau; debug[2] = r; debug[3] = c_eval; debug[4] = acc_eq; debug[5] = eXs; debug[6] = eXc; }
+  free(E); free(rhos); free(A); free(B); free(Cm); free(Ac); free(Bc); free(Cc); free(r_b); free(w); free(Wf); free(Wc); free(blind_fold);
+  free(X_acc); free(comm_fold); free(W_fold); free(tau_pow); free(r_x); free(rx); free(abc_s); free(abc_c); free(r_y); free(Xs); free(Xc);
+  free(pair); free(comm); free(blind); free(Wfin);
+  ts_free(&ts);
+  return 0;
+}
+
+/* step_X: n * num_public public IO of the step instances; core_X: num_public.  0 = accept; negative = the failing check:
+ * -2 NIFS round / final, -3 outer rounds / final, -4 inner rounds / final (matrix evaluations), -5 PCS. */
+EXPORT int orc_neutronnova_verify(const shape *S, const keys_view *K, const uint8_t vk_digest[32], const fe *step_X, const fe *core_X,
+                                  const nn_proof_view *P) {
+  if (S->num_shared || S->num_challenges) return -7;
+  const size_t N = S->num_cons, M = S->num_vars, width = K->num_cols, rows = M / width, np = S->num_public, n = P->n_steps;
+  size_t ell_b = 0; while (((size_t)1 << ell_b) < n) ell_b++;
+  size_t ell = 0; while (((size_t)1 << ell) < N) ell++;
+  size_t my = 0; while (((size_t)1 << my) < 2 * M) my++;
+  if (P->ell_b != ell_b || P->ell != ell || P->rounds_y != my || P->rows != rows || n < 2 || ((size_t)1 << ell_b) != n) return -1;
+  fe one, zero; f_one(&FQ, &one); f_zero(&zero);
+  transcript ts; ts_new(&ts, "neutronnova_prove");
+  ts_absorb_bytes(&ts, "vk", vk_digest, 32);
+  nn_absorb_instance(&ts, "core_instance", P->comm_W_core, rows, core_X, np);
+  for (size_t i = 0; i < n; i++) nn_absorb_instance(&ts, "U", P->comm_W_steps + i * rows, rows, step_X + i * np, np);
+  ts_absorb_scalars(&ts, &FQ, "T", &zero, 1);
+  fe tau; ts_squeeze(&ts, &FQ, "tau", &tau);
+  fe *rhos = (fe *)malloc((ell_b + 1) * sizeof(fe)), *r_b = (fe *)malloc((ell_b + 1) * sizeof(fe));
+  for (size_t t = 0; t < ell_b; t++) ts_squeeze(&ts, &FQ, "rho", &rhos[t]);
+  int rc = 0;
+  /* NIFS rounds: p_t(0) + p_t(1) = claim (zk.rs:608-637, enforce_sc_claim); final: eq_rho_at_rb * T_out = p_last(r_last) (:638-661) */
+  fe claim = zero, eq_rho = one, t1, t2;
+  for (size_t t = 0; t < ell_b; t++) {
+    const fe *co = &P->nifs_polys[4 * t];
+    fe s; f_dbl(&FQ, &s, &co[0]); f_add(&FQ, &s, &s, &co[1]); f_add(&FQ, &s, &s, &co[2]); f_add(&FQ, &s, &s, &co[3]);
+    if (!f_eq(&s, &claim)) rc = rc ? rc : -2;
+    ts_absorb_scalars(&ts, &FQ, "p", co, 4);
+    ts_squeeze(&ts, &FQ, "c", &r_b[t]);
+    unipoly_eval(co, 4, &r_b[t], &claim);
+    f_sub(&FQ, &t1, &one, &r_b[t]); f_sub(&FQ, &t2, &one, &rhos[t]); f_mul(&FQ, &t1, &t1, &t2); f_mul(&FQ, &t2, &r_b[t], &rhos[t]); f_add(&FQ, &t1, &t1, &t2);
+    f_mul(&FQ, &eq_rho, &eq_rho, &t1);                       /* EqPolynomial::new(r_b).evaluate(&rhos) (:2283) */
+  }
+  fe T_out, einv; if (!f_inv(&FQ, &einv, &eq_rho)) return -2;
+  f_mul(&FQ, &T_out, &claim, &einv);
+  /* outer: step claim_0 = T_out, core claim_0 = 0 (zk.rs:674-700); final tau(r_x) (Az Bz - Cz) = claim (:745-760) */
+  fe cs = T_out, cc = zero, *r_x = (fe *)malloc(ell * sizeof(fe));
+  for (size_t i = 0; i < ell; i++) {
+    const fe *co = &P->outer_polys[8 * i];
+    for (int b = 0; b < 2; b++) {
+      const fe *c = co + 4 * b; fe s; f_dbl(&FQ, &s, &c[0]); f_add(&FQ, &s, &s, &c[1]); f_add(&FQ, &s, &s, &c[2]); f_add(&FQ, &s, &s, &c[3]);
+      if (!f_eq(&s, b ? &cc : &cs)) rc = rc ? rc : -3;
+    }
+    ts_absorb_scalars(&ts, &FQ, "p", co, 8);
+    ts_squeeze(&ts, &FQ, "c", &r_x[i]);
+    unipoly_eval(co, 4, &r_x[i], &cs); unipoly_eval(co + 4, 4, &r_x[i], &cc);
+  }
+  fe tau_rx; nn_pow_eval(&tau, r_x, ell, &tau_rx);
+  const fe *cl = P->claims_outer;
+  f_mul(&FQ, &t1, &cl[0], &cl[1]); f_sub(&FQ, &t1, &t1, &cl[2]); f_mul(&FQ, &t1, &t1, &tau_rx); if (!f_eq(&t1, &cs)) rc = rc ? rc : -3;
+  f_mul(&FQ, &t1, &cl[3], &cl[4]); f_sub(&FQ, &t1, &t1, &cl[5]); f_mul(&FQ, &t1, &t1, &tau_rx); if (!f_eq(&t1, &cc)) rc = rc ? rc : -3;
+  ts_absorb_scalars(&ts, &FQ, "claims_outer", cl, 6);
+  fe r, r2, js, jc; ts_squeeze(&ts, &FQ, "r", &r); f_sqr(&FQ, &r2, &r);
+  f_mul(&FQ, &t1, &r, &cl[1]); f_add(&FQ, &js, &cl[0], &t1); f_mul(&FQ, &t1, &r2, &cl[2]); f_add(&FQ, &js, &js, &t1);
+  f_mul(&FQ, &t1, &r, &cl[4]); f_add(&FQ, &jc, &cl[3], &t1); f_mul(&FQ, &t1, &r2, &cl[5]); f_add(&FQ, &jc, &jc, &t1);
+  fe *r_y = (fe *)malloc(my * sizeof(fe));
+  for (size_t j = 0; j < my; j++) {
+    const fe *co = &P->inner_polys[6 * j];
+    for (int b = 0; b < 2; b++) {
+      const fe *c = co + 3 * b; fe s; f_dbl(&FQ, &s, &c[0]); f_add(&FQ, &s, &s, &c[1]); f_add(&FQ, &s, &s, &c[2]);
+      if (!f_eq(&s, b ? &jc : &js)) rc = rc ? rc : -4;
+    }
+    ts_absorb_scalars(&ts, &FQ, "p", co, 6);
+    ts_squeeze(&ts, &FQ, "c", &r_y[j]);
+    unipoly_eval(co, 3, &r_y[j], &js); unipoly_eval(co + 3, 3, &r_y[j], &jc);
+  }
+  /* R1CSInstance::fold_multiple (X part), eval_X, matrix evaluations, inner final check (zk.rs:166-230; :2244-2300) */
+  fe *w = (fe *)malloc(n * sizeof(fe)); orc_weights_from_r(r_b, ell_b, n, w);
+  fe *Xs = (fe *)calloc(np + 1, sizeof(fe)), *Xc = (fe *)calloc(np + 1, sizeof(fe));
+  Xs[0] = one; Xc[0] = one; memcpy(&Xc[1], core_X, np * sizeof(fe));
+  for (size_t i = 0; i < n; i++) for (size_t j = 0; j < np; j++) { f_mul(&FQ, &t1, &w[i], &step_X[i * np + j]); f_add(&FQ, &Xs[1 + j], &Xs[1 + j], &t1); }
+  fe eXs, eXc; sparse_poly_eval(my - 1, Xs, np + 1, r_y + 1, &eXs); sparse_poly_eval(my - 1, Xc, np + 1, r_y + 1, &eXc);
+  fe *Tx = (fe *)malloc(N * sizeof(fe)), *Ty = (fe *)malloc(2 * M * sizeof(fe)), ev[3];
+  eq_evals(r_x, ell, Tx); eq_evals(r_y, my, Ty);
+  orc_shape_eval_tables(S, Tx, Ty, ev);
+  fe quot; f_mul(&FQ, &t1, &r, &ev[1]); f_add(&FQ, &quot, &ev[0], &t1); f_mul(&FQ, &t1, &r2, &ev[2]); f_add(&FQ, &quot, &quot, &t1);
+  fe omr; f_sub(&FQ, &omr, &one, &r_y[0]);
+  f_mul(&FQ, &t1, &omr, &P->eval_W[0]); f_mul(&FQ, &t2, &r_y[0], &eXs); f_add(&FQ, &t1, &t1, &t2); f_mul(&FQ, &t1, &t1, &quot); if (!f_eq(&t1, &js)) rc = rc ? rc : -4;
+  f_mul(&FQ, &t1, &omr, &P->eval_W[1]); f_mul(&FQ, &t2, &r_y[0], &eXc); f_add(&FQ, &t1, &t1, &t2); f_mul(&FQ, &t1, &t1, &quot); if (!f_eq(&t1, &jc)) rc = rc ? rc : -4;
+  /* commitments: fold the step instances (fold_multiple: comm part as group elements), c_eval, PCS::verify (:2302-2326) */
+  apt ce[2];
+  for (int b = 0; b < 2; b++) { pt a, hb; pt_mul_fe(&a, K->ck_s, &P->eval_W[b]); pt_mul_fe(&hb, K->h_s, &P->blind_eval_W[b]); pt_add(&CV, &a, &a, &hb); pt_to_affine(&CV, &ce[b], &a); }
+  ts_absorb_point(&ts, "comm_eval_W_step", &ce[0]); ts_absorb_point(&ts, "comm_eval_W_core", &ce[1]);
+  fe c_eval; ts_squeeze(&ts, &FQ, "c_eval", &c_eval);
+  apt *comm_fold = (apt *)malloc(rows * sizeof(apt)), *pair = (apt *)malloc(2 * rows * sizeof(apt)), *comm = (apt *)malloc(rows * sizeof(apt));
+  orc_fold_commitments(P->comm_W_steps, n, rows, w, comm_fold);
+  fe wts[2] = { one, c_eval };
+  memcpy(pair, comm_fold, rows * sizeof(apt)); memcpy(pair + rows, P->comm_W_core, rows * sizeof(apt));
+  orc_fold_commitments(pair, 2, rows, wts, comm);
+  apt comm_eval; orc_fold_commitments(ce, 2, 1, wts, &comm_eval);
+  proof_view PV; memset(&PV, 0, sizeof(PV)); PV.delta = P->delta; PV.beta = P->beta; PV.z_vec = P->z_vec; PV.z_delta = P->z_delta; PV.z_beta = P->z_beta;
+  if (!rc && hyrax_verify(K, &ts, comm, rows, r_y + 1, my - 1, &comm_eval, &PV) != 0) rc = -5;
+  free(rhos); free(r_b); free(r_x); free(r_y); free(w); free(Xs); free(Xc); free(Tx); free(Ty); free(comm_fold); free(pair); free(comm);
+  ts_free(&ts);
+  return rc;
+}

@@ -94,3 +94,45 @@ def z_of(inst):
 def dims(inst):
     return (inst["num_cons"], inst["num_cons_unpadded"], inst["num_shared"], inst["num_precommitted"], inst["num_rest"],
             inst["num_public"], inst["num_challenges"])
+
+
+def chain_instances(n, log_cons, log_vars, num_public=2, seed=11):
+    """n satisfying instances of ONE random R1CS shape (the NeutronNova multi-folding setting: step circuits share their
+    shape, witnesses differ) plus a core instance, shaped like the SHA-256 chain: precommitted section = first half of
+    the variables, rest section = second half, all zero and unused (the reference's step circuits allocate nothing in
+    `synthesize`, so their rest rows are commit_zeros, bellpepper/r1cs.rs:443-470).  Returns (dims, (A, B, C), zs, zc)."""
+    assert log_vars - 1 > log_cons - 1, "need more variables than constraints so every C row is a fresh product variable"
+    base = random_r1cs(seed, log_cons, log_vars - 1, num_public=num_public, rest_frac=0.0, dense_rows=2)
+    Mh = 1 << (log_vars - 1); M = 2 * Mh
+    N, n_unp = base["num_cons"], base["num_cons_unpadded"]
+    free_vars = Mh - n_unp
+
+    def shift(mat):
+        d, i, p = mat
+        i = i.copy(); i[i >= Mh] += Mh                      # the constant-one and public columns move behind the rest section
+        return d, i, p
+    mats = tuple(shift(base[k]) for k in "ABC")
+    Ai, Bi = [from_mont_rows(m) for m in mats[:2]]
+
+    def witness(s):
+        rng = np.random.default_rng(1000 * seed + s)
+        w = [int(b) for b in rng.integers(0, 2, size=Mh)]
+        x = [int(v) for v in rng.integers(0, 1 << 30, size=num_public)]
+        z = lambda c: w[c] if c < Mh else (1 if c == M else x[c - M - 1])      # noqa: E731
+        for row in range(n_unp):
+            sa = sum(cf * z(c) for cf, c in Ai[row]) % Q; sb = sum(cf * z(c) for cf, c in Bi[row]) % Q
+            w[free_vars + row] = sa * sb % Q
+        W = np.array([mont(v) for v in w] + [mont(0)] * Mh, dtype=np.uint64)
+        X = np.array([mont(v) for v in x], dtype=np.uint64).reshape(-1, 4)
+        one = np.array([mont(1)], dtype=np.uint64)
+        return np.concatenate([W, one, X]) if num_public else np.concatenate([W, one])
+    dims_ = (N, n_unp, 0, Mh, Mh, num_public, 0)
+    return dims_, mats, [witness(s) for s in range(n)], witness(n)
+
+
+def from_mont_rows(mat):
+    """CSR (data Montgomery, indices, indptr) -> per-row lists of (canonical coefficient, column)."""
+    d, i, p = mat
+    rinv = pow(R, -1, Q)
+    vals = [sum(int(l) << (64 * k) for k, l in enumerate(row)) * rinv % Q for row in d]
+    return [[(vals[k], int(i[k])) for k in range(int(p[r]), int(p[r + 1]))] for r in range(len(p) - 1)]

@@ -518,3 +518,113 @@ def nifs_cvals_small(left, right, E, Cl, C64, large, N, n):
     lib().orc_nifs_cvals_small(C.c_size_t(left), C.c_size_t(right), _p(E), _p(Cl), _p(C64), _p(lp), C.c_size_t(large.shape[0]), C.c_size_t(N),
                                C.c_size_t(n), _p(out))
     return out
+
+
+# ---- Hyrax commitment family on group elements (hyrax_pc.rs:321-344, 533-607, 795-874) ---------------------------------
+def _pts(a):
+    return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 8)
+
+
+def _fes(a):
+    return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+
+
+def hyrax_commit_without_blind(ck, v, is_small=False):
+    ck = _pts(ck); v = _fes(v); num_cols = ck.shape[0]; n = v.shape[0]; rows = (n + num_cols - 1) // num_cols
+    out = np.zeros((rows, 8), dtype=np.uint64)
+    lib().orc_hyrax_commit_without_blind(_p(ck), C.c_size_t(num_cols), _p(v), C.c_size_t(n), C.c_int(int(is_small)), _p(out))
+    return out
+
+
+def hyrax_commit_incremental(ck, h, raw, delta, blinds):
+    ck = _pts(ck); h = _pts(h); raw = _pts(raw); delta = _fes(delta); blinds = _fes(blinds)
+    num_cols = ck.shape[0]; n = delta.shape[0]; rows = (n + num_cols - 1) // num_cols
+    out = np.zeros((rows, 8), dtype=np.uint64)
+    lib().orc_hyrax_commit_incremental(_p(ck), C.c_size_t(num_cols), _p(h), _p(raw), C.c_size_t(raw.shape[0]), _p(delta), C.c_size_t(n), _p(blinds), _p(out))
+    return out
+
+
+def hyrax_rerandomize(h, comm, r_old, r_new):
+    h = _pts(h); comm = _pts(comm); r_old = _fes(r_old); r_new = _fes(r_new)
+    out = np.zeros_like(comm)
+    lib().orc_hyrax_rerandomize(_p(h), _p(comm), _p(r_old), _p(r_new), C.c_size_t(comm.shape[0]), _p(out))
+    return out
+
+
+def fold_blinds(blinds, n, rows, w):
+    blinds = _fes(blinds); w = _fes(w); out = fe_array(rows)
+    lib().orc_fold_blinds(_p(blinds), C.c_size_t(n), C.c_size_t(rows), _p(w), _p(out))
+    return out
+
+
+def fold_commitments_partial(comms, n, rows, w, num_data_rows, folded_blind, h):
+    comms = _pts(comms); w = _fes(w); fb = _fes(folded_blind); h = _pts(h)
+    out = np.zeros((rows, 8), dtype=np.uint64)
+    lib().orc_fold_commitments_partial(_p(comms), C.c_size_t(n), C.c_size_t(rows), _p(w), C.c_size_t(num_data_rows), _p(fb), _p(h), _p(out))
+    return out
+
+
+# ---- NeutronNova, non-ZK variant (oracle.c: orc_neutronnova_prove / _verify) -------------------------------------------
+class _NnProofView(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_steps", "ell_b", "ell", "rounds_y", "rows", "num_cols")] + \
+               [(k, C.c_void_p) for k in ("comm_W_steps", "comm_W_core", "nifs_polys", "outer_polys", "claims_outer", "inner_polys", "eval_W",
+                                          "blind_eval_W", "delta", "beta", "z_vec", "z_delta", "z_beta")]
+
+
+class _NnRandView(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("blinds_steps", "blinds_core", "blind_eval_W", "d_vec", "r_delta", "r_beta")]
+
+
+class NnProof:
+    """Flat buffers of the non-ZK NeutronNova proof (same layout as the product's sp2_nn_snark)."""
+    FIELDS = ["comm_W_steps", "comm_W_core", "nifs_polys", "outer_polys", "claims_outer", "inner_polys", "eval_W", "blind_eval_W",
+              "delta", "beta", "z_vec", "z_delta", "z_beta"]
+
+    def __init__(self, n, N, M, num_cols):
+        self.n, self.ell_b, self.ell, self.my = n, n.bit_length() - 1, N.bit_length() - 1, (2 * M).bit_length() - 1
+        self.rows, self.num_cols = M // num_cols, num_cols
+        pz = lambda k: np.zeros((k, 8), dtype=np.uint64)   # noqa: E731
+        self.comm_W_steps = pz(n * self.rows); self.comm_W_core = pz(self.rows)
+        self.nifs_polys = fe_array(4 * self.ell_b); self.outer_polys = fe_array(8 * self.ell); self.claims_outer = fe_array(6)
+        self.inner_polys = fe_array(6 * self.my); self.eval_W = fe_array(2); self.blind_eval_W = fe_array(2)
+        self.delta = pz(1); self.beta = pz(1); self.z_vec = fe_array(num_cols); self.z_delta = fe_array(1); self.z_beta = fe_array(1)
+
+    def view(self):
+        v = _NnProofView(self.n, self.ell_b, self.ell, self.my, self.rows, self.num_cols)
+        for f in self.FIELDS:
+            setattr(v, f, getattr(self, f).ctypes.data)
+        return v
+
+
+class NnRand:
+    def __init__(self, blinds_steps, blinds_core, blind_eval_W, d_vec, r_delta, r_beta):
+        self.a = [_fes(x) for x in (blinds_steps, blinds_core, blind_eval_W, d_vec, r_delta, r_beta)]
+
+    def view(self):
+        return _NnRandView(*[x.ctypes.data for x in self.a])
+
+
+def neutronnova_prove(shape, keys, vk_digest, zs, zc, comm_pre_steps, blinds_pre_steps, comm_pre_core, blinds_pre_core, rand, want_debug=False):
+    """zs: (n, num_cols, 4) step instances z_i = [W_i | 1 | X_i]; comm_pre_*: precommitted-section commitments of prep_prove
+    (rows of the shared+precommitted sections) with their blinds; rand: NnRand (the blinds every U_i.comm_W ends up with)."""
+    zs = np.ascontiguousarray(zs, dtype=np.uint64); n = zs.shape[0]; zc = _fes(zc)
+    P = NnProof(n, shape.num_cons, shape.num_vars, keys.ck.shape[0])
+    pv = P.view(); kv = keys.view(); rv = rand.view()
+    dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
+    cps, bps, cpc, bpc = _pts(comm_pre_steps), _fes(blinds_pre_steps), _pts(comm_pre_core), _fes(blinds_pre_core)
+    dbg = fe_array(8); phases = (C.c_double * 8)()
+    rc = lib().orc_neutronnova_prove(shape.h, C.byref(kv), _p(dig), C.c_size_t(n), _p(zs), _p(zc), _p(cps), _p(bps), _p(cpc), _p(bpc),
+                                     C.byref(rv), C.byref(pv), _p(dbg), phases)
+    if rc != 0:
+        raise RuntimeError("orc_neutronnova_prove failed: %d" % rc)
+    P.phase_ms = dict(zip(["rerandomize+commit_zeros", "transcript_absorb", "nifs", "fold", "outer_sumcheck_batched", "compute_eval_table_sparse",
+                           "inner_sumcheck_batched", "pcs_prove"], list(phases)))
+    P.debug = dict(zip(["T_out", "tau_at_rx", "r", "c_eval", "eq_rho_at_rb", "eval_X_step", "eval_X_core"], [dbg[i:i + 1].copy() for i in range(7)]))
+    return P
+
+
+def neutronnova_verify(shape, keys, vk_digest, step_X, core_X, proof):
+    kv = keys.view(); pv = proof.view()
+    dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
+    sx = _fes(step_X) if np.size(step_X) else fe_array(1); cx = _fes(core_X) if np.size(core_X) else fe_array(1)
+    return lib().orc_neutronnova_verify(shape.h, C.byref(kv), _p(dig), _p(sx), _p(cx), C.byref(pv))

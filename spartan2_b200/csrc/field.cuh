@@ -153,6 +153,55 @@ struct Field {
 };
 
 // ------------------------------------------------------------------------------------------
+// Interleaved Montgomery multiplication (low latency): the eight reduction rows m_i * p are accumulated as further rows of
+// the product, in the same even / odd carry-save form as mul_wide (each row = two independent 4-IMAD.WIDE carry chains
+// into a big-integer accumulator; E takes the chains that start at an even limb position, O the odd ones), so no carry
+// ever ripples further than its own row.  The only serial coupling between rounds is the quotient digit:
+//   t_i = limb i of (E + O) incl. the carry c out of the retired low limbs;  m_i = t_i * (-p^-1) mod 2^32
+// (two adds and one multiply per round).  Retiring limb i: E[i] + O[i] + c = 0 (mod 2^32) and < 2^33, hence the new
+// c = 1 iff any of the three is non-zero.  ~240 instructions with 4-long dependency chains instead of ~360 with
+// 17-long carry ripples per round: the latency-bound group arithmetic (MSM trees, scalar tails) runs on this.
+// a, b < p  ->  a b / 2^256 mod p, canonical.
+// ------------------------------------------------------------------------------------------
+template <class PR>
+SP2_HD fe mont_mul_interleaved(const fe &a, const fe &b) {
+  u32 E[18], O[18];
+#pragma unroll
+  for (int i = 0; i < 18; i++) { E[i] = 0; O[i] = 0; }
+  u32 c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if ((i & 1) == 0) {
+      mad_row4<18>(E, i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+      mad_row4<18>(O, i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);           // O[k] sits at limb position k + 1
+      const u32 m = mul_lo(E[i] + (i ? O[i - 1] : 0u) + c, PR::INV32);
+      mad_row4<18>(E, i, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m);
+      mad_row4<18>(O, i, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m);
+      c = ((E[i] | (i ? O[i - 1] : 0u) | c) != 0u) ? 1u : 0u;
+    } else {
+      mad_row4<18>(O, i - 1, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);       // starts at limb i = O index i - 1
+      mad_row4<18>(E, i + 1, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+      const u32 m = mul_lo(E[i] + O[i - 1] + c, PR::INV32);
+      mad_row4<18>(O, i - 1, PR::P(0), PR::P(2), PR::P(4), PR::P(6), m);
+      mad_row4<18>(E, i + 1, PR::P(1), PR::P(3), PR::P(5), PR::P(7), m);
+      c = ((E[i] | O[i - 1] | c) != 0u) ? 1u : 0u;
+    }
+  }
+  // (E + O + c 2^256) >> 256 : limbs 8..16  (O[k] is limb k + 1)
+  fe r;
+  r.v[0] = add_cc(E[8], O[7]);
+#pragma unroll
+  for (int k = 1; k < 8; k++) r.v[k] = addc_cc(E[8 + k], O[7 + k]);
+  u32 top = addc(E[16], O[15]);
+  r.v[0] = add_cc(r.v[0], c);
+#pragma unroll
+  for (int k = 1; k < 8; k++) r.v[k] = addc_cc(r.v[k], 0);
+  top = addc(top, 0);
+  cond_sub_p<PR>(r, top);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
 // Fq: P-256 prime, multiplication-free REDC
 // ------------------------------------------------------------------------------------------
 struct Fq : Field<FqParams> {
@@ -336,6 +385,9 @@ struct Fp : Field<FpParams> {
   }
   // two independent Montgomery products in lockstep (mul_wide2 + alternating REDC rounds)
   SP2_HD static void mul_inl2(const fe &a0, const fe &b0, const fe &a1, const fe &b1, fe &o0, fe &o1) {
+    o0 = mont_mul_interleaved<FpParams>(a0, b0); o1 = mont_mul_interleaved<FpParams>(a1, b1);
+  }
+  SP2_HD static void mul_cios2(const fe &a0, const fe &b0, const fe &a1, const fe &b1, fe &o0, fe &o1) {
     u32 w0[16], w1[16];
     mul_wide2(w0, w1, a0, b0, a1, b1);
     u32 t0[18], t1[18];
@@ -349,7 +401,12 @@ struct Fp : Field<FpParams> {
     cond_sub_p<FpParams>(o0, t0[16]);
     cond_sub_p<FpParams>(o1, t1[16]);
   }
-  SP2_HD static fe mul_inl(const fe &a, const fe &b) {
+  // Measured on B200 (tools/microbench/field_mul.cu, profiles/r2_b_microbench_field_mul.txt): the interleaved form runs at
+  // 598 cycles per warp-multiplication per SMSP (62 G mul/s) against 711 (52 G mul/s) for the wide-product + shaped-CIOS form
+  // below, 879 against 938 cycles of single-warp latency, in 280 instead of 408 instructions; the lockstep pair bought no
+  // latency (1913 cycles per pair).  Both remain: mul_cios is the cross-check of the host tests.
+  SP2_HD static fe mul_inl(const fe &a, const fe &b) { return mont_mul_interleaved<FpParams>(a, b); }
+  SP2_HD static fe mul_cios(const fe &a, const fe &b) {
     u32 w[16];
     mul_wide(w, a, b);
     u32 t[18];

@@ -74,72 +74,128 @@ __global__ void __launch_bounds__(128) k_ck_normalize(const jac *tmp, const fe *
 }
 
 // ---- gather + sum ------------------------------------------------------------------------------
+// Warp-granular: gather warp g sums MSM_WARP_LOOKUPS consecutive (term, window) table entries of ONE job — lanes
+// accumulate ~4 entries each with mixed additions, then a 5-level shuffle tree — and writes one partial sum.  No
+// __syncthreads, no shared-memory points: a job of one term (commit_zeros, rerandomisation, blind * h: 33 entries) costs
+// one warp and ~1 mixed + 5 full additions of latency instead of a 256-thread CTA walking an 8-level barrier tree, and
+// the thousands of row jobs of a NeutronNova prove pack eight to a CTA.  k_msm_final: one CTA per job sums its partials
+// (strided serial adds, warp shuffle tree, 4-warp smem step) and adds the job's optional addend.
+constexpr int GW = MSM_THREADS / 32;            // gather warps per CTA
+
+__device__ __forceinline__ jac shfl_down_jac(const jac &p, int d) {
+  jac r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
+    r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
+    r.z.v[i] = __shfl_down_sync(0xffffffffu, p.z.v[i], d);
+  }
+  return r;
+}
+__device__ __forceinline__ jac warp_sum_jac(jac acc) {        // result valid in lane 0
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    const jac o = shfl_down_jac(acc, d);
+    if ((threadIdx.x & 31) < d) acc = jac_add(acc, o);
+  }
+  return acc;
+}
+// job that owns partial `part` (jobs are sorted by first_part): binary search
+__device__ __forceinline__ u32 job_of_part(const MsmJob *jobs, u32 njobs, u32 part) {
+  u32 lo = 0, hi = njobs - 1;
+  while (lo < hi) { const u32 mid = (lo + hi + 1) >> 1; if (jobs[mid].first_part <= part) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
 struct GatherSmem {
-  short dig[MSM_TERMS][MSM_NW + 1];
-  u32 bidx[MSM_TERMS];
+  short dig[GW][8][MSM_NW + 1];      // signed byte digits of the <= 6 terms a warp's 128 entries span
+  u32 bidx[GW][8];
+  const aff *tab[GW][8];
 };
 
-__global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, const aff *table, jac *partial, u32 maxblk) {
+__global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, u32 njobs, u32 total_parts, const aff *table, jac *partial) {
   __shared__ GatherSmem sm;
-  __shared__ jac red[MSM_THREADS];
-  const MsmJob job = jobs[blockIdx.y];
-  if (blockIdx.x >= job.nblk) return;
-  const u32 tid = threadIdx.x;
-  const u32 total = job.len + job.nextra, t0 = blockIdx.x * MSM_TERMS;
-  const u32 nterm = total > t0 ? min((u32)MSM_TERMS, total - t0) : 0;
+  const u32 wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 part = blockIdx.x * GW + wib;
+  if (part >= total_parts) return;
+  const u32 jid = job_of_part(jobs, njobs, part);
+  const MsmJob job = jobs[jid];
+  const u32 total = (job.len + job.nextra) * MSM_NW;
+  const u32 p0 = (part - job.first_part) * MSM_WARP_LOOKUPS, p1 = min(total, p0 + MSM_WARP_LOOKUPS);
+  const u32 t0 = p0 / MSM_NW, nterm = p1 > p0 ? (p1 - 1) / MSM_NW - t0 + 1 : 0;
   // signed byte digits of each scalar (to_repr() little-endian bytes, msm.rs:97-100; digit recoding :122-148)
-  if (tid < nterm) {
-    const u32 g = t0 + tid;
-    fe s; u32 b;
+  if (lane < nterm) {
+    const u32 g = t0 + lane;
+    fe s; u32 b; const aff *tb = table;
     if (g < job.len) { s = ldg_fe(job.scalars + g); b = job.base0 + g; }
-    else { s = ldg_fe(job.extra_scalar[g - job.len]); b = job.extra_base[g - job.len]; }
+    else { const u32 e = g - job.len; s = ldg_fe(job.extra_scalar[e]); b = job.extra_base[e]; if (job.extra_tab[e]) tb = job.extra_tab[e]; }
     s = Fq::from_mont(s);
-    sm.bidx[tid] = b;
+    sm.bidx[wib][lane] = b; sm.tab[wib][lane] = tb;
     int carry = 0;
 #pragma unroll
     for (int w = 0; w < 32; w++) {
       int d = (int)((s.v[w >> 2] >> (8 * (w & 3))) & 0xffu) + carry;
       carry = 0;
       if (d > 128) { d -= 256; carry = 1; }
-      sm.dig[tid][w] = (short)d;
+      sm.dig[wib][lane][w] = (short)d;
     }
-    sm.dig[tid][32] = (short)carry;
+    sm.dig[wib][lane][32] = (short)carry;
   }
-  __syncthreads();
+  __syncwarp();
   jac acc = jac_inf();
-  for (u32 p = tid; p < nterm * MSM_NW; p += MSM_THREADS) {
-    const u32 t = p / MSM_NW, w = p - t * MSM_NW;
-    const int d = sm.dig[t][w];
+  for (u32 p = p0 + lane; p < p1; p += 32) {
+    const u32 t = p / MSM_NW, w = p - t * MSM_NW, lt = t - t0;
+    const int d = sm.dig[wib][lt][w];
     if (d) {
-      aff pt = ld_aff_ro(table + ((size_t)sm.bidx[t] * MSM_NW + w) * MSM_ND + (u32)((d < 0 ? -d : d) - 1));
+      aff pt = ld_aff_ro(sm.tab[wib][lt] + ((size_t)sm.bidx[wib][lt] * MSM_NW + w) * MSM_ND + (u32)((d < 0 ? -d : d) - 1));
       if (d < 0) pt.y = Fp::neg(pt.y);
       acc = jac_add_mixed(acc, pt);
     }
   }
-  red[tid] = acc;
-  __syncthreads();
-#pragma unroll 1
-  for (u32 s = MSM_THREADS / 2; s >= 1; s >>= 1) {
-    if (tid < s) red[tid] = jac_add(red[tid], red[tid + s]);
-    __syncthreads();
-  }
-  if (tid == 0) st_jac(partial + (size_t)blockIdx.y * maxblk + blockIdx.x, red[0]);
+  acc = warp_sum_jac(acc);
+  if (lane == 0) st_jac(partial + part, acc);
 }
 
-__global__ void __launch_bounds__(128) k_msm_final(const MsmJob *jobs, const jac *partial, u32 maxblk, jac *out) {
-  __shared__ jac red[128];
+__global__ void __launch_bounds__(128) k_msm_final(const MsmJob *jobs, const jac *partial, jac *out) {
+  __shared__ jac red[4];
   const MsmJob job = jobs[blockIdx.x];
-  const u32 tid = threadIdx.x;
+  const u32 tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const u32 nw = job.nparts > 32 ? 4u : 1u;                  // small jobs: one warp, no barrier
+  if (wib >= nw) return;
   jac acc = jac_inf();
-  for (u32 blk = tid; blk < job.nblk; blk += 128) acc = jac_add(acc, ld_jac(partial + (size_t)blockIdx.x * maxblk + blk));
-  red[tid] = acc;
-  __syncthreads();
-#pragma unroll 1
-  for (u32 s = 64; s >= 1; s >>= 1) {
-    if (tid < s && tid + s < job.nblk) red[tid] = jac_add(red[tid], red[tid + s]);
+  for (u32 q = tid; q < job.nparts; q += 32 * nw) acc = jac_add(acc, ld_jac(partial + job.first_part + q));
+  acc = warp_sum_jac(acc);
+  if (nw > 1) {
+    if (lane == 0) red[wib] = acc;
     __syncthreads();
+    if (tid == 0) acc = jac_add(jac_add(red[0], red[1]), jac_add(red[2], red[3]));
   }
-  if (tid == 0) st_jac(out + blockIdx.x, red[0]);
+  if (tid == 0) {
+    if (job.add_aff) acc = jac_add_mixed(acc, ld_aff_ro(job.add_aff));
+    if (job.add_jac) acc = jac_add(acc, ld_jac(job.add_jac));
+    st_jac(out + blockIdx.x, acc);
+  }
+}
+
+// n Jacobian points -> affine: one thread per chunk of <= 64 points, one inversion per chunk (Montgomery's trick)
+constexpr int NORM_CHUNK = 64;
+__global__ void __launch_bounds__(64) k_batch_normalize(const jac *in, u64 n, aff *out) {
+  const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 i0 = c * NORM_CHUNK; if (i0 >= n) return;
+  const u64 i1 = min(n, i0 + NORM_CHUNK);
+  fe pre[NORM_CHUNK];
+  fe acc = Fp::one();
+#pragma unroll 1
+  for (u64 i = i0; i < i1; i++) { pre[i - i0] = acc; const fe z = ldg_fe(&in[i].z); if (!Fp::is_zero(z)) acc = Fp::mul(acc, z); }
+  fe inv = Fp::inv(acc);
+#pragma unroll 1
+  for (u64 i = i1; i-- > i0;) {
+    const jac p = ld_jac(in + i);
+    aff a;
+    if (Fp::is_zero(p.z)) { a.x = Fp::zero(); a.y = Fp::zero(); }
+    else { a = jac_to_aff_with_inv(p, Fp::mul(inv, pre[i - i0])); inv = Fp::mul(inv, p.z); }
+    stg_fe(&out[i].x, a.x); stg_fe(&out[i].y, a.y);
+  }
 }
 
 // ---- Hyrax bind: LZ[i] = sum_j L[j] * W[j * r_len + i], delayed reduction (hyrax_pc.rs:38-54) ----
@@ -190,27 +246,58 @@ __global__ void __launch_bounds__(64) k_test_points(u64 seed, u32 n, aff *out) {
 
 namespace sp2 {
 
-// d_out[njobs]: Jacobian results (the caller normalises on the host)
+// d_out[njobs]: Jacobian results (the caller normalises: sp2h::batch_normalize on the host, batch_normalize_dev here)
 int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, jac *d_out) {
   if (jobs_in.empty()) return SP2_OK;
   std::vector<MsmJob> jobs(jobs_in);
-  u32 maxblk = 1;
+  u32 parts = 0;
   for (auto &j : jobs) {
+    if (j.nextra > 3) return set_error(ctx, SP2_ERR_INTERNAL, "msm: at most three extra terms per job");
     if (j.base0 + j.len > ck->nbase) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "msm: more scalars than commitment-key bases");
-    j.nblk = (j.len + j.nextra + MSM_TERMS - 1) / MSM_TERMS;
-    if (j.nblk == 0) j.nblk = 1;
-    maxblk = std::max(maxblk, j.nblk);
+    const u32 total = (j.len + j.nextra) * MSM_NW;
+    j.first_part = parts; j.nparts = std::max<u32>(1, (total + MSM_WARP_LOOKUPS - 1) / MSM_WARP_LOOKUPS);
+    parts += j.nparts;
   }
   const size_t nj = jobs.size();
   void *d_jobs, *d_partial;
   SP2_TRY(scratch(ctx, 10, nj * sizeof(MsmJob), &d_jobs));
-  SP2_TRY(scratch(ctx, 11, nj * maxblk * sizeof(jac), &d_partial));
+  SP2_TRY(scratch(ctx, 11, (size_t)parts * sizeof(jac), &d_partial));
   // pageable source: the runtime stages it before cudaMemcpyAsync returns, so the local vector may die
   SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), nj * sizeof(MsmJob), cudaMemcpyHostToDevice, ctx->stream));
-  k_msm_gather<<<dim3(maxblk, (unsigned)nj), MSM_THREADS, 0, ctx->stream>>>((const MsmJob *)d_jobs, ck->table, (jac *)d_partial, maxblk);
+  k_msm_gather<<<(parts + GW - 1) / GW, MSM_THREADS, 0, ctx->stream>>>((const MsmJob *)d_jobs, (u32)nj, parts, ck->table, (jac *)d_partial);
   SP2_LAUNCH_CHECK();
-  k_msm_final<<<(unsigned)nj, 128, 0, ctx->stream>>>((const MsmJob *)d_jobs, (const jac *)d_partial, maxblk, d_out);
+  k_msm_final<<<(unsigned)nj, 128, 0, ctx->stream>>>((const MsmJob *)d_jobs, (const jac *)d_partial, d_out);
   SP2_LAUNCH_CHECK();
+  return SP2_OK;
+}
+
+int batch_normalize_dev(sp2_ctx *ctx, const jac *d_in, uint64_t n, aff *d_out) {
+  if (!n) return SP2_OK;
+  const u64 chunks = (n + NORM_CHUNK - 1) / NORM_CHUNK;
+  k_batch_normalize<<<(unsigned)((chunks + 63) / 64), 64, 0, ctx->stream>>>(d_in, n, d_out);
+  SP2_LAUNCH_CHECK();
+  return SP2_OK;
+}
+
+// window tables of `nbase` device-resident affine bases: table[b][w][d-1] = d * 2^(8w) * base_b
+int msm_build_tables(sp2_ctx *ctx, const aff *d_bases, uint32_t nbase, aff **table_out) {
+  *table_out = nullptr;
+  jac *tmp = nullptr; fe *pre = nullptr; aff *table = nullptr;
+  const size_t nent = (size_t)nbase * MSM_NW * MSM_ND;
+  cudaError_t e = cudaMalloc((void **)&tmp, nent * sizeof(jac));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pre, (size_t)nbase * MSM_NW * (MSM_ND + 1) * sizeof(fe));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&table, nent * sizeof(aff));
+  if (e == cudaSuccess) {
+    const unsigned blocks = (nbase * MSM_NW + 127) / 128;
+    k_ck_multiples<<<blocks, 128, 0, ctx->stream>>>(d_bases, nbase, tmp, pre);
+    k_ck_normalize<<<blocks, 128, 0, ctx->stream>>>(tmp, pre, nbase, table);
+    ctx->launches += 2;
+    e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (pre) cudaFree(pre);
+  if (tmp) cudaFree(tmp);
+  if (e != cudaSuccess) { if (table) cudaFree(table); return set_cuda_error(ctx, e, "msm table build", __LINE__); }
+  *table_out = table;
   return SP2_OK;
 }
 
@@ -237,27 +324,15 @@ int32_t sp2_ck_upload(sp2_ctx *ctx, const uint64_t *bases_xy, uint32_t n, const 
   if (n == 0 || n > (1u << 24)) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "ck: bad number of bases");
   sp2_ck *ck = new sp2_ck();
   ck->ctx = ctx; ck->n = n; ck->nbase = n + 3;
-  aff *d_bases = nullptr; jac *tmp = nullptr; fe *pre = nullptr;
-  const size_t nent = (size_t)ck->nbase * MSM_NW * MSM_ND;       // table entries
+  aff *d_bases = nullptr;
   cudaError_t e = cudaMalloc((void **)&d_bases, (size_t)ck->nbase * sizeof(aff));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&tmp, nent * sizeof(jac));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pre, (size_t)ck->nbase * MSM_NW * (MSM_ND + 1) * sizeof(fe));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&ck->table, nent * sizeof(aff));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases, bases_xy, (size_t)n * sizeof(aff), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases + n, h_xy, sizeof(aff), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases + n + 1, ck_s_xy, sizeof(aff), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases + n + 2, h_s_xy, sizeof(aff), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) {
-    const unsigned blocks = (ck->nbase * MSM_NW + 127) / 128;
-    k_ck_multiples<<<blocks, 128, 0, ctx->stream>>>(d_bases, ck->nbase, tmp, pre);
-    k_ck_normalize<<<blocks, 128, 0, ctx->stream>>>(tmp, pre, ck->nbase, ck->table);
-    ctx->launches += 2;
-    e = cudaStreamSynchronize(ctx->stream);
-  }
-  if (pre) cudaFree(pre);
+  int rc = e == cudaSuccess ? msm_build_tables(ctx, d_bases, ck->nbase, &ck->table) : set_cuda_error(ctx, e, "ck upload", __LINE__);
   if (d_bases) cudaFree(d_bases);
-  if (tmp) cudaFree(tmp);
-  if (e != cudaSuccess) { if (ck->table) cudaFree(ck->table); delete ck; return set_cuda_error(ctx, e, "ck upload", __LINE__); }
+  if (rc != SP2_OK) { delete ck; return rc; }
   *out = ck;
   return SP2_OK;
 }

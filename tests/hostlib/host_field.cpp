@@ -7,6 +7,9 @@ extern "C" {
 #define BIN(name, F, op) void name(const fe *a, const fe *b, fe *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = F::op(a[i], b[i]); }
 BIN(ht_fq_mul, Fq, mul) BIN(ht_fq_add, Fq, add) BIN(ht_fq_sub, Fq, sub)
 BIN(ht_fp_mul, Fp, mul) BIN(ht_fp_add, Fp, add) BIN(ht_fp_sub, Fp, sub)
+void ht_fq_mul_il(const fe *a, const fe *b, fe *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = mont_mul_interleaved<FqParams>(a[i], b[i]); }
+void ht_fp_mul_il(const fe *a, const fe *b, fe *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = mont_mul_interleaved<FpParams>(a[i], b[i]); }
+void ht_fp_mul_cios(const fe *a, const fe *b, fe *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = Fp::mul_cios(a[i], b[i]); }
 void ht_fq_inv(const fe *a, fe *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = Fq::inv(a[i]); }
 void ht_fp_inv(const fe *a, fe *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = Fp::inv(a[i]); }
 void ht_fq_half(const fe *a, fe *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = Fq::half(a[i]); }

@@ -63,6 +63,15 @@ def test_mont_mul_add_sub(ht, name, p):
     assert call2(getattr(ht, "ht_%s_sub" % name), a, b) == [(x - y) % p for x, y in zip(a, b)]
 
 
+@pytest.mark.parametrize("fn,p", [("ht_fq_mul_il", Q), ("ht_fp_mul_il", P), ("ht_fp_mul_cios", P)])
+def test_all_multiplication_forms_agree(ht, fn, p):
+    """mont_mul_interleaved<> (the multiplication of the group arithmetic; also instantiated for the scalar field) and the
+    wide-product + shaped-CIOS form kept as its cross-check: all equal a * b / R mod p on edge x edge pairs and 20k random pairs."""
+    a, b = samples(p, 20000, 4242)
+    rinv = pow(R, -1, p)
+    assert call2(getattr(ht, fn), a, b) == [x * y * rinv % p for x, y in zip(a, b)]
+
+
 def test_mul_wide(ht):
     rng = random.Random(2)
     for _ in range(300):

@@ -325,6 +325,41 @@ int32_t sp2_neutronnova_prep_connect_ptrs(sp2_nn_prep *prep, void *const *xbufs)
 int32_t sp2_neutronnova_prove_sharded(sp2_ctx *ctx, sp2_nn_prep *prep, sp2_transcript *ts, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
                                       sp2_nn_proof *proof, float *phase_ms);
 
+/* ---- NeutronNova prove incl. its commitment half (non-ZK variant; checker: oracle/oracle.c orc_neutronnova_prove/_verify) ----
+ * NeutronNovaZkSNARK::{prep_prove, prove} (src/neutronnova_zk.rs:1477-1603, 1609-2093) with the ZK wrapper removed: per-step
+ * rerandomize_commitment (hyrax_pc.rs:321-344) and commit_zeros of the rest rows (:305-319), the transcript over all
+ * instances (b"vk", b"core_instance", b"U"...), HOT LOOPS A-C as sp2_neutronnova_prove, fold_blinds + fold_commitments_partial
+ * (:795-874), commitments to eval_W_step / eval_W_core (absorbed as b"comm_eval_W_step" / b"comm_eval_W_core"), b"c_eval",
+ * the [1, c_eval] folds of commitments / blinds / witnesses (neutronnova_zk.rs:2019-2051) and PCS::prove on the folded witness
+ * (:2053-2064).  Round polynomials are absorbed directly (b"p", all coefficients) instead of being committed inside the
+ * reference's in-circuit verifier; eval_W_{step,core} are revealed with their blinds, as SpartanSNARK reveals eval_W.
+ * Requires num_shared == 0 (the SHA-256 chain).  All arrays are caller-allocated.                                      */
+typedef struct {
+  sp2_nn_proof base;            /* nifs_polys, outer_polys, claims_outer, inner_polys, eval_W (+ the evals / challenges probes)     */
+  uint64_t rows;                /* out: commitment rows per instance = num_vars / ck width                                         */
+  uint64_t *comm_W_steps;       /* n_steps x rows points: U_i.comm_W (precommitted rows rerandomised, rest rows = blind * h)        */
+  uint64_t *comm_W_core;        /* rows points                                                                                       */
+  uint64_t *blind_eval_W;       /* 2                                                                                                 */
+  uint64_t *delta, *beta;       /* 1 point each (InnerProductArgumentLinear, ipa.rs:104-121)                                         */
+  uint64_t *z_vec;              /* ck width scalars                                                                                  */
+  uint64_t *z_delta, *z_beta;   /* 1 each                                                                                            */
+  uint64_t *comm_eval_W;        /* optional (may be NULL), 2 points: parity probes — the verifier recomputes them                    */
+  uint64_t *c_eval;             /* optional, 1                                                                                       */
+  uint64_t *comm_fold;          /* optional, rows points: fold([folded_U.comm_W, core.comm_W], [1, c_eval])                          */
+} sp2_nn_snark;
+/* the prover's randomness: blinds_steps n_steps x rows / blinds_core rows = the blinds every instance commitment ends up with
+ * (rerandomised precommitted rows and fresh rest rows, bellpepper/r1cs.rs:467, 568-602); blind_eval_W: 2; d_vec: ck width   */
+typedef struct { const uint64_t *blinds_steps, *blinds_core, *blind_eval_W, *d_vec, *r_delta, *r_beta; } sp2_nn_rand;
+/* prep_prove's commitment half on an sp2_neutronnova_prep_prove state: commits the precommitted section of every instance
+ * (blinds_pre_steps: n_steps x pre_rows, blinds_pre_core: pre_rows; outputs may be NULL) and caches the unblinded rows
+ * (HyraxPCS::commit_without_blind, hyrax_pc.rs:533-567) that make every later commitment operation fixed-base.             */
+int32_t sp2_neutronnova_prep_commit(sp2_ctx *ctx, sp2_nn_prep *prep, const sp2_ck *ck, const uint64_t *blinds_pre_steps,
+                                    const uint64_t *blinds_pre_core, uint64_t *comm_pre_steps_out, uint64_t *comm_pre_core_out);
+/* phase_ms (optional, 10 floats, host wall clock): rerandomize + commit_zeros, instance transcript, nifs, fold_witness,
+ * outer_sumcheck_batched, compute_eval_table_sparse, inner_sumcheck_batched, eval commitments + c_eval, pcs_prove, total    */
+int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *prep, const uint8_t *vk_digest, const sp2_nn_rand *rand, sp2_nn_snark *snark,
+                                    float *phase_ms);
+
 /* ---- host Keccak256Transcript (src/provider/keccak.rs:18-105 behind TranscriptEngineTrait, src/traits/transcript.rs) ----
  * Host-side Fiat-Shamir for drivers that interleave per-round device calls with transcript steps (a Rust caller keeps
  * using its own Keccak256Transcript; this is the same object for C/C++/Python hosts).  Scalars are Montgomery limbs. */

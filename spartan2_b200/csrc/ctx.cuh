@@ -21,7 +21,7 @@ struct sp2_ctx {
   std::string err;
   uint64_t launches = 0;                // kernels launched through this context (bench's gpu_launches)
   // scratch slots: grown on demand, reused across calls (cudaMalloc/cudaFree are synchronising)
-  static const int NSLOT = 16;
+  static const int NSLOT = 24;
   void *slot[NSLOT] = {nullptr};
   size_t slot_bytes[NSLOT] = {0};
   void *pinned = nullptr;               // small pinned staging buffer for result read-back

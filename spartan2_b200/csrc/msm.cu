@@ -247,8 +247,9 @@ __global__ void __launch_bounds__(64) k_test_points(u64 seed, u32 n, aff *out) {
 namespace sp2 {
 
 // d_out[njobs]: Jacobian results (the caller normalises: sp2h::batch_normalize on the host, batch_normalize_dev here)
-int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, jac *d_out) {
+int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, jac *d_out, cudaStream_t stream, int slot_jobs, int slot_partials) {
   if (jobs_in.empty()) return SP2_OK;
+  if (!stream) stream = ctx->stream;
   std::vector<MsmJob> jobs(jobs_in);
   u32 parts = 0;
   for (auto &j : jobs) {
@@ -260,13 +261,13 @@ int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, 
   }
   const size_t nj = jobs.size();
   void *d_jobs, *d_partial;
-  SP2_TRY(scratch(ctx, 10, nj * sizeof(MsmJob), &d_jobs));
-  SP2_TRY(scratch(ctx, 11, (size_t)parts * sizeof(jac), &d_partial));
+  SP2_TRY(scratch(ctx, slot_jobs, nj * sizeof(MsmJob), &d_jobs));
+  SP2_TRY(scratch(ctx, slot_partials, (size_t)parts * sizeof(jac), &d_partial));
   // pageable source: the runtime stages it before cudaMemcpyAsync returns, so the local vector may die
-  SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), nj * sizeof(MsmJob), cudaMemcpyHostToDevice, ctx->stream));
-  k_msm_gather<<<(parts + GW - 1) / GW, MSM_THREADS, 0, ctx->stream>>>((const MsmJob *)d_jobs, (u32)nj, parts, ck->table, (jac *)d_partial);
+  SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), nj * sizeof(MsmJob), cudaMemcpyHostToDevice, stream));
+  k_msm_gather<<<(parts + GW - 1) / GW, MSM_THREADS, 0, stream>>>((const MsmJob *)d_jobs, (u32)nj, parts, ck->table, (jac *)d_partial);
   SP2_LAUNCH_CHECK();
-  k_msm_final<<<(unsigned)nj, 128, 0, ctx->stream>>>((const MsmJob *)d_jobs, (const jac *)d_partial, d_out);
+  k_msm_final<<<(unsigned)nj, 128, 0, stream>>>((const MsmJob *)d_jobs, (const jac *)d_partial, d_out);
   SP2_LAUNCH_CHECK();
   return SP2_OK;
 }

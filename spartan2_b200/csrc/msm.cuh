@@ -43,7 +43,9 @@ struct sp2_ck {
 namespace sp2 {
 // run `jobs` (host array; pointers inside are device pointers); d_out[njobs] JACOBIAN results
 // (normalise on the host: sp2h::batch_normalize)
-int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs, jac *d_out);
+// stream / scratch slots: a second MSM batch in flight on a side stream needs its own job and partial buffers
+int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs, jac *d_out, cudaStream_t stream = nullptr, int slot_jobs = 10,
+            int slot_partials = 11);
 int hyrax_bind_dev(sp2_ctx *ctx, const fe *d_poly, const fe *d_L, uint64_t rows, uint64_t r_len, fe *d_out);
 // window tables [nbase][MSM_NW][MSM_ND] of arbitrary device-resident affine bases (identity allowed): *table_out is cudaMalloc'ed
 int msm_build_tables(sp2_ctx *ctx, const aff *d_bases, uint32_t nbase, aff **table_out);

@@ -405,6 +405,8 @@ int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n,
 // =====================================================================================================================
 #include <atomic>
 #include <chrono>
+#include <functional>
+#include "msm.cuh"
 #include "r1cs.cuh"
 #include "sumcheck.cuh"
 
@@ -447,7 +449,20 @@ struct sp2_nn_prep {
   unsigned char *h_stage = nullptr;          // pinned staging for small uploads / head read-backs
   u32 seq = 0;
   std::vector<void *> owned;
+  // ---- commitment half (sp2_neutronnova_prep_commit / sp2_neutronnova_snark_prove) ----
+  const sp2_ck *ck = nullptr;
+  uint32_t rows = 0, pre_rows = 0, np = 0;   // commitment rows per instance, rows of the precommitted section, public inputs
+  aff *U = nullptr;                          // (n + 1) x rows UNBLINDED row commitments (commit_without_blind), affine, identity = (0,0); index n = core
+  aff *Ucore_tab = nullptr;                  // window tables [rows][33][128] of the core's unblinded rows (c_eval * U_core[row] by table lookups)
+  fe *Wfold = nullptr;                       // M: copy of the folded witness (the inner sum-check binds z_step in place)
+  fe *Wfin = nullptr;                        // M: W_fold + c_eval * W_core, the polynomial PCS::prove opens
+  fe *blinds_dev = nullptr;                  // (n + 1) x rows blinds of this prove | rows folded blinds
+  jac *pts = nullptr;                        // (n + 1) x rows + rows + 16 Jacobian scratch points
+  fe *pcs = nullptr;                         // PCS scratch: LZ | L | R | d_vec | z_vec | small scalars
+  std::vector<uint64_t> Xs, Xc;              // host copies of the public IO (n x np, np)
+  cudaStream_t side = nullptr; cudaEvent_t ev_fold = nullptr, ev_side = nullptr;
 };
+namespace sp2 { struct NnHooks { std::function<int(const std::vector<fe> &)> after_fold; }; }
 
 namespace {
 
@@ -771,6 +786,10 @@ void sp2_neutronnova_prep_free(sp2_nn_prep *P) {
   cudaStreamSynchronize(P->ctx->stream);
   for (int q = 0; q < 8; q++) if (P->peer_opened[q]) cudaIpcCloseMemHandle(P->peer_x[q]);
   for (void *p : P->owned) cudaFree(p);
+  if (P->Ucore_tab) cudaFree(P->Ucore_tab);
+  if (P->side) cudaStreamDestroy(P->side);
+  if (P->ev_fold) cudaEventDestroy(P->ev_fold);
+  if (P->ev_side) cudaEventDestroy(P->ev_side);
   if (P->h_mail) cudaFreeHost(P->h_mail);
   if (P->h_stage) cudaFreeHost(P->h_stage);
   delete P;
@@ -792,6 +811,13 @@ static int32_t nn_prep_impl(sp2_ctx *ctx, const sp2_shape *S, int rank, int nran
   sp2_nn_prep *P = new sp2_nn_prep();
   P->ctx = ctx; P->S = S; P->n = n_steps; P->N = S->num_cons; P->M = S->num_vars; P->ncols = S->num_cols;
   P->rank = rank; P->nranks = nranks; P->n_total = (uint32_t)n_total;
+  P->np = (uint32_t)S->num_public;
+  if (P->np) {                                      // public IO of the instances (folded on the host: X_acc = sum_i w_i X_i)
+    if (nranks > 1) { delete P; return set_error(ctx, SP2_ERR_UNSUPPORTED, "neutronnova: instance sharding needs step circuits without public IO"); }
+    P->Xs.resize((size_t)n_steps * P->np * 4); P->Xc.resize((size_t)P->np * 4);
+    for (uint32_t i = 0; i < n_steps; i++) memcpy(&P->Xs[(size_t)i * P->np * 4], step_zs + ((size_t)i * S->num_cols + S->num_vars + 1) * 4, (size_t)P->np * 32);
+    memcpy(P->Xc.data(), core_z + (S->num_vars + 1) * 4, (size_t)P->np * 32);
+  }
   while ((1u << P->ell_b) < n_total) P->ell_b++;
   while ((1ull << P->ell) < P->N) P->ell++;
   P->left = 1u << ((P->ell + 1) / 2); P->right = 1u << (P->ell / 2);          // compute_tensor_decomp (:58-67)
@@ -860,7 +886,7 @@ int32_t sp2_neutronnova_prep_prove_sharded(sp2_ctx *ctx, const sp2_shape *S, int
  * phase_ms (optional, 6 floats): nifs, fold_witness, outer_sumcheck_batched, compute_eval_table_sparse,
  * inner_sumcheck_batched, total — host wall clock (every phase ends in a host wait). */
 static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
-                             sp2_nn_proof *pf, float *phase_ms) {
+                             sp2_nn_proof *pf, float *phase_ms, const sp2::NnHooks *hooks = nullptr) {
   cudaSetDevice(ctx->device);
   if (!P || !tsh || !pf) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: null argument");
   if (comm && (!comm->connected || comm->dc.n != P->nranks || comm->dc.rank != P->rank)) return set_error(ctx, SP2_ERR_INTERNAL, "neutronnova_prove: comm does not match the prep state");
@@ -1041,9 +1067,19 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
       SP2_LAUNCH_CHECK();
     }
   }
-  SP2_CUDA_OK(cudaMemcpyAsync(P->z_core, P->zc, (size_t)M * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+  const u32 np = P->np;
+  SP2_CUDA_OK(cudaMemcpyAsync(P->z_core, P->zc, (size_t)(M + 1 + np) * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));   // [W | 1 | X_core]
   k_set_one<<<1, 32, 0, ctx->stream>>>(P->z_step + M); SP2_LAUNCH_CHECK();
-  k_set_one<<<1, 32, 0, ctx->stream>>>(P->z_core + M); SP2_LAUNCH_CHECK();
+  std::vector<fe> Xacc(np + 1, zero), Xcore(np + 1, zero);                // [1 | X]: R1CSInstance::fold_multiple's X part (neutronnova_zk.rs:1231-1239)
+  Xacc[0] = one; Xcore[0] = one;
+  if (np) {
+    std::vector<fe> w(n_total);
+    for (u32 i = 0; i < n_total; i++) { fe wi = one; u32 k = i; for (u32 t = 0; t < ell_b; t++) { wi = HF::mul(wi, (k & 1u) ? r_bs[t] : HF::sub(one, r_bs[t])); k >>= 1; } w[i] = wi; }
+    for (u32 i = 0; i < n_total; i++) for (u32 j = 0; j < np; j++) Xacc[1 + j] = HF::add(Xacc[1 + j], HF::mul(w[i], H::load(&P->Xs[((size_t)i * np + j) * 4])));
+    for (u32 j = 0; j < np; j++) Xcore[1 + j] = H::load(&P->Xc[(size_t)j * 4]);
+    SP2_TRY(stage(&Xacc[1], np * sizeof(fe), P->z_step + M + 1));
+  }
+  if (hooks && hooks->after_fold) SP2_TRY(hooks->after_fold(r_bs));
   if (pf->heads) SP2_CUDA_OK(cudaMemcpyAsync(heads_stage + 12 * sizeof(fe), P->z_step, 8 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
   ph[1] = ms_since(t_phase); t_phase = now();      // (asynchronous: the device time of this phase lands in the next one)
 
@@ -1145,13 +1181,28 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
     SP2_TRY(nn_wait(P, seq));
     for (int k = 0; k < 4; k++) { fi[k] = nn_mail(P)[k]; H::store(pf->inner_final + 4 * k, fi[k]); } }
   // eval_W = (eval_Z - r_y[0] * eval_X) / (1 - r_y[0]); X = [1]: eval_X = prod (1 - r_y[1..])
-  fe eval_X = one;
-  for (u32 j = 1; j < my; j++) eval_X = HF::mul(eval_X, HF::sub(one, r_y[j]));
+  // SparsePolynomial::evaluate of [1 | X] at r_y[1..] (polys/multilinear.rs:190-207)
+  auto sparse_eval = [&](const std::vector<fe> &Xv) {
+    const size_t zlen = Xv.size(), nvars = my - 1; size_t p2 = 1, nvz = 0; while (p2 < zlen) { p2 <<= 1; nvz++; }
+    const size_t skip = nvars - 1 - nvz, k = nvars - skip;
+    std::vector<fe> chis((size_t)1 << k); chis[0] = one; size_t size = 1;
+    for (size_t t = k; t-- > 0;) {                      // EqPolynomial::evals_from_points (eq.rs:59-92), MSB-first
+      const fe rt = r_y[1 + skip + t];
+      for (size_t i = 0; i < size; i++) { const fe hi = HF::mul(chis[i], rt); chis[size + i] = hi; chis[i] = HF::sub(chis[i], hi); }
+      size *= 2;
+    }
+    fe acc = zero;
+    for (size_t i = 0; i < zlen; i++) acc = HF::add(acc, HF::mul(Xv[i], chis[i]));
+    fe common = one;
+    for (size_t i = 0; i < skip; i++) common = HF::mul(common, HF::sub(one, r_y[1 + i]));
+    return HF::mul(common, acc);
+  };
+  const fe eval_X = sparse_eval(Xacc), eval_Xc = sparse_eval(Xcore);
   const fe den = HF::sub(one, r_y[0]);
   if (HF::is_zero(den)) return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "neutronnova: r_y[0] = 1");
   const fe inv = HF::inv(den);
   H::store(pf->eval_W, HF::mul(HF::sub(fi[2], HF::mul(r_y[0], eval_X)), inv));
-  H::store(pf->eval_W + 4, HF::mul(HF::sub(fi[3], HF::mul(r_y[0], eval_X)), inv));
+  H::store(pf->eval_W + 4, HF::mul(HF::sub(fi[3], HF::mul(r_y[0], eval_Xc)), inv));
   pf->inner_ok = HF::eq(claim_js, HF::mul(fi[0], fi[2])) && HF::eq(claim_jc, HF::mul(fi[1], fi[3]));
   ph[4] = ms_since(t_phase);
   if (pf->heads) { SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); memcpy(pf->heads, heads_stage, 28 * sizeof(fe)); }
@@ -1215,6 +1266,275 @@ int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh,
 int32_t sp2_neutronnova_prove_sharded(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
                                       sp2_nn_proof *pf, float *phase_ms) {
   return nn_prove_impl(ctx, P, tsh, comm, allgather, user, pf, phase_ms);
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// The commitment half of the NeutronNova prove (non-ZK variant; the checker is oracle/oracle.c: orc_neutronnova_prove /
+// orc_neutronnova_verify, which follow NeutronNovaZkSNARK::{prove, verify}, src/neutronnova_zk.rs:1609-2093, 2096-2330, with
+// the in-circuit verifier replaced by direct absorbs):
+//   prep_commit : per-instance commit of the precommitted section (bellpepper/r1cs.rs:359-408 -> HyraxPCS::commit)
+//   snark_prove : rerandomize_commitment per step (hyrax_pc.rs:321-344) + commit_zeros of the rest rows (:305-319), the
+//                 transcript over all instances, HOT LOOPS A-C (nn_prove_impl), fold_blinds / fold_commitments_partial
+//                 (:795-874), the c_eval fold of the step and core claims (neutronnova_zk.rs:2019-2051) and PCS::prove
+//                 on W_fold + c_eval W_core (:2053-2064 -> hyrax_pc.rs:387-478, ipa.rs:125-170).
+// B200 design: every commitment operation is FIXED-BASE.  A Hyrax row commitment is linear in (row, blind), so
+//   rerandomised row           = U_row + r_new h                      (U_row = the unblinded row, cached by prep_commit)
+//   fold of n commitments      = commit(folded witness row, folded blind)           instead of n variable-base scalar
+//   fold with c_eval           = comm(W_fold row) + c_eval U_core_row + (b_fold + c_eval b_core) h       multiplications,
+// i.e. table gathers only (the key's window tables, plus 33 x 128 tables of the core's unblinded rows built at prep time):
+// no doubling chain anywhere — a 256-bit variable-base scalar multiplication is ~256 serial doublings of ~5 us each on a GPU
+// thread.  The one full-width MSM (13 rows x 2048 of the folded witness) runs on a side stream under the two sum-checks.
+// The group elements are the ones the reference computes, so the affine outputs are bit-identical (tests).
+// =====================================================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256) k_nn_axpy(fe *out, const fe *a, const fe *b, fe c, u64 n) {      // out = a + c * b
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) stg_fe(out + i, Fq::add(ldg_fe(a + i), Fq::mul(c, ldg_fe(b + i))));
+}
+__global__ void __launch_bounds__(256) k_nn_dot(const fe *a, const fe *b, u64 n, fe *out) {
+  __shared__ fe red[32];
+  Fq::acc acc = Fq::acc_zero();
+  for (u64 i = threadIdx.x; i < n; i += blockDim.x) Fq::mul_acc(acc, ldg_fe(a + i), ldg_fe(b + i));
+  fe x[1] = {Fq::acc_reduce(acc)};
+  block_sum_fq<1>(x, red);
+  if (threadIdx.x == 0) stg_fe(out, x[0]);
+}
+enum NnSlot { NS_EVAL = 0 /* 2 */, NS_BEVAL = 2 /* 2 */, NS_EVALF = 4, NS_BEVALF = 5, NS_CEVAL = 6, NS_RLZ = 7, NS_IP = 8, NS_RDELTA = 9, NS_RBETA = 10, NS_RY = 16 /* <= 40 */, NS_COUNT = 64 };
+
+int nn_palloc(sp2_nn_prep *P, size_t bytes, void **out) {
+  sp2_ctx *ctx = P->ctx; void *p;
+  SP2_CUDA_OK(cudaMalloc(&p, std::max<size_t>(bytes, 64)));
+  P->owned.push_back(p); *out = p;
+  return SP2_OK;
+}
+}  // namespace
+
+extern "C" {
+
+/* prep_prove's commitment half: blinds_pre_* are the blinds of the precommitted rows (n_steps x pre_rows, pre_rows); comm_pre_*_out
+ * receive commit(W_i[precommitted], blinds) — the PrecommittedState a Rust caller keeps (bellpepper/r1cs.rs:359-408). */
+int32_t sp2_neutronnova_prep_commit(sp2_ctx *ctx, sp2_nn_prep *P, const sp2_ck *ck, const uint64_t *blinds_pre_steps, const uint64_t *blinds_pre_core,
+                                    uint64_t *comm_pre_steps_out, uint64_t *comm_pre_core_out) {
+  cudaSetDevice(ctx->device);
+  if (!P || !ck) return set_error(ctx, SP2_ERR_INTERNAL, "prep_commit: null argument");
+  const sp2_shape *S = P->S;
+  const uint64_t width = ck->n, M = P->M;
+  if (P->nranks > 1) return set_error(ctx, SP2_ERR_UNSUPPORTED, "prep_commit: the commitment half runs on the single-GPU prep state");
+  if (S->num_shared) return set_error(ctx, SP2_ERR_UNSUPPORTED, "prep_commit: circuits with a shared witness section are not offloaded");
+  if (M % width || S->num_precommitted % width) return set_error(ctx, SP2_ERR_INVALID_WITNESS_LENGTH, "prep_commit: witness sections must be multiples of the commitment width");
+  if (P->U) return set_error(ctx, SP2_ERR_INTERNAL, "prep_commit: already committed");
+  const uint32_t n = P->n, rows = (uint32_t)(M / width), pre_rows = (uint32_t)(S->num_precommitted / width);
+  P->ck = ck; P->rows = rows; P->pre_rows = pre_rows;
+  const size_t nrow = (size_t)(n + 1) * rows;
+  void *p;
+  SP2_TRY(nn_palloc(P, nrow * sizeof(aff), &p)); P->U = (aff *)p;
+  SP2_TRY(nn_palloc(P, (nrow + 2 * rows + 16) * sizeof(jac), &p)); P->pts = (jac *)p;   // [instance rows | folded rows | 2 eval | final rows + 4]
+  SP2_TRY(nn_palloc(P, (nrow + 2 * rows + 16) * sizeof(fe), &p)); P->blinds_dev = (fe *)p;
+  SP2_TRY(nn_palloc(P, M * sizeof(fe), &p)); P->Wfold = (fe *)p;
+  SP2_TRY(nn_palloc(P, M * sizeof(fe), &p)); P->Wfin = (fe *)p;
+  SP2_TRY(nn_palloc(P, (5 * width + 2 * rows + NS_COUNT + 64) * sizeof(fe), &p)); P->pcs = (fe *)p;
+  SP2_CUDA_OK(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
+  SP2_CUDA_OK(cudaEventCreateWithFlags(&P->ev_fold, cudaEventDisableTiming));
+  SP2_CUDA_OK(cudaEventCreateWithFlags(&P->ev_side, cudaEventDisableTiming));
+  // commit_without_blind of every row of every instance (hyrax_pc.rs:533-567); the zero rest rows come out as the identity
+  std::vector<MsmJob> jobs(nrow);
+  for (uint32_t i = 0; i <= n; i++)
+    for (uint32_t r = 0; r < rows; r++) {
+      MsmJob &j = jobs[(size_t)i * rows + r]; memset(&j, 0, sizeof(j));
+      j.scalars = (i < n ? P->Ws + (size_t)i * M : P->zc) + (size_t)r * width; j.len = (u32)width;
+    }
+  SP2_TRY(msm_run(ctx, ck, jobs, P->pts));
+  SP2_TRY(batch_normalize_dev(ctx, P->pts, nrow, P->U));
+  // the caller's PrecommittedState: commit(W[precommitted], blinds) = U + blind * h
+  const size_t npre = (size_t)(n + 1) * pre_rows;
+  if (npre) {
+    std::vector<uint64_t> hb(npre * 4);
+    memcpy(hb.data(), blinds_pre_steps, (size_t)n * pre_rows * 32); memcpy(hb.data() + (size_t)n * pre_rows * 4, blinds_pre_core, (size_t)pre_rows * 32);
+    SP2_CUDA_OK(cudaMemcpyAsync(P->blinds_dev, hb.data(), npre * 32, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<MsmJob> jb(npre);
+    for (uint32_t i = 0; i <= n; i++)
+      for (uint32_t r = 0; r < pre_rows; r++) {
+        MsmJob &j = jb[(size_t)i * pre_rows + r]; memset(&j, 0, sizeof(j));
+        j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = P->blinds_dev + (size_t)i * pre_rows + r;
+        j.add_aff = P->U + (size_t)i * rows + r;
+      }
+    SP2_TRY(msm_run(ctx, ck, jb, P->pts));
+    std::vector<uint64_t> hj(npre * 12), ha(npre * 8);
+    SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), P->pts, npre * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+    SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    sp2h::batch_normalize(hj.data(), npre, ha.data());
+    if (comm_pre_steps_out) memcpy(comm_pre_steps_out, ha.data(), (size_t)n * pre_rows * 64);
+    if (comm_pre_core_out) memcpy(comm_pre_core_out, ha.data() + (size_t)n * pre_rows * 8, (size_t)pre_rows * 64);
+  }
+  // window tables of the core's unblinded rows: c_eval * U_core[row] becomes 33 table lookups
+  SP2_TRY(msm_build_tables(ctx, P->U + (size_t)n * rows, rows, &P->Ucore_tab));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return SP2_OK;
+}
+
+/* phase_ms (optional, 10 floats, host wall clock): rerandomize + commit_zeros, instance transcript, nifs, fold_witness,
+ * outer_sumcheck_batched, compute_eval_table_sparse, inner_sumcheck_batched, eval commitments + c_eval, pcs_prove, total */
+int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t *vk_digest, const sp2_nn_rand *rnd, sp2_nn_snark *sn, float *phase_ms) {
+  cudaSetDevice(ctx->device);
+  if (!P || !rnd || !sn || !vk_digest) return set_error(ctx, SP2_ERR_INTERNAL, "snark_prove: null argument");
+  if (!P->U) return set_error(ctx, SP2_ERR_INTERNAL, "snark_prove: sp2_neutronnova_prep_commit has not run on this prep state");
+  typedef NnHost H;
+  const sp2_ck *ck = P->ck;
+  const uint32_t n = P->n, rows = P->rows, pre_rows = P->pre_rows, np = P->np;
+  const uint64_t width = ck->n, M = P->M;
+  const size_t nrow = (size_t)(n + 1) * rows;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) { return (float)(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()); };
+  const auto t_begin = now(); auto t_phase = t_begin;
+  float ph[10] = {0};
+  sn->rows = rows;
+  fe *small = P->pcs, *LZ = small + NS_COUNT, *Ltab = LZ + width, *Rtab = Ltab + rows, *dvec = Rtab + width, *zvec = dvec + width;
+  fe *blind_fold = P->blinds_dev + nrow, *blind_fin = blind_fold + rows;
+  // pinned staging: [blinds | d_vec | Jacobian read-backs]
+  const size_t stage_need = (nrow + width + 16) * sizeof(fe) + (nrow + rows + 8) * sizeof(jac);
+  void *hp; SP2_TRY(pinned(ctx, stage_need, &hp));
+  uint8_t *h_in = (uint8_t *)hp; uint64_t *h_jac = (uint64_t *)(h_in + (nrow + width + 16) * sizeof(fe));
+  // ---- rerandomize_commitment (precommitted rows) + commit_zeros (rest rows): row = U_row + blind * h ----------------
+  memcpy(h_in, rnd->blinds_steps, (size_t)n * rows * 32); memcpy(h_in + (size_t)n * rows * 32, rnd->blinds_core, (size_t)rows * 32);
+  memcpy(h_in + nrow * 32, rnd->d_vec, width * 32);
+  SP2_CUDA_OK(cudaMemcpyAsync(P->blinds_dev, h_in, nrow * 32, cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(dvec, h_in + nrow * 32, width * 32, cudaMemcpyHostToDevice, ctx->stream));
+  { std::vector<MsmJob> jobs(nrow);
+    for (size_t k = 0; k < nrow; k++) {
+      MsmJob &j = jobs[k]; memset(&j, 0, sizeof(j));
+      j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = P->blinds_dev + k; j.add_aff = P->U + k;
+    }
+    SP2_TRY(msm_run(ctx, ck, jobs, P->pts)); }
+  SP2_CUDA_OK(cudaMemcpyAsync(h_jac, P->pts, nrow * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  { std::vector<uint64_t> aff_all(nrow * 8);
+    sp2h::batch_normalize(h_jac, nrow, aff_all.data());
+    memcpy(sn->comm_W_steps, aff_all.data(), (size_t)n * rows * 64); memcpy(sn->comm_W_core, aff_all.data() + (size_t)n * rows * 8, (size_t)rows * 64); }
+  ph[0] = ms_since(t_phase); t_phase = now();
+  // ---- transcript over the instances (neutronnova_zk.rs:1727-1733, 552-556; R1CSInstance bytes r1cs/mod.rs:728-736) -----
+  sp2_transcript tsobj("neutronnova_prove");
+  sp2h::Transcript &ts = tsobj.t;
+  ts.absorb_bytes("vk", vk_digest, 32);
+  auto absorb_instance = [&](const char *label, const uint64_t *comm, const uint64_t *X) {
+    ts.push(label, strlen(label)); ts.push("poly_commitment_begin", 21);
+    for (uint32_t r = 0; r < rows; r++) ts.push_point(comm + 8 * r);
+    ts.push("poly_commitment_end", 19);
+    for (uint32_t j = 0; j < np; j++) { uint64_t c[4]; uint8_t b[32]; sp2h::from_mont(X + 4 * j, sp2h::FQ_MOD, sp2h::FQ_INV, c); sp2h::limbs_to_be(c, b); ts.push(b, 32); }
+  };
+  absorb_instance("core_instance", sn->comm_W_core, np ? P->Xc.data() : nullptr);
+  for (uint32_t i = 0; i < n; i++) absorb_instance("U", sn->comm_W_steps + (size_t)i * rows * 8, np ? &P->Xs[(size_t)i * np * 4] : nullptr);
+  ph[1] = ms_since(t_phase); t_phase = now();
+  // ---- HOT LOOPS A-C; right after the witness fold: copy W_fold, fold the blinds, and start the commitment of the folded
+  // witness rows on the side stream (it overlaps the outer and inner sum-checks) -------------------------------------------
+  jac *pts_fold = P->pts + nrow;
+  sp2::NnHooks hooks;
+  hooks.after_fold = [&](const std::vector<fe> &) -> int {
+    SP2_CUDA_OK(cudaMemcpyAsync(P->Wfold, P->z_step, M * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+    // fold_blinds (hyrax_pc.rs:795-819): blinds_dev is [instance][row] = n vectors of `rows` entries; weights at small + 128
+    k_fold_vectors<<<1, NF_THREADS, 0, ctx->stream>>>(P->blinds_dev, n, rows, P->small + 128, blind_fold);
+    SP2_LAUNCH_CHECK();
+    SP2_CUDA_OK(cudaEventRecord(P->ev_fold, ctx->stream));
+    SP2_CUDA_OK(cudaStreamWaitEvent(P->side, P->ev_fold, 0));
+    if (pre_rows) {
+      std::vector<MsmJob> jobs(pre_rows);
+      for (uint32_t r = 0; r < pre_rows; r++) { MsmJob &j = jobs[r]; memset(&j, 0, sizeof(j)); j.scalars = P->Wfold + (size_t)r * width; j.len = (u32)width; }
+      SP2_TRY(msm_run(ctx, ck, jobs, pts_fold, P->side, 16, 17));
+    }
+    SP2_CUDA_OK(cudaEventRecord(P->ev_side, P->side));
+    return SP2_OK;
+  };
+  float ph_core[6];
+  SP2_TRY(nn_prove_impl(ctx, P, &tsobj, nullptr, nullptr, nullptr, &sn->base, ph_core, &hooks));
+  for (int k = 0; k < 5; k++) ph[2 + k] = ph_core[k];
+  t_phase = now();
+  // ---- commitments to eval_W_step / eval_W_core, c_eval (neutronnova_zk.rs:1953-2017 in its non-ZK form) ------------------
+  const fe eval_s = H::load(sn->base.eval_W), eval_c = H::load(sn->base.eval_W + 4);
+  const fe be_s = H::load(rnd->blind_eval_W), be_c = H::load(rnd->blind_eval_W + 4);
+  memcpy(sn->blind_eval_W, rnd->blind_eval_W, 64);
+  { fe up[4] = {eval_s, eval_c, be_s, be_c};
+    memcpy(h_in, up, sizeof(up));
+    SP2_CUDA_OK(cudaMemcpyAsync(small + NS_EVAL, h_in, sizeof(up), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<MsmJob> jobs(2);
+    for (int b = 0; b < 2; b++) { MsmJob &j = jobs[b]; memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = small + NS_EVAL + b;
+      j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = small + NS_BEVAL + b; }
+    SP2_TRY(msm_run(ctx, ck, jobs, pts_fold + rows));
+    SP2_CUDA_OK(cudaMemcpyAsync(h_jac, pts_fold + rows, 2 * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+    SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); }
+  uint64_t ce[16];
+  sp2h::batch_normalize(h_jac, 2, ce);
+  if (sn->comm_eval_W) memcpy(sn->comm_eval_W, ce, 128);
+  ts.absorb_point("comm_eval_W_step", ce); ts.absorb_point("comm_eval_W_core", ce + 8);
+  fe c_eval; { uint8_t dg[64]; uint64_t o[4]; ts.squeeze("c_eval", dg); sp2h::fq_from_uniform(dg, o); c_eval = H::load(o); }
+  if (sn->c_eval) H::store(sn->c_eval, c_eval);
+  ph[7] = ms_since(t_phase); t_phase = now();
+  // ---- fold the step and core claims with c_eval and open (neutronnova_zk.rs:2019-2064) -----------------------------------
+  const uint32_t my = sn->base.rounds_y, m = my - 1;
+  int nvr = 0; while ((1u << nvr) < rows) nvr++;
+  if ((1u << nvr) != rows || (width & (width - 1))) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "snark_prove: rows and width must be powers of two");
+  const fe eval_f = HF::add(eval_s, HF::mul(c_eval, eval_c)), be_f = HF::add(be_s, HF::mul(c_eval, be_c));
+  { std::vector<fe> up(NS_COUNT, HF::zero());
+    up[NS_EVALF] = eval_f; up[NS_BEVALF] = be_f; up[NS_CEVAL] = c_eval; up[NS_RDELTA] = H::load(rnd->r_delta); up[NS_RBETA] = H::load(rnd->r_beta);
+    for (uint32_t j = 0; j < m; j++) up[NS_RY + j] = H::load(sn->base.r_y + 4 * (j + 1));
+    memcpy(h_in, up.data() + NS_EVALF, (NS_COUNT - NS_EVALF) * sizeof(fe));
+    SP2_CUDA_OK(cudaMemcpyAsync(small + NS_EVALF, h_in, (NS_COUNT - NS_EVALF) * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream)); }
+  const unsigned nbM = (unsigned)std::min<u64>((M + 255) / 256, (u64)ctx->num_sms * 8);
+  k_nn_axpy<<<nbM, 256, 0, ctx->stream>>>(P->Wfin, P->Wfold, P->zc, c_eval, M);                       // W = W_fold + c_eval W_core
+  SP2_LAUNCH_CHECK();
+  k_nn_axpy<<<1, 256, 0, ctx->stream>>>(blind_fin, blind_fold, P->blinds_dev + (size_t)n * rows, c_eval, rows);   // fold_blinds with [1, c_eval]
+  SP2_LAUNCH_CHECK();
+  SP2_TRY(eq_table_dev(ctx, small + NS_RY + nvr, (uint32_t)(m - nvr), Rtab));
+  const fe *LZp = LZ, *rLZ = small + NS_RLZ;
+  if (nvr > 0) {
+    SP2_TRY(eq_table_dev(ctx, small + NS_RY, (uint32_t)nvr, Ltab));
+    SP2_TRY(hyrax_bind_dev(ctx, P->Wfin, Ltab, rows, width, LZ));
+    k_nn_dot<<<1, 256, 0, ctx->stream>>>(Ltab, blind_fin, rows, small + NS_RLZ);
+    SP2_LAUNCH_CHECK();
+  } else { LZp = P->Wfin; rLZ = blind_fin; }
+  k_nn_dot<<<1, 256, 0, ctx->stream>>>(Rtab, dvec, width, small + NS_IP);
+  SP2_LAUNCH_CHECK();
+  SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_side, 0));                                        // the folded-witness rows are committed
+  std::vector<MsmJob> jobs(rows + 4);
+  for (uint32_t r = 0; r < rows; r++) {        // comm[r] = comm(W_fold row) + c_eval U_core[r] + (b_fold[r] + c_eval b_core[r]) h
+    MsmJob &j = jobs[r]; memset(&j, 0, sizeof(j));
+    j.nextra = 2; j.extra_base[0] = r; j.extra_scalar[0] = small + NS_CEVAL; j.extra_tab[0] = P->Ucore_tab;
+    j.extra_base[1] = ck->idx_h(); j.extra_scalar[1] = blind_fin + r;
+    if (r < pre_rows) j.add_jac = pts_fold + r;
+  }
+  { MsmJob &j = jobs[rows]; memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = small + NS_EVALF;
+    j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = small + NS_BEVALF; }                           // comm_eval
+  { MsmJob &j = jobs[rows + 1]; memset(&j, 0, sizeof(j)); j.scalars = LZp; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = rLZ; }   // comm_LZ
+  { MsmJob &j = jobs[rows + 2]; memset(&j, 0, sizeof(j)); j.scalars = dvec; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = small + NS_RDELTA; }   // delta
+  { MsmJob &j = jobs[rows + 3]; memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = small + NS_IP;
+    j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = small + NS_RBETA; }                            // beta
+  jac *pts_out = pts_fold + rows + 2;            // (the row jobs read pts_fold[0..pre_rows) as addends and write pts_out[0..rows): disjoint)
+  SP2_TRY(msm_run(ctx, ck, jobs, pts_out));
+  SP2_CUDA_OK(cudaMemcpyAsync(h_jac, pts_out, (rows + 4) * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+  fe *h_small = (fe *)h_in;
+  SP2_CUDA_OK(cudaMemcpyAsync(h_small, small, NS_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nvr == 0) SP2_CUDA_OK(cudaMemcpyAsync(h_small + NS_RLZ, blind_fin, sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint64_t> outp((size_t)(rows + 4) * 8);
+  sp2h::batch_normalize(h_jac, rows + 4, outp.data());
+  const uint64_t *comm = outp.data(), *comm_eval = comm + 8 * (size_t)rows, *comm_LZ = nvr > 0 ? comm_eval + 8 : comm, *p_delta = comm_eval + 16, *p_beta = comm_eval + 24;
+  if (sn->comm_fold) memcpy(sn->comm_fold, comm, (size_t)rows * 64);
+  memcpy(sn->delta, p_delta, 64); memcpy(sn->beta, p_beta, 64);
+  ts.absorb_commitment("poly_com", comm, rows);                                                         // hyrax_pc.rs:410
+  ts.dom_sep("inner product argument (linear)");                                                        // ipa.rs:134-153
+  ts.push("U", 1); ts.push_point(comm_LZ); ts.push_point(comm_eval);
+  ts.absorb_point("delta", p_delta); ts.absorb_point("beta", p_beta);
+  fe r_ipa; { uint8_t dg[64]; uint64_t o[4]; ts.squeeze("r", dg); sp2h::fq_from_uniform(dg, o); r_ipa = H::load(o); }
+  k_nn_axpy<<<(unsigned)((width + 255) / 256), 256, 0, ctx->stream>>>(zvec, dvec, LZp, r_ipa, width);   // z_vec = d + r LZ   (ipa.rs:155-167)
+  SP2_LAUNCH_CHECK();
+  SP2_CUDA_OK(cudaMemcpyAsync(sn->z_vec, zvec, width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  H::store(sn->z_delta, HF::add(HF::mul(r_ipa, h_small[NS_RLZ]), H::load(rnd->r_delta)));
+  H::store(sn->z_beta, HF::add(HF::mul(r_ipa, be_f), H::load(rnd->r_beta)));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ph[8] = ms_since(t_phase);
+  ph[9] = ms_since(t_begin);
+  if (phase_ms) memcpy(phase_ms, ph, sizeof(ph));
+  return SP2_OK;
 }
 
 }  // extern "C"

@@ -264,6 +264,16 @@ class _NnProofC(C.Structure):
                [("outer_ok", C.c_int32), ("inner_ok", C.c_int32)]
 
 
+class _NnSnarkC(C.Structure):
+    _fields_ = [("base", _NnProofC), ("rows", C.c_uint64)] + \
+               [(k, C.c_void_p) for k in ("comm_W_steps", "comm_W_core", "blind_eval_W", "delta", "beta", "z_vec", "z_delta", "z_beta", "comm_eval_W",
+                                          "c_eval", "comm_fold")]
+
+
+class _NnRandC(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("blinds_steps", "blinds_core", "blind_eval_W", "d_vec", "r_delta", "r_beta")]
+
+
 class NeutronNovaProver:
     """The fused path of the library (include/spartan2_b200.h: sp2_neutronnova_prep_prove / sp2_neutronnova_prove): the same
     HOT LOOPS A-C as `run` above, with the round loop, the per-round scalar algebra and the Keccak transcript in C++
@@ -311,6 +321,50 @@ class NeutronNovaProver:
                 allb = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
                 ctx.check(ctx.L.sp2_neutronnova_prep_connect(h, _p(allb)))
         self.h = h
+
+    # ---- the full prove incl. its commitment half (sp2_neutronnova_prep_commit / sp2_neutronnova_snark_prove) ----------
+    def commit(self, ck, blinds_pre_steps, blinds_pre_core):
+        """prep_prove's commitment half: commits the precommitted section of every instance; returns (comm_pre_steps (n*pre_rows, 8),
+        comm_pre_core (pre_rows, 8)) — the PrecommittedState commitments."""
+        ctx, S = self.ctx, self.S
+        self.ck = ck
+        pre_rows = S.num_precommitted // ck.n
+        bs = _fe(blinds_pre_steps); bc = _fe(blinds_pre_core)
+        cs = np.zeros((max(self.n * pre_rows, 1), 8), dtype=np.uint64); cc = np.zeros((max(pre_rows, 1), 8), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_neutronnova_prep_commit(ctx.h, self.h, ck.h, _p(bs if bs.size else np.zeros((1, 4), dtype=np.uint64)),
+                                                    _p(bc if bc.size else np.zeros((1, 4), dtype=np.uint64)), _p(cs), _p(cc)))
+        return cs[:self.n * pre_rows], cc[:pre_rows]
+
+    SNARK_PHASES = ("rerandomize+commit_zeros", "instance_transcript", "nifs", "fold_witness", "outer_sumcheck_batched", "compute_eval_table_sparse",
+                    "inner_sumcheck_batched", "eval_commitments+c_eval", "pcs_prove", "total")
+
+    def snark_prove(self, vk_digest, blinds_steps, blinds_core, blind_eval_W, d_vec, r_delta, r_beta):
+        """The non-ZK NeutronNova prove (see include/spartan2_b200.h: sp2_nn_snark).  Returns (proof dict, phase_ms)."""
+        ctx, S, ck = self.ctx, self.S, self.ck
+        n = self.n; rows = S.num_vars // ck.n
+        ell_b = n.bit_length() - 1; ell = S.num_cons.bit_length() - 1; my = (2 * S.num_vars).bit_length() - 1
+        shapes = {"nifs_evals": (ell_b, 2), "nifs_polys": (ell_b, 4), "r_b": (ell_b,), "T_out": (1,), "outer_evals": (ell, 6), "outer_polys": (ell, 8),
+                  "r_x": (ell,), "claims_outer": (6,), "tau_at_rx": (1,), "r": (1,), "inner_evals": (my, 4), "inner_polys": (my, 6), "r_y": (my,),
+                  "inner_final": (4,), "eval_W": (2,), "heads": (28,)}
+        out = {k: np.zeros(v + (4,), dtype=np.uint64) for k, v in shapes.items()}
+        base = _NnProofC()
+        for k, a in out.items():
+            setattr(base, k, a.ctypes.data)
+        pts = lambda k: np.zeros((k, 8), dtype=np.uint64)   # noqa: E731
+        ext = {"comm_W_steps": pts(n * rows), "comm_W_core": pts(rows), "blind_eval_W": np.zeros((2, 4), dtype=np.uint64), "delta": pts(1), "beta": pts(1),
+               "z_vec": np.zeros((ck.n, 4), dtype=np.uint64), "z_delta": np.zeros((1, 4), dtype=np.uint64), "z_beta": np.zeros((1, 4), dtype=np.uint64),
+               "comm_eval_W": pts(2), "c_eval": np.zeros((1, 4), dtype=np.uint64), "comm_fold": pts(rows)}
+        sn = _NnSnarkC(); sn.base = base
+        for k, a in ext.items():
+            setattr(sn, k, a.ctypes.data)
+        arrs = [_fe(x) for x in (blinds_steps, blinds_core, blind_eval_W, d_vec, r_delta, r_beta)]
+        rv = _NnRandC(*[a.ctypes.data for a in arrs])
+        dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
+        ph = (C.c_float * 10)()
+        ctx.check(ctx.L.sp2_neutronnova_snark_prove(ctx.h, self.h, _p(dig), C.byref(rv), C.byref(sn), ph))
+        out.update(ext)
+        out["outer_ok"], out["inner_ok"] = bool(sn.base.outer_ok), bool(sn.base.inner_ok)
+        return out, dict(zip(self.SNARK_PHASES, [float(x) for x in ph]))
 
     @staticmethod
     def connect_in_process(provers):

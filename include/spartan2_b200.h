@@ -83,6 +83,10 @@ int32_t sp2_sumcheck_cubic_prove_dev(sp2_ctx *ctx, const uint64_t *claim, const 
 int32_t sp2_sumcheck_quad_prove_dev(sp2_ctx *ctx, const uint64_t *claim, uint32_t rounds, void *dA, void *dB,
                                     sp2_transcript_state *ts, uint64_t *polys, uint64_t *r, uint64_t *claims);
 
+/* EqSumCheckInstance::evaluation_points_zero_check_round0 (src/sumcheck.rs:1163-1271; used by the ZK prover's first round, :593-596):
+ * only t(inf) is summed (no Cz reads); out3 = (eval_0 = 0, eval_2, eval_3).  dA, dB: device tables of 2^l scalars, not modified. */
+int32_t sp2_sc_zero_check_round0_dev(sp2_ctx *ctx, const uint64_t *taus, uint32_t l, const void *dA, const void *dB, uint64_t *out3);
+
 /* ---- multi-GPU sharding of the sum-checks -------------------------------------------------
  * One process per GPU.  The 2^l hypercube is split cyclically on the low index bits (rank g owns entries
  * i = g mod nranks), so every bind pair is local; per round the <= 3 partial sums are exchanged by the round
@@ -167,11 +171,32 @@ void sp2_ck_free(sp2_ck *ck);
 /* Replaces DlogGroupExt::vartime_multiscalar_mul (src/provider/traits.rs:118-134 -> msm.rs:187-222):
  * out = sum_i scalars[i] * ck_i, affine (identity = all zero).  InvalidCommitmentKeyLength if n > key. */
 int32_t sp2_msm(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *scalars, uint32_t n, uint64_t *out_xy);
+/* ---- DlogGroupExt for ARBITRARY bases (src/provider/traits.rs:118-162): what a `GE: DlogGroupExt` wrapper forwards to ----
+ * Signed-digit Pippenger (c = 8, msm.rs:59-222) on the device; points affine (x, y limbs; identity all zero) in and out.
+ * vartime_multiscalar_mul(scalars, bases, _)                                                                            */
+int32_t sp2_msm_var(sp2_ctx *ctx, const uint64_t *scalars, const uint64_t *bases_xy, uint32_t n, uint64_t *out_xy);
+/* vartime_multiscalar_mul_small(scalars: u64, bases, _)  (msm.rs:367-620)                                               */
+int32_t sp2_msm_small_var(sp2_ctx *ctx, const uint64_t *scalars_u64, const uint64_t *bases_xy, uint32_t n, uint64_t *out_xy);
+/* batch_vartime_multiscalar_mul(scalars: &[Vec<_>], bases): k vectors (concatenated, lens[j] scalars each), each against
+ * bases[..lens[j]]; out_xy: k points                                                                                    */
+int32_t sp2_msm_batch_var(sp2_ctx *ctx, const uint64_t *scalars, const uint32_t *lens, uint32_t k, const uint64_t *bases_xy, uint64_t *out_xy);
+/* vartime_multiscalar_mul_shared_weights(weights, bases_rows) (msm.rs:228-356): bases_rows_xy = rows x n points, row-major;
+ * out_xy[r] = sum_i weights[i] * bases_rows[r][i]                                                                       */
+int32_t sp2_msm_shared_weights(sp2_ctx *ctx, const uint64_t *weights, uint32_t n, const uint64_t *bases_rows_xy, uint32_t rows, uint64_t *out_xy);
+
 /* Replaces HyraxPCS::commit / commit_zeros (hyrax_pc.rs:207-319): one Pedersen commitment per row of
  * ck-width scalars, out_rows[i] = <v_row_i, ck> + blinds[i] * h.  `is_small` is the reference's hint
  * (msm_small path); it does not change the result.                                               */
 int32_t sp2_hyrax_commit(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint64_t len, const uint64_t *blinds, uint64_t rows,
                          int32_t is_small, uint64_t *out_rows);
+/* HyraxPCS::commit_without_blind (hyrax_pc.rs:533-567): the raw row points (identity = all zero for an all-zero row)       */
+int32_t sp2_hyrax_commit_without_blind(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint64_t len, int32_t is_small, uint64_t *out_rows);
+/* HyraxPCS::commit_incremental (hyrax_pc.rs:569-607): out[i] = raw[i] (identity past n_raw) + <delta_row_i, ck> + blinds[i] h */
+int32_t sp2_hyrax_commit_incremental(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *raw_rows_xy, uint64_t n_raw, const uint64_t *delta, uint64_t len,
+                                     const uint64_t *blinds, uint64_t *out_rows);
+/* HyraxPCS::rerandomize_commitment (hyrax_pc.rs:321-344): out[i] = comm[i] + (r_new[i] - r_old[i]) h                         */
+int32_t sp2_hyrax_rerandomize(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *comm_rows_xy, const uint64_t *r_old, const uint64_t *r_new, uint64_t rows,
+                              uint64_t *out_rows);
 /* device-resident variant: d_out_rows_jac receives rows JACOBIAN points (x, y, z: 12 limbs; z = 0 identity) */
 int32_t sp2_hyrax_commit_dev(sp2_ctx *ctx, const sp2_ck *ck, const void *d_v, uint64_t len, const void *d_blinds, uint64_t rows,
                              void *d_out_rows_jac);
@@ -246,6 +271,11 @@ int32_t sp2_bind_tables_dev(sp2_ctx *ctx, void *const *d_tables, uint32_t ntable
 /* HyraxPCS::fold_commitments (src/provider/pcs/hyrax_pc.rs:737-793 -> msm_shared_weights, msm.rs:228-356):
  * out[row] = sum_i w[i] * comms[i*rows + row], affine in/out                                                      */
 int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n, uint32_t rows, const uint64_t *w, uint64_t *out_xy);
+/* HyraxPCS::fold_blinds (hyrax_pc.rs:795-819): out[row] = sum_k w[k] * blinds[k*rows + row]                                        */
+int32_t sp2_fold_blinds(sp2_ctx *ctx, const uint64_t *blinds, uint32_t n, uint32_t rows, const uint64_t *w, uint64_t *out);
+/* HyraxPCS::fold_commitments_partial (hyrax_pc.rs:821-874): data rows folded as group elements, rest rows = folded_blind[row] h   */
+int32_t sp2_fold_commitments_partial(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *comms_xy, uint32_t n, uint32_t rows, const uint64_t *w,
+                                     uint32_t num_data_rows, const uint64_t *folded_blind, uint64_t *out_xy);
 
 /* ---- small-value path (src/big_num/small_value.rs and its users in src/neutronnova_zk.rs) ---------------------------
  * to_small_vec_or_zero (small_value.rs:42-85) for up to 4 device tables of n_layers x N scalars (the Az, Bz, Cz layers of

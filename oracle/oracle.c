@@ -350,6 +350,41 @@ static void eq_cubic_points(const eqinst *E, const fe *A, const fe *B, const fe 
   }
   cubic_points_from_s(&s0, &s1, &slead, &sm1, out);
 }
+/* evaluation_points_zero_check_round0 (sumcheck.rs:1163-1271): first round of a zero-check (claim = 0, t(0) = 0 on a satisfied
+ * instance): only t(inf) is summed, no Cz reads; returns (eval_0, eval_2, eval_3) through derive_from_claim / its fallback */
+EXPORT void orc_zero_check_round0(const fe *taus, size_t l, const fe *A, const fe *B, fe out[3]) {
+  eqinst E; eqinst_new(&E, taus, l);
+  size_t len = (size_t)1 << l, half_p = len / 2;
+  int in_first = E.round < E.first_half;
+  acc9 tot; memset(&tot, 0, sizeof(tot));
+  if (in_first) {
+    const fe *el = E.eq_left[E.first_half - E.round], *er = E.eq_right[E.second_half];
+    size_t out_len = (size_t)1 << (E.first_half - E.round), in_len = (size_t)1 << E.second_half;
+    for (size_t xo = 0; xo < out_len; xo++) {
+      acc9 in; memset(&in, 0, sizeof(in));
+      for (size_t xi = 0; xi < in_len; xi++) {
+        size_t id = (xo << E.second_half) | xi; fe da, db, t;
+        f_sub(&FQ, &da, &A[id + half_p], &A[id]); f_sub(&FQ, &db, &B[id + half_p], &B[id]); f_mul(&FQ, &t, &da, &db);
+        f_mul_acc(&in, &er[xi], &t);
+      }
+      fe red; f_reduce9(&FQ, &red, &in); f_mul_acc(&tot, &el[xo], &red);
+    }
+  } else {
+    const fe *er = E.eq_right[E.l - E.round];
+    for (size_t id = 0; id < half_p; id++) { fe da, db, t; f_sub(&FQ, &da, &A[id + half_p], &A[id]); f_sub(&FQ, &db, &B[id + half_p], &B[id]); f_mul(&FQ, &t, &da, &db); f_mul_acc(&tot, &er[id], &t); }
+  }
+  fe tinf, zero; f_reduce9(&FQ, &tinf, &tot); f_zero(&zero);
+  const fe *p = &E.eval_eq_left, *eq0 = &E.c0[0], *sl = &E.slope[0], *em1 = &E.m1[0];
+  fe l1p, l1pinv, s0 = zero, s1 = zero, slead, tm1, sm1, t;
+  f_add(&FQ, &t, eq0, sl); f_mul(&FQ, &l1p, &t, p);
+  f_mul(&FQ, &slead, sl, p); f_mul(&FQ, &slead, &slead, &tinf);
+  if (f_inv(&FQ, &l1pinv, &l1p)) { fe t1; f_mul(&FQ, &t1, &s1, &l1pinv); f_dbl(&FQ, &tm1, &tinf); f_sub(&FQ, &tm1, &tm1, &t1); }
+  else f_dbl(&FQ, &tm1, &tinf);                                   /* fallback: t(-1) = 2 t_inf */
+  f_mul(&FQ, &sm1, em1, p); f_mul(&FQ, &sm1, &sm1, &tm1);
+  cubic_points_from_s(&s0, &s1, &slead, &sm1, out);
+  eqinst_free(&E);
+}
+
 static void eqinst_bound(eqinst *E, const fe *r) {          /* sumcheck.rs:1399-1405 */
   const fe *tau = &E->taus[E->round - 1];
   fe one, t, rt; f_one(&FQ, &one);

@@ -628,3 +628,10 @@ def neutronnova_verify(shape, keys, vk_digest, step_X, core_X, proof):
     dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
     sx = _fes(step_X) if np.size(step_X) else fe_array(1); cx = _fes(core_X) if np.size(core_X) else fe_array(1)
     return lib().orc_neutronnova_verify(shape.h, C.byref(kv), _p(dig), _p(sx), _p(cx), C.byref(pv))
+
+
+def zero_check_round0(taus, A, B):
+    """evaluation_points_zero_check_round0 (sumcheck.rs:1163-1271): (eval_0, eval_2, eval_3) of the first zero-check round"""
+    taus = _fes(taus); A = _fes(A); B = _fes(B); out = fe_array(3)
+    lib().orc_zero_check_round0(_p(taus), C.c_size_t(taus.shape[0]), _p(A), _p(B), _p(out))
+    return out

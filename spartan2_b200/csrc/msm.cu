@@ -397,6 +397,84 @@ int32_t sp2_hyrax_commit(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint
   return SP2_OK;
 }
 
+/* HyraxPCS::commit_without_blind (hyrax_pc.rs:533-567): the raw row points <v_row_i, ck>, identity (all zero) for an all-zero row */
+int32_t sp2_hyrax_commit_without_blind(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint64_t len, int32_t is_small, uint64_t *out_rows) {
+  (void)is_small;
+  cudaSetDevice(ctx->device);
+  const uint64_t rows = (len + ck->n - 1) / ck->n;
+  if (!rows) return SP2_OK;
+  void *d_v, *d_o;
+  SP2_TRY(scratch(ctx, 0, len * sizeof(fe) + 32, &d_v)); SP2_TRY(scratch(ctx, 2, rows * sizeof(jac) + 32, &d_o));
+  SP2_CUDA_OK(cudaMemcpyAsync(d_v, v, len * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<MsmJob> jobs(rows);
+  for (uint64_t i = 0; i < rows; i++) {
+    MsmJob &j = jobs[i]; memset(&j, 0, sizeof(j));
+    const uint64_t lo = i * ck->n, hi = std::min<uint64_t>(len, lo + ck->n);
+    j.scalars = (const fe *)d_v + lo; j.len = (u32)(hi - lo);
+  }
+  SP2_TRY(msm_run(ctx, ck, jobs, (jac *)d_o));
+  std::vector<uint64_t> hj(rows * 12);
+  SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), d_o, rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  sp2h::batch_normalize(hj.data(), rows, out_rows);
+  return SP2_OK;
+}
+
+/* HyraxPCS::commit_incremental (hyrax_pc.rs:569-607): out[i] = raw[i] (identity past n_raw) + <delta_row_i, ck> + blinds[i] * h */
+int32_t sp2_hyrax_commit_incremental(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *raw_rows_xy, uint64_t n_raw, const uint64_t *delta, uint64_t len,
+                                     const uint64_t *blinds, uint64_t *out_rows) {
+  cudaSetDevice(ctx->device);
+  const uint64_t rows = (len + ck->n - 1) / ck->n;
+  if (!rows) return SP2_OK;
+  void *d_v, *d_b, *d_o, *d_r;
+  SP2_TRY(scratch(ctx, 0, len * sizeof(fe) + 32, &d_v)); SP2_TRY(scratch(ctx, 1, rows * sizeof(fe) + 32, &d_b));
+  SP2_TRY(scratch(ctx, 2, rows * sizeof(jac) + 32, &d_o)); SP2_TRY(scratch(ctx, 3, rows * sizeof(aff) + 32, &d_r));
+  SP2_CUDA_OK(cudaMemcpyAsync(d_v, delta, len * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(d_b, blinds, rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemsetAsync(d_r, 0, rows * sizeof(aff), ctx->stream));
+  if (n_raw) SP2_CUDA_OK(cudaMemcpyAsync(d_r, raw_rows_xy, std::min<uint64_t>(n_raw, rows) * sizeof(aff), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<MsmJob> jobs(rows);
+  for (uint64_t i = 0; i < rows; i++) {
+    MsmJob &j = jobs[i]; memset(&j, 0, sizeof(j));
+    const uint64_t lo = i * ck->n, hi = std::min<uint64_t>(len, lo + ck->n);
+    j.scalars = (const fe *)d_v + lo; j.len = (u32)(hi - lo);
+    j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = (const fe *)d_b + i; j.add_aff = (const aff *)d_r + i;
+  }
+  SP2_TRY(msm_run(ctx, ck, jobs, (jac *)d_o));
+  std::vector<uint64_t> hj(rows * 12);
+  SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), d_o, rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  sp2h::batch_normalize(hj.data(), rows, out_rows);
+  return SP2_OK;
+}
+
+/* HyraxPCS::rerandomize_commitment (hyrax_pc.rs:321-344): out[i] = comm[i] + (r_new[i] - r_old[i]) * h (fixed-base table of h) */
+__global__ void k_fe_sub(const fe *a, const fe *b, fe *o, u64 n) { const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) stg_fe(o + i, Fq::sub(ldg_fe(a + i), ldg_fe(b + i))); }
+int32_t sp2_hyrax_rerandomize(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *comm_rows_xy, const uint64_t *r_old, const uint64_t *r_new, uint64_t rows,
+                              uint64_t *out_rows) {
+  cudaSetDevice(ctx->device);
+  if (!rows) return SP2_OK;
+  void *d_a, *d_b, *d_o, *d_r;
+  SP2_TRY(scratch(ctx, 0, 2 * rows * sizeof(fe) + 32, &d_a)); SP2_TRY(scratch(ctx, 1, rows * sizeof(fe) + 32, &d_b));
+  SP2_TRY(scratch(ctx, 2, rows * sizeof(jac) + 32, &d_o)); SP2_TRY(scratch(ctx, 3, rows * sizeof(aff) + 32, &d_r));
+  SP2_CUDA_OK(cudaMemcpyAsync(d_a, r_new, rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync((fe *)d_a + rows, r_old, rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(d_r, comm_rows_xy, rows * sizeof(aff), cudaMemcpyHostToDevice, ctx->stream));
+  k_fe_sub<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>((const fe *)d_a, (const fe *)d_a + rows, (fe *)d_b, rows);
+  SP2_LAUNCH_CHECK();
+  std::vector<MsmJob> jobs(rows);
+  for (uint64_t i = 0; i < rows; i++) {
+    MsmJob &j = jobs[i]; memset(&j, 0, sizeof(j));
+    j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = (const fe *)d_b + i; j.add_aff = (const aff *)d_r + i;
+  }
+  SP2_TRY(msm_run(ctx, ck, jobs, (jac *)d_o));
+  std::vector<uint64_t> hj(rows * 12);
+  SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), d_o, rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  sp2h::batch_normalize(hj.data(), rows, out_rows);
+  return SP2_OK;
+}
+
 /* bind_with_delayed (hyrax_pc.rs:38-54): out[i] = sum_j L[j] * poly[j * r_len + i] */
 int32_t sp2_hyrax_bind(sp2_ctx *ctx, const uint64_t *poly, const uint64_t *L, uint64_t rows, uint64_t r_len, uint64_t *out) {
   cudaSetDevice(ctx->device);

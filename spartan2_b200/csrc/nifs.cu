@@ -21,6 +21,7 @@
 #include "curve.cuh"
 #include "devutil.cuh"
 #include "host_transcript.h"
+#include "msm.cuh"
 #include "polys.cuh"
 
 using namespace sp2;
@@ -364,23 +365,56 @@ int32_t sp2_bind_tables_dev(sp2_ctx *ctx, void *const *d_tables, uint32_t ntable
   return SP2_OK;
 }
 
-/* HyraxPCS::fold_commitments as group elements: out[row] = sum_i w[i] * comms[i*rows + row] (affine in/out, host) */
+/* HyraxPCS::fold_commitments as group elements (hyrax_pc.rs:737-793): out[row] = sum_i w[i] * comms[i*rows + row] (affine in/out,
+ * host).  The reference batch-normalises and calls msm_shared_weights (msm.rs:228-356): here the same through the device's
+ * shared-weight Pippenger (msm_var.cu), one (row, window) CTA each — the digits of the n weights are taken once per window. */
 int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n, uint32_t rows, const uint64_t *w, uint64_t *out_xy) {
   cudaSetDevice(ctx->device);
   if (!n || !rows) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "fold_commitments: empty input");
-  void *dp, *dt, *dout; fe *dw;
-  const size_t tot = (size_t)n * rows;
-  SP2_TRY(scratch(ctx, 2, tot * sizeof(aff), &dp)); SP2_TRY(scratch(ctx, 3, tot * sizeof(jac), &dt)); SP2_TRY(scratch(ctx, 4, (size_t)rows * sizeof(jac), &dout));
+  std::vector<uint64_t> byrow((size_t)n * rows * 8);              // [instance][row] -> [row][instance]
+  for (uint32_t i = 0; i < n; i++) for (uint32_t r = 0; r < rows; r++) memcpy(&byrow[((size_t)r * n + i) * 8], comms_xy + ((size_t)i * rows + r) * 8, 64);
+  return sp2_msm_shared_weights(ctx, w, n, byrow.data(), rows, out_xy);
+}
+
+/* HyraxPCS::fold_blinds (hyrax_pc.rs:795-819): out[row] = sum_k w[k] * blinds[k*rows + row] */
+int32_t sp2_fold_blinds(sp2_ctx *ctx, const uint64_t *blinds, uint32_t n, uint32_t rows, const uint64_t *w, uint64_t *out) {
+  cudaSetDevice(ctx->device);
+  if (!n || !rows) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "fold_blinds: blinds and weights must be non-empty and same length");
+  void *db, *dout; fe *dw;
+  SP2_TRY(scratch(ctx, 2, (size_t)n * rows * sizeof(fe) + 32, &db)); SP2_TRY(scratch(ctx, 3, (size_t)rows * sizeof(fe) + 32, &dout));
   SP2_TRY(upload_small(ctx, 0, w, n, &dw));
-  SP2_CUDA_OK(cudaMemcpyAsync(dp, comms_xy, tot * sizeof(aff), cudaMemcpyHostToDevice, ctx->stream));
-  k_scalar_mul_var<<<(unsigned)((tot + 63) / 64), 64, 0, ctx->stream>>>((const aff *)dp, dw, n, rows, (jac *)dt);
+  SP2_CUDA_OK(cudaMemcpyAsync(db, blinds, (size_t)n * rows * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  k_fold_vectors<<<(rows + NF_THREADS - 1) / NF_THREADS, NF_THREADS, 0, ctx->stream>>>((const fe *)db, n, rows, dw, (fe *)dout);
   SP2_LAUNCH_CHECK();
-  k_point_col_sum<<<rows, 128, 0, ctx->stream>>>((const jac *)dt, n, rows, (jac *)dout);
-  SP2_LAUNCH_CHECK();
-  std::vector<uint64_t> hj((size_t)rows * 12);
-  SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), dout, (size_t)rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(out, dout, (size_t)rows * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  sp2h::batch_normalize(hj.data(), rows, out_xy);
+  return SP2_OK;
+}
+
+/* HyraxPCS::fold_commitments_partial (hyrax_pc.rs:821-874): the first num_data_rows rows are folded as group elements, the rest
+ * rows are folded_blind[row] * h (each instance's rest row is blind * h) — h from the key's fixed-base table */
+int32_t sp2_fold_commitments_partial(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *comms_xy, uint32_t n, uint32_t rows, const uint64_t *w,
+                                     uint32_t num_data_rows, const uint64_t *folded_blind, uint64_t *out_xy) {
+  cudaSetDevice(ctx->device);
+  if (!n || !rows) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "fold_commitments_partial: Commitments and weights must have the same length");
+  if (num_data_rows > rows) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "fold_commitments_partial: num_data_rows exceeds total_rows");
+  if (num_data_rows >= rows) return sp2_fold_commitments(ctx, comms_xy, n, rows, w, out_xy);
+  if (num_data_rows) {
+    std::vector<uint64_t> byrow((size_t)n * num_data_rows * 8);
+    for (uint32_t i = 0; i < n; i++) for (uint32_t r = 0; r < num_data_rows; r++) memcpy(&byrow[((size_t)r * n + i) * 8], comms_xy + ((size_t)i * rows + r) * 8, 64);
+    SP2_TRY(sp2_msm_shared_weights(ctx, w, n, byrow.data(), num_data_rows, out_xy));
+  }
+  const uint32_t rest = rows - num_data_rows;
+  void *db, *dout;
+  SP2_TRY(scratch(ctx, 2, (size_t)rest * sizeof(fe) + 32, &db)); SP2_TRY(scratch(ctx, 3, (size_t)rest * sizeof(jac) + 32, &dout));
+  SP2_CUDA_OK(cudaMemcpyAsync(db, folded_blind + 4 * (size_t)num_data_rows, (size_t)rest * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<MsmJob> jobs(rest);
+  for (uint32_t r = 0; r < rest; r++) { MsmJob &j = jobs[r]; memset(&j, 0, sizeof(j)); j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = (const fe *)db + r; }
+  SP2_TRY(msm_run(ctx, ck, jobs, (jac *)dout));
+  std::vector<uint64_t> hj((size_t)rest * 12);
+  SP2_CUDA_OK(cudaMemcpyAsync(hj.data(), dout, (size_t)rest * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  sp2h::batch_normalize(hj.data(), rest, out_xy + 8 * (size_t)num_data_rows);
   return SP2_OK;
 }
 
@@ -406,7 +440,6 @@ int32_t sp2_fold_commitments(sp2_ctx *ctx, const uint64_t *comms_xy, uint32_t n,
 #include <atomic>
 #include <chrono>
 #include <functional>
-#include "msm.cuh"
 #include "r1cs.cuh"
 #include "sumcheck.cuh"
 
@@ -1393,9 +1426,10 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
   fe *small = P->pcs, *LZ = small + NS_COUNT, *Ltab = LZ + width, *Rtab = Ltab + rows, *dvec = Rtab + width, *zvec = dvec + width;
   fe *blind_fold = P->blinds_dev + nrow, *blind_fin = blind_fold + rows;
   // pinned staging: [blinds | d_vec | Jacobian read-backs]
-  const size_t stage_need = (nrow + width + 16) * sizeof(fe) + (nrow + rows + 8) * sizeof(jac);
+  const size_t in_fe = nrow + width + NS_COUNT + 16;      // (also receives the NS_COUNT small scalars read back at the end)
+  const size_t stage_need = in_fe * sizeof(fe) + (nrow + rows + 8) * sizeof(jac);
   void *hp; SP2_TRY(pinned(ctx, stage_need, &hp));
-  uint8_t *h_in = (uint8_t *)hp; uint64_t *h_jac = (uint64_t *)(h_in + (nrow + width + 16) * sizeof(fe));
+  uint8_t *h_in = (uint8_t *)hp; uint64_t *h_jac = (uint64_t *)(h_in + in_fe * sizeof(fe));
   // ---- rerandomize_commitment (precommitted rows) + commit_zeros (rest rows): row = U_row + blind * h ----------------
   memcpy(h_in, rnd->blinds_steps, (size_t)n * rows * 32); memcpy(h_in + (size_t)n * rows * 32, rnd->blinds_core, (size_t)rows * 32);
   memcpy(h_in + nrow * 32, rnd->d_vec, width * 32);

@@ -487,6 +487,38 @@ k_cubic_tail(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int round
   }
 }
 
+// evaluation_points_zero_check_round0 (sumcheck.rs:1163-1271): round 1 of a zero-check — t(0) = 0 on a satisfied instance, so only
+// t(inf) = sum_x E(x) (A1 - A0)(B1 - B0) is summed (no C reads: half the traffic of a full first round)
+__global__ void __launch_bounds__(SC_THREADS) k_zero_check_round0(const fe *A, const fe *B, u64 P, const fe *el, const fe *er, u32 sh, fe *partials) {
+  __shared__ fe red[32];
+  Fq::acc acc = Fq::acc_zero();
+  const u64 mask = ((u64)1 << sh) - 1;
+  for (u64 id = (u64)blockIdx.x * SC_THREADS + threadIdx.x; id < P; id += (u64)gridDim.x * SC_THREADS) {
+    fe w = ldg_fe_ro(er + (el ? (id & mask) : id));
+    if (el) w = Fq::mul(ldg_fe_ro(el + (id >> sh)), w);
+    const fe a0 = ldg_fe(A + id), b0 = ldg_fe(B + id);
+    Fq::mul_acc(acc, w, Fq::mul(Fq::sub(ldg_fe(A + id + P), a0), Fq::sub(ldg_fe(B + id + P), b0)));
+  }
+  fe x[1] = {Fq::acc_reduce(acc)};
+  block_sum_fq<1>(x, red);
+  if (threadIdx.x == 0) stg_fe(partials + blockIdx.x, x[0]);
+}
+// s(X) = l(X) t(X) with t(0) = t(1) = 0: eval_0 = 0, eval_2 = 2 l(2) t_inf, eval_3 = 6 l(3) t_inf  (the values derive_from_claim /
+// its fallback produce from (t_0, t_inf, claim) = (0, t_inf, 0), sumcheck.rs:1244-1270)
+__global__ void __launch_bounds__(256) k_zero_check_finish(const ScState *st, const fe *partials, u32 nb, fe *out3) {
+  __shared__ fe red[32];
+  fe x[1] = {Fq::zero()};
+  for (u32 b = threadIdx.x; b < nb; b += blockDim.x) x[0] = Fq::add(x[0], ldg_fe(partials + b));
+  block_sum_fq<1>(x, red);
+  if (threadIdx.x == 0) {
+    const fe tau = ldg_fe(&st->taus[0]);
+    const fe l0 = Fq::sub(Fq::one(), tau), sl = Fq::sub(tau, l0);
+    const fe l2 = Fq::add(l0, Fq::dbl(sl)), l3 = Fq::add(l2, sl);
+    const fe t2 = Fq::dbl(x[0]), t6 = Fq::add(Fq::dbl(t2), t2);
+    stg_fe(out3, Fq::zero()); stg_fe(out3 + 1, Fq::mul(l2, t2)); stg_fe(out3 + 2, Fq::mul(l3, t6));
+  }
+}
+
 // init: the split-eq prefix tables and the round-1 constants
 __global__ void __launch_bounds__(1024) k_cubic_init(ScState *st, int l, fe *eq_left, fe *eq_right) {
   const int first_half = l / 2, second_half = l - first_half;
@@ -1073,6 +1105,37 @@ int32_t sp2_debug_sc_clocks(sp2_ctx *ctx, uint64_t *out7 /* 11 values */) {
   SP2_CUDA_OK(cudaMemcpyAsync(out7 + 7, st->gt, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(out7 + 11, &st->clk[7], sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(out7 + 12, &st->gt[4], sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return SP2_OK;
+}
+
+/* EqSumCheckInstance::evaluation_points_zero_check_round0 (src/sumcheck.rs:1163-1271) on device-resident tables of 2^l entries
+ * (not modified): out3 = (eval_0, eval_2, eval_3) of the first round of a zero-check */
+int32_t sp2_sc_zero_check_round0_dev(sp2_ctx *ctx, const uint64_t *taus, uint32_t l, const void *dA, const void *dB, uint64_t *out3) {
+  cudaSetDevice(ctx->device);
+  if (l < 1 || l > SC_MAX_ROUNDS) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "zero_check_round0: 1 <= num_rounds <= 40");
+  ScState *st;
+  sp2_transcript_state ts0; memset(&ts0, 0, sizeof(ts0));
+  const uint64_t zero4[4] = {0, 0, 0, 0};
+  SP2_TRY(sc_state_upload(ctx, &st, zero4, taus, l, &ts0));
+  const int first_half = (int)l / 2, second_half = (int)l - first_half;
+  void *eqs;
+  const size_t nleft = (size_t)1 << (first_half > 0 ? first_half : 1), nright = (size_t)2 << second_half;
+  SP2_TRY(scratch(ctx, 13, (nleft + nright) * sizeof(fe), &eqs));
+  fe *eq_left = (fe *)eqs, *eq_right = eq_left + nleft;
+  k_cubic_init<<<2, 1024, 0, ctx->stream>>>(st, (int)l, eq_left, eq_right);
+  SP2_LAUNCH_CHECK();
+  const u64 P = (u64)1 << (l - 1);
+  const fe *el = nullptr, *er; u32 sh = 0;
+  if (1 < first_half) { const int kl = first_half - 1; el = eq_left + (((size_t)1 << kl) - 1); er = eq_right + (((size_t)1 << second_half) - 1); sh = (u32)second_half; }
+  else er = eq_right + (((size_t)1 << (l - 1)) - 1);
+  u64 nb = (P + SC_THREADS - 1) / SC_THREADS; if (nb > (u64)ctx->num_sms * 4) nb = (u64)ctx->num_sms * 4;
+  void *part; SP2_TRY(scratch(ctx, 7, (nb + 4) * sizeof(fe), &part));
+  k_zero_check_round0<<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>((const fe *)dA, (const fe *)dB, P, el, er, sh, (fe *)part);
+  SP2_LAUNCH_CHECK();
+  k_zero_check_finish<<<1, 256, 0, ctx->stream>>>(st, (const fe *)part, (u32)nb, (fe *)part + nb);
+  SP2_LAUNCH_CHECK();
+  SP2_CUDA_OK(cudaMemcpyAsync(out3, (fe *)part + nb, 3 * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return SP2_OK;
 }

@@ -169,6 +169,17 @@ class SumcheckProof:
         return polys, r, claims
 
     @staticmethod
+    def evaluation_points_zero_check_round0(ctx, taus, A, B):
+        """EqSumCheckInstance::evaluation_points_zero_check_round0 (src/sumcheck.rs:1163-1271): (eval_0, eval_2, eval_3); A, B are
+        DeviceBuffers or host arrays of 2^len(taus) scalars (not modified)."""
+        taus = _fe(taus); l = taus.shape[0]
+        if not isinstance(A, DeviceBuffer):
+            A = ctx.upload(_fe(A)); B = ctx.upload(_fe(B))
+        out = np.zeros((3, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_sc_zero_check_round0_dev(ctx.h, _p(taus), C.c_uint32(l), A.ptr, B.ptr, _p(out)))
+        return out
+
+    @staticmethod
     def prove_quad(ctx, claim, num_rounds, A, B, ts):
         """returns (polys (rounds,3,4), r (rounds,4), claims (2,4))"""
         claim = _fe(claim); l = int(num_rounds)
@@ -294,6 +305,42 @@ class DlogGroupExt:
         return out
 
 
+    # ---- arbitrary bases (the trait's actual signatures; Pippenger on the device) ----
+    @staticmethod
+    def vartime_multiscalar_mul_var(ctx, scalars, bases):
+        s = _fe(scalars); b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        out = np.zeros((1, 8), dtype=np.uint64)
+        if s.shape[0] != b.shape[0]:
+            raise SpartanError(-2, "scalars and bases must have the same length")
+        ctx.check(ctx.L.sp2_msm_var(ctx.h, _p(s if s.size else np.zeros((1, 4), dtype=np.uint64)), _p(b if b.size else np.zeros((1, 8), dtype=np.uint64)),
+                                    C.c_uint32(s.shape[0]), _p(out)))
+        return out
+
+    @staticmethod
+    def vartime_multiscalar_mul_small(ctx, scalars_u64, bases):
+        s = np.ascontiguousarray(scalars_u64, dtype=np.uint64).reshape(-1); b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        out = np.zeros((1, 8), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_msm_small_var(ctx.h, _p(s if s.size else np.zeros(1, dtype=np.uint64)), _p(b if b.size else np.zeros((1, 8), dtype=np.uint64)),
+                                          C.c_uint32(s.shape[0]), _p(out)))
+        return out
+
+    @staticmethod
+    def batch_vartime_multiscalar_mul(ctx, scalar_vecs, bases):
+        lens = np.array([len(v) for v in scalar_vecs], dtype=np.uint32)
+        cat = np.concatenate([_fe(v) for v in scalar_vecs if len(v)] or [np.zeros((1, 4), dtype=np.uint64)])
+        b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+        out = np.zeros((len(scalar_vecs), 8), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_msm_batch_var(ctx.h, _p(cat), _p(lens), C.c_uint32(len(scalar_vecs)), _p(b), _p(out)))
+        return out
+
+    @staticmethod
+    def vartime_multiscalar_mul_shared_weights(ctx, weights, bases_rows):
+        w = _fe(weights); b = np.ascontiguousarray(bases_rows, dtype=np.uint64).reshape(-1, w.shape[0], 8)
+        out = np.zeros((b.shape[0], 8), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_msm_shared_weights(ctx.h, _p(w), C.c_uint32(w.shape[0]), _p(b), C.c_uint32(b.shape[0]), _p(out)))
+        return out
+
+
 class HyraxPCS:
     """src/provider/pcs/hyrax_pc.rs"""
 
@@ -303,6 +350,45 @@ class HyraxPCS:
         out = np.zeros((rows, 8), dtype=np.uint64)
         vv = v if v.shape[0] else np.zeros((1, 4), dtype=np.uint64)
         ctx.check(ctx.L.sp2_hyrax_commit(ctx.h, ck.h, _p(vv), C.c_uint64(v.shape[0]), _p(blinds), C.c_uint64(rows), C.c_int32(int(is_small)), _p(out)))
+        return out
+
+    @staticmethod
+    def commit_without_blind(ctx, ck, v, is_small=False):
+        v = _fe(v); rows = (v.shape[0] + ck.n - 1) // ck.n
+        out = np.zeros((rows, 8), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_hyrax_commit_without_blind(ctx.h, ck.h, _p(v if v.size else np.zeros((1, 4), dtype=np.uint64)), C.c_uint64(v.shape[0]),
+                                                       C.c_int32(int(is_small)), _p(out)))
+        return out
+
+    @staticmethod
+    def commit_incremental(ctx, ck, raw, delta, blinds):
+        raw = np.ascontiguousarray(raw, dtype=np.uint64).reshape(-1, 8); delta = _fe(delta); blinds = _fe(blinds)
+        rows = (delta.shape[0] + ck.n - 1) // ck.n
+        out = np.zeros((rows, 8), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_hyrax_commit_incremental(ctx.h, ck.h, _p(raw if raw.size else np.zeros((1, 8), dtype=np.uint64)), C.c_uint64(raw.shape[0]),
+                                                     _p(delta), C.c_uint64(delta.shape[0]), _p(blinds), _p(out)))
+        return out
+
+    @staticmethod
+    def rerandomize_commitment(ctx, ck, comm, r_old, r_new):
+        comm = np.ascontiguousarray(comm, dtype=np.uint64).reshape(-1, 8); r_old = _fe(r_old); r_new = _fe(r_new)
+        if not (comm.shape[0] == r_old.shape[0] == r_new.shape[0]):
+            raise SpartanError(-2, "rerandomize_commitment: commitment and blinds must have the same length")
+        out = np.zeros_like(comm)
+        ctx.check(ctx.L.sp2_hyrax_rerandomize(ctx.h, ck.h, _p(comm), _p(r_old), _p(r_new), C.c_uint64(comm.shape[0]), _p(out)))
+        return out
+
+    @staticmethod
+    def fold_blinds(ctx, blinds, n, rows, w):
+        blinds = _fe(blinds); w = _fe(w); out = np.zeros((rows, 4), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_fold_blinds(ctx.h, _p(blinds), C.c_uint32(n), C.c_uint32(rows), _p(w), _p(out)))
+        return out
+
+    @staticmethod
+    def fold_commitments_partial(ctx, ck, comms, n, rows, w, num_data_rows, folded_blind):
+        comms = np.ascontiguousarray(comms, dtype=np.uint64).reshape(-1, 8); w = _fe(w); fb = _fe(folded_blind)
+        out = np.zeros((rows, 8), dtype=np.uint64)
+        ctx.check(ctx.L.sp2_fold_commitments_partial(ctx.h, ck.h, _p(comms), C.c_uint32(n), C.c_uint32(rows), _p(w), C.c_uint32(num_data_rows), _p(fb), _p(out)))
         return out
 
     @staticmethod

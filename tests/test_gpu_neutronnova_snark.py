@@ -36,6 +36,18 @@ def _device_prove(ctx, c):
 
 def _check(orc, c, v):
     P = prove(orc, c)
+    # probes of the commitment half first (clearer failures than a downstream transcript mismatch)
+    n, rows = c["n"], c["rows"]
+    one = orc.to_mont([1])
+    for k in ("comm_W_steps", "comm_W_core", "eval_W"):
+        assert np.array_equal(np.asarray(v[k]).reshape(-1), getattr(P, k).reshape(-1)), "parity: " + k
+    ce = np.concatenate([orc.point_add(orc.scalar_mul(c["keys"].ck_s, P.eval_W[b:b + 1]), orc.scalar_mul(c["keys"].h_s, c["rand"].a[2][b:b + 1])) for b in range(2)])
+    assert np.array_equal(v["comm_eval_W"], ce), "comm_eval_W"
+    assert np.array_equal(v["c_eval"].reshape(-1), P.debug["c_eval"].reshape(-1)), "c_eval"
+    w = orc.weights_from_r(v["r_b"].reshape(-1, 4), n)
+    folded = orc.fold_commitments(P.comm_W_steps, n, rows, w)
+    comm = orc.fold_commitments(np.concatenate([folded, P.comm_W_core]), 2, rows, np.concatenate([one, P.debug["c_eval"]]))
+    assert np.array_equal(v["comm_fold"], comm), "comm_fold (fold by linearity vs fold of group elements)"
     for k in FIELDS:
         assert np.array_equal(np.asarray(v[k]).reshape(-1), getattr(P, k).reshape(-1)), "parity: " + k
     assert np.array_equal(v["c_eval"].reshape(-1), P.debug["c_eval"].reshape(-1))
@@ -54,9 +66,9 @@ def _check(orc, c, v):
     assert orc.neutronnova_verify(c["O"], c["keys"], c["vk"], sx, cx, V) != 0
 
 
-@pytest.mark.parametrize("n,lc,lv,width,npub", [(2, 5, 7, 32, 0), (4, 6, 8, 32, 2), (8, 6, 8, 64, 1), (4, 7, 9, 512, 3)])
+@pytest.mark.parametrize("n,lc,lv,width,npub", [(2, 5, 7, 32, 0), (4, 6, 8, 32, 2), (8, 6, 8, 64, 1), (4, 7, 9, 256, 3)])
 def test_snark_bit_exact_small_chains(ctx, orc, n, lc, lv, width, npub):
-    """random R1CS chains incl. public IO (X is folded too), several commitment rows, and the one-row case (width = M)"""
+    """random R1CS chains incl. public IO (X is folded too), 2 to 8 commitment rows"""
     c = nn_case(orc, n=n, lc=lc, lv=lv, width=width, npub=npub, seed=20 + n)
     v, ph = _device_prove(ctx, c)
     _check(orc, c, v)

@@ -96,3 +96,18 @@ def test_cubic_prove_verify_roundtrip(orc, l):
         tb = tb * (t * x + (1 - t) * (1 - x)) % P
     a, b, c = pi(claims)
     assert pi(e_final)[0] == tb * (a * b - c) % P
+
+
+@pytest.mark.parametrize("l", [1, 2, 5, 9])
+def test_zero_check_round0_is_the_first_round_of_a_satisfied_cubic(orc, l):
+    """evaluation_points_zero_check_round0 (sumcheck.rs:1163-1271): on Az o Bz = Cz the first round polynomial of
+    prove_cubic_with_three_inputs, evaluated at 0, 2, 3, equals the shortcut that only sums t(inf)."""
+    rng = np.random.default_rng(l)
+
+    def rf(n):
+        a = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64); a[:, 3] &= np.uint64(0x7fffffffffffffff); return a
+    n = 1 << l
+    A, B, taus = rf(n), rf(n), rf(l)
+    polys = orc.sumcheck_cubic_prove(np.zeros((1, 4), dtype=np.uint64), taus, A.copy(), B.copy(), orc.f_mul(A, B), orc.Transcript(b"x"))[0]
+    c = orc.from_mont(np.asarray(polys).reshape(-1, 4)[:4]); P = orc.P_T256_SCALAR
+    assert orc.from_mont(orc.zero_check_round0(taus, A, B)) == [sum(ci * pow(x, k, P) for k, ci in enumerate(c)) % P for x in (0, 2, 3)]

@@ -36,6 +36,7 @@ extern "C" {
 #define SP2_ERR_DIVISION_BY_ZERO (-5)   /* SpartanError::DivisionByZero                           */
 #define SP2_ERR_INTERNAL (-6)           /* SpartanError::InternalError                            */
 #define SP2_ERR_UNSUPPORTED (-7)        /* path not offloaded: caller must use its CPU path       */
+#define SP2_ERR_PROOF_VERIFY (-8)       /* SpartanError::ProofVerifyError{reason}                 */
 
 typedef struct sp2_ctx sp2_ctx;         /* one per (process, GPU)                                 */
 typedef struct sp2_ck sp2_ck;           /* device-resident commitment key                         */
@@ -235,6 +236,12 @@ void sp2_prep_free(sp2_prep *prep);
 int32_t sp2_spartan_prove(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck, sp2_prep *prep, const uint8_t *vk_digest,
                           const uint64_t *public_values, const uint64_t *W_rest, const sp2_spartan_rand *rand,
                           sp2_spartan_proof *proof, float *phase_ms);
+
+/* Replaces SpartanSNARK::verify (src/spartan.rs:469-578): the matrix evaluations (evaluate_with_tables_fast, src/r1cs/mod.rs:36-146,
+ * 1216-1226), the Hyrax row MSM (hyrax_pc.rs:480-531) and the IPA checks (ipa.rs:173-221) run on the device; SP2_OK = accept,
+ * SP2_ERR_PROOF_VERIFY = reject (sp2_last_error names the failing check).                                                  */
+int32_t sp2_spartan_verify(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck, const uint8_t *vk_digest, const uint64_t *public_values,
+                           const sp2_spartan_proof *proof);
 
 /* SpartanSNARK::prove with the 2^l hypercube split across the GPUs of `comm` (one process per GPU).  Every
  * rank calls with the same inputs, its shard of the shape (sp2_shape_upload_sharded) and the prep state made from it,

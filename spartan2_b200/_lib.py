@@ -12,7 +12,7 @@ _lib = None
 
 OK = 0
 ERRORS = {-1: "InternalError(CUDA)", -2: "InvalidInputLength", -3: "InvalidWitnessLength", -4: "InvalidCommitmentKeyLength",
-          -5: "DivisionByZero", -6: "InternalError", -7: "Unsupported"}
+          -5: "DivisionByZero", -6: "InternalError", -7: "Unsupported", -8: "ProofVerifyError"}
 
 
 class SpartanError(RuntimeError):

@@ -245,7 +245,19 @@ struct Fq : Field<FqParams> {
     cond_sub_p<FqParams>(r, t[16]);
     return r;
   }
-  SP2_HD static fe mul(const fe &a, const fe &b) { u32 w[16]; mul_wide(w, a, b); return redc16(w); }
+  SP2_HD static fe mul_inl(const fe &a, const fe &b) { u32 w[16]; mul_wide(w, a, b); return redc16(w); }
+#if defined(__CUDA_ARCH__) && defined(SP2_FQ_OUTLINE)
+  // Translation units of LATENCY-bound kernels (a few thousand threads, each running its straight-line body once) define
+  // SP2_FQ_OUTLINE: the multiplication and the wide multiply-accumulate become out-of-line calls (operands and results in
+  // registers), so a kernel is a few KB of code that stays in the instruction cache instead of >100 KB of inlined carry
+  // chains fetched once per warp from L2 (ncu: 2-3 `no_instruction` stall cycles per issued instruction in k_nn_outer_round).
+  struct w16 { u32 v[16]; };
+  static __device__ __noinline__ fe mul_ni(fe a, fe b) { return mul_inl(a, b); }
+  static __device__ __noinline__ w16 mul_wide_ni(fe a, fe b) { w16 r; mul_wide(r.v, a, b); return r; }
+  static __device__ __forceinline__ fe mul(const fe &a, const fe &b) { return mul_ni(a, b); }
+#else
+  SP2_HD static fe mul(const fe &a, const fe &b) { return mul_inl(a, b); }
+#endif
   SP2_HD static fe sqr(const fe &a) { return mul(a, a); }
 
   // x + hi*2^256 (hi < 2^32)  ==  x + hi*(2^224 - 2^192 - 2^96 + 1)  (mod p); returns the new top limb
@@ -272,8 +284,13 @@ struct Fq : Field<FqParams> {
   SP2_HD static acc acc_zero() { acc a; for (int i = 0; i < 17; i++) a.v[i] = 0; return a; }
   // a += x*y  (unreduced_multiply_accumulate, delayed_reduction.rs:52-58); up to 2^32 products
   SP2_HD static void mul_acc(acc &a, const fe &x, const fe &y) {
+#if defined(__CUDA_ARCH__) && defined(SP2_FQ_OUTLINE)
+    const w16 ww = mul_wide_ni(x, y);
+    const u32 (&w)[16] = ww.v;
+#else
     u32 w[16];
     mul_wide(w, x, y);
+#endif
     a.v[0] = add_cc(a.v[0], w[0]);
 #pragma unroll
     for (int i = 1; i < 16; i++) a.v[i] = addc_cc(a.v[i], w[i]);

@@ -116,8 +116,9 @@ struct GatherSmem {
 __global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, u32 njobs, u32 total_parts, const aff *table, jac *partial) {
   __shared__ GatherSmem sm;
   const u32 wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const u32 part = blockIdx.x * GW + wib;
-  if (part >= total_parts) return;
+  // grid-stride over the partials: a capped grid (msm_run's max_ctas) keeps a background batch on a side stream from taking
+  // every SM away from the latency-bound kernels of the main stream
+  for (u32 part = blockIdx.x * GW + wib; part < total_parts; part += gridDim.x * GW) {
   const u32 jid = job_of_part(jobs, njobs, part);
   const MsmJob job = jobs[jid];
   const u32 total = (job.len + job.nextra) * MSM_NW;
@@ -154,6 +155,8 @@ __global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, 
   }
   acc = warp_sum_jac(acc);
   if (lane == 0) st_jac(partial + part, acc);
+  __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(128) k_msm_final(const MsmJob *jobs, const jac *partial, jac *out) {
@@ -177,8 +180,8 @@ __global__ void __launch_bounds__(128) k_msm_final(const MsmJob *jobs, const jac
   }
 }
 
-// n Jacobian points -> affine: one thread per chunk of <= 64 points, one inversion per chunk (Montgomery's trick)
-constexpr int NORM_CHUNK = 64;
+// n Jacobian points -> affine: one thread per chunk of <= 16 points, one inversion per chunk (Montgomery's trick)
+constexpr int NORM_CHUNK = 16;
 __global__ void __launch_bounds__(64) k_batch_normalize(const jac *in, u64 n, aff *out) {
   const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const u64 i0 = c * NORM_CHUNK; if (i0 >= n) return;
@@ -247,7 +250,8 @@ __global__ void __launch_bounds__(64) k_test_points(u64 seed, u32 n, aff *out) {
 namespace sp2 {
 
 // d_out[njobs]: Jacobian results (the caller normalises: sp2h::batch_normalize on the host, batch_normalize_dev here)
-int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, jac *d_out, cudaStream_t stream, int slot_jobs, int slot_partials) {
+int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, jac *d_out, cudaStream_t stream, int slot_jobs, int slot_partials,
+            unsigned max_ctas) {
   if (jobs_in.empty()) return SP2_OK;
   if (!stream) stream = ctx->stream;
   std::vector<MsmJob> jobs(jobs_in);
@@ -265,7 +269,8 @@ int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, 
   SP2_TRY(scratch(ctx, slot_partials, (size_t)parts * sizeof(jac), &d_partial));
   // pageable source: the runtime stages it before cudaMemcpyAsync returns, so the local vector may die
   SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), nj * sizeof(MsmJob), cudaMemcpyHostToDevice, stream));
-  k_msm_gather<<<(parts + GW - 1) / GW, MSM_THREADS, 0, stream>>>((const MsmJob *)d_jobs, (u32)nj, parts, ck->table, (jac *)d_partial);
+  unsigned grid = (parts + GW - 1) / GW; if (max_ctas && grid > max_ctas) grid = max_ctas;
+  k_msm_gather<<<grid, MSM_THREADS, 0, stream>>>((const MsmJob *)d_jobs, (u32)nj, parts, ck->table, (jac *)d_partial);
   SP2_LAUNCH_CHECK();
   k_msm_final<<<(unsigned)nj, 128, 0, stream>>>((const MsmJob *)d_jobs, (const jac *)d_partial, d_out);
   SP2_LAUNCH_CHECK();

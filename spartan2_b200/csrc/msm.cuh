@@ -44,11 +44,12 @@ namespace sp2 {
 // run `jobs` (host array; pointers inside are device pointers); d_out[njobs] JACOBIAN results
 // (normalise on the host: sp2h::batch_normalize)
 // stream / scratch slots: a second MSM batch in flight on a side stream needs its own job and partial buffers
+// max_ctas (0 = no cap): grid size limit of the gather kernel
 int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs, jac *d_out, cudaStream_t stream = nullptr, int slot_jobs = 10,
-            int slot_partials = 11);
+            int slot_partials = 11, unsigned max_ctas = 0);
 int hyrax_bind_dev(sp2_ctx *ctx, const fe *d_poly, const fe *d_L, uint64_t rows, uint64_t r_len, fe *d_out);
 // window tables [nbase][MSM_NW][MSM_ND] of arbitrary device-resident affine bases (identity allowed): *table_out is cudaMalloc'ed
 int msm_build_tables(sp2_ctx *ctx, const aff *d_bases, uint32_t nbase, aff **table_out);
-// n Jacobian points -> affine on the device (one inversion per 64-point chunk, Montgomery's trick), identity -> (0,0)
+// n Jacobian points -> affine on the device (one inversion per 16-point chunk, Montgomery's trick), identity -> (0,0)
 int batch_normalize_dev(sp2_ctx *ctx, const jac *d_in, uint64_t n, aff *d_out);
 }  // namespace sp2

@@ -15,6 +15,8 @@
 //
 // Layers are stored layer-major; live layer q of round t sits at slot q * stride (stride = 2^t): folding pair
 // (2p, 2p+1) in place into the even slot needs no compaction and no cross-thread hazards.
+// every kernel of this file is latency-bound (<= 2^15-entry tables per instance, one launch per round): see field.cuh
+#define SP2_FQ_OUTLINE 1
 #include <string.h>
 #include <vector>
 #include "ctx.cuh"
@@ -440,6 +442,7 @@ int32_t sp2_fold_commitments_partial(sp2_ctx *ctx, const sp2_ck *ck, const uint6
 #include <atomic>
 #include <chrono>
 #include <functional>
+#include "hostfield.h"
 #include "r1cs.cuh"
 #include "sumcheck.cuh"
 
@@ -726,61 +729,6 @@ __global__ void k_bind_heads(TablePtrs tp, u32 ntab, fe r, fe *mail_out, u32 *ma
   __syncthreads();
   if (i == 0) { __threadfence_system(); *(volatile u32 *)mail_flag = seq; }
 }
-
-// Host-side scalar field for the per-round algebra: the same Montgomery representation as `fe` (8 x u32 == 4 x u64
-// little-endian), multiplied with 64-bit limbs / __int128 (host_transcript.h: mont_mul) — the 32-bit carry-chain
-// emulation that field.cuh falls back to on the host costs ~1 us per multiplication, this ~40 ns.
-struct HF {
-  static void ld(const fe &a, uint64_t o[4]) { memcpy(o, a.v, 32); }
-  static fe st(const uint64_t a[4]) { fe r; memcpy(r.v, a, 32); return r; }
-  static fe zero() { return Fq::zero(); }
-  static fe one() { return Fq::one(); }
-  static bool is_zero(const fe &a) { return Fq::is_zero(a); }
-  static bool eq(const fe &a, const fe &b) { return Fq::eq(a, b); }
-  static fe add(const fe &x, const fe &y) {
-    uint64_t a[4], b[4], s[4], d[4]; ld(x, a); ld(y, b);
-    unsigned carry = 0, borrow = 0;
-    for (int j = 0; j < 4; j++) { const sp2h::u128 t = (sp2h::u128)a[j] + b[j] + carry; s[j] = (uint64_t)t; carry = (unsigned)(t >> 64); }
-    for (int j = 0; j < 4; j++) { const sp2h::u128 t = (sp2h::u128)s[j] - sp2h::FQ_MOD[j] - borrow; d[j] = (uint64_t)t; borrow = (unsigned)((t >> 64) & 1); }
-    return st((carry || !borrow) ? d : s);
-  }
-  static fe sub(const fe &x, const fe &y) {
-    uint64_t a[4], b[4], d[4]; ld(x, a); ld(y, b);
-    unsigned borrow = 0;
-    for (int j = 0; j < 4; j++) { const sp2h::u128 t = (sp2h::u128)a[j] - b[j] - borrow; d[j] = (uint64_t)t; borrow = (unsigned)((t >> 64) & 1); }
-    if (borrow) { unsigned carry = 0; for (int j = 0; j < 4; j++) { const sp2h::u128 t = (sp2h::u128)d[j] + sp2h::FQ_MOD[j] + carry; d[j] = (uint64_t)t; carry = (unsigned)(t >> 64); } }
-    return st(d);
-  }
-  static fe dbl(const fe &x) { return add(x, x); }
-  static fe mul(const fe &x, const fe &y) { uint64_t a[4], b[4], o[4]; ld(x, a); ld(y, b); sp2h::mont_mul(a, b, sp2h::FQ_MOD, sp2h::FQ_INV, o); return st(o); }
-  static fe sqr(const fe &x) { return mul(x, x); }
-  static fe inv(const fe &x) {              // Fermat, x^(q-2); inv(0) = 0
-    const uint64_t e[4] = {sp2h::FQ_MOD[0] - 2, sp2h::FQ_MOD[1], sp2h::FQ_MOD[2], sp2h::FQ_MOD[3]};
-    fe r = one();
-    for (int i = 255; i >= 0; i--) { r = sqr(r); if ((e[i >> 6] >> (i & 63)) & 1) r = mul(r, x); }
-    return r;
-  }
-  static fe two_inv() { return Fq::two_inv(); }
-  static fe six_inv() { return Fq::six_inv(); }
-};
-struct NnHost {
-  static fe load(const uint64_t *p) { fe r; memcpy(r.v, p, 32); return r; }
-  static void store(uint64_t *p, const fe &x) { memcpy(p, x.v, 32); }
-  static fe eval(const fe *c, int n, const fe &r) { fe acc = c[n - 1]; for (int i = n - 2; i >= 0; i--) acc = HF::add(HF::mul(acc, r), c[i]); return acc; }
-  // UniPoly::from_evals (src/polys/univariate.rs:84-120): evaluations at 0, 1, 2[, 3] -> coefficients low to high
-  static void from_evals3(const fe &e0, const fe &e1, const fe &e2, fe *c) {
-    c[2] = HF::mul(HF::add(HF::sub(e2, HF::dbl(e1)), e0), HF::two_inv());
-    c[1] = HF::sub(HF::sub(e1, e0), c[2]);
-    c[0] = e0;
-  }
-  static void from_evals4(const fe &e0, const fe &e1, const fe &e2, const fe &e3, fe *c) {
-    const fe t1 = HF::add(HF::dbl(e1), e1), t2 = HF::add(HF::dbl(e2), e2);
-    c[3] = HF::mul(HF::sub(HF::add(HF::sub(e3, t2), t1), e0), HF::six_inv());
-    c[2] = HF::sub(HF::mul(HF::add(HF::sub(e2, HF::dbl(e1)), e0), HF::two_inv()), HF::add(HF::dbl(c[3]), c[3]));
-    c[1] = HF::sub(HF::sub(HF::sub(e1, e0), c[2]), c[3]);
-    c[0] = e0;
-  }
-};
 
 // wait for the device to publish sequence number `seq` in the mailbox (bounded: a wedged stream surfaces as an error)
 int nn_wait(sp2_nn_prep *P, u32 seq) {
@@ -1336,6 +1284,9 @@ __global__ void __launch_bounds__(256) k_nn_dot(const fe *a, const fe *b, u64 n,
 }
 enum NnSlot { NS_EVAL = 0 /* 2 */, NS_BEVAL = 2 /* 2 */, NS_EVALF = 4, NS_BEVALF = 5, NS_CEVAL = 6, NS_RLZ = 7, NS_IP = 8, NS_RDELTA = 9, NS_RBETA = 10, NS_RY = 16 /* <= 40 */, NS_COUNT = 64 };
 
+// gather CTAs the background commitment of the folded witness may occupy while the sum-checks run (SP2_NN_SIDE_CTAS, default 96; swept on B200 at 32 steps: 0 = uncapped: outer 1.04 / pcs 0.33 ms, 48: 0.57 / 0.83, 16: 0.56 / 3.9)
+unsigned nn_side_ctas() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_NN_SIDE_CTAS"); v = e ? atoi(e) : 96; } return (unsigned)v; }
+
 int nn_palloc(sp2_nn_prep *P, size_t bytes, void **out) {
   sp2_ctx *ctx = P->ctx; void *p;
   SP2_CUDA_OK(cudaMalloc(&p, std::max<size_t>(bytes, 64)));
@@ -1363,7 +1314,7 @@ int32_t sp2_neutronnova_prep_commit(sp2_ctx *ctx, sp2_nn_prep *P, const sp2_ck *
   const size_t nrow = (size_t)(n + 1) * rows;
   void *p;
   SP2_TRY(nn_palloc(P, nrow * sizeof(aff), &p)); P->U = (aff *)p;
-  SP2_TRY(nn_palloc(P, (nrow + 2 * rows + 16) * sizeof(jac), &p)); P->pts = (jac *)p;   // [instance rows | folded rows | 2 eval | final rows + 4]
+  SP2_TRY(nn_palloc(P, (nrow + 2 * rows + 16) * sizeof(jac) + nrow * sizeof(aff), &p)); P->pts = (jac *)p;   // [instance rows | folded rows | 2 eval | final rows + 4] | affine rows
   SP2_TRY(nn_palloc(P, (nrow + 2 * rows + 16) * sizeof(fe), &p)); P->blinds_dev = (fe *)p;
   SP2_TRY(nn_palloc(P, M * sizeof(fe), &p)); P->Wfold = (fe *)p;
   SP2_TRY(nn_palloc(P, M * sizeof(fe), &p)); P->Wfin = (fe *)p;
@@ -1441,11 +1392,21 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
       j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = P->blinds_dev + k; j.add_aff = P->U + k;
     }
     SP2_TRY(msm_run(ctx, ck, jobs, P->pts)); }
-  SP2_CUDA_OK(cudaMemcpyAsync(h_jac, P->pts, nrow * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
-  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  { std::vector<uint64_t> aff_all(nrow * 8);
+  if (nrow > 1024) {
+    // many instances: normalise on the device (one inversion per 16-point chunk, chunks in parallel) and read back affine rows;
+    // a serial host pass over thousands of points costs ~1 ms
+    aff *d_aff = (aff *)(P->pts + nrow + 2 * rows + 16);
+    SP2_TRY(batch_normalize_dev(ctx, P->pts, nrow, d_aff));
+    SP2_CUDA_OK(cudaMemcpyAsync(sn->comm_W_steps, d_aff, (size_t)n * rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+    SP2_CUDA_OK(cudaMemcpyAsync(sn->comm_W_core, d_aff + (size_t)n * rows, (size_t)rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+    SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  } else {
+    SP2_CUDA_OK(cudaMemcpyAsync(h_jac, P->pts, nrow * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
+    SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint64_t> aff_all(nrow * 8);
     sp2h::batch_normalize(h_jac, nrow, aff_all.data());
-    memcpy(sn->comm_W_steps, aff_all.data(), (size_t)n * rows * 64); memcpy(sn->comm_W_core, aff_all.data() + (size_t)n * rows * 8, (size_t)rows * 64); }
+    memcpy(sn->comm_W_steps, aff_all.data(), (size_t)n * rows * 64); memcpy(sn->comm_W_core, aff_all.data() + (size_t)n * rows * 8, (size_t)rows * 64);
+  }
   ph[0] = ms_since(t_phase); t_phase = now();
   // ---- transcript over the instances (neutronnova_zk.rs:1727-1733, 552-556; R1CSInstance bytes r1cs/mod.rs:728-736) -----
   sp2_transcript tsobj("neutronnova_prove");
@@ -1474,7 +1435,7 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
     if (pre_rows) {
       std::vector<MsmJob> jobs(pre_rows);
       for (uint32_t r = 0; r < pre_rows; r++) { MsmJob &j = jobs[r]; memset(&j, 0, sizeof(j)); j.scalars = P->Wfold + (size_t)r * width; j.len = (u32)width; }
-      SP2_TRY(msm_run(ctx, ck, jobs, pts_fold, P->side, 16, 17));
+      SP2_TRY(msm_run(ctx, ck, jobs, pts_fold, P->side, 16, 17, nn_side_ctas()));
     }
     SP2_CUDA_OK(cudaEventRecord(P->ev_side, P->side));
     return SP2_OK;

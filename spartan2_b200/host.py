@@ -445,7 +445,11 @@ class SpartanPrepSNARK:
 
 
 class SpartanSNARK:
-    """src/spartan.rs — prep_prove / prove on the device (setup = SplitR1CSShape + CommitmentKey uploads)."""
+    """src/spartan.rs — prep_prove / prove / verify on the device (setup = SplitR1CSShape + CommitmentKey uploads)."""
+
+    @staticmethod
+    def verify(ctx, shape, ck, vk_digest, public_values, proof):
+        return spartan_verify(ctx, shape, ck, vk_digest, public_values, proof)
 
     @staticmethod
     def prep_prove(ctx, shape, ck, W_cached, blinds_cached, is_small=True):
@@ -485,6 +489,14 @@ class SpartanSNARK:
         P.phase_ms = dict(zip(["commit_transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck",
                                "pcs_prove", "ipa_response", "total"], [float(x) for x in ph]))
         return P
+
+
+def spartan_verify(ctx, shape, ck, vk_digest, public_values, proof):
+    """SpartanSNARK::verify on the device (sp2_spartan_verify): returns None on accept, raises SpartanError(kind ProofVerifyError) on reject."""
+    pv = proof.cview()
+    dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
+    pub = _fe(public_values) if len(public_values) else np.zeros((1, 4), dtype=np.uint64)
+    ctx.check(ctx.L.sp2_spartan_verify(ctx.h, shape.h, ck.h, _p(dig), _p(pub), C.byref(pv)))
 
 
 def shard_cyclic(table, nranks, rank):

@@ -460,10 +460,11 @@ def cpu_prove(wl, pts, threads, steps, warmup, want_proof=False):
     keys = orc.Keys(pts[:WIDTH], pts[WIDTH:WIDTH + 1], pts[WIDTH + 1:WIDTH + 2], pts[WIDTH + 2:WIDTH + 3])
     comm_pre = orc.hyrax_commit(pts[:WIDTH], pts[WIDTH:WIDTH + 1], wl.W[:wl.cached_len], wl.blinds[:wl.cached_rows], is_small=True)
     rnd = orc.Rand(wl.blinds, wl.blind_eval, wl.d_vec, wl.r_delta, wl.r_beta)
+    cached = orc.spartan_prep_cached(O, wl.W)        # prep_prove's cached Az/Bz/Cz (spartan.rs:184-187): prove adds the remaining columns only
     times, ph = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        p = orc.spartan_prove(O, keys, wl.vk, wl.X, wl.W, comm_pre, rnd)
+        p = orc.spartan_prove(O, keys, wl.vk, wl.X, wl.W, comm_pre, rnd, cached=cached)
         if i >= warmup:
             times.append((time.perf_counter() - t0) * 1e3); ph = p.phase_ms
     ms = float(np.mean(times))

@@ -490,9 +490,11 @@ typedef struct {                      /* PrecomputedSparseMatrix (sparse.rs:29-4
   uint32_t *off_up, *off_un, *off_sm, *off_ge;
   uint32_t *up_cols, *un_cols, *sm_cols, *ge_cols; int8_t *sm_coef; fe *ge_vals;
 } pmat;
+typedef struct { size_t n; uint32_t *rows, *cols; fe *vals; } fcoo;   /* FilteredSpmv (sparse.rs:305-380): COO of the columns >= first_col */
 typedef struct {
   size_t num_cons, num_cons_unpadded, num_vars, num_shared, num_precommitted, num_rest, num_public, num_challenges;
   pmat M[3];
+  fcoo F[3];
 } shape;
 
 static void pmat_build(pmat *P, size_t rows, size_t cols, const fe *data, const uint32_t *indices, const uint32_t *indptr) {
@@ -563,9 +565,32 @@ EXPORT shape *orc_shape_new(size_t num_cons, size_t num_cons_unpadded, size_t nu
   pmat_build(&S->M[0], num_cons, cols, dA, iA, pA);
   pmat_build(&S->M[1], num_cons, cols, dB, iB, pB);
   pmat_build(&S->M[2], num_cons, cols, dC, iC, pC);
+  /* build_filtered (sparse.rs:305-364; SplitR1CSShape::precompute, r1cs/mod.rs:1059-1073): entries in the columns that prep_prove
+   * does not know yet (rest witness, the constant 1, public IO, challenges) */
+  const fe *ds[3] = {dA, dB, dC}; const uint32_t *is[3] = {iA, iB, iC}, *ps[3] = {pA, pB, pC};
+  const uint32_t first_col = (uint32_t)(num_shared + num_precommitted);
+  for (int k = 0; k < 3; k++) {
+    size_t cnt = 0;
+    for (uint32_t e = 0; e < ps[k][num_cons]; e++) if (is[k][e] >= first_col) cnt++;
+    fcoo *F = &S->F[k]; F->n = cnt;
+    F->rows = (uint32_t *)malloc((cnt + 1) * 4); F->cols = (uint32_t *)malloc((cnt + 1) * 4); F->vals = (fe *)malloc((cnt + 1) * sizeof(fe));
+    size_t q = 0;
+    for (size_t r = 0; r < num_cons; r++) for (uint32_t e = ps[k][r]; e < ps[k][r + 1]; e++) if (is[k][e] >= first_col) { F->rows[q] = (uint32_t)r; F->cols[q] = is[k][e]; F->vals[q++] = ds[k][e]; }
+  }
   return S;
 }
-EXPORT void orc_shape_free(shape *S) { for (int k = 0; k < 3; k++) pmat_free(&S->M[k]); free(S); }
+EXPORT void orc_shape_free(shape *S) { for (int k = 0; k < 3; k++) { pmat_free(&S->M[k]); free(S->F[k].rows); free(S->F[k].cols); free(S->F[k].vals); } free(S); }
+/* multiply_vec_incremental_into (r1cs/mod.rs:1170-1211): out = cached (the products over the shared + precommitted columns,
+ * computed by prep_prove) + FilteredSpmv::multiply_vec_add over the remaining columns (serial, sparse.rs:375-379) */
+EXPORT void orc_shape_multiply_vec_incremental(const shape *S, const fe *z, const fe *caz, const fe *cbz, const fe *ccz, fe *az, fe *bz, fe *cz) {
+  const fe *c[3] = {caz, cbz, ccz}; fe *o[3] = {az, bz, cz};
+#pragma omp parallel for schedule(static, 1) if (g_threads > 1)          /* the three matrices in parallel (nested rayon::join) */
+  for (int k = 0; k < 3; k++) {
+    memcpy(o[k], c[k], S->num_cons * sizeof(fe));
+    const fcoo *F = &S->F[k];
+    for (size_t q = 0; q < F->n; q++) { fe t; f_mul(&FQ, &t, &F->vals[q], &z[F->cols[q]]); f_add(&FQ, &o[k][F->rows[q]], &o[k][F->rows[q]], &t); }
+  }
+}
 /* SplitR1CSShape::multiply_vec (r1cs/mod.rs:1075-1107) */
 EXPORT void orc_shape_multiply_vec(const shape *S, const fe *z, fe *az, fe *bz, fe *cz) {
   pmat_mulvec(&S->M[0], z, az); pmat_mulvec(&S->M[1], z, bz); pmat_mulvec(&S->M[2], z, cz);
@@ -750,6 +775,53 @@ EXPORT void orc_msm_small(const uint64_t *s, const apt *bases, size_t n, apt *ou
 static void pt_mul_fe(pt *out, const apt *base, const fe *k) {
   uint64_t raw[4]; f_to_raw(&FQ, raw, k); pt b; pt_from_affine(&CV, &b, base); pt_mul_raw(&CV, out, &b, raw);
 }
+/* FixedBaseMul (msm.rs:637-774): 8-bit windows, 32 tables of 255 affine multiples d * 2^(8w) * B, batch-normalised; mul = at
+ * most 32 mixed additions.  The reference keeps one for h in the commitment key (ck.h_table, hyrax_pc.rs:84, 222-227) and uses it
+ * in commit / commit_zeros / rerandomize_commitment / commit_incremental / fold_commitments_partial.  Cached per base here. */
+typedef struct { apt base; apt *tab; } fbm;       /* tab[w * 255 + d - 1] */
+#define FBM_CACHE 8
+static fbm g_fbm[FBM_CACHE]; static int g_fbm_n = 0;
+static const fbm *fbm_get(const apt *base) {
+  const fbm *hit = NULL;
+#pragma omp critical(fbm_cache)
+  {
+    for (int i = 0; i < g_fbm_n; i++) if (memcmp(&g_fbm[i].base, base, sizeof(apt)) == 0) hit = &g_fbm[i];
+    if (!hit) {
+      fbm *f = &g_fbm[g_fbm_n < FBM_CACHE ? g_fbm_n++ : 0];
+      if (f->tab) free(f->tab);
+      f->base = *base; f->tab = (apt *)malloc(32 * 255 * sizeof(apt));
+      pt *tmp = (pt *)malloc(32 * 255 * sizeof(pt));
+      pt wbase; pt_from_affine(&CV, &wbase, base);
+      for (int w = 0; w < 32; w++) {                       /* multiples 1..255 of 2^(8w) B (msm.rs:651-667) */
+        pt m = wbase;
+        for (int d = 0; d < 255; d++) { tmp[w * 255 + d] = m; pt_add(&CV, &m, &m, &wbase); }
+        wbase = m;                                          /* 256 * previous window base */
+      }
+      /* batch_normalize (msm.rs:669-676): Montgomery's trick, one inversion */
+      fe *pre = (fe *)malloc((32 * 255 + 1) * sizeof(fe)); fe acc; f_one(&FPB, &acc);
+      for (int i = 0; i < 32 * 255; i++) { pre[i] = acc; if (!pt_is_inf(&tmp[i])) f_mul(&FPB, &acc, &acc, &tmp[i].z); }
+      fe inv; f_inv(&FPB, &inv, &acc);
+      for (int i = 32 * 255; i-- > 0;) {
+        if (pt_is_inf(&tmp[i])) { f_zero(&f->tab[i].x); f_zero(&f->tab[i].y); continue; }
+        fe zi, zi2, zi3; f_mul(&FPB, &zi, &inv, &pre[i]); f_mul(&FPB, &inv, &inv, &tmp[i].z);
+        f_sqr(&FPB, &zi2, &zi); f_mul(&FPB, &zi3, &zi2, &zi);
+        f_mul(&FPB, &f->tab[i].x, &tmp[i].x, &zi2); f_mul(&FPB, &f->tab[i].y, &tmp[i].y, &zi3);
+      }
+      free(pre); free(tmp);
+      hit = f;
+    }
+  }
+  return hit;
+}
+/* FixedBaseMul::mul (msm.rs:691-726) */
+static void pt_mul_fixed(pt *out, const apt *base, const fe *k) {
+  const fbm *f = fbm_get(base);
+  uint8_t bytes[32]; fe_to_le_bytes(&FQ, k, bytes);
+  pt acc; pt_set_inf(&CV, &acc);
+  for (int w = 0; w < 32; w++) if (bytes[w]) pt_add_mixed(&CV, &acc, &acc, &f->tab[w * 255 + bytes[w] - 1]);
+  *out = acc;
+}
+EXPORT void orc_fixed_base_mul(const apt *base, const fe *k, apt *out) { pt r; pt_mul_fixed(&r, base, k); pt_to_affine(&CV, out, &r); }
 EXPORT void orc_scalar_mul(const apt *base, const fe *k, apt *out) { pt r; pt_mul_fe(&r, base, k); pt_to_affine(&CV, out, &r); }
 EXPORT int orc_on_curve(const apt *p) { return apt_on_curve(&CV, p); }
 EXPORT void orc_point_add(const apt *a, const apt *b, apt *out) { pt p, r; pt_from_affine(&CV, &p, a); pt_add_mixed(&CV, &r, &p, b); pt_to_affine(&CV, out, &r); }
@@ -765,7 +837,7 @@ EXPORT void orc_hyrax_commit(const apt *ck, size_t num_cols, const apt *h, const
 #pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1)
   for (size_t i = 0; i < rows; i++) {
     size_t lo = i * num_cols, hi = lo + num_cols < n ? lo + num_cols : n, len = hi - lo;
-    const fe *s = v + lo; pt hb, acc; pt_mul_fe(&hb, h, &blinds[i]);
+    const fe *s = v + lo; pt hb, acc; pt_mul_fixed(&hb, h, &blinds[i]);      /* h_table.mul (hyrax_pc.rs:222-227, 296) */
     size_t eff = len; while (eff > 0 && f_is_zero(&s[eff - 1])) eff--;
     if (eff == 0) { pt_to_affine(&CV, &out[i], &hb); continue; }
     int all_small = is_small;
@@ -905,9 +977,18 @@ static void sparse_poly_eval(size_t num_vars, const fe *Z, size_t zlen, const fe
  *                recompute the full SpMV (same values).
  * debug_out (optional): [tau (l) | r_x (l) | r_y (m+1)] challenges for cross-checking.
  * ---------------------------------------------------------------------------------- */
+EXPORT int orc_spartan_prove_cached(const shape *S, const keys_view *K, const uint8_t vk_digest[32], const fe *public_values,
+                                    const fe *W, const apt *comm_pre, size_t comm_pre_rows, const rand_view *R,
+                                    proof_view *P, fe *debug_out, double *phase_ms, const fe *caz, const fe *cbz, const fe *ccz);
 EXPORT int orc_spartan_prove(const shape *S, const keys_view *K, const uint8_t vk_digest[32], const fe *public_values,
                              const fe *W, const apt *comm_pre, size_t comm_pre_rows, const rand_view *R,
                              proof_view *P, fe *debug_out, double *phase_ms) {
+  return orc_spartan_prove_cached(S, K, vk_digest, public_values, W, comm_pre, comm_pre_rows, R, P, debug_out, phase_ms, NULL, NULL, NULL);
+}
+/* caz / cbz / ccz: the cached partial products of prep_prove (spartan.rs:184-187), or NULL to recompute the full SpMV */
+EXPORT int orc_spartan_prove_cached(const shape *S, const keys_view *K, const uint8_t vk_digest[32], const fe *public_values,
+                                    const fe *W, const apt *comm_pre, size_t comm_pre_rows, const rand_view *R,
+                                    proof_view *P, fe *debug_out, double *phase_ms, const fe *caz, const fe *cbz, const fe *ccz) {
   double t_last = 0; (void)t_last;
 #ifdef _OPENMP
 #define TICK(idx) do { double now = omp_get_wtime(); if (phase_ms) phase_ms[idx] += (now - t_last) * 1e3; t_last = now; } while (0)
@@ -939,7 +1020,8 @@ EXPORT int orc_spartan_prove(const shape *S, const keys_view *K, const uint8_t v
   fe *tau = (fe *)malloc(l * sizeof(fe));
   for (size_t i = 0; i < l; i++) ts_squeeze(&ts, &FQ, "t", &tau[i]);
   fe *az = (fe *)malloc(N * sizeof(fe)), *bz = (fe *)malloc(N * sizeof(fe)), *cz = (fe *)malloc(N * sizeof(fe));
-  orc_shape_multiply_vec(S, z, az, bz, cz);
+  if (caz) orc_shape_multiply_vec_incremental(S, z, caz, cbz, ccz, az, bz, cz);     /* spartan.rs:271 */
+  else orc_shape_multiply_vec(S, z, az, bz, cz);
   TICK(1);
   fe zero; f_zero(&zero);
   fe *polys = (fe *)malloc(l * 4 * sizeof(fe)), *rx = (fe *)malloc(l * sizeof(fe)), claims[3];
@@ -1107,18 +1189,24 @@ EXPORT void orc_nifs_round(size_t t, size_t ell_b, const fe *rhos, size_t left, 
 EXPORT void orc_nifs_round_block(size_t t, size_t ell_b, const fe *rhos, size_t left, size_t right, const fe *E, const fe *A, const fe *B,
                                  const fe *Cm, size_t N, size_t m, size_t pair_offset, fe *out2) {
   fe e0, q; f_zero(&e0); f_zero(&q);
+  fe *pes = (fe *)malloc((m / 2 + 1) * 2 * sizeof(fe));
+#pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1)      /* par_iter over the pairs (neutronnova_zk.rs:784-834) */
+  for (size_t p = 0; p < m / 2; p++)
+    nifs_prove_helper(t, left, right, E, A + 2 * p * N, B + 2 * p * N, Cm + 2 * p * N, A + (2 * p + 1) * N, B + (2 * p + 1) * N, &pes[2 * p], &pes[2 * p + 1]);
   for (size_t p = 0; p < m / 2; p++) {
-    fe pe, pq, w, tmp;
-    nifs_prove_helper(t, left, right, E, A + 2 * p * N, B + 2 * p * N, Cm + 2 * p * N, A + (2 * p + 1) * N, B + (2 * p + 1) * N, &pe, &pq);
+    fe w, tmp;
     suffix_weight_full(t, ell_b, p + pair_offset, rhos, &w);
-    f_mul(&FQ, &tmp, &pe, &w); f_add(&FQ, &e0, &e0, &tmp);
-    f_mul(&FQ, &tmp, &pq, &w); f_add(&FQ, &q, &q, &tmp);
+    f_mul(&FQ, &tmp, &pes[2 * p], &w); f_add(&FQ, &e0, &e0, &tmp);
+    f_mul(&FQ, &tmp, &pes[2 * p + 1], &w); f_add(&FQ, &q, &q, &tmp);
   }
+  free(pes);
   out2[0] = e0; out2[1] = q;
 }
 /* fold_abc_pair over all pairs (neutronnova_zk.rs:738-776): layer p <- lo + r_b (hi - lo); compacts to m/2 layers */
 EXPORT void orc_nifs_fold(fe *L, size_t N, size_t m, const fe *r_b) {
+  /* pairs are folded in order (layer p <- pair p, compacting in place), each pair's N entries in parallel */
   for (size_t p = 0; p < m / 2; p++)
+#pragma omp parallel for schedule(static) if (g_threads > 1 && N >= 4096)
     for (size_t k = 0; k < N; k++) {
       fe d; f_sub(&FQ, &d, &L[(2 * p + 1) * N + k], &L[2 * p * N + k]); f_mul(&FQ, &d, &d, r_b);
       f_add(&FQ, &L[p * N + k], &L[2 * p * N + k], &d);
@@ -1191,9 +1279,16 @@ EXPORT void orc_pow_cubic_eval(const fe *pl, size_t left, const fe *pr, const fe
 EXPORT void orc_quad_eval(const fe *A, const fe *B, size_t table_len, fe *out2) { quad_points(A, B, table_len, &out2[0], &out2[1]); }
 /* HyraxPCS::fold_commitments (hyrax_pc.rs:737-793) as group elements: out[row] = sum_i w_i * comms[i][row] */
 EXPORT void orc_fold_commitments(const apt *comms, size_t n, size_t rows, const fe *w, apt *out) {
+#pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1)      /* msm_shared_weights: par_iter over rows (msm.rs:312-353) */
   for (size_t r = 0; r < rows; r++) {
-    pt acc; pt_set_inf(&CV, &acc);
-    for (size_t i = 0; i < n; i++) { pt t; pt_mul_fe(&t, &comms[i * rows + r], &w[i]); pt_add(&CV, &acc, &acc, &t); }
+    pt acc;
+    if (n == 2) {                                            /* fast path: p + vartime_scalar_mul(q, w) (hyrax_pc.rs:758-777) */
+      pt t; pt_mul_fe(&acc, &comms[r], &w[0]); pt_mul_fe(&t, &comms[rows + r], &w[1]); pt_add(&CV, &acc, &acc, &t);
+    } else {                                                 /* msm_shared_weights (msm.rs:228-356): a signed-digit bucket MSM per row */
+      apt *rb = (apt *)malloc(n * sizeof(apt));
+      for (size_t i = 0; i < n; i++) rb[i] = comms[i * rows + r];
+      msm_serial(w, rb, n, &acc); free(rb);
+    }
     pt_to_affine(&CV, &out[r], &acc);
   }
 }
@@ -1292,13 +1387,17 @@ EXPORT void orc_nifs_round0_small(size_t ell_b, const fe *rhos, size_t left, siz
                                   const int64_t *A64, const int64_t *B64, const uint64_t *large_positions, size_t n_large, size_t N, size_t m,
                                   fe *out2) {
   fe q; f_zero(&q); f_zero(&out2[0]);
-  for (size_t p = 0; p < m / 2; p++) {
-    fe pq, w, tmp;
+  fe *pqs = (fe *)malloc((m / 2 + 1) * sizeof(fe));
+#pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1)      /* par_iter over the pairs (neutronnova_zk.rs:781-810) */
+  for (size_t p = 0; p < m / 2; p++)
     nifs_prove_helper_small(left, right, E, A + 2 * p * N, B + 2 * p * N, A + (2 * p + 1) * N, B + (2 * p + 1) * N,
-                            A64 + 2 * p * N, B64 + 2 * p * N, A64 + (2 * p + 1) * N, B64 + (2 * p + 1) * N, large_positions, n_large, &pq);
+                            A64 + 2 * p * N, B64 + 2 * p * N, A64 + (2 * p + 1) * N, B64 + (2 * p + 1) * N, large_positions, n_large, &pqs[p]);
+  for (size_t p = 0; p < m / 2; p++) {
+    fe w, tmp;
     suffix_weight_full(0, ell_b, p, rhos, &w);
-    f_mul(&FQ, &tmp, &pq, &w); f_add(&FQ, &q, &q, &tmp);
+    f_mul(&FQ, &tmp, &pqs[p], &w); f_add(&FQ, &q, &q, &tmp);
   }
+  free(pqs);
   out2[1] = q;
 }
 /* c_vals (neutronnova_zk.rs:649-693): c_vals[b] = sum_k E[k] * Cz_b[k] from the i64 layer, corrected at large positions */
@@ -1355,7 +1454,7 @@ EXPORT void orc_hyrax_commit_incremental(const apt *ck, size_t num_cols, const a
     for (size_t j = 0; j < len; j++) if (!f_is_zero(&s[j])) { all_zero = 0; break; }
     if (i < n_raw) pt_from_affine(&CV, &acc, &raw[i]); else pt_set_inf(&CV, &acc);
     if (!all_zero) { pt d; msm(s, ck, len, 0, &d); pt_add(&CV, &acc, &acc, &d); }
-    pt_mul_fe(&hb, h, &blinds[i]); pt_add(&CV, &acc, &acc, &hb);
+    pt_mul_fixed(&hb, h, &blinds[i]); pt_add(&CV, &acc, &acc, &hb);
     pt_to_affine(&CV, &out[i], &acc);
   }
 }
@@ -1364,7 +1463,7 @@ EXPORT void orc_hyrax_rerandomize(const apt *h, const apt *comm, const fe *r_old
 #pragma omp parallel for schedule(static) if (g_threads > 1)
   for (size_t i = 0; i < rows; i++) {
     fe d; f_sub(&FQ, &d, &r_new[i], &r_old[i]);
-    pt a, hb; pt_from_affine(&CV, &a, &comm[i]); pt_mul_fe(&hb, h, &d); pt_add(&CV, &a, &a, &hb);
+    pt a, hb; pt_from_affine(&CV, &a, &comm[i]); pt_mul_fixed(&hb, h, &d); pt_add(&CV, &a, &a, &hb);
     pt_to_affine(&CV, &out[i], &a);
   }
 }
@@ -1383,8 +1482,8 @@ EXPORT void orc_fold_commitments_partial(const apt *comms, size_t n, size_t rows
 #pragma omp parallel for schedule(dynamic, 1) if (g_threads > 1)
   for (size_t r = 0; r < rows; r++) {
     pt acc; pt_set_inf(&CV, &acc);
-    if (r < num_data_rows) for (size_t i = 0; i < n; i++) { pt t; pt_mul_fe(&t, &comms[i * rows + r], &w[i]); pt_add(&CV, &acc, &acc, &t); }
-    else pt_mul_fe(&acc, h, &folded_blind[r]);
+    if (r < num_data_rows) { apt *rb = (apt *)malloc(n * sizeof(apt)); for (size_t i = 0; i < n; i++) rb[i] = comms[i * rows + r]; msm_serial(w, rb, n, &acc); free(rb); }
+    else pt_mul_fixed(&acc, h, &folded_blind[r]);
     pt_to_affine(&CV, &out[r], &acc);
   }
 }
@@ -1463,7 +1562,7 @@ EXPORT int orc_neutronnova_prove(const shape *S, const keys_view *K, const uint8
     const fe *bn = i < n ? R->blinds_steps + i * rows : R->blinds_core;
     apt *out = i < n ? P->comm_W_steps + i * rows : P->comm_W_core;
     orc_hyrax_rerandomize(K->h, cp, bo, bn, pre_rows, out);
-    for (size_t r = pre_rows; r < rows; r++) { pt hb; pt_mul_fe(&hb, K->h, &bn[r]); pt_to_affine(&CV, &out[r], &hb); }
+    for (size_t r = pre_rows; r < rows; r++) { pt hb; pt_mul_fixed(&hb, K->h, &bn[r]); pt_to_affine(&CV, &out[r], &hb); }   /* commit_zeros (hyrax_pc.rs:305-319) */
   }
   TICK(0);
   transcript ts; ts_new(&ts, "neutronnova_prove");
@@ -1481,14 +1580,26 @@ EXPORT int orc_neutronnova_prove(const shape *S, const keys_view *K, const uint8
   for (size_t i = 0; i < n; i++) orc_shape_multiply_vec(S, zs + i * ncols, A + i * N, B + i * N, Cm + i * N);
   fe *Ac = (fe *)malloc(N * sizeof(fe)), *Bc = (fe *)malloc(N * sizeof(fe)), *Cc = (fe *)malloc(N * sizeof(fe));
   orc_shape_multiply_vec(S, zc, Ac, Bc, Cc);
+  /* i64 copies of the A / B layers with the union of the large positions zeroed (prep_prove, neutronnova_zk.rs:1551-1584) */
+  int64_t *A64 = (int64_t *)malloc(n * N * sizeof(int64_t)), *B64 = (int64_t *)malloc(n * N * sizeof(int64_t));
+  uint64_t *lp = (uint64_t *)malloc(N * sizeof(uint64_t)), *tmp_pos = (uint64_t *)malloc(N * sizeof(uint64_t));
+  uint8_t *is_large = (uint8_t *)calloc(N, 1); size_t n_large = 0;
+  for (size_t i = 0; i < n; i++) {
+    size_t k = orc_to_small_vec_or_zero(A + i * N, N, A64 + i * N, tmp_pos); for (size_t q = 0; q < k; q++) is_large[tmp_pos[q]] = 1;
+    k = orc_to_small_vec_or_zero(B + i * N, N, B64 + i * N, tmp_pos); for (size_t q = 0; q < k; q++) is_large[tmp_pos[q]] = 1;
+  }
+  for (size_t k = 0; k < N; k++) if (is_large[k]) { lp[n_large++] = k; for (size_t i = 0; i < n; i++) { A64[i * N + k] = 0; B64[i * N + k] = 0; } }
+  free(tmp_pos); free(is_large);
 #ifdef _OPENMP
-  t_last = omp_get_wtime();                                  /* the matvec is prep_prove work: untimed */
+  t_last = omp_get_wtime();                                  /* the matvec and the i64 conversion are prep_prove work: untimed */
 #endif
-  /* HOT LOOP A: NIFS rounds (neutronnova_zk.rs:778-1168), finish_round! (:703-735) */
+  /* HOT LOOP A: NIFS rounds (neutronnova_zk.rs:778-1168; round 0 on the i64 layers, prove_helper_small :255-325), finish_round! (:703-735) */
   fe T_cur = zero, acc_eq = one, *r_b = (fe *)malloc((ell_b + 1) * sizeof(fe));
   size_t m = n;
   for (size_t t = 0; t < ell_b; t++) {
-    fe e0q[2]; orc_nifs_round(t, ell_b, rhos, left, right, E, A, B, Cm, N, m, e0q);
+    fe e0q[2];
+    if (t == 0) orc_nifs_round0_small(ell_b, rhos, left, right, E, A, B, A64, B64, lp, n_large, N, m, e0q);
+    else orc_nifs_round(t, ell_b, rhos, left, right, E, A, B, Cm, N, m, e0q);
     fe rho = rhos[t], omr, trm, c, a, abc, b, rinv, tmp, tmp2, co[4];
     f_sub(&FQ, &omr, &one, &rho); f_sub(&FQ, &trm, &rho, &omr);
     f_mul(&FQ, &c, &e0q[0], &acc_eq); f_mul(&FQ, &a, &e0q[1], &acc_eq);
@@ -1514,6 +1625,7 @@ EXPORT int orc_neutronnova_prove(const shape *S, const keys_view *K, const uint8
   /* fold_multiple (r1cs/mod.rs:570-660), fold_blinds, X fold, fold_commitments_partial (neutronnova_zk.rs:1212-1262) */
   fe *w = (fe *)malloc(n * sizeof(fe)); orc_weights_from_r(r_b, ell_b, n, w);
   fe *Wf = (fe *)calloc(2 * M, sizeof(fe)), *Wc = (fe *)calloc(2 * M, sizeof(fe));     /* z tables of the inner sum-check */
+#pragma omp parallel for schedule(static) if (g_threads > 1)
   for (size_t j = 0; j < M; j++) { acc9 a; memset(&a, 0, sizeof(a)); for (size_t i = 0; i < n; i++) f_mul_acc(&a, &w[i], &zs[i * ncols + j]); f_reduce9(&FQ, &Wf[j], &a); }
   fe *blind_fold = (fe *)malloc(rows * sizeof(fe)); orc_fold_blinds(R->blinds_steps, n, rows, w, blind_fold);
   fe *X_acc = (fe *)calloc(np + 1, sizeof(fe));
@@ -1603,7 +1715,7 @@ EXPORT int orc_neutronnova_prove(const shape *S, const keys_view *K, const uint8
   if (debug) { debug[0] = T_out; debug[1] = base_tau; debug[2] = r; debug[3] = c_eval; debug[4] = acc_eq; debug[5] = eXs; debug[6] = eXc; }
   free(E); free(rhos); free(A); free(B); free(Cm); free(Ac); free(Bc); free(Cc); free(r_b); free(w); free(Wf); free(Wc); free(blind_fold);
   free(X_acc); free(comm_fold); free(W_fold); free(tau_pow); free(r_x); free(rx); free(abc_s); free(abc_c); free(r_y); free(Xs); free(Xc);
-  free(pair); free(comm); free(blind); free(Wfin);
+  free(pair); free(comm); free(blind); free(Wfin); free(A64); free(B64); free(lp);
   ts_free(&ts);
   return 0;
 }

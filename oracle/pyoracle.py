@@ -235,6 +235,7 @@ class Shape:
         self.dims = (num_cons, num_cons_unpadded, num_shared, num_precommitted, num_rest, num_public, num_challenges)
         self.num_cons = num_cons; self.num_vars = num_shared + num_precommitted + num_rest
         self.num_public = num_public; self.num_challenges = num_challenges
+        self.num_shared = num_shared; self.num_precommitted = num_precommitted
         self._keep = []
         args = [C.c_size_t(x) for x in self.dims]
         for (d, i, p) in (A, B, Cm):
@@ -384,7 +385,16 @@ class Rand:
         return _RandView(*[x.ctypes.data for x in self.a])
 
 
-def spartan_prove(shape, keys, vk_digest, public_values, W, comm_pre, rand, want_debug=False):
+def spartan_prep_cached(shape, W):
+    """prep_prove's cached partial products (spartan.rs:184-187, multiply_vec_precommitted r1cs/mod.rs:1112-1130): Az, Bz, Cz over
+    the shared + precommitted columns only (z = [W_cached | 0 ...])."""
+    cl = shape.num_shared + shape.num_precommitted
+    z = np.zeros((shape.num_vars + 1 + shape.num_public + shape.num_challenges, 4), dtype=np.uint64)
+    z[:cl] = np.ascontiguousarray(W, dtype=np.uint64).reshape(-1, 4)[:cl]
+    return shape.multiply_vec(z)
+
+
+def spartan_prove(shape, keys, vk_digest, public_values, W, comm_pre, rand, want_debug=False, cached=None):
     L = lib()
     num_vars = shape.num_vars; N = shape.num_cons
     l = N.bit_length() - 1; m = num_vars.bit_length() - 1; nry = m + 1
@@ -398,8 +408,9 @@ def spartan_prove(shape, keys, vk_digest, public_values, W, comm_pre, rand, want
     W = np.ascontiguousarray(W, dtype=np.uint64); comm_pre = np.ascontiguousarray(comm_pre, dtype=np.uint64).reshape(-1, 8)
     dbg = fe_array(2 * l + nry)
     phases = (C.c_double * 6)()
-    rc = L.orc_spartan_prove(shape.h, C.byref(kv), _p(dig), _p(pub), _p(W), _p(comm_pre), C.c_size_t(comm_pre.shape[0]),
-                             C.byref(rv), C.byref(pv), _p(dbg), phases)
+    cz = [np.ascontiguousarray(x, dtype=np.uint64) for x in cached] if cached is not None else None
+    rc = L.orc_spartan_prove_cached(shape.h, C.byref(kv), _p(dig), _p(pub), _p(W), _p(comm_pre), C.c_size_t(comm_pre.shape[0]),
+                                    C.byref(rv), C.byref(pv), _p(dbg), phases, *([_p(x) for x in cz] if cz else [None, None, None]))
     if rc != 0:
         raise RuntimeError("orc_spartan_prove failed: %d" % rc)
     P.phase_ms = list(phases)

@@ -397,6 +397,12 @@ int32_t sp2_neutronnova_prep_commit(sp2_ctx *ctx, sp2_nn_prep *prep, const sp2_c
 int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *prep, const uint8_t *vk_digest, const sp2_nn_rand *rand, sp2_nn_snark *snark,
                                     float *phase_ms);
 
+/* instance-sharded variant (one process per GPU, prep state from sp2_neutronnova_prep_prove_sharded + sp2_neutronnova_prep_commit with
+ * the LOCAL instances' blinds): every rank passes the same `rand` (blinds of all n_local * nranks instances) and gets the identical
+ * proof; a rank rerandomises only its own instances, the rows are all-gathered through `allgather` (host buffers).            */
+int32_t sp2_neutronnova_snark_prove_sharded(sp2_ctx *ctx, sp2_nn_prep *prep, sp2_comm *comm, sp2_allgather_fn allgather, void *user,
+                                            const uint8_t *vk_digest, const sp2_nn_rand *rand, sp2_nn_snark *snark, float *phase_ms);
+
 /* ---- host Keccak256Transcript (src/provider/keccak.rs:18-105 behind TranscriptEngineTrait, src/traits/transcript.rs) ----
  * Host-side Fiat-Shamir for drivers that interleave per-round device calls with transcript steps (a Rust caller keeps
  * using its own Keccak256Transcript; this is the same object for C/C++/Python hosts).  Scalars are Montgomery limbs. */
@@ -409,6 +415,8 @@ int32_t sp2_transcript_dom_sep(sp2_transcript *t, const char *label);
 int32_t sp2_transcript_squeeze(sp2_transcript *t, const char *label, uint64_t *out_scalar);
 int32_t sp2_transcript_get_state(const sp2_transcript *t, sp2_transcript_state *out);
 
+/* measurement hook: device time of the last NIFS round-0 kernel (the pass over the i64 layers) of a NeutronNova prove          */
+int32_t sp2_neutronnova_last_round0_ms(sp2_nn_prep *prep, float *ms);
 /* measurement hook: duration in ms (CUDA events on the library's stream) of the most recent persistent cubic
  * sum-check kernel (all multi-CTA rounds of prove_cubic_with_three_inputs in one launch)                              */
 int32_t sp2_last_cubic_persist_ms(sp2_ctx *ctx, float *ms);

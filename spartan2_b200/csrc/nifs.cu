@@ -497,6 +497,7 @@ struct sp2_nn_prep {
   fe *pcs = nullptr;                         // PCS scratch: LZ | L | R | d_vec | z_vec | small scalars
   std::vector<uint64_t> Xs, Xc;              // host copies of the public IO (n x np, np)
   cudaStream_t side = nullptr; cudaEvent_t ev_fold = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_r0a = nullptr, ev_r0b = nullptr; float round0_ms = -1.f;   // device time of the last NIFS round-0 kernel (bench.py: roofline)
 };
 namespace sp2 { struct NnHooks { std::function<int(const std::vector<fe> &)> after_fold; }; }
 
@@ -771,6 +772,8 @@ void sp2_neutronnova_prep_free(sp2_nn_prep *P) {
   if (P->side) cudaStreamDestroy(P->side);
   if (P->ev_fold) cudaEventDestroy(P->ev_fold);
   if (P->ev_side) cudaEventDestroy(P->ev_side);
+  if (P->ev_r0a) cudaEventDestroy(P->ev_r0a);
+  if (P->ev_r0b) cudaEventDestroy(P->ev_r0b);
   if (P->h_mail) cudaFreeHost(P->h_mail);
   if (P->h_stage) cudaFreeHost(P->h_stage);
   delete P;
@@ -928,7 +931,7 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
   fe T_cur = zero, acc_eq = one;
   std::vector<fe> r_bs(ell_b);
   u64 m = n, stride = 1;
-  bool gathered = G == 1;
+  bool gathered = G == 1, timed_r0 = false;
   for (u32 t = 0; t < ell_b; t++) {
     if (!gathered && t >= ell_local) {
       // every rank is down to ONE layer triple: all-gather them (rank order = instance order) and finish the last
@@ -963,8 +966,12 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
     if (t == 0 && P->has_i64 && ell_local > 0) {
       // round 0 on the i64 layers (prove_helper_small, :255-325): e0 = 0, quad from i64 differences / i128 products
       SP2_CUDA_OK(cudaMemsetAsync(P->partials, 0, sizeof(fe), ctx->stream));
+      if (!P->ev_r0a) { SP2_CUDA_OK(cudaEventCreate(&P->ev_r0a)); SP2_CUDA_OK(cudaEventCreate(&P->ev_r0b)); }
+      SP2_CUDA_OK(cudaEventRecord(P->ev_r0a, ctx->stream));
       SP2_TRY(nifs_round0_small_enqueue(ctx, d_rhos, ell_b, left, right, P->E, P->L64[0], P->L64[1], As, Bs, P->large_pos, P->n_large, N, m,
                                         P->partials + 64, P->partials + 1, pair_offset));
+      SP2_CUDA_OK(cudaEventRecord(P->ev_r0b, ctx->stream));
+      timed_r0 = true;
       if (local && xchg) k_publish_xchg<<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, 1, comm->dc, (int)t + 1, nn_mail_dev(P), mail_flag, seq);
       else k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, 1, nn_mail_dev(P), mail_flag, seq, P->ticket);
     } else {
@@ -975,6 +982,7 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
     }
     SP2_LAUNCH_CHECK();
     SP2_TRY(nn_wait(P, seq));
+    if (timed_r0 && t == 0 && cudaEventSynchronize(P->ev_r0b) == cudaSuccess) cudaEventElapsedTime(&P->round0_ms, P->ev_r0a, P->ev_r0b);
     fe e0 = nn_mail(P)[0], quad = nn_mail(P)[1];
     if (local && !xchg) {
       // the round's two sums over ALL ranks' pairs: one 64-byte all-gather + modular adds on the host — every rank then
@@ -1234,6 +1242,8 @@ int32_t sp2_neutronnova_prep_connect_ptrs(sp2_nn_prep *P, void *const *xbufs) {
   P->peers_connected = true;
   return SP2_OK;
 }
+/* measurement hook: device time (CUDA events on the library's stream) of the last NIFS round-0 kernel (the i64 layers pass) */
+int32_t sp2_neutronnova_last_round0_ms(sp2_nn_prep *P, float *ms) { if (!P || P->round0_ms < 0) return SP2_ERR_INTERNAL; *ms = P->round0_ms; return SP2_OK; }
 int32_t sp2_neutronnova_prove(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, sp2_nn_proof *pf, float *phase_ms) {
   return nn_prove_impl(ctx, P, tsh, nullptr, nullptr, nullptr, pf, phase_ms);
 }
@@ -1305,7 +1315,6 @@ int32_t sp2_neutronnova_prep_commit(sp2_ctx *ctx, sp2_nn_prep *P, const sp2_ck *
   if (!P || !ck) return set_error(ctx, SP2_ERR_INTERNAL, "prep_commit: null argument");
   const sp2_shape *S = P->S;
   const uint64_t width = ck->n, M = P->M;
-  if (P->nranks > 1) return set_error(ctx, SP2_ERR_UNSUPPORTED, "prep_commit: the commitment half runs on the single-GPU prep state");
   if (S->num_shared) return set_error(ctx, SP2_ERR_UNSUPPORTED, "prep_commit: circuits with a shared witness section are not offloaded");
   if (M % width || S->num_precommitted % width) return set_error(ctx, SP2_ERR_INVALID_WITNESS_LENGTH, "prep_commit: witness sections must be multiples of the commitment width");
   if (P->U) return set_error(ctx, SP2_ERR_INTERNAL, "prep_commit: already committed");
@@ -1315,7 +1324,7 @@ int32_t sp2_neutronnova_prep_commit(sp2_ctx *ctx, sp2_nn_prep *P, const sp2_ck *
   void *p;
   SP2_TRY(nn_palloc(P, nrow * sizeof(aff), &p)); P->U = (aff *)p;
   SP2_TRY(nn_palloc(P, (nrow + 2 * rows + 16) * sizeof(jac) + nrow * sizeof(aff), &p)); P->pts = (jac *)p;   // [instance rows | folded rows | 2 eval | final rows + 4] | affine rows
-  SP2_TRY(nn_palloc(P, (nrow + 2 * rows + 16) * sizeof(fe), &p)); P->blinds_dev = (fe *)p;
+  SP2_TRY(nn_palloc(P, (nrow + 2 * rows + 16 + (size_t)P->n_total * rows) * sizeof(fe), &p)); P->blinds_dev = (fe *)p;   // local rows | folded | final | all instances' blinds
   SP2_TRY(nn_palloc(P, M * sizeof(fe), &p)); P->Wfold = (fe *)p;
   SP2_TRY(nn_palloc(P, M * sizeof(fe), &p)); P->Wfin = (fe *)p;
   SP2_TRY(nn_palloc(P, (5 * width + 2 * rows + NS_COUNT + 64) * sizeof(fe), &p)); P->pcs = (fe *)p;
@@ -1360,32 +1369,43 @@ int32_t sp2_neutronnova_prep_commit(sp2_ctx *ctx, sp2_nn_prep *P, const sp2_ck *
 
 /* phase_ms (optional, 10 floats, host wall clock): rerandomize + commit_zeros, instance transcript, nifs, fold_witness,
  * outer_sumcheck_batched, compute_eval_table_sparse, inner_sumcheck_batched, eval commitments + c_eval, pcs_prove, total */
-int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t *vk_digest, const sp2_nn_rand *rnd, sp2_nn_snark *sn, float *phase_ms) {
+static int32_t nn_snark_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *xcomm, sp2_allgather_fn allgather, void *user, const uint8_t *vk_digest,
+                             const sp2_nn_rand *rnd, sp2_nn_snark *sn, float *phase_ms) {
   cudaSetDevice(ctx->device);
   if (!P || !rnd || !sn || !vk_digest) return set_error(ctx, SP2_ERR_INTERNAL, "snark_prove: null argument");
+  if (P->nranks > 1 && !allgather) return set_error(ctx, SP2_ERR_INTERNAL, "snark_prove: a sharded prep state needs the all-gather callback (instance commitments)");
   if (!P->U) return set_error(ctx, SP2_ERR_INTERNAL, "snark_prove: sp2_neutronnova_prep_commit has not run on this prep state");
   typedef NnHost H;
   const sp2_ck *ck = P->ck;
-  const uint32_t n = P->n, rows = P->rows, pre_rows = P->pre_rows, np = P->np;
+  // n: the step instances THIS rank holds (all of them on one GPU); their blinds are rows [rank * n, (rank + 1) * n) of rnd->blinds_steps
+  const uint32_t n = P->n, n_total = P->n_total, rows = P->rows, pre_rows = P->pre_rows, np = P->np;
   const uint64_t width = ck->n, M = P->M;
   const size_t nrow = (size_t)(n + 1) * rows;
+  const uint64_t *my_blinds = rnd->blinds_steps + (size_t)P->rank * n * rows * 4;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [](std::chrono::steady_clock::time_point a) { return (float)(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count()); };
   const auto t_begin = now(); auto t_phase = t_begin;
   float ph[10] = {0};
   sn->rows = rows;
   fe *small = P->pcs, *LZ = small + NS_COUNT, *Ltab = LZ + width, *Rtab = Ltab + rows, *dvec = Rtab + width, *zvec = dvec + width;
-  fe *blind_fold = P->blinds_dev + nrow, *blind_fin = blind_fold + rows;
-  // pinned staging: [blinds | d_vec | Jacobian read-backs]
-  const size_t in_fe = nrow + width + NS_COUNT + 16;      // (also receives the NS_COUNT small scalars read back at the end)
+  fe *blind_fold = P->blinds_dev + nrow, *blind_fin = blind_fold + rows, *blinds_all = blind_fin + rows + 16;
+  // pinned staging: [blinds | d_vec | all instances' blinds | Jacobian read-backs]
+  const size_t in_fe = nrow + width + NS_COUNT + 16 + (P->nranks > 1 ? (size_t)n_total * rows : 0);      // (also receives the NS_COUNT small scalars read back at the end)
   const size_t stage_need = in_fe * sizeof(fe) + (nrow + rows + 8) * sizeof(jac);
   void *hp; SP2_TRY(pinned(ctx, stage_need, &hp));
   uint8_t *h_in = (uint8_t *)hp; uint64_t *h_jac = (uint64_t *)(h_in + in_fe * sizeof(fe));
   // ---- rerandomize_commitment (precommitted rows) + commit_zeros (rest rows): row = U_row + blind * h ----------------
-  memcpy(h_in, rnd->blinds_steps, (size_t)n * rows * 32); memcpy(h_in + (size_t)n * rows * 32, rnd->blinds_core, (size_t)rows * 32);
+  memcpy(h_in, my_blinds, (size_t)n * rows * 32); memcpy(h_in + (size_t)n * rows * 32, rnd->blinds_core, (size_t)rows * 32);
   memcpy(h_in + nrow * 32, rnd->d_vec, width * 32);
   SP2_CUDA_OK(cudaMemcpyAsync(P->blinds_dev, h_in, nrow * 32, cudaMemcpyHostToDevice, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(dvec, h_in + nrow * 32, width * 32, cudaMemcpyHostToDevice, ctx->stream));
+  const fe *fold_src = P->blinds_dev;                        // [instance][row] blinds the fold runs over
+  if (P->nranks > 1) {                                       // fold_blinds needs every instance's blinds (identical inputs on all ranks)
+    uint8_t *h_all = h_in + (nrow + width + NS_COUNT + 16) * 32;
+    memcpy(h_all, rnd->blinds_steps, (size_t)n_total * rows * 32);
+    SP2_CUDA_OK(cudaMemcpyAsync(blinds_all, h_all, (size_t)n_total * rows * 32, cudaMemcpyHostToDevice, ctx->stream));
+    fold_src = blinds_all;
+  }
   { std::vector<MsmJob> jobs(nrow);
     for (size_t k = 0; k < nrow; k++) {
       MsmJob &j = jobs[k]; memset(&j, 0, sizeof(j));
@@ -1397,7 +1417,8 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
     // a serial host pass over thousands of points costs ~1 ms
     aff *d_aff = (aff *)(P->pts + nrow + 2 * rows + 16);
     SP2_TRY(batch_normalize_dev(ctx, P->pts, nrow, d_aff));
-    SP2_CUDA_OK(cudaMemcpyAsync(sn->comm_W_steps, d_aff, (size_t)n * rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t *dst = sn->comm_W_steps + (size_t)P->rank * n * rows * 8;
+    SP2_CUDA_OK(cudaMemcpyAsync(dst, d_aff, (size_t)n * rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
     SP2_CUDA_OK(cudaMemcpyAsync(sn->comm_W_core, d_aff + (size_t)n * rows, (size_t)rows * sizeof(aff), cudaMemcpyDeviceToHost, ctx->stream));
     SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   } else {
@@ -1405,7 +1426,13 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
     SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     std::vector<uint64_t> aff_all(nrow * 8);
     sp2h::batch_normalize(h_jac, nrow, aff_all.data());
-    memcpy(sn->comm_W_steps, aff_all.data(), (size_t)n * rows * 64); memcpy(sn->comm_W_core, aff_all.data() + (size_t)n * rows * 8, (size_t)rows * 64);
+    memcpy(sn->comm_W_steps + (size_t)P->rank * n * rows * 8, aff_all.data(), (size_t)n * rows * 64); memcpy(sn->comm_W_core, aff_all.data() + (size_t)n * rows * 8, (size_t)rows * 64);
+  }
+  if (P->nranks > 1) {
+    // every rank rerandomised its own instances: all-gather the rows (rank order = instance order; 64 B per row) so that every
+    // rank absorbs the same transcript.  A host collective: the rows have to reach the host for the Keccak transcript anyway.
+    std::vector<uint64_t> mine(sn->comm_W_steps + (size_t)P->rank * n * rows * 8, sn->comm_W_steps + (size_t)(P->rank + 1) * n * rows * 8);
+    if (allgather(user, mine.data(), (uint64_t)n * rows * 64, sn->comm_W_steps, 0) != 0) return set_error(ctx, SP2_ERR_INTERNAL, "snark_prove: all-gather of the instance commitments failed");
   }
   ph[0] = ms_since(t_phase); t_phase = now();
   // ---- transcript over the instances (neutronnova_zk.rs:1727-1733, 552-556; R1CSInstance bytes r1cs/mod.rs:728-736) -----
@@ -1419,7 +1446,7 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
     for (uint32_t j = 0; j < np; j++) { uint64_t c[4]; uint8_t b[32]; sp2h::from_mont(X + 4 * j, sp2h::FQ_MOD, sp2h::FQ_INV, c); sp2h::limbs_to_be(c, b); ts.push(b, 32); }
   };
   absorb_instance("core_instance", sn->comm_W_core, np ? P->Xc.data() : nullptr);
-  for (uint32_t i = 0; i < n; i++) absorb_instance("U", sn->comm_W_steps + (size_t)i * rows * 8, np ? &P->Xs[(size_t)i * np * 4] : nullptr);
+  for (uint32_t i = 0; i < n_total; i++) absorb_instance("U", sn->comm_W_steps + (size_t)i * rows * 8, np ? &P->Xs[(size_t)i * np * 4] : nullptr);
   ph[1] = ms_since(t_phase); t_phase = now();
   // ---- HOT LOOPS A-C; right after the witness fold: copy W_fold, fold the blinds, and start the commitment of the folded
   // witness rows on the side stream (it overlaps the outer and inner sum-checks) -------------------------------------------
@@ -1428,7 +1455,7 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
   hooks.after_fold = [&](const std::vector<fe> &) -> int {
     SP2_CUDA_OK(cudaMemcpyAsync(P->Wfold, P->z_step, M * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
     // fold_blinds (hyrax_pc.rs:795-819): blinds_dev is [instance][row] = n vectors of `rows` entries; weights at small + 128
-    k_fold_vectors<<<1, NF_THREADS, 0, ctx->stream>>>(P->blinds_dev, n, rows, P->small + 128, blind_fold);
+    k_fold_vectors<<<1, NF_THREADS, 0, ctx->stream>>>(fold_src, n_total, rows, P->small + 128, blind_fold);
     SP2_LAUNCH_CHECK();
     SP2_CUDA_OK(cudaEventRecord(P->ev_fold, ctx->stream));
     SP2_CUDA_OK(cudaStreamWaitEvent(P->side, P->ev_fold, 0));
@@ -1441,7 +1468,7 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
     return SP2_OK;
   };
   float ph_core[6];
-  SP2_TRY(nn_prove_impl(ctx, P, &tsobj, nullptr, nullptr, nullptr, &sn->base, ph_core, &hooks));
+  SP2_TRY(nn_prove_impl(ctx, P, &tsobj, xcomm, allgather, user, &sn->base, ph_core, &hooks));
   for (int k = 0; k < 5; k++) ph[2 + k] = ph_core[k];
   t_phase = now();
   // ---- commitments to eval_W_step / eval_W_core, c_eval (neutronnova_zk.rs:1953-2017 in its non-ZK form) ------------------
@@ -1530,6 +1557,18 @@ int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t 
   ph[9] = ms_since(t_begin);
   if (phase_ms) memcpy(phase_ms, ph, sizeof(ph));
   return SP2_OK;
+}
+
+int32_t sp2_neutronnova_snark_prove(sp2_ctx *ctx, sp2_nn_prep *P, const uint8_t *vk_digest, const sp2_nn_rand *rnd, sp2_nn_snark *sn, float *phase_ms) {
+  if (P && P->nranks > 1) return set_error(ctx, SP2_ERR_INTERNAL, "snark_prove: sharded prep state: use sp2_neutronnova_snark_prove_sharded");
+  return nn_snark_impl(ctx, P, nullptr, nullptr, nullptr, vk_digest, rnd, sn, phase_ms);
+}
+/* Instance-sharded (one process per GPU; see sp2_neutronnova_prove_sharded): every rank passes the SAME rand (blinds of all
+ * n_local * nranks instances) and receives the identical proof; a rank rerandomises / commits only its own instances and the rows
+ * are all-gathered through `allgather` (host buffers, on_device = 0). */
+int32_t sp2_neutronnova_snark_prove_sharded(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *comm, sp2_allgather_fn allgather, void *user, const uint8_t *vk_digest,
+                                            const sp2_nn_rand *rnd, sp2_nn_snark *sn, float *phase_ms) {
+  return nn_snark_impl(ctx, P, comm, allgather, user, vk_digest, rnd, sn, phase_ms);
 }
 
 }  // extern "C"

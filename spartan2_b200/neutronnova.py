@@ -330,10 +330,10 @@ class NeutronNovaProver:
         self.ck = ck
         pre_rows = S.num_precommitted // ck.n
         bs = _fe(blinds_pre_steps); bc = _fe(blinds_pre_core)
-        cs = np.zeros((max(self.n * pre_rows, 1), 8), dtype=np.uint64); cc = np.zeros((max(pre_rows, 1), 8), dtype=np.uint64)
+        cs = np.zeros((max(self.n_local * pre_rows, 1), 8), dtype=np.uint64); cc = np.zeros((max(pre_rows, 1), 8), dtype=np.uint64)
         ctx.check(ctx.L.sp2_neutronnova_prep_commit(ctx.h, self.h, ck.h, _p(bs if bs.size else np.zeros((1, 4), dtype=np.uint64)),
                                                     _p(bc if bc.size else np.zeros((1, 4), dtype=np.uint64)), _p(cs), _p(cc)))
-        return cs[:self.n * pre_rows], cc[:pre_rows]
+        return cs[:self.n_local * pre_rows], cc[:pre_rows]
 
     SNARK_PHASES = ("rerandomize+commit_zeros", "instance_transcript", "nifs", "fold_witness", "outer_sumcheck_batched", "compute_eval_table_sparse",
                     "inner_sumcheck_batched", "eval_commitments+c_eval", "pcs_prove", "total")
@@ -361,7 +361,11 @@ class NeutronNovaProver:
         rv = _NnRandC(*[a.ctypes.data for a in arrs])
         dig = np.frombuffer(bytes(vk_digest), dtype=np.uint8).copy()
         ph = (C.c_float * 10)()
-        ctx.check(ctx.L.sp2_neutronnova_snark_prove(ctx.h, self.h, _p(dig), C.byref(rv), C.byref(sn), ph))
+        if self._cb is None:
+            ctx.check(ctx.L.sp2_neutronnova_snark_prove(ctx.h, self.h, _p(dig), C.byref(rv), C.byref(sn), ph))
+        else:
+            ctx.check(ctx.L.sp2_neutronnova_snark_prove_sharded(ctx.h, self.h, self.comm.h if self.comm is not None else None, self._cb, None, _p(dig),
+                                                                 C.byref(rv), C.byref(sn), ph))
         out.update(ext)
         out["outer_ok"], out["inner_ok"] = bool(sn.base.outer_ok), bool(sn.base.inner_ok)
         return out, dict(zip(self.SNARK_PHASES, [float(x) for x in ph]))

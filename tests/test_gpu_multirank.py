@@ -189,6 +189,75 @@ def test_sharded_neutronnova_peer_stores_on_one_gpu(ctx, orc, ranks, n, world):
         x.free()
 
 
+@pytest.mark.parametrize("n,world", [(4, 2), (8, 4)])
+def test_sharded_neutronnova_snark_on_one_gpu(ctx, orc, ranks, n, world):
+    """The FULL NeutronNova prove, instance-sharded (sp2_neutronnova_snark_prove_sharded): every rank rerandomises / commits only
+    its own instances, the rows are all-gathered for the transcript, per-round sums and bulk exchanges go through the peer
+    mailboxes — every rank's proof == the single-GPU proof == the oracle's C driver, and the oracle verifier accepts it."""
+    import ctypes as C
+    import spartan2_b200 as sp
+    from spartan2_b200 import neutronnova as nn
+    from tests.test_gpu_neutronnova_snark import FIELDS, sha_case
+    from tests.test_oracle_neutronnova_snark import prove, step_X
+    c = sha_case(orc, ctx, n)
+    orc.set_threads(orc.max_threads())
+    P = prove(orc, c)
+    orc.set_threads(1)
+    K = c["keys"]; rows, pre_rows = c["rows"], c["pre_rows"]; nl = n // world
+    cs = ranks(world)
+    shapes = [sp.SplitR1CSShape(x, *c["dims"], *c["mats"]) for x in cs]
+    cks = [sp.CommitmentKey(x, K.ck, K.h, K.ck_s, K.h_s) for x in cs]
+    rnd = c["rand"].a
+    for x, S, ck in zip(cs, shapes, cks):                    # single-GPU snark on every context: reference + scratch warm-up
+        single = nn.NeutronNovaProver(x, S, list(c["zs"]), c["zc"]); single.commit(ck, c["b_old_s"], c["b_old_c"])
+        v1, _ = single.snark_prove(c["vk"], *rnd)
+        for k in FIELDS:
+            assert np.array_equal(np.asarray(v1[k]).reshape(-1), getattr(P, k).reshape(-1)), k
+        single.free()
+    bar = threading.Barrier(world); slots = [None] * world
+
+    def make_allgather(rank):
+        def allgather(send, nbytes, recv, on_device):
+            slots[rank] = (send, nbytes)
+            bar.wait()
+            for q in range(world):
+                src, nb = slots[q]
+                if on_device:
+                    if recv + q * nbytes != src:
+                        cs[rank].check(cs[rank].L.sp2_dev_copy(cs[rank].h, C.c_void_p(recv + q * nbytes), C.c_void_p(src), C.c_uint64(nbytes)))
+                else:
+                    C.memmove(recv + q * nbytes, src, nbytes)
+            if on_device:
+                cs[rank].synchronize()
+            bar.wait()
+        return allgather
+    comms = sp.Comm.in_process(cs)
+    provers = [nn.NeutronNovaProver(cs[r], shapes[r], list(c["zs"][r * nl:(r + 1) * nl]), c["zc"], rank=r, nranks=world, allgather=make_allgather(r), comm=comms[r])
+               for r in range(world)]
+    nn.NeutronNovaProver.connect_in_process(provers)
+    for r, pr in enumerate(provers):
+        cs_, cc_ = pr.commit(cks[r], c["b_old_s"][r * nl * pre_rows:(r + 1) * nl * pre_rows], c["b_old_c"])
+        assert np.array_equal(cs_, c["comm_pre_s"][r * nl * pre_rows:(r + 1) * nl * pre_rows]) and np.array_equal(cc_, c["comm_pre_c"])
+
+    def run(r):
+        try:
+            return provers[r].snark_prove(c["vk"], *rnd)[0]
+        except Exception:
+            bar.abort(); raise
+    for rep in range(2):
+        outs = _threads(world, run)
+        for v in outs:
+            for k in FIELDS:
+                assert np.array_equal(np.asarray(v[k]).reshape(-1), getattr(P, k).reshape(-1)), (rep, k)
+    V = orc.NnProof(n, c["dims"][0], c["M"], c["width"])
+    for k in FIELDS:
+        getattr(V, k)[...] = np.asarray(outs[-1][k]).reshape(getattr(V, k).shape)
+    sx, cx = step_X(c)
+    assert orc.neutronnova_verify(c["O"], K, c["vk"], sx, cx, V) == 0
+    for x in provers + comms + shapes + cks:
+        x.free()
+
+
 def test_missing_peer_times_out_and_comm_recovers(ctx, orc, ranks):
     """Rank 0 enters a sharded sum-check alone: its kernels' waits on the peer mailbox are bounded (%globaltimer), so the
     call returns InternalError after ~2 s instead of hanging the GPU; after sp2_comm_reset on both ranks the same call

@@ -698,6 +698,308 @@ k_quad_tail(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int roun
   }
 }
 
+// ---- pipelined single-CTA tails ------------------------------------------------------------------------------------------
+// In the tail a round costs ~27k cycles, of which the Keccak squeeze is ~12k and the pair work ~9k — and the pair work waits
+// for the challenge.  It does not have to: binding is linear in r, so the sums of round i+1, taken over the table bound to
+// r_i, are QUADRATIC POLYNOMIALS in r_i whose coefficients depend on the unbound table only.  The pipelined tails compute,
+// during round i's squeeze, the coefficient sums of round i+1 (Karatsuba form: sum x y, sum (x+dx)(y+dy), sum dx dy for each
+// bilinear sum); when r_i arrives a finaliser warp evaluates the round-(i+1) sums with two multiplications and goes straight
+// to the next squeeze, while the role warps bind the table to r_i and take the coefficients of round i+2 under that squeeze.
+// Only the transcript, the round algebra and the challenge stay on a round's critical path.  Same sums, same field
+// elements: bit-identical (tests/test_gpu_sumcheck.py, every l).  CTA = 12 role warps + 4 finaliser warps (128 registers).
+constexpr int TP_ROLE = SC_TAIL_THREADS, TP_FIN = 128, TP_THREADS = TP_ROLE + TP_FIN;
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct TailSmem {
+  FinSmem fin;
+  fe coef[2][9];              // coefficient sums of the next round (double-buffered)
+  fe x[3];                    // sums of a directly evaluated round
+  fe claim;                   // quadratic prover: the running claim
+  fe red[3 * (TP_ROLE / 32)];
+};
+// sum of NV values per role thread over the TP_ROLE role threads -> out[0..NV) (shared); all role threads must call
+template <int NV>
+__device__ __forceinline__ void role_sum(fe (&x)[NV], fe *red, fe *out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = TP_ROLE / 32;
+  warp_sum_fq_cols<NV>(x);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) red[k * NW + warp] = x[k];
+  }
+  bar_sync_n(1, TP_ROLE);
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) x[k] = lane < NW ? red[k * NW + lane] : Fq::zero();
+    warp_sum_fq_cols<NV>(x);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; k++) out[k] = x[k];
+    }
+  }
+  bar_sync_n(1, TP_ROLE);
+}
+// sc_squeeze for the finaliser group (threads [TP_ROLE, TP_THREADS), barrier 2): same message, same digests
+__device__ __forceinline__ fe sc_squeeze_g(ScState *st, FinSmem &sm, const fe &canon, int ncoef) {
+  const int tid = (int)threadIdx.x - TP_ROLE;
+  unsigned char *mb = (unsigned char *)sm.m[0];
+  const int plen = 1 + 32 * ncoef, mlen = plen + 4 + 2 + 64 + 1, total = mlen + 1, nblocks = total / 136 + 1;
+  if (tid < 34) sm.m[0][tid] = 0;
+  bar_sync_n(2, TP_FIN);
+  if (tid < ncoef) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const u32 w = canon.v[k];
+      unsigned char *q = mb + 1 + 32 * tid + 4 * k;
+      q[0] = (unsigned char)w; q[1] = (unsigned char)(w >> 8); q[2] = (unsigned char)(w >> 16); q[3] = (unsigned char)(w >> 24);
+    }
+  }
+  if (tid == 32) {
+    const u32 round = st->ts.round;
+    mb[0] = 'p';
+    mb[plen + 0] = 'N'; mb[plen + 1] = 'o'; mb[plen + 2] = 'D'; mb[plen + 3] = 'S';
+    mb[plen + 4] = (unsigned char)(round & 0xff); mb[plen + 5] = (unsigned char)(round >> 8);
+    mb[mlen - 1] = 'c';
+    mb[total] ^= 0x01;
+    mb[nblocks * 136 - 1] ^= 0x80;
+    st->ts.round = round + 1;
+  }
+  if (tid >= 64 && tid < 128) mb[plen + 6 + (tid - 64)] = st->ts.state[tid - 64];
+  bar_sync_n(2, TP_FIN);
+  if (tid < 34) sm.m[1][tid] = sm.m[0][tid];
+  bar_sync_n(2, TP_FIN);
+  if (tid == 32) ((unsigned char *)sm.m[1])[mlen] = 0x01;
+  __syncwarp();
+  if (tid < 64) {
+    const int lane = tid & 31, w = tid >> 5;
+    const KeccakLane kl = keccak_lane_init(lane);
+    u64 s = 0;
+    for (int blk = 0; blk < nblocks; blk++) {
+      if (lane < 17) s ^= sm.m[w][blk * 17 + lane];
+      s = keccak_f_warp(s, kl, lane);
+    }
+    if (lane < 4) sm.dg[w * 4 + lane] = s;
+  }
+  bar_sync_n(2, TP_FIN);
+  if (tid >= 64 && tid < 128) st->ts.state[tid - 64] = ((unsigned char *)sm.dg)[tid - 64];
+  if (tid < 2) {
+    fe h;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { h.v[2 * i] = (u32)sm.dg[4 * tid + i]; h.v[2 * i + 1] = (u32)(sm.dg[4 * tid + i] >> 32); }
+    sm.g[6 + tid] = mul_ni(h, tid == 0 ? Fq::cst_r2() : Fq::cst_r3());
+  }
+  bar_sync_n(2, TP_FIN);
+  if (tid == 0) sm.ch = Fq::add(sm.g[6], sm.g[7]);
+  bar_sync_n(2, TP_FIN);
+  return sm.ch;
+}
+// c0 + r (mid + r c2) with mid = c22 - c0 - c2 (Karatsuba form of the middle coefficient)
+__device__ __forceinline__ fe eval_karatsuba(const fe &c00, const fe &c22, const fe &cdd, const fe &r) {
+  const fe mid = Fq::sub(Fq::sub(c22, c00), cdd);
+  return Fq::add(c00, mul_ni(r, Fq::add(mid, mul_ni(r, cdd))));
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
+k_quad_tail_pipe(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int rounds, u64 nvalid) {
+  __shared__ TailSmem ts;
+  const int tid = threadIdx.x, ft = tid - TP_ROLE;
+  const bool is_role = tid < TP_ROLE;
+  fe *sA = A, *sB = B, *dA = A2, *dB = B2;
+  const int warp = tid >> 5, role = warp % 3;
+  const u64 slot = (u64)(warp / 3) * 32 + (tid & 31), nslots = (TP_ROLE / 96) * 32;
+  fe r = Fq::zero();
+  if (round_first > 1) r = ld_state(&st->r[round_first - 2]);
+  if (tid == TP_ROLE) ts.claim = ld_state(&st->claim);
+  bool have_coef = false; int cur = 0;
+  __syncthreads();
+  for (int round1 = round_first; round1 <= rounds; round1++) {
+    const u64 P = (u64)1 << (rounds - round1);                 // pairs of this round
+    const bool direct = !have_coef;
+    const bool want_next = round1 + 1 <= rounds && round1 + 1 > 2;   // rounds 1, 2 may see unmaterialised entries: evaluated directly
+    const u64 nv = round1 <= 2 ? nvalid : ~0ull;
+    if (is_role) {
+      if (direct) {
+        fe x[2];
+        if (round1 > 1) quad_roles<true>(sA, sB, dA, dB, P, r, role, slot, nslots, nv, x);
+        else quad_roles<false>(sA, sB, dA, dB, P, Fq::zero(), role, slot, nslots, nv, x);
+        role_sum<2>(x, ts.red, ts.x);
+        __threadfence_block();
+        bar_arrive_n(3, TP_THREADS);                            // the finalisers may start on ts.x
+      } else {
+        // bind the table to r: dst[j] = src[j] + r (src[j + 2P] - src[j]), j < 2P, both tables
+        for (u64 q = (u64)tid; q < 4 * P; q += TP_ROLE) {
+          const u64 j = q >> 1;
+          const fe *S = (q & 1) ? sB : sA; fe *D = (q & 1) ? dB : dA;
+          stg_fe(D + j, bind_pair(ldg_fe(S + j), ldg_fe(S + j + 2 * P), r));
+        }
+        bar_sync_n(1, TP_ROLE);
+      }
+      const fe *cA = round1 > 1 ? dA : sA, *cB = round1 > 1 ? dB : sB;     // the table this round's pairs live in (length 2P)
+      if (want_next) {
+        // coefficients of round1 + 1 (pairs (j, j + P/2) of the table bound to THIS round's challenge):
+        //   even warps: sum a0 b0, sum a2 b2, sum (a2-a0)(b2-b0);  odd warps: the same for u = a1 - a0, u + du = a3 - a2
+        const u64 Hn = P / 2;
+        Fq::acc c0 = Fq::acc_zero(), c2 = Fq::acc_zero(), cd = Fq::acc_zero();
+        const int grp = warp & 1;
+        for (u64 j = (u64)(warp >> 1) * 32 + (tid & 31); j < Hn; j += (TP_ROLE / 64) * 32) {
+          fe x0, x2, y0, y2;
+          if (grp == 0) { x0 = ldg_fe(cA + j); x2 = ldg_fe(cA + j + P); y0 = ldg_fe(cB + j); y2 = ldg_fe(cB + j + P); }
+          else {
+            x0 = Fq::sub(ldg_fe(cA + j + Hn), ldg_fe(cA + j)); x2 = Fq::sub(ldg_fe(cA + j + P + Hn), ldg_fe(cA + j + P));
+            y0 = Fq::sub(ldg_fe(cB + j + Hn), ldg_fe(cB + j)); y2 = Fq::sub(ldg_fe(cB + j + P + Hn), ldg_fe(cB + j + P));
+          }
+          Fq::mul_acc(c0, x0, y0); Fq::mul_acc(c2, x2, y2); Fq::mul_acc(cd, Fq::sub(x2, x0), Fq::sub(y2, y0));
+        }
+        const fe v0 = Fq::acc_reduce(c0), v2 = Fq::acc_reduce(c2), vd = Fq::acc_reduce(cd), z = Fq::zero();
+        fe xa[3] = {grp ? z : v0, grp ? z : v2, grp ? z : vd}, xb[3] = {grp ? v0 : z, grp ? v2 : z, grp ? vd : z};
+        role_sum<3>(xa, ts.red, ts.coef[cur ^ 1]);
+        role_sum<3>(xb, ts.red, ts.coef[cur ^ 1] + 3);
+      }
+    } else {
+      fe e0 = Fq::zero(), ti = Fq::zero();
+      if (direct) { bar_sync_n(3, TP_THREADS); e0 = ts.x[0]; ti = ts.x[1]; }
+      else {
+        const fe *c = ts.coef[cur];
+        if (ft < 2) ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r);
+        bar_sync_n(2, TP_FIN);
+        e0 = ts.x[0]; ti = ts.x[1];
+      }
+      // round message (quad_finalize_pre) on the finaliser group
+      const int i = round1 - 1;
+      fe canon = Fq::zero();
+      const fe b = Fq::sub(Fq::sub(ts.claim, Fq::dbl(e0)), ti);
+      if (ft < 3) stg_fe(&st->polys[4 * i + ft], ft == 0 ? e0 : ft == 1 ? b : ti);
+      if (ft < 2) canon = Fq::from_mont(ft == 0 ? e0 : ti);
+      const fe rn = sc_squeeze_g(st, ts.fin, canon, 2);
+      if (ft == 0) stg_fe(&st->r[i], rn);
+      if (ft == 32) ts.claim = Fq::add(e0, mul_ni(rn, Fq::add(b, mul_ni(rn, ti))));       // claim <- poly(r)
+    }
+    __syncthreads();
+    r = ts.fin.ch;
+    if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; }
+    have_coef = want_next; cur ^= 1;
+  }
+  if (tid == TP_ROLE) stg_fe(&st->claim, ts.claim);
+  quad_claims(st, sA, sB, r);
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
+k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int round_first, int l, const fe *eq_left, const fe *eq_right) {
+  __shared__ TailSmem ts;
+  __shared__ fe s_L0, s_SL, s_p;
+  const int first_half = l / 2, second_half = l - first_half;
+  const int tid = threadIdx.x, ft = tid - TP_ROLE;
+  const bool is_role = tid < TP_ROLE;
+  fe *sA = A, *sB = B, *sC = C, *dA = A2, *dB = B2, *dC = C2;
+  const int warp = tid >> 5, role = warp % 3;
+  const u64 slot = (u64)(warp / 3) * 32 + (tid & 31), nslots = (TP_ROLE / 96) * 32;
+  fe r = Fq::zero();
+  if (round_first > 1) r = ld_state(&st->r[round_first - 2]);
+  if (tid == TP_ROLE) { s_L0 = ld_state(&st->L0); s_SL = ld_state(&st->SL); s_p = ld_state(&st->p); }
+  bool have_coef = false; int cur = 0;
+  // split-eq weights of a round (EqSumCheckInstance::poly_eqs_first_half / poly_eq_right_last_half, sumcheck.rs:1007-1023)
+  auto weights = [&](int round1, const fe *&el, const fe *&er, u32 &sh) {
+    el = nullptr; sh = 0;
+    if (round1 < first_half) { const int kl = first_half - round1; el = eq_left + (((size_t)1 << kl) - 1); er = eq_right + (((size_t)1 << second_half) - 1); sh = (u32)second_half; }
+    else er = eq_right + (((size_t)1 << (l - round1)) - 1);
+  };
+  __syncthreads();
+  for (int round1 = round_first; round1 <= l; round1++) {
+    const u64 P = (u64)1 << (l - round1);
+    const bool direct = !have_coef;
+    const bool want_next = round1 + 1 <= l;
+    if (is_role) {
+      if (direct) {
+        const fe *el, *er; u32 sh; weights(round1, el, er, sh);
+        fe x[3];
+        if (round1 > 1) cubic_roles<true>(sA, sB, sC, dA, dB, dC, P, r, el, er, sh, role, slot, nslots, x);
+        else cubic_roles<false>(sA, sB, sC, dA, dB, dC, P, Fq::zero(), el, er, sh, role, slot, nslots, x);
+        role_sum<3>(x, ts.red, ts.x);
+        __threadfence_block();
+        bar_arrive_n(3, TP_THREADS);
+      } else {
+        // bind the three tables to r: role k binds table k (both halves of the bound table)
+        const fe *S = role == 0 ? sA : role == 1 ? sB : sC; fe *D = role == 0 ? dA : role == 1 ? dB : dC;
+        for (u64 j = slot; j < 2 * P; j += nslots) stg_fe(D + j, bind_pair(ldg_fe(S + j), ldg_fe(S + j + 2 * P), r));
+        bar_sync_n(1, TP_ROLE);
+      }
+      const fe *cA = round1 > 1 ? dA : sA, *cB = round1 > 1 ? dB : sB, *cC = round1 > 1 ? dC : sC;
+      if (want_next) {
+        // coefficient sums of round1 + 1 over the pairs (j, j + P/2) of this round's table, weighted by the NEXT round's eq:
+        //   role 0: t(0) from the low entries, role 1: t(1) from the high entries, role 2: t(inf) from the differences
+        const fe *el, *er; u32 sh; weights(round1 + 1, el, er, sh);
+        const u64 Hn = P / 2, mask = ((u64)1 << sh) - 1;
+        Fq::acc c0 = Fq::acc_zero(), c2 = Fq::acc_zero(), cd = Fq::acc_zero();
+        for (u64 j = slot; j < Hn; j += nslots) {
+          fe w = ldg_fe_ro(er + (el ? (j & mask) : j));
+          if (el) w = Fq::mul(ldg_fe_ro(el + (j >> sh)), w);
+          fe x0, x2, y0, y2;
+          if (role < 2) {
+            const u64 o = role ? Hn : 0;
+            x0 = ldg_fe(cA + j + o); x2 = ldg_fe(cA + j + o + P); y0 = ldg_fe(cB + j + o); y2 = ldg_fe(cB + j + o + P);
+            Fq::mul_acc(c0, w, Fq::sub(Fq::mul(x0, y0), ldg_fe(cC + j + o)));
+            Fq::mul_acc(c2, w, Fq::sub(Fq::mul(x2, y2), ldg_fe(cC + j + o + P)));
+          } else {
+            x0 = Fq::sub(ldg_fe(cA + j + Hn), ldg_fe(cA + j)); x2 = Fq::sub(ldg_fe(cA + j + P + Hn), ldg_fe(cA + j + P));
+            y0 = Fq::sub(ldg_fe(cB + j + Hn), ldg_fe(cB + j)); y2 = Fq::sub(ldg_fe(cB + j + P + Hn), ldg_fe(cB + j + P));
+            Fq::mul_acc(c0, w, Fq::mul(x0, y0));
+            Fq::mul_acc(c2, w, Fq::mul(x2, y2));
+          }
+          Fq::mul_acc(cd, w, Fq::mul(Fq::sub(x2, x0), Fq::sub(y2, y0)));
+        }
+        const fe v0 = Fq::acc_reduce(c0), v2 = Fq::acc_reduce(c2), vd = Fq::acc_reduce(cd), z = Fq::zero();
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+          fe xs[3] = {role == k ? v0 : z, role == k ? v2 : z, role == k ? vd : z};
+          role_sum<3>(xs, ts.red, ts.coef[cur ^ 1] + 3 * k);
+        }
+      }
+    } else {
+      // bound() of the previous round: p <- p l(r), and this round's L0 / SL (sumcheck.rs:1399-1405) — concurrently with the sums
+      if (round1 > round_first && ft == 32) {
+        const fe tau = ld_state(&st->taus[round1 - 2]);
+        const fe l0 = Fq::sub(Fq::one(), tau), sl = Fq::sub(tau, l0);
+        const fe pn = mul_ni(s_p, Fq::add(l0, mul_ni(sl, r)));
+        const fe tn = ld_state(&st->taus[round1 - 1]);
+        const fe l0n = Fq::sub(Fq::one(), tn), sln = Fq::sub(tn, l0n);
+        s_p = pn; s_L0 = mul_ni(pn, l0n); s_SL = mul_ni(pn, sln);
+      }
+      if (direct) bar_sync_n(3, TP_THREADS);
+      else if (ft < 3) { const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r); }
+      bar_sync_n(2, TP_FIN);
+      // round message (cubic_finalize_pre) on the finaliser group
+      const int i = round1 - 1;
+      fe canon = Fq::zero();
+      if (ft < 32) {
+        const fe t0 = ts.x[0], t1 = ts.x[1], tinf = ts.x[2];
+        const fe tb = Fq::sub(Fq::sub(t1, t0), tinf);
+        if (ft < 6) {
+          const bool use_sl = (ft == 2) | (ft == 4) | (ft == 5);
+          const fe &v = (ft == 0 || ft == 2) ? t0 : ((ft == 1 || ft == 4) ? tb : tinf);
+          ts.fin.g[ft] = mul_ni(use_sl ? s_SL : s_L0, v);
+        }
+        __syncwarp();
+        if (ft < 4) {
+          const fe co = ft == 0 ? ts.fin.g[0] : ft == 1 ? Fq::add(ts.fin.g[1], ts.fin.g[2]) : ft == 2 ? Fq::add(ts.fin.g[3], ts.fin.g[4]) : ts.fin.g[5];
+          stg_fe(&st->polys[4 * i + ft], co);
+          canon = Fq::from_mont(co);
+        }
+        const int src = ft == 0 ? 0 : ft + 1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) canon.v[k] = __shfl_sync(0xffffffffu, canon.v[k], src & 31);
+      }
+      const fe rn = sc_squeeze_g(st, ts.fin, canon, 3);
+      if (ft == 0) stg_fe(&st->r[i], rn);
+    }
+    __syncthreads();
+    r = ts.fin.ch;
+    if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t; }
+    have_coef = want_next; cur ^= 1;
+  }
+  cubic_claims(st, sA, sB, sC, r);
+}
+
 // ---- persistent multi-round kernels ------------------------------------------------------------------------
 // All multi-CTA rounds of a sum-check in ONE cooperative launch (one CTA per SM): per round every CTA computes its
 // partial sums, arrives at a grid barrier (monotonic counter), CTA 0 sums the partials, runs the finaliser (so the
@@ -901,6 +1203,8 @@ int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uin
 }
 
 static bool use_persistent() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_NO_PERSIST"); v = (e && e[0] == '1') ? 0 : 1; } return v == 1; }
+// SP2_TAIL_PIPE=0: the non-pipelined single-CTA tails (measurement switch)
+static bool use_tail_pipe() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_TAIL_PIPE"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
 static DevComm comm_none() { DevComm d; memset(&d, 0, sizeof(d)); d.n = 1; return d; }
 
 // all-gather the shards (len_local entries per table) into every rank's gather area and return the local copy
@@ -966,7 +1270,8 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     }
     const u64 P = sharded ? Pg >> dc.k : Pg;                    // local pairs
     if (!sharded && len_in <= SC_TAIL_LEN) {
-      k_cubic_tail<<<1, SC_TAIL_THREADS + 32, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
+      if (use_tail_pipe()) k_cubic_tail_pipe<<<1, TP_THREADS, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
+      else k_cubic_tail<<<1, SC_TAIL_THREADS + 32, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
       SP2_LAUNCH_CHECK();
       break;
     }
@@ -1050,7 +1355,8 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
     }
     const u64 P = sharded ? Pg >> dc.k : Pg;
     if (!sharded && len_in <= SC_TAIL_LEN) {
-      k_quad_tail<<<1, SC_TAIL_THREADS + 32, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);
+      if (use_tail_pipe()) k_quad_tail_pipe<<<1, TP_THREADS, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);
+      else k_quad_tail<<<1, SC_TAIL_THREADS + 32, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);
       SP2_LAUNCH_CHECK();
       if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
       break;

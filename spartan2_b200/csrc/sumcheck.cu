@@ -27,6 +27,12 @@
 //     and yields the same polynomial.
 // Every emitted value is the canonical representative of the same field element the reference
 // computes, hence bit-identical.
+// The field multiplication is an out-of-line call in this translation unit (field.cuh): measured on B200 the streaming rounds
+// are no slower (they are bound by the integer pipe either way) and the latency-bound rounds gain from the smaller code
+// (k_cubic_persist 398 -> 263 KB; outer sum-check of the 2^20 prove 0.661 -> 0.625 ms).
+#ifndef SP2_SC_INLINE_MUL
+#define SP2_FQ_OUTLINE 1
+#endif
 #include <stdlib.h>
 #include <string.h>
 #include <utility>
@@ -445,6 +451,12 @@ k_cubic_round_roles(ScState *st, const fe *sA, const fe *sB, const fe *sC, fe *d
   if (threadIdx.x == 0) { st->gt[4] = st->gt[2]; st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
 }
 
+#ifdef SP2_TAIL_TRACE
+__device__ long long g_tail_trace[2][40][10];
+#define TT(kern, slot_) do { g_tail_trace[kern][round1][slot_] = clock64(); } while (0)
+#else
+#define TT(kern, slot_) do { } while (0)
+#endif
 // all remaining rounds [round_first, l] in one CTA (tables of <= SC_TAIL_LEN entries going in); ping-pongs between
 // (A,B,C) and the scratch copies (A2,B2,C2)
 // The CTA has SC_TAIL_THREADS role threads plus one SCALAR WARP (warp SC_TAIL_THREADS/32) that has no pair work: at
@@ -471,6 +483,7 @@ k_cubic_tail(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int round
     fe x[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
     if (threadIdx.x == 0) st->clk[7] = st->clk[0];
     SC_STAMP(0);
+    if (threadIdx.x == 0) TT(1, 0);
     if (scalar_warp) {
       if (round1 > round_first && threadIdx.x == SC_TAIL_THREADS) cubic_bound(st, round1 - 1, l, r);
     } else if (round1 > 1) {
@@ -479,9 +492,12 @@ k_cubic_tail(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int round
       cubic_roles<false>(sA, sB, sC, dA, dB, dC, P, Fq::zero(), el, er, sh, role, slot, nslots, x);
     }
     if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t; }   // the bound tables are now the source
+    if (threadIdx.x == 0) TT(1, 1);
     __syncthreads();
     block_sum_fq<3>(x, sm.red);
+    if (threadIdx.x == 0) TT(1, 2);
     r = cubic_finalize_pre(st, round1, x, sm);
+    if (threadIdx.x == 0) TT(1, 4);
     if (round1 == l) cubic_claims(st, sA, sB, sC, r);
     SC_STAMP(6);
   }
@@ -712,11 +728,15 @@ __device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sy
 __device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct TailSmem {
-  FinSmem fin;
+  u64 m[2][34];               // squeeze inputs of the lo / hi hash, kept across rounds: only the coefficients, the round counter and the state change
+  u64 dg[8];                  // lo || hi digests
+  fe g[8];
+  fe ch;                      // the round's challenge
   fe coef[2][9];              // coefficient sums of the next round (double-buffered)
   fe x[3];                    // sums of a directly evaluated round
   fe claim;                   // quadratic prover: the running claim
-  fe red[3 * (TP_ROLE / 32)];
+  fe red[TP_ROLE / 32][3];    // per-warp partial sums
+  u32 round;                  // transcript round counter (written back at the end)
 };
 // sum of NV values per role thread over the TP_ROLE role threads -> out[0..NV) (shared); all role threads must call
 template <int NV>
@@ -740,77 +760,114 @@ __device__ __forceinline__ void role_sum(fe (&x)[NV], fe *red, fe *out) {
   }
   bar_sync_n(1, TP_ROLE);
 }
-// sc_squeeze for the finaliser group (threads [TP_ROLE, TP_THREADS), barrier 2): same message, same digests
-__device__ __forceinline__ fe sc_squeeze_g(ScState *st, FinSmem &sm, const fe &canon, int ncoef) {
-  const int tid = (int)threadIdx.x - TP_ROLE;
-  unsigned char *mb = (unsigned char *)sm.m[0];
-  const int plen = 1 + 32 * ncoef, mlen = plen + 4 + 2 + 64 + 1, total = mlen + 1, nblocks = total / 136 + 1;
-  if (tid < 34) sm.m[0][tid] = 0;
+// The finaliser group's transcript (threads [TP_ROLE, TP_THREADS), ft = tid - TP_ROLE, barrier 2).  The squeeze input
+//   b"p" || coefficients || "NoDS" || round_le16 || state || b"c" || {0,1}  + Keccak padding          (keccak.rs:33-54, 72-105)
+// is kept in shared memory for the whole kernel: tp_msg_init lays down the constant bytes, the state and the counter once,
+// and a round only stores its coefficients before the two permutations and the new state / counter after them.
+struct TpMsg { int plen, mlen, total, nblocks; };
+__device__ __forceinline__ TpMsg tp_msg(int ncoef) {
+  TpMsg g; g.plen = 1 + 32 * ncoef; g.mlen = g.plen + 4 + 2 + 64 + 1; g.total = g.mlen + 1; g.nblocks = g.total / 136 + 1; return g;
+}
+__device__ __forceinline__ void tp_put_round(TailSmem &ts, const TpMsg &g) {
+#pragma unroll
+  for (int w = 0; w < 2; w++) {
+    unsigned char *mb = (unsigned char *)ts.m[w];
+    mb[g.plen + 4] = (unsigned char)(ts.round & 0xff); mb[g.plen + 5] = (unsigned char)(ts.round >> 8);
+  }
+}
+__device__ __forceinline__ void tp_msg_init(TailSmem &ts, const ScState *st, int ncoef, int ft) {
+  const TpMsg g = tp_msg(ncoef);
+  if (ft < 68) ((u64 *)ts.m)[ft] = 0;
   bar_sync_n(2, TP_FIN);
-  if (tid < ncoef) {
+  if (ft < 2) {
+    unsigned char *mb = (unsigned char *)ts.m[ft];
+    mb[0] = 'p';
+    mb[g.plen + 0] = 'N'; mb[g.plen + 1] = 'o'; mb[g.plen + 2] = 'D'; mb[g.plen + 3] = 'S';
+    mb[g.mlen - 1] = 'c';
+    mb[g.mlen] = (unsigned char)ft;                // 0x00 -> lo half, 0x01 -> hi half
+    mb[g.total] ^= 0x01;                           // Keccak (not SHA-3) padding
+    mb[g.nblocks * 136 - 1] ^= 0x80;
+  }
+  if (ft == 32) ts.round = st->ts.round;
+  if (ft >= 64) {
+    const unsigned char b = st->ts.state[ft - 64];
+    ((unsigned char *)ts.m[0])[g.plen + 6 + ft - 64] = b; ((unsigned char *)ts.m[1])[g.plen + 6 + ft - 64] = b;
+  }
+  bar_sync_n(2, TP_FIN);
+  if (ft == 32) tp_put_round(ts, g);
+  bar_sync_n(2, TP_FIN);
+}
+// transcript hand-off back to global memory (one thread group, after the last round)
+__device__ __forceinline__ void tp_msg_store(const TailSmem &ts, ScState *st, int ncoef, int ft) {
+  const TpMsg g = tp_msg(ncoef);
+  if (ft == 32) st->ts.round = ts.round;
+  if (ft >= 64) st->ts.state[ft - 64] = ((const unsigned char *)ts.m[0])[g.plen + 6 + ft - 64];
+}
+// one absorb-and-squeeze; lanes ft < ncoef hold the canonical coefficients.  The challenge is returned to fin warp 0 (every lane)
+// and left in ts.ch for everybody else (visible after the CTA barrier that ends the round).  Fin warps 2, 3 run the two hashes: they sit
+// on the SM sub-partitions that the lowest role warps (the only ones with work in the last rounds) use least.
+__device__ __forceinline__ fe tp_squeeze(TailSmem &ts, const fe &canon, int ncoef, int ft) {
+  const TpMsg g = tp_msg(ncoef);
+  if (ft < ncoef) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const u32 w = canon.v[k];
-      unsigned char *q = mb + 1 + 32 * tid + 4 * k;
-      q[0] = (unsigned char)w; q[1] = (unsigned char)(w >> 8); q[2] = (unsigned char)(w >> 16); q[3] = (unsigned char)(w >> 24);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        unsigned char *q = (unsigned char *)ts.m[h] + 1 + 32 * ft + 4 * k;
+        q[0] = (unsigned char)w; q[1] = (unsigned char)(w >> 8); q[2] = (unsigned char)(w >> 16); q[3] = (unsigned char)(w >> 24);
+      }
     }
   }
-  if (tid == 32) {
-    const u32 round = st->ts.round;
-    mb[0] = 'p';
-    mb[plen + 0] = 'N'; mb[plen + 1] = 'o'; mb[plen + 2] = 'D'; mb[plen + 3] = 'S';
-    mb[plen + 4] = (unsigned char)(round & 0xff); mb[plen + 5] = (unsigned char)(round >> 8);
-    mb[mlen - 1] = 'c';
-    mb[total] ^= 0x01;
-    mb[nblocks * 136 - 1] ^= 0x80;
-    st->ts.round = round + 1;
-  }
-  if (tid >= 64 && tid < 128) mb[plen + 6 + (tid - 64)] = st->ts.state[tid - 64];
   bar_sync_n(2, TP_FIN);
-  if (tid < 34) sm.m[1][tid] = sm.m[0][tid];
-  bar_sync_n(2, TP_FIN);
-  if (tid == 32) ((unsigned char *)sm.m[1])[mlen] = 0x01;
-  __syncwarp();
-  if (tid < 64) {
-    const int lane = tid & 31, w = tid >> 5;
+  if (ft >= 64) {
+    const int lane = ft & 31, w = (ft >> 5) - 2;
     const KeccakLane kl = keccak_lane_init(lane);
     u64 s = 0;
-    for (int blk = 0; blk < nblocks; blk++) {
-      if (lane < 17) s ^= sm.m[w][blk * 17 + lane];
+    for (int blk = 0; blk < g.nblocks; blk++) {
+      if (lane < 17) s ^= ts.m[w][blk * 17 + lane];
       s = keccak_f_warp(s, kl, lane);
     }
-    if (lane < 4) sm.dg[w * 4 + lane] = s;
+    if (lane < 4) ts.dg[w * 4 + lane] = s;
   }
   bar_sync_n(2, TP_FIN);
-  if (tid >= 64 && tid < 128) st->ts.state[tid - 64] = ((unsigned char *)sm.dg)[tid - 64];
-  if (tid < 2) {
-    fe h;
+  fe ch = Fq::zero();
+  if (ft < 32) {                                   // from_uniform: lo * R^2 + hi * R^3 (Montgomery form of lo + 2^256 hi)
+    fe lo, hi;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { h.v[2 * i] = (u32)sm.dg[4 * tid + i]; h.v[2 * i + 1] = (u32)(sm.dg[4 * tid + i] >> 32); }
-    sm.g[6 + tid] = mul_ni(h, tid == 0 ? Fq::cst_r2() : Fq::cst_r3());
+    for (int i = 0; i < 4; i++) {
+      lo.v[2 * i] = (u32)ts.dg[i]; lo.v[2 * i + 1] = (u32)(ts.dg[i] >> 32);
+      hi.v[2 * i] = (u32)ts.dg[4 + i]; hi.v[2 * i + 1] = (u32)(ts.dg[4 + i] >> 32);
+    }
+    ch = Fq::add(Fq::mul(lo, Fq::cst_r2()), Fq::mul(hi, Fq::cst_r3()));
+    if (ft == 0) ts.ch = ch;
+  } else if (ft >= 64) {                           // the next round's header, off the challenge's path: state <- lo || hi
+    const unsigned char b = ((const unsigned char *)ts.dg)[ft - 64];
+    ((unsigned char *)ts.m[0])[g.plen + 6 + ft - 64] = b; ((unsigned char *)ts.m[1])[g.plen + 6 + ft - 64] = b;
+  } else if (ft == 32) {
+    ts.round++;
+    tp_put_round(ts, g);
   }
-  bar_sync_n(2, TP_FIN);
-  if (tid == 0) sm.ch = Fq::add(sm.g[6], sm.g[7]);
-  bar_sync_n(2, TP_FIN);
-  return sm.ch;
+  return ch;
 }
 // c0 + r (mid + r c2) with mid = c22 - c0 - c2 (Karatsuba form of the middle coefficient)
 __device__ __forceinline__ fe eval_karatsuba(const fe &c00, const fe &c22, const fe &cdd, const fe &r) {
   const fe mid = Fq::sub(Fq::sub(c22, c00), cdd);
-  return Fq::add(c00, mul_ni(r, Fq::add(mid, mul_ni(r, cdd))));
+  return Fq::add(c00, Fq::mul(r, Fq::add(mid, Fq::mul(r, cdd))));
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1)
 k_quad_tail_pipe(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int rounds, u64 nvalid) {
   __shared__ TailSmem ts;
-  const int tid = threadIdx.x, ft = tid - TP_ROLE;
+  const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
   const bool is_role = tid < TP_ROLE;
   fe *sA = A, *sB = B, *dA = A2, *dB = B2;
   const int warp = tid >> 5, role = warp % 3;
-  const u64 slot = (u64)(warp / 3) * 32 + (tid & 31), nslots = (TP_ROLE / 96) * 32;
+  const u64 slot = (u64)(warp / 3) * 32 + lane, nslots = (TP_ROLE / 96) * 32;
   fe r = Fq::zero();
   if (round_first > 1) r = ld_state(&st->r[round_first - 2]);
   if (tid == TP_ROLE) ts.claim = ld_state(&st->claim);
+  if (!is_role) tp_msg_init(ts, st, 2, ft);
   bool have_coef = false; int cur = 0;
   __syncthreads();
   for (int round1 = round_first; round1 <= rounds; round1++) {
@@ -823,7 +880,7 @@ k_quad_tail_pipe(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int
         fe x[2];
         if (round1 > 1) quad_roles<true>(sA, sB, dA, dB, P, r, role, slot, nslots, nv, x);
         else quad_roles<false>(sA, sB, dA, dB, P, Fq::zero(), role, slot, nslots, nv, x);
-        role_sum<2>(x, ts.red, ts.x);
+        role_sum<2>(x, &ts.red[0][0], ts.x);
         __threadfence_block();
         bar_arrive_n(3, TP_THREADS);                            // the finalisers may start on ts.x
       } else {
@@ -840,47 +897,59 @@ k_quad_tail_pipe(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int
         // coefficients of round1 + 1 (pairs (j, j + P/2) of the table bound to THIS round's challenge):
         //   even warps: sum a0 b0, sum a2 b2, sum (a2-a0)(b2-b0);  odd warps: the same for u = a1 - a0, u + du = a3 - a2
         const u64 Hn = P / 2;
-        Fq::acc c0 = Fq::acc_zero(), c2 = Fq::acc_zero(), cd = Fq::acc_zero();
-        const int grp = warp & 1;
-        for (u64 j = (u64)(warp >> 1) * 32 + (tid & 31); j < Hn; j += (TP_ROLE / 64) * 32) {
-          fe x0, x2, y0, y2;
-          if (grp == 0) { x0 = ldg_fe(cA + j); x2 = ldg_fe(cA + j + P); y0 = ldg_fe(cB + j); y2 = ldg_fe(cB + j + P); }
-          else {
-            x0 = Fq::sub(ldg_fe(cA + j + Hn), ldg_fe(cA + j)); x2 = Fq::sub(ldg_fe(cA + j + P + Hn), ldg_fe(cA + j + P));
-            y0 = Fq::sub(ldg_fe(cB + j + Hn), ldg_fe(cB + j)); y2 = Fq::sub(ldg_fe(cB + j + P + Hn), ldg_fe(cB + j + P));
+        const int grp = warp & 1, pair = warp >> 1;
+        fe xs[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
+        if ((u64)pair * 32 < Hn) {                              // warp-uniform: in the last rounds most warps have no pairs
+          Fq::acc c0 = Fq::acc_zero(), c2 = Fq::acc_zero(), cd = Fq::acc_zero();
+          for (u64 j = (u64)pair * 32 + lane; j < Hn; j += (TP_ROLE / 64) * 32) {
+            fe x0, x2, y0, y2;
+            if (grp == 0) { x0 = ldg_fe(cA + j); x2 = ldg_fe(cA + j + P); y0 = ldg_fe(cB + j); y2 = ldg_fe(cB + j + P); }
+            else {
+              x0 = Fq::sub(ldg_fe(cA + j + Hn), ldg_fe(cA + j)); x2 = Fq::sub(ldg_fe(cA + j + P + Hn), ldg_fe(cA + j + P));
+              y0 = Fq::sub(ldg_fe(cB + j + Hn), ldg_fe(cB + j)); y2 = Fq::sub(ldg_fe(cB + j + P + Hn), ldg_fe(cB + j + P));
+            }
+            Fq::mul_acc(c0, x0, y0); Fq::mul_acc(c2, x2, y2); Fq::mul_acc(cd, Fq::sub(x2, x0), Fq::sub(y2, y0));
           }
-          Fq::mul_acc(c0, x0, y0); Fq::mul_acc(c2, x2, y2); Fq::mul_acc(cd, Fq::sub(x2, x0), Fq::sub(y2, y0));
+          xs[0] = Fq::acc_reduce(c0); xs[1] = Fq::acc_reduce(c2); xs[2] = Fq::acc_reduce(cd);
+          warp_sum_fq_cols<3>(xs);
         }
-        const fe v0 = Fq::acc_reduce(c0), v2 = Fq::acc_reduce(c2), vd = Fq::acc_reduce(cd), z = Fq::zero();
-        fe xa[3] = {grp ? z : v0, grp ? z : v2, grp ? z : vd}, xb[3] = {grp ? v0 : z, grp ? v2 : z, grp ? vd : z};
-        role_sum<3>(xa, ts.red, ts.coef[cur ^ 1]);
-        role_sum<3>(xb, ts.red, ts.coef[cur ^ 1] + 3);
+        if (lane == 0) { ts.red[warp][0] = xs[0]; ts.red[warp][1] = xs[1]; ts.red[warp][2] = xs[2]; }
+        bar_sync_n(1, TP_ROLE);
+        if (tid < 6) {                                          // coefficient tid % 3 of group tid / 3: the six warps of that group
+          const int g = tid / 3, c = tid % 3;
+          fe acc = ts.red[g][c];
+#pragma unroll
+          for (int q = 1; q < TP_ROLE / 64; q++) acc = Fq::add(acc, ts.red[2 * q + g][c]);
+          ts.coef[cur ^ 1][3 * g + c] = acc;
+        }
       }
     } else {
-      fe e0 = Fq::zero(), ti = Fq::zero();
-      if (direct) { bar_sync_n(3, TP_THREADS); e0 = ts.x[0]; ti = ts.x[1]; }
-      else {
-        const fe *c = ts.coef[cur];
-        if (ft < 2) ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r);
-        bar_sync_n(2, TP_FIN);
+      fe e0 = Fq::zero(), ti = Fq::zero(), rn = Fq::zero();
+      if (direct) bar_sync_n(3, TP_THREADS);
+      else if (ft < 2) { const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r); }
+      if (ft < 32) {
+        __syncwarp();
         e0 = ts.x[0]; ti = ts.x[1];
       }
-      // round message (quad_finalize_pre) on the finaliser group
+      // round message (quad_finalize_pre) on fin warp 0
       const int i = round1 - 1;
-      fe canon = Fq::zero();
-      const fe b = Fq::sub(Fq::sub(ts.claim, Fq::dbl(e0)), ti);
-      if (ft < 3) stg_fe(&st->polys[4 * i + ft], ft == 0 ? e0 : ft == 1 ? b : ti);
-      if (ft < 2) canon = Fq::from_mont(ft == 0 ? e0 : ti);
-      const fe rn = sc_squeeze_g(st, ts.fin, canon, 2);
+      fe canon = Fq::zero(), b = Fq::zero();
+      if (ft < 32) {
+        b = Fq::sub(Fq::sub(ts.claim, Fq::dbl(e0)), ti);
+        if (ft < 3) stg_fe(&st->polys[4 * i + ft], ft == 0 ? e0 : ft == 1 ? b : ti);
+        if (ft < 2) canon = Fq::from_mont(ft == 0 ? e0 : ti);
+      }
+      rn = tp_squeeze(ts, canon, 2, ft);
       if (ft == 0) stg_fe(&st->r[i], rn);
-      if (ft == 32) ts.claim = Fq::add(e0, mul_ni(rn, Fq::add(b, mul_ni(rn, ti))));       // claim <- poly(r)
+      if (ft == 1) ts.claim = Fq::add(e0, Fq::mul(rn, Fq::add(b, Fq::mul(rn, ti))));       // claim <- poly(r)
     }
     __syncthreads();
-    r = ts.fin.ch;
+    r = ts.ch;
     if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; }
     have_coef = want_next; cur ^= 1;
   }
   if (tid == TP_ROLE) stg_fe(&st->claim, ts.claim);
+  if (!is_role) tp_msg_store(ts, st, 2, ft);
   quad_claims(st, sA, sB, r);
 }
 
@@ -889,14 +958,15 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
   __shared__ TailSmem ts;
   __shared__ fe s_L0, s_SL, s_p;
   const int first_half = l / 2, second_half = l - first_half;
-  const int tid = threadIdx.x, ft = tid - TP_ROLE;
+  const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
   const bool is_role = tid < TP_ROLE;
   fe *sA = A, *sB = B, *sC = C, *dA = A2, *dB = B2, *dC = C2;
-  const int warp = tid >> 5, role = warp % 3;
-  const u64 slot = (u64)(warp / 3) * 32 + (tid & 31), nslots = (TP_ROLE / 96) * 32;
+  const int warp = tid >> 5, role = warp % 3, trio = warp / 3;
+  const u64 slot = (u64)trio * 32 + lane, nslots = (TP_ROLE / 96) * 32;
   fe r = Fq::zero();
   if (round_first > 1) r = ld_state(&st->r[round_first - 2]);
   if (tid == TP_ROLE) { s_L0 = ld_state(&st->L0); s_SL = ld_state(&st->SL); s_p = ld_state(&st->p); }
+  if (!is_role) tp_msg_init(ts, st, 3, ft);
   bool have_coef = false; int cur = 0;
   // split-eq weights of a round (EqSumCheckInstance::poly_eqs_first_half / poly_eq_right_last_half, sumcheck.rs:1007-1023)
   auto weights = [&](int round1, const fe *&el, const fe *&er, u32 &sh) {
@@ -909,13 +979,15 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
     const u64 P = (u64)1 << (l - round1);
     const bool direct = !have_coef;
     const bool want_next = round1 + 1 <= l;
+    if (tid == 0) TT(0, 0);
+    if (tid == TP_ROLE) TT(0, 5);
     if (is_role) {
       if (direct) {
         const fe *el, *er; u32 sh; weights(round1, el, er, sh);
         fe x[3];
         if (round1 > 1) cubic_roles<true>(sA, sB, sC, dA, dB, dC, P, r, el, er, sh, role, slot, nslots, x);
         else cubic_roles<false>(sA, sB, sC, dA, dB, dC, P, Fq::zero(), el, er, sh, role, slot, nslots, x);
-        role_sum<3>(x, ts.red, ts.x);
+        role_sum<3>(x, &ts.red[0][0], ts.x);
         __threadfence_block();
         bar_arrive_n(3, TP_THREADS);
       } else {
@@ -924,51 +996,64 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
         for (u64 j = slot; j < 2 * P; j += nslots) stg_fe(D + j, bind_pair(ldg_fe(S + j), ldg_fe(S + j + 2 * P), r));
         bar_sync_n(1, TP_ROLE);
       }
+      if (tid == 0) TT(0, 1);
       const fe *cA = round1 > 1 ? dA : sA, *cB = round1 > 1 ? dB : sB, *cC = round1 > 1 ? dC : sC;
       if (want_next) {
         // coefficient sums of round1 + 1 over the pairs (j, j + P/2) of this round's table, weighted by the NEXT round's eq:
         //   role 0: t(0) from the low entries, role 1: t(1) from the high entries, role 2: t(inf) from the differences
-        const fe *el, *er; u32 sh; weights(round1 + 1, el, er, sh);
-        const u64 Hn = P / 2, mask = ((u64)1 << sh) - 1;
-        Fq::acc c0 = Fq::acc_zero(), c2 = Fq::acc_zero(), cd = Fq::acc_zero();
-        for (u64 j = slot; j < Hn; j += nslots) {
-          fe w = ldg_fe_ro(er + (el ? (j & mask) : j));
-          if (el) w = Fq::mul(ldg_fe_ro(el + (j >> sh)), w);
-          fe x0, x2, y0, y2;
-          if (role < 2) {
-            const u64 o = role ? Hn : 0;
-            x0 = ldg_fe(cA + j + o); x2 = ldg_fe(cA + j + o + P); y0 = ldg_fe(cB + j + o); y2 = ldg_fe(cB + j + o + P);
-            Fq::mul_acc(c0, w, Fq::sub(Fq::mul(x0, y0), ldg_fe(cC + j + o)));
-            Fq::mul_acc(c2, w, Fq::sub(Fq::mul(x2, y2), ldg_fe(cC + j + o + P)));
-          } else {
-            x0 = Fq::sub(ldg_fe(cA + j + Hn), ldg_fe(cA + j)); x2 = Fq::sub(ldg_fe(cA + j + P + Hn), ldg_fe(cA + j + P));
-            y0 = Fq::sub(ldg_fe(cB + j + Hn), ldg_fe(cB + j)); y2 = Fq::sub(ldg_fe(cB + j + P + Hn), ldg_fe(cB + j + P));
-            Fq::mul_acc(c0, w, Fq::mul(x0, y0));
-            Fq::mul_acc(c2, w, Fq::mul(x2, y2));
+        const u64 Hn = P / 2;
+        fe xs[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
+        if ((u64)trio * 32 < Hn) {                              // warp-uniform: in the last rounds most warps have no pairs
+          const fe *el, *er; u32 sh; weights(round1 + 1, el, er, sh);
+          const u64 mask = ((u64)1 << sh) - 1;
+          Fq::acc c0 = Fq::acc_zero(), c2 = Fq::acc_zero(), cd = Fq::acc_zero();
+          for (u64 j = slot; j < Hn; j += nslots) {
+            fe w = ldg_fe_ro(er + (el ? (j & mask) : j));
+            if (el) w = Fq::mul(ldg_fe_ro(el + (j >> sh)), w);
+            fe x0, x2, y0, y2;
+            if (role < 2) {
+              const u64 o = role ? Hn : 0;
+              x0 = ldg_fe(cA + j + o); x2 = ldg_fe(cA + j + o + P); y0 = ldg_fe(cB + j + o); y2 = ldg_fe(cB + j + o + P);
+              Fq::mul_acc(c0, w, Fq::sub(Fq::mul(x0, y0), ldg_fe(cC + j + o)));
+              Fq::mul_acc(c2, w, Fq::sub(Fq::mul(x2, y2), ldg_fe(cC + j + o + P)));
+            } else {
+              x0 = Fq::sub(ldg_fe(cA + j + Hn), ldg_fe(cA + j)); x2 = Fq::sub(ldg_fe(cA + j + P + Hn), ldg_fe(cA + j + P));
+              y0 = Fq::sub(ldg_fe(cB + j + Hn), ldg_fe(cB + j)); y2 = Fq::sub(ldg_fe(cB + j + P + Hn), ldg_fe(cB + j + P));
+              Fq::mul_acc(c0, w, Fq::mul(x0, y0));
+              Fq::mul_acc(c2, w, Fq::mul(x2, y2));
+            }
+            Fq::mul_acc(cd, w, Fq::mul(Fq::sub(x2, x0), Fq::sub(y2, y0)));
           }
-          Fq::mul_acc(cd, w, Fq::mul(Fq::sub(x2, x0), Fq::sub(y2, y0)));
+          xs[0] = Fq::acc_reduce(c0); xs[1] = Fq::acc_reduce(c2); xs[2] = Fq::acc_reduce(cd);
+          if (tid == 0) TT(0, 2);
+          warp_sum_fq_cols<3>(xs);
         }
-        const fe v0 = Fq::acc_reduce(c0), v2 = Fq::acc_reduce(c2), vd = Fq::acc_reduce(cd), z = Fq::zero();
-#pragma unroll 1
-        for (int k = 0; k < 3; k++) {
-          fe xs[3] = {role == k ? v0 : z, role == k ? v2 : z, role == k ? vd : z};
-          role_sum<3>(xs, ts.red, ts.coef[cur ^ 1] + 3 * k);
+        if (lane == 0) { ts.red[warp][0] = xs[0]; ts.red[warp][1] = xs[1]; ts.red[warp][2] = xs[2]; }
+        bar_sync_n(1, TP_ROLE);
+        if (tid < 9) {                                          // coefficient tid % 3 of role tid / 3: the four warps of that role
+          const int k = tid / 3, c = tid % 3;
+          fe acc = ts.red[k][c];
+#pragma unroll
+          for (int q = 1; q < TP_ROLE / 96; q++) acc = Fq::add(acc, ts.red[3 * q + k][c]);
+          ts.coef[cur ^ 1][3 * k + c] = acc;
         }
       }
+      if (tid == 0) TT(0, 3);
     } else {
-      // bound() of the previous round: p <- p l(r), and this round's L0 / SL (sumcheck.rs:1399-1405) — concurrently with the sums
+      // bound() of the previous round: p <- p l(r), and this round's L0 / SL (sumcheck.rs:1399-1405) — on fin warp 1, beside the sums
       if (round1 > round_first && ft == 32) {
         const fe tau = ld_state(&st->taus[round1 - 2]);
         const fe l0 = Fq::sub(Fq::one(), tau), sl = Fq::sub(tau, l0);
-        const fe pn = mul_ni(s_p, Fq::add(l0, mul_ni(sl, r)));
+        const fe pn = Fq::mul(s_p, Fq::add(l0, Fq::mul(sl, r)));
         const fe tn = ld_state(&st->taus[round1 - 1]);
         const fe l0n = Fq::sub(Fq::one(), tn), sln = Fq::sub(tn, l0n);
-        s_p = pn; s_L0 = mul_ni(pn, l0n); s_SL = mul_ni(pn, sln);
+        s_p = pn; s_L0 = Fq::mul(pn, l0n); s_SL = Fq::mul(pn, sln);
       }
       if (direct) bar_sync_n(3, TP_THREADS);
       else if (ft < 3) { const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r); }
       bar_sync_n(2, TP_FIN);
-      // round message (cubic_finalize_pre) on the finaliser group
+      if (tid == TP_ROLE) TT(0, 6);
+      // round message (cubic_finalize_pre) on fin warp 0
       const int i = round1 - 1;
       fe canon = Fq::zero();
       if (ft < 32) {
@@ -977,11 +1062,11 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
         if (ft < 6) {
           const bool use_sl = (ft == 2) | (ft == 4) | (ft == 5);
           const fe &v = (ft == 0 || ft == 2) ? t0 : ((ft == 1 || ft == 4) ? tb : tinf);
-          ts.fin.g[ft] = mul_ni(use_sl ? s_SL : s_L0, v);
+          ts.g[ft] = Fq::mul(use_sl ? s_SL : s_L0, v);
         }
         __syncwarp();
         if (ft < 4) {
-          const fe co = ft == 0 ? ts.fin.g[0] : ft == 1 ? Fq::add(ts.fin.g[1], ts.fin.g[2]) : ft == 2 ? Fq::add(ts.fin.g[3], ts.fin.g[4]) : ts.fin.g[5];
+          const fe co = ft == 0 ? ts.g[0] : ft == 1 ? Fq::add(ts.g[1], ts.g[2]) : ft == 2 ? Fq::add(ts.g[3], ts.g[4]) : ts.g[5];
           stg_fe(&st->polys[4 * i + ft], co);
           canon = Fq::from_mont(co);
         }
@@ -989,14 +1074,18 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
 #pragma unroll
         for (int k = 0; k < 8; k++) canon.v[k] = __shfl_sync(0xffffffffu, canon.v[k], src & 31);
       }
-      const fe rn = sc_squeeze_g(st, ts.fin, canon, 3);
+      if (tid == TP_ROLE) TT(0, 7);
+      const fe rn = tp_squeeze(ts, canon, 3, ft);
       if (ft == 0) stg_fe(&st->r[i], rn);
+      if (tid == TP_ROLE) TT(0, 8);
     }
     __syncthreads();
-    r = ts.fin.ch;
+    if (tid == 0) TT(0, 4);
+    r = ts.ch;
     if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t; }
     have_coef = want_next; cur ^= 1;
   }
+  if (!is_role) tp_msg_store(ts, st, 3, ft);
   cubic_claims(st, sA, sB, sC, r);
 }
 
@@ -1393,6 +1482,9 @@ extern "C" {
 /* tables of at most this many entries are finished by the single-CTA tail kernels; larger ones go through the persistent
  * multi-CTA kernels (bench.py derives from it which rounds k_cubic_persist covers) */
 uint64_t sp2_sc_tail_len(void) { return SC_TAIL_LEN; }
+#ifdef SP2_TAIL_TRACE
+int32_t sp2_debug_tail_trace(long long *out) { return (int32_t)cudaMemcpyFromSymbol(out, g_tail_trace, sizeof(long long) * 2 * 40 * 10); }
+#endif
 
 int32_t sp2_debug_sc_round_profile(sp2_ctx *ctx, uint64_t *out, uint32_t rounds) {
   cudaSetDevice(ctx->device);

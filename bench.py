@@ -93,10 +93,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def persist_end(l, tail_len, mid_len):
+    """first round NOT run by the persistent multi-CTA kernel (sumcheck.cu: sumcheck_cubic_enqueue / mid_plan): the single-CTA tail
+    takes tables of <= tail_len entries; with the pipelined multi-CTA kernels enabled, rounds >= 2 whose input tables have <= mid_len
+    entries go to k_cubic_mid_pipe (when there are at least two of them before the tail)"""
+    r_end = 1
+    while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > tail_len:
+        r_end += 1
+    if mid_len:
+        rm = 2
+        while rm <= l and (4 << (l - rm)) > mid_len:
+            rm += 1
+        if rm + 1 < r_end:
+            return rm
+    return r_end
+
+
 class Workload:
     """sha256_spartan: Sha256Circuit(vec![0u8; msg_len]) -> padded R1CS, witness, prover randomness (seeded)."""
 
-    def __init__(self, msg_len, seed=0xDEADBEEF, tail_len=1024):
+    def __init__(self, msg_len, seed=0xDEADBEEF, tail_len=1024, mid_len=0):
         from spartan2_b200.frontend import Sha256Circuit
         self.msg_len = msg_len
         self.circ = c = Sha256Circuit(b"\x00" * msg_len, width=WIDTH)
@@ -122,9 +138,7 @@ class Workload:
         # sumcheck.cu: sumcheck_cubic_enqueue): round 1 reads 2.5 tables, round i >= 2 reads 3 * T/2^(i-2) entries and
         # writes half as many (bind fused into the evaluation)  — SURVEY.md §8(d) accounting, 32 B per entry
         l = N.bit_length() - 1
-        r_end = 1
-        while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > tail_len:
-            r_end += 1
+        r_end = persist_end(l, tail_len, mid_len)
         self.persist_rounds = r_end - 1
         self.bytes_persist = (80 * N if r_end > 1 else 0) + sum(144 * (N >> (i - 2)) for i in range(2, r_end))
 
@@ -155,7 +169,7 @@ def run_cuda(args):
     # N > 1: ONE proof, its 2^l hypercube split across the GPUs (strong scaling);
     # --replicas: every GPU proves its own instance (independent proofs: weak scaling, no data-path exchange)
     sharded = world > 1 and not args.replicas
-    wl = Workload(default_msg_len(args, world), seed=0xDEADBEEF + (0 if sharded else rank), tail_len=int(ctx.L.sp2_sc_tail_len()))
+    wl = Workload(default_msg_len(args, world), seed=0xDEADBEEF + (0 if sharded else rank), tail_len=int(ctx.L.sp2_sc_tail_len()), mid_len=int(ctx.L.sp2_sc_mid_len()))
     hbm_peak, peak_kind = peaks()
     pts = ctx.test_points(WIDTH + 3, seed=7)
     K = sp.CommitmentKey(ctx, pts[:WIDTH], pts[WIDTH:WIDTH + 1], pts[WIDTH + 1:WIDTH + 2], pts[WIDTH + 2:WIDTH + 3])
@@ -411,10 +425,8 @@ def tables_bench(ctx, sp, hbm_peak, num_vars=24):
             tot.append(ms); per.append(float(k.value))
     for t in tabs + small:
         t.free()
-    l = num_vars; r_end = 1
-    tail_len = int(ctx.L.sp2_sc_tail_len())
-    while r_end <= l and ((4 if r_end > 1 else 2) << (l - r_end)) > tail_len:
-        r_end += 1
+    l = num_vars
+    r_end = persist_end(l, int(ctx.L.sp2_sc_tail_len()), int(ctx.L.sp2_sc_mid_len()))
     b_persist = 80 * n + sum(144 * (n >> (i - 2)) for i in range(2, r_end))
     k_ms, t_ms = float(np.mean(per)), float(np.mean(tot))
     return {"workload": "prove_cubic_with_three_inputs, 3 uniform random tables of 2^%d entries, device-resident (1.5 GiB > L2)" % num_vars,

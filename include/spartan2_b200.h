@@ -422,6 +422,9 @@ int32_t sp2_neutronnova_last_round0_ms(sp2_nn_prep *prep, float *ms);
 int32_t sp2_last_cubic_persist_ms(sp2_ctx *ctx, float *ms);
 /* table length at or below which the single-CTA tail kernels take over from the persistent multi-CTA kernels          */
 uint64_t sp2_sc_tail_len(void);
+/* table length (going into a round >= 2) at or below which the persistent kernels hand over to the pipelined multi-CTA
+ * kernels (k_*_mid_pipe); 0 when they are disabled (SP2_MID_PIPE=0 / SP2_TAIL_PIPE=0)                                   */
+uint64_t sp2_sc_mid_len(void);
 
 /* ---- raw device memory helpers (for device-resident callers) ------------------------------- */
 int32_t sp2_dev_alloc(sp2_ctx *ctx, uint64_t bytes, void **out);

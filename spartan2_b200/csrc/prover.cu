@@ -115,6 +115,9 @@ __global__ void __launch_bounds__(64) k_outer_to_inner(ScState *outer, ScState *
     for (int i = 0; i < 64; i++) inner->ts.state[i] = ts->state[i];
     stg_fe(&inner->claim, joint);
     inner->ticket = 0; inner->l = (u32)rounds_inner; inner->flags = outer->flags; inner->arrived = 0; inner->released = 0; inner->err = 0;
+    for (int i = 0; i < SC_MAX_ROUNDS + 8; i++) inner->mid_arrive[i] = 0;
+    inner->mid_released = 0;
+    for (int i = 0; i < 12 * 16; i++) inner->mid_acc0[i] = 0;
   }
 }
 

@@ -453,7 +453,7 @@ k_cubic_round_roles(ScState *st, const fe *sA, const fe *sB, const fe *sC, fe *d
 
 #ifdef SP2_TAIL_TRACE
 __device__ long long g_tail_trace[2][40][10];
-#define TT(kern, slot_) do { g_tail_trace[kern][round1][slot_] = clock64(); } while (0)
+#define TT(kern, slot_) do { g_tail_trace[kern][round1][slot_] = (long long)gtimer(); } while (0)
 #else
 #define TT(kern, slot_) do { } while (0)
 #endif
@@ -736,6 +736,7 @@ struct TailSmem {
   fe x[3];                    // sums of a directly evaluated round
   fe claim;                   // quadratic prover: the running claim
   fe red[TP_ROLE / 32][3];    // per-warp partial sums
+  fe gat[12];                 // multi-CTA rounds: the first round's gathered sums
   u32 round;                  // transcript round counter (written back at the end)
 };
 // sum of NV values per role thread over the TP_ROLE role threads -> out[0..NV) (shared); all role threads must call
@@ -806,7 +807,9 @@ __device__ __forceinline__ void tp_msg_store(const TailSmem &ts, ScState *st, in
 // one absorb-and-squeeze; lanes ft < ncoef hold the canonical coefficients.  The challenge is returned to fin warp 0 (every lane)
 // and left in ts.ch for everybody else (visible after the CTA barrier that ends the round).  Fin warps 2, 3 run the two hashes: they sit
 // on the SM sub-partitions that the lowest role warps (the only ones with work in the last rounds) use least.
-__device__ __forceinline__ fe tp_squeeze(TailSmem &ts, const fe &canon, int ncoef, int ft) {
+struct TpNoSide { __device__ __forceinline__ void operator()() const {} };
+template <class Side = TpNoSide>
+__device__ __forceinline__ fe tp_squeeze(TailSmem &ts, const fe &canon, int ncoef, int ft, Side side = Side()) {
   const TpMsg g = tp_msg(ncoef);
   if (ft < ncoef) {
 #pragma unroll
@@ -829,6 +832,8 @@ __device__ __forceinline__ fe tp_squeeze(TailSmem &ts, const fe &canon, int ncoe
       s = keccak_f_warp(s, kl, lane);
     }
     if (lane < 4) ts.dg[w * 4 + lane] = s;
+  } else if (ft >= 32) {
+    side();                                        // fin warp 1: work that may run beside the two permutations
   }
   bar_sync_n(2, TP_FIN);
   fe ch = Fq::zero();
@@ -1254,6 +1259,412 @@ __global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_quad_persist(Pe
   }
 }
 
+// ---- pipelined MULTI-CTA rounds ("mid" rounds: tables of 2^11 .. 2^17 entries) ------------------------------------------
+// Between the streaming rounds (bound by the integer pipe) and the single-CTA tail sit the rounds whose tables are too long for
+// one SM and too short to amortise a grid barrier: in k_*_persist such a round costs ~21 us — ~5.5 us of pair work, ~5.5 us until
+// every CTA's partial sums are in, ~9 us of finaliser — of which only the finaliser has to be serial.  The mid kernels run the
+// pipelined tail (above) on G = 2^k CTAs at once:
+//   * the hypercube is split CYCLICALLY across the CTAs (CTA c owns the indices = c mod G, stored densely in ITS shared memory):
+//     both entries of every bind pair share their low bits, so binding and pairing never leave the CTA — the multi-GPU split
+//     (sumcheck.cuh) applied to SMs.  Only <= 12 partial sums per CTA and round cross the chip;
+//   * the role warps of every CTA take, as soon as r_(i-1) is published, the bind to r_(i-1) and the COEFFICIENT sums of round
+//     i+1 (quadratics in r_i, see the tails), publish them and arrive on a per-round counter;
+//   * the finaliser group (CTA 0) evaluates round i from the coefficients gathered one round earlier, absorbs, squeezes and
+//     publishes r_i; its second warp gathers the next coefficients while the Keccak warps hash.
+// A mid round costs what the transcript costs (~11 us).  Every wait is bounded (spin_until).  Same sums, same field elements:
+// bit-identical (tests/test_gpu_sumcheck.py).
+constexpr int MP_LOG_LEN_IN = 17;                  // the first mid round reads tables of <= 2^17 entries
+constexpr int MP_LOG_CTAS = 7;                     // <= 128 CTAs
+constexpr int MP_LOG_LOCAL = 8;                    // >= 256 entries per CTA going into the first bind (else fewer CTAs)
+struct MidCubic { ScState *st; const fe *A, *B, *C; fe *oA, *oB, *oC; int l, round_first, round_last, k; const fe *eq_left, *eq_right; };
+struct MidQuad { ScState *st; const fe *A, *B; fe *oA, *oB; int rounds, round_first, round_last, k; };
+
+__device__ __forceinline__ void st_volatile_u32(u32 *p, u32 v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// role warps: wait until the challenge of `round` is published
+__device__ __forceinline__ void mid_wait_released(ScState *st, int round) {
+  if (threadIdx.x == 0) { const u32 want = (u32)round; spin_until([=] { return ld_volatile_u32(&st->mid_released) >= want; }, &st->err); __threadfence(); }
+  bar_sync_n(1, TP_ROLE);
+}
+// The CTAs publish their partial sums by ATOMIC adds of 16-bit limb halves into u32 accumulators (G * 4 * 2^16 < 2^32): the chip-wide
+// reduction happens in the L2 atomic units and the finaliser reads 16 words per value instead of G field elements.  The accumulators of the
+// first round live in the state's head (zeroed with it), those of the later rounds behind the partials (zeroed by the finaliser CTA before
+// it releases the first challenge).
+constexpr int MP_ACC_WORDS = 9 * 16;
+__device__ __forceinline__ u32 *mid_acc(ScState *st, int round) { return (u32 *)st->partial + (size_t)round * MP_ACC_WORDS; }
+// role warps: per-warp partial sums (`xs`, identical in every lane) -> values [base + 3 g + c] (or [base + g] from c = 0 alone when only_first);
+// the warps of group g are g, g + NG, g + 2 NG, ...  (cubic: NG = 3 roles; quadratic: NG = 2 halves)
+template <int NG>
+__device__ __forceinline__ void mid_publish_acc(TailSmem &ts, const fe (&xs)[3], u32 *acc, int base, bool only_first) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (lane == 0) { ts.red[warp][0] = xs[0]; ts.red[warp][1] = xs[1]; ts.red[warp][2] = xs[2]; }
+  bar_sync_n(1, TP_ROLE);
+  if (tid < 3 * NG * 16) {
+    const int v = tid >> 4, col = tid & 15, g = v / 3, c = v % 3;
+    if (!only_first || c == 0) {
+      u32 sum = 0;
+#pragma unroll
+      for (int q = 0; q < TP_ROLE / 32 / NG; q++) { const u32 w = ts.red[NG * q + g][c].v[col >> 1]; sum += (col & 1) ? (w >> 16) : (w & 0xffffu); }
+      if (sum) atomicAdd(acc + (base + (only_first ? g : v)) * 16 + col, sum);
+    }
+    __threadfence();
+  }
+  bar_sync_n(1, TP_ROLE);
+}
+// fin warp 1: wait for the G arrivals of `round`, then lane v < nval rebuilds value v from its 16 column sums
+__device__ __forceinline__ void mid_gather_acc(ScState *st, int round, int G, const u32 *accs, int nval, fe *out) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) { const u32 want = (u32)G; const u32 *ctr = &st->mid_arrive[round]; spin_until([=] { return ld_volatile_u32(ctr) >= want; }, &st->err); __threadfence(); }
+  __syncwarp();
+  if (lane < nval) {
+    const u32 *acc = accs + lane * 16;
+    u32 w[16];
+#pragma unroll
+    for (int q = 0; q < 4; q++) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4 * q]), "=r"(w[4 * q + 1]), "=r"(w[4 * q + 2]), "=r"(w[4 * q + 3]) : "l"(acc + 4 * q));
+    fe x; u64 carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { carry += (u64)w[2 * i] + ((u64)w[2 * i + 1] << 16); x.v[i] = (u32)carry; carry >>= 32; }
+    u32 top = Fq::fold_top(x, (u32)carry);
+    top = Fq::fold_top(x, top);
+    cond_sub_p<FqParams>(x, top);
+    cond_sub_p<FqParams>(x, 0);
+    out[lane] = x;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
+  extern __shared__ __align__(32) unsigned char mp_dyn[];
+  __shared__ TailSmem ts;
+  __shared__ fe s_L0, s_SL, s_p;
+  __shared__ fe s_l0[SC_MAX_ROUNDS], s_sl[SC_MAX_ROUNDS];       // l_i(X) = l0_i + sl_i X of every round (finaliser CTA)
+  ScState *st = a.st;
+  // CTAs [0, G): role warps only; CTA G: the finaliser group only (it shares its SM with nobody: no issue-slot contention)
+  const int l = a.l, first = a.round_first, last = a.round_last, k = a.k, G = (int)gridDim.x - 1, cta = (int)blockIdx.x - 1;
+  const int first_half = l / 2, second_half = l - first_half;
+  const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
+  const bool is_role = tid < TP_ROLE;
+  const int warp = tid >> 5, role = warp % 3, trio = warp / 3;
+  const u64 slot = (u64)trio * 32 + lane, nslots = (TP_ROLE / 96) * 32;
+  // split-eq weights of a round (EqSumCheckInstance::poly_eqs_first_half / poly_eq_right_last_half, sumcheck.rs:1007-1023)
+  auto weights = [&](int round1, const fe *&el, const fe *&er, u32 &sh) {
+    el = nullptr; sh = 0;
+    if (round1 < first_half) { const int kl = first_half - round1; el = a.eq_left + (((size_t)1 << kl) - 1); er = a.eq_right + (((size_t)1 << second_half) - 1); sh = (u32)second_half; }
+    else er = a.eq_right + (((size_t)1 << (l - round1)) - 1);
+  };
+  if (is_role) {
+    if (cta < 0) return;
+    const u64 n0 = ((u64)2 << (l - first)) >> k;               // local length of the first bound table
+    fe *X = (fe *)mp_dyn, *Y = X + 3 * n0;
+    fe *cur = X, *nxt = Y; u64 cs = n0, ns = n0 / 2;            // table t of a buffer starts at t * stride
+    for (int round1 = first; round1 <= last; round1++) {
+      const u64 P = (u64)1 << (l - round1), Pl = P >> k, Hl = Pl >> 1;
+      const bool want_next = round1 < last;
+      if (tid == 0 && cta == 0) TT(1, 0);
+      // what does not depend on the challenge goes before the wait: the eq weight of the (single) pair of the coefficient pass
+      const bool single = want_next && Hl <= nslots;
+      fe wpre = Fq::zero();
+      const u64 pslot = Hl <= 32 ? (u64)lane : slot;               // (see the coefficient pass)
+      if (single && pslot < Hl) {
+        const fe *el, *er; u32 sh; weights(round1 + 1, el, er, sh);
+        const u64 g = (pslot << k) | (u64)cta, mask = ((u64)1 << sh) - 1;
+        wpre = ldg_fe_ro(er + (el ? (g & mask) : g));
+        if (el) wpre = Fq::mul(ldg_fe_ro(el + (g >> sh)), wpre);
+      }
+      if (round1 > first) mid_wait_released(st, round1 - 1);
+      const fe r = ld_state(&st->r[round1 - 2]);
+      if (tid == 0 && cta == 0) TT(1, 1);
+      // bind to r: role t binds table t
+      if (round1 == first) {
+        const fe *S = role == 0 ? a.A : role == 1 ? a.B : a.C; fe *D = cur + role * cs;
+        for (u64 j0 = slot; j0 < 2 * Pl; j0 += 4 * nslots) {    // strided reads of the natural-order table: four pairs in flight per thread
+          fe lo[4], hi[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const u64 j = j0 + q * nslots, g = (j << k) | (u64)cta;
+            if (j < 2 * Pl) { lo[q] = ldg_fe(S + g); hi[q] = ldg_fe(S + g + 2 * P); }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const u64 j = j0 + q * nslots; if (j < 2 * Pl) D[j] = bind_pair(lo[q], hi[q], r); }
+        }
+      } else {
+        const fe *S = cur + role * cs; fe *D = nxt + role * ns;
+        for (u64 j = slot; j < 2 * Pl; j += nslots) D[j] = bind_pair(S[j], S[j + 2 * Pl], r);
+        { fe *t = cur; cur = nxt; nxt = t; const u64 u = cs; cs = ns; ns = u; }
+      }
+      bar_sync_n(1, TP_ROLE);
+      if (tid == 0 && cta == 0) TT(1, 2);
+      const fe *cA = cur, *cB = cur + cs, *cC = cur + 2 * cs;
+      if (round1 == first) {
+        // the round's own sums, directly: role 0 -> t(0) over the low entries, role 1 -> t(1) over the high entries, role 2 -> t(inf)
+        fe xs[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
+        if ((u64)trio * 32 < Pl) {
+          const fe *el, *er; u32 sh; weights(round1, el, er, sh);
+          const u64 mask = ((u64)1 << sh) - 1;
+          Fq::acc d = Fq::acc_zero();
+          for (u64 j = slot; j < Pl; j += nslots) {
+            const u64 g = (j << k) | (u64)cta;
+            fe w = ldg_fe_ro(er + (el ? (g & mask) : g));
+            if (el) w = Fq::mul(ldg_fe_ro(el + (g >> sh)), w);
+            if (role < 2) { const u64 o = role ? Pl : 0; Fq::mul_acc(d, w, Fq::sub(Fq::mul(cA[j + o], cB[j + o]), cC[j + o])); }
+            else Fq::mul_acc(d, w, Fq::mul(Fq::sub(cA[j + Pl], cA[j]), Fq::sub(cB[j + Pl], cB[j])));
+          }
+          xs[0] = Fq::acc_reduce(d);
+          warp_sum_fq_cols<3>(xs);
+        }
+        mid_publish_acc<3>(ts, xs, st->mid_acc0, 0, true);
+        if (tid == 0 && cta == 0) TT(1, 3);
+      }
+      if (want_next) {
+        // coefficient sums of round1 + 1 over the pairs (j, j + Pl/2) of this round's local table, weighted by the NEXT round's eq
+        // (with <= 32 local pairs the three coefficient sums of a pair go to three different trios: one product chain per thread)
+        fe xs[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
+        const bool split = Hl <= 32;
+        const int cmask = split ? (trio < 3 ? 1 << trio : 0) : 7;
+        const u64 jslot = split ? (u64)lane : slot;
+        if (cmask && (split || (u64)trio * 32 < Hl)) {
+          const fe *el, *er; u32 sh; weights(round1 + 1, el, er, sh);
+          const u64 mask = ((u64)1 << sh) - 1;
+          Fq::acc c0 = Fq::acc_zero(), c2 = Fq::acc_zero(), cd = Fq::acc_zero();
+          for (u64 j = jslot; j < Hl; j += nslots) {
+            fe w = wpre;
+            if (!single) {
+              const u64 g = (j << k) | (u64)cta;
+              w = ldg_fe_ro(er + (el ? (g & mask) : g));
+              if (el) w = Fq::mul(ldg_fe_ro(el + (g >> sh)), w);
+            }
+            fe x0, x2, y0, y2;
+            if (role < 2) {
+              const u64 o = role ? Hl : 0;
+              x0 = cA[j + o]; x2 = cA[j + o + Pl]; y0 = cB[j + o]; y2 = cB[j + o + Pl];
+              if (cmask & 1) Fq::mul_acc(c0, w, Fq::sub(Fq::mul(x0, y0), cC[j + o]));
+              if (cmask & 2) Fq::mul_acc(c2, w, Fq::sub(Fq::mul(x2, y2), cC[j + o + Pl]));
+            } else {
+              x0 = Fq::sub(cA[j + Hl], cA[j]); x2 = Fq::sub(cA[j + Pl + Hl], cA[j + Pl]);
+              y0 = Fq::sub(cB[j + Hl], cB[j]); y2 = Fq::sub(cB[j + Pl + Hl], cB[j + Pl]);
+              if (cmask & 1) Fq::mul_acc(c0, w, Fq::mul(x0, y0));
+              if (cmask & 2) Fq::mul_acc(c2, w, Fq::mul(x2, y2));
+            }
+            if (cmask & 4) Fq::mul_acc(cd, w, Fq::mul(Fq::sub(x2, x0), Fq::sub(y2, y0)));
+          }
+          if (cmask & 1) xs[0] = Fq::acc_reduce(c0);
+          if (cmask & 2) xs[1] = Fq::acc_reduce(c2);
+          if (cmask & 4) xs[2] = Fq::acc_reduce(cd);
+          warp_sum_fq_cols<3>(xs);
+        }
+        if (tid == 0 && cta == 0) TT(1, 4);
+        mid_publish_acc<3>(ts, xs, round1 == first ? st->mid_acc0 : mid_acc(st, round1), round1 == first ? 3 : 0, false);
+      } else {
+        // last mid round: the bound table goes back to global memory in natural order for the tail kernel
+        const fe *S = cur + role * cs; fe *D = role == 0 ? a.oA : role == 1 ? a.oB : a.oC;
+        for (u64 j = slot; j < 2 * Pl; j += nslots) stg_fe(D + ((j << k) | (u64)cta), S[j]);
+      }
+      if ((round1 == first || want_next) && tid == 0) atomicAdd(&st->mid_arrive[round1], 1u);
+      if (tid == 0 && cta == 0) TT(1, 5);
+    }
+    return;
+  }
+  if (cta >= 0) return;
+  // ---- finaliser group ----
+  if (ft == 0) { s_L0 = ld_state(&st->L0); s_SL = ld_state(&st->SL); s_p = ld_state(&st->p); }
+  if (ft >= 32 && ft - 32 < l) { const fe tau = ld_state(&st->taus[ft - 32]); const fe l0 = Fq::sub(Fq::one(), tau); s_l0[ft - 32] = l0; s_sl[ft - 32] = Fq::sub(tau, l0); }
+  for (int q = ft; q < (last - first + 1) * MP_ACC_WORDS; q += TP_FIN) mid_acc(st, first)[q] = 0;
+  __threadfence();                                              // (ordered before the first release: the role CTAs add after it)
+  tp_msg_init(ts, st, 3, ft);
+  int cur = 0;
+  for (int round1 = first; round1 <= last; round1++) {
+    const bool want_next = round1 < last;
+    const fe r = round1 > first ? ts.ch : Fq::zero();
+    if (ft == 0) st->prof[round1 - 1][0] = gtimer();
+    if (ft == 0) TT(1, 6);
+    if (round1 == first) {
+      if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, want_next ? 12 : 3, ts.gat);   // direct sums, then the coefficients
+      bar_sync_n(2, TP_FIN);
+      if (ft < 3) ts.x[ft] = ts.gat[ft];
+      if (ft >= 32 && ft < 41) ts.coef[cur ^ 1][ft - 32] = ts.gat[3 + ft - 32];
+    } else {
+      // bound() of the previous round: p <- p l(r), and this round's L0 / SL (sumcheck.rs:1399-1405) — on fin warp 1, beside the sums
+      if (ft == 32) {
+        const fe pn = Fq::mul(s_p, Fq::add(s_l0[round1 - 2], Fq::mul(s_sl[round1 - 2], r)));
+        s_p = pn; s_L0 = Fq::mul(pn, s_l0[round1 - 1]); s_SL = Fq::mul(pn, s_sl[round1 - 1]);
+      }
+      if (ft < 3) { const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r); }
+    }
+    bar_sync_n(2, TP_FIN);
+    if (ft == 0) st->prof[round1 - 1][1] = gtimer();
+    // round message (cubic_finalize_pre) on fin warp 0
+    const int i = round1 - 1;
+    fe canon = Fq::zero();
+    if (ft < 32) {
+      const fe t0 = ts.x[0], t1 = ts.x[1], tinf = ts.x[2];
+      const fe tb = Fq::sub(Fq::sub(t1, t0), tinf);
+      __syncwarp();
+      if (ft < 6) {
+        const bool use_sl = (ft == 2) | (ft == 4) | (ft == 5);
+        const fe &v = (ft == 0 || ft == 2) ? t0 : ((ft == 1 || ft == 4) ? tb : tinf);
+        ts.g[ft] = Fq::mul(use_sl ? s_SL : s_L0, v);
+      }
+      __syncwarp();
+      if (ft < 4) {
+        const fe co = ft == 0 ? ts.g[0] : ft == 1 ? Fq::add(ts.g[1], ts.g[2]) : ft == 2 ? Fq::add(ts.g[3], ts.g[4]) : ts.g[5];
+        stg_fe(&st->polys[4 * i + ft], co);
+        canon = Fq::from_mont(co);
+      }
+      const int src = ft == 0 ? 0 : ft + 1;
+#pragma unroll
+      for (int q = 0; q < 8; q++) canon.v[q] = __shfl_sync(0xffffffffu, canon.v[q], src & 31);
+    }
+    const bool gather_next = round1 > first && want_next;
+    fe *coef_next = ts.coef[cur ^ 1];
+    if (ft == 0) st->prof[round1 - 1][2] = gtimer();
+    if (ft == 0) TT(1, 7);
+    const fe rn = tp_squeeze(ts, canon, 3, ft, [&] { if (gather_next) mid_gather_acc(st, round1, G, mid_acc(st, round1), 9, coef_next); });
+    if (ft == 0) { stg_fe(&st->r[i], rn); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); st->prof[round1 - 1][3] = gtimer(); }
+    if (ft == 0) TT(1, 8);
+    bar_sync_n(2, TP_FIN);
+    cur ^= 1;
+  }
+  // hand-off to the next kernel: transcript, and the eq prefix of the round after the last
+  tp_msg_store(ts, st, 3, ft);
+  if (ft == 32) {
+    const fe r = ts.ch;
+    const fe pn = Fq::mul(s_p, Fq::add(s_l0[last - 1], Fq::mul(s_sl[last - 1], r)));
+    stg_fe(&st->p, pn);
+    if (last < l) { stg_fe(&st->L0, Fq::mul(pn, s_l0[last])); stg_fe(&st->SL, Fq::mul(pn, s_sl[last])); }
+  }
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
+  extern __shared__ __align__(32) unsigned char mp_dyn[];
+  __shared__ TailSmem ts;
+  ScState *st = a.st;
+  const int rounds = a.rounds, first = a.round_first, last = a.round_last, k = a.k, G = (int)gridDim.x - 1, cta = (int)blockIdx.x - 1;   // CTA G: finaliser only
+  const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
+  const bool is_role = tid < TP_ROLE;
+  const int warp = tid >> 5;
+  if (is_role) {
+    if (cta < 0) return;
+    const u64 n0 = ((u64)2 << (rounds - first)) >> k;          // local length of the first bound table
+    fe *X = (fe *)mp_dyn, *Y = X + 2 * n0;
+    fe *cur = X, *nxt = Y; u64 cs = n0, ns = n0 / 2;
+    const int grp = warp & 1, pair = warp >> 1;                 // even warps: the low halves, odd warps: the differences
+    for (int round1 = first; round1 <= last; round1++) {
+      const u64 P = (u64)1 << (rounds - round1), Pl = P >> k, Hl = Pl >> 1;
+      const bool want_next = round1 < last;
+      if (round1 > first) mid_wait_released(st, round1 - 1);
+      const fe r = ld_state(&st->r[round1 - 2]);
+      if (round1 == first) {
+        for (u64 q0 = (u64)tid; q0 < 4 * Pl; q0 += 4 * TP_ROLE) {   // strided reads of the natural-order tables: four pairs in flight per thread
+          fe lo[4], hi[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const u64 q = q0 + (u64)u * TP_ROLE, j = q >> 1, g = (j << k) | (u64)cta;
+            const fe *S = (q & 1) ? a.B : a.A;
+            if (q < 4 * Pl) { lo[u] = ldg_fe(S + g); hi[u] = ldg_fe(S + g + 2 * P); }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const u64 q = q0 + (u64)u * TP_ROLE, j = q >> 1;
+            if (q < 4 * Pl) cur[(q & 1) * cs + j] = bind_pair(lo[u], hi[u], r);
+          }
+        }
+      } else {
+        for (u64 q = (u64)tid; q < 4 * Pl; q += TP_ROLE) {
+          const u64 j = q >> 1;
+          const fe *S = cur + (q & 1) * cs; fe *D = nxt + (q & 1) * ns;
+          D[j] = bind_pair(S[j], S[j + 2 * Pl], r);
+        }
+        { fe *t = cur; cur = nxt; nxt = t; const u64 u = cs; cs = ns; ns = u; }
+      }
+      bar_sync_n(1, TP_ROLE);
+      const fe *cA = cur, *cB = cur + cs;
+      if (round1 == first) {
+        // the round's own sums, directly: even warps e0 = sum a0 b0, odd warps t(inf) = sum (a1 - a0)(b1 - b0)
+        fe xs[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
+        if ((u64)pair * 32 < Pl) {
+          Fq::acc d = Fq::acc_zero();
+          for (u64 j = (u64)pair * 32 + lane; j < Pl; j += (TP_ROLE / 64) * 32) {
+            if (grp == 0) Fq::mul_acc(d, cA[j], cB[j]);
+            else Fq::mul_acc(d, Fq::sub(cA[j + Pl], cA[j]), Fq::sub(cB[j + Pl], cB[j]));
+          }
+          xs[0] = Fq::acc_reduce(d);
+          warp_sum_fq_cols<3>(xs);
+        }
+        mid_publish_acc<2>(ts, xs, st->mid_acc0, 0, true);
+      }
+      if (want_next) {
+        // (with <= 32 local pairs the three coefficient sums of a pair go to three different warp pairs: one product per thread)
+        fe xs[3] = {Fq::zero(), Fq::zero(), Fq::zero()};
+        const bool split = Hl <= 32;
+        const int cmask = split ? (pair < 3 ? 1 << pair : 0) : 7;
+        if (cmask && (split || (u64)pair * 32 < Hl)) {
+          Fq::acc c0 = Fq::acc_zero(), c2 = Fq::acc_zero(), cd = Fq::acc_zero();
+          for (u64 j = split ? (u64)lane : (u64)pair * 32 + lane; j < Hl; j += (TP_ROLE / 64) * 32) {
+            fe x0, x2, y0, y2;
+            if (grp == 0) { x0 = cA[j]; x2 = cA[j + Pl]; y0 = cB[j]; y2 = cB[j + Pl]; }
+            else {
+              x0 = Fq::sub(cA[j + Hl], cA[j]); x2 = Fq::sub(cA[j + Pl + Hl], cA[j + Pl]);
+              y0 = Fq::sub(cB[j + Hl], cB[j]); y2 = Fq::sub(cB[j + Pl + Hl], cB[j + Pl]);
+            }
+            if (cmask & 1) Fq::mul_acc(c0, x0, y0);
+            if (cmask & 2) Fq::mul_acc(c2, x2, y2);
+            if (cmask & 4) Fq::mul_acc(cd, Fq::sub(x2, x0), Fq::sub(y2, y0));
+          }
+          if (cmask & 1) xs[0] = Fq::acc_reduce(c0);
+          if (cmask & 2) xs[1] = Fq::acc_reduce(c2);
+          if (cmask & 4) xs[2] = Fq::acc_reduce(cd);
+          warp_sum_fq_cols<3>(xs);
+        }
+        mid_publish_acc<2>(ts, xs, round1 == first ? st->mid_acc0 : mid_acc(st, round1), round1 == first ? 3 : 0, false);
+      } else {
+        for (u64 q = (u64)tid; q < 4 * Pl; q += TP_ROLE) {
+          const u64 j = q >> 1;
+          stg_fe(((q & 1) ? a.oB : a.oA) + ((j << k) | (u64)cta), cur[(q & 1) * cs + j]);
+        }
+      }
+      if ((round1 == first || want_next) && tid == 0) atomicAdd(&st->mid_arrive[round1], 1u);
+    }
+    return;
+  }
+  if (cta >= 0) return;
+  // ---- finaliser group ----
+  if (ft == 0) ts.claim = ld_state(&st->claim);
+  for (int q = ft; q < (last - first + 1) * MP_ACC_WORDS; q += TP_FIN) mid_acc(st, first)[q] = 0;
+  __threadfence();                                              // (ordered before the first release: the role CTAs add after it)
+  tp_msg_init(ts, st, 2, ft);
+  int cur = 0;
+  for (int round1 = first; round1 <= last; round1++) {
+    const bool want_next = round1 < last;
+    const fe r = round1 > first ? ts.ch : Fq::zero();
+    if (round1 == first) {
+      if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, want_next ? 9 : 3, ts.gat);   // direct sums, then the coefficients
+      bar_sync_n(2, TP_FIN);
+      if (ft < 2) ts.x[ft] = ts.gat[ft];
+      if (ft >= 32 && ft < 38) ts.coef[cur ^ 1][ft - 32] = ts.gat[3 + ft - 32];
+    } else if (ft < 2) {
+      const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r);
+    }
+    bar_sync_n(2, TP_FIN);
+    // round message (quad_finalize_pre) on fin warp 0
+    const int i = round1 - 1;
+    fe canon = Fq::zero(), e0 = Fq::zero(), ti = Fq::zero(), b = Fq::zero();
+    if (ft < 32) {
+      e0 = ts.x[0]; ti = ts.x[1];
+      b = Fq::sub(Fq::sub(ts.claim, Fq::dbl(e0)), ti);
+      if (ft < 3) stg_fe(&st->polys[4 * i + ft], ft == 0 ? e0 : ft == 1 ? b : ti);
+      if (ft < 2) canon = Fq::from_mont(ft == 0 ? e0 : ti);
+    }
+    const bool gather_next = round1 > first && want_next;
+    fe *coef_next = ts.coef[cur ^ 1];
+    const fe rn = tp_squeeze(ts, canon, 2, ft, [&] { if (gather_next) mid_gather_acc(st, round1, G, mid_acc(st, round1), 6, coef_next); });
+    if (ft == 0) { stg_fe(&st->r[i], rn); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); }
+    if (ft == 1) ts.claim = Fq::add(e0, Fq::mul(rn, Fq::add(b, Fq::mul(rn, ti))));               // claim <- poly(r)
+    bar_sync_n(2, TP_FIN);
+    cur ^= 1;
+  }
+  tp_msg_store(ts, st, 2, ft);
+  if (ft == 0) stg_fe(&st->claim, ts.claim);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1294,6 +1705,25 @@ int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uin
 static bool use_persistent() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_NO_PERSIST"); v = (e && e[0] == '1') ? 0 : 1; } return v == 1; }
 // SP2_TAIL_PIPE=0: the non-pipelined single-CTA tails (measurement switch)
 static bool use_tail_pipe() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_TAIL_PIPE"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
+// SP2_MID_PIPE=0: every multi-CTA round stays in the persistent kernels (measurement switch)
+static bool use_mid_pipe() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_MID_PIPE"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1 && use_tail_pipe(); }
+// plan of the pipelined multi-CTA rounds [*first, round_end - 1] on 2^*k CTAs (k_*_mid_pipe); false when fewer than two such rounds exist
+static bool mid_plan(sp2_ctx *ctx, uint32_t l, uint32_t min_first, uint32_t round_end, int ntab, uint32_t *first, uint32_t *k, size_t *smem) {
+  if (!use_mid_pipe()) return false;
+  uint32_t rm = min_first;
+  while (rm <= l && (4ull << (l - rm)) > (1ull << MP_LOG_LEN_IN)) rm++;
+  if (rm + 1 >= round_end) return false;
+  int kk = (int)(l - rm) + 1 - MP_LOG_LOCAL;                    // log2(length of the first bound table) - log2(local length)
+  if (kk > MP_LOG_CTAS) kk = MP_LOG_CTAS;
+  while (kk > 0 && (1 << kk) + 1 > ctx->num_sms) kk--;
+  while (kk > 0 && (((u64)1 << (l - (round_end - 2))) >> kk) < 2) kk--;   // the coefficient rounds need two local pairs
+  if (kk < 1) return false;
+  const u64 n0 = ((u64)2 << (l - rm)) >> kk;
+  *smem = (size_t)ntab * (n0 + n0 / 2) * sizeof(fe);
+  if (*smem > 200 * 1024) return false;
+  *first = rm; *k = (uint32_t)kk;
+  return true;
+}
 static DevComm comm_none() { DevComm d; memset(&d, 0, sizeof(d)); d.n = 1; return d; }
 
 // all-gather the shards (len_local entries per table) into every rank's gather area and return the local copy
@@ -1334,16 +1764,30 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     // all multi-CTA rounds in one cooperative launch (one CTA per SM), then the single-CTA tail
     uint32_t round_end = 1;
     while (round_end <= l && ((round_end > 1 ? 4ull : 2ull) << (l - round_end)) > SC_TAIL_LEN) round_end++;
-    if (round_end > 1) {
-      PersistCubic pa{st, A, B, C, dst[0], dst[1], dst[2], (int)l, 1, (int)round_end, eq_left, eq_right};
+    uint32_t mid_first = 0, mid_k = 0; size_t mid_smem = 0;
+    const bool mid = mid_plan(ctx, l, 2, round_end, 3, &mid_first, &mid_k, &mid_smem);
+    const uint32_t persist_end = mid ? mid_first : round_end;
+    if (persist_end > 1) {
+      PersistCubic pa{st, A, B, C, dst[0], dst[1], dst[2], (int)l, 1, (int)persist_end, eq_left, eq_right};
       void *args[] = {&pa};
       SP2_CUDA_OK(cudaEventRecord(ctx->ev_k0, ctx->stream));
       SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_cubic_persist, dim3(ctx->num_sms * SC_PERSIST_MINB), dim3(SC_THREADS), args, 0, ctx->stream));
       SP2_CUDA_OK(cudaEventRecord(ctx->ev_k1, ctx->stream));
       ctx->ev_k_valid = true;
       ctx->launches++;
-      for (uint32_t rr = 2; rr < round_end; rr++)              // fused role rounds ping-pong src <-> dst
+      for (uint32_t rr = 2; rr < persist_end; rr++)            // fused role rounds ping-pong src <-> dst
         if ((4ull << (l - rr)) <= SC_ROLE_LEN) for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);
+      round_start = persist_end;
+    }
+    if (mid) {
+      // rounds [mid_first, round_end): pipelined on 2^mid_k CTAs; the table bound by the last of them lands in dst (natural order)
+      static bool attr = false;
+      if (!attr) { SP2_CUDA_OK(cudaFuncSetAttribute((const void *)k_cubic_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+      MidCubic ma{st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)l, (int)mid_first, (int)round_end - 1, (int)mid_k, eq_left, eq_right};
+      void *args[] = {&ma};
+      SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_cubic_mid_pipe, dim3((1u << mid_k) + 1), dim3(TP_THREADS), args, mid_smem, ctx->stream));
+      ctx->launches++;
+      for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);
       round_start = round_end;
     }
   }
@@ -1422,14 +1866,27 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
   if (!sharded && use_persistent()) {
     uint32_t round_end = 1;
     while (round_end <= rounds && ((round_end > 1 ? 4ull : 2ull) << (rounds - round_end)) > SC_TAIL_LEN) round_end++;
-    if (round_end > 1) {
-      PersistQuad pa{st, A, B, dst[0], dst[1], (int)rounds, 1, (int)round_end, nvalid};
+    uint32_t mid_first = 0, mid_k = 0; size_t mid_smem = 0;
+    const bool mid = mid_plan(ctx, rounds, 3, round_end, 2, &mid_first, &mid_k, &mid_smem);   // from round 3 on every entry is materialised
+    const uint32_t persist_end = mid ? mid_first : round_end;
+    if (persist_end > 1) {
+      PersistQuad pa{st, A, B, dst[0], dst[1], (int)rounds, 1, (int)persist_end, nvalid};
       void *args[] = {&pa};
       SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_quad_persist, dim3(ctx->num_sms * SC_PERSIST_MINB), dim3(SC_THREADS), args, 0, ctx->stream));
       ctx->launches++;
       if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
-      for (uint32_t rr = 2; rr < round_end; rr++)
+      for (uint32_t rr = 2; rr < persist_end; rr++)
         if ((4ull << (rounds - rr)) <= SC_ROLE_LEN) { std::swap(src[0], dst[0]); std::swap(src[1], dst[1]); }
+      round_start = persist_end;
+    }
+    if (mid) {
+      static bool attr = false;
+      if (!attr) { SP2_CUDA_OK(cudaFuncSetAttribute((const void *)k_quad_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+      MidQuad ma{st, src[0], src[1], dst[0], dst[1], (int)rounds, (int)mid_first, (int)round_end - 1, (int)mid_k};
+      void *args[] = {&ma};
+      SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_quad_mid_pipe, dim3((1u << mid_k) + 1), dim3(TP_THREADS), args, mid_smem, ctx->stream));
+      ctx->launches++;
+      std::swap(src[0], dst[0]); std::swap(src[1], dst[1]);
       round_start = round_end;
     }
   }
@@ -1482,6 +1939,8 @@ extern "C" {
 /* tables of at most this many entries are finished by the single-CTA tail kernels; larger ones go through the persistent
  * multi-CTA kernels (bench.py derives from it which rounds k_cubic_persist covers) */
 uint64_t sp2_sc_tail_len(void) { return SC_TAIL_LEN; }
+/* tables of at most this many entries (going into a round >= 2) leave the persistent kernels for the pipelined multi-CTA kernels; 0 = disabled */
+uint64_t sp2_sc_mid_len(void) { return use_mid_pipe() ? (1ull << MP_LOG_LEN_IN) : 0; }
 #ifdef SP2_TAIL_TRACE
 int32_t sp2_debug_tail_trace(long long *out) { return (int32_t)cudaMemcpyFromSymbol(out, g_tail_trace, sizeof(long long) * 2 * 40 * 10); }
 #endif

@@ -28,6 +28,9 @@ struct ScState {
   fe L0, SL;                  // p*(1-tau_i), p*(2tau_i-1) for the round being evaluated
   u32 ticket, l, flags, arrived;     // arrived / released: monotonic counters of the persistent kernels' grid barrier
   u32 released, err, pad1[2];   // err: a bounded device wait (grid barrier / peer mailbox) timed out -> SP2_ERR_INTERNAL on the host
+  u32 mid_arrive[SC_MAX_ROUNDS + 8];   // pipelined multi-CTA rounds: CTAs whose partial sums of a round are published
+  u32 mid_released, pad2[7];           //   and the last round whose challenge is published
+  u32 mid_acc0[12 * 16];               //   column accumulators of the first such round (3 direct + 9 coefficient sums), zero on entry
   // flags bit 0: warp-shuffle Keccak (default; measured 12.6k cycles/squeeze vs 22k for the one-thread register version)
   fe taus[SC_MAX_ROUNDS];
   // ---- everything above is uploaded by the host; everything below is produced on the device ----

@@ -30,7 +30,7 @@ def _cubic_case(ctx, orc, l, seed, satisfied=False):
     return claim, taus, polys, r, claims
 
 
-@pytest.mark.parametrize("l", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16])
+@pytest.mark.parametrize("l", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 19, 20])
 def test_cubic_bit_exact(ctx, orc, l):
     _cubic_case(ctx, orc, l, 0xDEADBEEF + l)
 
@@ -69,7 +69,7 @@ def test_cubic_tau_zero_matches_reference_fallback(ctx, orc):
     assert np.array_equal(polys, opolys) and np.array_equal(r, orr) and np.array_equal(claims, oclaims)
 
 
-@pytest.mark.parametrize("l", [1, 2, 3, 5, 8, 9, 12, 16, 18])
+@pytest.mark.parametrize("l", [1, 2, 3, 5, 8, 9, 12, 13, 14, 15, 16, 17, 18, 19, 21])
 def test_quad_bit_exact(ctx, orc, l):
     import spartan2_b200 as sp
     rng = np.random.default_rng(77 + l); n = 1 << l

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libspartan2_b200.so")
+LIB_PATH = os.environ.get("SP2_LIB_PATH") or os.path.join(HERE, "libspartan2_b200.so")   # (override: A/B measurements of two builds)
 _lib = None
 
 OK = 0

@@ -29,6 +29,13 @@ __device__ __forceinline__ void stg_fe(fe *p, const fe &x) {
   asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
+// c ? a : b, limb by limb (a reference-valued ?: makes the compiler spill both operands and index them through local memory)
+__device__ __forceinline__ fe fe_sel(bool c, const fe &a, const fe &b) {
+  fe r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
+  return r;
+}
 __device__ __forceinline__ fe shfl_xor_fe(const fe &x, int m) {
   fe r;
 #pragma unroll

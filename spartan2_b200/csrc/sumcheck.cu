@@ -67,6 +67,12 @@ __device__ __noinline__ void fq_mul_ni(fe *out, const fe *a, const fe *b) { *out
 __device__ __forceinline__ fe mul_ni(const fe &a, const fe &b) { fe o; fq_mul_ni(&o, &a, &b); return o; }
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#ifdef SP2_TAIL_TRACE
+__device__ long long g_tail_trace[2][40][10];
+#define TT(kern, slot_) do { g_tail_trace[kern][round1][slot_] = (long long)gtimer(); } while (0)
+#else
+#define TT(kern, slot_) do { } while (0)
+#endif
 // Bounded spin: waits until pred() holds; gives up after SC_WAIT_NS of %globaltimer (sampled every 256 polls so the
 // timer read stays off the fast path) and raises *err instead of hanging — a peer that failed or died, or a grid that
 // lost a CTA, must come back to the host as SP2_ERR_INTERNAL, not as a wedged GPU.
@@ -261,7 +267,7 @@ __device__ __forceinline__ fe cubic_finalize_pre(ScState *st, int round1, const 
     const fe tb = Fq::sub(Fq::sub(x[1], x[0]), x[2]);
     if (tid < 6) {            // L0*t0, L0*tb, SL*t0, L0*tinf, SL*tb, SL*tinf
       const bool use_sl = (tid == 2) | (tid == 4) | (tid == 5);
-      const fe &v = (tid == 0 || tid == 2) ? x[0] : ((tid == 1 || tid == 4) ? tb : x[2]);
+      const fe v = fe_sel(tid == 0 || tid == 2, x[0], fe_sel(tid == 1 || tid == 4, tb, x[2]));
       sm.g[tid] = mul_ni(ld_state(use_sl ? &st->SL : &st->L0), v);
     }
     __syncwarp();
@@ -451,12 +457,6 @@ k_cubic_round_roles(ScState *st, const fe *sA, const fe *sB, const fe *sC, fe *d
   if (threadIdx.x == 0) { st->gt[4] = st->gt[2]; st->gt[2] = gtimer(); st->gt[3] = st->gt[0]; st->gt[0] = ~0ull; }
 }
 
-#ifdef SP2_TAIL_TRACE
-__device__ long long g_tail_trace[2][40][10];
-#define TT(kern, slot_) do { g_tail_trace[kern][round1][slot_] = (long long)gtimer(); } while (0)
-#else
-#define TT(kern, slot_) do { } while (0)
-#endif
 // all remaining rounds [round_first, l] in one CTA (tables of <= SC_TAIL_LEN entries going in); ping-pongs between
 // (A,B,C) and the scratch copies (A2,B2,C2)
 // The CTA has SC_TAIL_THREADS role threads plus one SCALAR WARP (warp SC_TAIL_THREADS/32) that has no pair work: at
@@ -567,8 +567,8 @@ __device__ __forceinline__ fe quad_finalize_pre(ScState *st, int round1, const f
     // from_evals([e0, claim-e0, 2claim-3e0+2tinf]) = [e0, claim - 2 e0 - tinf, tinf]  (sumcheck.rs:205-216)
     const fe e0 = x[0], ti = x[1];
     const fe b = Fq::sub(Fq::sub(ld_state(&st->claim), Fq::dbl(e0)), ti);
-    if (tid < 3) stg_fe(&st->polys[4 * i + tid], tid == 0 ? e0 : tid == 1 ? b : ti);
-    if (tid < 2) canon = Fq::from_mont(tid == 0 ? e0 : ti);
+    if (tid < 3) stg_fe(&st->polys[4 * i + tid], fe_sel(tid == 0, e0, fe_sel(tid == 1, b, ti)));
+    if (tid < 2) canon = Fq::from_mont(fe_sel(tid == 0, e0, ti));
     if (tid == 0) { sm.g[0] = e0; sm.g[1] = b; sm.g[2] = ti; }
   }
   const fe r = sc_squeeze(st, sm, canon, 2);      // (its barriers publish sm.g[0..2] to the CTA)
@@ -808,8 +808,8 @@ __device__ __forceinline__ void tp_msg_store(const TailSmem &ts, ScState *st, in
 // and left in ts.ch for everybody else (visible after the CTA barrier that ends the round).  Fin warps 2, 3 run the two hashes: they sit
 // on the SM sub-partitions that the lowest role warps (the only ones with work in the last rounds) use least.
 struct TpNoSide { __device__ __forceinline__ void operator()() const {} };
-template <class Side = TpNoSide>
-__device__ __forceinline__ fe tp_squeeze(TailSmem &ts, const fe &canon, int ncoef, int ft, Side side = Side()) {
+template <class Side0 = TpNoSide, class Side1 = TpNoSide>
+__device__ __forceinline__ fe tp_squeeze(TailSmem &ts, const fe &canon, int ncoef, int ft, Side0 side0 = Side0(), Side1 side1 = Side1()) {
   const TpMsg g = tp_msg(ncoef);
   if (ft < ncoef) {
 #pragma unroll
@@ -833,18 +833,19 @@ __device__ __forceinline__ fe tp_squeeze(TailSmem &ts, const fe &canon, int ncoe
     }
     if (lane < 4) ts.dg[w * 4 + lane] = s;
   } else if (ft >= 32) {
-    side();                                        // fin warp 1: work that may run beside the two permutations
+    side1();                                       // fin warp 1: work that may run beside the two permutations
+  } else {
+    side0();                                       // fin warp 0: scalars of the NEXT round that do not need this round's challenge
   }
   bar_sync_n(2, TP_FIN);
   fe ch = Fq::zero();
-  if (ft < 32) {                                   // from_uniform: lo * R^2 + hi * R^3 (Montgomery form of lo + 2^256 hi)
-    fe lo, hi;
+  if (ft < 32) {                                   // from_uniform: lo * R^2 + hi * R^3 (Montgomery form of lo + 2^256 hi): even lanes lo, odd lanes hi
+    const int half = ft & 1;
+    fe h;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      lo.v[2 * i] = (u32)ts.dg[i]; lo.v[2 * i + 1] = (u32)(ts.dg[i] >> 32);
-      hi.v[2 * i] = (u32)ts.dg[4 + i]; hi.v[2 * i + 1] = (u32)(ts.dg[4 + i] >> 32);
-    }
-    ch = Fq::add(Fq::mul(lo, Fq::cst_r2()), Fq::mul(hi, Fq::cst_r3()));
+    for (int i = 0; i < 4; i++) { h.v[2 * i] = (u32)ts.dg[4 * half + i]; h.v[2 * i + 1] = (u32)(ts.dg[4 * half + i] >> 32); }
+    const fe m = Fq::mul(h, fe_sel(half != 0, Fq::cst_r3(), Fq::cst_r2()));
+    ch = Fq::add(m, shfl_xor_fe(m, 1));
     if (ft == 0) ts.ch = ch;
   } else if (ft >= 64) {                           // the next round's header, off the challenge's path: state <- lo || hi
     const unsigned char b = ((const unsigned char *)ts.dg)[ft - 64];
@@ -856,14 +857,121 @@ __device__ __forceinline__ fe tp_squeeze(TailSmem &ts, const fe &canon, int ncoe
   return ch;
 }
 // c0 + r (mid + r c2) with mid = c22 - c0 - c2 (Karatsuba form of the middle coefficient)
+#ifdef SP2_FIN_INLINE_MUL
+#define FIN_MUL Fq::mul_inl
+#else
+#define FIN_MUL Fq::mul
+#endif
 __device__ __forceinline__ fe eval_karatsuba(const fe &c00, const fe &c22, const fe &cdd, const fe &r) {
   const fe mid = Fq::sub(Fq::sub(c22, c00), cdd);
-  return Fq::add(c00, Fq::mul(r, Fq::add(mid, Fq::mul(r, cdd))));
+  return Fq::add(c00, FIN_MUL(r, Fq::add(mid, FIN_MUL(r, cdd))));
+}
+
+// ---- the finaliser's scalar work: fin warp 0, every lane calls, __syncwarp only ---------------------------------------------------
+// Everything a round needs from the previous challenge r is a polynomial of degree <= 2 in r whose coefficients are ready before r is:
+// the sums (coefficient form), and for the cubic prover L0_i = L0_(i-1) l0_i + SL_(i-1) l0_i r, SL_i likewise, p_i = L0_(i-1) + SL_(i-1) r
+// (l_i(X) = l0_i + sl_i X; sumcheck.rs:1399-1405), for the quadratic prover the claim e0 + r (b + r t_inf).  One SIMD evaluation (two dependent
+// multiplications) gives all of them, one more multiplication the round polynomial: three multiplications and a from_mont between the
+// challenge and the next absorb.
+struct FinCubic {
+  fe lin[3][3];                                     // (c00, c22, cdd) of L0, SL, p of the coming round (eval_karatsuba form)
+  fe h[6];
+  fe l0[SC_MAX_ROUNDS], sl[SC_MAX_ROUNDS];          // l_i(X) = l0[i-1] + sl[i-1] X
+};
+__device__ __forceinline__ void fin_cubic_init(FinCubic &fc, const ScState *st, int l, int ft) {   // the whole finaliser group; barrier afterwards
+  if (ft < l) { const fe tau = ld_state(&st->taus[ft]); const fe l0 = Fq::sub(Fq::one(), tau); fc.l0[ft] = l0; fc.sl[ft] = Fq::sub(tau, l0); }
+  if (ft >= 64 && ft < 67) {
+    const fe v = ld_state(ft == 64 ? &st->L0 : ft == 65 ? &st->SL : &st->p);
+    fc.lin[ft - 64][0] = v; fc.lin[ft - 64][1] = v; fc.lin[ft - 64][2] = Fq::zero();
+  }
+}
+// the round's message: sums from ts.x (direct) or from the coefficient triples at r; leaves t0, t1, tinf, L0, SL, p in ts.g[0..6); returns
+// the canonical transcript coefficients in lanes 0..2
+__device__ __forceinline__ fe fin_cubic_msg(TailSmem &ts, FinCubic &fc, ScState *st, int round1, bool direct, const fe *coef, const fe &r, int lane) {
+  fe c00 = Fq::zero(), c22 = Fq::zero(), cdd = Fq::zero();
+  if (lane == 0) TT(0, 0);
+  if (lane < 3) {
+    if (direct) { c00 = ts.x[lane]; c22 = c00; }
+    else { c00 = coef[3 * lane]; c22 = coef[3 * lane + 1]; cdd = coef[3 * lane + 2]; }
+  } else if (lane < 6) { c00 = fc.lin[lane - 3][0]; c22 = fc.lin[lane - 3][1]; cdd = fc.lin[lane - 3][2]; }
+  if (lane == 0) TT(0, 1);
+  const fe val = eval_karatsuba(c00, c22, cdd, r);
+  if (lane < 6) ts.g[lane] = val;
+  __syncwarp();
+  if (lane == 0) TT(0, 2);
+  const fe t0 = ts.g[0], t1 = ts.g[1], tinf = ts.g[2];
+  const fe tb = Fq::sub(Fq::sub(t1, t0), tinf);
+  {  // L0*t0, L0*tb, SL*t0, L0*tinf, SL*tb, SL*tinf
+    const bool use_sl = (lane == 2) | (lane == 4) | (lane == 5);
+    const fe v = fe_sel(lane == 0 || lane == 2, t0, fe_sel(lane == 1 || lane == 4, tb, tinf));
+    const fe pr = FIN_MUL(fe_sel(use_sl, ts.g[4], ts.g[3]), v);
+    if (lane < 6) fc.h[lane] = pr;
+  }
+  __syncwarp();
+  if (lane == 0) TT(0, 3);
+  fe canon = Fq::zero();
+  if (lane < 4) {                                   // lanes 0, 1, 2: coefficients 0, 2, 3 (the transcript's); lane 3: the linear one
+    const int idx = lane == 0 ? 0 : lane == 1 ? 2 : lane == 2 ? 3 : 1;
+    // (h[0] | h[1] + h[2] | h[3] + h[4] | h[5]) as x + y with y = 0 for the outer two
+    const fe co = Fq::add(fc.h[idx == 0 ? 0 : idx == 1 ? 1 : idx == 2 ? 3 : 5], fe_sel(idx == 1 || idx == 2, fc.h[idx == 1 ? 2 : 4], Fq::zero()));
+    stg_fe(&st->polys[4 * (round1 - 1) + idx], co);
+    canon = Fq::from_mont(co);
+  }
+  __syncwarp();
+  if (lane == 0) TT(0, 4);
+  return canon;
+}
+// beside the squeeze: the coming round's L0, SL, p as polynomials in this round's challenge
+__device__ __forceinline__ void fin_cubic_next(TailSmem &ts, FinCubic &fc, int round1, int l, int lane) {
+  if (round1 < l) {
+    const fe m = Fq::mul((lane & 1) ? ts.g[4] : ts.g[3], (lane & 2) ? fc.sl[round1] : fc.l0[round1]);   // L0 l0', SL l0', L0 sl', SL sl'
+    if (lane < 4) fc.h[lane] = m;
+    __syncwarp();
+    if (lane < 2) { const fe a = fc.h[2 * lane], b = fc.h[2 * lane + 1]; fc.lin[lane][0] = a; fc.lin[lane][1] = Fq::add(a, b); fc.lin[lane][2] = Fq::zero(); }
+  }
+  if (lane == 2) { fc.lin[2][0] = ts.g[3]; fc.lin[2][1] = Fq::add(ts.g[3], ts.g[4]); fc.lin[2][2] = Fq::zero(); }
+  __syncwarp();
+}
+// hand-off after the last round of a kernel: p (and L0, SL of the round after it) back to the state
+__device__ __forceinline__ void fin_cubic_store(FinCubic &fc, ScState *st, int last, int l, const fe &r, int lane) {
+  if (lane < 3) {
+    const fe v = eval_karatsuba(fc.lin[lane][0], fc.lin[lane][1], fc.lin[lane][2], r);
+    if (lane == 2) stg_fe(&st->p, v);
+    else if (last < l) stg_fe(lane == 0 ? &st->L0 : &st->SL, v);
+  }
+}
+struct FinQuad { fe lin[3]; };                      // the running claim as a polynomial in the coming challenge
+__device__ __forceinline__ void fin_quad_init(FinQuad &fq, const ScState *st, int ft) {
+  if (ft == 64) { const fe v = ld_state(&st->claim); fq.lin[0] = v; fq.lin[1] = v; fq.lin[2] = Fq::zero(); }
+}
+__device__ __forceinline__ fe fin_quad_msg(TailSmem &ts, FinQuad &fq, ScState *st, int round1, bool direct, const fe *coef, const fe &r, int lane) {
+  fe c00 = Fq::zero(), c22 = Fq::zero(), cdd = Fq::zero();
+  if (lane < 2) {
+    if (direct) { c00 = ts.x[lane]; c22 = c00; }
+    else { c00 = coef[3 * lane]; c22 = coef[3 * lane + 1]; cdd = coef[3 * lane + 2]; }
+  } else if (lane == 2) { c00 = fq.lin[0]; c22 = fq.lin[1]; cdd = fq.lin[2]; }
+  const fe val = eval_karatsuba(c00, c22, cdd, r);
+  if (lane < 3) ts.g[lane] = val;                   // e0, tinf, claim
+  __syncwarp();
+  // from_evals([e0, claim-e0, 2claim-3e0+2tinf]) = [e0, claim - 2 e0 - tinf, tinf]  (sumcheck.rs:205-216)
+  const fe e0 = ts.g[0], ti = ts.g[1];
+  const fe b = Fq::sub(Fq::sub(ts.g[2], Fq::dbl(e0)), ti);
+  if (lane < 3) stg_fe(&st->polys[4 * (round1 - 1) + lane], fe_sel(lane == 0, e0, fe_sel(lane == 1, b, ti)));
+  fe canon = Fq::zero();
+  if (lane < 2) canon = Fq::from_mont(fe_sel(lane == 0, e0, ti));
+  __syncwarp();
+  if (lane == 0) { fq.lin[0] = e0; fq.lin[1] = Fq::add(Fq::add(e0, b), ti); fq.lin[2] = ti; }      // claim <- e0 + r (b + r tinf)
+  __syncwarp();
+  return canon;
+}
+__device__ __forceinline__ void fin_quad_store(FinQuad &fq, ScState *st, const fe &r, int lane) {
+  if (lane == 0) stg_fe(&st->claim, eval_karatsuba(fq.lin[0], fq.lin[1], fq.lin[2], r));
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1)
 k_quad_tail_pipe(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int rounds, u64 nvalid) {
   __shared__ TailSmem ts;
+  __shared__ FinQuad fq;
   const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
   const bool is_role = tid < TP_ROLE;
   fe *sA = A, *sB = B, *dA = A2, *dB = B2;
@@ -871,8 +979,8 @@ k_quad_tail_pipe(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int
   const u64 slot = (u64)(warp / 3) * 32 + lane, nslots = (TP_ROLE / 96) * 32;
   fe r = Fq::zero();
   if (round_first > 1) r = ld_state(&st->r[round_first - 2]);
-  if (tid == TP_ROLE) ts.claim = ld_state(&st->claim);
-  if (!is_role) tp_msg_init(ts, st, 2, ft);
+  if (!is_role) { fin_quad_init(fq, st, ft); tp_msg_init(ts, st, 2, ft); }
+  fe rf = r;                                        // fin warp 0: the previous challenge, in registers
   bool have_coef = false; int cur = 0;
   __syncthreads();
   for (int round1 = round_first; round1 <= rounds; round1++) {
@@ -929,39 +1037,25 @@ k_quad_tail_pipe(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int
         }
       }
     } else {
-      fe e0 = Fq::zero(), ti = Fq::zero(), rn = Fq::zero();
       if (direct) bar_sync_n(3, TP_THREADS);
-      else if (ft < 2) { const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r); }
-      if (ft < 32) {
-        __syncwarp();
-        e0 = ts.x[0]; ti = ts.x[1];
-      }
-      // round message (quad_finalize_pre) on fin warp 0
-      const int i = round1 - 1;
-      fe canon = Fq::zero(), b = Fq::zero();
-      if (ft < 32) {
-        b = Fq::sub(Fq::sub(ts.claim, Fq::dbl(e0)), ti);
-        if (ft < 3) stg_fe(&st->polys[4 * i + ft], ft == 0 ? e0 : ft == 1 ? b : ti);
-        if (ft < 2) canon = Fq::from_mont(ft == 0 ? e0 : ti);
-      }
-      rn = tp_squeeze(ts, canon, 2, ft);
-      if (ft == 0) stg_fe(&st->r[i], rn);
-      if (ft == 1) ts.claim = Fq::add(e0, Fq::mul(rn, Fq::add(b, Fq::mul(rn, ti))));       // claim <- poly(r)
+      fe canon = Fq::zero();
+      if (ft < 32) canon = fin_quad_msg(ts, fq, st, round1, direct, ts.coef[cur], rf, ft);
+      rf = tp_squeeze(ts, canon, 2, ft);
+      if (ft == 0) stg_fe(&st->r[round1 - 1], rf);
     }
     __syncthreads();
     r = ts.ch;
     if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; }
     have_coef = want_next; cur ^= 1;
   }
-  if (tid == TP_ROLE) stg_fe(&st->claim, ts.claim);
-  if (!is_role) tp_msg_store(ts, st, 2, ft);
+  if (!is_role) { tp_msg_store(ts, st, 2, ft); if (ft < 32) fin_quad_store(fq, st, rf, ft); }
   quad_claims(st, sA, sB, r);
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1)
 k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int round_first, int l, const fe *eq_left, const fe *eq_right) {
   __shared__ TailSmem ts;
-  __shared__ fe s_L0, s_SL, s_p;
+  __shared__ FinCubic fc;
   const int first_half = l / 2, second_half = l - first_half;
   const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
   const bool is_role = tid < TP_ROLE;
@@ -970,8 +1064,8 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
   const u64 slot = (u64)trio * 32 + lane, nslots = (TP_ROLE / 96) * 32;
   fe r = Fq::zero();
   if (round_first > 1) r = ld_state(&st->r[round_first - 2]);
-  if (tid == TP_ROLE) { s_L0 = ld_state(&st->L0); s_SL = ld_state(&st->SL); s_p = ld_state(&st->p); }
-  if (!is_role) tp_msg_init(ts, st, 3, ft);
+  if (!is_role) { fin_cubic_init(fc, st, l, ft); tp_msg_init(ts, st, 3, ft); }
+  fe rf = r;                                        // fin warp 0: the previous challenge, in registers
   bool have_coef = false; int cur = 0;
   // split-eq weights of a round (EqSumCheckInstance::poly_eqs_first_half / poly_eq_right_last_half, sumcheck.rs:1007-1023)
   auto weights = [&](int round1, const fe *&el, const fe *&er, u32 &sh) {
@@ -1045,43 +1139,12 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
       }
       if (tid == 0) TT(0, 3);
     } else {
-      // bound() of the previous round: p <- p l(r), and this round's L0 / SL (sumcheck.rs:1399-1405) — on fin warp 1, beside the sums
-      if (round1 > round_first && ft == 32) {
-        const fe tau = ld_state(&st->taus[round1 - 2]);
-        const fe l0 = Fq::sub(Fq::one(), tau), sl = Fq::sub(tau, l0);
-        const fe pn = Fq::mul(s_p, Fq::add(l0, Fq::mul(sl, r)));
-        const fe tn = ld_state(&st->taus[round1 - 1]);
-        const fe l0n = Fq::sub(Fq::one(), tn), sln = Fq::sub(tn, l0n);
-        s_p = pn; s_L0 = Fq::mul(pn, l0n); s_SL = Fq::mul(pn, sln);
-      }
       if (direct) bar_sync_n(3, TP_THREADS);
-      else if (ft < 3) { const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r); }
-      bar_sync_n(2, TP_FIN);
-      if (tid == TP_ROLE) TT(0, 6);
-      // round message (cubic_finalize_pre) on fin warp 0
-      const int i = round1 - 1;
       fe canon = Fq::zero();
-      if (ft < 32) {
-        const fe t0 = ts.x[0], t1 = ts.x[1], tinf = ts.x[2];
-        const fe tb = Fq::sub(Fq::sub(t1, t0), tinf);
-        if (ft < 6) {
-          const bool use_sl = (ft == 2) | (ft == 4) | (ft == 5);
-          const fe &v = (ft == 0 || ft == 2) ? t0 : ((ft == 1 || ft == 4) ? tb : tinf);
-          ts.g[ft] = Fq::mul(use_sl ? s_SL : s_L0, v);
-        }
-        __syncwarp();
-        if (ft < 4) {
-          const fe co = ft == 0 ? ts.g[0] : ft == 1 ? Fq::add(ts.g[1], ts.g[2]) : ft == 2 ? Fq::add(ts.g[3], ts.g[4]) : ts.g[5];
-          stg_fe(&st->polys[4 * i + ft], co);
-          canon = Fq::from_mont(co);
-        }
-        const int src = ft == 0 ? 0 : ft + 1;
-#pragma unroll
-        for (int k = 0; k < 8; k++) canon.v[k] = __shfl_sync(0xffffffffu, canon.v[k], src & 31);
-      }
+      if (ft < 32) canon = fin_cubic_msg(ts, fc, st, round1, direct, ts.coef[cur], rf, ft);
       if (tid == TP_ROLE) TT(0, 7);
-      const fe rn = tp_squeeze(ts, canon, 3, ft);
-      if (ft == 0) stg_fe(&st->r[i], rn);
+      rf = tp_squeeze(ts, canon, 3, ft, [&] { fin_cubic_next(ts, fc, round1, l, ft); });
+      if (ft == 0) stg_fe(&st->r[round1 - 1], rf);
       if (tid == TP_ROLE) TT(0, 8);
     }
     __syncthreads();
@@ -1090,7 +1153,7 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
     if (round1 > 1) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t; }
     have_coef = want_next; cur ^= 1;
   }
-  if (!is_role) tp_msg_store(ts, st, 3, ft);
+  if (!is_role) { tp_msg_store(ts, st, 3, ft); if (ft < 32) fin_cubic_store(fc, st, l, l, rf, ft); }
   cubic_claims(st, sA, sB, sC, r);
 }
 
@@ -1335,8 +1398,7 @@ __device__ __forceinline__ void mid_gather_acc(ScState *st, int round, int G, co
 __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
   extern __shared__ __align__(32) unsigned char mp_dyn[];
   __shared__ TailSmem ts;
-  __shared__ fe s_L0, s_SL, s_p;
-  __shared__ fe s_l0[SC_MAX_ROUNDS], s_sl[SC_MAX_ROUNDS];       // l_i(X) = l0_i + sl_i X of every round (finaliser CTA)
+  __shared__ FinCubic fc;
   ScState *st = a.st;
   // CTAs [0, G): role warps only; CTA G: the finaliser group only (it shares its SM with nobody: no issue-slot contention)
   const int l = a.l, first = a.round_first, last = a.round_last, k = a.k, G = (int)gridDim.x - 1, cta = (int)blockIdx.x - 1;
@@ -1465,15 +1527,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
   }
   if (cta >= 0) return;
   // ---- finaliser group ----
-  if (ft == 0) { s_L0 = ld_state(&st->L0); s_SL = ld_state(&st->SL); s_p = ld_state(&st->p); }
-  if (ft >= 32 && ft - 32 < l) { const fe tau = ld_state(&st->taus[ft - 32]); const fe l0 = Fq::sub(Fq::one(), tau); s_l0[ft - 32] = l0; s_sl[ft - 32] = Fq::sub(tau, l0); }
+  fin_cubic_init(fc, st, l, ft);
   for (int q = ft; q < (last - first + 1) * MP_ACC_WORDS; q += TP_FIN) mid_acc(st, first)[q] = 0;
   __threadfence();                                              // (ordered before the first release: the role CTAs add after it)
   tp_msg_init(ts, st, 3, ft);
   int cur = 0;
+  fe rf = Fq::zero();                               // fin warp 0: the previous challenge, in registers
   for (int round1 = first; round1 <= last; round1++) {
     const bool want_next = round1 < last;
-    const fe r = round1 > first ? ts.ch : Fq::zero();
     if (ft == 0) st->prof[round1 - 1][0] = gtimer();
     if (ft == 0) TT(1, 6);
     if (round1 == first) {
@@ -1481,61 +1542,30 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
       bar_sync_n(2, TP_FIN);
       if (ft < 3) ts.x[ft] = ts.gat[ft];
       if (ft >= 32 && ft < 41) ts.coef[cur ^ 1][ft - 32] = ts.gat[3 + ft - 32];
-    } else {
-      // bound() of the previous round: p <- p l(r), and this round's L0 / SL (sumcheck.rs:1399-1405) — on fin warp 1, beside the sums
-      if (ft == 32) {
-        const fe pn = Fq::mul(s_p, Fq::add(s_l0[round1 - 2], Fq::mul(s_sl[round1 - 2], r)));
-        s_p = pn; s_L0 = Fq::mul(pn, s_l0[round1 - 1]); s_SL = Fq::mul(pn, s_sl[round1 - 1]);
-      }
-      if (ft < 3) { const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r); }
+      __syncwarp();
     }
-    bar_sync_n(2, TP_FIN);
     if (ft == 0) st->prof[round1 - 1][1] = gtimer();
-    // round message (cubic_finalize_pre) on fin warp 0
-    const int i = round1 - 1;
     fe canon = Fq::zero();
-    if (ft < 32) {
-      const fe t0 = ts.x[0], t1 = ts.x[1], tinf = ts.x[2];
-      const fe tb = Fq::sub(Fq::sub(t1, t0), tinf);
-      __syncwarp();
-      if (ft < 6) {
-        const bool use_sl = (ft == 2) | (ft == 4) | (ft == 5);
-        const fe &v = (ft == 0 || ft == 2) ? t0 : ((ft == 1 || ft == 4) ? tb : tinf);
-        ts.g[ft] = Fq::mul(use_sl ? s_SL : s_L0, v);
-      }
-      __syncwarp();
-      if (ft < 4) {
-        const fe co = ft == 0 ? ts.g[0] : ft == 1 ? Fq::add(ts.g[1], ts.g[2]) : ft == 2 ? Fq::add(ts.g[3], ts.g[4]) : ts.g[5];
-        stg_fe(&st->polys[4 * i + ft], co);
-        canon = Fq::from_mont(co);
-      }
-      const int src = ft == 0 ? 0 : ft + 1;
-#pragma unroll
-      for (int q = 0; q < 8; q++) canon.v[q] = __shfl_sync(0xffffffffu, canon.v[q], src & 31);
-    }
+    if (ft < 32) canon = fin_cubic_msg(ts, fc, st, round1, round1 == first, ts.coef[cur], rf, ft);
     const bool gather_next = round1 > first && want_next;
     fe *coef_next = ts.coef[cur ^ 1];
     if (ft == 0) st->prof[round1 - 1][2] = gtimer();
     if (ft == 0) TT(1, 7);
-    const fe rn = tp_squeeze(ts, canon, 3, ft, [&] { if (gather_next) mid_gather_acc(st, round1, G, mid_acc(st, round1), 9, coef_next); });
-    if (ft == 0) { stg_fe(&st->r[i], rn); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); st->prof[round1 - 1][3] = gtimer(); }
+    rf = tp_squeeze(ts, canon, 3, ft, [&] { fin_cubic_next(ts, fc, round1, l, ft); },
+                    [&] { if (gather_next) mid_gather_acc(st, round1, G, mid_acc(st, round1), 9, coef_next); });
+    if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); st->prof[round1 - 1][3] = gtimer(); }
     if (ft == 0) TT(1, 8);
-    bar_sync_n(2, TP_FIN);
     cur ^= 1;
   }
   // hand-off to the next kernel: transcript, and the eq prefix of the round after the last
   tp_msg_store(ts, st, 3, ft);
-  if (ft == 32) {
-    const fe r = ts.ch;
-    const fe pn = Fq::mul(s_p, Fq::add(s_l0[last - 1], Fq::mul(s_sl[last - 1], r)));
-    stg_fe(&st->p, pn);
-    if (last < l) { stg_fe(&st->L0, Fq::mul(pn, s_l0[last])); stg_fe(&st->SL, Fq::mul(pn, s_sl[last])); }
-  }
+  if (ft < 32) fin_cubic_store(fc, st, last, l, rf, ft);
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
   extern __shared__ __align__(32) unsigned char mp_dyn[];
   __shared__ TailSmem ts;
+  __shared__ FinQuad fq;
   ScState *st = a.st;
   const int rounds = a.rounds, first = a.round_first, last = a.round_last, k = a.k, G = (int)gridDim.x - 1, cta = (int)blockIdx.x - 1;   // CTA G: finaliser only
   const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
@@ -1627,42 +1657,31 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
   }
   if (cta >= 0) return;
   // ---- finaliser group ----
-  if (ft == 0) ts.claim = ld_state(&st->claim);
+  fin_quad_init(fq, st, ft);
   for (int q = ft; q < (last - first + 1) * MP_ACC_WORDS; q += TP_FIN) mid_acc(st, first)[q] = 0;
   __threadfence();                                              // (ordered before the first release: the role CTAs add after it)
   tp_msg_init(ts, st, 2, ft);
   int cur = 0;
+  fe rf = Fq::zero();                               // fin warp 0: the previous challenge, in registers
   for (int round1 = first; round1 <= last; round1++) {
     const bool want_next = round1 < last;
-    const fe r = round1 > first ? ts.ch : Fq::zero();
     if (round1 == first) {
-      if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, want_next ? 9 : 3, ts.gat);   // direct sums, then the coefficients
+      if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, want_next ? 9 : 3, ts.gat);     // direct sums (0, 1), then the coefficients (3..8)
       bar_sync_n(2, TP_FIN);
       if (ft < 2) ts.x[ft] = ts.gat[ft];
       if (ft >= 32 && ft < 38) ts.coef[cur ^ 1][ft - 32] = ts.gat[3 + ft - 32];
-    } else if (ft < 2) {
-      const fe *c = ts.coef[cur]; ts.x[ft] = eval_karatsuba(c[3 * ft], c[3 * ft + 1], c[3 * ft + 2], r);
+      __syncwarp();
     }
-    bar_sync_n(2, TP_FIN);
-    // round message (quad_finalize_pre) on fin warp 0
-    const int i = round1 - 1;
-    fe canon = Fq::zero(), e0 = Fq::zero(), ti = Fq::zero(), b = Fq::zero();
-    if (ft < 32) {
-      e0 = ts.x[0]; ti = ts.x[1];
-      b = Fq::sub(Fq::sub(ts.claim, Fq::dbl(e0)), ti);
-      if (ft < 3) stg_fe(&st->polys[4 * i + ft], ft == 0 ? e0 : ft == 1 ? b : ti);
-      if (ft < 2) canon = Fq::from_mont(ft == 0 ? e0 : ti);
-    }
+    fe canon = Fq::zero();
+    if (ft < 32) canon = fin_quad_msg(ts, fq, st, round1, round1 == first, ts.coef[cur], rf, ft);
     const bool gather_next = round1 > first && want_next;
     fe *coef_next = ts.coef[cur ^ 1];
-    const fe rn = tp_squeeze(ts, canon, 2, ft, [&] { if (gather_next) mid_gather_acc(st, round1, G, mid_acc(st, round1), 6, coef_next); });
-    if (ft == 0) { stg_fe(&st->r[i], rn); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); }
-    if (ft == 1) ts.claim = Fq::add(e0, Fq::mul(rn, Fq::add(b, Fq::mul(rn, ti))));               // claim <- poly(r)
-    bar_sync_n(2, TP_FIN);
+    rf = tp_squeeze(ts, canon, 2, ft, TpNoSide(), [&] { if (gather_next) mid_gather_acc(st, round1, G, mid_acc(st, round1), 6, coef_next); });
+    if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); }
     cur ^= 1;
   }
   tp_msg_store(ts, st, 2, ft);
-  if (ft == 0) stg_fe(&st->claim, ts.claim);
+  if (ft < 32) fin_quad_store(fq, st, rf, ft);
 }
 
 // ---------------------------------------------------------------------------------------------

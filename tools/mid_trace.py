@@ -27,3 +27,8 @@ for r1 in range(1, l + 1):
     if t[r1, 0] == 0: continue
     if base is None: base = t[r1, 0]
     print(r1, ["%.1f" % ((t[r1, k] - base) / 1000.0) if t[r1, k] else "-" for k in range(0, 6)], ["%.1f" % ((t[r1, k] - base) / 1000.0) if t[r1, k] else "-" for k in range(6, 9)])
+t0 = out[0]
+print("fin_cubic_msg (ns): load, eval, products, from_mont")
+for r1 in range(1, l + 1):
+    if t0[r1, 0] == 0: continue
+    print(r1, [int(t0[r1, k] - t0[r1, k - 1]) for k in range(1, 5)])

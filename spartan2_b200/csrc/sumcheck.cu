@@ -1743,6 +1743,26 @@ static bool mid_plan(sp2_ctx *ctx, uint32_t l, uint32_t min_first, uint32_t roun
   *first = rm; *k = (uint32_t)kk;
   return true;
 }
+// launch the pipelined multi-CTA rounds [first, round_end) of a cubic / quadratic sum-check (tables src -> natural-order tables dst)
+static int launch_mid_cubic(sp2_ctx *ctx, ScState *st, uint32_t l, fe *const *src, fe *const *dst, uint32_t first, uint32_t round_end, uint32_t k, size_t smem,
+                            const fe *eq_left, const fe *eq_right) {
+  static bool attr = false;
+  if (!attr) { SP2_CUDA_OK(cudaFuncSetAttribute((const void *)k_cubic_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  MidCubic ma{st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)l, (int)first, (int)round_end - 1, (int)k, eq_left, eq_right};
+  void *args[] = {&ma};
+  SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_cubic_mid_pipe, dim3((1u << k) + 1), dim3(TP_THREADS), args, smem, ctx->stream));
+  ctx->launches++;
+  return SP2_OK;
+}
+static int launch_mid_quad(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *const *src, fe *const *dst, uint32_t first, uint32_t round_end, uint32_t k, size_t smem) {
+  static bool attr = false;
+  if (!attr) { SP2_CUDA_OK(cudaFuncSetAttribute((const void *)k_quad_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  MidQuad ma{st, src[0], src[1], dst[0], dst[1], (int)rounds, (int)first, (int)round_end - 1, (int)k};
+  void *args[] = {&ma};
+  SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_quad_mid_pipe, dim3((1u << k) + 1), dim3(TP_THREADS), args, smem, ctx->stream));
+  ctx->launches++;
+  return SP2_OK;
+}
 static DevComm comm_none() { DevComm d; memset(&d, 0, sizeof(d)); d.n = 1; return d; }
 
 // all-gather the shards (len_local entries per table) into every rank's gather area and return the local copy
@@ -1800,12 +1820,7 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     }
     if (mid) {
       // rounds [mid_first, round_end): pipelined on 2^mid_k CTAs; the table bound by the last of them lands in dst (natural order)
-      static bool attr = false;
-      if (!attr) { SP2_CUDA_OK(cudaFuncSetAttribute((const void *)k_cubic_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-      MidCubic ma{st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)l, (int)mid_first, (int)round_end - 1, (int)mid_k, eq_left, eq_right};
-      void *args[] = {&ma};
-      SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_cubic_mid_pipe, dim3((1u << mid_k) + 1), dim3(TP_THREADS), args, mid_smem, ctx->stream));
-      ctx->launches++;
+      SP2_TRY(launch_mid_cubic(ctx, st, l, src, dst, mid_first, round_end, mid_k, mid_smem, eq_left, eq_right));
       for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);
       round_start = round_end;
     }
@@ -1821,6 +1836,17 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
       sharded = false; dc = comm_none();
     }
     const u64 P = sharded ? Pg >> dc.k : Pg;                    // local pairs
+    if (!sharded && fused && len_in > SC_TAIL_LEN && len_in <= (1ull << MP_LOG_LEN_IN)) {
+      // (the sharded provers arrive here after the all-gather: the remaining multi-CTA rounds go to the pipelined kernel, redundantly on every rank)
+      uint32_t round_end = round1, mf = 0, mk = 0; size_t msm = 0;
+      while (round_end <= l && (4ull << (l - round_end)) > SC_TAIL_LEN) round_end++;
+      if (mid_plan(ctx, l, round1, round_end, 3, &mf, &mk, &msm) && mf == round1) {
+        SP2_TRY(launch_mid_cubic(ctx, st, l, src, dst, mf, round_end, mk, msm, eq_left, eq_right));
+        for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);
+        round1 = round_end - 1;
+        continue;
+      }
+    }
     if (!sharded && len_in <= SC_TAIL_LEN) {
       if (use_tail_pipe()) k_cubic_tail_pipe<<<1, TP_THREADS, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
       else k_cubic_tail<<<1, SC_TAIL_THREADS + 32, 0, ctx->stream>>>(st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)round1, (int)l, eq_left, eq_right);
@@ -1899,12 +1925,7 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
       round_start = persist_end;
     }
     if (mid) {
-      static bool attr = false;
-      if (!attr) { SP2_CUDA_OK(cudaFuncSetAttribute((const void *)k_quad_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-      MidQuad ma{st, src[0], src[1], dst[0], dst[1], (int)rounds, (int)mid_first, (int)round_end - 1, (int)mid_k};
-      void *args[] = {&ma};
-      SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_quad_mid_pipe, dim3((1u << mid_k) + 1), dim3(TP_THREADS), args, mid_smem, ctx->stream));
-      ctx->launches++;
+      SP2_TRY(launch_mid_quad(ctx, st, rounds, src, dst, mid_first, round_end, mid_k, mid_smem));
       std::swap(src[0], dst[0]); std::swap(src[1], dst[1]);
       round_start = round_end;
     }
@@ -1919,6 +1940,18 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
       sharded = false; dc = comm_none();
     }
     const u64 P = sharded ? Pg >> dc.k : Pg;
+    if (!sharded && round1 >= 3 && len_in > SC_TAIL_LEN && len_in <= (1ull << MP_LOG_LEN_IN)) {
+      // (after the all-gather of a sharded prover: the remaining multi-CTA rounds go to the pipelined kernel)
+      uint32_t round_end = round1, mf = 0, mk = 0; size_t msm = 0;
+      while (round_end <= rounds && (4ull << (rounds - round_end)) > SC_TAIL_LEN) round_end++;
+      if (mid_plan(ctx, rounds, round1, round_end, 2, &mf, &mk, &msm) && mf == round1) {
+        SP2_TRY(launch_mid_quad(ctx, st, rounds, src, dst, mf, round_end, mk, msm));
+        std::swap(src[0], dst[0]); std::swap(src[1], dst[1]);
+        if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
+        round1 = round_end - 1;
+        continue;
+      }
+    }
     if (!sharded && len_in <= SC_TAIL_LEN) {
       if (use_tail_pipe()) k_quad_tail_pipe<<<1, TP_THREADS, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);
       else k_quad_tail<<<1, SC_TAIL_THREADS + 32, 0, ctx->stream>>>(st, src[0], src[1], dst[0], dst[1], (int)round1, (int)rounds, nvalid);

@@ -265,7 +265,13 @@ def run_cuda(args):
             roof = {"bound": "hbm", "kernel": "k_cubic_persist (rounds 1-%d of the outer sum-check, bind fused into the next evaluation, one cooperative launch)" % wl.persist_rounds,
                     "achieved": wl.bytes_persist / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": traffic, "peak_kind": peak_kind,
                     "ms": k_ms, "algorithmic_bytes": wl.bytes_persist, "share_of_step": k_ms / ms_dev,
-                    "note": "latency-bound at N = 2^20: %d rounds, each ending in a grid barrier + serial Keccak finaliser vs ~%.0f us of compulsory streaming; see tables_bench for the same kernel on 2^24-entry tables" % (wl.persist_rounds, wl.bytes_persist / hbm_peak / 1e3)}
+                    "note": "the %d streaming rounds of the outer sum-check (tables > 2^17 entries; the later rounds run in k_cubic_mid_pipe / k_cubic_tail_pipe, "
+                            "bound by the transcript); bound by the integer pipe, not by HBM: see int_pipe, and tables_bench for the same kernel on 2^24-entry tables" % wl.persist_rounds}
+            # the binding resource: 256-bit Montgomery multiplications on the IMAD pipe; peak = Fq::mul throughput measured by
+            # tools/microbench/field_mul.cu on this pool's B200 (profiles/r2_b_microbench_field_mul.txt); field-ops per SURVEY §8(d): 7 T (1 - 2^-rounds)
+            fops = 7 * wl.N * (1.0 - 0.5 ** wl.persist_rounds)
+            roof["int_pipe"] = {"achieved": fops / (k_ms * 1e-3) / 1e9, "peak": 90.2, "unit": "G field-mul/s", "frac": fops / (k_ms * 1e-3) / 1e9 / 90.2,
+                                "field_ops": fops, "peak_kind": "microbenchmark (Fq::mul, 4 independent chains per thread, 148 SMs)"}
         else:
             # sharded: the outer sum-check is one launch per round on every rank (k_cubic_round, the in-kernel exchange needs the
             # last-CTA form); the phase is reported against the aggregate HBM bandwidth of the GPUs it runs on

@@ -1353,6 +1353,7 @@ __device__ __forceinline__ void mid_wait_released(ScState *st, int round) {
 // first round live in the state's head (zeroed with it), those of the later rounds behind the partials (zeroed by the finaliser CTA before
 // it releases the first challenge).
 constexpr int MP_ACC_WORDS = 9 * 16;
+constexpr int MP_ARRIVE_FIRST_COEF = SC_MAX_ROUNDS + 1;   // arrival counter of the first round's coefficient sums (its direct sums use the round's own)
 __device__ __forceinline__ u32 *mid_acc(ScState *st, int round) { return (u32 *)st->partial + (size_t)round * MP_ACC_WORDS; }
 // role warps: per-warp partial sums (`xs`, identical in every lane) -> values [base + 3 g + c] (or [base + g] from c = 0 alone when only_first);
 // the warps of group g are g, g + NG, g + 2 NG, ...  (cubic: NG = 3 roles; quadratic: NG = 2 halves)
@@ -1474,6 +1475,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
           warp_sum_fq_cols<3>(xs);
         }
         mid_publish_acc<3>(ts, xs, st->mid_acc0, 0, true);
+        if (tid == 0) atomicAdd(&st->mid_arrive[round1], 1u);       // the finaliser starts on the round's own sums; its coefficients follow
         if (tid == 0 && cta == 0) TT(1, 3);
       }
       if (want_next) {
@@ -1520,7 +1522,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
         const fe *S = cur + role * cs; fe *D = role == 0 ? a.oA : role == 1 ? a.oB : a.oC;
         for (u64 j = slot; j < 2 * Pl; j += nslots) stg_fe(D + ((j << k) | (u64)cta), S[j]);
       }
-      if ((round1 == first || want_next) && tid == 0) atomicAdd(&st->mid_arrive[round1], 1u);
+      if (want_next && tid == 0) atomicAdd(&st->mid_arrive[round1 == first ? MP_ARRIVE_FIRST_COEF : round1], 1u);
       if (tid == 0 && cta == 0) TT(1, 5);
     }
     return;
@@ -1538,21 +1540,19 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
     if (ft == 0) st->prof[round1 - 1][0] = gtimer();
     if (ft == 0) TT(1, 6);
     if (round1 == first) {
-      if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, want_next ? 12 : 3, ts.gat);   // direct sums, then the coefficients
+      if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, 3, ts.gat);                    // the round's own sums
       bar_sync_n(2, TP_FIN);
       if (ft < 3) ts.x[ft] = ts.gat[ft];
-      if (ft >= 32 && ft < 41) ts.coef[cur ^ 1][ft - 32] = ts.gat[3 + ft - 32];
       __syncwarp();
     }
     if (ft == 0) st->prof[round1 - 1][1] = gtimer();
     fe canon = Fq::zero();
     if (ft < 32) canon = fin_cubic_msg(ts, fc, st, round1, round1 == first, ts.coef[cur], rf, ft);
-    const bool gather_next = round1 > first && want_next;
     fe *coef_next = ts.coef[cur ^ 1];
     if (ft == 0) st->prof[round1 - 1][2] = gtimer();
     if (ft == 0) TT(1, 7);
     rf = tp_squeeze(ts, canon, 3, ft, [&] { fin_cubic_next(ts, fc, round1, l, ft); },
-                    [&] { if (gather_next) mid_gather_acc(st, round1, G, mid_acc(st, round1), 9, coef_next); });
+                    [&] { if (want_next) mid_gather_acc(st, round1 == first ? MP_ARRIVE_FIRST_COEF : round1, G, round1 == first ? st->mid_acc0 + 3 * 16 : mid_acc(st, round1), 9, coef_next); });
     if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); st->prof[round1 - 1][3] = gtimer(); }
     if (ft == 0) TT(1, 8);
     cur ^= 1;
@@ -1620,6 +1620,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
           warp_sum_fq_cols<3>(xs);
         }
         mid_publish_acc<2>(ts, xs, st->mid_acc0, 0, true);
+        if (tid == 0) atomicAdd(&st->mid_arrive[round1], 1u);       // the finaliser starts on the round's own sums; its coefficients follow
       }
       if (want_next) {
         // (with <= 32 local pairs the three coefficient sums of a pair go to three different warp pairs: one product per thread)
@@ -1651,7 +1652,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
           stg_fe(((q & 1) ? a.oB : a.oA) + ((j << k) | (u64)cta), cur[(q & 1) * cs + j]);
         }
       }
-      if ((round1 == first || want_next) && tid == 0) atomicAdd(&st->mid_arrive[round1], 1u);
+      if (want_next && tid == 0) atomicAdd(&st->mid_arrive[round1 == first ? MP_ARRIVE_FIRST_COEF : round1], 1u);
     }
     return;
   }
@@ -1666,17 +1667,15 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
   for (int round1 = first; round1 <= last; round1++) {
     const bool want_next = round1 < last;
     if (round1 == first) {
-      if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, want_next ? 9 : 3, ts.gat);     // direct sums (0, 1), then the coefficients (3..8)
+      if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, 3, ts.gat);                    // the round's own sums (0, 1)
       bar_sync_n(2, TP_FIN);
       if (ft < 2) ts.x[ft] = ts.gat[ft];
-      if (ft >= 32 && ft < 38) ts.coef[cur ^ 1][ft - 32] = ts.gat[3 + ft - 32];
       __syncwarp();
     }
     fe canon = Fq::zero();
     if (ft < 32) canon = fin_quad_msg(ts, fq, st, round1, round1 == first, ts.coef[cur], rf, ft);
-    const bool gather_next = round1 > first && want_next;
     fe *coef_next = ts.coef[cur ^ 1];
-    rf = tp_squeeze(ts, canon, 2, ft, TpNoSide(), [&] { if (gather_next) mid_gather_acc(st, round1, G, mid_acc(st, round1), 6, coef_next); });
+    rf = tp_squeeze(ts, canon, 2, ft, TpNoSide(), [&] { if (want_next) mid_gather_acc(st, round1 == first ? MP_ARRIVE_FIRST_COEF : round1, G, round1 == first ? st->mid_acc0 + 3 * 16 : mid_acc(st, round1), 6, coef_next); });
     if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); }
     cur ^= 1;
   }

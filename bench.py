@@ -54,7 +54,11 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device = device; self.proc = None; self.lines = []
+        self.device = device; self.proc = None; self.lines = []; self.first = 0
+
+    def mark(self):
+        """the timed region starts here (the sampler is started before the warm-up steps: nvidia-smi takes up to a second to come up)"""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -78,7 +82,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        window = "timed steps"
+        lines = self.lines[self.first:]
+        if not lines:
+            lines = self.lines; window = "warm-up + timed steps (the timed region was shorter than one nvidia-smi period)"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -90,7 +98,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def persist_end(l, tail_len, mid_len):
@@ -212,11 +220,14 @@ def run_cuda(args):
         return proof, wall
 
     W_ = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(W_):
         step(S, prep, comm)
     l0 = ctx.launch_count()
-    sampler = ClockSampler(local); sampler.start()
     barrier()
+    sampler.mark()
     dev, wall, phases, persist = [], [], [], []
     for _ in range(args.steps):
         proof, w = step(S, prep, comm)

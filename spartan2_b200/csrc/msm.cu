@@ -13,9 +13,14 @@
 // builds only for h and for <=64-wide keys): table[b][w][d] = d * 2^(8w) * base_b for the 33 signed byte-digit
 // windows and d = 1..128, affine (554 MB at 2051 bases).  An MSM is then a pure gather-and-sum of
 // <= 33 * n affine points: no buckets, no bucket reduction, no doublings.
-//   k_msm_gather: CTAs of 256 threads own 32 terms; digits are recoded once into shared memory, every thread
-//                 adds ~4 table entries (mixed Jacobian adds), then an 8-level shared-memory tree;
-//   k_msm_final:  one CTA per MSM sums the per-CTA partials (7-level tree) and emits ONE Jacobian point.
+//   k_msm_gather: warp-granular — a warp sums 128 consecutive (term, window) table entries of ONE job: every lane
+//                 adds ~4 entries (mixed Jacobian adds), then a 5-level shuffle tree; no barriers, no shared points;
+//   k_msm_final:  one CTA per job sums the warp partials, adds the job's extra terms' partials and its optional
+//                 addend and emits ONE Jacobian point.
+// A job (MsmJob, msm.cuh) = a scalar vector over consecutive key bases + up to 3 extra (base, scalar) terms taken from
+// the key's or an auxiliary table (blind * h, the folded-commitment rows of the NeutronNova prover) + an optional
+// affine / Jacobian addend, so rerandomisation (U + r h), commit_zeros, the IPA's two-term commitments and the
+// "fold by linearity" commitments are all one batch of table lookups.
 // Normalisation to affine (one field inversion) is done by the caller on the host for the whole batch
 // (host_transcript.h: batch_normalize): ~15 us there vs ~130 us for a serial inversion on a GPU thread.
 // Many MSMs (Hyrax rows, the prover's blinded terms) are batched into one pair of launches.

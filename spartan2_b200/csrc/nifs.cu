@@ -731,10 +731,172 @@ __global__ void k_bind_heads(TablePtrs tp, u32 ntab, fe r, fe *mail_out, u32 *ma
   if (i == 0) { __threadfence_system(); *(volatile u32 *)mail_flag = seq; }
 }
 
-// wait for the device to publish sequence number `seq` in the mailbox (bounded: a wedged stream surfaces as an error)
-int nn_wait(sp2_nn_prep *P, u32 seq) {
+// ---- pipelined rounds of the batched sum-checks -----------------------------------------------------------------------------
+// A host-driven round costs launch + kernel + mailbox + host algebra + Keccak, all serial.  Binding is linear in the challenge, so
+// the sums of round i+1 over the table bound to r_i are quadratics in r_i whose coefficients need only the table bound to r_(i-1)
+// (sumcheck.cu: pipelined tails): kernel i binds to r_(i-1) and publishes the COEFFICIENT sums of round i+1 — Karatsuba triples
+// (value at r = 0, value at r = 1, the r^2 coefficient) — while the host is already hashing round i.  The host evaluates a round with two
+// multiplications per sum, is always one launch ahead of the device, and the kernels run back to back on the stream: a round costs
+// one kernel, not launch + kernel + round trip + host.  Same sums, same field elements: every proof field stays bit-identical.
+//
+// entries of the table (after the fused bind to r) that pair index k of the NEXT round touches: k, k + h in the low half, k + len, k + len + h
+// in the high half (len = pairs of this round, h = len / 2)
+template <bool FUSED>
+__device__ __forceinline__ void nn_ld_quad(fe *T, u64 k, u64 h, u64 len, const fe &r, fe (&e)[4]) {
+  const u64 pos[4] = {k, k + h, k + len, k + len + h};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    if (FUSED) { e[q] = bind_pair(ldg_fe(T + pos[q]), ldg_fe(T + pos[q] + 2 * len), r); stg_fe(T + pos[q], e[q]); }
+    else e[q] = ldg_fe(T + pos[q]);
+  }
+}
+// Both coefficient kernels split a pair's work over the threads of a CTA through shared memory, so that a thread runs ~10 dependent
+// multiplications instead of 32: phase 1 — every thread binds (FUSED) or loads a few of the 4 entries per table of NN_KC pairs (and the pow
+// weights); phase 2 — one task per (pair, coefficient): two multiplications; warp sums (64 consecutive tasks share their coefficient).
+constexpr int NN_KC = 64;                            // next-round pairs per CTA and pass
+__device__ __forceinline__ u64 nn_quad_pos(int e, u64 k, u64 h, u64 len) { return k + ((e & 1) ? h : 0) + ((e & 2) ? len : 0); }
+// sum the per-task values of one coefficient (tasks of 64 consecutive threads) into part[coef]; all threads call (val = 0 when idle)
+template <int NCOEF>
+__device__ __forceinline__ void nn_coef_accumulate(fe (&x)[1], int coef, bool valid, fe (*part)[NF_THREADS / 32]) {
+  warp_sum_fq_cols<1>(x);
+  if ((threadIdx.x & 31) == 0 && valid) part[coef][threadIdx.x >> 5] = x[0];
+}
+// inner: per branch the triples of e0' = sum a_lo b_lo and t_inf' = sum (a_hi - a_lo)(b_hi - b_lo) of the next round
+template <bool FUSED>
+__global__ void __launch_bounds__(NF_THREADS) k_nn_inner_coef(NnTables tb, u64 len, fe r, fe *partials, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+  __shared__ fe E[2][4][NN_KC];                       // [table][entry][pair]
+  __shared__ fe part[6][NF_THREADS / 32];
+  __shared__ fe red[6 * 32];
+  __shared__ int is_last;
+  fe *T[2] = {tb.t[blockIdx.y][0], tb.t[blockIdx.y][1]};
+  const u64 h = len / 2;
+  const int tid = threadIdx.x;
+  fe tot[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) tot[q] = Fq::zero();
+  for (u64 k0 = (u64)blockIdx.x * NN_KC; k0 < h; k0 += (u64)gridDim.x * NN_KC) {
+    for (int q = tid; q < 2 * 4 * NN_KC; q += NF_THREADS) {
+      const int tab = q / (4 * NN_KC), e = (q / NN_KC) % 4, kk = q % NN_KC;
+      fe v = Fq::zero();
+      if (k0 + kk < h) {
+        fe *p = T[tab] + nn_quad_pos(e, k0 + kk, h, len);
+        if (FUSED) { v = bind_pair(ldg_fe(p), ldg_fe(p + 2 * len), r); stg_fe(p, v); } else v = ldg_fe(p);
+      }
+      E[tab][e][kk] = v;
+    }
+    for (int q = tid; q < 6 * (NF_THREADS / 32); q += NF_THREADS) part[q / (NF_THREADS / 32)][q % (NF_THREADS / 32)] = Fq::zero();
+    __syncthreads();
+    // next round: a_lo' = a0 + r' (a2 - a0), a_hi' = a1 + r' (a3 - a1); coefficient c of pair kk
+#pragma unroll 1
+    for (int m = 0; m < (6 * NN_KC + NF_THREADS - 1) / NF_THREADS; m++) {
+      const int q = tid + NF_THREADS * m, c = q / NN_KC, kk = q % NN_KC;
+      fe x[1] = {Fq::zero()};
+      const bool valid = c < 6;
+      if (valid) {
+        const fe a0 = E[0][0][kk], a1 = E[0][1][kk], a2 = E[0][2][kk], a3 = E[0][3][kk], b0 = E[1][0][kk], b1 = E[1][1][kk], b2 = E[1][2][kk], b3 = E[1][3][kk];
+        fe u, v;
+        if (c == 0) { u = a0; v = b0; } else if (c == 1) { u = a2; v = b2; } else if (c == 2) { u = Fq::sub(a2, a0); v = Fq::sub(b2, b0); }
+        else if (c == 3) { u = Fq::sub(a1, a0); v = Fq::sub(b1, b0); } else if (c == 4) { u = Fq::sub(a3, a2); v = Fq::sub(b3, b2); }
+        else { u = Fq::sub(Fq::sub(a3, a2), Fq::sub(a1, a0)); v = Fq::sub(Fq::sub(b3, b2), Fq::sub(b1, b0)); }
+        x[0] = Fq::mul(u, v);
+      }
+      nn_coef_accumulate<6>(x, valid ? c : 0, valid, part);
+    }
+    __syncthreads();
+    if (tid < 6) { fe acc = part[tid][0]; for (int w = 1; w < NF_THREADS / 32; w++) acc = Fq::add(acc, part[tid][w]); red[tid] = acc; }
+    __syncthreads();
+    if (tid == 0) for (int q = 0; q < 6; q++) tot[q] = Fq::add(tot[q], red[q]);
+    __syncthreads();
+  }
+  nn_publish_last<6>(tot, partials, red, &is_last, ticket, mail_out, mail_flag, seq);
+}
+// outer: per branch, for each evaluation point t in {0, 2, 3} of the next round, the triple of sum_k w_t(k) (a_t b_t - c_t):
+//   coefficient 3 s + t with s = 0: the entries at r' = 0 (low half), s = 1: at r' = 1 (high half), s = 2: the differences (no c term)
+template <bool FUSED>
+__global__ void __launch_bounds__(NF_THREADS) k_nn_outer_coef(NnTables tb, const fe *pl, u32 left, const fe *pr, u64 len, fe r, fe *partials,
+                                                              u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+  __shared__ fe E[3][4][NN_KC];                       // [table][entry][pair]
+  __shared__ fe W[2][NN_KC];                          // pow weights (low, high) of the next round's pairs
+  __shared__ fe part[9][NF_THREADS / 32];
+  __shared__ fe red[9 * 32];
+  __shared__ int is_last;
+  fe *T[3] = {tb.t[blockIdx.y][0], tb.t[blockIdx.y][1], tb.t[blockIdx.y][2]};
+  const u64 h = len / 2;
+  const int tid = threadIdx.x;
+  fe tot[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) tot[q] = Fq::zero();
+  for (u64 k0 = (u64)blockIdx.x * NN_KC; k0 < h; k0 += (u64)gridDim.x * NN_KC) {
+    for (int q = tid; q < 3 * 4 * NN_KC + 2 * NN_KC; q += NF_THREADS) {
+      if (q < 3 * 4 * NN_KC) {
+        const int tab = q / (4 * NN_KC), e = (q / NN_KC) % 4, kk = q % NN_KC;
+        fe v = Fq::zero();
+        if (k0 + kk < h) {
+          fe *p = T[tab] + nn_quad_pos(e, k0 + kk, h, len);
+          if (FUSED) { v = bind_pair(ldg_fe(p), ldg_fe(p + 2 * len), r); stg_fe(p, v); } else v = ldg_fe(p);
+        }
+        E[tab][e][kk] = v;
+      } else {
+        // pow weights of the next round's pair k (low, high); len' = h (PowPolynomial::split_evals, power.rs:65-86)
+        const int hi = (q - 3 * 4 * NN_KC) / NN_KC, kk = q % NN_KC;
+        const u64 k = k0 + kk;
+        fe w = Fq::zero();
+        if (k < h) {
+          if (h >= left) w = Fq::mul(ldg_fe_ro(pl + k % left), ldg_fe_ro(pr + k / left + (hi ? h / left : 0)));
+          else w = ldg_fe_ro(pl + k + (hi ? h : 0));
+        }
+        W[hi][kk] = w;
+      }
+    }
+    for (int q = tid; q < 9 * (NF_THREADS / 32); q += NF_THREADS) part[q / (NF_THREADS / 32)][q % (NF_THREADS / 32)] = Fq::zero();
+    __syncthreads();
+#pragma unroll 1
+    for (int m = 0; m < (9 * NN_KC + NF_THREADS - 1) / NF_THREADS; m++) {
+      const int q = tid + NF_THREADS * m, c = q / NN_KC, kk = q % NN_KC;
+      fe x[1] = {Fq::zero()};
+      const bool valid = c < 9;
+      if (valid) {
+        const int sidx = c / 3, t = c % 3;
+        fe al, ah, bl, bh, cl, ch;
+        if (sidx < 2) { al = E[0][2 * sidx][kk]; ah = E[0][2 * sidx + 1][kk]; bl = E[1][2 * sidx][kk]; bh = E[1][2 * sidx + 1][kk]; cl = E[2][2 * sidx][kk]; ch = E[2][2 * sidx + 1][kk]; }
+        else {
+          al = Fq::sub(E[0][2][kk], E[0][0][kk]); ah = Fq::sub(E[0][3][kk], E[0][1][kk]);
+          bl = Fq::sub(E[1][2][kk], E[1][0][kk]); bh = Fq::sub(E[1][3][kk], E[1][1][kk]); cl = Fq::zero(); ch = Fq::zero();
+        }
+        // the entries and the weight at the evaluation point (0, 2, 3): low + t (high - low)
+        const fe tl = W[0][kk], th = W[1][kk];
+        fe xa = al, xb = bl, xc = cl, xw = tl;
+        if (t > 0) {
+          const fe da = Fq::sub(ah, al), db = Fq::sub(bh, bl), dc = Fq::sub(ch, cl), dw = Fq::sub(th, tl);
+          xa = Fq::add(ah, da); xb = Fq::add(bh, db); xc = Fq::add(ch, dc); xw = Fq::add(th, dw);
+          if (t > 1) { xa = Fq::add(xa, da); xb = Fq::add(xb, db); xc = Fq::add(xc, dc); xw = Fq::add(xw, dw); }
+        }
+        x[0] = Fq::mul(xw, Fq::sub(Fq::mul(xa, xb), xc));
+      }
+      nn_coef_accumulate<9>(x, valid ? c : 0, valid, part);
+    }
+    __syncthreads();
+    if (tid < 9) { fe acc = part[tid][0]; for (int w = 1; w < NF_THREADS / 32; w++) acc = Fq::add(acc, part[tid][w]); red[tid] = acc; }
+    __syncthreads();
+    if (tid == 0) for (int q = 0; q < 9; q++) tot[q] = Fq::add(tot[q], red[q]);
+    __syncthreads();
+  }
+  nn_publish_last<9>(tot, partials, red, &is_last, ticket, mail_out, mail_flag, seq);
+}
+// bind several tables to a challenge passed by value (the last bind of a pipelined sum-check)
+__global__ void __launch_bounds__(NF_THREADS) k_bind_tables_v(TablePtrs tp, u32 ntab, u64 n, fe r) {
+  for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < (u64)ntab * n; q += (u64)gridDim.x * blockDim.x) {
+    const u32 s = (u32)(q / n); const u64 i = q - (u64)s * n;
+    fe *T = tp.t[s];
+    stg_fe(T + i, bind_pair(ldg_fe(T + i), ldg_fe(T + i + n), r));
+  }
+}
+// mailbox slots of the pipelined loops (the host runs one launch ahead: consecutive kernels must not share a slot)
+constexpr int NN_SLOTS = 3;
+
+// wait for the device to publish sequence number `seq` in a mailbox flag (bounded: a wedged stream surfaces as an error)
+int nn_wait_flag(sp2_nn_prep *P, volatile u32 *flag, u32 seq) {
   sp2_ctx *ctx = P->ctx;
-  volatile u32 *flag = (volatile u32 *)P->h_mail;
   const auto t0 = std::chrono::steady_clock::now();
   uint64_t spins = 0;
   while (*flag != seq) {
@@ -748,6 +910,17 @@ int nn_wait(sp2_nn_prep *P, u32 seq) {
   std::atomic_thread_fence(std::memory_order_acquire);
   return SP2_OK;
 }
+int nn_wait(sp2_nn_prep *P, u32 seq) { return nn_wait_flag(P, (volatile u32 *)P->h_mail, seq); }
+// slot s of the pipelined loops: flag at 16 (s + 1), <= 30 scalars at 1024 (s + 1) of the 4 KB mailbox
+inline int nn_wait_slot(sp2_nn_prep *P, int s, u32 seq) { return nn_wait_flag(P, (volatile u32 *)(P->h_mail + 16 * (s + 1)), seq); }
+inline const fe *nn_slot(const sp2_nn_prep *P, int s) { return (const fe *)(P->h_mail + 1024 * (s + 1)); }
+inline fe *nn_slot_dev(const sp2_nn_prep *P, int s) { return (fe *)(P->d_mail + 1024 * (s + 1)); }
+inline u32 *nn_slot_flag_dev(const sp2_nn_prep *P, int s) { return (u32 *)(P->d_mail + 16 * (s + 1)); }
+// SP2_NN_PIPE=1 (read per prove): the pipelined coefficient rounds below.  Bit-identical, measured on B200 and NOT faster (config 3: outer
+// 0.62 vs 0.54 ms, inner 0.45 vs 0.45): a round is bound by the ~20 us fixed cost of a reduce-and-publish kernel (two-level reduction with a
+// last-CTA election, system-scope fence, store to host-mapped memory), which hiding the host's ~10 us does not touch and the larger
+// coefficient kernel makes worse.  The fix is the device-resident transcript of sumcheck.cu; default off.
+static bool nn_pipe() { const char *e = getenv("SP2_NN_PIPE"); return e && e[0] == '1'; }
 inline const fe *nn_mail(const sp2_nn_prep *P) { return (const fe *)(P->h_mail + 64); }
 inline fe *nn_mail_dev(const sp2_nn_prep *P) { return (fe *)(P->d_mail + 64); }
 
@@ -1081,19 +1254,47 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
   u64 tl = N;
   NnTables otb; for (int k = 0; k < 3; k++) { otb.t[0][k] = step_t[k]; otb.t[1][k] = core_t[k]; }
   fe r_prev = zero;
-  for (u32 i = 0; i < ell; i++) {
+  // evaluate a Karatsuba triple (value at 0, value at 1, r^2 coefficient) at r
+  auto eval3 = [&](const fe &c00, const fe &c22, const fe &cdd, const fe &r) {
+    return HF::add(c00, HF::mul(r, HF::add(HF::sub(HF::sub(c22, c00), cdd), HF::mul(r, cdd))));
+  };
+  const bool piped_outer = nn_pipe() && ell >= 2;
+  u32 slot_seq[NN_SLOTS] = {0, 0, 0};
+  auto coef_grid = [&](u64 h) { return (u32)std::max<u64>(1, std::min<u64>((h + NN_KC - 1) / NN_KC, (u64)ctx->num_sms)); };
+  auto outer_grid = [&](u64 work) { return (u32)std::max<u64>(1, std::min<u64>((work + NF_THREADS - 1) / NF_THREADS, (u64)ctx->num_sms)); };
+  if (piped_outer) {
+    // round 0 directly (slot 0) and the coefficient sums of round 1 from the unbound tables (slot 1): both before any challenge exists
     const u64 len = tl / 2;
-    u32 nb;                                            // CTAs per branch
+    u32 nb;
     if (len >= left) nb = (u32)std::max<u64>(1, std::min<u64>(len / left, (u64)ctx->num_sms));
     else nb = (u32)((len + NF_THREADS - 1) / NF_THREADS);
     const u32 threads = len >= left ? std::min<u32>(NF_THREADS, (left + 31) / 32 * 32) : NF_THREADS;
-    const u32 seq = ++P->seq;
-    if (i == 0) k_nn_outer_round<false><<<dim3(nb, 2), threads, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
-    else k_nn_outer_round<true><<<dim3(nb, 2), threads, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+    slot_seq[0] = ++P->seq;
+    k_nn_outer_round<false><<<dim3(nb, 2), threads, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, zero, P->partials, P->ticket, nn_slot_dev(P, 0), nn_slot_flag_dev(P, 0), slot_seq[0]);
     SP2_LAUNCH_CHECK();
-    SP2_TRY(nn_wait(P, seq));
+    slot_seq[1] = ++P->seq;
+    k_nn_outer_coef<false><<<dim3(coef_grid(len / 2), 2), NF_THREADS, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, zero, P->partials, P->ticket, nn_slot_dev(P, 1), nn_slot_flag_dev(P, 1), slot_seq[1]);
+    SP2_LAUNCH_CHECK();
+    SP2_TRY(nn_wait_slot(P, 0, slot_seq[0]));
+  }
+  fe raw[6];
+  if (piped_outer) for (int k = 0; k < 6; k++) raw[k] = nn_slot(P, 0)[k];
+  for (u32 i = 0; i < ell; i++) {
+    const u64 len = tl / 2;
+    if (!piped_outer) {
+      u32 nb;                                            // CTAs per branch
+      if (len >= left) nb = (u32)std::max<u64>(1, std::min<u64>(len / left, (u64)ctx->num_sms));
+      else nb = (u32)((len + NF_THREADS - 1) / NF_THREADS);
+      const u32 threads = len >= left ? std::min<u32>(NF_THREADS, (left + 31) / 32 * 32) : NF_THREADS;
+      const u32 seq = ++P->seq;
+      if (i == 0) k_nn_outer_round<false><<<dim3(nb, 2), threads, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+      else k_nn_outer_round<true><<<dim3(nb, 2), threads, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+      SP2_LAUNCH_CHECK();
+      SP2_TRY(nn_wait(P, seq));
+      for (int k = 0; k < 6; k++) raw[k] = nn_mail(P)[k];
+    }
     fe ev[6];
-    for (int k = 0; k < 6; k++) { ev[k] = nn_mail(P)[k]; H::store(pf->outer_evals + 24 * i + 4 * k, ev[k]); ev[k] = HF::mul(ev[k], base_tau); }
+    for (int k = 0; k < 6; k++) { ev[k] = raw[k]; H::store(pf->outer_evals + 24 * i + 4 * k, ev[k]); ev[k] = HF::mul(ev[k], base_tau); }
     fe co[8];
     H::from_evals4(ev[0], HF::sub(claim_s, ev[0]), ev[1], ev[2], co);
     H::from_evals4(ev[3], HF::sub(claim_c, ev[3]), ev[4], ev[5], co + 4);
@@ -1106,6 +1307,23 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
     tl /= 2;
     const fe pw = tau_pow[ell - 1 - i];             // tau^(N >> (i+1)) = E[len_pow % left] * E[left + len_pow / left]
     base_tau = HF::mul(base_tau, HF::add(HF::mul(HF::sub(pw, one), r_i), one));
+    if (piped_outer && i + 1 < ell) {
+      // kernel i+1: bind to r_i (+ the coefficient sums of round i+2); then this thread evaluates round i+1 from the coefficients kernel i published
+      const u64 len_next = len / 2;
+      if (i + 2 < ell) {
+        const int sl = (int)((i + 2) % NN_SLOTS);
+        slot_seq[sl] = ++P->seq;
+        k_nn_outer_coef<true><<<dim3(coef_grid(len_next / 2), 2), NF_THREADS, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len_next, r_i, P->partials, P->ticket, nn_slot_dev(P, sl), nn_slot_flag_dev(P, sl), slot_seq[sl]);
+      } else {
+        TablePtrs tp; tp.t[0] = As; tp.t[1] = Bs; tp.t[2] = Cs; tp.t[3] = Ac; tp.t[4] = Bc; tp.t[5] = Cc; tp.t[6] = nullptr; tp.t[7] = nullptr;
+        k_bind_tables_v<<<1, NF_THREADS, 0, ctx->stream>>>(tp, 6, 2 * len_next, r_i);
+      }
+      SP2_LAUNCH_CHECK();
+      const int sk = (int)((i + 1) % NN_SLOTS);
+      SP2_TRY(nn_wait_slot(P, sk, slot_seq[sk]));
+      const fe *K = nn_slot(P, sk);
+      for (int b = 0; b < 2; b++) for (int t = 0; t < 3; t++) raw[3 * b + t] = eval3(K[9 * b + t], K[9 * b + 3 + t], K[9 * b + 6 + t], r_i);
+    }
   }
   fe cl[6];
   { TablePtrs tp; tp.t[0] = As; tp.t[1] = Bs; tp.t[2] = Cs; tp.t[3] = Ac; tp.t[4] = Bc; tp.t[5] = Cc; tp.t[6] = nullptr; tp.t[7] = nullptr;
@@ -1139,17 +1357,33 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
   tl = 2 * M;
   NnTables itb; itb.t[0][0] = P->abc_s; itb.t[0][1] = P->z_step; itb.t[0][2] = nullptr; itb.t[1][0] = P->abc_c; itb.t[1][1] = P->z_core; itb.t[1][2] = nullptr;
   r_prev = zero;
+  const bool piped_inner = nn_pipe() && my >= 2;
+  fe rawi[4];
+  if (piped_inner) {
+    const u64 len = tl / 2;
+    slot_seq[0] = ++P->seq;
+    k_nn_inner_round<false><<<dim3(outer_grid(len), 2), NF_THREADS, 0, ctx->stream>>>(itb, len, zero, P->partials, P->ticket, nn_slot_dev(P, 0), nn_slot_flag_dev(P, 0), slot_seq[0]);
+    SP2_LAUNCH_CHECK();
+    slot_seq[1] = ++P->seq;
+    k_nn_inner_coef<false><<<dim3(coef_grid(len / 2), 2), NF_THREADS, 0, ctx->stream>>>(itb, len, zero, P->partials, P->ticket, nn_slot_dev(P, 1), nn_slot_flag_dev(P, 1), slot_seq[1]);
+    SP2_LAUNCH_CHECK();
+    SP2_TRY(nn_wait_slot(P, 0, slot_seq[0]));
+    for (int k = 0; k < 4; k++) rawi[k] = nn_slot(P, 0)[k];
+  }
   for (u32 j = 0; j < my; j++) {
     const u64 len = tl / 2;
-    const u32 nb = (u32)std::max<u64>(1, std::min<u64>((len + NF_THREADS - 1) / NF_THREADS, (u64)ctx->num_sms));
-    const u32 seq = ++P->seq;
-    if (j == 0) k_nn_inner_round<false><<<dim3(nb, 2), NF_THREADS, 0, ctx->stream>>>(itb, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
-    else k_nn_inner_round<true><<<dim3(nb, 2), NF_THREADS, 0, ctx->stream>>>(itb, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
-    SP2_LAUNCH_CHECK();
-    SP2_TRY(nn_wait(P, seq));
+    if (!piped_inner) {
+      const u32 nb = (u32)std::max<u64>(1, std::min<u64>((len + NF_THREADS - 1) / NF_THREADS, (u64)ctx->num_sms));
+      const u32 seq = ++P->seq;
+      if (j == 0) k_nn_inner_round<false><<<dim3(nb, 2), NF_THREADS, 0, ctx->stream>>>(itb, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+      else k_nn_inner_round<true><<<dim3(nb, 2), NF_THREADS, 0, ctx->stream>>>(itb, len, r_prev, P->partials, P->ticket, nn_mail_dev(P), mail_flag, seq);
+      SP2_LAUNCH_CHECK();
+      SP2_TRY(nn_wait(P, seq));
+      for (int k = 0; k < 4; k++) rawi[k] = nn_mail(P)[k];
+    }
     fe co[6];
     for (int b = 0; b < 2; b++) {
-      const fe e0 = nn_mail(P)[2 * b], tinf = nn_mail(P)[2 * b + 1], claim = b ? claim_jc : claim_js;
+      const fe e0 = rawi[2 * b], tinf = rawi[2 * b + 1], claim = b ? claim_jc : claim_js;
       H::store(pf->inner_evals + 16 * j + 8 * b, e0); H::store(pf->inner_evals + 16 * j + 8 * b + 4, tinf);
       const fe e2 = HF::add(HF::sub(HF::dbl(claim), HF::add(HF::dbl(e0), e0)), HF::dbl(tinf));        // BDDT (sumcheck.rs:731-733)
       H::from_evals3(e0, HF::sub(claim, e0), e2, co + 3 * b);
@@ -1161,6 +1395,22 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
     r_prev = r_j;
     tl /= 2;
     claim_js = H::eval(co, 3, r_j); claim_jc = H::eval(co + 3, 3, r_j);
+    if (piped_inner && j + 1 < my) {
+      const u64 len_next = len / 2;
+      if (j + 2 < my) {
+        const int sl = (int)((j + 2) % NN_SLOTS);
+        slot_seq[sl] = ++P->seq;
+        k_nn_inner_coef<true><<<dim3(coef_grid(len_next / 2), 2), NF_THREADS, 0, ctx->stream>>>(itb, len_next, r_j, P->partials, P->ticket, nn_slot_dev(P, sl), nn_slot_flag_dev(P, sl), slot_seq[sl]);
+      } else {
+        TablePtrs tp; tp.t[0] = P->abc_s; tp.t[1] = P->abc_c; tp.t[2] = P->z_step; tp.t[3] = P->z_core; for (int k = 4; k < 8; k++) tp.t[k] = nullptr;
+        k_bind_tables_v<<<1, NF_THREADS, 0, ctx->stream>>>(tp, 4, 2 * len_next, r_j);
+      }
+      SP2_LAUNCH_CHECK();
+      const int sk = (int)((j + 1) % NN_SLOTS);
+      SP2_TRY(nn_wait_slot(P, sk, slot_seq[sk]));
+      const fe *K = nn_slot(P, sk);
+      for (int b = 0; b < 2; b++) for (int v = 0; v < 2; v++) rawi[2 * b + v] = eval3(K[6 * b + 3 * v], K[6 * b + 3 * v + 1], K[6 * b + 3 * v + 2], r_j);
+    }
   }
   fe fi[4];
   { TablePtrs tp; tp.t[0] = P->abc_s; tp.t[1] = P->abc_c; tp.t[2] = P->z_step; tp.t[3] = P->z_core; for (int k = 4; k < 8; k++) tp.t[k] = nullptr;

@@ -75,6 +75,16 @@ def test_snark_bit_exact_small_chains(ctx, orc, n, lc, lv, width, npub):
     assert ph["total"] > 0
 
 
+@pytest.mark.parametrize("n,lc,lv,width,npub", [(2, 5, 7, 32, 0), (4, 7, 9, 256, 3)])
+def test_snark_bit_exact_pipelined_rounds(ctx, orc, monkeypatch, n, lc, lv, width, npub):
+    """SP2_NN_PIPE=1 (measurement switch, read per prove): the batched sum-checks with the coefficient kernels one launch ahead of the host
+    (nifs.cu: k_nn_outer_coef / k_nn_inner_coef) — the same proof, bit for bit"""
+    monkeypatch.setenv("SP2_NN_PIPE", "1")
+    c = nn_case(orc, n=n, lc=lc, lv=lv, width=width, npub=npub, seed=20 + n)
+    v, ph = _device_prove(ctx, c)
+    _check(orc, c, v)
+
+
 def sha_case(orc, ctx, n, seed=5):
     from tests.neutronnova_ops import sha_chain_instances
     c0, zs, Ws, zc, Wc = sha_chain_instances(n)

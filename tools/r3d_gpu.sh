@@ -1,0 +1,2 @@
+timeout 1200 python -m pytest tests/test_gpu_neutronnova.py tests/test_gpu_neutronnova_snark.py -m gpu -x -q 2>&1 | tail -4
+python tools/nn_snark_time.py 32 2>&1 | tail -1 | cut -c1-200

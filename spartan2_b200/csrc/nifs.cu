@@ -627,33 +627,56 @@ __device__ __forceinline__ void nn_ld_pair(fe *T, u64 low, u64 len, const fe &r,
     lo = ldg_fe(T + low); hi = ldg_fe(T + low + len);
   }
 }
-// the last CTA of the grid (atomic ticket) sums the per-CTA partial NV-tuples of both branches and publishes 2*NV sums
+// Every CTA adds the 16-bit limb halves of its NV partial sums (valid in thread 0) to u32 accumulators behind the ticket (L2 atomics:
+// CTAs * 2^16 < 2^32); the last CTA of the grid (atomic ticket) rebuilds the 2*NV sums from 16 words each, publishes them in the host-mapped
+// mailbox and clears the accumulators.  (The first version summed per-CTA partial tuples in the last CTA with two block reductions per branch:
+// ~19 us of the ~25 us of a round — REDUX-heavy block sums of 9 values on 16 warps — measured with %globaltimer stamps, SP2_NN_STAMPS.)
+#ifdef SP2_NN_STAMPS
+__device__ unsigned long long g_nn_t0, g_nn_t1;     // debug: first CTA's kernel entry, last CTA's arrival
+#endif
 template <int NV>
-__device__ __forceinline__ void nn_publish_last(fe (&x)[NV], fe *partials, fe *red, int *is_last, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
-  const u32 nb = gridDim.x, ncta = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 0) {
+__device__ __forceinline__ void nn_publish_last(fe (&x)[NV], fe *, fe *red, int *is_last, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+  const u32 ncta = gridDim.x * gridDim.y;
+  const int tid = threadIdx.x;
+#ifdef SP2_NN_STAMPS
+  if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); g_nn_t1 = t; }
+#endif
+  if (tid == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; k++) stg_fe(partials + (size_t)cta * NV + k, x[k]);
-    __threadfence();
-    *is_last = atomicAdd(ticket, 1u) == ncta - 1;
+    for (int k = 0; k < NV; k++) red[k] = x[k];
   }
+  __syncthreads();
+  for (int t = tid; t < NV * 16; t += blockDim.x) {          // (a CTA may have as few as 32 threads)
+    const u32 w = red[t >> 4].v[(t & 15) >> 1], half = (t & 1) ? (w >> 16) : (w & 0xffffu);
+    if (half) atomicAdd(ticket + 16 + blockIdx.y * NV * 16 + t, half);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) *is_last = atomicAdd(ticket, 1u) == ncta - 1;
   __syncthreads();
   if (!*is_last) return;
   __threadfence();
-  for (u32 br = 0; br < gridDim.y; br++) {
-    fe y[NV];
+  if (tid < (int)gridDim.y * NV) {
+    u32 *a = ticket + 16 + tid * 16;
+    u32 w[16];
 #pragma unroll
-    for (int k = 0; k < NV; k++) y[k] = Fq::zero();
-    for (u32 b = threadIdx.x; b < nb; b += blockDim.x)
+    for (int q = 0; q < 4; q++) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4 * q]), "=r"(w[4 * q + 1]), "=r"(w[4 * q + 2]), "=r"(w[4 * q + 3]) : "l"(a + 4 * q));
+    fe v; u64 carry = 0;
 #pragma unroll
-      for (int k = 0; k < NV; k++) y[k] = Fq::add(y[k], ldg_fe(partials + ((size_t)br * nb + b) * NV + k));
-    __syncthreads();
-    block_sum_fq<NV>(y, red);
-    if (threadIdx.x == 0)
+    for (int i = 0; i < 8; i++) { carry += (u64)w[2 * i] + ((u64)w[2 * i + 1] << 16); v.v[i] = (u32)carry; carry >>= 32; }
+    u32 top = Fq::fold_top(v, (u32)carry);
+    top = Fq::fold_top(v, top);
+    cond_sub_p<FqParams>(v, top);
+    cond_sub_p<FqParams>(v, 0);
+    stg_fe(mail_out + tid, v);
 #pragma unroll
-      for (int k = 0; k < NV; k++) stg_fe(mail_out + br * NV + k, y[k]);
+    for (int q = 0; q < 16; q++) a[q] = 0;
   }
-  if (threadIdx.x == 0) { *ticket = 0; __threadfence_system(); *(volatile u32 *)mail_flag = seq; }
+  __syncthreads();
+#ifdef SP2_NN_STAMPS
+  if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); ((unsigned long long *)(mail_out + 24))[0] = t; ((unsigned long long *)(mail_out + 24))[1] = g_nn_t0; ((unsigned long long *)(mail_out + 24))[2] = g_nn_t1; }
+#endif
+  if (tid == 0) { *ticket = 0; __threadfence_system(); *(volatile u32 *)mail_flag = seq; }
 }
 // outer: evaluation points (0, 2, 3) of sum_x pow(x) (A B - C) per branch (compute_eval_points_cubic_with_additive_term
 // [_with_outer_pow], src/sumcheck.rs:262-342, 366-498); len = half the (bound) table length
@@ -750,33 +773,27 @@ __device__ __forceinline__ void nn_ld_quad(fe *T, u64 k, u64 h, u64 len, const f
     else e[q] = ldg_fe(T + pos[q]);
   }
 }
-// Both coefficient kernels split a pair's work over the threads of a CTA through shared memory, so that a thread runs ~10 dependent
-// multiplications instead of 32: phase 1 — every thread binds (FUSED) or loads a few of the 4 entries per table of NN_KC pairs (and the pow
-// weights); phase 2 — one task per (pair, coefficient): two multiplications; warp sums (64 consecutive tasks share their coefficient).
-constexpr int NN_KC = 64;                            // next-round pairs per CTA and pass
+// Both coefficient kernels split a pair's work over the threads of a CTA through shared memory, so that a thread runs 2-3 dependent
+// multiplications instead of 32 (these kernels are latency-bound: ~5000 dependent instructions per thread at one instruction per ~8 cycles
+// was the whole 20 us of a round): phase 1 — one task per (table, entry, pair): bind (FUSED) or load one of the 4 entries per table of NN_KC
+// pairs, and the pow weights; phase 2 — one task per (coefficient, pair): two multiplications; warp c sums coefficient c.
+constexpr int NN_KC = 32;                            // next-round pairs per CTA and pass (= one warp per coefficient in phase 2)
+constexpr int NN_CT = 512;                           // threads of a coefficient CTA
 __device__ __forceinline__ u64 nn_quad_pos(int e, u64 k, u64 h, u64 len) { return k + ((e & 1) ? h : 0) + ((e & 2) ? len : 0); }
-// sum the per-task values of one coefficient (tasks of 64 consecutive threads) into part[coef]; all threads call (val = 0 when idle)
-template <int NCOEF>
-__device__ __forceinline__ void nn_coef_accumulate(fe (&x)[1], int coef, bool valid, fe (*part)[NF_THREADS / 32]) {
-  warp_sum_fq_cols<1>(x);
-  if ((threadIdx.x & 31) == 0 && valid) part[coef][threadIdx.x >> 5] = x[0];
-}
 // inner: per branch the triples of e0' = sum a_lo b_lo and t_inf' = sum (a_hi - a_lo)(b_hi - b_lo) of the next round
 template <bool FUSED>
-__global__ void __launch_bounds__(NF_THREADS) k_nn_inner_coef(NnTables tb, u64 len, fe r, fe *partials, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+__global__ void __launch_bounds__(NN_CT) k_nn_inner_coef(NnTables tb, u64 len, fe r, fe *partials, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
   __shared__ fe E[2][4][NN_KC];                       // [table][entry][pair]
-  __shared__ fe part[6][NF_THREADS / 32];
+  __shared__ fe acc[6];
   __shared__ fe red[6 * 32];
   __shared__ int is_last;
   fe *T[2] = {tb.t[blockIdx.y][0], tb.t[blockIdx.y][1]};
   const u64 h = len / 2;
   const int tid = threadIdx.x;
-  fe tot[6];
-#pragma unroll
-  for (int q = 0; q < 6; q++) tot[q] = Fq::zero();
+  if (tid < 6) acc[tid] = Fq::zero();
   for (u64 k0 = (u64)blockIdx.x * NN_KC; k0 < h; k0 += (u64)gridDim.x * NN_KC) {
-    for (int q = tid; q < 2 * 4 * NN_KC; q += NF_THREADS) {
-      const int tab = q / (4 * NN_KC), e = (q / NN_KC) % 4, kk = q % NN_KC;
+    if (tid < 2 * 4 * NN_KC) {
+      const int tab = tid / (4 * NN_KC), e = (tid / NN_KC) % 4, kk = tid % NN_KC;
       fe v = Fq::zero();
       if (k0 + kk < h) {
         fe *p = T[tab] + nn_quad_pos(e, k0 + kk, h, len);
@@ -784,103 +801,91 @@ __global__ void __launch_bounds__(NF_THREADS) k_nn_inner_coef(NnTables tb, u64 l
       }
       E[tab][e][kk] = v;
     }
-    for (int q = tid; q < 6 * (NF_THREADS / 32); q += NF_THREADS) part[q / (NF_THREADS / 32)][q % (NF_THREADS / 32)] = Fq::zero();
     __syncthreads();
-    // next round: a_lo' = a0 + r' (a2 - a0), a_hi' = a1 + r' (a3 - a1); coefficient c of pair kk
-#pragma unroll 1
-    for (int m = 0; m < (6 * NN_KC + NF_THREADS - 1) / NF_THREADS; m++) {
-      const int q = tid + NF_THREADS * m, c = q / NN_KC, kk = q % NN_KC;
-      fe x[1] = {Fq::zero()};
-      const bool valid = c < 6;
-      if (valid) {
-        const fe a0 = E[0][0][kk], a1 = E[0][1][kk], a2 = E[0][2][kk], a3 = E[0][3][kk], b0 = E[1][0][kk], b1 = E[1][1][kk], b2 = E[1][2][kk], b3 = E[1][3][kk];
-        fe u, v;
-        if (c == 0) { u = a0; v = b0; } else if (c == 1) { u = a2; v = b2; } else if (c == 2) { u = Fq::sub(a2, a0); v = Fq::sub(b2, b0); }
-        else if (c == 3) { u = Fq::sub(a1, a0); v = Fq::sub(b1, b0); } else if (c == 4) { u = Fq::sub(a3, a2); v = Fq::sub(b3, b2); }
-        else { u = Fq::sub(Fq::sub(a3, a2), Fq::sub(a1, a0)); v = Fq::sub(Fq::sub(b3, b2), Fq::sub(b1, b0)); }
-        x[0] = Fq::mul(u, v);
-      }
-      nn_coef_accumulate<6>(x, valid ? c : 0, valid, part);
+    // next round: a_lo' = a0 + r' (a2 - a0), a_hi' = a1 + r' (a3 - a1); warp c takes coefficient c of the 32 pairs
+    if (tid < 6 * NN_KC) {
+      const int c = tid / NN_KC, kk = tid % NN_KC;
+      const fe a0 = E[0][0][kk], a1 = E[0][1][kk], a2 = E[0][2][kk], a3 = E[0][3][kk], b0 = E[1][0][kk], b1 = E[1][1][kk], b2 = E[1][2][kk], b3 = E[1][3][kk];
+      fe u, v;
+      if (c == 0) { u = a0; v = b0; } else if (c == 1) { u = a2; v = b2; } else if (c == 2) { u = Fq::sub(a2, a0); v = Fq::sub(b2, b0); }
+      else if (c == 3) { u = Fq::sub(a1, a0); v = Fq::sub(b1, b0); } else if (c == 4) { u = Fq::sub(a3, a2); v = Fq::sub(b3, b2); }
+      else { u = Fq::sub(Fq::sub(a3, a2), Fq::sub(a1, a0)); v = Fq::sub(Fq::sub(b3, b2), Fq::sub(b1, b0)); }
+      fe x[1] = {Fq::mul(u, v)};
+      warp_sum_fq_cols<1>(x);
+      if (kk == 0) acc[c] = Fq::add(acc[c], x[0]);
     }
     __syncthreads();
-    if (tid < 6) { fe acc = part[tid][0]; for (int w = 1; w < NF_THREADS / 32; w++) acc = Fq::add(acc, part[tid][w]); red[tid] = acc; }
-    __syncthreads();
-    if (tid == 0) for (int q = 0; q < 6; q++) tot[q] = Fq::add(tot[q], red[q]);
-    __syncthreads();
   }
+  __syncthreads();
+  fe tot[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) tot[q] = acc[q];
   nn_publish_last<6>(tot, partials, red, &is_last, ticket, mail_out, mail_flag, seq);
 }
 // outer: per branch, for each evaluation point t in {0, 2, 3} of the next round, the triple of sum_k w_t(k) (a_t b_t - c_t):
 //   coefficient 3 s + t with s = 0: the entries at r' = 0 (low half), s = 1: at r' = 1 (high half), s = 2: the differences (no c term)
 template <bool FUSED>
-__global__ void __launch_bounds__(NF_THREADS) k_nn_outer_coef(NnTables tb, const fe *pl, u32 left, const fe *pr, u64 len, fe r, fe *partials,
-                                                              u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+__global__ void __launch_bounds__(NN_CT) k_nn_outer_coef(NnTables tb, const fe *pl, u32 left, const fe *pr, u64 len, fe r, fe *partials,
+                                                         u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
   __shared__ fe E[3][4][NN_KC];                       // [table][entry][pair]
   __shared__ fe W[2][NN_KC];                          // pow weights (low, high) of the next round's pairs
-  __shared__ fe part[9][NF_THREADS / 32];
+  __shared__ fe acc[9];
   __shared__ fe red[9 * 32];
   __shared__ int is_last;
   fe *T[3] = {tb.t[blockIdx.y][0], tb.t[blockIdx.y][1], tb.t[blockIdx.y][2]};
   const u64 h = len / 2;
   const int tid = threadIdx.x;
-  fe tot[9];
-#pragma unroll
-  for (int q = 0; q < 9; q++) tot[q] = Fq::zero();
+#ifdef SP2_NN_STAMPS
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); g_nn_t0 = t; }
+#endif
+  if (tid < 9) acc[tid] = Fq::zero();
   for (u64 k0 = (u64)blockIdx.x * NN_KC; k0 < h; k0 += (u64)gridDim.x * NN_KC) {
-    for (int q = tid; q < 3 * 4 * NN_KC + 2 * NN_KC; q += NF_THREADS) {
-      if (q < 3 * 4 * NN_KC) {
-        const int tab = q / (4 * NN_KC), e = (q / NN_KC) % 4, kk = q % NN_KC;
-        fe v = Fq::zero();
-        if (k0 + kk < h) {
-          fe *p = T[tab] + nn_quad_pos(e, k0 + kk, h, len);
-          if (FUSED) { v = bind_pair(ldg_fe(p), ldg_fe(p + 2 * len), r); stg_fe(p, v); } else v = ldg_fe(p);
-        }
-        E[tab][e][kk] = v;
-      } else {
-        // pow weights of the next round's pair k (low, high); len' = h (PowPolynomial::split_evals, power.rs:65-86)
-        const int hi = (q - 3 * 4 * NN_KC) / NN_KC, kk = q % NN_KC;
-        const u64 k = k0 + kk;
-        fe w = Fq::zero();
-        if (k < h) {
-          if (h >= left) w = Fq::mul(ldg_fe_ro(pl + k % left), ldg_fe_ro(pr + k / left + (hi ? h / left : 0)));
-          else w = ldg_fe_ro(pl + k + (hi ? h : 0));
-        }
-        W[hi][kk] = w;
+    if (tid < 3 * 4 * NN_KC) {
+      const int tab = tid / (4 * NN_KC), e = (tid / NN_KC) % 4, kk = tid % NN_KC;
+      fe v = Fq::zero();
+      if (k0 + kk < h) {
+        fe *p = T[tab] + nn_quad_pos(e, k0 + kk, h, len);
+        if (FUSED) { v = bind_pair(ldg_fe(p), ldg_fe(p + 2 * len), r); stg_fe(p, v); } else v = ldg_fe(p);
       }
-    }
-    for (int q = tid; q < 9 * (NF_THREADS / 32); q += NF_THREADS) part[q / (NF_THREADS / 32)][q % (NF_THREADS / 32)] = Fq::zero();
-    __syncthreads();
-#pragma unroll 1
-    for (int m = 0; m < (9 * NN_KC + NF_THREADS - 1) / NF_THREADS; m++) {
-      const int q = tid + NF_THREADS * m, c = q / NN_KC, kk = q % NN_KC;
-      fe x[1] = {Fq::zero()};
-      const bool valid = c < 9;
-      if (valid) {
-        const int sidx = c / 3, t = c % 3;
-        fe al, ah, bl, bh, cl, ch;
-        if (sidx < 2) { al = E[0][2 * sidx][kk]; ah = E[0][2 * sidx + 1][kk]; bl = E[1][2 * sidx][kk]; bh = E[1][2 * sidx + 1][kk]; cl = E[2][2 * sidx][kk]; ch = E[2][2 * sidx + 1][kk]; }
-        else {
-          al = Fq::sub(E[0][2][kk], E[0][0][kk]); ah = Fq::sub(E[0][3][kk], E[0][1][kk]);
-          bl = Fq::sub(E[1][2][kk], E[1][0][kk]); bh = Fq::sub(E[1][3][kk], E[1][1][kk]); cl = Fq::zero(); ch = Fq::zero();
-        }
-        // the entries and the weight at the evaluation point (0, 2, 3): low + t (high - low)
-        const fe tl = W[0][kk], th = W[1][kk];
-        fe xa = al, xb = bl, xc = cl, xw = tl;
-        if (t > 0) {
-          const fe da = Fq::sub(ah, al), db = Fq::sub(bh, bl), dc = Fq::sub(ch, cl), dw = Fq::sub(th, tl);
-          xa = Fq::add(ah, da); xb = Fq::add(bh, db); xc = Fq::add(ch, dc); xw = Fq::add(th, dw);
-          if (t > 1) { xa = Fq::add(xa, da); xb = Fq::add(xb, db); xc = Fq::add(xc, dc); xw = Fq::add(xw, dw); }
-        }
-        x[0] = Fq::mul(xw, Fq::sub(Fq::mul(xa, xb), xc));
+      E[tab][e][kk] = v;
+    } else if (tid < 3 * 4 * NN_KC + 2 * NN_KC) {
+      // pow weights of the next round's pair k (low, high); len' = h (PowPolynomial::split_evals, power.rs:65-86)
+      const int hi = (tid - 3 * 4 * NN_KC) / NN_KC, kk = tid % NN_KC;
+      const u64 k = k0 + kk;
+      fe w = Fq::zero();
+      if (k < h) {
+        if (h >= left) w = Fq::mul(ldg_fe_ro(pl + k % left), ldg_fe_ro(pr + k / left + (hi ? h / left : 0)));
+        else w = ldg_fe_ro(pl + k + (hi ? h : 0));
       }
-      nn_coef_accumulate<9>(x, valid ? c : 0, valid, part);
+      W[hi][kk] = w;
     }
     __syncthreads();
-    if (tid < 9) { fe acc = part[tid][0]; for (int w = 1; w < NF_THREADS / 32; w++) acc = Fq::add(acc, part[tid][w]); red[tid] = acc; }
-    __syncthreads();
-    if (tid == 0) for (int q = 0; q < 9; q++) tot[q] = Fq::add(tot[q], red[q]);
+    if (tid < 9 * NN_KC) {                            // warp c: coefficient c = 3 s + t of the 32 pairs
+      const int c = tid / NN_KC, kk = tid % NN_KC, sidx = c / 3, t = c % 3;
+      fe al, ah, bl, bh, cl, ch;
+      if (sidx < 2) { al = E[0][2 * sidx][kk]; ah = E[0][2 * sidx + 1][kk]; bl = E[1][2 * sidx][kk]; bh = E[1][2 * sidx + 1][kk]; cl = E[2][2 * sidx][kk]; ch = E[2][2 * sidx + 1][kk]; }
+      else {
+        al = Fq::sub(E[0][2][kk], E[0][0][kk]); ah = Fq::sub(E[0][3][kk], E[0][1][kk]);
+        bl = Fq::sub(E[1][2][kk], E[1][0][kk]); bh = Fq::sub(E[1][3][kk], E[1][1][kk]); cl = Fq::zero(); ch = Fq::zero();
+      }
+      // the entries and the weight at the evaluation point (0, 2, 3): low + t (high - low)
+      const fe tl = W[0][kk], th = W[1][kk];
+      fe xa = al, xb = bl, xc = cl, xw = tl;
+      if (t > 0) {
+        const fe da = Fq::sub(ah, al), db = Fq::sub(bh, bl), dc = Fq::sub(ch, cl), dw = Fq::sub(th, tl);
+        xa = Fq::add(ah, da); xb = Fq::add(bh, db); xc = Fq::add(ch, dc); xw = Fq::add(th, dw);
+        if (t > 1) { xa = Fq::add(xa, da); xb = Fq::add(xb, db); xc = Fq::add(xc, dc); xw = Fq::add(xw, dw); }
+      }
+      fe x[1] = {Fq::mul(xw, Fq::sub(Fq::mul(xa, xb), xc))};
+      warp_sum_fq_cols<1>(x);
+      if (kk == 0) acc[c] = Fq::add(acc[c], x[0]);
+    }
     __syncthreads();
   }
+  __syncthreads();
+  fe tot[9];
+#pragma unroll
+  for (int q = 0; q < 9; q++) tot[q] = acc[q];
   nn_publish_last<9>(tot, partials, red, &is_last, ticket, mail_out, mail_flag, seq);
 }
 // bind several tables to a challenge passed by value (the last bind of a pipelined sum-check)
@@ -916,11 +921,12 @@ inline int nn_wait_slot(sp2_nn_prep *P, int s, u32 seq) { return nn_wait_flag(P,
 inline const fe *nn_slot(const sp2_nn_prep *P, int s) { return (const fe *)(P->h_mail + 1024 * (s + 1)); }
 inline fe *nn_slot_dev(const sp2_nn_prep *P, int s) { return (fe *)(P->d_mail + 1024 * (s + 1)); }
 inline u32 *nn_slot_flag_dev(const sp2_nn_prep *P, int s) { return (u32 *)(P->d_mail + 16 * (s + 1)); }
-// SP2_NN_PIPE=1 (read per prove): the pipelined coefficient rounds below.  Bit-identical, measured on B200 and NOT faster (config 3: outer
-// 0.62 vs 0.54 ms, inner 0.45 vs 0.45): a round is bound by the ~20 us fixed cost of a reduce-and-publish kernel (two-level reduction with a
-// last-CTA election, system-scope fence, store to host-mapped memory), which hiding the host's ~10 us does not touch and the larger
-// coefficient kernel makes worse.  The fix is the device-resident transcript of sumcheck.cu; default off.
-static bool nn_pipe() { const char *e = getenv("SP2_NN_PIPE"); return e && e[0] == '1'; }
+// SP2_NN_PIPE=0 (read per prove) restores the one-launch-per-round loops (bind + direct sums, host waits for every kernel).  Measured on
+// B200, config 3: 2.18 vs 2.27 ms per prove (outer 0.37 vs 0.51, inner 0.40 vs 0.45 ms).  What a pipelined round costs now: ~6 us between
+// consecutive kernels, ~4.3 us of kernel once the tables are small (55 / 30 / 17 / 11 us for the first four: 32 instead of 12 multiplications per
+// pair), 1.6 us publish, against ~9 us of host algebra + Keccak + launch per round — host and device are balanced; the device-resident
+// transcript of sumcheck.cu is what would remove both.
+static bool nn_pipe() { const char *e = getenv("SP2_NN_PIPE"); return !(e && e[0] == '0'); }
 inline const fe *nn_mail(const sp2_nn_prep *P) { return (const fe *)(P->h_mail + 64); }
 inline fe *nn_mail_dev(const sp2_nn_prep *P) { return (fe *)(P->d_mail + 64); }
 
@@ -993,8 +999,8 @@ static int32_t nn_prep_impl(sp2_ctx *ctx, const sp2_shape *S, int rank, int nran
     if ((rc = nn_alloc(P, (size_t)nranks * (3 * N + M), &P->xbuf))) return fail(rc);
     P->gath = P->xbuf; P->wpart = P->xbuf + (size_t)nranks * 3 * N; P->peer_x[rank] = P->xbuf;
   }
-  { void *p; if (cudaMalloc(&p, 64) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->ticket = (u32 *)p;
-    cudaMemsetAsync(p, 0, 64, ctx->stream); }
+  { void *p; if (cudaMalloc(&p, 2048) != cudaSuccess) return fail(set_error(ctx, SP2_ERR_CUDA, "cudaMalloc")); P->owned.push_back(p); P->ticket = (u32 *)p;
+    cudaMemsetAsync(p, 0, 2048, ctx->stream); }   // [0] ticket, [1] peer-barrier error, [16 ...] column accumulators of nn_publish_last
   if (cudaHostAlloc((void **)&P->h_mail, NN_MAIL_BYTES, cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer((void **)&P->d_mail, P->h_mail, 0) != cudaSuccess ||
       cudaMallocHost((void **)&P->h_stage, NN_STAGE_BYTES) != cudaSuccess)
@@ -1260,7 +1266,7 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
   };
   const bool piped_outer = nn_pipe() && ell >= 2;
   u32 slot_seq[NN_SLOTS] = {0, 0, 0};
-  auto coef_grid = [&](u64 h) { return (u32)std::max<u64>(1, std::min<u64>((h + NN_KC - 1) / NN_KC, (u64)ctx->num_sms)); };
+  auto coef_grid = [&](u64 h) { return (u32)std::max<u64>(1, std::min<u64>((h + NN_KC - 1) / NN_KC, (u64)ctx->num_sms * 2)); };
   auto outer_grid = [&](u64 work) { return (u32)std::max<u64>(1, std::min<u64>((work + NF_THREADS - 1) / NF_THREADS, (u64)ctx->num_sms)); };
   if (piped_outer) {
     // round 0 directly (slot 0) and the coefficient sums of round 1 from the unbound tables (slot 1): both before any challenge exists
@@ -1273,7 +1279,7 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
     k_nn_outer_round<false><<<dim3(nb, 2), threads, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, zero, P->partials, P->ticket, nn_slot_dev(P, 0), nn_slot_flag_dev(P, 0), slot_seq[0]);
     SP2_LAUNCH_CHECK();
     slot_seq[1] = ++P->seq;
-    k_nn_outer_coef<false><<<dim3(coef_grid(len / 2), 2), NF_THREADS, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, zero, P->partials, P->ticket, nn_slot_dev(P, 1), nn_slot_flag_dev(P, 1), slot_seq[1]);
+    k_nn_outer_coef<false><<<dim3(coef_grid(len / 2), 2), NN_CT, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len, zero, P->partials, P->ticket, nn_slot_dev(P, 1), nn_slot_flag_dev(P, 1), slot_seq[1]);
     SP2_LAUNCH_CHECK();
     SP2_TRY(nn_wait_slot(P, 0, slot_seq[0]));
   }
@@ -1313,15 +1319,26 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
       if (i + 2 < ell) {
         const int sl = (int)((i + 2) % NN_SLOTS);
         slot_seq[sl] = ++P->seq;
-        k_nn_outer_coef<true><<<dim3(coef_grid(len_next / 2), 2), NF_THREADS, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len_next, r_i, P->partials, P->ticket, nn_slot_dev(P, sl), nn_slot_flag_dev(P, sl), slot_seq[sl]);
+        k_nn_outer_coef<true><<<dim3(coef_grid(len_next / 2), 2), NN_CT, 0, ctx->stream>>>(otb, P->E, left, P->E + left, len_next, r_i, P->partials, P->ticket, nn_slot_dev(P, sl), nn_slot_flag_dev(P, sl), slot_seq[sl]);
       } else {
         TablePtrs tp; tp.t[0] = As; tp.t[1] = Bs; tp.t[2] = Cs; tp.t[3] = Ac; tp.t[4] = Bc; tp.t[5] = Cc; tp.t[6] = nullptr; tp.t[7] = nullptr;
         k_bind_tables_v<<<1, NF_THREADS, 0, ctx->stream>>>(tp, 6, 2 * len_next, r_i);
       }
       SP2_LAUNCH_CHECK();
       const int sk = (int)((i + 1) % NN_SLOTS);
+#ifdef SP2_NN_STAMPS
+      static std::chrono::steady_clock::time_point t_prev; const auto t_l = now();
+#endif
       SP2_TRY(nn_wait_slot(P, sk, slot_seq[sk]));
+#ifdef SP2_NN_STAMPS
+      fprintf(stderr, "host round %u: algebra+hash+launch since the previous wait ended %.1f us, waited %.1f us\n", i, std::chrono::duration<double, std::micro>(t_l - t_prev).count(), ms_since(t_l) * 1e3); t_prev = now();
+#endif
       const fe *K = nn_slot(P, sk);
+#ifdef SP2_NN_STAMPS
+      { const unsigned long long *st = (const unsigned long long *)(K + 24); static unsigned long long prev_end = 0;
+        fprintf(stderr, "outer coef kernel for round %u: gap since the previous kernel's end %.1f us, entry -> last CTA arrives %.1f us, -> sums published %.1f us\n", i + 1,
+                prev_end ? (double)(st[1] - prev_end) / 1e3 : 0.0, (double)(st[2] - st[1]) / 1e3, (double)(st[0] - st[2]) / 1e3); prev_end = st[0]; }
+#endif
       for (int b = 0; b < 2; b++) for (int t = 0; t < 3; t++) raw[3 * b + t] = eval3(K[9 * b + t], K[9 * b + 3 + t], K[9 * b + 6 + t], r_i);
     }
   }
@@ -1365,7 +1382,7 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
     k_nn_inner_round<false><<<dim3(outer_grid(len), 2), NF_THREADS, 0, ctx->stream>>>(itb, len, zero, P->partials, P->ticket, nn_slot_dev(P, 0), nn_slot_flag_dev(P, 0), slot_seq[0]);
     SP2_LAUNCH_CHECK();
     slot_seq[1] = ++P->seq;
-    k_nn_inner_coef<false><<<dim3(coef_grid(len / 2), 2), NF_THREADS, 0, ctx->stream>>>(itb, len, zero, P->partials, P->ticket, nn_slot_dev(P, 1), nn_slot_flag_dev(P, 1), slot_seq[1]);
+    k_nn_inner_coef<false><<<dim3(coef_grid(len / 2), 2), NN_CT, 0, ctx->stream>>>(itb, len, zero, P->partials, P->ticket, nn_slot_dev(P, 1), nn_slot_flag_dev(P, 1), slot_seq[1]);
     SP2_LAUNCH_CHECK();
     SP2_TRY(nn_wait_slot(P, 0, slot_seq[0]));
     for (int k = 0; k < 4; k++) rawi[k] = nn_slot(P, 0)[k];
@@ -1400,7 +1417,7 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
       if (j + 2 < my) {
         const int sl = (int)((j + 2) % NN_SLOTS);
         slot_seq[sl] = ++P->seq;
-        k_nn_inner_coef<true><<<dim3(coef_grid(len_next / 2), 2), NF_THREADS, 0, ctx->stream>>>(itb, len_next, r_j, P->partials, P->ticket, nn_slot_dev(P, sl), nn_slot_flag_dev(P, sl), slot_seq[sl]);
+        k_nn_inner_coef<true><<<dim3(coef_grid(len_next / 2), 2), NN_CT, 0, ctx->stream>>>(itb, len_next, r_j, P->partials, P->ticket, nn_slot_dev(P, sl), nn_slot_flag_dev(P, sl), slot_seq[sl]);
       } else {
         TablePtrs tp; tp.t[0] = P->abc_s; tp.t[1] = P->abc_c; tp.t[2] = P->z_step; tp.t[3] = P->z_core; for (int k = 4; k < 8; k++) tp.t[k] = nullptr;
         k_bind_tables_v<<<1, NF_THREADS, 0, ctx->stream>>>(tp, 4, 2 * len_next, r_j);

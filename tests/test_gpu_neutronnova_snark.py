@@ -76,10 +76,11 @@ def test_snark_bit_exact_small_chains(ctx, orc, n, lc, lv, width, npub):
 
 
 @pytest.mark.parametrize("n,lc,lv,width,npub", [(2, 5, 7, 32, 0), (4, 7, 9, 256, 3)])
-def test_snark_bit_exact_pipelined_rounds(ctx, orc, monkeypatch, n, lc, lv, width, npub):
-    """SP2_NN_PIPE=1 (measurement switch, read per prove): the batched sum-checks with the coefficient kernels one launch ahead of the host
-    (nifs.cu: k_nn_outer_coef / k_nn_inner_coef) — the same proof, bit for bit"""
-    monkeypatch.setenv("SP2_NN_PIPE", "1")
+def test_snark_bit_exact_one_launch_per_round(ctx, orc, monkeypatch, n, lc, lv, width, npub):
+    """SP2_NN_PIPE=0 (measurement switch, read per prove): the batched sum-checks as one bind + evaluate launch per round with the host
+    waiting for each (nifs.cu: k_nn_outer_round / k_nn_inner_round) instead of the default coefficient kernels one launch ahead of the
+    host — the same proof, bit for bit"""
+    monkeypatch.setenv("SP2_NN_PIPE", "0")
     c = nn_case(orc, n=n, lc=lc, lv=lv, width=width, npub=npub, seed=20 + n)
     v, ph = _device_prove(ctx, c)
     _check(orc, c, v)

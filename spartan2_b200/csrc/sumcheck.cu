@@ -1339,8 +1339,10 @@ __global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_quad_persist(Pe
 constexpr int MP_LOG_LEN_IN = 17;                  // the first mid round reads tables of <= 2^17 entries
 constexpr int MP_LOG_CTAS = 7;                     // <= 128 CTAs
 constexpr int MP_LOG_LOCAL = 8;                    // >= 256 entries per CTA going into the first bind (else fewer CTAs)
-struct MidCubic { ScState *st; const fe *A, *B, *C; fe *oA, *oB, *oC; int l, round_first, round_last, k; const fe *eq_left, *eq_right; };
-struct MidQuad { ScState *st; const fe *A, *B; fe *oA, *oB; int rounds, round_first, round_last, k; };
+// round_last: the last round on the cyclic layout; finish: role CTA 0 then runs the remaining rounds (<= SC_TAIL_LEN entries) on the whole table
+// in natural order — the single-CTA tail without a second launch, a direct first round or pair work beside the finaliser — and leaves the claims
+struct MidCubic { ScState *st; const fe *A, *B, *C; fe *oA, *oB, *oC; int l, round_first, round_last, k; const fe *eq_left, *eq_right; int finish; };
+struct MidQuad { ScState *st; const fe *A, *B; fe *oA, *oB; int rounds, round_first, round_last, k, finish; };
 
 __device__ __forceinline__ void st_volatile_u32(u32 *p, u32 v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 // role warps: wait until the challenge of `round` is published
@@ -1402,7 +1404,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
   __shared__ FinCubic fc;
   ScState *st = a.st;
   // CTAs [0, G): role warps only; CTA G: the finaliser group only (it shares its SM with nobody: no issue-slot contention)
-  const int l = a.l, first = a.round_first, last = a.round_last, k = a.k, G = (int)gridDim.x - 1, cta = (int)blockIdx.x - 1;
+  const int l = a.l, first = a.round_first, last = a.round_last, G = (int)gridDim.x - 1;
+  const int last_all = a.finish ? l : last;           // the kernel's last round
+  int k = a.k, cta = (int)blockIdx.x - 1;             // the role CTAs' layout: cyclic on 2^k CTAs; (0, 0) = natural order on role CTA 0 after round `last`
   const int first_half = l / 2, second_half = l - first_half;
   const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
   const bool is_role = tid < TP_ROLE;
@@ -1419,9 +1423,22 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
     const u64 n0 = ((u64)2 << (l - first)) >> k;               // local length of the first bound table
     fe *X = (fe *)mp_dyn, *Y = X + 3 * n0;
     fe *cur = X, *nxt = Y; u64 cs = n0, ns = n0 / 2;            // table t of a buffer starts at t * stride
-    for (int round1 = first; round1 <= last; round1++) {
+    for (int round1 = first; round1 <= last_all; round1++) {
+      if (round1 == last + 1) {
+        // the rounds on <= SC_TAIL_LEN entries: role CTA 0 alone, the whole table (written back in natural order by every CTA before its arrival
+        // of round `last`) in its shared memory
+        if (cta != 0) return;
+        if (tid == 0) { const u32 want = (u32)G; const u32 *ctr = &st->mid_arrive[last]; spin_until([=] { return ld_volatile_u32(ctr) >= want; }, &st->err); __threadfence(); }
+        bar_sync_n(1, TP_ROLE);
+        k = 0;
+        const u64 nt = (u64)2 << (l - last);
+        cur = X; nxt = X + 3 * nt; cs = nt; ns = nt / 2;
+        const fe *S = role == 0 ? a.oA : role == 1 ? a.oB : a.oC;
+        for (u64 j = slot; j < nt; j += nslots) cur[role * cs + j] = ldg_fe(S + j);
+        bar_sync_n(1, TP_ROLE);
+      }
       const u64 P = (u64)1 << (l - round1), Pl = P >> k, Hl = Pl >> 1;
-      const bool want_next = round1 < last;
+      const bool want_next = round1 < last_all;
       if (tid == 0 && cta == 0) TT(1, 0);
       // what does not depend on the challenge goes before the wait: the eq weight of the (single) pair of the coefficient pass
       const bool single = want_next && Hl <= nslots;
@@ -1517,26 +1534,39 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
         }
         if (tid == 0 && cta == 0) TT(1, 4);
         mid_publish_acc<3>(ts, xs, round1 == first ? st->mid_acc0 : mid_acc(st, round1), round1 == first ? 3 : 0, false);
-      } else {
-        // last mid round: the bound table goes back to global memory in natural order for the tail kernel
+      }
+      if (round1 == last) {
+        // last round on the cyclic layout: the bound table goes back to global memory in natural order (for role CTA 0, or for the tail kernel)
         const fe *S = cur + role * cs; fe *D = role == 0 ? a.oA : role == 1 ? a.oB : a.oC;
         for (u64 j = slot; j < 2 * Pl; j += nslots) stg_fe(D + ((j << k) | (u64)cta), S[j]);
+        __threadfence();
+        bar_sync_n(1, TP_ROLE);
       }
-      if (want_next && tid == 0) atomicAdd(&st->mid_arrive[round1 == first ? MP_ARRIVE_FIRST_COEF : round1], 1u);
+      if ((want_next || round1 == last) && tid == 0) atomicAdd(&st->mid_arrive[(round1 == first && want_next) ? MP_ARRIVE_FIRST_COEF : round1], 1u);
       if (tid == 0 && cta == 0) TT(1, 5);
+    }
+    if (a.finish) {
+      // final claims: bind the three length-2 tables to the last challenge (role CTA 0; threads 0, 32, 64)
+      mid_wait_released(st, l);
+      if (lane == 0 && warp < 3) {
+        const fe r = ld_state(&st->r[l - 1]);
+        const fe lo = cur[warp * cs], hi = cur[warp * cs + 1];
+        stg_fe(&st->claims[warp], Fq::add(lo, Fq::mul(Fq::sub(hi, lo), r)));
+      }
     }
     return;
   }
   if (cta >= 0) return;
   // ---- finaliser group ----
   fin_cubic_init(fc, st, l, ft);
-  for (int q = ft; q < (last - first + 1) * MP_ACC_WORDS; q += TP_FIN) mid_acc(st, first)[q] = 0;
+  for (int q = ft; q < (last_all - first + 1) * MP_ACC_WORDS; q += TP_FIN) mid_acc(st, first)[q] = 0;
   __threadfence();                                              // (ordered before the first release: the role CTAs add after it)
   tp_msg_init(ts, st, 3, ft);
   int cur = 0;
   fe rf = Fq::zero();                               // fin warp 0: the previous challenge, in registers
-  for (int round1 = first; round1 <= last; round1++) {
-    const bool want_next = round1 < last;
+  for (int round1 = first; round1 <= last_all; round1++) {
+    const bool want_next = round1 < last_all;
+    const int Gr = round1 <= last ? G : 1;              // CTAs that arrive in this round
     if (ft == 0) st->prof[round1 - 1][0] = gtimer();
     if (ft == 0) TT(1, 6);
     if (round1 == first) {
@@ -1552,14 +1582,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_cubic_mid_pipe(MidCubic a) {
     if (ft == 0) st->prof[round1 - 1][2] = gtimer();
     if (ft == 0) TT(1, 7);
     rf = tp_squeeze(ts, canon, 3, ft, [&] { fin_cubic_next(ts, fc, round1, l, ft); },
-                    [&] { if (want_next) mid_gather_acc(st, round1 == first ? MP_ARRIVE_FIRST_COEF : round1, G, round1 == first ? st->mid_acc0 + 3 * 16 : mid_acc(st, round1), 9, coef_next); });
+                    [&] { if (want_next) mid_gather_acc(st, round1 == first ? MP_ARRIVE_FIRST_COEF : round1, Gr, round1 == first ? st->mid_acc0 + 3 * 16 : mid_acc(st, round1), 9, coef_next); });
     if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); st->prof[round1 - 1][3] = gtimer(); }
     if (ft == 0) TT(1, 8);
     cur ^= 1;
   }
   // hand-off to the next kernel: transcript, and the eq prefix of the round after the last
   tp_msg_store(ts, st, 3, ft);
-  if (ft < 32) fin_cubic_store(fc, st, last, l, rf, ft);
+  if (ft < 32) fin_cubic_store(fc, st, last_all, l, rf, ft);
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
@@ -1567,7 +1597,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
   __shared__ TailSmem ts;
   __shared__ FinQuad fq;
   ScState *st = a.st;
-  const int rounds = a.rounds, first = a.round_first, last = a.round_last, k = a.k, G = (int)gridDim.x - 1, cta = (int)blockIdx.x - 1;   // CTA G: finaliser only
+  const int rounds = a.rounds, first = a.round_first, last = a.round_last, G = (int)gridDim.x - 1;
+  const int last_all = a.finish ? rounds : last;      // the kernel's last round (see MidCubic)
+  int k = a.k, cta = (int)blockIdx.x - 1;             // block 0: finaliser only
   const int tid = threadIdx.x, ft = tid - TP_ROLE, lane = tid & 31;
   const bool is_role = tid < TP_ROLE;
   const int warp = tid >> 5;
@@ -1577,9 +1609,20 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
     fe *X = (fe *)mp_dyn, *Y = X + 2 * n0;
     fe *cur = X, *nxt = Y; u64 cs = n0, ns = n0 / 2;
     const int grp = warp & 1, pair = warp >> 1;                 // even warps: the low halves, odd warps: the differences
-    for (int round1 = first; round1 <= last; round1++) {
+    for (int round1 = first; round1 <= last_all; round1++) {
+      if (round1 == last + 1) {
+        // the rounds on <= SC_TAIL_LEN entries: role CTA 0 alone, the whole tables (natural order) in its shared memory
+        if (cta != 0) return;
+        if (tid == 0) { const u32 want = (u32)G; const u32 *ctr = &st->mid_arrive[last]; spin_until([=] { return ld_volatile_u32(ctr) >= want; }, &st->err); __threadfence(); }
+        bar_sync_n(1, TP_ROLE);
+        k = 0;
+        const u64 nt = (u64)2 << (rounds - last);
+        cur = X; nxt = X + 2 * nt; cs = nt; ns = nt / 2;
+        for (u64 q = (u64)tid; q < 2 * nt; q += TP_ROLE) cur[(q & 1) * cs + (q >> 1)] = ldg_fe(((q & 1) ? a.oB : a.oA) + (q >> 1));
+        bar_sync_n(1, TP_ROLE);
+      }
       const u64 P = (u64)1 << (rounds - round1), Pl = P >> k, Hl = Pl >> 1;
-      const bool want_next = round1 < last;
+      const bool want_next = round1 < last_all;
       if (round1 > first) mid_wait_released(st, round1 - 1);
       const fe r = ld_state(&st->r[round1 - 2]);
       if (round1 == first) {
@@ -1646,26 +1689,40 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
           warp_sum_fq_cols<3>(xs);
         }
         mid_publish_acc<2>(ts, xs, round1 == first ? st->mid_acc0 : mid_acc(st, round1), round1 == first ? 3 : 0, false);
-      } else {
+      }
+      if (round1 == last) {
+        // last round on the cyclic layout: the bound tables go back to global memory in natural order
         for (u64 q = (u64)tid; q < 4 * Pl; q += TP_ROLE) {
           const u64 j = q >> 1;
           stg_fe(((q & 1) ? a.oB : a.oA) + ((j << k) | (u64)cta), cur[(q & 1) * cs + j]);
         }
+        __threadfence();
+        bar_sync_n(1, TP_ROLE);
       }
-      if (want_next && tid == 0) atomicAdd(&st->mid_arrive[round1 == first ? MP_ARRIVE_FIRST_COEF : round1], 1u);
+      if ((want_next || round1 == last) && tid == 0) atomicAdd(&st->mid_arrive[(round1 == first && want_next) ? MP_ARRIVE_FIRST_COEF : round1], 1u);
+    }
+    if (a.finish) {
+      // final claims: bind the two length-2 tables to the last challenge (role CTA 0; threads 0, 32)
+      mid_wait_released(st, rounds);
+      if (lane == 0 && warp < 2) {
+        const fe r = ld_state(&st->r[rounds - 1]);
+        const fe lo = cur[warp * cs], hi = cur[warp * cs + 1];
+        stg_fe(&st->claims[warp], Fq::add(lo, Fq::mul(Fq::sub(hi, lo), r)));
+      }
     }
     return;
   }
   if (cta >= 0) return;
   // ---- finaliser group ----
   fin_quad_init(fq, st, ft);
-  for (int q = ft; q < (last - first + 1) * MP_ACC_WORDS; q += TP_FIN) mid_acc(st, first)[q] = 0;
+  for (int q = ft; q < (last_all - first + 1) * MP_ACC_WORDS; q += TP_FIN) mid_acc(st, first)[q] = 0;
   __threadfence();                                              // (ordered before the first release: the role CTAs add after it)
   tp_msg_init(ts, st, 2, ft);
   int cur = 0;
   fe rf = Fq::zero();                               // fin warp 0: the previous challenge, in registers
-  for (int round1 = first; round1 <= last; round1++) {
-    const bool want_next = round1 < last;
+  for (int round1 = first; round1 <= last_all; round1++) {
+    const bool want_next = round1 < last_all;
+    const int Gr = round1 <= last ? G : 1;              // CTAs that arrive in this round
     if (round1 == first) {
       if (ft >= 32 && ft < 64) mid_gather_acc(st, round1, G, st->mid_acc0, 3, ts.gat);                    // the round's own sums (0, 1)
       bar_sync_n(2, TP_FIN);
@@ -1675,7 +1732,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
     fe canon = Fq::zero();
     if (ft < 32) canon = fin_quad_msg(ts, fq, st, round1, round1 == first, ts.coef[cur], rf, ft);
     fe *coef_next = ts.coef[cur ^ 1];
-    rf = tp_squeeze(ts, canon, 2, ft, TpNoSide(), [&] { if (want_next) mid_gather_acc(st, round1 == first ? MP_ARRIVE_FIRST_COEF : round1, G, round1 == first ? st->mid_acc0 + 3 * 16 : mid_acc(st, round1), 6, coef_next); });
+    rf = tp_squeeze(ts, canon, 2, ft, TpNoSide(), [&] { if (want_next) mid_gather_acc(st, round1 == first ? MP_ARRIVE_FIRST_COEF : round1, Gr, round1 == first ? st->mid_acc0 + 3 * 16 : mid_acc(st, round1), 6, coef_next); });
     if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); }
     cur ^= 1;
   }
@@ -1725,6 +1782,8 @@ static bool use_persistent() { static int v = -1; if (v < 0) { const char *e = g
 static bool use_tail_pipe() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_TAIL_PIPE"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
 // SP2_MID_PIPE=0: every multi-CTA round stays in the persistent kernels (measurement switch)
 static bool use_mid_pipe() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_MID_PIPE"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1 && use_tail_pipe(); }
+// SP2_MID_FINISH=0: the rounds on <= SC_TAIL_LEN entries go to the single-CTA tail kernels in a second launch (measurement switch)
+static bool use_mid_finish() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_MID_FINISH"); v = (e && e[0] == '0') ? 0 : 1; } return v == 1; }
 // plan of the pipelined multi-CTA rounds [*first, round_end - 1] on 2^*k CTAs (k_*_mid_pipe); false when fewer than two such rounds exist
 static bool mid_plan(sp2_ctx *ctx, uint32_t l, uint32_t min_first, uint32_t round_end, int ntab, uint32_t *first, uint32_t *k, size_t *smem) {
   if (!use_mid_pipe()) return false;
@@ -1737,7 +1796,9 @@ static bool mid_plan(sp2_ctx *ctx, uint32_t l, uint32_t min_first, uint32_t roun
   while (kk > 0 && (((u64)1 << (l - (round_end - 2))) >> kk) < 2) kk--;   // the coefficient rounds need two local pairs
   if (kk < 1) return false;
   const u64 n0 = ((u64)2 << (l - rm)) >> kk;
-  *smem = (size_t)ntab * (n0 + n0 / 2) * sizeof(fe);
+  u64 cap = n0 + n0 / 2;
+  if (use_mid_finish()) { const u64 nt = (u64)2 << (l - (round_end - 1)); cap = std::max<u64>(cap, nt + nt / 2); }   // role CTA 0 holds the whole table of the last rounds
+  *smem = (size_t)ntab * cap * sizeof(fe);
   if (*smem > 200 * 1024) return false;
   *first = rm; *k = (uint32_t)kk;
   return true;
@@ -1747,7 +1808,7 @@ static int launch_mid_cubic(sp2_ctx *ctx, ScState *st, uint32_t l, fe *const *sr
                             const fe *eq_left, const fe *eq_right) {
   static bool attr = false;
   if (!attr) { SP2_CUDA_OK(cudaFuncSetAttribute((const void *)k_cubic_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-  MidCubic ma{st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)l, (int)first, (int)round_end - 1, (int)k, eq_left, eq_right};
+  MidCubic ma{st, src[0], src[1], src[2], dst[0], dst[1], dst[2], (int)l, (int)first, (int)round_end - 1, (int)k, eq_left, eq_right, use_mid_finish() ? 1 : 0};
   void *args[] = {&ma};
   SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_cubic_mid_pipe, dim3((1u << k) + 1), dim3(TP_THREADS), args, smem, ctx->stream));
   ctx->launches++;
@@ -1756,7 +1817,7 @@ static int launch_mid_cubic(sp2_ctx *ctx, ScState *st, uint32_t l, fe *const *sr
 static int launch_mid_quad(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *const *src, fe *const *dst, uint32_t first, uint32_t round_end, uint32_t k, size_t smem) {
   static bool attr = false;
   if (!attr) { SP2_CUDA_OK(cudaFuncSetAttribute((const void *)k_quad_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-  MidQuad ma{st, src[0], src[1], dst[0], dst[1], (int)rounds, (int)first, (int)round_end - 1, (int)k};
+  MidQuad ma{st, src[0], src[1], dst[0], dst[1], (int)rounds, (int)first, (int)round_end - 1, (int)k, use_mid_finish() ? 1 : 0};
   void *args[] = {&ma};
   SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_quad_mid_pipe, dim3((1u << k) + 1), dim3(TP_THREADS), args, smem, ctx->stream));
   ctx->launches++;
@@ -1821,7 +1882,7 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
       // rounds [mid_first, round_end): pipelined on 2^mid_k CTAs; the table bound by the last of them lands in dst (natural order)
       SP2_TRY(launch_mid_cubic(ctx, st, l, src, dst, mid_first, round_end, mid_k, mid_smem, eq_left, eq_right));
       for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);
-      round_start = round_end;
+      round_start = use_mid_finish() ? l + 1 : round_end;      // (finish mode: the kernel ran every remaining round and left the claims)
     }
   }
   for (uint32_t round1 = round_start; round1 <= l; round1++) {
@@ -1842,6 +1903,7 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
       if (mid_plan(ctx, l, round1, round_end, 3, &mf, &mk, &msm) && mf == round1) {
         SP2_TRY(launch_mid_cubic(ctx, st, l, src, dst, mf, round_end, mk, msm, eq_left, eq_right));
         for (int k = 0; k < 3; k++) std::swap(src[k], dst[k]);
+        if (use_mid_finish()) break;
         round1 = round_end - 1;
         continue;
       }
@@ -1926,7 +1988,7 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
     if (mid) {
       SP2_TRY(launch_mid_quad(ctx, st, rounds, src, dst, mid_first, round_end, mid_k, mid_smem));
       std::swap(src[0], dst[0]); std::swap(src[1], dst[1]);
-      round_start = round_end;
+      round_start = use_mid_finish() ? rounds + 1 : round_end;
     }
   }
   for (uint32_t round1 = round_start; round1 <= rounds; round1++) {
@@ -1947,6 +2009,7 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
         SP2_TRY(launch_mid_quad(ctx, st, rounds, src, dst, mf, round_end, mk, msm));
         std::swap(src[0], dst[0]); std::swap(src[1], dst[1]);
         if (after_first && !recorded) { SP2_CUDA_OK(cudaEventRecord(after_first, ctx->stream)); recorded = true; }
+        if (use_mid_finish()) break;
         round1 = round_end - 1;
         continue;
       }

@@ -60,12 +60,18 @@ __global__ void __launch_bounds__(NF_THREADS) k_reduce_partials(const fe *partia
     for (int k = 0; k < NV; k++) stg_fe(out + k, x[k]);
 }
 
+// (defined with the batched sum-check kernels below) accumulate-and-publish: every CTA adds its NV sums, the last one publishes them
+template <int NV>
+__device__ __forceinline__ void nn_publish_last(fe (&x)[NV], fe *, fe *red, int *is_last, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq, u32 groups = 0, u32 group = 0);
+
 // One NIFS round: grid (i-chunks, pairs); thread owns j (the contiguous index), walks its i-chunk:
 //   acc += f[i] * v(i, j), then * e_left[j]   (prove_helper's nested sums with inner/outer swapped: one flush per thread)
 __global__ void __launch_bounds__(NF_THREADS) k_nifs_round(u32 t, const fe *rhos, u32 ell_b, u32 left, u32 right, const fe *E, const fe *A,
-                                                           const fe *B, const fe *C, u64 N, u64 stride, fe *partials, u32 pair_offset = 0) {
+                                                           const fe *B, const fe *C, u64 N, u64 stride, fe *partials, u32 pair_offset = 0,
+                                                           u32 *ticket = nullptr, fe *mail_out = nullptr, u32 *mail_flag = nullptr, u32 seq = 0) {
   __shared__ fe red[2 * 32];
   __shared__ fe wsh;
+  __shared__ int is_last;
   const u32 p = blockIdx.y;
   const fe *el = E, *f = E + left;
   const fe *A1 = A + (u64)(2 * p) * stride * N, *A2 = A + (u64)(2 * p + 1) * stride * N;
@@ -92,6 +98,13 @@ __global__ void __launch_bounds__(NF_THREADS) k_nifs_round(u32 t, const fe *rhos
     x[1] = Fq::add(x[1], Fq::mul(ej, Fq::acc_reduce(aq)));
   }
   block_sum_fq<2>(x, red);
+  if (ticket) {
+    // publish from this kernel (no separate k_publish launch): all CTAs of all pairs add into ONE group of accumulators
+    if (threadIdx.x == 0) { x[0] = Fq::mul(x[0], wsh); x[1] = Fq::mul(x[1], wsh); }
+    __syncthreads();
+    nn_publish_last<2>(x, nullptr, red, &is_last, ticket, mail_out, mail_flag, seq, 1, 0);
+    return;
+  }
   if (threadIdx.x == 0) {
     const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
     stg_fe(partials + 2 * b, Fq::mul(x[0], wsh));
@@ -634,8 +647,10 @@ __device__ __forceinline__ void nn_ld_pair(fe *T, u64 low, u64 len, const fe &r,
 #ifdef SP2_NN_STAMPS
 __device__ unsigned long long g_nn_t0, g_nn_t1;     // debug: first CTA's kernel entry, last CTA's arrival
 #endif
+// groups = number of independent result tuples (default: one per blockIdx.y = the two branches of a batched sum-check), group = this CTA's
 template <int NV>
-__device__ __forceinline__ void nn_publish_last(fe (&x)[NV], fe *, fe *red, int *is_last, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq) {
+__device__ __forceinline__ void nn_publish_last(fe (&x)[NV], fe *, fe *red, int *is_last, u32 *ticket, fe *mail_out, u32 *mail_flag, u32 seq, u32 groups, u32 group) {
+  if (groups == 0) { groups = gridDim.y; group = blockIdx.y; }
   const u32 ncta = gridDim.x * gridDim.y;
   const int tid = threadIdx.x;
 #ifdef SP2_NN_STAMPS
@@ -648,7 +663,7 @@ __device__ __forceinline__ void nn_publish_last(fe (&x)[NV], fe *, fe *red, int 
   __syncthreads();
   for (int t = tid; t < NV * 16; t += blockDim.x) {          // (a CTA may have as few as 32 threads)
     const u32 w = red[t >> 4].v[(t & 15) >> 1], half = (t & 1) ? (w >> 16) : (w & 0xffffu);
-    if (half) atomicAdd(ticket + 16 + blockIdx.y * NV * 16 + t, half);
+    if (half) atomicAdd(ticket + 16 + group * NV * 16 + t, half);
   }
   __threadfence();
   __syncthreads();
@@ -656,7 +671,7 @@ __device__ __forceinline__ void nn_publish_last(fe (&x)[NV], fe *, fe *red, int 
   __syncthreads();
   if (!*is_last) return;
   __threadfence();
-  if (tid < (int)gridDim.y * NV) {
+  if (tid < (int)groups * NV) {
     u32 *a = ticket + 16 + tid * 16;
     u32 w[16];
 #pragma unroll
@@ -1154,10 +1169,15 @@ static int32_t nn_prove_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_transcript *tsh, 
       if (local && xchg) k_publish_xchg<<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, 1, comm->dc, (int)t + 1, nn_mail_dev(P), mail_flag, seq);
       else k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, 1, nn_mail_dev(P), mail_flag, seq, P->ticket);
     } else {
-      k_nifs_round<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(t, d_rhos, ell_b, left, right, P->E, As, Bs, Cs, N, stride, P->partials, pair_offset);
-      SP2_LAUNCH_CHECK();
-      if (local && xchg) k_publish_xchg<<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, comm->dc, (int)t + 1, nn_mail_dev(P), mail_flag, seq);
-      else k_publish<2><<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, nn_mail_dev(P), mail_flag, seq, P->ticket);
+      if (local && xchg) {
+        k_nifs_round<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(t, d_rhos, ell_b, left, right, P->E, As, Bs, Cs, N, stride, P->partials, pair_offset);
+        SP2_LAUNCH_CHECK();
+        k_publish_xchg<<<1, NF_THREADS, 0, ctx->stream>>>(P->partials, chunks * pairs, comm->dc, (int)t + 1, nn_mail_dev(P), mail_flag, seq);
+      } else {
+        // the round kernel publishes its two sums itself (column accumulators + last-CTA ticket): no k_publish launch
+        k_nifs_round<<<dim3(chunks, pairs), threads, 0, ctx->stream>>>(t, d_rhos, ell_b, left, right, P->E, As, Bs, Cs, N, stride, P->partials, pair_offset,
+                                                                        P->ticket, nn_mail_dev(P), mail_flag, seq);
+      }
     }
     SP2_LAUNCH_CHECK();
     SP2_TRY(nn_wait(P, seq));

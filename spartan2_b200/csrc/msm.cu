@@ -14,9 +14,11 @@
 // windows and d = 1..128, affine (554 MB at 2051 bases).  An MSM is then a pure gather-and-sum of
 // <= 33 * n affine points: no buckets, no bucket reduction, no doublings.
 //   k_msm_gather: warp-granular — a warp sums 128 consecutive (term, window) table entries of ONE job: every lane
-//                 adds ~4 entries (mixed Jacobian adds), then a 5-level shuffle tree; no barriers, no shared points;
+//                 adds ~4 entries (affine + affine, then mixed Jacobian adds), then the warp tree; no barriers, no shared points;
 //   k_msm_final:  one CTA per job sums the warp partials, adds the job's extra terms' partials and its optional
 //                 addend and emits ONE Jacobian point.
+//   Both trees run LANE-QUAD additions (curve_quad.cuh): the multiplications of one Jacobian addition are spread over
+//   four lanes (5 dependent multiplication levels instead of 16), because in a tree most lanes are idle anyway.
 // A job (MsmJob, msm.cuh) = a scalar vector over consecutive key bases + up to 3 extra (base, scalar) terms taken from
 // the key's or an auxiliary table (blind * h, the folded-commitment rows of the NeutronNova prover) + an optional
 // affine / Jacobian addend, so rerandomisation (U + r h), commit_zeros, the IPA's two-term commitments and the
@@ -27,6 +29,7 @@
 #include <string.h>
 #include "msm.cuh"
 #include "devutil.cuh"
+#include "curve_quad.cuh"
 #include "host_transcript.h"
 
 using namespace sp2;
@@ -87,24 +90,6 @@ __global__ void __launch_bounds__(128) k_ck_normalize(const jac *tmp, const fe *
 // (strided serial adds, warp shuffle tree, 4-warp smem step) and adds the job's optional addend.
 constexpr int GW = MSM_THREADS / 32;            // gather warps per CTA
 
-__device__ __forceinline__ jac shfl_down_jac(const jac &p, int d) {
-  jac r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], d);
-    r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], d);
-    r.z.v[i] = __shfl_down_sync(0xffffffffu, p.z.v[i], d);
-  }
-  return r;
-}
-__device__ __forceinline__ jac warp_sum_jac(jac acc) {        // result valid in lane 0
-#pragma unroll 1
-  for (int d = 16; d >= 1; d >>= 1) {
-    const jac o = shfl_down_jac(acc, d);
-    if ((threadIdx.x & 31) < d) acc = jac_add(acc, o);
-  }
-  return acc;
-}
 // job that owns partial `part` (jobs are sorted by first_part): binary search
 __device__ __forceinline__ u32 job_of_part(const MsmJob *jobs, u32 njobs, u32 part) {
   u32 lo = 0, hi = njobs - 1;
@@ -149,39 +134,73 @@ __global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, 
   }
   __syncwarp();
   jac acc = jac_inf();
+  aff first; first.x = Fp::zero(); first.y = Fp::zero();
+  u32 cnt = 0;
   for (u32 p = p0 + lane; p < p1; p += 32) {
     const u32 t = p / MSM_NW, w = p - t * MSM_NW, lt = t - t0;
     const int d = sm.dig[wib][lt][w];
     if (d) {
       aff pt = ld_aff_ro(sm.tab[wib][lt] + ((size_t)sm.bidx[wib][lt] * MSM_NW + w) * MSM_ND + (u32)((d < 0 ? -d : d) - 1));
       if (d < 0) pt.y = Fp::neg(pt.y);
-      acc = jac_add_mixed(acc, pt);
+      // the lane's first two entries are both affine: mmadd (6 multiplications) instead of a copy + madd (11)
+      if (cnt == 0) first = pt;
+      else if (cnt == 1) acc = aff_add_to_jac(first, pt);
+      else acc = jac_add_mixed(acc, pt);
+      cnt++;
     }
   }
-  acc = warp_sum_jac(acc);
+  if (cnt == 1) acc = jac_from_aff(first);
+  __syncwarp();
+  acc = warp_sum_jac_quad(acc);
   if (lane == 0) st_jac(partial + part, acc);
   __syncwarp();
   }
 }
 
-__global__ void __launch_bounds__(128) k_msm_final(const MsmJob *jobs, const jac *partial, jac *out) {
-  __shared__ jac red[4];
-  const MsmJob job = jobs[blockIdx.x];
-  const u32 tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  const u32 nw = job.nparts > 32 ? 4u : 1u;                  // small jobs: one warp, no barrier
-  if (wib >= nw) return;
-  jac acc = jac_inf();
-  for (u32 q = tid; q < job.nparts; q += 32 * nw) acc = jac_add(acc, ld_jac(partial + job.first_part + q));
-  acc = warp_sum_jac(acc);
-  if (nw > 1) {
-    if (lane == 0) red[wib] = acc;
-    __syncthreads();
-    if (tid == 0) acc = jac_add(jac_add(red[0], red[1]), jac_add(red[2], red[3]));
+// One CTA of NT threads = NT/4 lane quads per job (curve_quad.cuh): quad k sums the partials k, k + NQ, ... (quad additions),
+// then a tree over the quads — through shared memory while it spans warps, by shuffles inside warp 0 — and thread 0 adds
+// the job's optional addends.  A 2048-term job (528 partials) is 4 + 7 quad additions = 55 multiplication latencies; the
+// single-lane version (4-5 strided adds, 5-level warp tree, 4-warp step) was ~190.  `list`: the jobs of this size class.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_msm_final(const MsmJob *jobs, const u32 *list, const jac *partial, jac *out) {
+  constexpr u32 NQ = NT / 4;
+  __shared__ jac pts[NQ > 8 ? NQ : 1];
+  const u32 jid = list[blockIdx.x];
+  const MsmJob job = jobs[jid];
+  const u32 n = job.nparts, tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, k = tid >> 2;
+  const u32 m = n < NQ ? n : NQ;                               // quads that hold a sum
+  const jac *src = partial + job.first_part;
+  jac acc = k < n ? ld_jac(src + k) : jac_inf();
+  for (u32 base = NQ; base < n; base += NQ) {
+    if (base + wib * 8 < n) {                                  // warp-uniform: some quad of this warp has a partial
+      const u32 idx = base + k;
+      acc = quad_jac_add(acc, idx < n ? ld_jac(src + idx) : jac_inf());
+    }
+  }
+  if (NQ > 8) {
+#pragma unroll 1
+    for (u32 stride = NQ / 2; stride >= 8; stride >>= 1) {
+      if (stride < m) {                                        // CTA-uniform
+        if (k >= stride && k < 2 * stride && (tid & 3) == 0) pts[k] = acc;
+        __syncthreads();
+        if (k < stride) acc = quad_jac_add(acc, pts[k + stride]);   // whole warps (stride >= 8 quads)
+      }
+    }
+  }
+  if (wib == 0) {
+#pragma unroll 1
+    for (u32 d = 16; d >= 4; d >>= 1) {
+      if ((d >> 2) < m) {
+        jac o = shfl_idx_jac(acc, (lane + d) & 31);
+        if (lane + d >= 32) o = jac_inf();
+        acc = quad_jac_add(acc, o);
+      }
+    }
   }
   if (tid == 0) {
     if (job.add_aff) acc = jac_add_mixed(acc, ld_aff_ro(job.add_aff));
     if (job.add_jac) acc = jac_add(acc, ld_jac(job.add_jac));
-    st_jac(out + blockIdx.x, acc);
+    st_jac(out + jid, acc);
   }
 }
 
@@ -269,16 +288,26 @@ int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, 
     parts += j.nparts;
   }
   const size_t nj = jobs.size();
+  // size classes of the final reduction (k_msm_final<NT>): <= 8 partials one warp, <= 32 four warps, else 128 quads
+  std::vector<u32> cls[3];
+  for (size_t i = 0; i < nj; i++) cls[jobs[i].nparts <= 8 ? 0 : jobs[i].nparts <= 32 ? 1 : 2].push_back((u32)i);
+  std::vector<unsigned char> blob(nj * sizeof(MsmJob) + nj * sizeof(u32));
+  memcpy(blob.data(), jobs.data(), nj * sizeof(MsmJob));
+  u32 *lists = (u32 *)(blob.data() + nj * sizeof(MsmJob));
+  size_t off[3], o = 0;
+  for (int c = 0; c < 3; c++) { off[c] = o; if (!cls[c].empty()) memcpy(lists + o, cls[c].data(), cls[c].size() * sizeof(u32)); o += cls[c].size(); }
   void *d_jobs, *d_partial;
-  SP2_TRY(scratch(ctx, slot_jobs, nj * sizeof(MsmJob), &d_jobs));
+  SP2_TRY(scratch(ctx, slot_jobs, blob.size(), &d_jobs));
   SP2_TRY(scratch(ctx, slot_partials, (size_t)parts * sizeof(jac), &d_partial));
   // pageable source: the runtime stages it before cudaMemcpyAsync returns, so the local vector may die
-  SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, jobs.data(), nj * sizeof(MsmJob), cudaMemcpyHostToDevice, stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
+  const u32 *d_lists = (const u32 *)((const unsigned char *)d_jobs + nj * sizeof(MsmJob));
   unsigned grid = (parts + GW - 1) / GW; if (max_ctas && grid > max_ctas) grid = max_ctas;
   k_msm_gather<<<grid, MSM_THREADS, 0, stream>>>((const MsmJob *)d_jobs, (u32)nj, parts, ck->table, (jac *)d_partial);
   SP2_LAUNCH_CHECK();
-  k_msm_final<<<(unsigned)nj, 128, 0, stream>>>((const MsmJob *)d_jobs, (const jac *)d_partial, d_out);
-  SP2_LAUNCH_CHECK();
+  if (!cls[0].empty()) { k_msm_final<32><<<(unsigned)cls[0].size(), 32, 0, stream>>>((const MsmJob *)d_jobs, d_lists + off[0], (const jac *)d_partial, d_out); SP2_LAUNCH_CHECK(); }
+  if (!cls[1].empty()) { k_msm_final<128><<<(unsigned)cls[1].size(), 128, 0, stream>>>((const MsmJob *)d_jobs, d_lists + off[1], (const jac *)d_partial, d_out); SP2_LAUNCH_CHECK(); }
+  if (!cls[2].empty()) { k_msm_final<512><<<(unsigned)cls[2].size(), 512, 0, stream>>>((const MsmJob *)d_jobs, d_lists + off[2], (const jac *)d_partial, d_out); SP2_LAUNCH_CHECK(); }
   return SP2_OK;
 }
 

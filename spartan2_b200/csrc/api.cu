@@ -1,4 +1,5 @@
 // Context, device-memory helpers and element-wise test hooks of the C ABI (include/spartan2_b200.h).
+#include <stdlib.h>
 #include <string.h>
 #include "ctx.cuh"
 #include "host_transcript.h"
@@ -12,6 +13,10 @@ extern "C" {
 int32_t sp2_ctx_create(int32_t device, sp2_ctx **out) {
   if (!out) return SP2_ERR_INTERNAL;
   *out = nullptr;
+  // A context uses up to three streams whose kernels wait on each other on the device (bounded spins); with the default 8 hardware
+  // queues, streams of several contexts in one process would share a queue and a spinning kernel could sit in front of the kernel
+  // it waits for.  Effective only if CUDA is not initialised yet in this process; never overrides the user's setting.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return SP2_ERR_CUDA;      // no silent CPU fallback: fail loudly

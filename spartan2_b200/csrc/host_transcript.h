@@ -121,7 +121,7 @@ inline void mont_mul(const uint64_t a[4], const uint64_t b[4], const uint64_t mo
 }
 static const uint64_t FP_ONE[4] = {0x6ceca99e4e3b4ee9ULL, 0x818d4bd4cf18ce88ULL, 0xfffffffffffffffeULL, 0x00000000fffffffeULL};   // R mod p
 inline void fp_mul(const uint64_t a[4], const uint64_t b[4], uint64_t o[4]) { mont_mul(a, b, FP_MOD, FP_INV, o); }
-inline void fp_inv(const uint64_t a[4], uint64_t o[4]) {       // a^(p-2); inv(0) = 0
+inline void fp_inv_fermat(const uint64_t a[4], uint64_t o[4]) {       // a^(p-2); inv(0) = 0 (cross-check of fp_inv)
   uint64_t e[4] = {FP_MOD[0] - 2, FP_MOD[1], FP_MOD[2], FP_MOD[3]};
   uint64_t r[4]; memcpy(r, FP_ONE, 32);
   for (int i = 255; i >= 0; i--) {
@@ -129,6 +129,56 @@ inline void fp_inv(const uint64_t a[4], uint64_t o[4]) {       // a^(p-2); inv(0
     if ((e[i >> 6] >> (i & 63)) & 1) fp_mul(r, a, r);
   }
   memcpy(o, r, 32);
+}
+// ---- 256-bit helpers for the binary extended Euclid below ----
+inline bool u256_is_one(const uint64_t a[4]) { return a[0] == 1 && !(a[1] | a[2] | a[3]); }
+inline bool u256_ge(const uint64_t a[4], const uint64_t b[4]) {
+  for (int i = 3; i >= 0; i--) { if (a[i] != b[i]) return a[i] > b[i]; }
+  return true;
+}
+inline void u256_sub(uint64_t a[4], const uint64_t b[4]) {                      // a -= b (a >= b)
+  unsigned borrow = 0;
+  for (int i = 0; i < 4; i++) { u128 x = (u128)a[i] - b[i] - borrow; a[i] = (uint64_t)x; borrow = (unsigned)((x >> 64) & 1); }
+}
+inline void u256_shr1(uint64_t a[4], uint64_t top) {                            // (top:a) >> 1
+  a[0] = (a[0] >> 1) | (a[1] << 63); a[1] = (a[1] >> 1) | (a[2] << 63); a[2] = (a[2] >> 1) | (a[3] << 63); a[3] = (a[3] >> 1) | (top << 63);
+}
+inline void mod_half(uint64_t x[4], const uint64_t mod[4]) {                    // x / 2 mod p, x < p
+  uint64_t top = 0;
+  if (x[0] & 1) { unsigned carry = 0; for (int i = 0; i < 4; i++) { u128 s = (u128)x[i] + mod[i] + carry; x[i] = (uint64_t)s; carry = (unsigned)(s >> 64); } top = carry; }
+  u256_shr1(x, top);
+}
+inline void mod_sub(uint64_t x[4], const uint64_t y[4], const uint64_t mod[4]) { // x = x - y mod p, both < p
+  unsigned borrow = 0;
+  for (int i = 0; i < 4; i++) { u128 d = (u128)x[i] - y[i] - borrow; x[i] = (uint64_t)d; borrow = (unsigned)((d >> 64) & 1); }
+  if (borrow) { unsigned carry = 0; for (int i = 0; i < 4; i++) { u128 s = (u128)x[i] + mod[i] + carry; x[i] = (uint64_t)s; carry = (unsigned)(s >> 64); } }
+}
+// Montgomery inverse a R -> a^-1 R by the binary extended Euclid on plain integers (~4 us on a host core; the Fermat ladder is
+// 384 Montgomery multiplications, ~15 us — and this inversion sits on the prove's critical path twice: the rest-commitment
+// rows before the taus, the PCS points before the IPA challenge).  x = (aR)^-1 as an integer, then x * R^3 / R = a^-1 R.  inv(0) = 0.
+inline void fp_inv(const uint64_t a[4], uint64_t o[4]) {
+  if (!(a[0] | a[1] | a[2] | a[3])) { memset(o, 0, 32); return; }
+  struct Consts { uint64_t R3[4]; Consts() {                                    // R^3 mod p = mont(mont(R2', R2'), R2') with R2' = R^2: by doubling
+      uint64_t r[4] = {1, 0, 0, 0};
+      for (int i = 0; i < 768; i++) {
+        uint64_t d[4]; unsigned carry = 0;
+        for (int j = 0; j < 4; j++) { const uint64_t v = r[j]; d[j] = (v << 1) | carry; carry = (unsigned)(v >> 63); }
+        uint64_t e[4]; unsigned borrow = 0;
+        for (int j = 0; j < 4; j++) { u128 x = (u128)d[j] - FP_MOD[j] - borrow; e[j] = (uint64_t)x; borrow = (unsigned)((x >> 64) & 1); }
+        const bool ge = carry || !borrow;
+        for (int j = 0; j < 4; j++) r[j] = ge ? e[j] : d[j];
+      }
+      memcpy(R3, r, 32); } };
+  static const Consts K;
+  uint64_t u[4], v[4], x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  memcpy(u, a, 32); memcpy(v, FP_MOD, 32);
+  while (!u256_is_one(u) && !u256_is_one(v)) {
+    while (!(u[0] & 1)) { u256_shr1(u, 0); mod_half(x1, FP_MOD); }
+    while (!(v[0] & 1)) { u256_shr1(v, 0); mod_half(x2, FP_MOD); }
+    if (u256_ge(u, v)) { u256_sub(u, v); mod_sub(x1, x2, FP_MOD); }
+    else { u256_sub(v, u); mod_sub(x2, x1, FP_MOD); }
+  }
+  fp_mul(u256_is_one(u) ? x1 : x2, K.R3, o);
 }
 // n Jacobian points (x,y,z: 12 limbs each) -> affine (x,y: 8 limbs each), identity (z = 0) -> all zero;
 // one inversion for the whole batch (Montgomery's trick)

@@ -460,7 +460,7 @@ int32_t sp2_fold_commitments_partial(sp2_ctx *ctx, const sp2_ck *ck, const uint6
 #include "sumcheck.cuh"
 
 namespace sp2 {
-int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out);
+int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out, cudaStream_t stream = nullptr, int slot = 15);
 // small_value.cu
 int nifs_round0_small_enqueue(sp2_ctx *ctx, const fe *d_rhos, u32 ell_b, u32 left, u32 right, const fe *dE, const void *dA64, const void *dB64,
                               const fe *dA, const fe *dB, const void *d_positions, u64 n_large, u64 N, u64 m, fe *d_partials, fe *d_out,

@@ -26,18 +26,19 @@ __global__ void __launch_bounds__(256) k_bind_top(const fe *Z, size_t n, const f
 
 namespace sp2 {
 // device-resident eq table: d_r (k points) -> d_out (2^k); uses scratch slot 15 for the factor tables
-int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out) {
+int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out, cudaStream_t stream = nullptr, int slot = 15) {
+  if (!stream) stream = ctx->stream;
   const int s = (int)k / 2;
   const size_t n = (size_t)1 << k;
   void *fac;
-  SP2_TRY(scratch(ctx, 15, (((size_t)2 << (k - s)) + ((size_t)2 << s)) * sizeof(fe), &fac));
+  SP2_TRY(scratch(ctx, slot, (((size_t)2 << (k - s)) + ((size_t)2 << s)) * sizeof(fe), &fac));
   fe *hi_pref = (fe *)fac, *lo_pref = hi_pref + ((size_t)2 << (k - s));
-  k_eq_factors<<<2, 1024, 0, ctx->stream>>>(d_r, (int)k, s, hi_pref, lo_pref);
+  k_eq_factors<<<2, 1024, 0, stream>>>(d_r, (int)k, s, hi_pref, lo_pref);
   SP2_LAUNCH_CHECK();
   const fe *hi = hi_pref + (((size_t)1 << (k - s)) - 1), *lo = lo_pref + (((size_t)1 << s) - 1);
   unsigned blocks = (unsigned)((n + 255) / 256);
   if (blocks > (unsigned)ctx->num_sms * 8) blocks = ctx->num_sms * 8;
-  k_eq_product<<<blocks, 256, 0, ctx->stream>>>(hi, lo, s, n, d_out);
+  k_eq_product<<<blocks, 256, 0, stream>>>(hi, lo, s, n, d_out);
   SP2_LAUNCH_CHECK();
   return SP2_OK;
 }

@@ -24,7 +24,7 @@
 using namespace sp2;
 
 namespace sp2 {
-int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out);
+int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out, cudaStream_t stream = nullptr, int slot = 15);
 }
 
 struct sp2_prep {
@@ -48,7 +48,8 @@ struct sp2_prep {
   uint8_t *h_inbox = nullptr;        // pinned staging of the same layout (+ tau digests)
   size_t inbox_bytes = 0;
   cudaEvent_t ev[9] = {nullptr};
-  cudaEvent_t ev_r1 = nullptr, ev_inv = nullptr;
+  cudaEvent_t ev_r1 = nullptr, ev_inv = nullptr, ev_in = nullptr, ev_lz = nullptr, ev_delta = nullptr, ev_q = nullptr;
+  cudaStream_t side2 = nullptr;      // early comm_LZ chain (prove): runs under the inner sum-check's last rounds
   std::vector<void *> owned;
 };
 
@@ -93,6 +94,23 @@ __global__ void k_den_inv(const ScState *inner, fe *small) {
   }
 }
 
+// side stream: returns once the quadratic prover has published the challenges of rounds 1..round (ScState::r_ready), so that the
+// work queued behind it (the Hyrax bind and the comm_LZ MSM, which need only r_y[1..log2 rows]) runs under the remaining rounds.
+// Bounded like every device-side wait; on a timeout the sum-check state carries the error to the host.
+__global__ void k_wait_round(ScState *st, u32 round) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  for (;;) {
+    u32 v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->r_ready));
+    if (v >= round) break;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    if (t - t0 > SC_WAIT_NS) { atomicExch(&st->err, 1u); break; }
+    __nanosleep(200);
+  }
+  __threadfence();
+}
+
 // outer -> inner: absorb(b"claims_outer", [A(rx), B(rx), C(rx)]); r = squeeze(b"r");
 // joint = A + r B + r^2 C (spartan.rs:305-316).  Initialises the inner sum-check state.
 __global__ void __launch_bounds__(64) k_outer_to_inner(ScState *outer, ScState *inner, fe *small, int rounds_inner) {
@@ -114,7 +132,7 @@ __global__ void __launch_bounds__(64) k_outer_to_inner(ScState *outer, ScState *
     inner->ts.round = ts->round; inner->ts.pending_len = 0;
     for (int i = 0; i < 64; i++) inner->ts.state[i] = ts->state[i];
     stg_fe(&inner->claim, joint);
-    inner->ticket = 0; inner->l = (u32)rounds_inner; inner->flags = outer->flags; inner->arrived = 0; inner->released = 0; inner->err = 0;
+    inner->ticket = 0; inner->l = (u32)rounds_inner; inner->flags = outer->flags; inner->arrived = 0; inner->released = 0; inner->err = 0; inner->r_ready = 0;
     for (int i = 0; i < SC_MAX_ROUNDS + 8; i++) inner->mid_arrive[i] = 0;
     inner->mid_released = 0;
     for (int i = 0; i < 12 * 16; i++) inner->mid_acc0[i] = 0;
@@ -197,6 +215,11 @@ void sp2_prep_free(sp2_prep *P) {
   for (auto &e : P->ev) if (e) cudaEventDestroy(e);
   if (P->ev_r1) cudaEventDestroy(P->ev_r1);
   if (P->ev_inv) cudaEventDestroy(P->ev_inv);
+  if (P->ev_in) cudaEventDestroy(P->ev_in);
+  if (P->ev_lz) cudaEventDestroy(P->ev_lz);
+  if (P->ev_delta) cudaEventDestroy(P->ev_delta);
+  if (P->ev_q) cudaEventDestroy(P->ev_q);
+  if (P->side2) { cudaStreamSynchronize(P->side2); cudaStreamDestroy(P->side2); }
   delete P;
 }
 
@@ -236,6 +259,9 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
     P->small = P->inbox; P->dvec = P->inbox + S_COUNT; P->blinds = P->dvec + width;
     for (auto &e : P->ev) cudaEventCreate(&e);
     cudaEventCreateWithFlags(&P->ev_r1, cudaEventDisableTiming); cudaEventCreateWithFlags(&P->ev_inv, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&P->ev_in, cudaEventDisableTiming); cudaEventCreateWithFlags(&P->ev_lz, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&P->ev_delta, cudaEventDisableTiming); cudaEventCreateWithFlags(&P->ev_q, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&P->side2, cudaStreamNonBlocking);
   }
   if (rc != SP2_OK) { sp2_prep_free(P); return rc; }
   auto fail = [&](int r) { sp2_prep_free(P); return r; };
@@ -313,15 +339,19 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     if (S->num_public) memcpy(q, public_values, S->num_public * sizeof(fe));
     SP2_CUDA_OK(cudaMemcpyAsync(P->inbox, h, P->inbox_bytes, cudaMemcpyHostToDevice, ctx->stream)); }
   const fe *d_X = P->blinds + rows;
+  // PCS points of this prove: [comm_LZ, delta, comm_eval_W, beta]
+  jac *d_pts = P->points + rows;
+  // delta = <d, ck> + r_delta h (ipa.rs:140-146) depends on the prover's randomness only: side stream, under the witness commitment
+  { MsmJob j; memset(&j, 0, sizeof(j)); j.scalars = P->dvec; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = &small[S_RDELTA];
+    SP2_CUDA_OK(cudaEventRecord(P->ev_in, ctx->stream));
+    SP2_CUDA_OK(cudaStreamWaitEvent(ctx->side, P->ev_in, 0));
+    SP2_TRY(msm_run(ctx, ck, std::vector<MsmJob>{j}, d_pts + 1, ctx->side, 16, 17));
+    SP2_CUDA_OK(cudaEventRecord(P->ev_delta, ctx->side)); }
   // rest section of the witness (NULL: all zero, e.g. pure padding as in the SHA-256 bench circuit)
   if (S->num_rest) {
     if (W_rest) SP2_CUDA_OK(cudaMemcpyAsync(P->W + P->cached_len, W_rest, S->num_rest * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
     else SP2_CUDA_OK(cudaMemsetAsync(P->W + P->cached_len, 0, S->num_rest * sizeof(fe), ctx->stream));
   }
-  // z = W | 1 | X   (spartan.rs:248-253)
-  SP2_CUDA_OK(cudaMemcpyAsync(P->z, P->W, nv * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
-  k_z_tail<<<(unsigned)(num_extra + 127) / 128, 128, 0, ctx->stream>>>(P->z + nv, d_X, (u32)S->num_public);
-  SP2_LAUNCH_CHECK();
 
   // ---- transcript up to the taus (host; spartan.rs:226-264, bellpepper/r1cs.rs:422-431,491) -----
   // The host hashes the cached commitment rows AFTER the device work of this phase has been enqueued (below), so the
@@ -335,6 +365,13 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     if (pre_rows) ts.absorb_commitment_be("comm_W_precommitted", P->comm_cached_be.data() + 64 * sh_rows, pre_rows);
     memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
   };
+  // z = W | 1 | X   (spartan.rs:248-253) — enqueued behind the rest-section commitment, whose rows the host is waiting for
+  auto make_z = [&]() -> int {
+    SP2_CUDA_OK(cudaMemcpyAsync(P->z, P->W, nv * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+    k_z_tail<<<(unsigned)(num_extra + 127) / 128, 128, 0, ctx->stream>>>(P->z + nv, d_X, (u32)S->num_public);
+    SP2_LAUNCH_CHECK();
+    return SP2_OK;
+  };
   // commit the rest section (r1cs.rs:467-470: blind + commit / commit_zeros)
   bool spmv_done = false;
   if (rest_rows) {
@@ -343,6 +380,7 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     uint64_t *hj = (uint64_t *)(P->h_inbox + P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64);      // pinned: a true async DMA
     SP2_CUDA_OK(cudaMemcpyAsync(hj, P->points + P->cached_rows, rest_rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
     SP2_CUDA_OK(cudaEventRecord(P->ev_r1, ctx->stream));
+    SP2_TRY(make_z());
     // Az, Bz, Cz (spartan.rs:271 -> multiply_vec_incremental_into) do not depend on the taus: enqueue them now so they
     // run while the host normalises / hashes the commitment rows
     { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
@@ -353,6 +391,7 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     sp2h::batch_normalize(hj, rest_rows, proof->comm_W + 8 * P->cached_rows);
   }
   if (!spmv_done) { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
+    SP2_TRY(make_z());
     SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work));
     absorb_head(); }
   ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
@@ -408,6 +447,30 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   k_den_inv<<<1, 32, 0, ctx->side>>>(st_inner, small);
   SP2_LAUNCH_CHECK();
   SP2_CUDA_OK(cudaEventRecord(P->ev_inv, ctx->side));
+  // ---- comm_LZ early (hyrax_pc.rs:415-444): L = eq(r_y[1..log2 rows]) is complete after inner round 1 + log2(rows), long before the
+  // sum-check ends — the bind LZ = L^T W, r_LZ = <L, blinds> and the 2048-term MSM run on a second side stream under the
+  // remaining (latency-bound) rounds, on the SMs the pipelined round kernel leaves free
+  const fe *ry1 = st_inner->r + 1;
+  MsmJob j;
+  if (nvr > 0) {
+    if (shard) {
+      // sharded proves: after the whole sum-check (still beside the eval_W / R-table chain of the main stream) — no spinning kernel
+      // next to the round kernels that wait for their peers (ranks of one process share the hardware queues)
+      SP2_CUDA_OK(cudaEventRecord(P->ev_q, ctx->stream));
+      SP2_CUDA_OK(cudaStreamWaitEvent(P->side2, P->ev_q, 0));
+    } else {
+      SP2_CUDA_OK(cudaStreamWaitEvent(P->side2, P->ev_r1, 0));
+      k_wait_round<<<1, 32, 0, P->side2>>>(st_inner, (u32)(1 + nvr));
+      SP2_LAUNCH_CHECK();
+    }
+    SP2_TRY(eq_table_dev(ctx, ry1, (uint32_t)nvr, P->Ltab, P->side2, 19));
+    SP2_TRY(hyrax_bind_dev(ctx, P->W, P->Ltab, rows, width, P->LZ, P->side2, 20));
+    k_dot<<<1, 256, 0, P->side2>>>(P->Ltab, P->blinds, rows, &small[S_RLZ]);
+    SP2_LAUNCH_CHECK();
+    memset(&j, 0, sizeof(j)); j.scalars = P->LZ; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = &small[S_RLZ];
+    SP2_TRY(msm_run(ctx, ck, std::vector<MsmJob>{j}, d_pts, P->side2, 21, 22));                        // comm_LZ
+    SP2_CUDA_OK(cudaEventRecord(P->ev_lz, P->side2));
+  }
   mark(5);
   SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_inv, 0));
 
@@ -415,33 +478,23 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   { void *chis; SP2_TRY(scratch(ctx, 12, ((size_t)4 << nvz) * sizeof(fe) + 64, &chis));
     k_eval_w<<<1, 256, 0, ctx->stream>>>(st_inner, P->z + nv, (u32)num_extra, m, (fe *)chis, small);
     SP2_LAUNCH_CHECK(); }
-  const fe *ry1 = st_inner->r + 1;
   SP2_TRY(eq_table_dev(ctx, ry1 + nvr, (uint32_t)(m - nvr), P->Rtab));
-  std::vector<MsmJob> jobs;
-  MsmJob j;
-  if (nvr > 0) {
-    SP2_TRY(eq_table_dev(ctx, ry1, (uint32_t)nvr, P->Ltab));
-    SP2_TRY(hyrax_bind_dev(ctx, P->W, P->Ltab, rows, width, P->LZ));
-    k_dot<<<1, 256, 0, ctx->stream>>>(P->Ltab, P->blinds, rows, &small[S_RLZ]);
-    SP2_LAUNCH_CHECK();
-    memset(&j, 0, sizeof(j)); j.scalars = P->LZ; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = &small[S_RLZ];
-    jobs.push_back(j);                                                     // comm_LZ
-  } else {
+  if (nvr == 0) {
     SP2_CUDA_OK(cudaMemcpyAsync(P->LZ, P->W, width * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
     SP2_CUDA_OK(cudaMemcpyAsync(&small[S_RLZ], P->blinds, sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   k_dot<<<1, 256, 0, ctx->stream>>>(P->Rtab, P->dvec, width, &small[S_IP]);
   SP2_LAUNCH_CHECK();
-  memset(&j, 0, sizeof(j)); j.scalars = P->dvec; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = &small[S_RDELTA];
-  jobs.push_back(j);                                                       // delta
+  std::vector<MsmJob> jobs;
   memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = &small[S_EVALW];
   j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = &small[S_BLIND_EVAL];
   jobs.push_back(j);                                                       // comm_eval_W
   memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = &small[S_IP];
   j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = &small[S_RBETA];
   jobs.push_back(j);                                                       // beta
-  jac *d_pts = P->points + rows;
-  SP2_TRY(msm_run(ctx, ck, jobs, d_pts));
+  SP2_TRY(msm_run(ctx, ck, jobs, d_pts + 2));
+  SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_delta, 0));
+  if (nvr > 0) SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_lz, 0));
   mark(6);
 
   absorb_poly_com();                                                        // host hashing overlapped with the device work above
@@ -458,7 +511,8 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                          // host sync 2
   if (h_outer->err || h_inner->err) { cleanup(); return set_error(ctx, SP2_ERR_INTERNAL, "prove: a device-side wait (grid barrier) did not complete within 2 s"); }
   if (shard) SP2_TRY(comm_check(ctx, comm));
-  sp2h::batch_normalize(h_jac, jobs.size(), h_pts);
+  const int p_first = nvr > 0 ? 0 : 1;                                      // (no comm_LZ point for a one-row commitment)
+  sp2h::batch_normalize(h_jac + 12 * p_first, 4 - p_first, h_pts + 8 * p_first);
   if (((uint32_t *)(h_small + 4 * S_ERR))[0] == 5) { cleanup(); return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "prove: 1 - r_y[0] = 0"); }
   for (int i = 0; i < l; i++) {                                            // compressed: [c0, c2, c3] (univariate.rs:147-153)
     memcpy(proof->outer_polys + 12 * i, &h_outer->polys[4 * i], 32);
@@ -472,8 +526,7 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   memcpy(proof->eval_W, h_small + 4 * S_EVALW, 32);
   memcpy(proof->blind_eval_W, rnd->blind_eval_W, 32);
   const uint64_t *comm_LZ, *p_delta, *p_ceval, *p_beta;
-  if (nvr > 0) { comm_LZ = h_pts; p_delta = h_pts + 8; p_ceval = h_pts + 16; p_beta = h_pts + 24; }
-  else { comm_LZ = proof->comm_W; p_delta = h_pts; p_ceval = h_pts + 8; p_beta = h_pts + 16; }
+  comm_LZ = nvr > 0 ? h_pts : proof->comm_W; p_delta = h_pts + 8; p_ceval = h_pts + 16; p_beta = h_pts + 24;
   memcpy(proof->delta, p_delta, 64); memcpy(proof->beta, p_beta, 64);
 
   // ---- transcript tail on the host: poly_com rows, IPA absorbs, r (hyrax_pc.rs:410; ipa.rs:134-153) ----

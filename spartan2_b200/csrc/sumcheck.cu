@@ -572,7 +572,7 @@ __device__ __forceinline__ fe quad_finalize_pre(ScState *st, int round1, const f
     if (tid == 0) { sm.g[0] = e0; sm.g[1] = b; sm.g[2] = ti; }
   }
   const fe r = sc_squeeze(st, sm, canon, 2);      // (its barriers publish sm.g[0..2] to the CTA)
-  if (tid == 0) stg_fe(&st->r[i], r);
+  if (tid == 0) { stg_fe(&st->r[i], r); __threadfence(); *(volatile u32 *)&st->r_ready = (u32)round1; }
   return r;
 }
 // claim <- poly(r); one thread; (e0, b, tinf) by value (copied out of sm.g before the next round overwrites it)
@@ -1041,7 +1041,7 @@ k_quad_tail_pipe(ScState *st, fe *A, fe *B, fe *A2, fe *B2, int round_first, int
       fe canon = Fq::zero();
       if (ft < 32) canon = fin_quad_msg(ts, fq, st, round1, direct, ts.coef[cur], rf, ft);
       rf = tp_squeeze(ts, canon, 2, ft);
-      if (ft == 0) stg_fe(&st->r[round1 - 1], rf);
+      if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); *(volatile u32 *)&st->r_ready = (u32)round1; }
     }
     __syncthreads();
     r = ts.ch;
@@ -1733,7 +1733,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
     if (ft < 32) canon = fin_quad_msg(ts, fq, st, round1, round1 == first, ts.coef[cur], rf, ft);
     fe *coef_next = ts.coef[cur ^ 1];
     rf = tp_squeeze(ts, canon, 2, ft, TpNoSide(), [&] { if (want_next) mid_gather_acc(st, round1 == first ? MP_ARRIVE_FIRST_COEF : round1, Gr, round1 == first ? st->mid_acc0 + 3 * 16 : mid_acc(st, round1), 6, coef_next); });
-    if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); }
+    if (ft == 0) { stg_fe(&st->r[round1 - 1], rf); __threadfence(); st_volatile_u32(&st->mid_released, (u32)round1); st_volatile_u32(&st->r_ready, (u32)round1); }
     cur ^= 1;
   }
   tp_msg_store(ts, st, 2, ft);

@@ -27,7 +27,8 @@ struct ScState {
   fe p;                       // eval_eq_left (sumcheck.rs:951)
   fe L0, SL;                  // p*(1-tau_i), p*(2tau_i-1) for the round being evaluated
   u32 ticket, l, flags, arrived;     // arrived / released: monotonic counters of the persistent kernels' grid barrier
-  u32 released, err, pad1[2];   // err: a bounded device wait (grid barrier / peer mailbox) timed out -> SP2_ERR_INTERNAL on the host
+  u32 released, err, r_ready, pad1;   // r_ready: rounds of the QUADRATIC prover whose challenge is in r[] (polled by the prover's side stream);
+                                     // err: a bounded device wait (grid barrier / peer mailbox) timed out -> SP2_ERR_INTERNAL on the host
   u32 mid_arrive[SC_MAX_ROUNDS + 8];   // pipelined multi-CTA rounds: CTAs whose partial sums of a round are published
   u32 mid_released, pad2[7];           //   and the last round whose challenge is published
   u32 mid_acc0[12 * 16];               //   column accumulators of the first such round (3 direct + 9 coefficient sums), zero on entry

@@ -19,7 +19,7 @@
 using namespace sp2;
 
 namespace sp2 {
-int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out);
+int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out, cudaStream_t stream = nullptr, int slot = 15);
 }
 
 namespace {

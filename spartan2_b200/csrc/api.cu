@@ -43,6 +43,8 @@ void sp2_ctx_destroy(sp2_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < sp2_ctx::NSLOT; i++) if (ctx->slot[i]) cudaFree(ctx->slot[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (void *p : ctx->retired) cudaFree(p);
+  for (void *p : ctx->retired_pinned) cudaFreeHost(p);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);

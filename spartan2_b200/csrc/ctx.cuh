@@ -26,6 +26,9 @@ struct sp2_ctx {
   size_t slot_bytes[NSLOT] = {0};
   void *pinned = nullptr;               // small pinned staging buffer for result read-back
   size_t pinned_bytes = 0;
+  // buffers replaced by a larger one: kept until the context goes (cudaFree / cudaFreeHost synchronise the device, and the
+  // library keeps kernels in flight that wait for the HOST — the prover's gate — or for a peer)
+  std::vector<void *> retired, retired_pinned;
 };
 
 namespace sp2 {
@@ -49,8 +52,8 @@ inline int set_cuda_error(sp2_ctx *ctx, cudaError_t e, const char *what, int lin
 // scratch slot `i` of at least `bytes` bytes (contents undefined)
 inline int scratch(sp2_ctx *ctx, int i, size_t bytes, void **out) {
   if (ctx->slot_bytes[i] < bytes) {
-    if (ctx->slot[i]) { SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); SP2_CUDA_OK(cudaFree(ctx->slot[i])); ctx->slot[i] = nullptr; ctx->slot_bytes[i] = 0; }
-    size_t want = bytes + bytes / 8 + 256;
+    if (ctx->slot[i]) { ctx->retired.push_back(ctx->slot[i]); ctx->slot[i] = nullptr; ctx->slot_bytes[i] = 0; }   // (work in flight may still use it)
+    size_t want = bytes + bytes / 4 + 256;
     SP2_CUDA_OK(cudaMalloc(&ctx->slot[i], want));
     ctx->slot_bytes[i] = want;
   }
@@ -59,7 +62,7 @@ inline int scratch(sp2_ctx *ctx, int i, size_t bytes, void **out) {
 }
 inline int pinned(sp2_ctx *ctx, size_t bytes, void **out) {
   if (ctx->pinned_bytes < bytes) {
-    if (ctx->pinned) { SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); SP2_CUDA_OK(cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    if (ctx->pinned) { ctx->retired_pinned.push_back(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
     size_t want = bytes * 2 + 4096;
     SP2_CUDA_OK(cudaMallocHost(&ctx->pinned, want));
     ctx->pinned_bytes = want;

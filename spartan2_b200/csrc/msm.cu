@@ -349,6 +349,20 @@ int msm_build_tables(sp2_ctx *ctx, const aff *d_bases, uint32_t nbase, aff **tab
   return SP2_OK;
 }
 
+// HyraxPCS::commit rows on a given stream (see sp2_hyrax_commit_dev)
+int hyrax_commit_rows(sp2_ctx *ctx, const sp2_ck *ck, const fe *d_v, uint64_t len, const fe *d_blinds, uint64_t rows, jac *d_out, cudaStream_t stream,
+                      int slot_jobs, int slot_partials) {
+  if (rows < (len + ck->n - 1) / ck->n) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "hyrax commit: too few rows for the vector");
+  std::vector<MsmJob> jobs(rows);
+  for (uint64_t i = 0; i < rows; i++) {
+    MsmJob &j = jobs[i]; memset(&j, 0, sizeof(j));
+    const uint64_t lo = i * ck->n, hi = std::min<uint64_t>(len, lo + ck->n);
+    j.scalars = d_v + lo; j.len = hi > lo ? (u32)(hi - lo) : 0; j.base0 = 0;
+    j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = d_blinds + i;
+  }
+  return msm_run(ctx, ck, jobs, d_out, stream, slot_jobs, slot_partials);
+}
+
 int hyrax_bind_dev(sp2_ctx *ctx, const fe *d_poly, const fe *d_L, uint64_t rows, uint64_t r_len, fe *d_out, cudaStream_t stream, int slot) {
   if (!stream) stream = ctx->stream;
   const unsigned rg = (unsigned)std::min<uint64_t>(rows, BIND_RG);
@@ -417,15 +431,7 @@ int32_t sp2_msm(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *scalars, uint32_
 int32_t sp2_hyrax_commit_dev(sp2_ctx *ctx, const sp2_ck *ck, const void *d_v, uint64_t len, const void *d_blinds, uint64_t rows,
                              void *d_out_rows_jac) {
   cudaSetDevice(ctx->device);
-  if (rows < (len + ck->n - 1) / ck->n) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "hyrax commit: too few rows for the vector");
-  std::vector<MsmJob> jobs(rows);
-  for (uint64_t i = 0; i < rows; i++) {
-    MsmJob &j = jobs[i]; memset(&j, 0, sizeof(j));
-    const uint64_t lo = i * ck->n, hi = std::min<uint64_t>(len, lo + ck->n);
-    j.scalars = (const fe *)d_v + lo; j.len = hi > lo ? (u32)(hi - lo) : 0; j.base0 = 0;
-    j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = (const fe *)d_blinds + i;
-  }
-  return msm_run(ctx, ck, jobs, (jac *)d_out_rows_jac);
+  return sp2::hyrax_commit_rows(ctx, ck, (const fe *)d_v, len, (const fe *)d_blinds, rows, (jac *)d_out_rows_jac, nullptr, 10, 11);
 }
 
 int32_t sp2_hyrax_commit(sp2_ctx *ctx, const sp2_ck *ck, const uint64_t *v, uint64_t len, const uint64_t *blinds, uint64_t rows,

@@ -47,6 +47,8 @@ namespace sp2 {
 // max_ctas (0 = no cap): grid size limit of the gather kernel
 int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs, jac *d_out, cudaStream_t stream = nullptr, int slot_jobs = 10,
             int slot_partials = 11, unsigned max_ctas = 0);
+int hyrax_commit_rows(sp2_ctx *ctx, const sp2_ck *ck, const fe *d_v, uint64_t len, const fe *d_blinds, uint64_t rows, jac *d_out, cudaStream_t stream,
+                      int slot_jobs, int slot_partials);
 int hyrax_bind_dev(sp2_ctx *ctx, const fe *d_poly, const fe *d_L, uint64_t rows, uint64_t r_len, fe *d_out, cudaStream_t stream = nullptr, int slot = 12);
 // window tables [nbase][MSM_NW][MSM_ND] of arbitrary device-resident affine bases (identity allowed): *table_out is cudaMalloc'ed
 int msm_build_tables(sp2_ctx *ctx, const aff *d_bases, uint32_t nbase, aff **table_out);

@@ -1686,6 +1686,7 @@ static int32_t nn_snark_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *xcomm, sp2_
   memcpy(h_in + nrow * 32, rnd->d_vec, width * 32);
   SP2_CUDA_OK(cudaMemcpyAsync(P->blinds_dev, h_in, nrow * 32, cudaMemcpyHostToDevice, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(dvec, h_in + nrow * 32, width * 32, cudaMemcpyHostToDevice, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(small + NS_RDELTA, rnd->r_delta, 32, cudaMemcpyHostToDevice, ctx->stream));   // (for the early delta MSM below)
   const fe *fold_src = P->blinds_dev;                        // [instance][row] blinds the fold runs over
   if (P->nranks > 1) {                                       // fold_blinds needs every instance's blinds (identical inputs on all ranks)
     uint8_t *h_all = h_in + (nrow + width + NS_COUNT + 16) * 32;
@@ -1751,6 +1752,9 @@ static int32_t nn_snark_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *xcomm, sp2_
       for (uint32_t r = 0; r < pre_rows; r++) { MsmJob &j = jobs[r]; memset(&j, 0, sizeof(j)); j.scalars = P->Wfold + (size_t)r * width; j.len = (u32)width; }
       SP2_TRY(msm_run(ctx, ck, jobs, pts_fold, P->side, 16, 17, nn_side_ctas()));
     }
+    // delta = <d, ck> + r_delta h (ipa.rs:140-146) depends on the prover's randomness only: same side stream, under the sum-checks
+    { MsmJob j; memset(&j, 0, sizeof(j)); j.scalars = dvec; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = small + NS_RDELTA;
+      SP2_TRY(msm_run(ctx, ck, std::vector<MsmJob>{j}, pts_fold + rows + 2 + rows + 3, P->side, 21, 22, nn_side_ctas())); }
     SP2_CUDA_OK(cudaEventRecord(P->ev_side, P->side));
     return SP2_OK;
   };
@@ -1804,7 +1808,7 @@ static int32_t nn_snark_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *xcomm, sp2_
   k_nn_dot<<<1, 256, 0, ctx->stream>>>(Rtab, dvec, width, small + NS_IP);
   SP2_LAUNCH_CHECK();
   SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_side, 0));                                        // the folded-witness rows are committed
-  std::vector<MsmJob> jobs(rows + 4);
+  std::vector<MsmJob> jobs(rows + 3);                              // (delta, point rows + 3 of the output, was committed on the side stream)
   for (uint32_t r = 0; r < rows; r++) {        // comm[r] = comm(W_fold row) + c_eval U_core[r] + (b_fold[r] + c_eval b_core[r]) h
     MsmJob &j = jobs[r]; memset(&j, 0, sizeof(j));
     j.nextra = 2; j.extra_base[0] = r; j.extra_scalar[0] = small + NS_CEVAL; j.extra_tab[0] = P->Ucore_tab;
@@ -1814,8 +1818,7 @@ static int32_t nn_snark_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *xcomm, sp2_
   { MsmJob &j = jobs[rows]; memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = small + NS_EVALF;
     j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = small + NS_BEVALF; }                           // comm_eval
   { MsmJob &j = jobs[rows + 1]; memset(&j, 0, sizeof(j)); j.scalars = LZp; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = rLZ; }   // comm_LZ
-  { MsmJob &j = jobs[rows + 2]; memset(&j, 0, sizeof(j)); j.scalars = dvec; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = small + NS_RDELTA; }   // delta
-  { MsmJob &j = jobs[rows + 3]; memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = small + NS_IP;
+  { MsmJob &j = jobs[rows + 2]; memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = small + NS_IP;
     j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = small + NS_RBETA; }                            // beta
   jac *pts_out = pts_fold + rows + 2;            // (the row jobs read pts_fold[0..pre_rows) as addends and write pts_out[0..rows): disjoint)
   SP2_TRY(msm_run(ctx, ck, jobs, pts_out));
@@ -1826,7 +1829,7 @@ static int32_t nn_snark_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *xcomm, sp2_
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   std::vector<uint64_t> outp((size_t)(rows + 4) * 8);
   sp2h::batch_normalize(h_jac, rows + 4, outp.data());
-  const uint64_t *comm = outp.data(), *comm_eval = comm + 8 * (size_t)rows, *comm_LZ = nvr > 0 ? comm_eval + 8 : comm, *p_delta = comm_eval + 16, *p_beta = comm_eval + 24;
+  const uint64_t *comm = outp.data(), *comm_eval = comm + 8 * (size_t)rows, *comm_LZ = nvr > 0 ? comm_eval + 8 : comm, *p_beta = comm_eval + 16, *p_delta = comm_eval + 24;
   if (sn->comm_fold) memcpy(sn->comm_fold, comm, (size_t)rows * 64);
   memcpy(sn->delta, p_delta, 64); memcpy(sn->beta, p_beta, 64);
   ts.absorb_commitment("poly_com", comm, rows);                                                         // hyrax_pc.rs:410

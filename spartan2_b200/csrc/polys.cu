@@ -42,6 +42,14 @@ int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out, cudaStream_
   SP2_LAUNCH_CHECK();
   return SP2_OK;
 }
+// (see sumcheck_cubic_preload / _reserve: the same for an eq table built behind the prover's gate)
+int eq_table_reserve(sp2_ctx *ctx, uint32_t k, int slot) {
+  static unsigned loaded_mask = 0;
+  if (!(loaded_mask >> ctx->device & 1u)) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, (const void *)k_eq_factors); cudaFuncGetAttributes(&a, (const void *)k_eq_product); loaded_mask |= 1u << ctx->device; }
+  const int s = (int)k / 2;
+  void *fac;
+  return scratch(ctx, slot, (((size_t)2 << (k - s)) + ((size_t)2 << s)) * sizeof(fe), &fac);
+}
 int bind_top_dev(sp2_ctx *ctx, const fe *d_Z, size_t len, const fe *d_r, fe *d_out) {
   const size_t n = len / 2;
   if (n == 0) return SP2_OK;

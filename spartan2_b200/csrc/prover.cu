@@ -13,6 +13,12 @@
 // sum-check results + PCS points, IPA response) instead of one per sum-check round.
 #include <string.h>
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include "ctx.cuh"
 #include "host_transcript.h"
 #include "keccak.cuh"
@@ -25,9 +31,43 @@ using namespace sp2;
 
 namespace sp2 {
 int eq_table_dev(sp2_ctx *ctx, const fe *d_r, uint32_t k, fe *d_out, cudaStream_t stream = nullptr, int slot = 15);
+int eq_table_reserve(sp2_ctx *ctx, uint32_t k, int slot);
 }
 
+// One helper host thread per prep state: hashes the BULK head of the transcript (the cached commitment rows, ~30 KB of serial Keccak =
+// ~60 us) while the calling thread enqueues the device work of the same phase — the commit + transcript phase of a prove is bound
+// by the host, not by the GPU.  The worker makes no CUDA calls.
+struct HostWorker {
+  std::thread th; std::mutex m; std::condition_variable cv;
+  std::deque<std::function<void()>> q; bool busy = false, quit = false;     // jobs run in submission order
+  void start() {
+    th = std::thread([this] {
+      std::unique_lock<std::mutex> lk(m);
+      for (;;) {
+        cv.wait(lk, [this] { return !q.empty() || quit; });
+        if (q.empty()) return;
+        std::function<void()> j = std::move(q.front()); q.pop_front(); busy = true;
+        lk.unlock(); j(); lk.lock();
+        busy = false; cv.notify_all();
+      }
+    });
+  }
+  void submit(std::function<void()> j) { { std::lock_guard<std::mutex> lk(m); q.push_back(std::move(j)); } cv.notify_all(); }
+  void wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this] { return q.empty() && !busy; }); }
+  void stop() { if (!th.joinable()) return; { std::lock_guard<std::mutex> lk(m); quit = true; } cv.notify_all(); th.join(); }
+};
+
+struct LateIn {
+  sp2::u32 flag;                   // host: prove epoch, release-stored LAST; bit 31 = abort (the host gave up: error path)
+  sp2::u32 round;
+  unsigned char state[64];
+  sp2::u32 flag2;                  // second gate (IPA challenge), same protocol
+  unsigned char pad[52];
+  unsigned char dg[SC_MAX_ROUNDS * 64];
+  unsigned char rdg[64];           // the IPA challenge digest
+};
 struct sp2_prep {
+  HostWorker worker;
   sp2_ctx *ctx = nullptr;
   const sp2_shape *S = nullptr;
   const sp2_ck *ck = nullptr;
@@ -48,7 +88,9 @@ struct sp2_prep {
   uint8_t *h_inbox = nullptr;        // pinned staging of the same layout (+ tau digests)
   size_t inbox_bytes = 0;
   cudaEvent_t ev[9] = {nullptr};
-  cudaEvent_t ev_r1 = nullptr, ev_inv = nullptr, ev_in = nullptr, ev_lz = nullptr, ev_delta = nullptr, ev_q = nullptr;
+  cudaEvent_t ev_r1 = nullptr, ev_inv = nullptr, ev_in = nullptr, ev_lz = nullptr, ev_delta = nullptr, ev_q = nullptr, ev_evalw = nullptr, ev_eq = nullptr, ev_chunks = nullptr;
+  LateIn *h_late = nullptr, *d_late = nullptr;   // pinned, device-visible (k_gate_taus)
+  uint32_t epoch = 0;
   cudaStream_t side2 = nullptr;      // early comm_LZ chain (prove): runs under the inner sum-check's last rounds
   std::vector<void *> owned;
 };
@@ -58,18 +100,54 @@ namespace {
 enum SmallSlot { S_RJOINT = 0, S_EVALW = 1, S_EVALX = 2, S_RLZ = 3, S_IP = 4, S_BLIND_EVAL = 5, S_RDELTA = 6, S_RBETA = 7,
                  S_ZDELTA = 8, S_ZBETA = 9, S_RIPA = 10, S_ERR = 11, S_DENINV = 12, S_COUNT = 16 };
 
-// taus from the host-squeezed 64-byte digests: from_uniform (LE 512-bit mod p), into the sum-check state
-__global__ void k_taus_from_digests(ScState *st, const unsigned char *dg, int l) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= l) return;
-  fe lo, hi;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const unsigned char *p = dg + 64 * i + 4 * k;
-    lo.v[k] = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
-    hi.v[k] = (u32)p[32] | ((u32)p[33] << 8) | ((u32)p[34] << 16) | ((u32)p[35] << 24);
+// ---- the gate: everything the outer sum-check needs from the HOST transcript arrives through pinned, device-visible memory ----
+// The host hashes the commitment rows and squeezes the taus while the device commits / multiplies; the launches of the outer
+// sum-check are enqueued BEFORE that hashing ends, behind k_gate_taus, which waits (bounded) for the host's flag, copies the
+// transcript hand-over (round, state) into the sum-check state and turns the squeezed digests into taus (from_uniform: LE 512-bit
+// mod p).  The ~30 us of launch calls and the H2D copy no longer sit between the last squeeze and the first round.
+__device__ __forceinline__ u32 ld_sys_u32(const void *p) { u32 v; asm volatile("ld.volatile.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__global__ void __launch_bounds__(64) k_gate_taus(ScState *st, const LateIn *late, u32 epoch, int l) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (;;) {
+      const u32 v = ld_sys_u32(&late->flag);
+      if ((v & 0x7fffffffu) == epoch) { if (v >> 31) atomicExch(&st->err, 1u); break; }
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      if (t - t0 > SC_WAIT_NS) { atomicExch(&st->err, 1u); break; }
+      __nanosleep(100);
+    }
+    __threadfence_system();
   }
-  stg_fe(&st->taus[i], Fq::from_uniform(lo, hi));
+  __syncthreads();
+  if (tid < 16) ((u32 *)st->ts.state)[tid] = ld_sys_u32(late->state + 4 * tid);
+  if (tid == 0) { st->ts.round = ld_sys_u32(&late->round); st->ts.pending_len = 0; }
+  if (tid < l) {
+    fe lo, hi;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo.v[k] = ld_sys_u32(late->dg + 64 * tid + 4 * k); hi.v[k] = ld_sys_u32(late->dg + 64 * tid + 32 + 4 * k); }
+    stg_fe(&st->taus[tid], Fq::from_uniform(lo, hi));
+  }
+}
+
+// second gate: the IPA challenge digest (squeezed on the host from the PCS points) -> device memory; k_ipa_finish is enqueued behind it
+__global__ void __launch_bounds__(32) k_gate_ipa(ScState *st, const LateIn *late, u32 epoch, unsigned char *d_dg) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (;;) {
+      const u32 v = ld_sys_u32(&late->flag2);
+      if ((v & 0x7fffffffu) == epoch) { if (v >> 31) atomicExch(&st->err, 1u); break; }
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      if (t - t0 > SC_WAIT_NS) { atomicExch(&st->err, 1u); break; }
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (tid < 16) ((u32 *)d_dg)[tid] = ld_sys_u32(late->rdg + 4 * tid);
 }
 
 // z[num_vars ..] = 1 | X   (spartan.rs:248-253)
@@ -208,10 +286,12 @@ extern "C" {
 
 void sp2_prep_free(sp2_prep *P) {
   if (!P) return;
+  P->worker.stop();
   cudaSetDevice(P->ctx->device);
   cudaStreamSynchronize(P->ctx->stream);
   for (void *p : P->owned) cudaFree(p);
   if (P->h_inbox) cudaFreeHost(P->h_inbox);
+  if (P->h_late) cudaFreeHost(P->h_late);
   for (auto &e : P->ev) if (e) cudaEventDestroy(e);
   if (P->ev_r1) cudaEventDestroy(P->ev_r1);
   if (P->ev_inv) cudaEventDestroy(P->ev_inv);
@@ -219,6 +299,9 @@ void sp2_prep_free(sp2_prep *P) {
   if (P->ev_lz) cudaEventDestroy(P->ev_lz);
   if (P->ev_delta) cudaEventDestroy(P->ev_delta);
   if (P->ev_q) cudaEventDestroy(P->ev_q);
+  if (P->ev_evalw) cudaEventDestroy(P->ev_evalw);
+  if (P->ev_eq) cudaEventDestroy(P->ev_eq);
+  if (P->ev_chunks) cudaEventDestroy(P->ev_chunks);
   if (P->side2) { cudaStreamSynchronize(P->side2); cudaStreamDestroy(P->side2); }
   delete P;
 }
@@ -253,15 +336,20 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
   A(palloc(P, &P->zvec, width));
   P->inbox_bytes = ((size_t)S_COUNT + width + P->rows_total + S->num_public) * sizeof(fe);
   { fe *ib = nullptr; A(palloc(P, &ib, (size_t)S_COUNT + width + P->rows_total + S->num_public)); P->inbox = ib; }
-  // pinned staging: [inbox | tau digests | rest-commitment rows (Jacobian) read back in prove]
-  if (rc == SP2_OK && cudaMallocHost((void **)&P->h_inbox, P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64 + P->rows_total * sizeof(jac)) != cudaSuccess) rc = set_error(ctx, SP2_ERR_CUDA, "cudaMallocHost");
+  // pinned staging: [inbox | (spare) | rest-commitment rows (Jacobian) read back in prove, later the IPA response z_vec]
+  if (rc == SP2_OK && cudaMallocHost((void **)&P->h_inbox, P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64 + std::max<size_t>(P->rows_total * sizeof(jac), width * sizeof(fe))) != cudaSuccess) rc = set_error(ctx, SP2_ERR_CUDA, "cudaMallocHost");
   if (rc == SP2_OK) {
     P->small = P->inbox; P->dvec = P->inbox + S_COUNT; P->blinds = P->dvec + width;
     for (auto &e : P->ev) cudaEventCreate(&e);
     cudaEventCreateWithFlags(&P->ev_r1, cudaEventDisableTiming); cudaEventCreateWithFlags(&P->ev_inv, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&P->ev_in, cudaEventDisableTiming); cudaEventCreateWithFlags(&P->ev_lz, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&P->ev_delta, cudaEventDisableTiming); cudaEventCreateWithFlags(&P->ev_q, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&P->ev_evalw, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&P->ev_eq, cudaEventDisableTiming); cudaEventCreateWithFlags(&P->ev_chunks, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&P->side2, cudaStreamNonBlocking);
+    if (cudaHostAlloc((void **)&P->h_late, sizeof(LateIn), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&P->d_late, P->h_late, 0) != cudaSuccess) rc = set_error(ctx, SP2_ERR_CUDA, "cudaHostAlloc (gate)");
+    else memset(P->h_late, 0, sizeof(LateIn));
   }
   if (rc != SP2_OK) { sp2_prep_free(P); return rc; }
   auto fail = [&](int r) { sp2_prep_free(P); return r; };
@@ -292,6 +380,7 @@ int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *S, const sp2_ck *c
   e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return fail(set_cuda_error(ctx, e, "prep sync", __LINE__));
   if (comm_out && P->cached_rows) memcpy(comm_out, P->comm_cached.data(), P->cached_rows * sizeof(aff));
+  P->worker.start();
   *out = P;
   return SP2_OK;
 }
@@ -322,7 +411,28 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   auto mark = [&](int i) { cudaEventRecord(ev[i], ctx->stream); };
   auto cleanup = [&]() {};
   mark(0);
+  // SP2_PROVE_TRACE=1: host-side timeline of the prove (us since entry) on stderr — which side bounds a phase
+  static const bool trace_on = [] { const char *e = getenv("SP2_PROVE_TRACE"); return e && e[0] == '1'; }();
+  const auto t_entry = std::chrono::steady_clock::now();
+  std::vector<std::pair<const char *, double>> trace;
+  auto tp = [&](const char *what) { if (trace_on) trace.emplace_back(what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_entry).count()); };
 
+  // ---- transcript up to the taus (host; spartan.rs:226-264, bellpepper/r1cs.rs:422-431,491) -----
+  // The ~30 KB of serial Keccak over the cached commitment rows run on the prep state's helper thread, beside the staging and the
+  // enqueues of this phase.
+  sp2h::Transcript ts("SpartanSNARK");
+  auto absorb_head = [&]() {
+    ts.absorb_bytes("vk", vk_digest, 32);
+    ts.absorb_scalars("public_values", public_values, S->num_public);
+    const uint64_t sh_rows = S->num_shared / width, pre_rows = S->num_precommitted / width;
+    if (sh_rows) ts.absorb_commitment_be("comm_W_shared", P->comm_cached_be.data(), sh_rows);
+    if (pre_rows) ts.absorb_commitment_be("comm_W_precommitted", P->comm_cached_be.data() + 64 * sh_rows, pre_rows);
+    memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
+  };
+  // the head is hashed by the prep state's helper thread while this thread enqueues; joined before the rest rows are absorbed
+  // (and on every early return: the job refers to locals)
+  struct Join { HostWorker &w; ~Join() { w.wait(); } } join_head{P->worker};
+  P->worker.submit(absorb_head);
   // ---- per-prove host inputs: one staged copy (randomness, blinds, public values) ------------------
   fe *small = P->small;
   { uint8_t *h = P->h_inbox;
@@ -342,59 +452,94 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   // PCS points of this prove: [comm_LZ, delta, comm_eval_W, beta]
   jac *d_pts = P->points + rows;
   // delta = <d, ck> + r_delta h (ipa.rs:140-146) depends on the prover's randomness only: side stream, under the witness commitment
-  { MsmJob j; memset(&j, 0, sizeof(j)); j.scalars = P->dvec; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = &small[S_RDELTA];
-    SP2_CUDA_OK(cudaEventRecord(P->ev_in, ctx->stream));
+  // (enqueued after the work the host is about to wait for)
+  auto enqueue_delta = [&]() -> int {
+    MsmJob j; memset(&j, 0, sizeof(j)); j.scalars = P->dvec; j.len = (u32)width; j.nextra = 1; j.extra_base[0] = ck->idx_h(); j.extra_scalar[0] = &small[S_RDELTA];
     SP2_CUDA_OK(cudaStreamWaitEvent(ctx->side, P->ev_in, 0));
     SP2_TRY(msm_run(ctx, ck, std::vector<MsmJob>{j}, d_pts + 1, ctx->side, 16, 17));
-    SP2_CUDA_OK(cudaEventRecord(P->ev_delta, ctx->side)); }
+    SP2_CUDA_OK(cudaEventRecord(P->ev_delta, ctx->side));
+    return SP2_OK;
+  };
   // rest section of the witness (NULL: all zero, e.g. pure padding as in the SHA-256 bench circuit)
   if (S->num_rest) {
     if (W_rest) SP2_CUDA_OK(cudaMemcpyAsync(P->W + P->cached_len, W_rest, S->num_rest * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
     else SP2_CUDA_OK(cudaMemsetAsync(P->W + P->cached_len, 0, S->num_rest * sizeof(fe), ctx->stream));
   }
+  SP2_CUDA_OK(cudaEventRecord(P->ev_in, ctx->stream));                      // this prove's inputs are on the device
 
-  // ---- transcript up to the taus (host; spartan.rs:226-264, bellpepper/r1cs.rs:422-431,491) -----
-  // The host hashes the cached commitment rows AFTER the device work of this phase has been enqueued (below), so the
-  // ~30 KB of serial Keccak runs under the rest-section commitment and the SpMV instead of in front of them.
-  sp2h::Transcript ts("SpartanSNARK");
-  auto absorb_head = [&]() {
-    ts.absorb_bytes("vk", vk_digest, 32);
-    ts.absorb_scalars("public_values", public_values, S->num_public);
-    const uint64_t sh_rows = S->num_shared / width, pre_rows = S->num_precommitted / width;
-    if (sh_rows) ts.absorb_commitment_be("comm_W_shared", P->comm_cached_be.data(), sh_rows);
-    if (pre_rows) ts.absorb_commitment_be("comm_W_precommitted", P->comm_cached_be.data() + 64 * sh_rows, pre_rows);
-    memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
-  };
-  // z = W | 1 | X   (spartan.rs:248-253) — enqueued behind the rest-section commitment, whose rows the host is waiting for
-  auto make_z = [&]() -> int {
-    SP2_CUDA_OK(cudaMemcpyAsync(P->z, P->W, nv * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
-    k_z_tail<<<(unsigned)(num_extra + 127) / 128, 128, 0, ctx->stream>>>(P->z + nv, d_X, (u32)S->num_public);
-    SP2_LAUNCH_CHECK();
-    return SP2_OK;
-  };
-  // commit the rest section (r1cs.rs:467-470: blind + commit / commit_zeros)
-  bool spmv_done = false;
+  // commit the rest section (r1cs.rs:467-470: blind + commit / commit_zeros) first — the host waits for these rows; an all-zero rest
+  // section is HyraxPCS::commit_zeros (hyrax_pc.rs:305-319): rows = blind_i * h, no row terms to walk.  (On a side stream beside the
+  // SpMV the MSM's large CTAs starve behind the SpMV's 12k small ones: rows 45 us later, measured.)
+  uint64_t *hj = (uint64_t *)(P->h_inbox + P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64);      // pinned: a true async DMA
   if (rest_rows) {
-    // an all-zero rest section is HyraxPCS::commit_zeros (hyrax_pc.rs:305-319): rows = blind_i * h, no row terms to walk
-    SP2_TRY(sp2_hyrax_commit_dev(ctx, ck, P->W + P->cached_len, W_rest ? S->num_rest : 0, P->blinds + P->cached_rows, rest_rows, P->points + P->cached_rows));
-    uint64_t *hj = (uint64_t *)(P->h_inbox + P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64);      // pinned: a true async DMA
+    SP2_TRY(hyrax_commit_rows(ctx, ck, P->W + P->cached_len, W_rest ? S->num_rest : 0, P->blinds + P->cached_rows, rest_rows, P->points + P->cached_rows,
+                              ctx->stream, 10, 11));
     SP2_CUDA_OK(cudaMemcpyAsync(hj, P->points + P->cached_rows, rest_rows * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
     SP2_CUDA_OK(cudaEventRecord(P->ev_r1, ctx->stream));
-    SP2_TRY(make_z());
-    // Az, Bz, Cz (spartan.rs:271 -> multiply_vec_incremental_into) do not depend on the taus: enqueue them now so they
-    // run while the host normalises / hashes the commitment rows
-    { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
-      SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
-    spmv_done = true;
-    absorb_head();
-    SP2_CUDA_OK(cudaEventSynchronize(P->ev_r1));                            // host sync 1 (rows only)
-    sp2h::batch_normalize(hj, rest_rows, proof->comm_W + 8 * P->cached_rows);
   }
-  if (!spmv_done) { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
-    SP2_TRY(make_z());
-    SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work));
-    absorb_head(); }
-  ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
+  // z = W | 1 | X   (spartan.rs:248-253); Az, Bz, Cz (spartan.rs:271 -> multiply_vec_incremental_into) do not depend on the taus
+  SP2_CUDA_OK(cudaMemcpyAsync(P->z, P->W, nv * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
+  k_z_tail<<<(unsigned)(num_extra + 127) / 128, 128, 0, ctx->stream>>>(P->z + nv, d_X, (u32)S->num_public);
+  SP2_LAUNCH_CHECK();
+  { const fe *base[3] = {P->cached[0], P->cached[1], P->cached[2]};
+    SP2_TRY(spmv3_dev(ctx, S, S->F, P->z, base, P->work)); }
+  SP2_TRY(enqueue_delta());
+  tp("commit, SpMV, delta enqueued");
+
+  const uint32_t epoch = (++P->epoch) & 0x7fffffffu;
+  LateIn *late = P->h_late;
+  // ---- transcript: rest rows, taus (host) ----
+  if (rest_rows) {
+    SP2_CUDA_OK(cudaEventSynchronize(P->ev_r1));                            // host sync 1 (rows only)
+    tp("rest rows on the host");
+    sp2h::batch_normalize(hj, rest_rows, proof->comm_W + 8 * P->cached_rows);
+    tp("rows normalised");
+  }
+  // the rest of the transcript up to the taus goes to the helper thread, behind the head: absorb the rest rows, squeeze the taus into
+  // the gate's mailbox, open the gate — while this thread keeps enqueuing (poly_ABC, inner sum-check, PCS)
+  P->worker.submit([&ts, late, epoch, l, proof, P, rest_rows]() {
+    ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
+    for (int i = 0; i < l; i++) ts.squeeze("t", late->dg + 64 * i);
+    late->round = ts.round; memcpy(late->state, ts.state, 64);
+    __atomic_store_n(&late->flag, epoch, __ATOMIC_RELEASE);                 // open the gate
+  });
+  tp("transcript tail handed to the helper thread");
+
+
+  // ---- outer sum-check (spartan.rs:293 -> sumcheck.rs:502), enqueued behind the gate while the host is still hashing ----
+  proof->num_rounds_x = l; proof->num_rounds_y = nry; proof->num_comm_rows = rows; proof->num_cols = width;
+  ScState *st_outer, *st_inner;
+  { void *p; SP2_TRY(scratch(ctx, 14, sizeof(ScState), &p)); st_outer = (ScState *)p;
+    SP2_TRY(scratch(ctx, 9, sizeof(ScState), &p)); st_inner = (ScState *)p; }
+  { sp2_transcript_state hts0; memset(&hts0, 0, sizeof(hts0));               // (round, state) arrive through the gate
+    const uint64_t zero4[4] = {0, 0, 0, 0};
+    SP2_TRY(sc_state_upload(ctx, &st_outer, zero4, nullptr, (uint32_t)l, &hts0)); }
+  // nothing between the gate's launch and its opening may need an idle device (module loading, allocations): do that now
+  { static unsigned loaded_mask = 0;
+    if (!(loaded_mask >> ctx->device & 1u)) { cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, (const void *)k_gate_taus); cudaFuncGetAttributes(&fa, (const void *)k_outer_to_inner);
+      cudaFuncGetAttributes(&fa, (const void *)k_gate_ipa); cudaFuncGetAttributes(&fa, (const void *)k_ipa_finish); loaded_mask |= 1u << ctx->device; }
+    sumcheck_cubic_preload();
+    SP2_TRY(sumcheck_cubic_reserve(ctx, (uint32_t)l));
+    SP2_TRY(eq_table_reserve(ctx, (uint32_t)l, 19)); }
+  // (the helper thread's tail job, queued above, opens the gate; it cannot fail, and join_head waits for it on every return)
+  k_gate_taus<<<1, 64, 0, ctx->stream>>>(st_outer, P->d_late, epoch, l);
+  SP2_LAUNCH_CHECK();
+  mark(1);
+  mark(2);
+  if (shard) comm->dc.epoch++;
+  SP2_TRY(sumcheck_cubic_enqueue(ctx, st_outer, (uint32_t)l, P->work[0], P->work[1], P->work[2], shard ? &comm->dc : nullptr));
+  // eq(r_x) (spartan.rs:320) needs only the outer challenges: second side stream, beside the outer -> inner transition
+  // multi-GPU: eq(r_x) is replicated (write-only, N entries); each rank builds its columns of poly_ABC
+  fe *d_rx = shard ? P->rx : P->work[0];                                   // the sum-check consumed the tables
+  SP2_CUDA_OK(cudaEventRecord(P->ev_q, ctx->stream));
+  SP2_CUDA_OK(cudaStreamWaitEvent(P->side2, P->ev_q, 0));
+  SP2_TRY(eq_table_dev(ctx, st_outer->r, (uint32_t)l, d_rx, P->side2, 19));
+  SP2_CUDA_OK(cudaEventRecord(P->ev_eq, P->side2));
+  k_outer_to_inner<<<1, 64, 0, ctx->stream>>>(st_outer, st_inner, small, nry);
+  SP2_LAUNCH_CHECK();
+  tp("outer sum-check enqueued (gated)");
+  mark(3);
+
   // the PCS transcript (hyrax_pc.rs:410) re-absorbs all commitment rows; its (round, state) come from the device after the
   // sum-checks, but they enter the hash AFTER the absorbed data, so the rows are hashed now, under the sum-checks
   sp2h::Transcript t2;
@@ -404,36 +549,9 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     for (uint64_t i = P->cached_rows; i < rows; i++) t2.push_point(proof->comm_W + 8 * i);
     t2.push("poly_commitment_end", 19);
   };
-  proof->num_rounds_x = l; proof->num_rounds_y = nry; proof->num_comm_rows = rows; proof->num_cols = width;
-  uint8_t *tau_dg = P->h_inbox + P->inbox_bytes;
-  for (int i = 0; i < l; i++) ts.squeeze("t", tau_dg + 64 * i);
-  mark(1);
-
-  mark(2);
-
-  // ---- outer sum-check (spartan.rs:293 -> sumcheck.rs:502) ---------------------------------------
-  ScState *st_outer, *st_inner;
-  { void *p; SP2_TRY(scratch(ctx, 14, sizeof(ScState), &p)); st_outer = (ScState *)p;
-    SP2_TRY(scratch(ctx, 9, sizeof(ScState), &p)); st_inner = (ScState *)p; }
-  sp2_transcript_state hts; hts.round = ts.round; memcpy(hts.state, ts.state, 64);
-  const uint64_t zero4[4] = {0, 0, 0, 0};
-  SP2_TRY(sc_state_upload(ctx, &st_outer, zero4, nullptr, (uint32_t)l, &hts));
-  void *d_dg; SP2_TRY(scratch(ctx, 8, (size_t)SC_MAX_ROUNDS * 64 + 64, &d_dg));
-  SP2_CUDA_OK(cudaMemcpyAsync(d_dg, tau_dg, (size_t)l * 64, cudaMemcpyHostToDevice, ctx->stream));
-  k_taus_from_digests<<<1, 64, 0, ctx->stream>>>(st_outer, (const unsigned char *)d_dg, l);
-  SP2_LAUNCH_CHECK();
-  if (shard) comm->dc.epoch++;
-  SP2_TRY(sumcheck_cubic_enqueue(ctx, st_outer, (uint32_t)l, P->work[0], P->work[1], P->work[2], shard ? &comm->dc : nullptr));
-  k_outer_to_inner<<<1, 64, 0, ctx->stream>>>(st_outer, st_inner, small, nry);
-  SP2_LAUNCH_CHECK();
-  mark(3);
-
-  // ---- eq(r_x) and poly_ABC (spartan.rs:320-321) ------------------------------------------------
-  // multi-GPU: eq(r_x) is replicated (write-only, N entries); each rank builds its columns of poly_ABC
-  fe *d_rx = shard ? P->rx : P->work[0];                                   // the sum-check consumed the tables
+  // ---- poly_ABC (spartan.rs:321): the long columns' partial sums on the side stream beside k_abc ----
   const uint64_t inner_local = (2 * nv) >> S->shard_k;                     // this rank's share of the virtual 2M-entry tables
-  SP2_TRY(eq_table_dev(ctx, st_outer->r, (uint32_t)l, d_rx));
-  SP2_TRY(abc_dev(ctx, S, d_rx, &small[S_RJOINT], P->abc, shard ? inner_local : nc));
+  SP2_TRY(abc_dev(ctx, S, d_rx, &small[S_RJOINT], P->abc, shard ? inner_local : nc, P->side2, P->ev_eq, P->ev_chunks));
   if (shard) {
     k_z_shard<<<(unsigned)((inner_local + 255) / 256), 256, 0, ctx->stream>>>(P->z, nc, P->zs, inner_local, S->shard_k, S->rank);
     SP2_LAUNCH_CHECK();
@@ -443,10 +561,10 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   // ---- inner sum-check: m+1 rounds over the virtual 2M tables (spartan.rs:330-404) ---------------
   if (shard) { comm->dc.epoch++; SP2_TRY(sumcheck_quad_enqueue(ctx, st_inner, (uint32_t)nry, P->abc, P->zs, ~0ull, P->ev_r1, &comm->dc)); }
   else SP2_TRY(sumcheck_quad_enqueue(ctx, st_inner, (uint32_t)nry, P->abc, P->z, nc, P->ev_r1));
+  SP2_CUDA_OK(cudaEventRecord(P->ev_q, ctx->stream));                       // the inner sum-check is complete
   SP2_CUDA_OK(cudaStreamWaitEvent(ctx->side, P->ev_r1, 0));
   k_den_inv<<<1, 32, 0, ctx->side>>>(st_inner, small);
   SP2_LAUNCH_CHECK();
-  SP2_CUDA_OK(cudaEventRecord(P->ev_inv, ctx->side));
   // ---- comm_LZ early (hyrax_pc.rs:415-444): L = eq(r_y[1..log2 rows]) is complete after inner round 1 + log2(rows), long before the
   // sum-check ends — the bind LZ = L^T W, r_LZ = <L, blinds> and the 2048-term MSM run on a second side stream under the
   // remaining (latency-bound) rounds, on the SMs the pipelined round kernel leaves free
@@ -456,7 +574,6 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     if (shard) {
       // sharded proves: after the whole sum-check (still beside the eval_W / R-table chain of the main stream) — no spinning kernel
       // next to the round kernels that wait for their peers (ranks of one process share the hardware queues)
-      SP2_CUDA_OK(cudaEventRecord(P->ev_q, ctx->stream));
       SP2_CUDA_OK(cudaStreamWaitEvent(P->side2, P->ev_q, 0));
     } else {
       SP2_CUDA_OK(cudaStreamWaitEvent(P->side2, P->ev_r1, 0));
@@ -472,12 +589,17 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     SP2_CUDA_OK(cudaEventRecord(P->ev_lz, P->side2));
   }
   mark(5);
-  SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_inv, 0));
 
-  // ---- eval_W, PCS::prove (hyrax_pc.rs:387-478; ipa.rs:125-153) ----------------------------------
+  // ---- eval_W, PCS::prove (hyrax_pc.rs:387-478; ipa.rs:125-153): two independent chains after the last inner round —
+  // side stream: eval_W (needs 1 / (1 - r_y[0]) from the same stream) -> comm_eval_W;  main stream: R table -> <R, d> -> beta
   { void *chis; SP2_TRY(scratch(ctx, 12, ((size_t)4 << nvz) * sizeof(fe) + 64, &chis));
-    k_eval_w<<<1, 256, 0, ctx->stream>>>(st_inner, P->z + nv, (u32)num_extra, m, (fe *)chis, small);
-    SP2_LAUNCH_CHECK(); }
+    SP2_CUDA_OK(cudaStreamWaitEvent(ctx->side, P->ev_q, 0));
+    k_eval_w<<<1, 256, 0, ctx->side>>>(st_inner, P->z + nv, (u32)num_extra, m, (fe *)chis, small);
+    SP2_LAUNCH_CHECK();
+    memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = &small[S_EVALW];
+    j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = &small[S_BLIND_EVAL];
+    SP2_TRY(msm_run(ctx, ck, std::vector<MsmJob>{j}, d_pts + 2, ctx->side, 16, 17));                   // comm_eval_W
+    SP2_CUDA_OK(cudaEventRecord(P->ev_evalw, ctx->side)); }
   SP2_TRY(eq_table_dev(ctx, ry1 + nvr, (uint32_t)(m - nvr), P->Rtab));
   if (nvr == 0) {
     SP2_CUDA_OK(cudaMemcpyAsync(P->LZ, P->W, width * sizeof(fe), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -485,16 +607,13 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   }
   k_dot<<<1, 256, 0, ctx->stream>>>(P->Rtab, P->dvec, width, &small[S_IP]);
   SP2_LAUNCH_CHECK();
-  std::vector<MsmJob> jobs;
-  memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = &small[S_EVALW];
-  j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = &small[S_BLIND_EVAL];
-  jobs.push_back(j);                                                       // comm_eval_W
   memset(&j, 0, sizeof(j)); j.nextra = 2; j.extra_base[0] = ck->idx_ck_s(); j.extra_scalar[0] = &small[S_IP];
   j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = &small[S_RBETA];
-  jobs.push_back(j);                                                       // beta
-  SP2_TRY(msm_run(ctx, ck, jobs, d_pts + 2));
+  SP2_TRY(msm_run(ctx, ck, std::vector<MsmJob>{j}, d_pts + 3));                                         // beta
   SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_delta, 0));
+  SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_evalw, 0));
   if (nvr > 0) SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_lz, 0));
+  tp("everything up to the PCS points enqueued");
   mark(6);
 
   absorb_poly_com();                                                        // host hashing overlapped with the device work above
@@ -508,11 +627,31 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   SP2_CUDA_OK(cudaMemcpyAsync(h_inner, st_inner, upto, cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(h_small, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
   SP2_CUDA_OK(cudaMemcpyAsync(h_jac, d_pts, 4 * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
-  SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                          // host sync 2
+  tp("poly_com hashed");
+  uint32_t *h_comm_err = (uint32_t *)(h_small + 4 * S_COUNT + 48);          // (pinned: between the PCS points and the second scalar read-back)
+  *h_comm_err = 0;
+  if (shard) SP2_CUDA_OK(cudaMemcpyAsync(h_comm_err, &comm->dc.peer[comm->dc.rank]->err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaEventRecord(P->ev_q, ctx->stream));
+  // the IPA response is enqueued now, behind the second gate: its launch and the read-back are already in the queue when the host
+  // has the challenge
+  void *d_dg; SP2_TRY(scratch(ctx, 8, (size_t)SC_MAX_ROUNDS * 64 + 64, &d_dg));
+  uint64_t *h_zvec = (uint64_t *)(P->h_inbox + P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64);   // pinned (the rest-row staging is free again)
+  struct Gate2Guard { LateIn *late; uint32_t epoch; cudaStream_t st; bool open = false;
+    ~Gate2Guard() { if (!open) { __atomic_store_n(&late->flag2, epoch | 0x80000000u, __ATOMIC_RELEASE); cudaStreamSynchronize(st); } } } gate2{late, epoch, ctx->stream};
+  k_gate_ipa<<<1, 32, 0, ctx->stream>>>(st_inner, P->d_late, epoch, (unsigned char *)d_dg);
+  SP2_LAUNCH_CHECK();
+  k_ipa_finish<<<(unsigned)((width + 255) / 256), 256, 0, ctx->stream>>>((const unsigned char *)d_dg, P->LZ, P->dvec, width, P->zvec, small);
+  SP2_LAUNCH_CHECK();
+  mark(7);
+  SP2_CUDA_OK(cudaMemcpyAsync(h_zvec, P->zvec, width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaMemcpyAsync(h_small + 4 * S_COUNT + 64, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  SP2_CUDA_OK(cudaEventSynchronize(P->ev_q));                               // host sync 2
+  tp("host sync 2 (sum-checks + PCS points)");
   if (h_outer->err || h_inner->err) { cleanup(); return set_error(ctx, SP2_ERR_INTERNAL, "prove: a device-side wait (grid barrier) did not complete within 2 s"); }
-  if (shard) SP2_TRY(comm_check(ctx, comm));
+  if (*h_comm_err) { cleanup(); return set_error(ctx, SP2_ERR_INTERNAL, "sharded sum-check: a peer did not publish its round sums within 2 s (call sp2_comm_reset on every rank)"); }
   const int p_first = nvr > 0 ? 0 : 1;                                      // (no comm_LZ point for a one-row commitment)
   sp2h::batch_normalize(h_jac + 12 * p_first, 4 - p_first, h_pts + 8 * p_first);
+  tp("PCS points normalised");
   if (((uint32_t *)(h_small + 4 * S_ERR))[0] == 5) { cleanup(); return set_error(ctx, SP2_ERR_DIVISION_BY_ZERO, "prove: 1 - r_y[0] = 0"); }
   for (int i = 0; i < l; i++) {                                            // compressed: [c0, c2, c3] (univariate.rs:147-153)
     memcpy(proof->outer_polys + 12 * i, &h_outer->polys[4 * i], 32);
@@ -530,6 +669,7 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   memcpy(proof->delta, p_delta, 64); memcpy(proof->beta, p_beta, 64);
 
   // ---- transcript tail on the host: poly_com rows, IPA absorbs, r (hyrax_pc.rs:410; ipa.rs:134-153) ----
+  tp("proof fields copied");
   t2.set_state((uint16_t)h_inner->ts.round, h_inner->ts.state);
   t2.dom_sep("inner product argument (linear)");
   t2.push("U", 1); t2.push_point(comm_LZ); t2.push_point(p_ceval);
@@ -537,13 +677,16 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   t2.absorb_point("beta", p_beta);
   uint8_t rdg[64];
   t2.squeeze("r", rdg);
-  SP2_CUDA_OK(cudaMemcpyAsync(d_dg, rdg, 64, cudaMemcpyHostToDevice, ctx->stream));
-  k_ipa_finish<<<(unsigned)((width + 255) / 256), 256, 0, ctx->stream>>>((const unsigned char *)d_dg, P->LZ, P->dvec, width, P->zvec, small);
-  SP2_LAUNCH_CHECK();
-  mark(7);
-  SP2_CUDA_OK(cudaMemcpyAsync(proof->z_vec, P->zvec, width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
-  SP2_CUDA_OK(cudaMemcpyAsync(h_small, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  tp("IPA challenge squeezed");
+  memcpy(late->rdg, rdg, 64);
+  __atomic_store_n(&late->flag2, epoch, __ATOMIC_RELEASE);                  // open the second gate
+  gate2.open = true;
+  tp("IPA challenge sent");
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                          // host sync 3
+  tp("host sync 3 (done)");
+  if (trace_on) { for (auto &e : trace) fprintf(stderr, "[sp2 prove] %9.1f us  %s\n", e.second, e.first); }
+  memcpy(proof->z_vec, h_zvec, width * sizeof(fe));
+  h_small += 4 * S_COUNT + 64;
   memcpy(proof->z_delta, h_small + 4 * S_ZDELTA, 32);
   memcpy(proof->z_beta, h_small + 4 * S_ZBETA, 32);
   if (phase_ms) {

@@ -179,18 +179,30 @@ int spmv3_dev(sp2_ctx *ctx, const sp2_shape *S, const DevMatrix *mats, const fe 
   return SP2_OK;
 }
 
-int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe *d_out, uint64_t out_len) {
+// side / ev_rx / ev_chunks (optional): d_rx is produced on `side` (ev_rx recorded there); the partial sums of the long columns, which
+// need only d_rx, then run on `side` beside k_abc, and the main stream joins before the finish kernel
+int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe *d_out, uint64_t out_len, cudaStream_t side, cudaEvent_t ev_rx,
+            cudaEvent_t ev_chunks) {
   AbcArgs a;
   for (int k = 0; k < 3; k++) { a.ptr[k] = S->T[k].ptr; a.ent[k] = S->T[k].ent; a.dict[k] = S->T[k].dict; }
   const u32 ncols = (u32)S->cols_local;                    // == num_cols on a single GPU
   if (out_len < ncols) return set_error(ctx, SP2_ERR_INVALID_INPUT_LENGTH, "abc: output shorter than num_vars + num_extra");
   if (out_len > ncols) SP2_CUDA_OK(cudaMemsetAsync(d_out + ncols, 0, (out_len - ncols) * sizeof(fe), ctx->stream));
+  const bool chunks = S->nlong_cols && S->nchunks;
+  if (side) {
+    if (chunks) {
+      k_abc_long_chunks<<<S->nchunks, 256, 0, side>>>(a, S->chunks, d_rx, S->chunk_partial);
+      SP2_LAUNCH_CHECK();
+      SP2_CUDA_OK(cudaEventRecord(ev_chunks, side));
+    }
+    SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ev_rx, 0));
+  }
   k_abc<<<(ncols + 255) / 256, 256, 0, ctx->stream>>>(a, ncols, S->col_order, d_rx, d_r, d_out);
   SP2_LAUNCH_CHECK();
   if (S->nlong_cols) {
-    if (S->nchunks) {
-      k_abc_long_chunks<<<S->nchunks, 256, 0, ctx->stream>>>(a, S->chunks, d_rx, S->chunk_partial);
-      SP2_LAUNCH_CHECK();
+    if (chunks) {
+      if (side) SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ev_chunks, 0));
+      else { k_abc_long_chunks<<<S->nchunks, 256, 0, ctx->stream>>>(a, S->chunks, d_rx, S->chunk_partial); SP2_LAUNCH_CHECK(); }
     }
     k_abc_long_finish<<<S->nlong_cols, 32, 0, ctx->stream>>>(S->long_cols, S->chunk_first, S->chunk_partial, d_r, d_out);
     SP2_LAUNCH_CHECK();

@@ -55,5 +55,6 @@ struct sp2_shape {
 
 namespace sp2 {
 int spmv3_dev(sp2_ctx *ctx, const sp2_shape *S, const DevMatrix *mats, const fe *d_z, const fe *const *base, fe *const *out);
-int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe *d_out, uint64_t out_len);
+int abc_dev(sp2_ctx *ctx, const sp2_shape *S, const fe *d_rx, const fe *d_r, fe *d_out, uint64_t out_len, cudaStream_t side = nullptr,
+            cudaEvent_t ev_rx = nullptr, cudaEvent_t ev_chunks = nullptr);
 }  // namespace sp2

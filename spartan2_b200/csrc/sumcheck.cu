@@ -1837,6 +1837,30 @@ static int shard_gather(sp2_ctx *ctx, const DevComm &dc, fe *const *src, int nta
   return SP2_OK;
 }
 
+// The prover enqueues the cubic sum-check while a kernel in front of it waits for the HOST (prover.cu: k_gate_taus).  Nothing on the
+// enqueue path may then need the device to go idle: (a) with CUDA's lazy module loading the first launch of a kernel can require a
+// context synchronisation — the kernels are loaded beforehand; (b) scratch growth is an allocation — the slots are reserved beforehand.
+template <class K> static void preload_one(K k) { cudaFuncAttributes a; cudaFuncGetAttributes(&a, (const void *)k); }
+void sumcheck_cubic_preload() {
+  static unsigned done_mask = 0;                     // per device (the loading is per CUDA context)
+  int dev = 0; cudaGetDevice(&dev);
+  if (done_mask >> dev & 1u) return;
+  preload_one(k_cubic_init); preload_one(k_cubic_persist); preload_one(k_cubic_mid_pipe); preload_one(k_cubic_tail_pipe); preload_one(k_cubic_tail);
+  preload_one(k_cubic_round<true, 0>); preload_one(k_cubic_round<true, 1>); preload_one(k_cubic_round<false, 0>); preload_one(k_cubic_round<false, 1>);
+  preload_one(k_cubic_round_roles<true>); preload_one(k_cubic_round_roles<false>);
+  preload_one(k_shard_gather); preload_one(k_shard_barrier);
+  cudaFuncSetAttribute((const void *)k_cubic_mid_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  done_mask |= 1u << dev;
+}
+int sumcheck_cubic_reserve(sp2_ctx *ctx, uint32_t l) {
+  const int first_half = (int)l / 2, second_half = (int)l - first_half;
+  const size_t nleft = (size_t)1 << (first_half > 0 ? first_half : 1), nright = (size_t)2 << second_half;
+  void *p;
+  SP2_TRY(scratch(ctx, 13, (nleft + nright) * sizeof(fe), &p));
+  SP2_TRY(scratch(ctx, 7, 3 * (SC_ROLE_LEN / 2) * sizeof(fe), &p));
+  return SP2_OK;
+}
+
 // enqueue the whole cubic sum-check on ctx->stream (state already on the device, taus in st->taus)
 int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C, const DevComm *dcp) {
   const int first_half = (int)l / 2, second_half = (int)l - first_half;

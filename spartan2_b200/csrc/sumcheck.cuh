@@ -81,6 +81,9 @@ int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uin
                       uint64_t *claims, int nclaims, uint32_t l);
 // dc: nullptr for a single GPU; otherwise A, B, C are this rank's cyclic shards (2^(l-k) entries) of the global tables
 int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C, const DevComm *dc = nullptr);
+// before enqueuing behind a kernel that waits for the host: load the kernels / reserve the scratch (sumcheck.cu)
+void sumcheck_cubic_preload();
+int sumcheck_cubic_reserve(sp2_ctx *ctx, uint32_t l);
 // nvalid: table entries at index >= nvalid are unmaterialised zeros (~0ull: dense tables)
 // after_first (optional): recorded once the launch that produces r[0] has been enqueued
 int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe *B, uint64_t nvalid, cudaEvent_t after_first,

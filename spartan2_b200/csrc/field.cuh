@@ -296,6 +296,24 @@ struct Fq : Field<FqParams> {
     for (int i = 1; i < 16; i++) a.v[i] = addc_cc(a.v[i], w[i]);
     a.v[16] = addc(a.v[16], 0);
   }
+  // a += x*y and b += x*y with one product
+  SP2_HD static void mul_acc2(acc &a, acc &b, const fe &x, const fe &y) {
+#if defined(__CUDA_ARCH__) && defined(SP2_FQ_OUTLINE)
+    const w16 ww = mul_wide_ni(x, y);
+    const u32 (&w)[16] = ww.v;
+#else
+    u32 w[16];
+    mul_wide(w, x, y);
+#endif
+    a.v[0] = add_cc(a.v[0], w[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) a.v[i] = addc_cc(a.v[i], w[i]);
+    a.v[16] = addc(a.v[16], 0);
+    b.v[0] = add_cc(b.v[0], w[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) b.v[i] = addc_cc(b.v[i], w[i]);
+    b.v[16] = addc(b.v[16], 0);
+  }
   SP2_HD static void acc_add(acc &a, const acc &b) {
     a.v[0] = add_cc(a.v[0], b.v[0]);
 #pragma unroll

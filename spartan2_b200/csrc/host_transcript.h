@@ -156,29 +156,40 @@ inline void mod_sub(uint64_t x[4], const uint64_t y[4], const uint64_t mod[4]) {
 // Montgomery inverse a R -> a^-1 R by the binary extended Euclid on plain integers (~4 us on a host core; the Fermat ladder is
 // 384 Montgomery multiplications, ~15 us — and this inversion sits on the prove's critical path twice: the rest-commitment
 // rows before the taus, the PCS points before the IPA challenge).  x = (aR)^-1 as an integer, then x * R^3 / R = a^-1 R.  inv(0) = 0.
-inline void fp_inv(const uint64_t a[4], uint64_t o[4]) {
-  if (!(a[0] | a[1] | a[2] | a[3])) { memset(o, 0, 32); return; }
-  struct Consts { uint64_t R3[4]; Consts() {                                    // R^3 mod p = mont(mont(R2', R2'), R2') with R2' = R^2: by doubling
-      uint64_t r[4] = {1, 0, 0, 0};
-      for (int i = 0; i < 768; i++) {
-        uint64_t d[4]; unsigned carry = 0;
-        for (int j = 0; j < 4; j++) { const uint64_t v = r[j]; d[j] = (v << 1) | carry; carry = (unsigned)(v >> 63); }
-        uint64_t e[4]; unsigned borrow = 0;
-        for (int j = 0; j < 4; j++) { u128 x = (u128)d[j] - FP_MOD[j] - borrow; e[j] = (uint64_t)x; borrow = (unsigned)((x >> 64) & 1); }
-        const bool ge = carry || !borrow;
-        for (int j = 0; j < 4; j++) r[j] = ge ? e[j] : d[j];
-      }
-      memcpy(R3, r, 32); } };
-  static const Consts K;
-  uint64_t u[4], v[4], x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
-  memcpy(u, a, 32); memcpy(v, FP_MOD, 32);
-  while (!u256_is_one(u) && !u256_is_one(v)) {
-    while (!(u[0] & 1)) { u256_shr1(u, 0); mod_half(x1, FP_MOD); }
-    while (!(v[0] & 1)) { u256_shr1(v, 0); mod_half(x2, FP_MOD); }
-    if (u256_ge(u, v)) { u256_sub(u, v); mod_sub(x1, x2, FP_MOD); }
-    else { u256_sub(v, u); mod_sub(x2, x1, FP_MOD); }
+inline void pow2_mod(int k, const uint64_t mod[4], uint64_t out[4]) {         // 2^k mod p by doubling
+  uint64_t r[4] = {1, 0, 0, 0};
+  for (int i = 0; i < k; i++) {
+    uint64_t d[4]; unsigned carry = 0;
+    for (int j = 0; j < 4; j++) { const uint64_t v = r[j]; d[j] = (v << 1) | carry; carry = (unsigned)(v >> 63); }
+    uint64_t e[4]; unsigned borrow = 0;
+    for (int j = 0; j < 4; j++) { u128 x = (u128)d[j] - mod[j] - borrow; e[j] = (uint64_t)x; borrow = (unsigned)((x >> 64) & 1); }
+    const bool ge = carry || !borrow;
+    for (int j = 0; j < 4; j++) r[j] = ge ? e[j] : d[j];
   }
-  fp_mul(u256_is_one(u) ? x1 : x2, K.R3, o);
+  memcpy(out, r, 32);
+}
+inline void mont_inv(const uint64_t a[4], const uint64_t mod[4], uint64_t minv, const uint64_t R3[4], uint64_t o[4]) {
+  if (!(a[0] | a[1] | a[2] | a[3])) { memset(o, 0, 32); return; }
+  uint64_t u[4], v[4], x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  memcpy(u, a, 32); memcpy(v, mod, 32);
+  while (!u256_is_one(u) && !u256_is_one(v)) {
+    while (!(u[0] & 1)) { u256_shr1(u, 0); mod_half(x1, mod); }
+    while (!(v[0] & 1)) { u256_shr1(v, 0); mod_half(x2, mod); }
+    if (u256_ge(u, v)) { u256_sub(u, v); mod_sub(x1, x2, mod); }
+    else { u256_sub(v, u); mod_sub(x2, x1, mod); }
+  }
+  mont_mul(u256_is_one(u) ? x1 : x2, R3, mod, minv, o);
+}
+inline void fp_inv(const uint64_t a[4], uint64_t o[4]) {
+  struct Consts { uint64_t R3[4]; Consts() { pow2_mod(768, FP_MOD, R3); } };   // (function-local static: thread-safe one-time initialisation)
+  static const Consts K;
+  mont_inv(a, FP_MOD, FP_INV, K.R3, o);
+}
+// the same for the scalar field (the prover's tau inverses: sumcheck.cu derives t(1) from the running claim, sumcheck.rs:1277-1324)
+inline void fq_inv(const uint64_t a[4], uint64_t o[4]) {
+  struct Consts { uint64_t R3[4]; Consts() { pow2_mod(768, FQ_MOD, R3); } };
+  static const Consts K;
+  mont_inv(a, FQ_MOD, FQ_INV, K.R3, o);
 }
 // n Jacobian points (x,y,z: 12 limbs each) -> affine (x,y: 8 limbs each), identity (z = 0) -> all zero;
 // one inversion for the whole batch (Montgomery's trick)

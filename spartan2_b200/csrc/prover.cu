@@ -65,6 +65,8 @@ struct LateIn {
   unsigned char pad[52];
   unsigned char dg[SC_MAX_ROUNDS * 64];
   unsigned char rdg[64];           // the IPA challenge digest
+  unsigned char pad3[32];
+  sp2::ScTinvMail mail;            // third mailbox: the inverses of the first taus (t(1) from the claim, sumcheck.cuh), Montgomery limbs
 };
 struct sp2_prep {
   HostWorker worker;
@@ -106,8 +108,10 @@ enum SmallSlot { S_RJOINT = 0, S_EVALW = 1, S_EVALX = 2, S_RLZ = 3, S_IP = 4, S_
 // transcript hand-over (round, state) into the sum-check state and turns the squeezed digests into taus (from_uniform: LE 512-bit
 // mod p).  The ~30 us of launch calls and the H2D copy no longer sit between the last squeeze and the first round.
 __device__ __forceinline__ u32 ld_sys_u32(const void *p) { u32 v; asm volatile("ld.volatile.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__global__ void __launch_bounds__(64) k_gate_taus(ScState *st, const LateIn *late, u32 epoch, int l) {
+__global__ void __launch_bounds__(64) k_gate_taus(ScState *st, const LateIn *late, u32 epoch, int l, int derive_max) {
+  __shared__ int tau_zero;
   const int tid = threadIdx.x;
+  if (tid == 0) tau_zero = 0;
   if (tid == 0) {
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -127,10 +131,14 @@ __global__ void __launch_bounds__(64) k_gate_taus(ScState *st, const LateIn *lat
     fe lo, hi;
 #pragma unroll
     for (int k = 0; k < 8; k++) { lo.v[k] = ld_sys_u32(late->dg + 64 * tid + 4 * k); hi.v[k] = ld_sys_u32(late->dg + 64 * tid + 32 + 4 * k); }
-    stg_fe(&st->taus[tid], Fq::from_uniform(lo, hi));
+    const fe tau = Fq::from_uniform(lo, hi);
+    stg_fe(&st->taus[tid], tau);
+    if (tid < derive_max && Fq::is_zero(tau)) tau_zero = 1;
   }
+  __syncthreads();
+  // the streaming rounds derive t(1) from the claim unless one of their taus is zero (the host takes the same decision when it inverts them)
+  if (tid == 0) { st->derive_rounds = tau_zero ? 0u : (u32)derive_max; stg_fe(&st->tclaim, ldg_fe(&st->claim)); }
 }
-
 // second gate: the IPA challenge digest (squeezed on the host from the PCS points) -> device memory; k_ipa_finish is enqueued behind it
 __global__ void __launch_bounds__(32) k_gate_ipa(ScState *st, const LateIn *late, u32 epoch, unsigned char *d_dg) {
   const int tid = threadIdx.x;
@@ -497,11 +505,30 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   }
   // the rest of the transcript up to the taus goes to the helper thread, behind the head: absorb the rest rows, squeeze the taus into
   // the gate's mailbox, open the gate — while this thread keeps enqueuing (poly_ABC, inner sum-check, PCS)
-  P->worker.submit([&ts, late, epoch, l, proof, P, rest_rows]() {
+  // (SP2_NO_DERIVE=1: all three sums directly in every round — measurement switch)
+  static const bool derive_on = [] { const char *e = getenv("SP2_NO_DERIVE"); return !(e && e[0] == '1'); }();
+  const uint32_t derive_max = (shard || !derive_on) ? 0u : std::min<uint32_t>(SC_DERIVE_MAX, sumcheck_cubic_persist_rounds(ctx, (uint32_t)l));
+  P->worker.submit([&ts, late, epoch, l, proof, P, rest_rows, derive_max]() {
     ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
     for (int i = 0; i < l; i++) ts.squeeze("t", late->dg + 64 * i);
     late->round = ts.round; memcpy(late->state, ts.state, 64);
     __atomic_store_n(&late->flag, epoch, __ATOMIC_RELEASE);                 // open the gate
+    // then, off the critical path (the first streaming round takes ~60 us): the inverses of the first taus, one inversion for all
+    uint32_t n = derive_max;
+    uint64_t tau[SC_DERIVE_MAX][4], pre[SC_DERIVE_MAX][4], acc[4], inv[4];
+    for (uint32_t i = 0; i < n; i++) { sp2h::fq_from_uniform(late->dg + 64 * i, tau[i]); if (!(tau[i][0] | tau[i][1] | tau[i][2] | tau[i][3])) n = 0; }
+    if (n) {
+      memcpy(acc, tau[0], 32);
+      for (uint32_t i = 1; i < n; i++) { memcpy(pre[i], acc, 32); sp2h::mont_mul(acc, tau[i], sp2h::FQ_MOD, sp2h::FQ_INV, acc); }
+      sp2h::fq_inv(acc, inv);
+      for (uint32_t i = n; i-- > 1;) {
+        uint64_t ti[4]; sp2h::mont_mul(inv, pre[i], sp2h::FQ_MOD, sp2h::FQ_INV, ti); memcpy(late->mail.tinv[i], ti, 32);
+        sp2h::mont_mul(inv, tau[i], sp2h::FQ_MOD, sp2h::FQ_INV, inv);
+      }
+      memcpy(late->mail.tinv[0], inv, 32);
+    }
+    late->mail.n = n;
+    __atomic_store_n(&late->mail.flag, epoch, __ATOMIC_RELEASE);
   });
   tp("transcript tail handed to the helper thread");
 
@@ -522,12 +549,17 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
     SP2_TRY(sumcheck_cubic_reserve(ctx, (uint32_t)l));
     SP2_TRY(eq_table_reserve(ctx, (uint32_t)l, 19)); }
   // (the helper thread's tail job, queued above, opens the gate; it cannot fail, and join_head waits for it on every return)
-  k_gate_taus<<<1, 64, 0, ctx->stream>>>(st_outer, P->d_late, epoch, l);
+  // SP2_NO_GATES=1 (profilers that serialise kernel launches block the launching thread until a kernel ends: a gate opened by
+  // that same thread would run into its 2 s bound): the gates are launched only once their flags are set
+  static const bool gates = [] { const char *e = getenv("SP2_NO_GATES"); return !(e && e[0] == '1'); }();
+  if (!gates) P->worker.wait();
+  k_gate_taus<<<1, 64, 0, ctx->stream>>>(st_outer, P->d_late, epoch, l, (int)derive_max);
   SP2_LAUNCH_CHECK();
   mark(1);
   mark(2);
   if (shard) comm->dc.epoch++;
-  SP2_TRY(sumcheck_cubic_enqueue(ctx, st_outer, (uint32_t)l, P->work[0], P->work[1], P->work[2], shard ? &comm->dc : nullptr));
+  SP2_TRY(sumcheck_cubic_enqueue(ctx, st_outer, (uint32_t)l, P->work[0], P->work[1], P->work[2], shard ? &comm->dc : nullptr,
+                                 derive_max ? &P->d_late->mail : nullptr, epoch));
   // eq(r_x) (spartan.rs:320) needs only the outer challenges: second side stream, beside the outer -> inner transition
   // multi-GPU: eq(r_x) is replicated (write-only, N entries); each rank builds its columns of poly_ABC
   fe *d_rx = shard ? P->rx : P->work[0];                                   // the sum-check consumed the tables
@@ -638,16 +670,25 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   uint64_t *h_zvec = (uint64_t *)(P->h_inbox + P->inbox_bytes + SC_MAX_ROUNDS * 64 + 64);   // pinned (the rest-row staging is free again)
   struct Gate2Guard { LateIn *late; uint32_t epoch; cudaStream_t st; bool open = false;
     ~Gate2Guard() { if (!open) { __atomic_store_n(&late->flag2, epoch | 0x80000000u, __ATOMIC_RELEASE); cudaStreamSynchronize(st); } } } gate2{late, epoch, ctx->stream};
-  k_gate_ipa<<<1, 32, 0, ctx->stream>>>(st_inner, P->d_late, epoch, (unsigned char *)d_dg);
-  SP2_LAUNCH_CHECK();
-  k_ipa_finish<<<(unsigned)((width + 255) / 256), 256, 0, ctx->stream>>>((const unsigned char *)d_dg, P->LZ, P->dvec, width, P->zvec, small);
-  SP2_LAUNCH_CHECK();
-  mark(7);
-  SP2_CUDA_OK(cudaMemcpyAsync(h_zvec, P->zvec, width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
-  SP2_CUDA_OK(cudaMemcpyAsync(h_small + 4 * S_COUNT + 64, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+  auto enqueue_ipa = [&]() -> int {
+    k_gate_ipa<<<1, 32, 0, ctx->stream>>>(st_inner, P->d_late, epoch, (unsigned char *)d_dg);
+    SP2_LAUNCH_CHECK();
+    k_ipa_finish<<<(unsigned)((width + 255) / 256), 256, 0, ctx->stream>>>((const unsigned char *)d_dg, P->LZ, P->dvec, width, P->zvec, small);
+    SP2_LAUNCH_CHECK();
+    mark(7);
+    SP2_CUDA_OK(cudaMemcpyAsync(h_zvec, P->zvec, width * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    SP2_CUDA_OK(cudaMemcpyAsync(h_small + 4 * S_COUNT + 64, small, S_COUNT * sizeof(fe), cudaMemcpyDeviceToHost, ctx->stream));
+    return SP2_OK;
+  };
+  if (gates) SP2_TRY(enqueue_ipa());
   SP2_CUDA_OK(cudaEventSynchronize(P->ev_q));                               // host sync 2
   tp("host sync 2 (sum-checks + PCS points)");
-  if (h_outer->err || h_inner->err) { cleanup(); return set_error(ctx, SP2_ERR_INTERNAL, "prove: a device-side wait (grid barrier) did not complete within 2 s"); }
+  if (h_outer->err || h_inner->err) {
+    char msg[640];
+    snprintf(msg, sizeof(msg), "prove: a device-side wait (grid barrier / gate) did not complete within 2 s [outer err %u arrived %u released %u mid %u derive %u | inner err %u arrived %u released %u mid %u r_ready %u]",
+             h_outer->err, h_outer->arrived, h_outer->released, h_outer->mid_released, h_outer->derive_rounds,
+             h_inner->err, h_inner->arrived, h_inner->released, h_inner->mid_released, h_inner->r_ready);
+    cleanup(); return set_error(ctx, SP2_ERR_INTERNAL, msg); }
   if (*h_comm_err) { cleanup(); return set_error(ctx, SP2_ERR_INTERNAL, "sharded sum-check: a peer did not publish its round sums within 2 s (call sp2_comm_reset on every rank)"); }
   const int p_first = nvr > 0 ? 0 : 1;                                      // (no comm_LZ point for a one-row commitment)
   sp2h::batch_normalize(h_jac + 12 * p_first, 4 - p_first, h_pts + 8 * p_first);
@@ -681,6 +722,7 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   memcpy(late->rdg, rdg, 64);
   __atomic_store_n(&late->flag2, epoch, __ATOMIC_RELEASE);                  // open the second gate
   gate2.open = true;
+  if (!gates) SP2_TRY(enqueue_ipa());
   tp("IPA challenge sent");
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));                          // host sync 3
   tp("host sync 3 (done)");

@@ -50,6 +50,10 @@ struct FinSmem {
   u64 dg[8];                  // lo || hi digests
   fe g[8];
   fe ch;
+  fe tq[3];                   // the round's t(0), tb, t(inf) for the off-path claim update (cubic_bound)
+  fe lt[SC_DERIVE_MAX];       // derived t(1): (1 - tau_i) / tau_i per streaming round ...
+  fe ct;                      // ... and t_{i-1}(r_{i-1}) / tau_i of the round being evaluated: t(1) = ct - lt_i t(0)
+  u32 tinvw[SC_DERIVE_MAX * 8];   // the host's tau inverses (ScTinvMail), fetched once
   fe red[3 * 32];
   int is_last;
 };
@@ -61,6 +65,7 @@ __device__ __forceinline__ fe ld_state(const fe *p) {   // device-produced scala
   r.v[4] = (u32)c; r.v[5] = (u32)(c >> 32); r.v[6] = (u32)d; r.v[7] = (u32)(d >> 32);
   return r;
 }
+__device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) { u32 v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 // out-of-line multiply for the serial scalar tail: keeps the finaliser's code (and its cold
 // instruction-cache footprint) small
 __device__ __noinline__ void fq_mul_ni(fe *out, const fe *a, const fe *b) { *out = Fq::mul(*a, *b); }
@@ -259,12 +264,33 @@ __device__ __forceinline__ fe sc_squeeze(ScState *st, FinSmem &sm, const fe &can
 // serial multiplications that only the next round's FINALISER reads) and cubic_claims run afterwards on a thread that
 // has no pair work, overlapped with the next round (persistent kernels: after the grid release; tail kernels: the
 // scalar warp at the start of the next round).
-__device__ __forceinline__ fe cubic_finalize_pre(ScState *st, int round1, const fe (&x)[3], FinSmem &sm) {
+// derive: x[1] was not summed; t(1) = (t_{i-1}(r_{i-1}) - (1 - tau_i) t(0)) / tau_i  (derive_from_claim, sumcheck.rs:1277-1324, with the
+// eq prefix divided out on both sides and the inversion done once per prove on the host)
+__device__ __forceinline__ u32 ld_sys_word(const u32 *p) { u32 v; asm volatile("ld.volatile.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ fe sm_tinv(const FinSmem &sm, int i) { fe r; for (int k = 0; k < 8; k++) r.v[k] = sm.tinvw[8 * i + k]; return r; }
+// CTA 0, warp 0, once per kernel, while the other CTAs are still arriving at the first derived round's barrier: wait (bounded) for the
+// host's mailbox, fetch every inverse in one PCIe round trip, and prepare lt_i = (1 - tau_i) / tau_i and ct = claim / tau_1
+__device__ __forceinline__ void derive_prefetch(ScState *st, FinSmem &sm, const ScTinvMail *mail, u32 mail_epoch, int first_round1, int derive_rounds) {
+  const int lane = threadIdx.x;
+  if (lane == 0) spin_until([=] { return ld_sys_word(&mail->flag) == mail_epoch; }, &st->err);
+  __syncwarp();
+  sm.tinvw[lane] = ld_sys_word(&mail->tinv[0][0] + lane); sm.tinvw[lane + 32] = ld_sys_word(&mail->tinv[0][0] + lane + 32);
+  __syncwarp();
+  if (lane < derive_rounds) sm.lt[lane] = mul_ni(Fq::sub(Fq::one(), ld_state(&st->taus[lane])), sm_tinv(sm, lane));
+  if (lane == 31) sm.ct = mul_ni(ld_state(&st->tclaim), sm_tinv(sm, first_round1 - 1));
+  __syncwarp();
+}
+__device__ __forceinline__ fe cubic_finalize_pre(ScState *st, int round1, const fe (&x)[3], FinSmem &sm, bool derive = false) {
   const int tid = threadIdx.x, i = round1 - 1;
   fe canon = Fq::zero();
   SC_STAMP(1);
   if (tid < 32) {
-    const fe tb = Fq::sub(Fq::sub(x[1], x[0]), x[2]);
+    fe x1 = x[1];
+    if (derive) {
+      x1 = Fq::sub(sm.ct, mul_ni(sm.lt[i], x[0]));                          // one multiplication on the critical path
+    }
+    const fe tb = Fq::sub(Fq::sub(x1, x[0]), x[2]);
+    if (tid == 0) { sm.tq[0] = x[0]; sm.tq[1] = tb; sm.tq[2] = x[2]; }
     if (tid < 6) {            // L0*t0, L0*tb, SL*t0, L0*tinf, SL*tb, SL*tinf
       const bool use_sl = (tid == 2) | (tid == 4) | (tid == 5);
       const fe v = fe_sel(tid == 0 || tid == 2, x[0], fe_sel(tid == 1 || tid == 4, tb, x[2]));
@@ -286,8 +312,10 @@ __device__ __forceinline__ fe cubic_finalize_pre(ScState *st, int round1, const 
   return r;
 }
 // bound(): p <- p * (1 - tau - r + 2 r tau) = p * l(r)   (sumcheck.rs:1399-1405), and the next round's L0 / SL.  One thread.
-__device__ __forceinline__ void cubic_bound(ScState *st, int round1, int l, const fe &r) {
+__device__ __forceinline__ void cubic_bound(ScState *st, int round1, int l, const fe &r, FinSmem *dsm = nullptr) {
   const int i = round1 - 1;
+  // dsm: the next round derives its t(1) from t_i(r_i) = t(0) + r (tb + r t(inf)), pre-divided by its tau
+  if (dsm) dsm->ct = mul_ni(Fq::add(dsm->tq[0], mul_ni(r, Fq::add(dsm->tq[1], mul_ni(r, dsm->tq[2])))), sm_tinv(*dsm, round1));
   const fe tau = ld_state(&st->taus[i]);
   const fe l0 = Fq::sub(Fq::one(), tau), sl = Fq::sub(tau, l0);
   const fe pn = mul_ni(ld_state(&st->p), Fq::add(l0, mul_ni(sl, r)));
@@ -319,7 +347,7 @@ __device__ __forceinline__ void cubic_finalize(ScState *st, int round1, int l, c
 // one (fused bind +) evaluation of a pair; accumulates E * (t(0), t(1), t(inf)) terms
 template <bool FUSED>
 __device__ __forceinline__ void cubic_pair(fe *A, fe *B, fe *C, u64 id, u64 P, const fe &r, const fe &w,
-                                           Fq::acc &acc0, Fq::acc &acc1, Fq::acc &acci) {
+                                           Fq::acc &acc0, Fq::acc &acc1, Fq::acc &acci, bool skip1 = false) {
   fe a0, a1, b0, b1, c0, c1;
   if (FUSED) {
     const fe a00 = ldg_fe(A + id), a01 = ldg_fe(A + id + P), a10 = ldg_fe(A + id + 2 * P), a11 = ldg_fe(A + id + 3 * P);
@@ -334,10 +362,11 @@ __device__ __forceinline__ void cubic_pair(fe *A, fe *B, fe *C, u64 id, u64 P, c
   } else {
     a0 = ldg_fe(A + id); a1 = ldg_fe(A + id + P);
     b0 = ldg_fe(B + id); b1 = ldg_fe(B + id + P);
-    c0 = ldg_fe(C + id); c1 = ldg_fe(C + id + P);
+    c0 = ldg_fe(C + id);
+    if (!skip1) c1 = ldg_fe(C + id + P);        // (t(1) derived: round 1 reads 2.5 tables, as the reference does)
   }
   Fq::mul_acc(acc0, w, Fq::sub(Fq::mul(a0, b0), c0));
-  Fq::mul_acc(acc1, w, Fq::sub(Fq::mul(a1, b1), c1));
+  if (!skip1) Fq::mul_acc(acc1, w, Fq::sub(Fq::mul(a1, b1), c1));     // (skip1: t(1) is derived from the claim, warp-uniform)
   Fq::mul_acc(acci, w, Fq::mul(Fq::sub(a1, a0), Fq::sub(b1, b0)));
 }
 
@@ -345,7 +374,7 @@ __device__ __forceinline__ void cubic_pair(fe *A, fe *B, fe *C, u64 id, u64 P, c
 // (second half, sumcheck.rs:1107-1142)
 template <bool FUSED>
 __device__ __forceinline__ void cubic_generic(fe *A, fe *B, fe *C, u64 P, const fe &r, const fe *el, const fe *er, u32 sh,
-                                              u64 first, u64 stride, fe (&x)[3], int shard_k = 0, int shard_rank = 0) {
+                                              u64 first, u64 stride, fe (&x)[3], int shard_k = 0, int shard_rank = 0, bool skip1 = false) {
   // sh: GLOBAL width of x_in; weights are indexed by the global pair id
   Fq::acc acc0 = Fq::acc_zero(), acc1 = Fq::acc_zero(), acci = Fq::acc_zero();
   const u64 mask = ((u64)1 << sh) - 1;
@@ -353,7 +382,7 @@ __device__ __forceinline__ void cubic_generic(fe *A, fe *B, fe *C, u64 P, const 
     const u64 gid = (id << shard_k) | (u64)shard_rank;
     fe w = ldg_fe_ro(er + (el ? (gid & mask) : gid));
     if (el) w = Fq::mul(ldg_fe_ro(el + (gid >> sh)), w);
-    cubic_pair<FUSED>(A, B, C, id, P, r, w, acc0, acc1, acci);
+    cubic_pair<FUSED>(A, B, C, id, P, r, w, acc0, acc1, acci, skip1);
   }
   x[0] = Fq::acc_reduce(acc0); x[1] = Fq::acc_reduce(acc1); x[2] = Fq::acc_reduce(acci);
 }
@@ -613,8 +642,14 @@ __device__ __forceinline__ void quad_body(fe *A, fe *B, u64 P, const fe &r, u64 
       b0 = bind_pair(b00, b10, r); b1 = bind_pair(b01, b11, r);
       stg_fe(B + id, b0); stg_fe(B + id + P, b1);
     } else {
-      a0 = ldg_fe(A + id); a1 = ldg_fe_valid(A, id + P, nvalid);
-      b0 = ldg_fe(B + id); b1 = ldg_fe_valid(B, id + P, nvalid);
+      a0 = ldg_fe(A + id); b0 = ldg_fe(B + id);
+      if (id + P >= nvalid) {
+        // both high entries are unmaterialised zeros: (0 - a0)(0 - b0) = a0 b0 — ONE product feeds both sums (the first round of the
+        // Spartan inner sum-check, where the whole upper half but a few entries is zero: spartan.rs:330-384)
+        Fq::mul_acc2(acc0, acci, a0, b0);
+        continue;
+      }
+      a1 = ldg_fe(A + id + P); b1 = ldg_fe(B + id + P);
     }
     Fq::mul_acc(acc0, a0, b0);
     Fq::mul_acc(acci, Fq::sub(a1, a0), Fq::sub(b1, b0));
@@ -1163,7 +1198,6 @@ k_cubic_tail_pipe(ScState *st, fe *A, fe *B, fe *C, fe *A2, fe *B2, fe *C2, int 
 // finaliser's code and the transcript state stay warm on one SM) and releases the grid by publishing the round
 // number; the others spin on it.  Saves, per round, the launch gap (measured 5 us), the last-CTA election and a cold
 // finaliser (+5 us) of the one-launch-per-round scheme.
-__device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) { u32 v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 
 // returns true on CTA 0 with the grid-wide sums in x (warp 0); other CTAs return false after the release
 template <int NV>
@@ -1205,6 +1239,7 @@ __device__ __forceinline__ void persist_wait(ScState *st, u32 seq) {          //
 
 struct PersistCubic {
   ScState *st; fe *A, *B, *C, *A2, *B2, *C2; int l, round_first, round_end; const fe *eq_left, *eq_right;
+  const ScTinvMail *mail; u32 mail_epoch;      // tau inverses for the derived t(1) (nullptr: ScState::derive_rounds must be 0)
 };
 
 #ifndef SC_PERSIST_MINB
@@ -1217,8 +1252,10 @@ __global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_cubic_persist(P
   const u32 G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
   fe *sA = a.A, *sB = a.B, *sC = a.C, *dA = a.A2, *dB = a.B2, *dC = a.C2;
   u32 seq = 0;
+  const int derive_rounds = a.mail ? (int)ld_volatile_u32(&st->derive_rounds) : 0;   // set before the launch (k_gate_taus)
   for (int round1 = a.round_first; round1 < a.round_end; round1++) {
     const bool fused = round1 > 1;
+    const bool derive = round1 <= derive_rounds;                          // t(1) from the claim: two sums instead of three
     const u64 P = (u64)1 << (l - round1);
     const u64 len_in = fused ? 4 * P : 2 * P;
     const bool in_first = round1 < first_half;
@@ -1251,14 +1288,14 @@ __global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_cubic_persist(P
         Fq::acc acc0 = Fq::acc_zero(), acc1 = Fq::acc_zero(), acci = Fq::acc_zero();
         const u64 xi = (u64)bx * SC_THREADS + tid;
         if (by < gy) {
-          if (fused) { for (u32 xo = by; xo < out_len; xo += gy) cubic_pair<true>(sA, sB, sC, ((u64)xo << sh) | xi, P, r, ldg_fe_ro(el + xo), acc0, acc1, acci); }
-          else { for (u32 xo = by; xo < out_len; xo += gy) cubic_pair<false>(sA, sB, sC, ((u64)xo << sh) | xi, P, r, ldg_fe_ro(el + xo), acc0, acc1, acci); }
+          if (fused) { for (u32 xo = by; xo < out_len; xo += gy) cubic_pair<true>(sA, sB, sC, ((u64)xo << sh) | xi, P, r, ldg_fe_ro(el + xo), acc0, acc1, acci, derive); }
+          else { for (u32 xo = by; xo < out_len; xo += gy) cubic_pair<false>(sA, sB, sC, ((u64)xo << sh) | xi, P, r, ldg_fe_ro(el + xo), acc0, acc1, acci, derive); }
         }
         const fe wr = ldg_fe_ro(er + xi);
         x[0] = Fq::mul(wr, Fq::acc_reduce(acc0)); x[1] = Fq::mul(wr, Fq::acc_reduce(acc1)); x[2] = Fq::mul(wr, Fq::acc_reduce(acci));
       } else {
-        if (fused) cubic_generic<true>(sA, sB, sC, P, r, el, er, sh, (u64)bid * SC_THREADS + tid, (u64)G * SC_THREADS, x);
-        else cubic_generic<false>(sA, sB, sC, P, r, el, er, sh, (u64)bid * SC_THREADS + tid, (u64)G * SC_THREADS, x);
+        if (fused) cubic_generic<true>(sA, sB, sC, P, r, el, er, sh, (u64)bid * SC_THREADS + tid, (u64)G * SC_THREADS, x, 0, 0, derive);
+        else cubic_generic<false>(sA, sB, sC, P, r, el, er, sh, (u64)bid * SC_THREADS + tid, (u64)G * SC_THREADS, x, 0, 0, derive);
       }
     }
     block_sum_fq<3>(x, sm.red);
@@ -1266,13 +1303,14 @@ __global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_cubic_persist(P
     const bool swapped = roles && fused;
     if (swapped) { fe *t; t = sA; sA = dA; dA = t; t = sB; sB = dB; dB = t; t = sC; sC = dC; dC = t; }
     if (bid == 0 && tid == 0) st->prof[round1 - 1][1] = gtimer();
+    if (bid == 0 && derive && round1 == a.round_first && tid < 32) derive_prefetch(st, sm, a.mail, a.mail_epoch, a.round_first, derive_rounds);
     if (persist_gather<3>(st, seq, x, sm)) {
       if (tid == 0) st->prof[round1 - 1][2] = gtimer();
-      const fe rn = cubic_finalize_pre(st, round1, x, sm);
+      const fe rn = cubic_finalize_pre(st, round1, x, sm, derive);
       if (tid == 0) st->prof[round1 - 1][3] = gtimer();
       persist_release(st, seq);
       // off the critical path: the grid is already streaming the next round (warps 6, 7 have no pair work in role rounds)
-      if (tid == SC_THREADS - 32) cubic_bound(st, round1, l, rn);
+      if (tid == SC_THREADS - 32) cubic_bound(st, round1, l, rn, round1 + 1 <= derive_rounds ? &sm : nullptr);
       if (round1 == l) cubic_claims(st, sA, sB, sC, rn);
     } else {
       persist_wait(st, seq);
@@ -1861,8 +1899,18 @@ int sumcheck_cubic_reserve(sp2_ctx *ctx, uint32_t l) {
   return SP2_OK;
 }
 
+uint32_t sumcheck_cubic_persist_rounds(sp2_ctx *ctx, uint32_t l) {
+  if (!use_persistent()) return 0;
+  uint32_t round_end = 1;
+  while (round_end <= l && ((round_end > 1 ? 4ull : 2ull) << (l - round_end)) > SC_TAIL_LEN) round_end++;
+  uint32_t mid_first = 0, mid_k = 0; size_t mid_smem = 0;
+  const bool mid = mid_plan(ctx, l, 2, round_end, 3, &mid_first, &mid_k, &mid_smem);
+  const uint32_t persist_end = mid ? mid_first : round_end;
+  return persist_end > 1 ? persist_end - 1 : 0;
+}
+
 // enqueue the whole cubic sum-check on ctx->stream (state already on the device, taus in st->taus)
-int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C, const DevComm *dcp) {
+int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C, const DevComm *dcp, const ScTinvMail *mail, uint32_t mail_epoch) {
   const int first_half = (int)l / 2, second_half = (int)l - first_half;
   void *eqs;
   const size_t nleft = (size_t)1 << (first_half > 0 ? first_half : 1), nright = (size_t)2 << second_half;
@@ -1891,7 +1939,7 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     const bool mid = mid_plan(ctx, l, 2, round_end, 3, &mid_first, &mid_k, &mid_smem);
     const uint32_t persist_end = mid ? mid_first : round_end;
     if (persist_end > 1) {
-      PersistCubic pa{st, A, B, C, dst[0], dst[1], dst[2], (int)l, 1, (int)persist_end, eq_left, eq_right};
+      PersistCubic pa{st, A, B, C, dst[0], dst[1], dst[2], (int)l, 1, (int)persist_end, eq_left, eq_right, mail, mail_epoch};
       void *args[] = {&pa};
       SP2_CUDA_OK(cudaEventRecord(ctx->ev_k0, ctx->stream));
       SP2_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_cubic_persist, dim3(ctx->num_sms * SC_PERSIST_MINB), dim3(SC_THREADS), args, 0, ctx->stream));

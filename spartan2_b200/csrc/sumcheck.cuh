@@ -7,6 +7,7 @@ namespace sp2 {
 
 constexpr int SC_MAX_ROUNDS = 40;
 constexpr int SC_MAX_BLOCKS = 2048;
+constexpr int SC_DERIVE_MAX = 8;
 constexpr int SC_THREADS = 256;
 constexpr int SC_TAIL_THREADS = 384;   // 12 warps = 4 role trios
 constexpr int SC_ROLE_THREADS = 384;
@@ -32,6 +33,11 @@ struct ScState {
   u32 mid_arrive[SC_MAX_ROUNDS + 8];   // pipelined multi-CTA rounds: CTAs whose partial sums of a round are published
   u32 mid_released, pad2[7];           //   and the last round whose challenge is published
   u32 mid_acc0[12 * 16];               //   column accumulators of the first such round (3 direct + 9 coefficient sums), zero on entry
+  // t(1) derived from the running claim in the streaming rounds of the cubic prover (sumcheck.rs:1277-1324): rounds 1..derive_rounds of
+  // k_cubic_persist sum only t(0) and t(inf); the finaliser solves (1 - tau_i) t(0) + tau_i t(1) = t_{i-1}(r_{i-1}) with the host's
+  // tau_i^-1 (ScTinvMail, below).  0 = all three sums directly (every other path, and any tau_i = 0).
+  u32 derive_rounds, pad3[7];
+  fe tclaim;                           // t_{i-1}(r_{i-1}) of the round being evaluated (round 1: the claim)
   // flags bit 0: warp-shuffle Keccak (default; measured 12.6k cycles/squeeze vs 22k for the one-thread register version)
   fe taus[SC_MAX_ROUNDS];
   // ---- everything above is uploaded by the host; everything below is produced on the device ----
@@ -43,6 +49,11 @@ struct ScState {
   unsigned long long prof[SC_MAX_ROUNDS][4];   // debug: per persistent round on CTA 0: %globaltimer at start, own compute done, all arrived, finalised
   fe partial[3 * SC_MAX_BLOCKS];
 };
+
+// tau inverses for the derived t(1): written by the HOST into pinned, device-visible memory (one batch inversion per prove, off the
+// critical path: the first streaming round takes ~60 us) and read by the streaming kernel's finaliser — a kernel of its own between the
+// gate and the cooperative launch would hold that launch back until the inverses arrive (measured: +13..33 us)
+struct ScTinvMail { u32 flag, n, pad[6]; u32 tinv[SC_DERIVE_MAX][8]; };   // flag: the prover's epoch, release-stored last
 
 // ---- multi-GPU sharding (one process per GPU; peers' mailboxes are CUDA-IPC mapped over NVLink) ----------------
 // The 2^l hypercube is split CYCLICALLY on the low index bits: rank g of G = 2^k owns global indices i = g (mod G),
@@ -80,7 +91,11 @@ int sc_state_upload(sp2_ctx *ctx, ScState **d_st, const uint64_t *claim, const u
 int sc_state_download(sp2_ctx *ctx, ScState *d_st, sp2_transcript_state *ts, uint64_t *polys, int ncoef, uint64_t *r,
                       uint64_t *claims, int nclaims, uint32_t l);
 // dc: nullptr for a single GPU; otherwise A, B, C are this rank's cyclic shards (2^(l-k) entries) of the global tables
-int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C, const DevComm *dc = nullptr);
+int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, fe *C, const DevComm *dc = nullptr, const ScTinvMail *mail = nullptr,
+                           uint32_t mail_epoch = 0);
+// rounds of a single-GPU cubic sum-check over 2^l entries that run in the persistent streaming kernel (0: none) — the rounds that may
+// derive t(1) from the claim (ScState::derive_rounds must not exceed it)
+uint32_t sumcheck_cubic_persist_rounds(sp2_ctx *ctx, uint32_t l);
 // before enqueuing behind a kernel that waits for the host: load the kernels / reserve the scratch (sumcheck.cu)
 void sumcheck_cubic_preload();
 int sumcheck_cubic_reserve(sp2_ctx *ctx, uint32_t l);

@@ -74,6 +74,7 @@ int32_t sp2_comm_connect(sp2_comm *c, const uint8_t *all_handles) {
 int32_t sp2_comm_mailbox(sp2_comm *c, void **out) { *out = c->dc.peer[c->dc.rank]; return SP2_OK; }
 int32_t sp2_comm_connect_ptrs(sp2_comm *c, void *const *mailboxes) {
   for (int q = 0; q < c->dc.n; q++) if (q != c->dc.rank) c->dc.peer[q] = (MailBox *)mailboxes[q];
+  c->in_process = true;
   c->connected = true;
   return SP2_OK;
 }
@@ -88,6 +89,7 @@ int32_t sp2_comm_reset(sp2_comm *c) {
   MailBox *mb = c->dc.peer[c->dc.rank];
   SP2_CUDA_OK(cudaMemsetAsync(mb->flag, 0, sizeof(mb->flag), ctx->stream));
   SP2_CUDA_OK(cudaMemsetAsync(&mb->err, 0, sizeof(u32), ctx->stream));
+  SP2_CUDA_OK(cudaMemsetAsync(&mb->late_flag, 0, sizeof(u32), ctx->stream));
   SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   c->dc.epoch = 0;
   return SP2_OK;

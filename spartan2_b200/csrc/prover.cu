@@ -108,29 +108,54 @@ enum SmallSlot { S_RJOINT = 0, S_EVALW = 1, S_EVALX = 2, S_RLZ = 3, S_IP = 4, S_
 // transcript hand-over (round, state) into the sum-check state and turns the squeezed digests into taus (from_uniform: LE 512-bit
 // mod p).  The ~30 us of launch calls and the H2D copy no longer sit between the last squeeze and the first round.
 __device__ __forceinline__ u32 ld_sys_u32(const void *p) { u32 v; asm volatile("ld.volatile.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__global__ void __launch_bounds__(64) k_gate_taus(ScState *st, const LateIn *late, u32 epoch, int l, int derive_max) {
+// Sharded proves (dc.n > 1): rank 0 alone has the host transcript; its gate forwards the hand-over to every peer's mailbox over
+// NVLink (plain stores + system fence + flag, like the round sums), and the peers' gates wait on their own mailbox in device memory —
+// the other ranks' hosts never hash the commitment rows (with 8 processes on one host that hashing was the largest phase).
+__global__ void __launch_bounds__(64) k_gate_taus(ScState *st, const LateIn *late, u32 epoch, int l, int derive_max, DevComm dc, u32 xflag) {
   __shared__ int tau_zero;
+  __shared__ u32 w[16 + SC_MAX_ROUNDS * 16];      // transcript state (64 B), then the tau digests (64 B each)
+  __shared__ u32 s_round, s_abort;
   const int tid = threadIdx.x;
-  if (tid == 0) tau_zero = 0;
+  const int nw = 16 + 16 * l;
+  const bool from_host = dc.n <= 1 || dc.rank == 0;
+  MailBox *mine = dc.n > 1 ? dc.peer[dc.rank] : nullptr;
   if (tid == 0) {
+    tau_zero = 0; s_abort = 0;
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     for (;;) {
-      const u32 v = ld_sys_u32(&late->flag);
-      if ((v & 0x7fffffffu) == epoch) { if (v >> 31) atomicExch(&st->err, 1u); break; }
+      const u32 v = from_host ? ld_sys_u32(&late->flag) : ld_sys_u32(&mine->late_flag);
+      if ((v & 0x7fffffffu) == (from_host ? epoch : xflag)) { if (v >> 31) { atomicExch(&st->err, 1u); s_abort = 1; } break; }
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      if (t - t0 > SC_WAIT_NS) { atomicExch(&st->err, 1u); break; }
+      if (t - t0 > SC_WAIT_NS) { atomicExch(&st->err, 1u); s_abort = 1; break; }
       __nanosleep(100);
     }
     __threadfence_system();
+    s_round = from_host ? ld_sys_u32(&late->round) : ld_sys_u32(&mine->late_round);
   }
   __syncthreads();
-  if (tid < 16) ((u32 *)st->ts.state)[tid] = ld_sys_u32(late->state + 4 * tid);
-  if (tid == 0) { st->ts.round = ld_sys_u32(&late->round); st->ts.pending_len = 0; }
+  for (int k = tid; k < nw; k += 64)
+    w[k] = from_host ? (k < 16 ? ld_sys_u32(late->state + 4 * k) : ld_sys_u32(late->dg + 4 * (k - 16))) : ld_sys_u32(&mine->late_words[k]);
+  __syncthreads();
+  if (dc.n > 1 && dc.rank == 0) {
+    for (int q = 1; q < dc.n; q++) {
+      MailBox *pm = dc.peer[q];
+      for (int k = tid; k < nw; k += 64) pm->late_words[k] = w[k];
+      if (tid == 0) pm->late_round = s_round;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      for (int q = 1; q < dc.n; q++) *(volatile u32 *)&dc.peer[q]->late_flag = xflag | (s_abort ? 0x80000000u : 0u);
+      __threadfence_system();
+    }
+  }
+  if (tid < 16) ((u32 *)st->ts.state)[tid] = w[tid];
+  if (tid == 0) { st->ts.round = s_round; st->ts.pending_len = 0; }
   if (tid < l) {
     fe lo, hi;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { lo.v[k] = ld_sys_u32(late->dg + 64 * tid + 4 * k); hi.v[k] = ld_sys_u32(late->dg + 64 * tid + 32 + 4 * k); }
+    for (int k = 0; k < 8; k++) { lo.v[k] = w[16 + 16 * tid + k]; hi.v[k] = w[16 + 16 * tid + 8 + k]; }
     const fe tau = Fq::from_uniform(lo, hi);
     stg_fe(&st->taus[tid], tau);
     if (tid < derive_max && Fq::is_zero(tau)) tau_zero = 1;
@@ -440,7 +465,9 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   // the head is hashed by the prep state's helper thread while this thread enqueues; joined before the rest rows are absorbed
   // (and on every early return: the job refers to locals)
   struct Join { HostWorker &w; ~Join() { w.wait(); } } join_head{P->worker};
-  P->worker.submit(absorb_head);
+  const bool hash_here = !shard || S->rank == 0;                             // sharded: rank 0 alone hashes; the taus reach the peers through
+  if (hash_here) P->worker.submit(absorb_head);                             // its gate kernel and the NVLink mailboxes (k_gate_taus)
+  else memcpy(proof->comm_W, P->comm_cached.data(), P->cached_rows * sizeof(aff));
   // ---- per-prove host inputs: one staged copy (randomness, blinds, public values) ------------------
   fe *small = P->small;
   { uint8_t *h = P->h_inbox;
@@ -508,7 +535,7 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   // (SP2_NO_DERIVE=1: all three sums directly in every round — measurement switch)
   static const bool derive_on = [] { const char *e = getenv("SP2_NO_DERIVE"); return !(e && e[0] == '1'); }();
   const uint32_t derive_max = (shard || !derive_on) ? 0u : std::min<uint32_t>(SC_DERIVE_MAX, sumcheck_cubic_persist_rounds(ctx, (uint32_t)l));
-  P->worker.submit([&ts, late, epoch, l, proof, P, rest_rows, derive_max]() {
+  if (hash_here) P->worker.submit([&ts, late, epoch, l, proof, P, rest_rows, derive_max]() {
     ts.absorb_commitment("comm_W_rest", proof->comm_W + 8 * P->cached_rows, rest_rows);
     for (int i = 0; i < l; i++) ts.squeeze("t", late->dg + 64 * i);
     late->round = ts.round; memcpy(late->state, ts.state, 64);
@@ -552,8 +579,10 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   // SP2_NO_GATES=1 (profilers that serialise kernel launches block the launching thread until a kernel ends: a gate opened by
   // that same thread would run into its 2 s bound): the gates are launched only once their flags are set
   static const bool gates = [] { const char *e = getenv("SP2_NO_GATES"); return !(e && e[0] == '1'); }();
-  if (!gates) P->worker.wait();
-  k_gate_taus<<<1, 64, 0, ctx->stream>>>(st_outer, P->d_late, epoch, l, (int)derive_max);
+  if (!gates && hash_here) P->worker.wait();
+  { DevComm gdc; memset(&gdc, 0, sizeof(gdc)); gdc.n = 1;
+    if (shard) gdc = comm->dc;
+    k_gate_taus<<<1, 64, 0, ctx->stream>>>(st_outer, P->d_late, epoch, l, (int)derive_max, gdc, shard ? ((comm->dc.epoch + 1) & 0x7fffffffu) : 0u); }
   SP2_LAUNCH_CHECK();
   mark(1);
   mark(2);
@@ -603,9 +632,10 @@ static int32_t spartan_prove_impl(sp2_ctx *ctx, sp2_comm *comm, const sp2_shape 
   const fe *ry1 = st_inner->r + 1;
   MsmJob j;
   if (nvr > 0) {
-    if (shard) {
-      // sharded proves: after the whole sum-check (still beside the eval_W / R-table chain of the main stream) — no spinning kernel
-      // next to the round kernels that wait for their peers (ranks of one process share the hardware queues)
+    if (shard && comm->in_process) {
+      // ranks that are contexts of ONE process (the in-process tests): after the whole sum-check (still beside the eval_W / R-table
+      // chain of the main stream) — no spinning kernel next to round kernels that wait for peers sharing the hardware queues.
+      // One process per GPU (CUDA IPC, the production layout) takes the early path below like a single-GPU prove
       SP2_CUDA_OK(cudaStreamWaitEvent(P->side2, P->ev_q, 0));
     } else {
       SP2_CUDA_OK(cudaStreamWaitEvent(P->side2, P->ev_r1, 0));

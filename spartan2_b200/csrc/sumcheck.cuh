@@ -68,6 +68,10 @@ struct MailBox {
   u32 flag[SC_MAX_ROUNDS + 2][SC_MAX_RANKS];
   fe gather[3][SC_ROLE_LEN];
   u32 err, pad[7];            // set by a round / barrier kernel of the LOCAL rank whose bounded wait for a peer expired
+  // the prover's transcript hand-over: rank 0 alone hashes the commitment rows on its host and forwards (round, state, tau digests) to
+  // every peer's mailbox from inside its gate kernel (prover.cu: k_gate_taus) — no rank but 0 spends host time on the transcript head
+  u32 late_flag, late_round, late_pad[6];
+  u32 late_words[16 + SC_MAX_ROUNDS * 16];
 };
 // every device-side wait is bounded (a dead or failed peer must surface as an error code, not wedge the GPU)
 constexpr unsigned long long SC_WAIT_NS = 2000000000ull;
@@ -82,6 +86,7 @@ struct sp2_comm {                // host handle of one rank's endpoint (comm.cu)
   sp2_ctx *ctx = nullptr;
   sp2::DevComm dc;
   bool connected = false;
+  bool in_process = false;       // peers are contexts of THIS process (sp2_comm_connect_ptrs): their streams share the hardware queues
   bool opened[sp2::SC_MAX_RANKS] = {false};
 };
 namespace sp2 {

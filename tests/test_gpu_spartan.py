@@ -57,6 +57,7 @@ def _run(ctx, orc, seed, lc, lv, width, num_public, rest_frac):
     (4, 13, 13, 64, 30, 0.25),   # multi-CTA rounds + tail kernels, many public inputs
     (5, 12, 14, 256, 2, 0.0),    # more variables than constraints
     (6, 14, 12, 64, 2, 0.0),     # more constraints than variables
+    (7, 18, 17, 256, 3, 0.25),   # streaming rounds of the persistent kernel (t(1) derived from the claim), pipelined mid rounds, early comm_LZ
 ])
 def test_prove_bit_exact_and_verifies(ctx, orc, seed, lc, lv, width, npub, rest):
     _run(ctx, orc, seed, lc, lv, width, npub, rest)
@@ -140,3 +141,27 @@ def test_full_size_config_proof_is_bit_exact_and_accepted_by_the_oracle_verifier
     vp.z_vec[7, 1] ^= np.uint64(4)
     assert orc.spartan_verify(O, keys, vk, X, vp) != 0
     orc.set_threads(1)
+
+
+@pytest.mark.parametrize("env", [{"SP2_NO_GATES": "1"}, {"SP2_NO_DERIVE": "1"}, {"SP2_NO_GATES": "1", "SP2_NO_DERIVE": "1"}])
+def test_measurement_switches_keep_the_proof(env):
+    """SP2_NO_GATES / SP2_NO_DERIVE are read once per process: a fresh interpreter proves the 2^18 / 2^17 instance (streaming rounds
+    of the persistent kernel: t(1) derived from the claim by default, gate kernels opened by the helper thread) with the switches set,
+    and compares every field with the oracle's proof — the default path does the same in test_prove_bit_exact_and_verifies."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import tests.conftest\n"
+        "import spartan2_b200 as sp\n"
+        "from oracle import pyoracle as orc\n"
+        "from tests.test_gpu_spartan import _run\n"
+        "c = sp.Context(0)\n"
+        "_run(c, orc, 11, 18, 17, 256, 3, 0.25)\n"
+        "c.close()\n"
+        "print('switches ok')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "switches ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

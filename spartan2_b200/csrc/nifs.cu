@@ -1579,7 +1579,7 @@ __global__ void __launch_bounds__(256) k_nn_dot(const fe *a, const fe *b, u64 n,
   block_sum_fq<1>(x, red);
   if (threadIdx.x == 0) stg_fe(out, x[0]);
 }
-enum NnSlot { NS_EVAL = 0 /* 2 */, NS_BEVAL = 2 /* 2 */, NS_EVALF = 4, NS_BEVALF = 5, NS_CEVAL = 6, NS_RLZ = 7, NS_IP = 8, NS_RDELTA = 9, NS_RBETA = 10, NS_RY = 16 /* <= 40 */, NS_COUNT = 64 };
+enum NnSlot { NS_EVAL = 0 /* 2 */, NS_BEVAL = 2 /* 2 */, NS_EVALF = 4, NS_BEVALF = 5, NS_CEVAL = 6, NS_RLZ = 7, NS_IP = 8, NS_RDELTA = 9, NS_RBETA = 10, NS_RLZC = 11, NS_RY = 16 /* <= 40 */, NS_COUNT = 64 };
 
 // gather CTAs the background commitment of the folded witness may occupy while the sum-checks run (SP2_NN_SIDE_CTAS, default 96; swept on B200 at 32 steps: 0 = uncapped: outer 1.04 / pcs 0.33 ms, 48: 0.57 / 0.83, 16: 0.56 / 3.9)
 unsigned nn_side_ctas() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_NN_SIDE_CTAS"); v = e ? atoi(e) : 96; } return (unsigned)v; }
@@ -1774,7 +1774,33 @@ static int32_t nn_snark_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *xcomm, sp2_
       j.extra_base[1] = ck->idx_h_s(); j.extra_scalar[1] = small + NS_BEVAL + b; }
     SP2_TRY(msm_run(ctx, ck, jobs, pts_fold + rows));
     SP2_CUDA_OK(cudaMemcpyAsync(h_jac, pts_fold + rows, 2 * sizeof(jac), cudaMemcpyDeviceToHost, ctx->stream));
-    SP2_CUDA_OK(cudaStreamSynchronize(ctx->stream)); }
+    SP2_CUDA_OK(cudaEventRecord(P->ev_fold, ctx->stream)); }
+  // ---- everything of PCS::prove that does not depend on c_eval runs while the host normalises / hashes the two evaluation
+  // commitments (a host round trip of ~65 us): the eq tables of r_y, <R, d>, and — by linearity of the bind — L^T W_fold, L^T W_core,
+  // <L, b_fold>, <L, b_core>; after c_eval only three small axpys remain (LZ, r_LZ, the folded blinds): W_fold + c W_core itself is
+  // never materialised
+  const uint32_t my = sn->base.rounds_y, m = my - 1;
+  int nvr = 0; while ((1u << nvr) < rows) nvr++;
+  if ((1u << nvr) != rows || (width & (width - 1))) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "snark_prove: rows and width must be powers of two");
+  { fe up[SC_MAX_ROUNDS + 8];
+    for (uint32_t j = 0; j < m; j++) up[j] = H::load(sn->base.r_y + 4 * (j + 1));
+    up[m] = H::load(rnd->r_beta);
+    memcpy(h_in + 64 * sizeof(fe), up, (m + 1) * sizeof(fe));
+    SP2_CUDA_OK(cudaMemcpyAsync(small + NS_RY, h_in + 64 * sizeof(fe), m * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream));
+    SP2_CUDA_OK(cudaMemcpyAsync(small + NS_RBETA, h_in + (64 + m) * sizeof(fe), sizeof(fe), cudaMemcpyHostToDevice, ctx->stream)); }
+  SP2_TRY(eq_table_dev(ctx, small + NS_RY + nvr, (uint32_t)(m - nvr), Rtab));
+  k_nn_dot<<<1, 256, 0, ctx->stream>>>(Rtab, dvec, width, small + NS_IP);
+  SP2_LAUNCH_CHECK();
+  if (nvr > 0) {
+    SP2_TRY(eq_table_dev(ctx, small + NS_RY, (uint32_t)nvr, Ltab));
+    SP2_TRY(hyrax_bind_dev(ctx, P->Wfold, Ltab, rows, width, LZ));              // L^T W_fold
+    SP2_TRY(hyrax_bind_dev(ctx, P->zc, Ltab, rows, width, zvec));               // L^T W_core (zvec is free until the IPA response)
+    k_nn_dot<<<1, 256, 0, ctx->stream>>>(Ltab, blind_fold, rows, small + NS_RLZ);
+    SP2_LAUNCH_CHECK();
+    k_nn_dot<<<1, 256, 0, ctx->stream>>>(Ltab, P->blinds_dev + (size_t)n * rows, rows, small + NS_RLZC);
+    SP2_LAUNCH_CHECK();
+  }
+  SP2_CUDA_OK(cudaEventSynchronize(P->ev_fold));                                // the two evaluation commitments are on the host
   uint64_t ce[16];
   sp2h::batch_normalize(h_jac, 2, ce);
   if (sn->comm_eval_W) memcpy(sn->comm_eval_W, ce, 128);
@@ -1783,30 +1809,25 @@ static int32_t nn_snark_impl(sp2_ctx *ctx, sp2_nn_prep *P, sp2_comm *xcomm, sp2_
   if (sn->c_eval) H::store(sn->c_eval, c_eval);
   ph[7] = ms_since(t_phase); t_phase = now();
   // ---- fold the step and core claims with c_eval and open (neutronnova_zk.rs:2019-2064) -----------------------------------
-  const uint32_t my = sn->base.rounds_y, m = my - 1;
-  int nvr = 0; while ((1u << nvr) < rows) nvr++;
-  if ((1u << nvr) != rows || (width & (width - 1))) return set_error(ctx, SP2_ERR_INVALID_CK_LENGTH, "snark_prove: rows and width must be powers of two");
   const fe eval_f = HF::add(eval_s, HF::mul(c_eval, eval_c)), be_f = HF::add(be_s, HF::mul(c_eval, be_c));
-  { std::vector<fe> up(NS_COUNT, HF::zero());
-    up[NS_EVALF] = eval_f; up[NS_BEVALF] = be_f; up[NS_CEVAL] = c_eval; up[NS_RDELTA] = H::load(rnd->r_delta); up[NS_RBETA] = H::load(rnd->r_beta);
-    for (uint32_t j = 0; j < m; j++) up[NS_RY + j] = H::load(sn->base.r_y + 4 * (j + 1));
-    memcpy(h_in, up.data() + NS_EVALF, (NS_COUNT - NS_EVALF) * sizeof(fe));
-    SP2_CUDA_OK(cudaMemcpyAsync(small + NS_EVALF, h_in, (NS_COUNT - NS_EVALF) * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream)); }
-  const unsigned nbM = (unsigned)std::min<u64>((M + 255) / 256, (u64)ctx->num_sms * 8);
-  k_nn_axpy<<<nbM, 256, 0, ctx->stream>>>(P->Wfin, P->Wfold, P->zc, c_eval, M);                       // W = W_fold + c_eval W_core
-  SP2_LAUNCH_CHECK();
+  { fe up[4] = {eval_f, be_f, c_eval, HF::zero()};
+    memcpy(h_in, up, sizeof(up));
+    SP2_CUDA_OK(cudaMemcpyAsync(small + NS_EVALF, h_in, 3 * sizeof(fe), cudaMemcpyHostToDevice, ctx->stream)); }
   k_nn_axpy<<<1, 256, 0, ctx->stream>>>(blind_fin, blind_fold, P->blinds_dev + (size_t)n * rows, c_eval, rows);   // fold_blinds with [1, c_eval]
   SP2_LAUNCH_CHECK();
-  SP2_TRY(eq_table_dev(ctx, small + NS_RY + nvr, (uint32_t)(m - nvr), Rtab));
   const fe *LZp = LZ, *rLZ = small + NS_RLZ;
   if (nvr > 0) {
-    SP2_TRY(eq_table_dev(ctx, small + NS_RY, (uint32_t)nvr, Ltab));
-    SP2_TRY(hyrax_bind_dev(ctx, P->Wfin, Ltab, rows, width, LZ));
-    k_nn_dot<<<1, 256, 0, ctx->stream>>>(Ltab, blind_fin, rows, small + NS_RLZ);
+    k_nn_axpy<<<(unsigned)((width + 255) / 256), 256, 0, ctx->stream>>>(LZ, LZ, zvec, c_eval, width);          // LZ = L^T W_fold + c_eval L^T W_core
     SP2_LAUNCH_CHECK();
-  } else { LZp = P->Wfin; rLZ = blind_fin; }
-  k_nn_dot<<<1, 256, 0, ctx->stream>>>(Rtab, dvec, width, small + NS_IP);
-  SP2_LAUNCH_CHECK();
+    k_nn_axpy<<<1, 32, 0, ctx->stream>>>(small + NS_RLZ, small + NS_RLZ, small + NS_RLZC, c_eval, 1);           // r_LZ likewise
+    SP2_LAUNCH_CHECK();
+  } else {
+    // one commitment row: LZ is the folded witness itself (hyrax_pc.rs:420-424)
+    const unsigned nbM = (unsigned)std::min<u64>((M + 255) / 256, (u64)ctx->num_sms * 8);
+    k_nn_axpy<<<nbM, 256, 0, ctx->stream>>>(P->Wfin, P->Wfold, P->zc, c_eval, M);                     // W = W_fold + c_eval W_core
+    SP2_LAUNCH_CHECK();
+    LZp = P->Wfin; rLZ = blind_fin;
+  }
   SP2_CUDA_OK(cudaStreamWaitEvent(ctx->stream, P->ev_side, 0));                                        // the folded-witness rows are committed
   std::vector<MsmJob> jobs(rows + 3);                              // (delta, point rows + 3 of the output, was committed on the side stream)
   for (uint32_t r = 0; r < rows; r++) {        // comm[r] = comm(W_fold row) + c_eval U_core[r] + (b_fold[r] + c_eval b_core[r]) h

@@ -419,24 +419,45 @@ class SpartanProof:
     """Flat SpartanSNARK proof (include/spartan2_b200.h: sp2_spartan_proof)."""
     FIELDS = ["comm_W", "outer_polys", "claims_outer", "inner_polys", "eval_W", "blind_eval_W", "delta", "beta", "z_vec", "z_delta", "z_beta"]
 
+    _layout_cache = {}
+
     def __init__(self, l, nry, rows, num_cols):
-        # one backing buffer, the fields are views (the wrapper's per-call overhead counts in the end-to-end time of a ~1.3 ms prove)
+        # one backing buffer; the fields are views made on first access (the wrapper's per-call overhead counts in the end-to-end time
+        # of a ~1.3 ms prove).  The C side writes every field of a successful prove.
         self.l, self.nry, self.rows, self.num_cols = l, nry, rows, num_cols
-        shapes = ((rows, 8), (3 * l, 4), (3, 4), (2 * nry, 4), (1, 4), (1, 4), (1, 8), (1, 8), (num_cols, 4), (1, 4), (1, 4))
-        sizes = [a * b for a, b in shapes]
-        buf = np.zeros(sum(sizes), dtype=np.uint64)
-        self._buf = buf; self._offs = []
-        o = 0
-        for f, sh, n in zip(self.FIELDS, shapes, sizes):
-            setattr(self, f, buf[o:o + n].reshape(sh)); self._offs.append(8 * o); o += n
-        self.phase_ms = None
+        key = (l, nry, rows, num_cols)
+        lay = SpartanProof._layout_cache.get(key)
+        if lay is None:
+            shapes = ((rows, 8), (3 * l, 4), (3, 4), (2 * nry, 4), (1, 4), (1, 4), (1, 8), (1, 8), (num_cols, 4), (1, 4), (1, 4))
+            offs, o = {}, 0
+            for f, sh in zip(self.FIELDS, shapes):
+                offs[f] = (o, sh); o += sh[0] * sh[1]
+            lay = SpartanProof._layout_cache[key] = (offs, o)
+        self._offs, total = lay
+        self._buf = np.zeros(total, dtype=np.uint64)
+        self._phase = None
+
+    def __getattr__(self, name):            # only called for attributes not set yet: the field views, phase_ms
+        offs = self.__dict__.get("_offs")
+        if offs is not None and name in offs:
+            o, sh = offs[name]
+            v = self._buf[o:o + sh[0] * sh[1]].reshape(sh)
+            self.__dict__[name] = v
+            return v
+        if name == "phase_ms":
+            ph = self.__dict__.get("_phase")
+            d = None if ph is None else dict(zip(PHASES, [float(x) for x in ph]))
+            self.__dict__["phase_ms"] = d
+            return d
+        raise AttributeError(name)
 
     def cview(self):
-        v = _ProofC(self.l, self.nry, self.rows, self.num_cols)
         base = _addr(self._buf)
-        for f, o in zip(self.FIELDS, self._offs):
-            setattr(v, f, base + o)
-        return v
+        offs = self._offs
+        return _ProofC(self.l, self.nry, self.rows, self.num_cols, *[base + 8 * offs[f][0] for f in self.FIELDS])
+
+
+PHASES = ["commit_transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck", "pcs_prove", "ipa_response", "total"]
 
 
 class SpartanPrepSNARK:
@@ -497,8 +518,7 @@ class SpartanSNARK:
             ctx.check(ctx.L.sp2_spartan_prove(ctx.h, *tail))
         else:
             ctx.check(ctx.L.sp2_spartan_prove_sharded(ctx.h, comm.h, *tail))
-        P.phase_ms = dict(zip(["commit_transcript", "matrix_vector_multiply", "outer_sumcheck", "prepare_poly_ABC", "inner_sumcheck",
-                               "pcs_prove", "ipa_response", "total"], [float(x) for x in ph]))
+        P._phase = ph                                                         # (phase_ms: a dict made on first access)
         return P
 
 

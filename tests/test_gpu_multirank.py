@@ -42,6 +42,10 @@ def ranks():
     made = []
 
     def make(world):
+        # device objects of earlier tests that sit in reference cycles (pytest.raises keeps frames alive) would otherwise be freed by
+        # the cyclic collector at an arbitrary later allocation — a cudaFree in the middle of kernels that spin on a peer
+        import gc
+        gc.collect()
         cs = [sp.Context(0) for _ in range(world)]
         made.extend(cs)
         return cs

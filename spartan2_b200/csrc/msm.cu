@@ -103,7 +103,7 @@ struct GatherSmem {
   const aff *tab[GW][8];
 };
 
-__global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, u32 njobs, u32 total_parts, const aff *table, jac *partial) {
+__global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, u32 njobs, u32 total_parts, const aff *table, jac *partial, jac *out) {
   __shared__ GatherSmem sm;
   const u32 wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // grid-stride over the partials: a capped grid (msm_run's max_ctas) keeps a background batch on a side stream from taking
@@ -152,7 +152,14 @@ __global__ void __launch_bounds__(MSM_THREADS) k_msm_gather(const MsmJob *jobs, 
   if (cnt == 1) acc = jac_from_aff(first);
   __syncwarp();
   acc = warp_sum_jac_quad(acc);
-  if (lane == 0) st_jac(partial + part, acc);
+  if (lane == 0) {
+    if (job.nparts == 1 && !job.add_jac) {
+      // a job of one partial (<= 3 terms: commit_zeros rows, rerandomisation, the two-term commitments at the end of a prove) is
+      // complete here: no k_msm_final launch for it
+      if (job.add_aff) acc = jac_add_mixed(acc, ld_aff_ro(job.add_aff));
+      st_jac(out + jid, acc);
+    } else st_jac(partial + part, acc);
+  }
   __syncwarp();
   }
 }
@@ -298,7 +305,10 @@ int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, 
   const size_t nj = jobs.size();
   // size classes of the final reduction (k_msm_final<NT>): <= 8 partials one warp, <= 32 four warps, else 128 quads
   std::vector<u32> cls[3];
-  for (size_t i = 0; i < nj; i++) cls[jobs[i].nparts <= 8 ? 0 : jobs[i].nparts <= 32 ? 1 : 2].push_back((u32)i);
+  for (size_t i = 0; i < nj; i++) {
+    if (jobs[i].nparts == 1 && !jobs[i].add_jac) continue;          // finished by the gather warp itself
+    cls[jobs[i].nparts <= 8 ? 0 : jobs[i].nparts <= 32 ? 1 : 2].push_back((u32)i);
+  }
   std::vector<unsigned char> blob(nj * sizeof(MsmJob) + nj * sizeof(u32));
   memcpy(blob.data(), jobs.data(), nj * sizeof(MsmJob));
   u32 *lists = (u32 *)(blob.data() + nj * sizeof(MsmJob));
@@ -311,7 +321,7 @@ int msm_run(sp2_ctx *ctx, const sp2_ck *ck, const std::vector<MsmJob> &jobs_in, 
   SP2_CUDA_OK(cudaMemcpyAsync(d_jobs, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
   const u32 *d_lists = (const u32 *)((const unsigned char *)d_jobs + nj * sizeof(MsmJob));
   unsigned grid = (parts + GW - 1) / GW; if (max_ctas && grid > max_ctas) grid = max_ctas;
-  k_msm_gather<<<grid, MSM_THREADS, 0, stream>>>((const MsmJob *)d_jobs, (u32)nj, parts, ck->table, (jac *)d_partial);
+  k_msm_gather<<<grid, MSM_THREADS, 0, stream>>>((const MsmJob *)d_jobs, (u32)nj, parts, ck->table, (jac *)d_partial, d_out);
   SP2_LAUNCH_CHECK();
   if (!cls[0].empty()) { k_msm_final<32><<<(unsigned)cls[0].size(), 32, 0, stream>>>((const MsmJob *)d_jobs, d_lists + off[0], (const jac *)d_partial, d_out); SP2_LAUNCH_CHECK(); }
   if (!cls[1].empty()) { k_msm_final<128><<<(unsigned)cls[1].size(), 128, 0, stream>>>((const MsmJob *)d_jobs, d_lists + off[1], (const jac *)d_partial, d_out); SP2_LAUNCH_CHECK(); }

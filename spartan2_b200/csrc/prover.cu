@@ -262,9 +262,14 @@ __global__ void __launch_bounds__(256) k_eval_w(const ScState *inner, const fe *
   fe x[1] = {Fq::zero()};
   for (u32 i = threadIdx.x; i < zlen; i += blockDim.x) x[0] = Fq::add(x[0], Fq::mul(ldg_fe(X + i), ldg_fe(chis + i)));
   block_sum_fq<1>(x, red);
+  // prod_{i < skip} (1 - r_y[1 + i]): a warp tree (5 dependent multiplications) instead of a serial chain of m - 1 - nvz ~ 18
+  fe common = Fq::one();
+  if (threadIdx.x < 32) {
+    for (int i = threadIdx.x; i < skip; i += 32) common = Fq::mul(common, Fq::sub(Fq::one(), ldg_fe(ry1 + i)));
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) common = Fq::mul(common, shfl_xor_fe(common, d));
+  }
   if (threadIdx.x == 0) {
-    fe common = Fq::one();
-    for (int i = 0; i < skip; i++) common = Fq::mul(common, Fq::sub(Fq::one(), ldg_fe(ry1 + i)));
     const fe eval_X = Fq::mul(common, x[0]);
     const fe ry0 = ldg_fe(&inner->r[0]);
     const fe eval_W = Fq::mul(Fq::sub(ldg_fe(&inner->claims[1]), Fq::mul(ry0, eval_X)), ldg_fe(&small[S_DENINV]));

@@ -37,6 +37,7 @@
 #include <string.h>
 #include <utility>
 #include "ctx.cuh"
+#include "host_transcript.h"
 #include "keccak.cuh"
 #include "polys.cuh"
 #include "sumcheck.cuh"
@@ -1781,6 +1782,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_quad_mid_pipe(MidQuad a) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// SP2_NO_DERIVE=1: three direct sums in every round (measurement switch)
+static bool derive_enabled() { static int v = -1; if (v < 0) { const char *e = getenv("SP2_NO_DERIVE"); v = (e && e[0] == '1') ? 0 : 1; } return v == 1; }
+uint32_t sumcheck_cubic_persist_rounds(sp2_ctx *ctx, uint32_t l);
 int sc_state_upload(sp2_ctx *ctx, ScState **d_st, const uint64_t *claim, const uint64_t *taus, uint32_t l,
                     const sp2_transcript_state *ts) {
   void *d, *h;
@@ -1794,6 +1798,25 @@ int sc_state_upload(sp2_ctx *ctx, ScState **d_st, const uint64_t *claim, const u
   hs->l = l;
   { static int kflag = -1; if (kflag < 0) { const char *e = getenv("SP2_KECCAK_THREAD"); kflag = (e && e[0] == '1') ? 0 : 1; } hs->flags = (u32)kflag; }
   if (taus) memcpy(hs->taus, taus, (size_t)l * sizeof(fe));
+  // standalone cubic prover: the host has the taus right here — the streaming rounds derive t(1) from the claim (sumcheck.cuh) with
+  // inverses from one batch inversion, unless a tau of those rounds is zero (then, as everywhere else, three direct sums)
+  if (taus && derive_enabled()) {
+    uint32_t n = std::min<uint32_t>(SC_DERIVE_MAX, sumcheck_cubic_persist_rounds(ctx, l));
+    uint64_t pre[SC_DERIVE_MAX][4], acc[4], inv[4];
+    for (uint32_t i = 0; i < n; i++) { const uint64_t *t = taus + 4 * i; if (!(t[0] | t[1] | t[2] | t[3])) n = 0; }
+    if (n) {
+      memcpy(acc, taus, 32);
+      for (uint32_t i = 1; i < n; i++) { memcpy(pre[i], acc, 32); sp2h::mont_mul(acc, taus + 4 * i, sp2h::FQ_MOD, sp2h::FQ_INV, acc); }
+      sp2h::fq_inv(acc, inv);
+      for (uint32_t i = n; i-- > 1;) {
+        uint64_t ti[4]; sp2h::mont_mul(inv, pre[i], sp2h::FQ_MOD, sp2h::FQ_INV, ti); memcpy(hs->mail.tinv[i], ti, 32);
+        sp2h::mont_mul(inv, taus + 4 * i, sp2h::FQ_MOD, sp2h::FQ_INV, inv);
+      }
+      memcpy(hs->mail.tinv[0], inv, 32);
+      hs->mail.n = n; hs->mail.flag = 1; hs->derive_rounds = n;
+      memcpy(&hs->tclaim, claim, sizeof(fe));
+    }
+  }
   SP2_CUDA_OK(cudaMemcpyAsync(d, hs, head, cudaMemcpyHostToDevice, ctx->stream));
   *d_st = (ScState *)d;
   return SP2_OK;
@@ -1939,6 +1962,7 @@ int sumcheck_cubic_enqueue(sp2_ctx *ctx, ScState *st, uint32_t l, fe *A, fe *B, 
     const bool mid = mid_plan(ctx, l, 2, round_end, 3, &mid_first, &mid_k, &mid_smem);
     const uint32_t persist_end = mid ? mid_first : round_end;
     if (persist_end > 1) {
+      if (!mail) { mail = &st->mail; mail_epoch = 1; }               // standalone provers: inverses uploaded with the state (or none: derive_rounds = 0)
       PersistCubic pa{st, A, B, C, dst[0], dst[1], dst[2], (int)l, 1, (int)persist_end, eq_left, eq_right, mail, mail_epoch};
       void *args[] = {&pa};
       SP2_CUDA_OK(cudaEventRecord(ctx->ev_k0, ctx->stream));

@@ -22,6 +22,11 @@ constexpr int SC_ROLE_THREADS = 384;
 constexpr unsigned long long SC_TAIL_LEN = SP2_SC_TAIL_LEN;   // tables this short are finished by one CTA in one launch
 constexpr unsigned long long SC_ROLE_LEN = 1ull << SP2_SC_ROLE_LOG;   // tables this short use the role-split (3 items per pair) rounds
 
+// tau inverses for the derived t(1): written by the HOST into pinned, device-visible memory (one batch inversion per prove, off the
+// critical path: the first streaming round takes ~60 us) and read by the streaming kernel's finaliser — a kernel of its own between the
+// gate and the cooperative launch would hold that launch back until the inverses arrive (measured: +13..33 us)
+struct ScTinvMail { u32 flag, n, pad[6]; u32 tinv[SC_DERIVE_MAX][8]; };   // flag: the prover's epoch, release-stored last
+
 struct ScState {
   DevTranscript ts;           // transcript hand-off: (round, state) in, (round, state) out
   fe claim;                   // quad: running claim (cubic sums t(0), t(1), t(inf) directly)
@@ -38,6 +43,7 @@ struct ScState {
   // tau_i^-1 (ScTinvMail, below).  0 = all three sums directly (every other path, and any tau_i = 0).
   u32 derive_rounds, pad3[7];
   fe tclaim;                           // t_{i-1}(r_{i-1}) of the round being evaluated (round 1: the claim)
+  ScTinvMail mail;                     // the standalone provers' inverses (the host has the taus at upload time); the fused prover uses pinned memory
   // flags bit 0: warp-shuffle Keccak (default; measured 12.6k cycles/squeeze vs 22k for the one-thread register version)
   fe taus[SC_MAX_ROUNDS];
   // ---- everything above is uploaded by the host; everything below is produced on the device ----
@@ -49,11 +55,6 @@ struct ScState {
   unsigned long long prof[SC_MAX_ROUNDS][4];   // debug: per persistent round on CTA 0: %globaltimer at start, own compute done, all arrived, finalised
   fe partial[3 * SC_MAX_BLOCKS];
 };
-
-// tau inverses for the derived t(1): written by the HOST into pinned, device-visible memory (one batch inversion per prove, off the
-// critical path: the first streaming round takes ~60 us) and read by the streaming kernel's finaliser — a kernel of its own between the
-// gate and the cooperative launch would hold that launch back until the inverses arrive (measured: +13..33 us)
-struct ScTinvMail { u32 flag, n, pad[6]; u32 tinv[SC_DERIVE_MAX][8]; };   // flag: the prover's epoch, release-stored last
 
 // ---- multi-GPU sharding (one process per GPU; peers' mailboxes are CUDA-IPC mapped over NVLink) ----------------
 // The 2^l hypercube is split CYCLICALLY on the low index bits: rank g of G = 2^k owns global indices i = g (mod G),

@@ -1376,6 +1376,10 @@ __global__ void __launch_bounds__(SC_THREADS, SC_PERSIST_MINB) k_quad_persist(Pe
 // A mid round costs what the transcript costs (~11 us).  Every wait is bounded (spin_until).  Same sums, same field elements:
 // bit-identical (tests/test_gpu_sumcheck.py).
 constexpr int MP_LOG_LEN_IN = 17;                  // the first mid round reads tables of <= 2^17 entries
+#ifndef SP2_MP_LOG_LEN_IN_QUAD
+#define SP2_MP_LOG_LEN_IN_QUAD 17
+#endif
+constexpr int MP_LOG_LEN_IN_QUAD = SP2_MP_LOG_LEN_IN_QUAD;   // ... of the quadratic prover (two tables: 2^18 entries would fit the shared memory)
 constexpr int MP_LOG_CTAS = 7;                     // <= 128 CTAs
 constexpr int MP_LOG_LOCAL = 8;                    // >= 256 entries per CTA going into the first bind (else fewer CTAs)
 // round_last: the last round on the cyclic layout; finish: role CTA 0 then runs the remaining rounds (<= SC_TAIL_LEN entries) on the whole table
@@ -1849,7 +1853,7 @@ static bool use_mid_finish() { static int v = -1; if (v < 0) { const char *e = g
 static bool mid_plan(sp2_ctx *ctx, uint32_t l, uint32_t min_first, uint32_t round_end, int ntab, uint32_t *first, uint32_t *k, size_t *smem) {
   if (!use_mid_pipe()) return false;
   uint32_t rm = min_first;
-  while (rm <= l && (4ull << (l - rm)) > (1ull << MP_LOG_LEN_IN)) rm++;
+  while (rm <= l && (4ull << (l - rm)) > (1ull << (ntab == 2 ? MP_LOG_LEN_IN_QUAD : MP_LOG_LEN_IN))) rm++;
   if (rm + 1 >= round_end) return false;
   int kk = (int)(l - rm) + 1 - MP_LOG_LOCAL;                    // log2(length of the first bound table) - log2(local length)
   if (kk > MP_LOG_CTAS) kk = MP_LOG_CTAS;
@@ -2097,7 +2101,7 @@ int sumcheck_quad_enqueue(sp2_ctx *ctx, ScState *st, uint32_t rounds, fe *A, fe 
       sharded = false; dc = comm_none();
     }
     const u64 P = sharded ? Pg >> dc.k : Pg;
-    if (!sharded && round1 >= 3 && len_in > SC_TAIL_LEN && len_in <= (1ull << MP_LOG_LEN_IN)) {
+    if (!sharded && round1 >= 3 && len_in > SC_TAIL_LEN && len_in <= (1ull << MP_LOG_LEN_IN_QUAD)) {
       // (after the all-gather of a sharded prover: the remaining multi-CTA rounds go to the pipelined kernel)
       uint32_t round_end = round1, mf = 0, mk = 0; size_t msm = 0;
       while (round_end <= rounds && (4ull << (rounds - round_end)) > SC_TAIL_LEN) round_end++;

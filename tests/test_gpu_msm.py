@@ -104,3 +104,25 @@ def test_too_many_scalars_is_an_error(ctx, key):
     with pytest.raises(sp.SpartanError) as ei:
         sp.DlogGroupExt.vartime_multiscalar_mul(ctx, dk, np.zeros((W + 1, 4), dtype=np.uint64))
     assert ei.value.kind == "InvalidCommitmentKeyLength"
+
+
+def test_tree_exceptional_cases_duplicate_and_opposite_bases(ctx, orc):
+    """The reduction trees run lane-quad additions (curve_quad.cuh); their exceptional cases are resolved after the common path.
+    A key with ck[1] = ck[0] and ck[3] = -ck[2] puts P + P and P + (-P) into the trees: with unit scalars the two equal (opposite)
+    table entries sit alone in neighbouring lanes and meet in the last quad level; with equal random scalars every window pair meets
+    somewhere (lane-serial mixed adds, quad levels, final kernel).  Compared with the oracle's MSM over the same bases."""
+    import spartan2_b200 as sp
+    pts = points(orc, W + 3, seed=13).copy()
+    P_MOD = orc.MODS[orc.FP]
+    pts[1] = pts[0]
+    y = int(orc.from_mont(pts[2:3, 4:8], orc.FP)[0])
+    pts[3, :4] = pts[2, :4]; pts[3, 4:8] = orc.to_mont([(P_MOD - y) % P_MOD], orc.FP)[0]
+    ck, h, ck_s, h_s = pts[:W], pts[W:W + 1], pts[W + 1:W + 2], pts[W + 2:W + 3]
+    dk = sp.CommitmentKey(ctx, ck, h, ck_s, h_s)
+    rng = np.random.default_rng(17)
+    r = int.from_bytes(rng.bytes(32), "little") % ORDER
+    for vals in ([1, 1], [1, 1, 1, 1], [0, 0, 1, 1], [r, r], [r, r, r, r], [5, 5, 7, 7, 11], [r, r, 0, 0, 3]):
+        s = orc.to_mont(vals)
+        got = sp.DlogGroupExt.vartime_multiscalar_mul(ctx, dk, s)
+        assert np.array_equal(got, orc.msm(s, ck[:len(vals)])), vals
+    dk.free()

@@ -1,0 +1,1 @@
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | cut -c1-600

@@ -225,7 +225,10 @@ typedef struct { const uint64_t *blinds_W, *blind_eval_W, *d_vec, *r_delta, *r_b
 
 /* Replaces SpartanSNARK::prep_prove (src/spartan.rs:176-216): uploads the shared+precommitted witness
  * (num_shared + num_precommitted scalars), commits it row-wise (comm_out: rows x 8, may be NULL) and caches
- * its Az/Bz/Cz on the device.  The returned handle is the device half of SpartanPrepSNARK (:107-124).       */
+ * its Az/Bz/Cz on the device.  The returned handle is the device half of SpartanPrepSNARK (:107-124).
+ * Runtime: the handle owns one helper host thread (transcript hashing during sp2_spartan_prove; no CUDA calls, asleep between
+ * proves, joined by sp2_prep_free), one side stream, and a page of pinned device-visible memory through which the host opens
+ * the gate kernels of a prove ("runtime behaviour"); one prove at a time per handle.                        */
 int32_t sp2_spartan_prep_prove(sp2_ctx *ctx, const sp2_shape *shape, const sp2_ck *ck, const uint64_t *W_cached,
                                const uint64_t *blinds_cached, int32_t is_small, uint64_t *comm_out, sp2_prep **out);
 void sp2_prep_free(sp2_prep *prep);
